@@ -1,0 +1,814 @@
+/*
+ * fpt_api.cu — host side of libfpt_b200.so: the C ABI declared in include/fpt_b200.h.
+ *
+ * Replaces, for the two hot paths only, the reference's drivers
+ *   fisher/threadfisher.c:47-251 (threadcompute/mycompute), fisher/cFisher.c:38-115 (compute),
+ *   css/threadcss.c:52-293,       css/css.c:49-156
+ * (paths relative to /root/reference/statistics/): instead of 64 pthreads pulling tasks of 100 windows
+ * off a mutex-protected counter, the whole chromosome goes to the GPU once and every SNP / window is a
+ * thread / CTA of a handful of kernel launches.
+ *
+ * No CPU fallback: every compute entry point needs a CUDA device.
+ */
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "../../include/fpt_b200.h"
+#include "fpt_css.cuh"
+#include "fpt_fet.cuh"
+#include "fpt_rt.cuh"
+#include "fpt_tables.h"
+
+/* ================================================================================================ state */
+static thread_local char g_err[512] = "";
+static uint64_t g_seed = 20261018ULL;
+static int g_device = -1;               /* -1: whatever device is current */
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(FPT_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define CHECK(call)                     \
+    do {                                \
+        int rc_ = (call);               \
+        if (rc_ != FPT_OK) return rc_;  \
+    } while (0)
+
+struct DeviceCtx {
+    int device = -1;
+    int sms = 0;
+    int smem_optin = 0;
+    unsigned long long *binom = nullptr;
+    double *lf = nullptr;
+    int lf_maxn = -1;
+    bool pool_ready = false;
+};
+static DeviceCtx g_ctx[64];
+static std::mutex g_mu;
+
+static int get_ctx(DeviceCtx **out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(FPT_ERR_NO_DEVICE, "no CUDA device available (%s); libfpt_b200 has no CPU path",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    int dev = 0;
+    if (g_device >= 0) { CU(cudaSetDevice(g_device)); dev = g_device; }
+    else CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(FPT_ERR_ARG, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceCtx &c = g_ctx[dev];
+    if (c.device < 0) {
+        cudaDeviceProp pr;
+        CU(cudaGetDeviceProperties(&pr, dev));
+        c.sms = pr.multiProcessorCount;
+        c.smem_optin = (int)pr.sharedMemPerBlockOptin;
+        std::vector<unsigned long long> b = fpt_build_binom_table();
+        CU(cudaMalloc(&c.binom, b.size() * sizeof(unsigned long long)));
+        CU(cudaMemcpy(c.binom, b.data(), b.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;                 /* keep freed blocks cached between calls */
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            c.pool_ready = true;
+        }
+        cudaGetLastError();
+        c.device = dev;
+    }
+    *out = &c;
+    return FPT_OK;
+}
+
+/* log-factorial table, grown on demand (rare: once per process for a given coverage) */
+static int ensure_lf(DeviceCtx *c, int maxn) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (maxn <= c->lf_maxn) return FPT_OK;
+    int want = std::max(maxn, 1024);
+    std::vector<double> t = fpt_build_lfact_table(want);
+    double *d = nullptr;
+    CU(cudaMalloc(&d, t.size() * sizeof(double)));
+    CU(cudaMemcpy(d, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (c->lf) { CU(cudaDeviceSynchronize()); cudaFree(c->lf); }
+    c->lf = d;
+    c->lf_maxn = want;
+    return FPT_OK;
+}
+
+/* stream-ordered scratch allocations of one host-level call */
+struct Arena {
+    cudaStream_t st;
+    std::vector<void *> blocks;
+    std::vector<void *> pinned;
+    explicit Arena(cudaStream_t s) : st(s) {}
+    ~Arena() {
+        for (void *p : blocks) cudaFreeAsync(p, st);
+        cudaStreamSynchronize(st);
+        for (void *p : pinned) cudaFreeHost(p);
+    }
+    template <typename T>
+    int get(T **out, size_t count) {
+        void *p = nullptr;
+        size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+        cudaError_t e = cudaMallocAsync(&p, bytes, st);
+        if (e != cudaSuccess) return fail(FPT_ERR_CUDA, "cudaMallocAsync(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        blocks.push_back(p);
+        *out = (T *)p;
+        return FPT_OK;
+    }
+    template <typename T>
+    int host(T **out, size_t count) {
+        void *p = nullptr;
+        size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e != cudaSuccess) return fail(FPT_ERR_CUDA, "cudaMallocHost(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        pinned.push_back(p);
+        *out = (T *)p;
+        return FPT_OK;
+    }
+};
+
+template <typename K>
+static int persistent_grid(DeviceCtx *c, K kernel, int block, size_t smem, long long items, int *grid) {
+    if (smem > 48 * 1024) {
+        if ((int)smem > c->smem_optin) return fail(FPT_ERR_ARG, "kernel needs %zu bytes of shared memory, device allows %d", smem, c->smem_optin);
+        CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)per_sm * c->sms;
+    if (items < g) g = items;
+    if (g < 1) g = 1;
+    *grid = (int)g;
+    return FPT_OK;
+}
+
+/* ================================================================================================ library state */
+extern "C" const char *fpt_last_error(void) { return g_err; }
+
+extern "C" int fpt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int fpt_set_device(int device) {
+    int n = fpt_device_count();
+    if (device < 0 || device >= n) return fail(FPT_ERR_ARG, "device %d not in [0,%d)", device, n);
+    g_device = device;
+    CU(cudaSetDevice(device));
+    return FPT_OK;
+}
+
+extern "C" void fpt_set_seed(uint64_t seed) { g_seed = seed; }
+extern "C" uint64_t fpt_get_seed(void) { return g_seed; }
+extern "C" uint64_t fpt_window_state(uint64_t seed, int64_t window, int stream) {
+    return fpt_stream_state(seed, (long long)window, stream);
+}
+
+extern "C" void fpt_release(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int d = 0; d < 64; d++) {
+        DeviceCtx &c = g_ctx[d];
+        if (c.device < 0) continue;
+        cudaSetDevice(d);
+        cudaDeviceSynchronize();
+        if (c.binom) cudaFree(c.binom);
+        if (c.lf) cudaFree(c.lf);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        c = DeviceCtx();
+    }
+    cudaGetLastError();
+}
+
+/* ================================================================================================ device API: FET */
+static int count_tile(DeviceCtx *c, int asize, int bsize, size_t *smem) {
+    /* SNPs per shared-memory tile: one byte per genotype, <= 40 KB, even (keeps 16-byte tile starts) */
+    long long per = (long long)asize + bsize;
+    long long tile = (40 * 1024) / per;
+    if (tile > 512) tile = 512;
+    tile &= ~1LL;
+    if (tile < 2) tile = 2;
+    *smem = (((size_t)tile * asize + 15) & ~(size_t)15) + (size_t)tile * bsize + 16;
+    if ((int)*smem > c->smem_optin) return -1;
+    return (int)tile;
+}
+
+template <typename T>
+static int dev_fet_count(const T *a, const T *b, int64_t nsnp, int asize, int bsize, int32_t *tables, cudaStream_t st) {
+    DeviceCtx *c;
+    CHECK(get_ctx(&c));
+    if (nsnp < 0 || asize <= 0 || bsize <= 0) return fail(FPT_ERR_ARG, "fet_count: nsnp=%lld asize=%d bsize=%d", (long long)nsnp, asize, bsize);
+    if (nsnp == 0) return FPT_OK;
+    size_t smem;
+    int tile = count_tile(c, asize, bsize, &smem);
+    if (tile < 0) return fail(FPT_ERR_ARG, "populations of %d+%d individuals exceed the shared-memory tile", asize, bsize);
+    int grid;
+    CHECK(persistent_grid(c, fpt_fet_count_kernel<T>, 256, smem, (nsnp + tile - 1) / tile, &grid));
+    fpt_fet_count_kernel<T><<<grid, 256, smem, st>>>(a, b, nsnp, asize, bsize, tile, (int4 *)tables);
+    CU(cudaGetLastError());
+    return FPT_OK;
+}
+
+extern "C" int fpt_dev_fet_count_f64(const double *a, const double *b, int64_t nsnp, int asize, int bsize,
+                                     int32_t *tables, void *stream) {
+    return dev_fet_count<double>(a, b, nsnp, asize, bsize, tables, (cudaStream_t)stream);
+}
+extern "C" int fpt_dev_fet_count_i8(const int8_t *a, const int8_t *b, int64_t nsnp, int asize, int bsize,
+                                    int32_t *tables, void *stream) {
+    return dev_fet_count<signed char>((const signed char *)a, (const signed char *)b, nsnp, asize, bsize, tables,
+                                      (cudaStream_t)stream);
+}
+
+extern "C" int fpt_dev_fet_score(const int32_t *tables, int64_t n, int max_n, int force_log, double *out, void *stream) {
+    DeviceCtx *c;
+    CHECK(get_ctx(&c));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n < 0) return fail(FPT_ERR_ARG, "fet_score: n=%lld", (long long)n);
+    if (n == 0) return FPT_OK;
+    if (max_n <= 0) {
+        int *d_max;
+        CU(cudaMallocAsync((void **)&d_max, sizeof(int), st));
+        CU(cudaMemsetAsync(d_max, 0, sizeof(int), st));
+        int g = (int)std::min<long long>((n + 255) / 256, (long long)c->sms * 8);
+        fpt_fet_maxn_kernel<<<g, 256, 0, st>>>((const int4 *)tables, n, d_max);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&max_n, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaFreeAsync(d_max, st));
+    }
+    CHECK(ensure_lf(c, max_n));
+    size_t lf_bytes = ((size_t)max_n + 1) * sizeof(double);
+    int lf_in_smem = lf_bytes <= 96 * 1024;
+    size_t smem = FPT_BINOM_ENTRIES * sizeof(unsigned long long) + (lf_in_smem ? lf_bytes : 0);
+    int grid;
+    CHECK(persistent_grid(c, fpt_fet_score_kernel, 256, smem, (n + 255) / 256, &grid));
+    fpt_fet_score_kernel<<<grid, 256, smem, st>>>((const int4 *)tables, n, c->binom, c->lf, max_n, lf_in_smem, force_log, out);
+    CU(cudaGetLastError());
+    return FPT_OK;
+}
+
+static int check_range(const fpt_scan_range *r, long long *nwin) {
+    if (!r) return fail(FPT_ERR_ARG, "scan range is NULL");
+    if (r->wsize <= 0 || r->wstep <= 0 || r->regend < 0) return fail(FPT_ERR_ARG, "bad window geometry regend=%d wsize=%d wstep=%d", r->regend, r->wsize, r->wstep);
+    if (r->window_begin < 0 || r->window_end < r->window_begin) return fail(FPT_ERR_ARG, "bad window range [%lld,%lld)", (long long)r->window_begin, (long long)r->window_end);
+    if (r->semantics != FPT_SCAN_SERIAL && r->semantics != FPT_SCAN_THREADED) return fail(FPT_ERR_ARG, "unknown scan semantics %d", r->semantics);
+    *nwin = r->window_end - r->window_begin;
+    return FPT_OK;
+}
+
+extern "C" int fpt_dev_window_table(const int32_t *pos, int64_t nsnp, const fpt_scan_range *r, int32_t *wleft,
+                                    int32_t *wright, int32_t *max_npos, void *stream) {
+    DeviceCtx *c;
+    CHECK(get_ctx(&c));
+    long long nwin;
+    CHECK(check_range(r, &nwin));
+    if (nwin == 0) return FPT_OK;
+    unsigned grid = (unsigned)((nwin + 255) / 256);
+    fpt_window_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pos, nsnp, r->window_begin, nwin, r->regend, r->wsize,
+                                                                   r->wstep, r->semantics, wleft, wright, max_npos);
+    CU(cudaGetLastError());
+    return FPT_OK;
+}
+
+extern "C" int fpt_dev_fet_windows(const double *snp_scores, const int32_t *wleft, const int32_t *wright,
+                                   const fpt_scan_range *r, int max_npos, double perc, const uint64_t *states,
+                                   double *scores, double *stddev, uint8_t *written, void *stream) {
+    DeviceCtx *c;
+    CHECK(get_ctx(&c));
+    long long nwin;
+    CHECK(check_range(r, &nwin));
+    if (nwin == 0 || max_npos <= 0) return FPT_OK;
+    if (!(perc >= 0.0 && perc <= 1.0)) return fail(FPT_ERR_ARG, "percentile %g not in [0,1]", perc);
+    int npad = 2;
+    while (npad < max_npos) npad <<= 1;
+    int use_hist = max_npos <= FPT_FET_HIST_MAX_NPOS;
+    size_t smem = (size_t)npad * sizeof(double) + (use_hist ? (size_t)FPT_FET_NSAMPLES * max_npos * sizeof(unsigned short) : 0);
+    if ((int)smem > c->smem_optin)
+        return fail(FPT_ERR_WINDOW_TOO_LARGE, "a window holds %d SNPs; at most %d fit one CTA's shared memory", max_npos,
+                    c->smem_optin / 8);
+    int grid;
+    CHECK(persistent_grid(c, fpt_fet_window_kernel, 128, smem, nwin, &grid));
+    fpt_fet_window_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(snp_scores, wleft, wright, r->window_begin, nwin, perc,
+                                                                    r->seed, states, npad, use_hist, scores, stddev, written);
+    CU(cudaGetLastError());
+    return FPT_OK;
+}
+
+/* ================================================================================================ device API: CSS */
+extern "C" size_t fpt_dev_css_planes_bytes(int64_t nsnp, int m) {
+    return (size_t)((nsnp + 31) / 32) * 2 * (size_t)m * sizeof(uint32_t);
+}
+
+template <typename T>
+static int dev_css_pack(const T *a, const T *b, int64_t nsnp, int asize, int bsize, uint32_t *planes, cudaStream_t st) {
+    DeviceCtx *c;
+    CHECK(get_ctx(&c));
+    if (nsnp < 0 || asize <= 0 || bsize <= 0) return fail(FPT_ERR_ARG, "css_pack: nsnp=%lld asize=%d bsize=%d", (long long)nsnp, asize, bsize);
+    if (nsnp == 0) return FPT_OK;
+    long long per = (long long)asize + bsize;
+    long long wpt = (40 * 1024) / (per * 32);
+    if (wpt > 8) wpt = 8;
+    if (wpt < 1) wpt = 1;
+    size_t smem = (((size_t)wpt * 32 * asize + 15) & ~(size_t)15) + (size_t)wpt * 32 * bsize + 16;
+    if ((int)smem > c->smem_optin) return fail(FPT_ERR_ARG, "populations of %d+%d individuals exceed the shared-memory tile", asize, bsize);
+    long long nwords = (nsnp + 31) / 32;
+    int grid;
+    CHECK(persistent_grid(c, fpt_css_pack_kernel<T>, 256, smem, (nwords + wpt - 1) / wpt, &grid));
+    fpt_css_pack_kernel<T><<<grid, 256, smem, st>>>(a, b, nsnp, asize, bsize, (int)wpt, planes);
+    CU(cudaGetLastError());
+    return FPT_OK;
+}
+
+extern "C" int fpt_dev_css_pack_f64(const double *a, const double *b, int64_t nsnp, int asize, int bsize,
+                                    uint32_t *planes, void *stream) {
+    return dev_css_pack<double>(a, b, nsnp, asize, bsize, planes, (cudaStream_t)stream);
+}
+extern "C" int fpt_dev_css_pack_i8(const int8_t *a, const int8_t *b, int64_t nsnp, int asize, int bsize,
+                                   uint32_t *planes, void *stream) {
+    return dev_css_pack<signed char>((const signed char *)a, (const signed char *)b, nsnp, asize, bsize, planes,
+                                     (cudaStream_t)stream);
+}
+
+extern "C" int fpt_dev_css_absdiff(const double *a, const double *b, int64_t nsnp, double *out, void *stream) {
+    DeviceCtx *c;
+    CHECK(get_ctx(&c));
+    if (nsnp <= 0) return FPT_OK;
+    int g = (int)std::min<long long>((nsnp + 255) / 256, (long long)c->sms * 8);
+    fpt_css_absdiff_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(a, b, nsnp, out);
+    CU(cudaGetLastError());
+    return FPT_OK;
+}
+
+/* launch geometry of the per-window CSS kernels for a cohort of m individuals */
+struct CssPlan {
+    int m, wch, mats_in_smem;
+    size_t smem_win;                 /* mds / smacof kernels */
+    int perm_threads, wide_tracks, dist_in_smem, tracks_in_smem;
+    size_t smem_perm, perm_scratch_per_cta;
+    int max_ctas;                    /* upper bound on persistent CTAs (sizes the global scratch) */
+};
+
+static CssPlan css_plan(const DeviceCtx *c, int m) {
+    CssPlan p;
+    p.m = m;
+    p.wch = 8;
+    const size_t budget = (size_t)c->smem_optin - 1024;
+    p.mats_in_smem = fpt_css_smem_bytes(m, p.wch, 1) <= budget;
+    if (!p.mats_in_smem && fpt_css_smem_bytes(m, p.wch, 0) > budget) p.wch = 1;
+    p.smem_win = fpt_css_smem_bytes(m, p.wch, p.mats_in_smem);
+    p.perm_threads = 256;
+    p.wide_tracks = m > 256;
+    const int tb = p.wide_tracks ? 2 : 1;
+    p.dist_in_smem = (size_t)m * m * 8 + (size_t)4 * 1024 <= budget;
+    p.tracks_in_smem = fpt_css_perm_smem_bytes(m, p.perm_threads, tb, p.dist_in_smem, 1) <= budget;
+    p.smem_perm = fpt_css_perm_smem_bytes(m, p.perm_threads, tb, p.dist_in_smem, p.tracks_in_smem);
+    size_t per = (p.dist_in_smem ? 0 : (size_t)m * m * 8) + (p.tracks_in_smem ? 0 : (size_t)2 * p.perm_threads * m * tb);
+    p.perm_scratch_per_cta = (per + 255) & ~(size_t)255;
+    p.max_ctas = c->sms * 16;
+    return p;
+}
+
+struct CssWorkspace {
+    double *X, *Xruns, *sigma, *evals, *gscratch;
+    int *iters;
+    unsigned char *perm_scratch;
+    size_t total;
+};
+
+static CssWorkspace css_carve(const CssPlan &p, long long nwin, int mds, unsigned char *base) {
+    CssWorkspace w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const int nruns = mds == 1 ? 4 : (mds == 2 ? 1 : 0);
+    const size_t m2 = (size_t)2 * p.m;
+    size_t oX = take((size_t)nwin * m2 * 8);
+    size_t oXr = take((size_t)nwin * nruns * m2 * 8);
+    size_t oS = take((size_t)nwin * nruns * 8);
+    size_t oE = take((size_t)nwin * 3 * 8);
+    size_t oI = take((size_t)nwin * nruns * 4);
+    size_t oG = take(p.mats_in_smem ? 0 : (size_t)p.max_ctas * 2 * p.m * p.m * 8);
+    size_t oP = take((size_t)p.max_ctas * p.perm_scratch_per_cta);
+    w.total = off + 256;
+    if (base) {
+        w.X = (double *)(base + oX); w.Xruns = (double *)(base + oXr); w.sigma = (double *)(base + oS);
+        w.evals = (double *)(base + oE); w.iters = (int *)(base + oI);
+        w.gscratch = p.mats_in_smem ? nullptr : (double *)(base + oG);
+        w.perm_scratch = p.perm_scratch_per_cta ? base + oP : nullptr;
+    }
+    return w;
+}
+
+extern "C" size_t fpt_dev_css_workspace_bytes(int m, int64_t nwin, int mds) {
+    DeviceCtx *c;
+    if (get_ctx(&c) != FPT_OK || m <= 0 || nwin < 0) return 0;
+    CssPlan p = css_plan(c, m);
+    return css_carve(p, nwin, mds, nullptr).total;
+}
+
+template <typename TrackT>
+static int launch_perm(DeviceCtx *c, const CssPlan &p, const CssWorkspace &ws, int asize, int bsize, long long wbase,
+                       long long nwin, const uint8_t *status, int treshold, int runs, uint64_t seed, const uint64_t *states,
+                       double *scores, double *pv, int *hits, int *nperm, cudaStream_t st) {
+    int grid;
+    CHECK(persistent_grid(c, fpt_css_perm_kernel<TrackT>, p.perm_threads, p.smem_perm, nwin, &grid));
+    grid = std::min(grid, p.max_ctas);
+    fpt_css_perm_kernel<TrackT><<<grid, p.perm_threads, p.smem_perm, st>>>(
+        ws.X, p.m, asize, bsize, wbase, nwin, status, treshold, runs, seed, states, p.dist_in_smem, p.tracks_in_smem,
+        (double *)ws.perm_scratch, p.perm_scratch_per_cta, scores, pv, hits, nperm);
+    CU(cudaGetLastError());
+    return FPT_OK;
+}
+
+extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff, int asize, int bsize,
+                                   const int32_t *wleft, const int32_t *wright, const fpt_scan_range *r, int treshold,
+                                   int runs, int mds, void *workspace, size_t workspace_bytes, double *scores, double *pv,
+                                   uint8_t *status, const fpt_css_probes *probes, void *stream) {
+    DeviceCtx *c;
+    CHECK(get_ctx(&c));
+    cudaStream_t st = (cudaStream_t)stream;
+    long long nwin;
+    CHECK(check_range(r, &nwin));
+    if (asize <= 0 || bsize <= 0) return fail(FPT_ERR_ARG, "css: asize=%d bsize=%d", asize, bsize);
+    if (mds < 0 || mds > 2) return fail(FPT_ERR_ARG, "css: mds must be 0, 1 or 2 (got %d)", mds);
+    if (absdiff && (asize != 1 || bsize != 1)) return fail(FPT_ERR_ARG, "the frequency metric needs one track per population (got %d+%d)", asize, bsize);
+    if (!absdiff && !planes) return fail(FPT_ERR_ARG, "css: neither bit-planes nor frequency differences given");
+    if (nwin == 0) return FPT_OK;
+    const int m = asize + bsize;
+    CssPlan p = css_plan(c, m);
+    if (p.smem_win > (size_t)c->smem_optin || p.smem_perm > (size_t)c->smem_optin)
+        return fail(FPT_ERR_ARG, "cohort of %d individuals does not fit the kernels' shared-memory plan", m);
+    CssWorkspace ws = css_carve(p, nwin, mds, (unsigned char *)workspace);
+    if (!workspace || workspace_bytes < ws.total)
+        return fail(FPT_ERR_ARG, "css workspace too small: %zu < %zu bytes", workspace_bytes, ws.total);
+    const uint64_t *st_perm = r->states_resample, *st_init = r->states_init;
+
+    int grid;
+    if (mds == 0 || mds == 2) {
+        CHECK(persistent_grid(c, fpt_css_mds_kernel, 128, p.smem_win, nwin, &grid));
+        grid = std::min(grid, p.max_ctas);
+        fpt_css_mds_kernel<<<grid, 128, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, nwin, p.wch, p.mats_in_smem,
+                                                         ws.gscratch, ws.X, ws.evals, status);
+        CU(cudaGetLastError());
+    }
+    if (mds == 1 || mds == 2) {
+        const int nruns = mds == 1 ? 4 : 1;
+        CHECK(persistent_grid(c, fpt_css_smacof_kernel, 128, p.smem_win, nwin * nruns, &grid));
+        grid = std::min(grid, p.max_ctas);
+        fpt_css_smacof_kernel<<<grid, 128, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, r->window_begin, nwin, p.wch,
+                                                            p.mats_in_smem, ws.gscratch, nruns, mds == 1, r->seed, st_init,
+                                                            300, 0.000001, ws.X, ws.Xruns, ws.sigma, ws.iters, status);
+        CU(cudaGetLastError());
+        int g2 = (int)std::min<long long>(nwin, (long long)c->sms * 16);
+        fpt_css_pick_kernel<<<g2, 64, 0, st>>>(ws.Xruns, ws.sigma, m, nruns, nwin, status, ws.X);
+        CU(cudaGetLastError());
+    }
+    int *hits = probes ? probes->hits : nullptr, *nperm = probes ? probes->nperm : nullptr;
+    if (p.wide_tracks)
+        CHECK(launch_perm<unsigned short>(c, p, ws, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed,
+                                          st_perm, scores, pv, hits, nperm, st));
+    else
+        CHECK(launch_perm<unsigned char>(c, p, ws, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed,
+                                         st_perm, scores, pv, hits, nperm, st));
+    if (probes) {
+        const int nruns = mds == 1 ? 4 : (mds == 2 ? 1 : 0);
+        if (probes->X) CU(cudaMemcpyAsync(probes->X, ws.X, (size_t)nwin * 2 * m * 8, cudaMemcpyDeviceToDevice, st));
+        if (probes->evals) {
+            if (mds == 1) CU(cudaMemsetAsync(probes->evals, 0, (size_t)nwin * 3 * 8, st));
+            else CU(cudaMemcpyAsync(probes->evals, ws.evals, (size_t)nwin * 3 * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        if (probes->smacof_iters && nruns) CU(cudaMemcpyAsync(probes->smacof_iters, ws.iters, (size_t)nwin * nruns * 4, cudaMemcpyDeviceToDevice, st));
+        if (probes->smacof_sigma && nruns) CU(cudaMemcpyAsync(probes->smacof_sigma, ws.sigma, (size_t)nwin * nruns * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    return FPT_OK;
+}
+
+/* ================================================================================================ host entry points */
+static int check_genotypes(const fpt_genotypes *g) {
+    if (!g) return fail(FPT_ERR_ARG, "genotypes are NULL");
+    const bool f64 = g->avals && g->bvals, i8 = g->acodes && g->bcodes;
+    if (f64 == i8) return fail(FPT_ERR_ARG, "give either float64 values or int8 codes for both populations");
+    if (g->nsnp < 0 || g->asize <= 0 || g->bsize <= 0) return fail(FPT_ERR_ARG, "nsnp=%lld asize=%d bsize=%d", (long long)g->nsnp, g->asize, g->bsize);
+    if (g->nsnp > 0x7fffffffLL) return fail(FPT_ERR_ARG, "more than 2^31-1 SNPs in one scan");
+    return FPT_OK;
+}
+
+/* copy both populations to the device in the layout the caller has them */
+struct DevGenotypes { const double *a64 = nullptr, *b64 = nullptr; const signed char *a8 = nullptr, *b8 = nullptr; };
+
+static int upload_genotypes(Arena &ar, const fpt_genotypes *g, DevGenotypes *d) {
+    const size_t na = (size_t)g->nsnp * g->asize, nb = (size_t)g->nsnp * g->bsize;
+    if (g->avals) {
+        double *a, *b;
+        CHECK(ar.get(&a, na)); CHECK(ar.get(&b, nb));
+        CU(cudaMemcpyAsync(a, g->avals, na * sizeof(double), cudaMemcpyHostToDevice, ar.st));
+        CU(cudaMemcpyAsync(b, g->bvals, nb * sizeof(double), cudaMemcpyHostToDevice, ar.st));
+        d->a64 = a; d->b64 = b;
+    } else {
+        signed char *a, *b;
+        CHECK(ar.get(&a, na)); CHECK(ar.get(&b, nb));
+        CU(cudaMemcpyAsync(a, g->acodes, na, cudaMemcpyHostToDevice, ar.st));
+        CU(cudaMemcpyAsync(b, g->bcodes, nb, cudaMemcpyHostToDevice, ar.st));
+        d->a8 = a; d->b8 = b;
+    }
+    return FPT_OK;
+}
+
+struct HostStream {
+    cudaStream_t st = nullptr;
+    int make() { CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); return FPT_OK; }
+    ~HostStream() { if (st) cudaStreamDestroy(st); }
+};
+
+extern "C" int fpt_fet_per_snp(const fpt_genotypes *g, int32_t *tables, double *neglog10p) {
+    DeviceCtx *c;
+    CHECK(get_ctx(&c));
+    CHECK(check_genotypes(g));
+    if (g->nsnp == 0) return FPT_OK;
+    HostStream hs;
+    CHECK(hs.make());
+    Arena ar(hs.st);
+    DevGenotypes d;
+    CHECK(upload_genotypes(ar, g, &d));
+    int32_t *d_tab; double *d_sc;
+    CHECK(ar.get(&d_tab, (size_t)g->nsnp * 4));
+    CHECK(ar.get(&d_sc, (size_t)g->nsnp));
+    if (d.a64) CHECK(fpt_dev_fet_count_f64(d.a64, d.b64, g->nsnp, g->asize, g->bsize, d_tab, hs.st));
+    else CHECK(fpt_dev_fet_count_i8((const int8_t *)d.a8, (const int8_t *)d.b8, g->nsnp, g->asize, g->bsize, d_tab, hs.st));
+    if (neglog10p) {
+        CHECK(fpt_dev_fet_score(d_tab, g->nsnp, g->asize + g->bsize, 0, d_sc, hs.st));
+        CU(cudaMemcpyAsync(neglog10p, d_sc, (size_t)g->nsnp * sizeof(double), cudaMemcpyDeviceToHost, hs.st));
+    }
+    if (tables) CU(cudaMemcpyAsync(tables, d_tab, (size_t)g->nsnp * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, hs.st));
+    CU(cudaStreamSynchronize(hs.st));
+    return FPT_OK;
+}
+
+extern "C" int fpt_fet_tables(const int32_t *tables, int64_t n, int force_log, double *neglog10p) {
+    DeviceCtx *c;
+    CHECK(get_ctx(&c));
+    if (n < 0 || (n > 0 && (!tables || !neglog10p))) return fail(FPT_ERR_ARG, "fet_tables: bad arguments");
+    if (n == 0) return FPT_OK;
+    HostStream hs;
+    CHECK(hs.make());
+    Arena ar(hs.st);
+    int32_t *d_tab; double *d_sc;
+    CHECK(ar.get(&d_tab, (size_t)n * 4));
+    CHECK(ar.get(&d_sc, (size_t)n));
+    CU(cudaMemcpyAsync(d_tab, tables, (size_t)n * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, hs.st));
+    CHECK(fpt_dev_fet_score(d_tab, n, 0, force_log, d_sc, hs.st));
+    CU(cudaMemcpyAsync(neglog10p, d_sc, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, hs.st));
+    CU(cudaStreamSynchronize(hs.st));
+    return FPT_OK;
+}
+
+/* shared front half of both scans: positions to the device, window table, largest window */
+struct ScanFront {
+    int32_t *d_pos = nullptr, *d_wl = nullptr, *d_wr = nullptr, *d_max = nullptr;
+    long long nwin = 0;
+    int max_npos = 0;
+};
+
+static int scan_front(Arena &ar, const fpt_genotypes *g, const fpt_scan_range *r, ScanFront *f) {
+    CHECK(check_range(r, &f->nwin));
+    if (f->nwin > 0x7fffffffLL) return fail(FPT_ERR_ARG, "more than 2^31-1 windows in one scan");
+    CHECK(ar.get(&f->d_pos, (size_t)g->nsnp));
+    CHECK(ar.get(&f->d_wl, (size_t)f->nwin));
+    CHECK(ar.get(&f->d_wr, (size_t)f->nwin));
+    CHECK(ar.get(&f->d_max, 1));
+    CU(cudaMemcpyAsync(f->d_pos, g->pos, (size_t)g->nsnp * sizeof(int32_t), cudaMemcpyHostToDevice, ar.st));
+    CU(cudaMemsetAsync(f->d_max, 0, sizeof(int32_t), ar.st));
+    CHECK(fpt_dev_window_table(f->d_pos, g->nsnp, r, f->d_wl, f->d_wr, f->d_max, ar.st));
+    return FPT_OK;
+}
+
+extern "C" int fpt_fet_scan(const fpt_genotypes *g, const fpt_scan_range *r, double perc, double *scores,
+                            double *stddev, uint8_t *written) {
+    DeviceCtx *c;
+    CHECK(get_ctx(&c));
+    CHECK(check_genotypes(g));
+    long long nwin;
+    CHECK(check_range(r, &nwin));
+    if (nwin == 0 || g->nsnp == 0) return FPT_OK;
+    if (!g->pos || !scores || !stddev) return fail(FPT_ERR_ARG, "fet_scan: positions and both outputs are required");
+    HostStream hs;
+    CHECK(hs.make());
+    Arena ar(hs.st);
+    ScanFront f;
+    CHECK(scan_front(ar, g, r, &f));                       /* small copies first: the table overlaps the big upload */
+    DevGenotypes d;
+    CHECK(upload_genotypes(ar, g, &d));
+    int32_t *d_tab; double *d_snp, *d_sc, *d_sd; uint8_t *d_fl; uint64_t *d_states = nullptr;
+    CHECK(ar.get(&d_tab, (size_t)g->nsnp * 4));
+    CHECK(ar.get(&d_snp, (size_t)g->nsnp));
+    CHECK(ar.get(&d_sc, (size_t)nwin)); CHECK(ar.get(&d_sd, (size_t)nwin)); CHECK(ar.get(&d_fl, (size_t)nwin));
+    if (r->states_resample) {
+        CHECK(ar.get(&d_states, (size_t)nwin));
+        CU(cudaMemcpyAsync(d_states, r->states_resample, (size_t)nwin * 8, cudaMemcpyHostToDevice, hs.st));
+    }
+    CU(cudaMemsetAsync(d_fl, 0, (size_t)nwin, hs.st));
+    if (d.a64) CHECK(fpt_dev_fet_count_f64(d.a64, d.b64, g->nsnp, g->asize, g->bsize, d_tab, hs.st));
+    else CHECK(fpt_dev_fet_count_i8((const int8_t *)d.a8, (const int8_t *)d.b8, g->nsnp, g->asize, g->bsize, d_tab, hs.st));
+    CHECK(fpt_dev_fet_score(d_tab, g->nsnp, g->asize + g->bsize, 0, d_snp, hs.st));
+    CU(cudaMemcpyAsync(&f.max_npos, f.d_max, sizeof(int), cudaMemcpyDeviceToHost, hs.st));
+    CU(cudaStreamSynchronize(hs.st));
+    CHECK(fpt_dev_fet_windows(d_snp, f.d_wl, f.d_wr, r, f.max_npos, perc, d_states, d_sc, d_sd, d_fl, hs.st));
+    double *h_sc, *h_sd; uint8_t *h_fl;
+    CHECK(ar.host(&h_sc, (size_t)nwin)); CHECK(ar.host(&h_sd, (size_t)nwin)); CHECK(ar.host(&h_fl, (size_t)nwin));
+    CU(cudaMemcpyAsync(h_sc, d_sc, (size_t)nwin * 8, cudaMemcpyDeviceToHost, hs.st));
+    CU(cudaMemcpyAsync(h_sd, d_sd, (size_t)nwin * 8, cudaMemcpyDeviceToHost, hs.st));
+    CU(cudaMemcpyAsync(h_fl, d_fl, (size_t)nwin, cudaMemcpyDeviceToHost, hs.st));
+    CU(cudaStreamSynchronize(hs.st));
+    for (long long w = 0; w < nwin; w++) {                  /* un-scored windows stay as the caller left them */
+        if (h_fl[w]) { scores[w] = h_sc[w]; stddev[w] = h_sd[w]; }
+        if (written) written[w] = h_fl[w];
+    }
+    return FPT_OK;
+}
+
+extern "C" int fpt_css_scan(const fpt_genotypes *g, const fpt_scan_range *r, int treshold, int runs, int drosophila,
+                            int mds, double *scores, double *p, uint8_t *written, const fpt_css_probes *probes) {
+    DeviceCtx *c;
+    CHECK(get_ctx(&c));
+    if (!g) return fail(FPT_ERR_ARG, "genotypes are NULL");
+    if (drosophila) {
+        if (!g->avals || !g->bvals || g->asize != 1 || g->bsize != 1)
+            return fail(FPT_ERR_ARG, "the frequency metric takes float64 frequencies, one track per population");
+        if (g->nsnp < 0 || g->nsnp > 0x7fffffffLL) return fail(FPT_ERR_ARG, "bad nsnp");
+    } else {
+        CHECK(check_genotypes(g));
+    }
+    long long nwin;
+    CHECK(check_range(r, &nwin));
+    if (mds < 0 || mds > 2) return fail(FPT_ERR_ARG, "css: mds must be 0, 1 or 2 (got %d)", mds);
+    if (nwin == 0 || g->nsnp == 0) return FPT_OK;
+    if (!g->pos || !scores || !p) return fail(FPT_ERR_ARG, "css_scan: positions and both outputs are required");
+    const int m = g->asize + g->bsize;
+    HostStream hs;
+    CHECK(hs.make());
+    Arena ar(hs.st);
+    ScanFront f;
+    CHECK(scan_front(ar, g, r, &f));
+    DevGenotypes d;
+    CHECK(upload_genotypes(ar, g, &d));
+    uint32_t *d_planes = nullptr; double *d_abs = nullptr;
+    if (drosophila) {
+        CHECK(ar.get(&d_abs, (size_t)g->nsnp));
+        CHECK(fpt_dev_css_absdiff(d.a64, d.b64, g->nsnp, d_abs, hs.st));
+    } else {
+        CHECK(ar.get(&d_planes, fpt_dev_css_planes_bytes(g->nsnp, m) / 4));
+        if (d.a64) CHECK(fpt_dev_css_pack_f64(d.a64, d.b64, g->nsnp, g->asize, g->bsize, d_planes, hs.st));
+        else CHECK(fpt_dev_css_pack_i8((const int8_t *)d.a8, (const int8_t *)d.b8, g->nsnp, g->asize, g->bsize, d_planes, hs.st));
+    }
+    const int nruns = mds == 1 ? 4 : (mds == 2 ? 1 : 0);
+    size_t ws_bytes = fpt_dev_css_workspace_bytes(m, nwin, mds);
+    unsigned char *d_ws; double *d_sc, *d_p; uint8_t *d_st;
+    CHECK(ar.get(&d_ws, ws_bytes));
+    CHECK(ar.get(&d_sc, (size_t)nwin)); CHECK(ar.get(&d_p, (size_t)nwin)); CHECK(ar.get(&d_st, (size_t)nwin));
+    CU(cudaMemsetAsync(d_st, 0, (size_t)nwin, hs.st));
+    fpt_scan_range rd = *r;
+    uint64_t *d_s0 = nullptr, *d_s1 = nullptr;
+    if (r->states_resample) { CHECK(ar.get(&d_s0, (size_t)nwin)); CU(cudaMemcpyAsync(d_s0, r->states_resample, (size_t)nwin * 8, cudaMemcpyHostToDevice, hs.st)); }
+    if (r->states_init) { CHECK(ar.get(&d_s1, (size_t)nwin)); CU(cudaMemcpyAsync(d_s1, r->states_init, (size_t)nwin * 8, cudaMemcpyHostToDevice, hs.st)); }
+    rd.states_resample = d_s0; rd.states_init = d_s1;
+    fpt_css_probes dp;
+    memset(&dp, 0, sizeof dp);
+    if (probes) {
+        if (probes->X) CHECK(ar.get(&dp.X, (size_t)nwin * 2 * m));
+        if (probes->evals) CHECK(ar.get(&dp.evals, (size_t)nwin * 3));
+        if (probes->hits) CHECK(ar.get(&dp.hits, (size_t)nwin));
+        if (probes->nperm) CHECK(ar.get(&dp.nperm, (size_t)nwin));
+        if (probes->smacof_iters && nruns) CHECK(ar.get(&dp.smacof_iters, (size_t)nwin * nruns));
+        if (probes->smacof_sigma && nruns) CHECK(ar.get(&dp.smacof_sigma, (size_t)nwin * nruns));
+        if (dp.hits) CU(cudaMemsetAsync(dp.hits, 0, (size_t)nwin * 4, hs.st));
+        if (dp.nperm) CU(cudaMemsetAsync(dp.nperm, 0, (size_t)nwin * 4, hs.st));
+        if (dp.X) CU(cudaMemsetAsync(dp.X, 0, (size_t)nwin * 2 * m * 8, hs.st));
+    }
+    CHECK(fpt_dev_css_windows(d_planes, d_abs, g->asize, g->bsize, f.d_wl, f.d_wr, &rd, treshold, runs, mds, d_ws, ws_bytes,
+                              d_sc, d_p, d_st, probes ? &dp : nullptr, hs.st));
+    double *h_sc, *h_p; uint8_t *h_st;
+    CHECK(ar.host(&h_sc, (size_t)nwin)); CHECK(ar.host(&h_p, (size_t)nwin)); CHECK(ar.host(&h_st, (size_t)nwin));
+    CU(cudaMemcpyAsync(h_sc, d_sc, (size_t)nwin * 8, cudaMemcpyDeviceToHost, hs.st));
+    CU(cudaMemcpyAsync(h_p, d_p, (size_t)nwin * 8, cudaMemcpyDeviceToHost, hs.st));
+    CU(cudaMemcpyAsync(h_st, d_st, (size_t)nwin, cudaMemcpyDeviceToHost, hs.st));
+    if (probes) {
+        if (probes->X) CU(cudaMemcpyAsync(probes->X, dp.X, (size_t)nwin * 2 * m * 8, cudaMemcpyDeviceToHost, hs.st));
+        if (probes->evals) CU(cudaMemcpyAsync(probes->evals, dp.evals, (size_t)nwin * 3 * 8, cudaMemcpyDeviceToHost, hs.st));
+        if (probes->hits) CU(cudaMemcpyAsync(probes->hits, dp.hits, (size_t)nwin * 4, cudaMemcpyDeviceToHost, hs.st));
+        if (probes->nperm) CU(cudaMemcpyAsync(probes->nperm, dp.nperm, (size_t)nwin * 4, cudaMemcpyDeviceToHost, hs.st));
+        if (probes->smacof_iters && nruns) CU(cudaMemcpyAsync(probes->smacof_iters, dp.smacof_iters, (size_t)nwin * nruns * 4, cudaMemcpyDeviceToHost, hs.st));
+        if (probes->smacof_sigma && nruns) CU(cudaMemcpyAsync(probes->smacof_sigma, dp.smacof_sigma, (size_t)nwin * nruns * 8, cudaMemcpyDeviceToHost, hs.st));
+    }
+    CU(cudaStreamSynchronize(hs.st));
+    for (long long w = 0; w < nwin; w++) {
+        /* css.c:126-132: score and p are stored only when the scorer did not return -1 */
+        if (h_st[w] == FPT_WIN_SCORED) { scores[w] = h_sc[w]; p[w] = h_p[w]; }
+        if (written) written[w] = h_st[w] == FPT_WIN_SCORED;
+        if (probes && probes->status) probes->status[w] = h_st[w];
+    }
+    return FPT_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ drop-ins */
+/* comparative.c:25-34 get_population_size, bounded by the array length (the reference runs off the end
+   when every position is equal) */
+static int population_size(const int *pos, int len) {
+    int n = 0;
+    while (n < len && pos[n] == pos[0]) n++;
+    return n;
+}
+
+/* reference layout -> one position per SNP; verifies that A and B describe the same SNPs */
+static int unique_positions(const int *apos, const int *bpos, int alen, int blen, int *asize, int *bsize,
+                            std::vector<int32_t> *pos) {
+    if (alen <= 0 || blen <= 0 || !apos || !bpos) return fail(FPT_ERR_ARG, "empty position arrays");
+    *asize = population_size(apos, alen);
+    *bsize = population_size(bpos, blen);
+    const long long na = alen / *asize, nb = blen / *bsize;
+    if (na != nb)
+        return fail(FPT_ERR_POSITIONS, "population A has %lld SNPs (%d individuals), B has %lld (%d individuals)", na, *asize, nb, *bsize);
+    pos->resize((size_t)na);
+    for (long long k = 0; k < na; k++) {
+        const int pa = apos[k * *asize];
+        if (pa != bpos[k * *bsize]) return fail(FPT_ERR_POSITIONS, "SNP %lld: position %d in A but %d in B", k, pa, bpos[k * *bsize]);
+        (*pos)[(size_t)k] = pa;
+    }
+    return FPT_OK;
+}
+
+static fpt_scan_range full_range(int regend, int wsize, int wstep, int semantics) {
+    fpt_scan_range r;
+    memset(&r, 0, sizeof r);
+    r.regend = regend; r.wsize = wsize; r.wstep = wstep; r.semantics = semantics;
+    r.window_begin = 0;
+    r.window_end = wstep > 0 ? regend / wstep : 0;       /* length of the caller's output arrays (Q17) */
+    r.seed = g_seed;
+    return r;
+}
+
+static int fet_dropin(double *avals, double *bvals, int *apos, int *bpos, int regend, int wsize, int wstep, int alen,
+                      int blen, double perc, double *scores, double *stddev, int semantics) {
+    if (wsize <= 0 || wstep <= 0) return fail(FPT_ERR_ARG, "bad window geometry wsize=%d wstep=%d", wsize, wstep);
+    fpt_genotypes g;
+    memset(&g, 0, sizeof g);
+    std::vector<int32_t> pos;
+    CHECK(unique_positions(apos, bpos, alen, blen, &g.asize, &g.bsize, &pos));
+    g.avals = avals; g.bvals = bvals; g.pos = pos.data(); g.nsnp = (int64_t)pos.size();
+    fpt_scan_range r = full_range(regend, wsize, wstep, semantics);
+    return fpt_fet_scan(&g, &r, perc, scores, stddev, nullptr);
+}
+
+static int css_dropin(double *avals, double *bvals, int *apos, int *bpos, int regend, int wsize, int wstep, int alen,
+                      int blen, int treshold, int runs, int drosophila, int mds, double *scores, double *p, int semantics) {
+    if (wsize <= 0 || wstep <= 0) return fail(FPT_ERR_ARG, "bad window geometry wsize=%d wstep=%d", wsize, wstep);
+    fpt_genotypes g;
+    memset(&g, 0, sizeof g);
+    std::vector<int32_t> pos;
+    CHECK(unique_positions(apos, bpos, alen, blen, &g.asize, &g.bsize, &pos));
+    g.avals = avals; g.bvals = bvals; g.pos = pos.data(); g.nsnp = (int64_t)pos.size();
+    fpt_scan_range r = full_range(regend, wsize, wstep, semantics);
+    return fpt_css_scan(&g, &r, treshold, runs, drosophila, mds, scores, p, nullptr, nullptr);
+}
+
+/* regstart is accepted and ignored, as in the reference (windows always start at 0) */
+extern "C" int fpt_fet_threadcompute(double *avals, double *bvals, int *apos, int *bpos, int regstart, int regend,
+                                     int wsize, int wstep, int alen, int blen, double perc, double *scores, double *stddev) {
+    (void)regstart;
+    return fet_dropin(avals, bvals, apos, bpos, regend, wsize, wstep, alen, blen, perc, scores, stddev, FPT_SCAN_THREADED);
+}
+extern "C" int fpt_fet_compute(double *avals, double *bvals, int *apos, int *bpos, int regstart, int regend, int wsize,
+                               int wstep, int alen, int blen, double perc, double *scores, double *stddev) {
+    (void)regstart;
+    return fet_dropin(avals, bvals, apos, bpos, regend, wsize, wstep, alen, blen, perc, scores, stddev, FPT_SCAN_SERIAL);
+}
+extern "C" int fpt_css_threadcompute(double *avals, double *bvals, int *apos, int *bpos, int regstart, int regend,
+                                     int wsize, int wstep, int alen, int blen, int treshold, int runs, int drosophila,
+                                     int mds, double *scores, double *p) {
+    (void)regstart;
+    return css_dropin(avals, bvals, apos, bpos, regend, wsize, wstep, alen, blen, treshold, runs, drosophila, mds, scores, p, FPT_SCAN_THREADED);
+}
+extern "C" int fpt_css_compute(double *avals, double *bvals, int *apos, int *bpos, int regstart, int regend, int wsize,
+                               int wstep, int alen, int blen, int treshold, int runs, int drosophila, int mds,
+                               double *scores, double *p) {
+    (void)regstart;
+    return css_dropin(avals, bvals, apos, bpos, regend, wsize, wstep, alen, blen, treshold, runs, drosophila, mds, scores, p, FPT_SCAN_SERIAL);
+}

@@ -1,0 +1,629 @@
+/*
+ * fpt_css.cuh — Cluster-Separation-Score hot path on the device.
+ *
+ *   fpt_css_pack_kernel     genotype codes -> two bit-planes per individual ("is 3", "is -3"),
+ *                           32 SNPs per word, word-major so a window is one contiguous slab
+ *   fpt_css_mds_kernel      per window: pairwise opposite-homozygote counts (compare_all,
+ *                           css/css.c:277-327) or frequency difference (compare_freq, css.c:245-264),
+ *                           fill_averages (css.c:337-366), classical MDS (cmds, css.c:505-560)
+ *   fpt_css_smacof_kernel   per (window, start): SMACOF majorisation (smacof / guttman_transform /
+ *                           stress, css.c:767-938) from a random start (smacof_runs, css.c:852-884)
+ *                           or from the classical-MDS solution (css.c:216-217)
+ *   fpt_css_pick_kernel     best of the random starts (css.c:876-881)
+ *   fpt_css_perm_kernel     embedding distances (calc_dist, css.c:573-587), the score (css,
+ *                           css.c:608-647) and the Monte-Carlo p-value (significance_treshold /
+ *                           random_shuffle, css.c:700-752)
+ *
+ * Paths are relative to /root/reference/statistics/.
+ */
+#ifndef FPT_CSS_CUH
+#define FPT_CSS_CUH
+
+#include "fpt_rt.cuh"
+#include "fpt_fet.cuh"     /* fpt_code_of / fpt_stage_codes */
+
+/* window status */
+#define FPT_WIN_EMPTY 0      /* not visited or no SNPs: outputs untouched */
+#define FPT_WIN_DISCARDED 1  /* fill_averages said "more than half blank": scorer returns -1 */
+#define FPT_WIN_SCORED 2
+
+/* ============================================================================================
+ * Packing. planes[(word*2 + plane)*m + individual], plane 0 = genotype 3, plane 1 = genotype -3;
+ * bit b of word w is SNP 32*w + b; individuals 0..asize-1 are group A, asize..m-1 group B.
+ * An opposite-homozygote count over a window is then popc(P_i & M_j) + popc(M_i & P_j) summed over
+ * the window's words (first/last masked) — exact small integers, like the reference's count++.
+ */
+template <typename T>
+__global__ void __launch_bounds__(256)
+fpt_css_pack_kernel(const T *__restrict__ avals, const T *__restrict__ bvals, long long nsnp, int asize, int bsize,
+                    int words_per_tile, unsigned *__restrict__ planes) {
+    FPT_DYN_SMEM(smem);
+    const int m = asize + bsize, tile = words_per_tile * 32;
+    unsigned char *sa = smem;
+    unsigned char *sb = smem + (((size_t)tile * asize + 15) & ~(size_t)15);
+    const long long nwords = (nsnp + 31) >> 5;
+    for (long long w0 = (long long)blockIdx.x * words_per_tile; w0 < nwords; w0 += (long long)gridDim.x * words_per_tile) {
+        const long long t0 = w0 * 32;
+        const int nt = (int)min((long long)tile, nsnp - t0);
+        const int nw = (nt + 31) >> 5;
+        fpt_stage_codes<T>(avals + t0 * asize, (long long)nt * asize, sa);
+        fpt_stage_codes<T>(bvals + t0 * bsize, (long long)nt * bsize, sb);
+        __syncthreads();
+        for (int item = threadIdx.x; item < nw * m; item += blockDim.x) {
+            const int w = item / m, i = item - w * m;
+            const unsigned char *col = i < asize ? sa + i : sb + (i - asize);
+            const int stride = i < asize ? asize : bsize;
+            unsigned P = 0, M = 0;
+            const int nb = min(32, nt - w * 32);
+            for (int b = 0; b < nb; b++) {
+                unsigned c = col[(size_t)(w * 32 + b) * stride];
+                P |= (unsigned)(c == 1) << b;
+                M |= (unsigned)(c == 2) << b;
+            }
+            planes[((size_t)(w0 + w) * 2 + 0) * m + i] = P;
+            planes[((size_t)(w0 + w) * 2 + 1) * m + i] = M;
+        }
+        __syncthreads();
+    }
+}
+
+/* drosophila metric (compare_freq): per-SNP |a - b| of two frequency tracks */
+__global__ void fpt_css_absdiff_kernel(const double *__restrict__ a, const double *__restrict__ b, long long n,
+                                       double *__restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = fabs(__dsub_rn(a[i], b[i]));
+}
+
+/* ============================================================================================
+ * Per-window dissimilarity matrix D (m x m doubles, row-major) into `D`; returns 1 to keep the
+ * window, 0 to discard it. `wbuf` is shared scratch for wch*2*m words, `red` 33 doubles + 33 int64.
+ */
+struct FptCssScratch {
+    double *red;            /* 33 doubles */
+    long long *redi;        /* 33 int64 */
+    unsigned *wbuf;         /* wch * 2 * m words */
+    int wch;
+};
+
+FPT_D void fpt_css_counts(const unsigned *__restrict__ planes, int m, int l, int r, double *D, const FptCssScratch &sc) {
+    const int w0 = l >> 5, w1 = (r - 1) >> 5, mm = m * m;
+    for (int e = threadIdx.x; e < mm; e += blockDim.x) D[e] = 0.0;
+    for (int wc = w0; wc <= w1; wc += sc.wch) {
+        const int nw = min(sc.wch, w1 - wc + 1);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nw * 2 * m; e += blockDim.x) {
+            const int w = wc + e / (2 * m);
+            unsigned mask = 0xffffffffu;
+            if (w == w0) mask &= 0xffffffffu << (l & 31);
+            if (w == w1) mask &= 0xffffffffu >> (31 - ((r - 1) & 31));
+            sc.wbuf[e] = planes[(size_t)wc * 2 * m + e] & mask;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < mm; e += blockDim.x) {
+            const int i = e / m, j = e - i * m;
+            if (j < i) {
+                int cnt = 0;
+                for (int w = 0; w < nw; w++) {
+                    const unsigned *row = sc.wbuf + (size_t)w * 2 * m;
+                    cnt += __popc(row[i] & row[m + j]) + __popc(row[m + i] & row[j]);
+                }
+                D[e] += (double)cnt;
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < mm; e += blockDim.x) {
+        const int i = e / m, j = e - i * m;
+        if (j > i) D[e] = D[j * m + i];
+    }
+    __syncthreads();
+}
+
+/* css.c:337-366: blanks (< 1e-5, diagonal included) become sum/m^2; discard when blanks > m*m/2 */
+FPT_D int fpt_css_fill(double *D, int m, const FptCssScratch &sc) {
+    const int mm = m * m;
+    long long blanks = 0;
+    double sum = 0.0;
+    for (int e = threadIdx.x; e < mm; e += blockDim.x) {
+        double v = D[e];
+        if (v < 0.00001) blanks++; else sum += v;
+    }
+    blanks = fpt_block_sum_i64(blanks, sc.redi);
+    sum = fpt_block_sum(sum, sc.red);
+    if (blanks > (long long)(mm / 2)) return 0;
+    const double avg = __ddiv_rn(sum, (double)mm);
+    for (int e = threadIdx.x; e < mm; e += blockDim.x) if (D[e] < 0.00001) D[e] = avg;
+    __syncthreads();
+    return 1;
+}
+
+/* window -> filled dissimilarity matrix; handles both metrics. absdiff != NULL selects compare_freq (m = 2). */
+FPT_D int fpt_css_dissimilarity(const unsigned *__restrict__ planes, const double *__restrict__ absdiff, int m, int l, int r,
+                                double *D, const FptCssScratch &sc) {
+    if (absdiff) {
+        /* css.c:245-264: mean over the window, accumulated from the last SNP down */
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int i = r; i-- > l;) s = __dadd_rn(s, absdiff[i]);
+            s = __ddiv_rn(s, (double)(r - l));
+            D[0] = 0.0; D[1] = s; D[2] = s; D[3] = 0.0;
+        }
+        __syncthreads();
+    } else {
+        fpt_css_counts(planes, m, l, r, D, sc);
+    }
+    return fpt_css_fill(D, m, sc);
+}
+
+/* ============================================================================================
+ * Classical MDS. B = -1/2 Z (D.D) Z, Z = I - 11'/m, written in its closed double-centred form
+ * b_ij = -1/2 (s_ij - r_i - r_j + g) (the reference forms the same matrix with two dgemm calls);
+ * eigen-decomposition by two-sided Jacobi with a round-robin ordering so that m/2 disjoint rotations
+ * run concurrently; X = [v1 v2] diag(sqrt(l1), sqrt(l2)) for the two largest eigenvalues BY VALUE,
+ * with no guard against negative ones (css.c:543-558: sqrt gives NaN, as in the reference).
+ * A holds D on entry and is destroyed; V receives the eigenvectors (columns).
+ */
+struct FptJacobiScratch {
+    double *rmean;   /* m */
+    double *rc;      /* ceil(m/2)+1 rotation cosines */
+    double *rs;      /* sines */
+    int *rp, *rq;    /* pair indices */
+};
+
+FPT_D void fpt_css_cmds(double *A, double *V, int m, double *X, double *evals3, const FptJacobiScratch &js,
+                        const FptCssScratch &sc) {
+    const int mm = m * m;
+    for (int e = threadIdx.x; e < mm; e += blockDim.x) { double d = A[e]; A[e] = d * d; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {        /* column sums = row sums (symmetric), conflict-free */
+        double s = 0.0;
+        for (int j = 0; j < m; j++) s += A[j * m + i];
+        js.rmean[i] = s / m;
+    }
+    __syncthreads();
+    double g = 0.0;
+    for (int i = 0; i < m; i++) g += js.rmean[i];
+    g /= m;
+    for (int e = threadIdx.x; e < mm; e += blockDim.x) {       /* lower triangle and diagonal in place */
+        const int i = e / m, j = e - i * m;
+        V[e] = (i == j) ? 1.0 : 0.0;
+        if (j <= i) A[e] = -0.5 * (((A[e] - js.rmean[i]) - js.rmean[j]) + g);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < mm; e += blockDim.x) {       /* mirror: B is exactly symmetric */
+        const int i = e / m, j = e - i * m;
+        if (j > i) A[e] = A[j * m + i];
+    }
+    __syncthreads();
+
+    const int n = (m + 1) & ~1, half = n >> 1;
+    for (int sweep = 0; sweep < 40; sweep++) {
+        double off = 0.0, dia = 0.0;
+        for (int e = threadIdx.x; e < mm; e += blockDim.x) {
+            const int i = e / m, j = e - i * m;
+            const double v = A[e];
+            if (i == j) dia += v * v; else if (j > i) off += v * v;
+        }
+        off = fpt_block_sum(off, sc.red);
+        dia = fpt_block_sum(dia, sc.red);
+        if (off <= 1e-300 || off <= 1e-32 * (dia + off)) break;
+        for (int round = 0; round < n - 1; round++) {
+            if ((int)threadIdx.x < half) {
+                const int t = threadIdx.x;
+                int a, b;
+                if (t == 0) { a = n - 1; b = round; }
+                else { a = (round + t) % (n - 1); b = (round - t + (n - 1)) % (n - 1); }
+                const int p = a < b ? a : b, q = a < b ? b : a;
+                double c = 1.0, s = 0.0;
+                if (q < m) {
+                    const double apq = A[p * m + q];
+                    if (apq != 0.0) {
+                        const double th = (A[q * m + q] - A[p * m + p]) / (2.0 * apq);
+                        const double tt = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                        c = 1.0 / sqrt(tt * tt + 1.0);
+                        s = tt * c;
+                    }
+                }
+                js.rp[t] = p; js.rq[t] = q < m ? q : p;      /* a bye rotates p with itself by the identity */
+                js.rc[t] = c; js.rs[t] = s;
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < m * half; e += blockDim.x) {      /* columns p,q of A and V */
+                const int k = e / half, t = e - k * half;
+                const double c = js.rc[t], s = js.rs[t];
+                if (s != 0.0) {
+                    const int p = js.rp[t], q = js.rq[t];
+                    double x = A[k * m + p], y = A[k * m + q];
+                    A[k * m + p] = c * x - s * y; A[k * m + q] = s * x + c * y;
+                    x = V[k * m + p]; y = V[k * m + q];
+                    V[k * m + p] = c * x - s * y; V[k * m + q] = s * x + c * y;
+                }
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < m * half; e += blockDim.x) {      /* rows p,q of A */
+                const int t = e / m, k = e - t * m;
+                const double c = js.rc[t], s = js.rs[t];
+                if (s != 0.0) {
+                    const int p = js.rp[t], q = js.rq[t];
+                    const double x = A[p * m + k], y = A[q * m + k];
+                    A[p * m + k] = c * x - s * y; A[q * m + k] = s * x + c * y;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    /* two (three, for diagnostics) largest eigenvalues by value; earliest index wins ties */
+    __shared__ int top[3];
+    if (threadIdx.x == 0) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        for (int i = 0; i < m; i++) {
+            const double e = A[i * m + i];
+            if (i1 < 0 || e > A[i1 * m + i1]) { i3 = i2; i2 = i1; i1 = i; }
+            else if (i2 < 0 || e > A[i2 * m + i2]) { i3 = i2; i2 = i; }
+            else if (i3 < 0 || e > A[i3 * m + i3]) { i3 = i; }
+        }
+        top[0] = i1; top[1] = i2; top[2] = i3;
+        if (evals3) {
+            evals3[0] = A[i1 * m + i1];
+            evals3[1] = i2 >= 0 ? A[i2 * m + i2] : 0.0;
+            evals3[2] = i3 >= 0 ? A[i3 * m + i3] : 0.0;
+        }
+    }
+    __syncthreads();
+    const int i1 = top[0], i2 = top[1];
+    const double s1 = sqrt(A[i1 * m + i1]), s2 = i2 >= 0 ? sqrt(A[i2 * m + i2]) : 0.0;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        X[2 * j] = V[j * m + i1] * s1;
+        X[2 * j + 1] = i2 >= 0 ? V[j * m + i2] * s2 : 0.0;
+    }
+    __syncthreads();
+}
+
+/* dynamic shared memory carve-up shared by the window kernels */
+struct FptCssSmem {
+    double *M0, *M1;          /* two m x m matrices (or global scratch when m is too large) */
+    double *X, *Z;            /* m x 2 each */
+    FptCssScratch sc;
+    FptJacobiScratch js;
+};
+
+FPT_D FptCssSmem fpt_css_carve(unsigned char *smem, int m, int wch, int mats_in_smem, double *gscratch) {
+    FptCssSmem s;
+    size_t off = 0;
+    const size_t mm = (size_t)m * m;
+    if (mats_in_smem) { s.M0 = (double *)(smem + off); off += mm * 8; s.M1 = (double *)(smem + off); off += mm * 8; }
+    else { s.M0 = gscratch; s.M1 = gscratch + mm; }
+    s.X = (double *)(smem + off); off += (size_t)2 * m * 8;
+    s.Z = (double *)(smem + off); off += (size_t)2 * m * 8;
+    s.js.rmean = (double *)(smem + off); off += (size_t)m * 8;
+    const int half = ((m + 1) >> 1) + 1;
+    s.js.rc = (double *)(smem + off); off += (size_t)half * 8;
+    s.js.rs = (double *)(smem + off); off += (size_t)half * 8;
+    s.sc.red = (double *)(smem + off); off += 33 * 8;
+    s.sc.redi = (long long *)(smem + off); off += 33 * 8;
+    s.js.rp = (int *)(smem + off); off += (size_t)half * 4;
+    s.js.rq = (int *)(smem + off); off += (size_t)half * 4;
+    off = (off + 15) & ~(size_t)15;
+    s.sc.wbuf = (unsigned *)(smem + off);
+    s.sc.wch = wch;
+    return s;
+}
+
+FPT_HD size_t fpt_css_smem_bytes(int m, int wch, int mats_in_smem) {
+    const size_t mm = (size_t)m * m;
+    const int half = ((m + 1) >> 1) + 1;
+    size_t off = (mats_in_smem ? 2 * mm * 8 : 0) + (size_t)4 * m * 8 + (size_t)m * 8 + (size_t)2 * half * 8 + 66 * 8 +
+                 (size_t)2 * half * 4;
+    off = (off + 15) & ~(size_t)15;
+    return off + (size_t)wch * 2 * m * 4;
+}
+
+/* mds 0 and the first half of mds 2: one CTA walks windows blockIdx.x, +gridDim.x, ... */
+__global__ void __launch_bounds__(128)
+fpt_css_mds_kernel(const unsigned *__restrict__ planes, const double *__restrict__ absdiff, int m,
+                   const int *__restrict__ wleft, const int *__restrict__ wright, long long nwin, int wch,
+                   int mats_in_smem, double *__restrict__ gscratch, double *__restrict__ Xout,
+                   double *__restrict__ evals_out, unsigned char *__restrict__ status) {
+    FPT_DYN_SMEM(smem);
+    FptCssSmem s = fpt_css_carve(smem, m, wch, mats_in_smem, gscratch ? gscratch + (size_t)blockIdx.x * 2 * m * m : 0);
+    for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
+        const int l = wleft[w], r = wright[w];
+        if (r <= l) { if (threadIdx.x == 0) status[w] = FPT_WIN_EMPTY; continue; }
+        const int keep = fpt_css_dissimilarity(planes, absdiff, m, l, r, s.M0, s.sc);
+        if (!keep) { if (threadIdx.x == 0) status[w] = FPT_WIN_DISCARDED; __syncthreads(); continue; }
+        fpt_css_cmds(s.M0, s.M1, m, s.X, evals_out ? evals_out + 3 * w : 0, s.js, s.sc);
+        for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) Xout[(size_t)w * 2 * m + e] = s.X[e];
+        if (threadIdx.x == 0) status[w] = FPT_WIN_SCORED;
+        __syncthreads();
+    }
+}
+
+/* ============================================================================================
+ * SMACOF (css.c:907-938). Per iteration, exactly the reference's sequence: B(Z) from the current
+ * distances (b_ij = -delta_ij/d_ij, 0 when d_ij < 1e-5; b_ii = -sum_j b_ij accumulated with j counting
+ * down), X = B Z / m with the products accumulated over ascending j (dgemm order), new distances,
+ * stress, Z = X; loop while first pass or (stress drop > eps and k <= max_iters). Distances and B are
+ * symmetric, so each pair is evaluated once and mirrored. The only departure from the reference's
+ * operation order is the stress sum, which is a fixed-order parallel tree instead of one running sum.
+ */
+FPT_D double fpt_css_dist_stress(const double *X, const double *delta, double *Dm, int m, const FptCssScratch &sc) {
+    const int mm = m * m;
+    double part = 0.0;
+    for (int e = threadIdx.x; e < mm; e += blockDim.x) {
+        const int i = e / m, j = e - i * m;
+        if (j < i) {
+            const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
+            const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+            Dm[e] = d; Dm[j * m + i] = d;
+            const double err = __dsub_rn(d, delta[e]);
+            part = __dadd_rn(part, __dmul_rn(err, err));
+        } else if (j == i) {
+            Dm[e] = 0.0;
+        }
+    }
+    return fpt_block_sum(part, sc.red);      /* has the barriers that publish Dm */
+}
+
+FPT_D double fpt_css_smacof(const double *delta, double *Dm, int m, double *X, double *Z, int max_iters, double eps,
+                            const FptCssScratch &sc, int *iters_out) {
+    const int mm = m * m;
+    for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) Z[e] = X[e];
+    __syncthreads();
+    double sigma = fpt_css_dist_stress(X, delta, Dm, m, sc), prev = 0.0;
+    int k = 0;
+    while (k == 0 || (__dsub_rn(prev, sigma) > eps && k <= max_iters)) {
+        prev = sigma;
+        k++;
+        for (int e = threadIdx.x; e < mm; e += blockDim.x) {             /* Dm: distances -> B off-diagonal */
+            const int i = e / m, j = e - i * m;
+            if (j < i) {
+                const double d = Dm[e];
+                const double b = d < 0.00001 ? 0.0 : __ddiv_rn(__dmul_rn(-1.0, delta[e]), d);
+                Dm[e] = b; Dm[j * m + i] = b;
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {           /* one (row, coordinate) per thread */
+            const int i = e >> 1, c = e & 1;
+            const double *brow = Dm + (size_t)i * m;
+            double dsum = 0.0;
+            for (int j = m; j--;) if (j != i) dsum = __dadd_rn(dsum, brow[j]);
+            const double bii = __dmul_rn(-1.0, dsum);
+            double acc = 0.0;
+            for (int j = 0; j < m; j++) acc = __dadd_rn(acc, __dmul_rn(j == i ? bii : brow[j], Z[2 * j + c]));
+            X[e] = __ddiv_rn(acc, (double)m);
+        }
+        __syncthreads();
+        sigma = fpt_css_dist_stress(X, delta, Dm, m, sc);
+        for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) Z[e] = X[e];
+        __syncthreads();
+    }
+    if (iters_out) *iters_out = k;
+    return sigma;
+}
+
+/* one CTA per (window, start). nruns = 4 random starts (mds 1) or 1 start from Xin (mds 2). */
+__global__ void __launch_bounds__(128)
+fpt_css_smacof_kernel(const unsigned *__restrict__ planes, const double *__restrict__ absdiff, int m,
+                      const int *__restrict__ wleft, const int *__restrict__ wright, long long wbase, long long nwin,
+                      int wch, int mats_in_smem, double *__restrict__ gscratch, int nruns, int random_start, uint64_t seed,
+                      const uint64_t *__restrict__ state_override, int max_iters, double eps,
+                      const double *__restrict__ Xin, double *__restrict__ Xruns, double *__restrict__ sigma_runs,
+                      int *__restrict__ iters_runs, unsigned char *__restrict__ status) {
+    FPT_DYN_SMEM(smem);
+    FptCssSmem s = fpt_css_carve(smem, m, wch, mats_in_smem, gscratch ? gscratch + (size_t)blockIdx.x * 2 * m * m : 0);
+    const long long nitems = nwin * nruns;
+    for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const long long w = it / nruns;
+        const int run = (int)(it - w * nruns);
+        const int l = wleft[w], r = wright[w];
+        if (r <= l) { if (threadIdx.x == 0 && run == 0 && random_start) status[w] = FPT_WIN_EMPTY; continue; }
+        if (!random_start && status[w] != FPT_WIN_SCORED) continue;        /* cmds already discarded it */
+        const int keep = fpt_css_dissimilarity(planes, absdiff, m, l, r, s.M0, s.sc);
+        if (!keep) { if (threadIdx.x == 0 && run == 0) status[w] = FPT_WIN_DISCARDED; __syncthreads(); continue; }
+        if (random_start) {
+            /* css.c:861-865: x then y per individual from drand48; start `run` begins 2*m*run draws in */
+            const uint64_t st0 = state_override ? state_override[w] : fpt_stream_state(seed, wbase + w, FPT_STREAM_INIT);
+            for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {
+                uint64_t st = fpt_lcg_skip(st0, (uint64_t)run * 2 * m + e);
+                s.X[e] = fpt_drand48(st);
+            }
+        } else {
+            for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) s.X[e] = Xin[(size_t)w * 2 * m + e];
+        }
+        __syncthreads();
+        int iters = 0;
+        const double sigma = fpt_css_smacof(s.M0, s.M1, m, s.X, s.Z, max_iters, eps, s.sc, &iters);
+        for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) Xruns[(size_t)it * 2 * m + e] = s.X[e];
+        if (threadIdx.x == 0) {
+            sigma_runs[it] = sigma;
+            if (iters_runs) iters_runs[it] = iters;
+            if (run == 0) status[w] = FPT_WIN_SCORED;
+        }
+        __syncthreads();
+    }
+}
+
+/* css.c:876-881: the lowest stress wins, the earliest on ties. (The reference additionally refuses
+   every run at or above its 99999 sentinel and then keeps stale coordinates, Q12; not reproduced.) */
+__global__ void fpt_css_pick_kernel(const double *__restrict__ Xruns, const double *__restrict__ sigma_runs, int m,
+                                    int nruns, long long nwin, const unsigned char *__restrict__ status,
+                                    double *__restrict__ Xout) {
+    for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
+        if (status[w] != FPT_WIN_SCORED) continue;
+        int best = 0;
+        for (int r = 1; r < nruns; r++) if (sigma_runs[w * nruns + r] < sigma_runs[w * nruns + best]) best = r;
+        for (int e = threadIdx.x; e < 2 * m; e += blockDim.x)
+            Xout[(size_t)w * 2 * m + e] = Xruns[((size_t)w * nruns + best) * 2 * m + e];
+    }
+}
+
+/* ============================================================================================
+ * Score and permutation test. One CTA per window; the embedding distances live in shared memory.
+ *
+ * css(): between-group mean minus (asize+bsize) x the within-group terms, which visit only ADJACENT
+ * pairs in track order; every sum is a single running sum counting down, exactly as css.c:608-647,
+ * so a permuted score compares against the observed one the way it does in the reference.
+ *
+ * significance_treshold(): the reference shuffles ONE persistent label array again and again
+ * (Fisher-Yates, m-1 draws each) and stops as soon as `treshold` permuted scores reach the observed
+ * one. Here permutation k of a chunk is generated independently from the stream position k*(m-1)
+ * (skip-ahead) as the permutation it applies to positions, the chain is rebuilt with a prefix scan
+ * under composition, and the early stop is a prefix count of hits — same labels, same hits, same n.
+ */
+template <typename TrackT>
+FPT_D double fpt_css_score(const double *dist, int m, const TrackT *at, const TrackT *bt, int asize, int bsize) {
+    double bet = 0.0;
+    for (int i = asize; i--;) {
+        const double *row = dist + (size_t)at[i] * m;
+        for (int j = bsize; j--;) bet = __dadd_rn(bet, row[bt[j]]);
+    }
+    bet = __ddiv_rn(bet, (double)((long long)asize * bsize));
+    double wa = 0.0, wb = 0.0;
+    if (asize > 1) {
+        for (int i = asize - 1; i--;) wa = __dadd_rn(wa, dist[(size_t)at[i] * m + at[i + 1]]);
+        wa = __ddiv_rn(wa, (double)((long long)asize * asize * (asize - 1)));
+    }
+    if (bsize > 1) {
+        for (int i = bsize - 1; i--;) wb = __dadd_rn(wb, dist[(size_t)bt[i] * m + bt[i + 1]]);
+        wb = __ddiv_rn(wb, (double)((long long)bsize * bsize * (bsize - 1)));
+    }
+    return __dsub_rn(bet, __dmul_rn((double)(asize + bsize), __dadd_rn(wa, wb)));
+}
+
+FPT_HD size_t fpt_css_perm_smem_bytes(int m, int nthreads, int track_bytes, int dist_in_smem, int tracks_in_smem) {
+    size_t off = dist_in_smem ? (size_t)m * m * 8 : 0;
+    off += (size_t)2 * m * 8;                                   /* X */
+    off += (size_t)nthreads * 4 * 2;                            /* offs, cons */
+    off += 33 * 4 + 16;
+    off = (off + 15) & ~(size_t)15;
+    off += (size_t)m * track_bytes;                             /* carry */
+    off = (off + 15) & ~(size_t)15;
+    if (tracks_in_smem) off += (size_t)2 * nthreads * m * track_bytes;
+    return off;
+}
+
+template <typename TrackT>
+__global__ void __launch_bounds__(256)
+fpt_css_perm_kernel(const double *__restrict__ Xall, int m, int asize, int bsize, long long wbase, long long nwin,
+                    const unsigned char *__restrict__ status, int treshold, int runs, uint64_t seed,
+                    const uint64_t *__restrict__ state_override, int dist_in_smem, int tracks_in_smem,
+                    double *__restrict__ gscratch, size_t gscratch_per_cta, double *__restrict__ out_score,
+                    double *__restrict__ out_p, int *__restrict__ out_hits, int *__restrict__ out_n) {
+    FPT_DYN_SMEM(smem);
+    const int T = blockDim.x, tid = threadIdx.x;
+    size_t off = 0;
+    unsigned char *gs = gscratch ? (unsigned char *)gscratch + (size_t)blockIdx.x * gscratch_per_cta : 0;
+    double *dist;
+    if (dist_in_smem) { dist = (double *)(smem + off); off += (size_t)m * m * 8; }
+    else { dist = (double *)gs; gs += (size_t)m * m * 8; }
+    double *X = (double *)(smem + off); off += (size_t)2 * m * 8;
+    int *offs = (int *)(smem + off); off += (size_t)T * 4;
+    int *cons = (int *)(smem + off); off += (size_t)T * 4;
+    int *scan = (int *)(smem + off); off += 33 * 4 + 16;
+    off = (off + 15) & ~(size_t)15;
+    TrackT *carry = (TrackT *)(smem + off); off += (size_t)m * sizeof(TrackT);
+    off = (off + 15) & ~(size_t)15;
+    TrackT *buf0, *buf1;
+    if (tracks_in_smem) { buf0 = (TrackT *)(smem + off); buf1 = buf0 + (size_t)T * m; }
+    else { buf0 = (TrackT *)gs; buf1 = buf0 + (size_t)T * m; }
+    __shared__ double s_score;
+    __shared__ int s_flag;
+
+    for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
+        if (status[w] != FPT_WIN_SCORED) continue;
+        for (int e = tid; e < 2 * m; e += T) X[e] = Xall[(size_t)w * 2 * m + e];
+        __syncthreads();
+        for (int e = tid; e < m * m; e += T) {                  /* calc_dist, css.c:573-587 */
+            const int i = e / m, j = e - i * m;
+            if (j < i) {
+                const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
+                const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                dist[e] = d; dist[j * m + i] = d;
+            } else if (j == i) dist[e] = 0.0;
+        }
+        for (int e = tid; e < m; e += T) carry[e] = (TrackT)e;
+        __syncthreads();
+        if (tid == 0) s_score = fpt_css_score<TrackT>(dist, m, carry, carry + asize, asize, bsize);
+        __syncthreads();
+        const double score = s_score;
+        const uint64_t st_win = state_override ? state_override[w] : fpt_stream_state(seed, wbase + w, FPT_STREAM_RESAMPLE);
+        const int draws = m - 1;
+        long long stream_pos = 0;                               /* draws consumed by finished chunks */
+        int hits = 0, ndone = 0;
+        bool stopped = false;
+        while (!stopped && hits < treshold && ndone < runs) {
+            const int nvalid = min(T, runs - ndone);
+            offs[tid] = tid * draws;
+            __syncthreads();
+            TrackT *mine = buf0 + (size_t)tid * m;
+            for (;;) {                                          /* generate; repair offsets after rejections */
+                int used = 0;
+                if (tid < nvalid) {
+                    uint64_t st = fpt_lcg_skip(st_win, (uint64_t)(stream_pos + offs[tid]));
+                    for (int e = 0; e < m; e++) mine[e] = (TrackT)e;
+                    for (int i = m - 1; i > 0; i--) {
+                        const int rr = (int)fpt_randint((uint32_t)(i + 1), st, used);
+                        const TrackT t = mine[i]; mine[i] = mine[rr]; mine[rr] = t;
+                    }
+                }
+                int total = 0;
+                const int incl = fpt_block_scan_incl(used, scan, &total);
+                const int want = incl - used;
+                const int bad = (tid < nvalid && want != offs[tid]) ? 1 : 0;
+                if (bad) offs[tid] = want;
+                cons[tid] = total;
+                if (!__syncthreads_or(bad)) break;
+            }
+            const int chunk_draws = cons[0];
+            /* inclusive scan under composition: G_k = s_1 o ... o s_k, (f o g)[pos] = f[g[pos]] */
+            TrackT *src = buf0, *dst = buf1;
+            for (int d = 1; d < nvalid; d <<= 1) {
+                __syncthreads();
+                if (tid < nvalid) {
+                    const TrackT *g = src + (size_t)tid * m;
+                    TrackT *o = dst + (size_t)tid * m;
+                    if (tid >= d) {
+                        const TrackT *f = src + (size_t)(tid - d) * m;
+                        for (int e = 0; e < m; e++) o[e] = f[g[e]];
+                    } else {
+                        for (int e = 0; e < m; e++) o[e] = g[e];
+                    }
+                }
+                TrackT *tmp = src; src = dst; dst = tmp;
+            }
+            __syncthreads();
+            int hit = 0;
+            if (tid < nvalid) {
+                const TrackT *g = src + (size_t)tid * m;
+                TrackT *o = dst + (size_t)tid * m;                /* labels after permutation ndone+tid+1 */
+                for (int e = 0; e < m; e++) o[e] = carry[g[e]];
+                hit = fpt_css_score<TrackT>(dist, m, o, o + asize, asize, bsize) >= score ? 1 : 0;
+            }
+            int chunk_hits = 0;
+            const int hincl = fpt_block_scan_incl(hit, scan, &chunk_hits);
+            if (tid == 0) s_flag = -1;
+            __syncthreads();
+            if (hit && hits + hincl == treshold) s_flag = tid;  /* the permutation at which the loop exits */
+            __syncthreads();
+            if (s_flag >= 0) {
+                ndone += s_flag + 1; hits = treshold; stopped = true;
+            } else {
+                hits += chunk_hits; ndone += nvalid;
+                const TrackT *last = dst + (size_t)(nvalid - 1) * m;
+                for (int e = tid; e < m; e += T) carry[e] = last[e];
+                stream_pos += chunk_draws;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            out_score[w] = score;
+            out_p[w] = __ddiv_rn(__dmul_rn((double)(hits + 1), 1.0), (double)(ndone + 1));
+            if (out_hits) out_hits[w] = hits;
+            if (out_n) out_n[w] = ndone;
+        }
+        __syncthreads();
+    }
+}
+
+#endif

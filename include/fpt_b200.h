@@ -1,0 +1,173 @@
+/*
+ * fpt_b200.h — C ABI of libfpt_b200.so, the B200 (sm_100a) implementation of the reference's two
+ * genome-wide divergence scans: the per-SNP Fisher's exact test with its per-window percentile and
+ * bootstrap sigma (FET) and the per-window Cluster Separation Score with MDS and permutation test (CSS).
+ *
+ * Plain C: pointers, sizes and scalars only. Reference paths below are relative to
+ * /root/reference/statistics/.
+ *
+ * Three layers, all in one library:
+ *   1. drop-in entry points with the reference's exact argument lists (host pointers);
+ *   2. extended host entry points (compact inputs, window ranges for sharding, explicit RNG control,
+ *      parity probes);
+ *   3. a device-resident API (device pointers + cudaStream_t) used by pipelines that keep data in HBM.
+ *
+ * Every function returns FPT_OK (0) or a negative FPT_ERR_* code; fpt_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * FPT_ERR_NO_DEVICE.
+ */
+#ifndef FPT_B200_H
+#define FPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPT_OK 0
+#define FPT_ERR_CUDA (-1)              /* a CUDA runtime call or kernel failed */
+#define FPT_ERR_ARG (-2)               /* invalid argument */
+#define FPT_ERR_POSITIONS (-3)         /* populations A and B do not share the same SNP positions (the
+                                          reference silently mis-pairs SNPs in that case) */
+#define FPT_ERR_WINDOW_TOO_LARGE (-4)  /* a window holds more SNPs than one CTA can sort in shared memory */
+#define FPT_ERR_NO_DEVICE (-5)         /* no usable CUDA device */
+
+/* scan semantics: which windows a scan visits */
+#define FPT_SCAN_SERIAL 0              /* `compute`:       fisher/cFisher.c:81, css/css.c:117 */
+#define FPT_SCAN_THREADED 1            /* `threadcompute`: fisher/threadfisher.c:55-58,191-218 (tasks of 100
+                                          windows; nothing at all when regend/wstep < 103) */
+
+/* per-window status reported by the CSS probes */
+#define FPT_WIN_EMPTY 0
+#define FPT_WIN_DISCARDED 1
+#define FPT_WIN_SCORED 2
+
+/* ------------------------------------------------------------------------------------------------
+ * library state
+ */
+const char *fpt_last_error(void);
+int fpt_device_count(void);                 /* number of CUDA devices, 0 if none / no driver */
+int fpt_set_device(int device);             /* device used by the host entry points of this process */
+void fpt_set_seed(uint64_t seed);           /* seed of the window-keyed random streams (default 20261018) */
+uint64_t fpt_get_seed(void);
+void fpt_release(void);                     /* free cached device/pinned buffers */
+/* 48-bit LCG state of (seed, global window index, stream); stream 0 = bootstrap / label shuffles
+   (nrand48 draws), 1 = SMACOF starts (drand48 draws). Pure host arithmetic. */
+uint64_t fpt_window_state(uint64_t seed, int64_t window, int stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 1. drop-in entry points (host pointers, caller-owned, outputs pre-zeroed by the caller; only scored
+ *    windows are written, at index window_start / wstep; nothing is written at or beyond index
+ *    regend / wstep).
+ *
+ * fpt_fet_threadcompute == `threadcompute` of fisher/threadfisher.h:33-34 (fisher/threadfisher.c:47-100),
+ *                          bound by fisher/fisher_cython_parallel.pyx:4-5,14-15
+ * fpt_fet_compute       == `compute` of fisher/cFisher.h:11 (fisher/cFisher.c:38-115),
+ *                          bound by fisher/fisher_cython.pyx:4-5,10-11
+ * fpt_css_threadcompute == `threadcompute` of css/threadcss.h:36-37 (css/threadcss.c:52-109),
+ *                          bound by css/css_cython_parallel.pyx:4-5,14-15
+ * fpt_css_compute       == `compute` of css/css.h:10 (css/css.c:49-156), bound by css/css_cython.pyx
+ *
+ * vals: float64 genotype codes (3, -3, 0, -10000), position-major / individual-minor;
+ * pos: int32 position of every value (each SNP position repeated once per individual).
+ */
+int fpt_fet_threadcompute(double *avals, double *bvals, int *apos, int *bpos, int regstart, int regend, int wsize,
+                          int wstep, int alen, int blen, double perc, double *scores, double *stddev);
+int fpt_fet_compute(double *avals, double *bvals, int *apos, int *bpos, int regstart, int regend, int wsize,
+                    int wstep, int alen, int blen, double perc, double *scores, double *stddev);
+int fpt_css_threadcompute(double *avals, double *bvals, int *apos, int *bpos, int regstart, int regend, int wsize,
+                          int wstep, int alen, int blen, int treshold, int runs, int drosophila, int mds,
+                          double *scores, double *p);
+int fpt_css_compute(double *avals, double *bvals, int *apos, int *bpos, int regstart, int regend, int wsize,
+                    int wstep, int alen, int blen, int treshold, int runs, int drosophila, int mds, double *scores,
+                    double *p);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2. extended host entry points
+ */
+
+/* Input description shared by the extended scans. Exactly one of {avals/bvals} (float64, reference
+   layout) or {acodes/bcodes} (int8: 3, -3, anything else = other) must be set; pos holds ONE int32
+   position per SNP (nsnp entries, sorted ascending). */
+typedef struct fpt_genotypes {
+    const double *avals, *bvals;
+    const int8_t *acodes, *bcodes;
+    const int32_t *pos;
+    int64_t nsnp;
+    int asize, bsize;
+} fpt_genotypes;
+
+/* Window range and RNG control. Windows window_begin <= w < window_end (global indices, w = start/wstep)
+   are processed; outputs are indexed by w - window_begin and must hold window_end - window_begin entries.
+   states_* (optional, same indexing) override the window-keyed streams with explicit 48-bit LCG states. */
+typedef struct fpt_scan_range {
+    int regend, wsize, wstep;
+    int semantics;                      /* FPT_SCAN_SERIAL or FPT_SCAN_THREADED */
+    int64_t window_begin, window_end;
+    uint64_t seed;
+    const uint64_t *states_resample;    /* bootstrap (FET) / permutation (CSS) streams */
+    const uint64_t *states_init;        /* SMACOF random starts (CSS, mds = 1) */
+} fpt_scan_range;
+
+/* optional per-window probes of the CSS scan (any pointer may be NULL) */
+typedef struct fpt_css_probes {
+    uint8_t *status;                    /* FPT_WIN_* */
+    double *X;                          /* final embedding, m x 2 per window */
+    double *evals;                      /* three largest eigenvalues of the classical-MDS matrix */
+    int32_t *hits, *nperm;              /* permutation test: hits and permutations actually drawn */
+    int32_t *smacof_iters;              /* nruns entries per window (mds 1: 4, mds 2: 1) */
+    double *smacof_sigma;
+} fpt_css_probes;
+
+int fpt_fet_scan(const fpt_genotypes *g, const fpt_scan_range *r, double perc, double *scores, double *stddev,
+                 uint8_t *written);
+int fpt_css_scan(const fpt_genotypes *g, const fpt_scan_range *r, int treshold, int runs, int drosophila, int mds,
+                 double *scores, double *p, uint8_t *written, const fpt_css_probes *probes);
+
+/* per-SNP stage on its own: tables[4*nsnp] = {A major, A minor, B major, B minor} (fetcount,
+   fisher/cFisher.c:208-238) and/or neglog10p[nsnp] = -log10 P (fet, cFisher.c:405-455); either output
+   may be NULL */
+int fpt_fet_per_snp(const fpt_genotypes *g, int32_t *tables, double *neglog10p);
+/* direct 2x2 tables (BASELINE config "genome-scale FET"): tables[4*n] -> neglog10p[n];
+   force_log != 0 evaluates every table in log mode (cross-check of the two arithmetic modes) */
+int fpt_fet_tables(const int32_t *tables, int64_t n, int force_log, double *neglog10p);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3. device-resident API. All pointers are DEVICE pointers of the current device; `stream` is a
+ *    cudaStream_t passed as void* (NULL = default stream). Calls only enqueue work unless noted.
+ */
+int fpt_dev_fet_count_f64(const double *avals, const double *bvals, int64_t nsnp, int asize, int bsize,
+                          int32_t *tables, void *stream);
+int fpt_dev_fet_count_i8(const int8_t *acodes, const int8_t *bcodes, int64_t nsnp, int asize, int bsize,
+                         int32_t *tables, void *stream);
+/* max_n = largest a+b+c+d among the tables (sizes the log-factorial table); <= 0: computed (synchronises) */
+int fpt_dev_fet_score(const int32_t *tables, int64_t n, int max_n, int force_log, double *neglog10p, void *stream);
+/* wleft/wright: nwin int32 each; max_npos: one int32 (device), must be zeroed by the caller */
+int fpt_dev_window_table(const int32_t *pos, int64_t nsnp, const fpt_scan_range *r, int32_t *wleft, int32_t *wright,
+                         int32_t *max_npos, void *stream);
+/* max_npos: host value read back from fpt_dev_window_table's counter */
+int fpt_dev_fet_windows(const double *snp_scores, const int32_t *wleft, const int32_t *wright,
+                        const fpt_scan_range *r, int max_npos, double perc, const uint64_t *states, double *scores,
+                        double *stddev, uint8_t *written, void *stream);
+/* planes: 2 * m * ceil(nsnp/32) uint32 */
+size_t fpt_dev_css_planes_bytes(int64_t nsnp, int m);
+int fpt_dev_css_pack_f64(const double *avals, const double *bvals, int64_t nsnp, int asize, int bsize,
+                         uint32_t *planes, void *stream);
+int fpt_dev_css_pack_i8(const int8_t *acodes, const int8_t *bcodes, int64_t nsnp, int asize, int bsize,
+                        uint32_t *planes, void *stream);
+int fpt_dev_css_absdiff(const double *afreq, const double *bfreq, int64_t nsnp, double *absdiff, void *stream);
+/* workspace for fpt_dev_css_windows (embeddings of every window and start, per-CTA scratch for large m) */
+size_t fpt_dev_css_workspace_bytes(int m, int64_t nwin, int mds);
+/* planes (or absdiff when drosophila != 0) -> scores, p, status (nwin each). states_* and probes hold
+   DEVICE pointers here. */
+int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff, int asize, int bsize, const int32_t *wleft,
+                        const int32_t *wright, const fpt_scan_range *r, int treshold, int runs, int mds,
+                        void *workspace, size_t workspace_bytes, double *scores, double *p, uint8_t *status,
+                        const fpt_css_probes *probes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,142 @@
+/*
+ * emu_driver.cpp — runs the product's kernels (csrc/fpt_*.cuh) on the CPU through tests/emu/cuda_emu.h.
+ * TEST INFRASTRUCTURE ONLY: built by tests/emu/build.sh into tests/emu/libfpt_emu.so and loaded by
+ * tests/test_emu_*.py so that kernel logic is exercised in the CPU-only test suite. The product never
+ * loads this library.
+ */
+#include "cuda_emu.h"
+FPT_EMU_DEFINE_GLOBALS
+
+#include "fpt_rt.cuh"
+#include "fpt_fet.cuh"
+#include "fpt_css.cuh"
+#include "fpt_tables.h"
+
+template <class F>
+static void run_grid(unsigned nb, unsigned nt, size_t smem, F f) {
+    emu::launch(nb, nt, smem, [](void *p) { (*(F *)p)(); }, &f);
+}
+
+extern "C" {
+
+uint64_t emu_window_state(uint64_t seed, long long w, int stream) { return fpt_stream_state(seed, w, stream); }
+uint64_t emu_lcg_skip(uint64_t s, uint64_t n) { return fpt_lcg_skip(s, n); }
+
+void emu_fet_count_f64(const double *a, const double *b, long long nsnp, int asize, int bsize, int tile, int grid,
+                       int *tables) {
+    size_t smem = (((size_t)tile * asize + 15) & ~(size_t)15) + (size_t)tile * bsize + 16;
+    run_grid(grid, 64, smem, [=]() { fpt_fet_count_kernel<double>(a, b, nsnp, asize, bsize, tile, (int4 *)tables); });
+}
+
+void emu_fet_count_i8(const signed char *a, const signed char *b, long long nsnp, int asize, int bsize, int tile,
+                      int grid, int *tables) {
+    size_t smem = (((size_t)tile * asize + 15) & ~(size_t)15) + (size_t)tile * bsize + 16;
+    run_grid(grid, 64, smem, [=]() { fpt_fet_count_kernel<signed char>(a, b, nsnp, asize, bsize, tile, (int4 *)tables); });
+}
+
+void emu_fet_score(const int *tables, long long n, int maxn, int lf_in_smem, int force_log, int grid, double *scores) {
+    std::vector<unsigned long long> binom = fpt_build_binom_table();
+    std::vector<double> lf = fpt_build_lfact_table(maxn);
+    size_t smem = FPT_BINOM_ENTRIES * 8 + (lf_in_smem ? ((size_t)maxn + 1) * 8 : 0);
+    const unsigned long long *bp = binom.data();
+    const double *lp = lf.data();
+    run_grid(grid, 64, smem, [=]() {
+        fpt_fet_score_kernel((const int4 *)tables, n, bp, lp, maxn, lf_in_smem, force_log, scores);
+    });
+}
+
+int emu_fet_maxn(const int *tables, long long n) {
+    int out = 0;
+    int *po = &out;
+    run_grid(2, 64, 0, [=]() { fpt_fet_maxn_kernel((const int4 *)tables, n, po); });
+    return out;
+}
+
+int emu_window_table(const int *pos, long long nsnp, long long wbase, long long nwin, int regend, int wsize, int wstep, int threaded,
+                     int *wleft, int *wright) {
+    int mx = 0;
+    int *pm = &mx;
+    unsigned nb = (unsigned)((nwin + 63) / 64);
+    run_grid(nb, 64, 0, [=]() { fpt_window_table_kernel(pos, nsnp, wbase, nwin, regend, wsize, wstep, threaded, wleft, wright, pm); });
+    return mx;
+}
+
+void emu_fet_window(const double *snp_scores, const int *wleft, const int *wright, long long wbase, long long nwin, double perc,
+                    uint64_t seed, const uint64_t *state_override, int max_npos, int use_hist, int grid,
+                    double *out_score, double *out_std, unsigned char *out_flag) {
+    int npad = 2;
+    while (npad < max_npos) npad <<= 1;
+    size_t smem = (size_t)npad * 8 + (use_hist ? (size_t)FPT_FET_NSAMPLES * max_npos * 2 : 0);
+    run_grid(grid, 128, smem, [=]() {
+        fpt_fet_window_kernel(snp_scores, wleft, wright, wbase, nwin, perc, seed, state_override, npad, use_hist, out_score,
+                              out_std, out_flag);
+    });
+}
+
+void emu_css_pack_f64(const double *a, const double *b, long long nsnp, int asize, int bsize, int wpt, int grid,
+                      unsigned *planes) {
+    size_t smem = (((size_t)wpt * 32 * asize + 15) & ~(size_t)15) + (size_t)wpt * 32 * bsize + 16;
+    run_grid(grid, 64, smem, [=]() { fpt_css_pack_kernel<double>(a, b, nsnp, asize, bsize, wpt, planes); });
+}
+
+void emu_css_pack_i8(const signed char *a, const signed char *b, long long nsnp, int asize, int bsize, int wpt,
+                     int grid, unsigned *planes) {
+    size_t smem = (((size_t)wpt * 32 * asize + 15) & ~(size_t)15) + (size_t)wpt * 32 * bsize + 16;
+    run_grid(grid, 64, smem, [=]() { fpt_css_pack_kernel<signed char>(a, b, nsnp, asize, bsize, wpt, planes); });
+}
+
+void emu_css_absdiff(const double *a, const double *b, long long n, double *out) {
+    run_grid(2, 64, 0, [=]() { fpt_css_absdiff_kernel(a, b, n, out); });
+}
+
+void emu_css_mds(const unsigned *planes, const double *absdiff, int m, const int *wleft, const int *wright,
+                 long long nwin, int wch, int mats_in_smem, int grid, double *X, double *evals, unsigned char *status) {
+    size_t smem = fpt_css_smem_bytes(m, wch, mats_in_smem);
+    std::vector<double> gs(mats_in_smem ? 1 : (size_t)grid * 2 * m * m);
+    double *gp = mats_in_smem ? 0 : gs.data();
+    run_grid(grid, 128, smem, [=]() {
+        fpt_css_mds_kernel(planes, absdiff, m, wleft, wright, nwin, wch, mats_in_smem, gp, X, evals, status);
+    });
+}
+
+void emu_css_smacof(const unsigned *planes, const double *absdiff, int m, const int *wleft, const int *wright,
+                    long long wbase, long long nwin, int wch, int mats_in_smem, int grid, int nruns, int random_start, uint64_t seed,
+                    const uint64_t *state_override, int max_iters, double eps, const double *Xin, double *Xruns,
+                    double *sigma_runs, int *iters_runs, unsigned char *status) {
+    size_t smem = fpt_css_smem_bytes(m, wch, mats_in_smem);
+    std::vector<double> gs(mats_in_smem ? 1 : (size_t)grid * 2 * m * m);
+    double *gp = mats_in_smem ? 0 : gs.data();
+    run_grid(grid, 128, smem, [=]() {
+        fpt_css_smacof_kernel(planes, absdiff, m, wleft, wright, wbase, nwin, wch, mats_in_smem, gp, nruns, random_start, seed,
+                              state_override, max_iters, eps, Xin, Xruns, sigma_runs, iters_runs, status);
+    });
+}
+
+void emu_css_pick(const double *Xruns, const double *sigma_runs, int m, int nruns, long long nwin,
+                  const unsigned char *status, double *Xout) {
+    run_grid(2, 64, 0, [=]() { fpt_css_pick_kernel(Xruns, sigma_runs, m, nruns, nwin, status, Xout); });
+}
+
+void emu_css_perm(const double *Xall, int m, int asize, int bsize, long long wbase, long long nwin, const unsigned char *status,
+                  int treshold, int runs, uint64_t seed, const uint64_t *state_override, int dist_in_smem,
+                  int tracks_in_smem, int nthreads, int grid, int wide_tracks, double *out_score, double *out_p,
+                  int *out_hits, int *out_n) {
+    int tb = wide_tracks ? 2 : 1;
+    size_t smem = fpt_css_perm_smem_bytes(m, nthreads, tb, dist_in_smem, tracks_in_smem);
+    size_t per_cta = (dist_in_smem ? 0 : (size_t)m * m * 8) + (tracks_in_smem ? 0 : (size_t)2 * nthreads * m * tb);
+    per_cta = (per_cta + 15) & ~(size_t)15;
+    std::vector<double> gs(per_cta ? (size_t)grid * per_cta / 8 + 2 : 1);
+    double *gp = per_cta ? gs.data() : 0;
+    if (wide_tracks)
+        run_grid(grid, nthreads, smem, [=]() {
+            fpt_css_perm_kernel<unsigned short>(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override,
+                                                dist_in_smem, tracks_in_smem, gp, per_cta, out_score, out_p, out_hits, out_n);
+        });
+    else
+        run_grid(grid, nthreads, smem, [=]() {
+            fpt_css_perm_kernel<unsigned char>(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override,
+                                               dist_in_smem, tracks_in_smem, gp, per_cta, out_score, out_p, out_hits, out_n);
+        });
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes, host buffers), against the CPU
+oracle (oracle/liboracle.so) and — where oracle/_ref travelled along — the compiled reference itself, on the
+same seeded inputs.
+
+Tolerances (BASELINE.json north_star): contingency tables, window indexing and scored/discarded calls bit-exact;
+FET -log10 P within 1e-9 relative; CSS scores within 1e-5 relative; permutation p-values identical for the same
+random stream.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import checkers
+from checkers import dptr, iptr
+
+pytestmark = pytest.mark.gpu
+
+FET_RTOL = 1e-9
+CSS_RTOL = 1e-5
+
+
+def _synth(seed, length, nsnp, asize, bsize, **kw):
+    import fpt_b200.synth as synth
+    ch = synth.chromosome(seed, length, nsnp, asize, bsize, **kw)
+    return ch, synth.reference_layout(ch)
+
+
+# ------------------------------------------------------------------------------------------------ FET
+@pytest.mark.parametrize("asize,bsize,nsnp", [(20, 20, 20000), (11, 10, 3001), (1, 1, 257), (33, 40, 5000), (300, 250, 700)])
+def test_fet_per_snp_tables_and_scores(fpt, oracle, asize, bsize, nsnp):
+    ch, (av, bv, _, _) = _synth(11 + asize, 10 * nsnp, nsnp, asize, bsize)
+    tab_o = np.zeros((nsnp, 4), dtype=np.int32)
+    sc_o = np.zeros(nsnp)
+    oracle.fpt_oracle_fet_per_snp(dptr(av), dptr(bv), nsnp, asize, bsize, iptr(tab_o), dptr(sc_o))
+    for a, b in ((av, bv), (ch["acodes"], ch["bcodes"])):        # reference layout and compact codes
+        tab, sc = fpt.fet_per_snp(a, b, asize, bsize)
+        assert np.array_equal(tab, tab_o)                        # bit-exact contingency tables
+        np.testing.assert_allclose(sc, sc_o, rtol=FET_RTOL, atol=1e-13)
+        assert np.array_equal(sc == 0, sc_o == 0)
+
+
+def test_fet_exact_domain_all_small_tables(fpt, oracle):
+    """every 2x2 table with N <= 24 plus a sample up to N = 67: the exact-arithmetic domain of the reference"""
+    t = [(a, b, c, n - a - b - c) for n in range(25) for a in range(n + 1) for b in range(n + 1 - a) for c in range(n + 1 - a - b)]
+    rng = np.random.default_rng(5)
+    for _ in range(40000):
+        n = int(rng.integers(25, 68))
+        cuts = np.sort(rng.integers(0, n + 1, size=3))
+        t.append((cuts[0], cuts[1] - cuts[0], cuts[2] - cuts[1], n - cuts[2]))
+    T = np.array(t, dtype=np.int32)
+    so = np.zeros(len(T))
+    oracle.fpt_oracle_fet_tables(iptr(T), len(T), dptr(so))
+    sg = fpt.fet_tables(T)
+    np.testing.assert_allclose(sg, so, rtol=FET_RTOL, atol=1e-13)
+    assert np.array_equal(sg == 0, so == 0)
+    if checkers.ref_available():                                  # and against the compiled reference's fet()
+        rf = checkers.load_ref_fet()
+        tmp = (C.c_int * 4)()
+        idx = rng.choice(len(T), size=20000, replace=False)
+        for i in idx:
+            f = (C.c_int * 4)(*[int(v) for v in T[i]])
+            pr = rf.fet(f, tmp)
+            want = -1.0 * np.log10(pr)
+            assert abs(sg[i] - want) <= FET_RTOL * abs(want) + 1e-13
+
+
+def test_fet_log_mode_high_coverage(fpt, oracle):
+    import fpt_b200.synth as synth
+    T = synth.coverage_tables(3, 200000, 20, 500)
+    so = np.zeros(len(T))
+    oracle.fpt_oracle_fet_tables(iptr(T), len(T), dptr(so))
+    sg = fpt.fet_tables(T)
+    np.testing.assert_allclose(sg, so, rtol=FET_RTOL, atol=1e-12)
+    # forcing log mode on small tables agrees with exact mode except on the reference's rounding-dependent ties
+    Ts = synth.coverage_tables(4, 50000, 2, 30)
+    e, l = fpt.fet_tables(Ts), fpt.fet_tables(Ts, force_log=True)
+    close = np.isclose(e, l, rtol=1e-9, atol=1e-12)
+    assert close.mean() > 0.99
+
+
+@pytest.mark.parametrize("semantics", [0, 1])
+@pytest.mark.parametrize("geom", [(2500, 500), (1000, 1000), (700, 300)])
+def test_fet_scan_matches_oracle(fpt, oracle, semantics, geom):
+    wsize, wstep = geom
+    regend, nsnp, asize, bsize, seed = 150000, 4000, 20, 20, 99
+    ch, (av, bv, apos, bpos) = _synth(21, regend, nsnp, asize, bsize)
+    n = regend // wstep
+    s_o, d_o = np.zeros(n), np.zeros(n)
+    assert oracle.fpt_oracle_fet_scan(dptr(av), dptr(bv), iptr(apos), iptr(bpos), 0, regend, wsize, wstep, av.size, bv.size,
+                                      0.95, dptr(s_o), dptr(d_o), semantics, seed) == 0
+    s_g, d_g, wr = fpt.fet_scan(av, bv, ch["pos"], asize, bsize, regend, wsize, wstep, 0.95, semantics=semantics, seed=seed)
+    np.testing.assert_allclose(s_g, s_o, rtol=FET_RTOL, atol=1e-13)
+    np.testing.assert_allclose(d_g, d_o, rtol=1e-9, atol=1e-13)
+    # sharded: two window ranges reproduce the full scan exactly (streams are keyed by global window index)
+    h = n // 2 + 3
+    s1, d1, _ = fpt.fet_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 0.95, semantics=semantics,
+                             seed=seed, window_begin=0, window_end=h)
+    s2, d2, _ = fpt.fet_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 0.95, semantics=semantics,
+                             seed=seed, window_begin=h, window_end=n)
+    assert np.array_equal(np.concatenate([s1, s2]), s_g) and np.array_equal(np.concatenate([d1, d2]), d_g)
+
+
+def test_fet_dropin_matches_reference(fpt, ref_fet):
+    """the drop-in Cython-signature call against the reference's own serial `compute` (deterministic column)"""
+    import fpt_b200.fisher_cython as serial
+    import fpt_b200.fisher_cython_parallel as par
+    regend, wsize, wstep, nsnp, asize, bsize = 120000, 2500, 500, 3000, 20, 20
+    ch, (av, bv, apos, bpos) = _synth(31, regend, nsnp, asize, bsize)
+    n = regend // wstep
+    s_r, d_r = np.zeros(n), np.zeros(n)
+    with checkers.silence_stdout():
+        ref_fet.compute(dptr(av), dptr(bv), iptr(apos), iptr(bpos), 0, regend, wsize, wstep, av.size, bv.size, 0.95, dptr(s_r), dptr(d_r))
+    for mod in (serial, par):
+        s_g, d_g = np.zeros(n), np.zeros(n)
+        mod.fisher_exact_tester(av, bv, apos, bpos, 0, regend, wsize, wstep, av.size, bv.size, 0.95, s_g, d_g)
+        np.testing.assert_allclose(s_g, s_r, rtol=FET_RTOL, atol=1e-13)
+    # threaded semantics: nothing is computed below 103 windows
+    s_g, d_g = np.zeros(100), np.zeros(100)
+    par.fisher_exact_tester(av, bv, apos, bpos, 0, 50000, wsize, wstep, av.size, bv.size, 0.95, s_g, d_g)
+    assert not s_g.any() and not d_g.any()
+
+
+def test_fet_window_bootstrap_matches_reference_stream(fpt, ref_fet):
+    """one window, explicit 48-bit state: sigma equals the reference's fisher_exact_test run from that state"""
+    asize = bsize = 20
+    for npos, state in ((37, 0x1234ABCD5678), (5, 42), (1, 7), (300, 0xFFFFFFFFFFFF), (1000, 99)):
+        ch, (av, bv, _, _) = _synth(npos, 100000, npos, asize, bsize)
+        res = np.zeros(2)
+        f, tmp = (C.c_int * 4)(), (C.c_int * 4)()
+        samples, stds, fets = np.zeros(npos), np.zeros(100), np.zeros(npos)
+        st = checkers.state_to_ushort3(state)
+        ref_fet.fisher_exact_test(dptr(res), dptr(av), dptr(bv), asize, bsize, npos, f, tmp, dptr(samples), dptr(stds), 100, dptr(fets), st, 0.95)
+        pos = np.arange(npos, dtype=np.int32)
+        s, d, w = fpt.fet_scan(av, bv, pos, asize, bsize, 100000, 100000, 100000, 0.95, states=np.array([state], dtype=np.uint64))
+        assert w[0] == 1
+        if npos > 1:                                   # n == 1 makes the reference read one past its array (Q8)
+            np.testing.assert_allclose(s[0], res[0], rtol=FET_RTOL, atol=1e-13)
+            np.testing.assert_allclose(d[0], res[1], rtol=1e-9, atol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------------ CSS
+def _css_oracle_scan(oracle, av, bv, apos, bpos, regend, wsize, wstep, mct, mcr, mds, semantics, seed, dros=0):
+    n = regend // wstep
+    s_o, p_o = np.zeros(n), np.zeros(n)
+    assert oracle.fpt_oracle_css_scan(dptr(av), dptr(bv), iptr(apos), iptr(bpos), 0, regend, wsize, wstep, av.size, bv.size,
+                                      mct, mcr, dros, mds, dptr(s_o), dptr(p_o), semantics, seed) == 0
+    return s_o, p_o
+
+
+@pytest.mark.parametrize("mds", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(20, 20, 2500, 500), (7, 9, 3000, 1000), (2, 2, 2500, 500)])
+def test_css_scan_matches_oracle(fpt, oracle, mds, shape):
+    asize, bsize, wsize, wstep = shape
+    regend, nsnp, seed = 60000, 1500, 5
+    ch, (av, bv, apos, bpos) = _synth(41 + asize, regend, nsnp, asize, bsize)
+    s_o, p_o = _css_oracle_scan(oracle, av, bv, apos, bpos, regend, wsize, wstep, 10, 200, mds, 0, seed)
+    s_g, p_g, wr, pr = fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 10, 200, mds=mds,
+                                    seed=seed, probes=True)
+    assert np.array_equal(wr == 1, p_o != 0)                     # same windows scored / discarded
+    finite = np.isfinite(s_o) & np.isfinite(s_g)
+    if mds != 1:
+        # with lambda2 ~ lambda3 the embedding depends on the eigensolver's arbitrary basis
+        ev = pr["evals"]
+        finite &= ~((wr == 1) & ((ev[:, 1] - ev[:, 2]) < 1e-8 * np.maximum(ev[:, 0], 1e-300)))
+    assert finite.sum() >= 0.8 * (wr == 1).sum()
+    # SMACOF's stopping rule leaves the embedding converged to ~1e-5 only, so a window whose iteration count
+    # differs by one (stress drop within rounding of the 1e-6 threshold) may move by that much; allow a few.
+    rel = np.abs(s_g[finite] - s_o[finite]) / np.maximum(np.abs(s_o[finite]), 1e-300)
+    bad = rel > CSS_RTOL
+    assert bad.sum() <= (0 if mds == 0 else max(1, int(0.01 * finite.sum()))), "CSS score mismatches: %d (max rel %g)" % (bad.sum(), rel.max())
+    agree = ~bad
+    assert np.array_equal(p_g[finite][agree], p_o[finite][agree])      # identical permutation p-values
+    # f64 reference layout gives the same bits as compact codes
+    s_f, p_f, _ = fpt.css_scan(av, bv, ch["pos"], asize, bsize, regend, wsize, wstep, 10, 200, mds=mds, seed=seed)
+    assert np.array_equal(s_f, s_g, equal_nan=True) and np.array_equal(p_f, p_g)
+
+
+@pytest.mark.parametrize("mct,mcr", [(1000, 1000), (10, 5000), (1, 300), (0, 100), (3, 0)])
+def test_css_permutation_early_stop_matches_oracle(fpt, oracle, mct, mcr):
+    asize, bsize, wsize, wstep, regend, nsnp, seed = 20, 20, 2500, 500, 40000, 1000, 17
+    ch, (av, bv, apos, bpos) = _synth(61, regend, nsnp, asize, bsize, planted_every=4, planted_len=10)
+    s_o, p_o = _css_oracle_scan(oracle, av, bv, apos, bpos, regend, wsize, wstep, mct, mcr, 0, 0, seed)
+    s_g, p_g, wr = fpt.css_scan(av, bv, ch["pos"], asize, bsize, regend, wsize, wstep, mct, mcr, mds=0, seed=seed)
+    np.testing.assert_allclose(s_g, s_o, rtol=CSS_RTOL, atol=1e-12)
+    assert np.array_equal(p_g, p_o)
+
+
+def test_css_dropin_matches_reference(fpt, ref_css):
+    """drop-in call vs the reference's serial `compute`, classical MDS (deterministic score column)"""
+    import fpt_b200.css_cython as serial
+    regend, wsize, wstep, nsnp, asize, bsize = 60000, 2500, 500, 1500, 20, 20
+    ch, (av, bv, apos, bpos) = _synth(71, regend, nsnp, asize, bsize)
+    n = regend // wstep
+    s_r, p_r = np.zeros(n), np.zeros(n)
+    with checkers.silence_stdout():
+        ref_css.compute(dptr(av), dptr(bv), iptr(apos), iptr(bpos), 0, regend, wsize, wstep, av.size, bv.size, 10, 50, 0, 0, dptr(s_r), dptr(p_r))
+    s_g, p_g = np.zeros(n), np.zeros(n)
+    serial.cluster_separation_scorer(av, bv, apos, bpos, 0, regend, wsize, wstep, av.size, bv.size, 10, 50, 0, 0, s_g, p_g)
+    np.testing.assert_allclose(s_g, s_r, rtol=CSS_RTOL, atol=1e-12)
+    assert np.array_equal(p_g != 0, p_r != 0)
+
+
+def test_css_significance_matches_reference_stream(fpt, ref_css, oracle):
+    """per window, explicit state: p equals the reference's significance_treshold run on fresh identity labels"""
+    asize, bsize, wsize, wstep, regend, nsnp = 12, 9, 5000, 5000, 40000, 900
+    m = asize + bsize
+    ch, (av, bv, apos, bpos) = _synth(81, regend, nsnp, asize, bsize)
+    n = regend // wstep
+    states = np.array([0x5EED0000 + 977 * i for i in range(n)], dtype=np.uint64)
+    s_g, p_g, wr, pr = fpt.css_scan(av, bv, ch["pos"], asize, bsize, regend, wsize, wstep, 5, 400, mds=0, states_perm=states, probes=True)
+    checked = 0
+    for w in range(n):
+        if not wr[w]:
+            continue
+        X = checkers.RefMatrix(m, 2, pr["X"][w])
+        dist = checkers.RefMatrix(m, m)
+        ref_css.calc_dist(X.pp, dist.pp, m)
+        tracks = np.arange(m, dtype=np.int32)
+        score = ref_css.css(dist.pp, iptr(tracks), iptr(tracks[asize:]), asize, bsize)
+        assert score == s_g[w]                       # same embedding -> bit-identical score arithmetic
+        st = checkers.state_to_ushort3(int(states[w]))
+        p_ref = ref_css.significance_treshold(dist.pp, iptr(tracks), asize, bsize, score, 5, 400, st)
+        assert p_ref == p_g[w]
+        checked += 1
+    assert checked >= 4
+
+
+def test_css_frequency_metric(fpt, oracle):
+    """drosophila = 1: two frequency tracks, m = 2 (compare_freq)"""
+    rng = np.random.default_rng(3)
+    nsnp, regend, wsize, wstep = 2000, 100000, 5000, 2500
+    pos = np.sort(rng.choice(regend, size=nsnp, replace=False)).astype(np.int32)
+    fa, fb = rng.random(nsnp), rng.random(nsnp)
+    s_o, p_o = _css_oracle_scan(oracle, fa, fb, pos, pos, regend, wsize, wstep, 5, 20, 0, 0, 1, dros=1)
+    s_g, p_g, wr = fpt.css_scan(fa, fb, pos, 1, 1, regend, wsize, wstep, 5, 20, drosophila=1, mds=0, seed=1)
+    ok = np.isfinite(s_o) & np.isfinite(s_g)
+    assert ok.sum() > 0
+    np.testing.assert_allclose(s_g[ok], s_o[ok], rtol=CSS_RTOL, atol=1e-12)
+
+
+def test_position_mismatch_is_an_error(fpt):
+    import fpt_b200.fisher_cython as serial
+    ch, (av, bv, apos, bpos) = _synth(91, 50000, 500, 4, 4)
+    bpos = bpos.copy()
+    bpos[40:44] += 1
+    with pytest.raises(fpt.FptError) as e:
+        serial.fisher_exact_tester(av, bv, apos, bpos, 0, 50000, 2500, 500, av.size, bv.size, 0.95, np.zeros(100), np.zeros(100))
+    assert e.value.code == -3
