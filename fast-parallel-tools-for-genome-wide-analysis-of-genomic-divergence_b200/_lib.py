@@ -46,6 +46,8 @@ SYMBOLS = {
     "fpt_get_seed": (C.c_uint64, []),
     "fpt_release": (None, []),
     "fpt_window_state": (C.c_uint64, [C.c_uint64, C.c_int64, _I]),
+    "fpt_profile_enable": (_I, [_I]),
+    "fpt_profile_summary": (_I, [C.c_char_p, C.c_size_t]),
     "fpt_fet_threadcompute": (_I, _DROPIN_FET),
     "fpt_fet_compute": (_I, _DROPIN_FET),
     "fpt_css_threadcompute": (_I, _DROPIN_CSS),

@@ -161,6 +161,63 @@ static int persistent_grid(DeviceCtx *c, K kernel, int block, size_t smem, long 
     return FPT_OK;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Optional per-kernel timing: when enabled, every launch made through this library is bracketed by a
+ * pair of CUDA events on the launching stream; fpt_profile_summary() synchronises and reports the
+ * summed device time per kernel. Used by bench.py for the roofline of the dominant kernel.
+ */
+struct ProfRec { const char *name; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_free;
+
+static cudaEvent_t prof_event() {
+    cudaEvent_t e;
+    if (!g_prof_free.empty()) { e = g_prof_free.back(); g_prof_free.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ProfScope {
+    const char *name; cudaStream_t st; cudaEvent_t a = nullptr;
+    ProfScope(const char *n, cudaStream_t s) : name(n), st(s) {
+        if (g_prof_on) { a = prof_event(); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (a) { cudaEvent_t b = prof_event(); cudaEventRecord(b, st); g_prof.push_back({ name, a, b }); }
+    }
+};
+
+extern "C" int fpt_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return FPT_OK;
+}
+
+extern "C" int fpt_profile_summary(char *buf, size_t buflen) {
+    struct Acc { const char *name; double ms; long n; };
+    std::vector<Acc> acc;
+    for (ProfRec &r : g_prof) {
+        cudaEventSynchronize(r.b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        bool found = false;
+        for (Acc &a : acc) if (!strcmp(a.name, r.name)) { a.ms += ms; a.n++; found = true; break; }
+        if (!found) acc.push_back({ r.name, (double)ms, 1 });
+        g_prof_free.push_back(r.a); g_prof_free.push_back(r.b);
+    }
+    g_prof.clear();
+    cudaGetLastError();
+    size_t off = 0;
+    if (buf && buflen) {
+        off += snprintf(buf + off, buflen - off, "{");
+        for (size_t i = 0; i < acc.size() && off < buflen; i++)
+            off += snprintf(buf + off, buflen - off, "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f}", i ? ", " : "", acc[i].name,
+                            acc[i].n, acc[i].ms);
+        if (off < buflen) snprintf(buf + off, buflen - off, "}");
+    }
+    return FPT_OK;
+}
+
 /* ================================================================================================ library state */
 extern "C" const char *fpt_last_error(void) { return g_err; }
 
@@ -224,7 +281,7 @@ static int dev_fet_count(const T *a, const T *b, int64_t nsnp, int asize, int bs
     if (tile < 0) return fail(FPT_ERR_ARG, "populations of %d+%d individuals exceed the shared-memory tile", asize, bsize);
     int grid;
     CHECK(persistent_grid(c, fpt_fet_count_kernel<T>, 256, smem, (nsnp + tile - 1) / tile, &grid));
-    fpt_fet_count_kernel<T><<<grid, 256, smem, st>>>(a, b, nsnp, asize, bsize, tile, (int4 *)tables);
+    { ProfScope ps_("fet_count", st); fpt_fet_count_kernel<T><<<grid, 256, smem, st>>>(a, b, nsnp, asize, bsize, tile, (int4 *)tables); }
     CU(cudaGetLastError());
     return FPT_OK;
 }
@@ -250,7 +307,7 @@ extern "C" int fpt_dev_fet_score(const int32_t *tables, int64_t n, int max_n, in
         CU(cudaMallocAsync((void **)&d_max, sizeof(int), st));
         CU(cudaMemsetAsync(d_max, 0, sizeof(int), st));
         int g = (int)std::min<long long>((n + 255) / 256, (long long)c->sms * 8);
-        fpt_fet_maxn_kernel<<<g, 256, 0, st>>>((const int4 *)tables, n, d_max);
+        { ProfScope ps_("fet_maxn", st); fpt_fet_maxn_kernel<<<g, 256, 0, st>>>((const int4 *)tables, n, d_max); }
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(&max_n, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -262,7 +319,7 @@ extern "C" int fpt_dev_fet_score(const int32_t *tables, int64_t n, int max_n, in
     size_t smem = FPT_BINOM_ENTRIES * sizeof(unsigned long long) + (lf_in_smem ? lf_bytes : 0);
     int grid;
     CHECK(persistent_grid(c, fpt_fet_score_kernel, 256, smem, (n + 255) / 256, &grid));
-    fpt_fet_score_kernel<<<grid, 256, smem, st>>>((const int4 *)tables, n, c->binom, c->lf, max_n, lf_in_smem, force_log, out);
+    { ProfScope ps_("fet_score", st); fpt_fet_score_kernel<<<grid, 256, smem, st>>>((const int4 *)tables, n, c->binom, c->lf, max_n, lf_in_smem, force_log, out); }
     CU(cudaGetLastError());
     return FPT_OK;
 }
@@ -284,8 +341,8 @@ extern "C" int fpt_dev_window_table(const int32_t *pos, int64_t nsnp, const fpt_
     CHECK(check_range(r, &nwin));
     if (nwin == 0) return FPT_OK;
     unsigned grid = (unsigned)((nwin + 255) / 256);
-    fpt_window_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pos, nsnp, r->window_begin, nwin, r->regend, r->wsize,
-                                                                   r->wstep, r->semantics, wleft, wright, max_npos);
+    { ProfScope ps_("window_table", (cudaStream_t)stream); fpt_window_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pos, nsnp, r->window_begin, nwin, r->regend, r->wsize,
+                                                                   r->wstep, r->semantics, wleft, wright, max_npos); }
     CU(cudaGetLastError());
     return FPT_OK;
 }
@@ -308,8 +365,8 @@ extern "C" int fpt_dev_fet_windows(const double *snp_scores, const int32_t *wlef
                     c->smem_optin / 8);
     int grid;
     CHECK(persistent_grid(c, fpt_fet_window_kernel, 128, smem, nwin, &grid));
-    fpt_fet_window_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(snp_scores, wleft, wright, r->window_begin, nwin, perc,
-                                                                    r->seed, states, npad, use_hist, scores, stddev, written);
+    { ProfScope ps_("fet_window", (cudaStream_t)stream); fpt_fet_window_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(snp_scores, wleft, wright, r->window_begin, nwin, perc,
+                                                                    r->seed, states, npad, use_hist, scores, stddev, written); }
     CU(cudaGetLastError());
     return FPT_OK;
 }
@@ -334,7 +391,7 @@ static int dev_css_pack(const T *a, const T *b, int64_t nsnp, int asize, int bsi
     long long nwords = (nsnp + 31) / 32;
     int grid;
     CHECK(persistent_grid(c, fpt_css_pack_kernel<T>, 256, smem, (nwords + wpt - 1) / wpt, &grid));
-    fpt_css_pack_kernel<T><<<grid, 256, smem, st>>>(a, b, nsnp, asize, bsize, (int)wpt, planes);
+    { ProfScope ps_("css_pack", st); fpt_css_pack_kernel<T><<<grid, 256, smem, st>>>(a, b, nsnp, asize, bsize, (int)wpt, planes); }
     CU(cudaGetLastError());
     return FPT_OK;
 }
@@ -354,7 +411,7 @@ extern "C" int fpt_dev_css_absdiff(const double *a, const double *b, int64_t nsn
     CHECK(get_ctx(&c));
     if (nsnp <= 0) return FPT_OK;
     int g = (int)std::min<long long>((nsnp + 255) / 256, (long long)c->sms * 8);
-    fpt_css_absdiff_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(a, b, nsnp, out);
+    { ProfScope ps_("css_absdiff", (cudaStream_t)stream); fpt_css_absdiff_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(a, b, nsnp, out); }
     CU(cudaGetLastError());
     return FPT_OK;
 }
@@ -432,9 +489,9 @@ static int launch_perm(DeviceCtx *c, const CssPlan &p, const CssWorkspace &ws, i
     int grid;
     CHECK(persistent_grid(c, fpt_css_perm_kernel<TrackT>, p.perm_threads, p.smem_perm, nwin, &grid));
     grid = std::min(grid, p.max_ctas);
-    fpt_css_perm_kernel<TrackT><<<grid, p.perm_threads, p.smem_perm, st>>>(
+    { ProfScope ps_("css_perm", st); fpt_css_perm_kernel<TrackT><<<grid, p.perm_threads, p.smem_perm, st>>>(
         ws.X, p.m, asize, bsize, wbase, nwin, status, treshold, runs, seed, states, p.dist_in_smem, p.tracks_in_smem,
-        (double *)ws.perm_scratch, p.perm_scratch_per_cta, scores, pv, hits, nperm);
+        (double *)ws.perm_scratch, p.perm_scratch_per_cta, scores, pv, hits, nperm); }
     CU(cudaGetLastError());
     return FPT_OK;
 }
@@ -466,20 +523,20 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
     if (mds == 0 || mds == 2) {
         CHECK(persistent_grid(c, fpt_css_mds_kernel, 128, p.smem_win, nwin, &grid));
         grid = std::min(grid, p.max_ctas);
-        fpt_css_mds_kernel<<<grid, 128, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, nwin, p.wch, p.mats_in_smem,
-                                                         ws.gscratch, ws.X, ws.evals, status);
+        { ProfScope ps_("css_mds", st); fpt_css_mds_kernel<<<grid, 128, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, nwin, p.wch, p.mats_in_smem,
+                                                         ws.gscratch, ws.X, ws.evals, status); }
         CU(cudaGetLastError());
     }
     if (mds == 1 || mds == 2) {
         const int nruns = mds == 1 ? 4 : 1;
         CHECK(persistent_grid(c, fpt_css_smacof_kernel, 128, p.smem_win, nwin * nruns, &grid));
         grid = std::min(grid, p.max_ctas);
-        fpt_css_smacof_kernel<<<grid, 128, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, r->window_begin, nwin, p.wch,
+        { ProfScope ps_("css_smacof", st); fpt_css_smacof_kernel<<<grid, 128, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, r->window_begin, nwin, p.wch,
                                                             p.mats_in_smem, ws.gscratch, nruns, mds == 1, r->seed, st_init,
-                                                            300, 0.000001, ws.X, ws.Xruns, ws.sigma, ws.iters, status);
+                                                            300, 0.000001, ws.X, ws.Xruns, ws.sigma, ws.iters, status); }
         CU(cudaGetLastError());
         int g2 = (int)std::min<long long>(nwin, (long long)c->sms * 16);
-        fpt_css_pick_kernel<<<g2, 64, 0, st>>>(ws.Xruns, ws.sigma, m, nruns, nwin, status, ws.X);
+        { ProfScope ps_("css_pick", st); fpt_css_pick_kernel<<<g2, 64, 0, st>>>(ws.Xruns, ws.sigma, m, nruns, nwin, status, ws.X); }
         CU(cudaGetLastError());
     }
     int *hits = probes ? probes->hits : nullptr, *nperm = probes ? probes->nperm : nullptr;

@@ -56,6 +56,11 @@ void fpt_release(void);                     /* free cached device/pinned buffers
 /* 48-bit LCG state of (seed, global window index, stream); stream 0 = bootstrap / label shuffles
    (nrand48 draws), 1 = SMACOF starts (drand48 draws). Pure host arithmetic. */
 uint64_t fpt_window_state(uint64_t seed, int64_t window, int stream);
+/* Per-kernel device timing. While enabled, every kernel this library launches is bracketed by CUDA events on
+   its stream; fpt_profile_summary() waits for them, writes a JSON object {"kernel": {"launches": n, "ms": t}, ...}
+   into buf and clears the record. Not thread-safe; meant for benchmarks. */
+int fpt_profile_enable(int on);
+int fpt_profile_summary(char *buf, size_t buflen);
 
 /* ------------------------------------------------------------------------------------------------
  * 1. drop-in entry points (host pointers, caller-owned, outputs pre-zeroed by the caller; only scored
