@@ -206,7 +206,9 @@ FPT_D void fpt_css_cmds(double *A, double *V, int m, double *X, double *evals3, 
         }
         off = fpt_block_sum(off, sc.red);
         dia = fpt_block_sum(dia, sc.red);
-        if (off <= 1e-300 || off <= 1e-32 * (dia + off)) break;
+        /* Jacobi converges quadratically and its rounding floor sits near 1e-29 (m^2/2 rotations each leaving
+           ~eps^2 behind), so the first sweep that lands below 1e-24 is already at that floor */
+        if (off <= 1e-300 || off <= 1e-24 * (dia + off)) break;
         for (int round = 0; round < n - 1; round++) {
             if ((int)threadIdx.x < half) {
                 const int t = threadIdx.x;
