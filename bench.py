@@ -477,11 +477,14 @@ def main():
     ap.add_argument("--skip-fet", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--small", action="store_true", help="tiny shapes: checks that the script runs, not a benchmark")
+    ap.add_argument("--chromosomes", type=int, default=None, help="profiling aid: fewer chromosomes than the 21 of the workload")
     args = ap.parse_args()
     if args.small:
         CSS.update(chromosomes=2, length=2_000_000, nsnp=20_000)
         FET.update(length=10_000_000, nsnp=100_000)
         FET_TABLES.update(n=200_000)
+    if args.chromosomes:
+        CSS.update(chromosomes=args.chromosomes)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -21,6 +21,7 @@
 
 #include "../../include/fpt_b200.h"
 #include "fpt_css.cuh"
+#include "fpt_css_eig.cuh"
 #include "fpt_fet.cuh"
 #include "fpt_rt.cuh"
 #include "fpt_tables.h"
@@ -419,7 +420,9 @@ extern "C" int fpt_dev_css_absdiff(const double *a, const double *b, int64_t nsn
 /* launch geometry of the per-window CSS kernels for a cohort of m individuals */
 struct CssPlan {
     int m, wch, mats_in_smem;
-    size_t smem_win;                 /* mds / smacof kernels */
+    size_t smem_win;                 /* CTA-per-window kernels (SMACOF, Jacobi fallback) */
+    int mds_warps;                   /* > 0: classical MDS runs one warp per window, this many warps per CTA */
+    size_t smem_mds_warp;
     int perm_threads, wide_tracks, dist_in_smem, tracks_in_smem;
     size_t smem_perm, perm_scratch_per_cta;
     int max_ctas;                    /* upper bound on persistent CTAs (sizes the global scratch) */
@@ -433,6 +436,9 @@ static CssPlan css_plan(const DeviceCtx *c, int m) {
     p.mats_in_smem = fpt_css_smem_bytes(m, p.wch, 1) <= budget;
     if (!p.mats_in_smem && fpt_css_smem_bytes(m, p.wch, 0) > budget) p.wch = 1;
     p.smem_win = fpt_css_smem_bytes(m, p.wch, p.mats_in_smem);
+    const size_t per_warp = fpt_eig_work_bytes(m, 4);
+    p.mds_warps = 4 * per_warp <= budget / 2 ? 4 : (per_warp <= budget ? 1 : 0);
+    p.smem_mds_warp = per_warp * (p.mds_warps > 0 ? p.mds_warps : 1);
     p.perm_threads = 256;
     p.wide_tracks = m > 256;
     const int tb = p.wide_tracks ? 2 : 1;
@@ -521,10 +527,16 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
 
     int grid;
     if (mds == 0 || mds == 2) {
-        CHECK(persistent_grid(c, fpt_css_mds_kernel, 128, p.smem_win, nwin, &grid));
-        grid = std::min(grid, p.max_ctas);
-        { ProfScope ps_("css_mds", st); fpt_css_mds_kernel<<<grid, 128, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, nwin, p.wch, p.mats_in_smem,
-                                                         ws.gscratch, ws.X, ws.evals, status); }
+        if (p.mds_warps > 0) {
+            const int block = 32 * p.mds_warps;
+            CHECK(persistent_grid(c, fpt_css_mds_warp_kernel, block, p.smem_mds_warp, (nwin + p.mds_warps - 1) / p.mds_warps, &grid));
+            { ProfScope ps_("css_mds", st); fpt_css_mds_warp_kernel<<<grid, block, p.smem_mds_warp, st>>>(planes, absdiff, m, wleft, wright, nwin, 4, ws.X, ws.evals, status); }
+        } else {                                           /* cohorts too large for a warp's shared-memory slice */
+            CHECK(persistent_grid(c, fpt_css_mds_kernel, 128, p.smem_win, nwin, &grid));
+            grid = std::min(grid, p.max_ctas);
+            { ProfScope ps_("css_mds", st); fpt_css_mds_kernel<<<grid, 128, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, nwin, p.wch, p.mats_in_smem,
+                                                             ws.gscratch, ws.X, ws.evals, status); }
+        }
         CU(cudaGetLastError());
     }
     if (mds == 1 || mds == 2) {

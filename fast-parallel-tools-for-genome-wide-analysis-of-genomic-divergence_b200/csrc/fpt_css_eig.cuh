@@ -1,0 +1,395 @@
+/*
+ * fpt_css_eig.cuh — classical MDS of one window by ONE WARP (reference: cmds, css/css.c:505-560, which
+ * calls GSL's dense symmetric eigensolver and keeps the two largest eigenpairs).
+ *
+ * The reference needs only the two largest eigenvalues BY VALUE and their vectors, so a full
+ * diagonalisation is two orders of magnitude more work than necessary. Per window this file does:
+ *
+ *   1. pairwise opposite-homozygote counts from the window's bit-plane slab, fill_averages,
+ *      double centring  B = -1/2 (S - r 1' - 1 r' + g),  S = D.D                     (O(m^2))
+ *   2. Householder reduction of B to tridiagonal T (LAPACK dsytd2 scheme, lower)       (4/3 m^3 flops)
+ *   3. the two (optionally three) largest eigenvalues of T by Sturm-count multisection, both searched
+ *      at once, 16 lanes each                                                          (O(m) per probe)
+ *   4. their eigenvectors by inverse iteration on T (tridiagonal LU with partial pivoting, lanes 0/1)
+ *   5. back-transformation through the stored reflectors, X = [v1 v2] diag(sqrt l1, sqrt l2)
+ *
+ * No __syncthreads anywhere: each warp of the CTA owns its own window and its own slice of shared
+ * memory. Rows are padded to an odd number of doubles so that "lane = row" accesses are conflict-free.
+ */
+#ifndef FPT_CSS_EIG_CUH
+#define FPT_CSS_EIG_CUH
+
+#include "fpt_rt.cuh"
+
+FPT_D double fpt_warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FPT_FULL_MASK, v, o);
+    return v;
+}
+FPT_D long long fpt_warp_sum_i64(long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FPT_FULL_MASK, v, o);
+    return v;
+}
+FPT_D double fpt_warp_max(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FPT_FULL_MASK, v, o));
+    return v;
+}
+FPT_D double fpt_warp_min(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FPT_FULL_MASK, v, o));
+    return v;
+}
+
+/* per-warp shared-memory work area */
+struct FptEigWork {
+    double *A;        /* m x ld, ld odd */
+    int ld;
+    double *d, *e;    /* tridiagonal: m diagonal, m-1 off-diagonal (e2 overwrites nothing: kept in tau2) */
+    double *tau;      /* m reflector scales */
+    double *pv, *wv;  /* m each: Householder work vectors */
+    double *y;        /* 2 x m eigenvectors */
+    double *lu;       /* 2 x 3 x m tridiagonal solver arrays */
+    unsigned *wbuf;   /* wch x 2 x m bit-plane words */
+    int wch;
+};
+
+FPT_HD int fpt_eig_ld(int m) { return m | 1; }
+
+FPT_HD size_t fpt_eig_work_bytes(int m, int wch) {
+    size_t doubles = (size_t)m * fpt_eig_ld(m) + (size_t)5 * m + (size_t)2 * m + (size_t)6 * m;
+    size_t bytes = doubles * 8 + (size_t)wch * 2 * m * 4;
+    return (bytes + 15) & ~(size_t)15;
+}
+
+FPT_D FptEigWork fpt_eig_carve(unsigned char *base, int m, int wch) {
+    FptEigWork w;
+    double *p = (double *)base;
+    w.ld = fpt_eig_ld(m);
+    w.A = p; p += (size_t)m * w.ld;
+    w.d = p; p += m;
+    w.e = p; p += m;
+    w.tau = p; p += m;
+    w.pv = p; p += m;
+    w.wv = p; p += m;
+    w.y = p; p += 2 * m;
+    w.lu = p; p += 6 * m;
+    w.wbuf = (unsigned *)p;
+    w.wch = wch;
+    return w;
+}
+
+/* ---- step 1a: D (full, mirrored, zero diagonal) from the bit-planes of SNPs [l, r); warp-level twin of fpt_css_counts */
+FPT_D void fpt_warp_counts(const unsigned *__restrict__ planes, int m, int l, int r, const FptEigWork &w) {
+    const int lane = threadIdx.x & 31, ld = w.ld;
+    const int w0 = l >> 5, w1 = (r - 1) >> 5, mm = m * m;
+    for (int e = lane; e < mm; e += 32) { const int i = e / m, j = e - i * m; w.A[i * ld + j] = 0.0; }
+    for (int wc = w0; wc <= w1; wc += w.wch) {
+        const int nw = min(w.wch, w1 - wc + 1);
+        __syncwarp();
+        for (int e = lane; e < nw * 2 * m; e += 32) {
+            const int ww = wc + e / (2 * m);
+            unsigned mask = 0xffffffffu;
+            if (ww == w0) mask &= 0xffffffffu << (l & 31);
+            if (ww == w1) mask &= 0xffffffffu >> (31 - ((r - 1) & 31));
+            w.wbuf[e] = planes[(size_t)wc * 2 * m + e] & mask;
+        }
+        __syncwarp();
+        for (int e = lane; e < mm; e += 32) {
+            const int i = e / m, j = e - i * m;
+            if (j < i) {
+                int cnt = 0;
+                for (int q = 0; q < nw; q++) {
+                    const unsigned *row = w.wbuf + (size_t)q * 2 * m;
+                    cnt += __popc(row[i] & row[m + j]) + __popc(row[m + i] & row[j]);
+                }
+                w.A[i * ld + j] += (double)cnt;
+            }
+        }
+    }
+    __syncwarp();
+    for (int e = lane; e < mm; e += 32) {
+        const int i = e / m, j = e - i * m;
+        if (j > i) w.A[i * ld + j] = w.A[j * ld + i];
+    }
+    __syncwarp();
+}
+
+/* ---- step 1b: fill_averages (css.c:337-366); returns 1 to keep the window */
+FPT_D int fpt_warp_fill(int m, const FptEigWork &w) {
+    const int lane = threadIdx.x & 31, ld = w.ld, mm = m * m;
+    long long blanks = 0;
+    double sum = 0.0;
+    for (int e = lane; e < mm; e += 32) {
+        const int i = e / m, j = e - i * m;
+        const double v = w.A[i * ld + j];
+        if (v < 0.00001) blanks++; else sum += v;
+    }
+    blanks = fpt_warp_sum_i64(blanks);
+    sum = fpt_warp_sum(sum);
+    if (blanks > (long long)(mm / 2)) return 0;
+    const double avg = __ddiv_rn(sum, (double)mm);
+    for (int e = lane; e < mm; e += 32) {
+        const int i = e / m, j = e - i * m;
+        if (w.A[i * ld + j] < 0.00001) w.A[i * ld + j] = avg;
+    }
+    __syncwarp();
+    return 1;
+}
+
+/* number of eigenvalues of the tridiagonal (d, e2 = e^2) below x: negative pivots of T - xI (LAPACK dstebz scheme) */
+FPT_D int fpt_sturm_count(const double *d, const double *e2, int n, double x, double pivmin) {
+    double q = d[0] - x;
+    int cnt = q < 0.0 ? 1 : 0;
+    for (int i = 1; i < n; i++) {
+        if (fabs(q) < pivmin) q = -pivmin;
+        q = d[i] - x - e2[i - 1] / q;
+        cnt += q < 0.0 ? 1 : 0;
+    }
+    return cnt;
+}
+
+/* ---- steps 1c-5. A holds the filled D on entry; X (2m doubles) and evals3 are written by the warp. */
+FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, int want_third) {
+    const int lane = threadIdx.x & 31, ld = w.ld, mm = m * m;
+    double *A = w.A;
+    if (m == 1) {
+        if (lane == 0) { X[0] = 0.0; X[1] = 0.0; if (evals3) { evals3[0] = 0.0; evals3[1] = 0.0; evals3[2] = 0.0; } }
+        __syncwarp();
+        return;
+    }
+    /* double centring */
+    for (int e = lane; e < mm; e += 32) { const int i = e / m, j = e - i * m; const double v = A[i * ld + j]; A[i * ld + j] = v * v; }
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) {
+        double s = 0.0;
+        for (int j = 0; j < m; j++) s += A[i * ld + j];
+        w.pv[i] = s / m;
+    }
+    __syncwarp();
+    double g = 0.0;
+    for (int i = 0; i < m; i++) g += w.pv[i];
+    g /= m;
+    for (int e = lane; e < mm; e += 32) {
+        const int i = e / m, j = e - i * m;
+        if (j <= i) A[i * ld + j] = -0.5 * (((A[i * ld + j] - w.pv[i]) - w.pv[j]) + g);
+    }
+    __syncwarp();
+    for (int e = lane; e < mm; e += 32) { const int i = e / m, j = e - i * m; if (j > i) A[i * ld + j] = A[j * ld + i]; }
+    __syncwarp();
+
+    /* Householder tridiagonalisation, lower form: H_k = I - tau v v', v(k+1) = 1, v(k+2:) stored in column k */
+    for (int k = 0; k + 2 < m; k++) {
+        const double x0 = A[(k + 1) * ld + k];
+        double s2 = 0.0;
+        for (int i = k + 2 + lane; i < m; i += 32) { const double x = A[i * ld + k]; s2 += x * x; }
+        s2 = fpt_warp_sum(s2);
+        if (lane == 0) w.d[k] = A[k * ld + k];
+        if (s2 == 0.0) {                                  /* column already tridiagonal: H = I */
+            if (lane == 0) { w.e[k] = x0; w.tau[k] = 0.0; }
+            __syncwarp();
+            continue;
+        }
+        const double nrm = sqrt(x0 * x0 + s2);
+        const double alpha = x0 >= 0.0 ? -nrm : nrm;
+        const double tau = (alpha - x0) / alpha;
+        const double scal = 1.0 / (x0 - alpha);
+        for (int i = k + 2 + lane; i < m; i += 32) A[i * ld + k] *= scal;
+        if (lane == 0) { A[(k + 1) * ld + k] = 1.0; w.e[k] = alpha; w.tau[k] = tau; }
+        __syncwarp();
+        /* p = tau * A22 v */
+        double pvdot = 0.0;
+        for (int i = k + 1 + lane; i < m; i += 32) {
+            const double *row = A + (size_t)i * ld;
+            double s = 0.0;
+            for (int j = k + 1; j < m; j++) s += row[j] * A[j * ld + k];
+            s *= tau;
+            w.pv[i] = s;
+            pvdot += s * A[i * ld + k];
+        }
+        pvdot = fpt_warp_sum(pvdot);
+        const double K = -0.5 * tau * pvdot;
+        for (int i = k + 1 + lane; i < m; i += 32) w.wv[i] = w.pv[i] + K * A[i * ld + k];
+        __syncwarp();
+        /* A22 -= v w' + w v' */
+        for (int i = k + 1 + lane; i < m; i += 32) {
+            double *row = A + (size_t)i * ld;
+            const double vi = row[k], wi = w.wv[i];
+            for (int j = k + 1; j < m; j++) row[j] -= vi * w.wv[j] + wi * A[j * ld + k];
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        w.d[m - 2] = A[(m - 2) * ld + (m - 2)];
+        w.e[m - 2] = A[(m - 1) * ld + (m - 2)];
+        w.d[m - 1] = A[(m - 1) * ld + (m - 1)];
+        if (m == 2) w.tau[0] = 0.0;
+    }
+    __syncwarp();
+
+    /* Gershgorin bounds, squared off-diagonals (into wv), pivot floor */
+    double glo = 1e300, ghi = -1e300, emax = 0.0;
+    for (int i = lane; i < m; i += 32) {
+        const double el = i > 0 ? fabs(w.e[i - 1]) : 0.0, er = i < m - 1 ? fabs(w.e[i]) : 0.0;
+        glo = fmin(glo, w.d[i] - el - er);
+        ghi = fmax(ghi, w.d[i] + el + er);
+        if (i < m - 1) { w.wv[i] = w.e[i] * w.e[i]; emax = fmax(emax, w.wv[i]); }
+    }
+    glo = fpt_warp_min(glo); ghi = fpt_warp_max(ghi); emax = fpt_warp_max(emax);
+    __syncwarp();
+    const double tnorm = fmax(fabs(glo), fabs(ghi));
+    const double pivmin = 2.2250738585072014e-308 * fmax(1.0, emax);
+    const double pad = 2.0 * tnorm * 2.220446049250313e-16 * m + 2.0 * pivmin;
+    glo -= pad; ghi += pad;
+
+    /* two largest eigenvalues at once: lanes 0-15 bracket index m-1, lanes 16-31 index m-2; 17-section */
+    const int half = lane >> 4, hl = lane & 15;
+    const int want = m - 1 - half;                         /* ascending index searched by this half-warp */
+    double lo = glo, hi = ghi;
+    for (int round = 0; round < 14; round++) {
+        const double x = lo + (hi - lo) * ((double)(hl + 1) / 17.0);
+        const int flag = fpt_sturm_count(w.d, w.wv, m, x, pivmin) >= want + 1;
+        const unsigned bal = (__ballot_sync(FPT_FULL_MASK, flag) >> (16 * half)) & 0xffffu;
+        int js = 16;                                       /* first probe already above the eigenvalue */
+        for (int b = 0; b < 16; b++) if ((bal >> b) & 1u) { js = b; break; }
+        const double xl = __shfl_sync(FPT_FULL_MASK, x, 16 * half + (js > 0 ? js - 1 : 0));
+        const double xh = __shfl_sync(FPT_FULL_MASK, x, 16 * half + (js < 16 ? js : 15));
+        if (js > 0) lo = xl;
+        if (js < 16) hi = xh;
+    }
+    const double lam_mine = 0.5 * (lo + hi);
+    const double lam1 = __shfl_sync(FPT_FULL_MASK, lam_mine, 0);
+    const double lam2 = __shfl_sync(FPT_FULL_MASK, lam_mine, 16);
+    double lam3 = 0.0;
+    if (want_third && m >= 3) {                            /* diagnostics only: 33-section, 7 rounds */
+        double l3 = glo, h3 = ghi;
+        for (int round = 0; round < 7; round++) {
+            const double x = l3 + (h3 - l3) * ((double)(lane + 1) / 33.0);
+            const int flag = fpt_sturm_count(w.d, w.wv, m, x, pivmin) >= m - 2;
+            const unsigned bal = __ballot_sync(FPT_FULL_MASK, flag);
+            int js = 32;
+            for (int b = 0; b < 32; b++) if ((bal >> b) & 1u) { js = b; break; }
+            const double xl = __shfl_sync(FPT_FULL_MASK, x, js > 0 ? js - 1 : 0);
+            const double xh = __shfl_sync(FPT_FULL_MASK, x, js < 32 ? js : 31);
+            if (js > 0) l3 = xl;
+            if (js < 32) h3 = xh;
+        }
+        lam3 = 0.5 * (l3 + h3);
+    }
+
+    /* eigenvectors of T by inverse iteration: lane c (0, 1) owns vector c and its solver arrays */
+    const double epsT = 2.220446049250313e-16 * fmax(tnorm, 1e-300);
+    for (int iter = 0; iter < 3; iter++) {
+        if (lane < 2) {
+            const int c = lane;
+            const double lam = c == 0 ? lam1 : lam2;
+            double *dd = w.lu + (size_t)c * 3 * m, *du = dd + m, *dl = du + m, *y = w.y + (size_t)c * m;
+            for (int i = 0; i < m; i++) {
+                dd[i] = w.d[i] - lam;
+                if (i < m - 1) { du[i] = w.e[i]; dl[i] = w.e[i]; }
+                if (iter == 0) {
+                    const unsigned hsh = ((unsigned)i * 2654435761u + (unsigned)c * 40503u + 12345u) >> 8;
+                    y[i] = ((double)(hsh & 0xffffu) / 65536.0) - 0.5 + (c == 0 ? 1.0 : 0.0);
+                }
+            }
+            /* LAPACK dgtsv elimination with partial pivoting; dl becomes the second super-diagonal */
+            for (int i = 0; i < m - 1; i++) {
+                if (fabs(dd[i]) >= fabs(dl[i])) {
+                    if (dd[i] == 0.0) dd[i] = epsT;
+                    const double f = dl[i] / dd[i];
+                    dd[i + 1] -= f * du[i];
+                    y[i + 1] -= f * y[i];
+                    dl[i] = 0.0;
+                } else {
+                    const double f = dd[i] / dl[i];
+                    dd[i] = dl[i];
+                    double t = dd[i + 1];
+                    dd[i + 1] = du[i] - f * t;
+                    if (i < m - 2) { dl[i] = du[i + 1]; du[i + 1] = -f * dl[i]; } else dl[i] = 0.0;
+                    du[i] = t;
+                    t = y[i]; y[i] = y[i + 1]; y[i + 1] = t - f * y[i + 1];
+                }
+            }
+            if (dd[m - 1] == 0.0) dd[m - 1] = epsT;
+            y[m - 1] /= dd[m - 1];
+            if (m > 1) {
+                if (dd[m - 2] == 0.0) dd[m - 2] = epsT;
+                y[m - 2] = (y[m - 2] - du[m - 2] * y[m - 1]) / dd[m - 2];
+            }
+            for (int i = m - 3; i >= 0; i--) {
+                if (dd[i] == 0.0) dd[i] = epsT;
+                y[i] = (y[i] - du[i] * y[i + 1] - dl[i] * y[i + 2]) / dd[i];
+            }
+            double mx = 0.0;
+            for (int i = 0; i < m; i++) mx = fmax(mx, fabs(y[i]));
+            if (!(mx > 0.0) || !(mx < 1e300)) {            /* overflow / breakdown: restart from a unit vector */
+                for (int i = 0; i < m; i++) y[i] = i == c ? 1.0 : 0.0;
+                mx = 1.0;
+            }
+            double nn = 0.0;
+            for (int i = 0; i < m; i++) { y[i] /= mx; nn += y[i] * y[i]; }
+            nn = 1.0 / sqrt(nn);
+            for (int i = 0; i < m; i++) y[i] *= nn;
+        }
+        __syncwarp();
+        if (lane == 1) {                                   /* keep the second vector orthogonal to the first */
+            double *y0 = w.y, *y1 = w.y + m;
+            double dot = 0.0;
+            for (int i = 0; i < m; i++) dot += y0[i] * y1[i];
+            double nn = 0.0;
+            for (int i = 0; i < m; i++) { y1[i] -= dot * y0[i]; nn += y1[i] * y1[i]; }
+            if (nn > 0.0) { nn = 1.0 / sqrt(nn); for (int i = 0; i < m; i++) y1[i] *= nn; }
+        }
+        __syncwarp();
+    }
+
+    /* back-transform: z = H_0 H_1 ... H_{m-3} y, applied last reflector first */
+    for (int k = m - 3; k >= 0; k--) {
+        const double tau = w.tau[k];
+        if (tau == 0.0) continue;
+        double s0 = 0.0, s1 = 0.0;
+        for (int i = k + 1 + lane; i < m; i += 32) {
+            const double v = A[i * ld + k];
+            s0 += v * w.y[i]; s1 += v * w.y[m + i];
+        }
+        s0 = tau * fpt_warp_sum(s0); s1 = tau * fpt_warp_sum(s1);
+        for (int i = k + 1 + lane; i < m; i += 32) {
+            const double v = A[i * ld + k];
+            w.y[i] -= s0 * v; w.y[m + i] -= s1 * v;
+        }
+        __syncwarp();
+    }
+    const double r1 = sqrt(lam1), r2 = sqrt(lam2);         /* negative eigenvalue -> NaN, as in css.c:558 */
+    for (int j = lane; j < m; j += 32) { X[2 * j] = w.y[j] * r1; X[2 * j + 1] = w.y[m + j] * r2; }
+    if (lane == 0 && evals3) { evals3[0] = lam1; evals3[1] = lam2; evals3[2] = lam3; }
+    __syncwarp();
+}
+
+/* mds 0 and the first half of mds 2: one WARP per window; warps of a CTA work on different windows.
+   Dynamic shared memory: (blockDim.x/32) work areas of fpt_eig_work_bytes(m, wch). */
+__global__ void __launch_bounds__(128)
+fpt_css_mds_warp_kernel(const unsigned *__restrict__ planes, const double *__restrict__ absdiff, int m,
+                        const int *__restrict__ wleft, const int *__restrict__ wright, long long nwin, int wch,
+                        double *__restrict__ Xout, double *__restrict__ evals_out, unsigned char *__restrict__ status) {
+    FPT_DYN_SMEM(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const FptEigWork w = fpt_eig_carve(smem + (size_t)warp * fpt_eig_work_bytes(m, wch), m, wch);
+    for (long long win = (long long)blockIdx.x * nwarp + warp; win < nwin; win += (long long)gridDim.x * nwarp) {
+        const int l = wleft[win], r = wright[win];
+        if (r <= l) { if (lane == 0) status[win] = 0; continue; }
+        if (absdiff) {
+            if (lane == 0) {                               /* compare_freq, css.c:245-264 */
+                double s = 0.0;
+                for (int i = r; i-- > l;) s = __dadd_rn(s, absdiff[i]);
+                s = __ddiv_rn(s, (double)(r - l));
+                w.A[0] = 0.0; w.A[1] = s; w.A[w.ld] = s; w.A[w.ld + 1] = 0.0;
+            }
+            __syncwarp();
+        } else {
+            fpt_warp_counts(planes, m, l, r, w);
+        }
+        if (!fpt_warp_fill(m, w)) { if (lane == 0) status[win] = 1; __syncwarp(); continue; }
+        fpt_warp_cmds(m, w, Xout + (size_t)win * 2 * m, evals_out ? evals_out + 3 * win : 0, evals_out != 0);
+        if (lane == 0) status[win] = 2;
+        __syncwarp();
+    }
+}
+
+#endif

@@ -10,6 +10,7 @@ FPT_EMU_DEFINE_GLOBALS
 #include "fpt_rt.cuh"
 #include "fpt_fet.cuh"
 #include "fpt_css.cuh"
+#include "fpt_css_eig.cuh"
 #include "fpt_tables.h"
 
 template <class F>
@@ -96,6 +97,14 @@ void emu_css_mds(const unsigned *planes, const double *absdiff, int m, const int
     double *gp = mats_in_smem ? 0 : gs.data();
     run_grid(grid, 128, smem, [=]() {
         fpt_css_mds_kernel(planes, absdiff, m, wleft, wright, nwin, wch, mats_in_smem, gp, X, evals, status);
+    });
+}
+
+void emu_css_mds_warp(const unsigned *planes, const double *absdiff, int m, const int *wleft, const int *wright,
+                      long long nwin, int wch, int warps, int grid, double *X, double *evals, unsigned char *status) {
+    size_t smem = fpt_eig_work_bytes(m, wch) * warps;
+    run_grid(grid, 32 * warps, smem, [=]() {
+        fpt_css_mds_warp_kernel(planes, absdiff, m, wleft, wright, nwin, wch, X, evals, status);
     });
 }
 
