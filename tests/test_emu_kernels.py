@@ -1,0 +1,255 @@
+"""The product's CUDA kernels (csrc/fpt_*.cuh) executed on the CPU through tests/emu/cuda_emu.h — one pthread per
+CUDA thread, real barriers, emulated warp collectives — and compared with the oracle. This keeps kernel LOGIC
+(indexing, barriers, scans, skip-ahead streams, rejection repair) under test where no GPU exists; the same source
+is what nvcc compiles for sm_100a. Sizes are tiny because every __syncthreads is a pthread barrier."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from checkers import dptr, iptr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CODES = np.array([3.0, -3.0, 0.0, -10000.0])
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run([os.path.join(HERE, "emu", "build.sh")], check=True, capture_output=True)
+    return C.CDLL(os.path.join(HERE, "emu", "libfpt_emu.so"))
+
+
+def vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def ll(v):
+    return C.c_longlong(int(v))
+
+
+def test_skip_ahead_matches_stepping(emu, oracle):
+    emu.emu_lcg_skip.restype = C.c_uint64
+    emu.emu_lcg_skip.argtypes = [C.c_uint64, C.c_uint64]
+    emu.emu_window_state.restype = C.c_uint64
+    emu.emu_window_state.argtypes = [C.c_uint64, C.c_longlong, C.c_int]
+    for seed, w, stream in ((1, 0, 0), (20261018, 123456, 1), (2 ** 64 - 1, 2 ** 31, 0)):
+        assert emu.emu_window_state(seed, w, stream) == oracle.fpt_oracle_window_state(seed, w, stream)
+    s = C.c_uint64(0x1234ABCD5678)
+    for n in (0, 1, 2, 39, 1000, 12345):
+        t = C.c_uint64(0x1234ABCD5678)
+        for _ in range(n):
+            oracle.fpt_oracle_nrand48(C.byref(t))
+        assert emu.emu_lcg_skip(s.value, n) == t.value
+
+
+def test_fet_count_and_score_kernels(emu, oracle):
+    rng = np.random.default_rng(1)
+    asize, bsize, S = 20, 17, 333
+    av, bv = rng.choice(CODES, S * asize, p=[.45, .3, .23, .02]), rng.choice(CODES, S * bsize, p=[.3, .45, .23, .02])
+    tab = np.zeros((S, 4), dtype=np.int32)
+    emu.emu_fet_count_f64(dptr(av), dptr(bv), ll(S), asize, bsize, 64, 3, iptr(tab))
+    tab_o, sc_o = np.zeros((S, 4), dtype=np.int32), np.zeros(S)
+    oracle.fpt_oracle_fet_per_snp(dptr(av), dptr(bv), S, asize, bsize, iptr(tab_o), dptr(sc_o))
+    assert np.array_equal(tab, tab_o)
+    a8 = np.where(av == -10000, -128, av).astype(np.int8)
+    b8 = np.where(bv == -10000, -128, bv).astype(np.int8)
+    tab8 = np.zeros((S, 4), dtype=np.int32)
+    emu.emu_fet_count_i8(vp(a8), vp(b8), ll(S), asize, bsize, 64, 3, iptr(tab8))
+    assert np.array_equal(tab8, tab_o)
+    sc = np.zeros(S)
+    emu.emu_fet_score(iptr(tab), ll(S), asize + bsize, 1, 0, 2, dptr(sc))
+    assert np.array_equal(sc, sc_o)                  # same libm on the host: bit-identical
+    # log mode, coverage up to 500, log-factorials read from "global" memory
+    n1, n2 = rng.integers(20, 501, 500), rng.integers(20, 501, 500)
+    f = np.clip(rng.beta(.5, .5, 500), .02, .98)
+    a, c = rng.binomial(n1, f), rng.binomial(n2, np.clip(f + rng.normal(0, .1, 500), .01, .99))
+    T = np.stack([a, n1 - a, c, n2 - c], 1).astype(np.int32).copy()
+    so, se = np.zeros(500), np.zeros(500)
+    oracle.fpt_oracle_fet_tables(iptr(T), 500, dptr(so))
+    assert emu.emu_fet_maxn(iptr(T), ll(500)) == T.sum(1).max()
+    emu.emu_fet_score(iptr(T), ll(500), int(T.sum(1).max()), 0, 0, 2, dptr(se))
+    assert np.array_equal(se, so)
+
+
+@pytest.mark.parametrize("threaded", [0, 1])
+def test_window_table_kernel(emu, oracle, threaded):
+    rng = np.random.default_rng(2)
+    for regend, wsize, wstep, S in ((60000, 2500, 500, 400), (51000, 1000, 1000, 300), (33333, 700, 300, 300), (20000, 2500, 500, 100)):
+        pos = np.sort(rng.choice(regend, size=S, replace=False)).astype(np.int32)
+        nwin = regend // wstep
+        for wbase in (0, 7):
+            n = nwin - wbase
+            wl, wr = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+            emu.emu_window_table(iptr(pos), ll(S), ll(wbase), ll(n), regend, wsize, wstep, threaded, iptr(wl), iptr(wr))
+            for j in range(n):
+                w = wbase + j
+                l, r = C.c_int64(), C.c_int64()
+                oracle.fpt_oracle_window_bounds(iptr(pos), S, w, wsize, wstep, C.byref(l), C.byref(r))
+                if oracle.fpt_oracle_window_scheduled(w, regend, wsize, wstep, threaded):
+                    assert (wl[j], wr[j]) == (l.value, r.value)
+                else:
+                    assert wl[j] == wr[j]
+
+
+@pytest.mark.parametrize("use_hist", [1, 0])
+def test_fet_window_kernel(emu, oracle, use_hist):
+    rng = np.random.default_rng(3)
+    asize = bsize = 10
+    regend, wsize, wstep, S = 30000, 2500, 500, 260
+    pos = np.sort(rng.choice(regend, size=S, replace=False)).astype(np.int32)
+    av, bv = rng.choice(CODES, S * asize, p=[.45, .3, .23, .02]), rng.choice(CODES, S * bsize, p=[.3, .45, .23, .02])
+    apos, bpos = np.repeat(pos, asize).astype(np.int32), np.repeat(pos, bsize).astype(np.int32)
+    n = regend // wstep
+    s_o, d_o = np.zeros(n), np.zeros(n)
+    oracle.fpt_oracle_fet_scan(dptr(av), dptr(bv), iptr(apos), iptr(bpos), 0, regend, wsize, wstep, av.size, bv.size, 0.95,
+                               dptr(s_o), dptr(d_o), 0, 777)
+    snp = np.zeros(S)
+    oracle.fpt_oracle_fet_per_snp(dptr(av), dptr(bv), S, asize, bsize, None, dptr(snp))
+    wl, wr = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    mx = emu.emu_window_table(iptr(pos), ll(S), ll(0), ll(n), regend, wsize, wstep, 0, iptr(wl), iptr(wr))
+    s_e, d_e, fl = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.uint8)
+    emu.emu_fet_window(dptr(snp), iptr(wl), iptr(wr), ll(0), ll(n), C.c_double(0.95), C.c_uint64(777), None, int(mx), use_hist, 3,
+                       dptr(s_e), dptr(d_e), vp(fl))
+    assert np.array_equal(s_e, s_o) and np.array_equal(d_e, d_o)
+    assert np.array_equal(fl == 1, (wr - wl) > 0)
+
+
+def _css_input(seed, asize, bsize, S, L):
+    rng = np.random.default_rng(seed)
+    pos = np.sort(rng.choice(L, size=S, replace=False)).astype(np.int32)
+    f = np.clip(rng.beta(.5, .5, S), .02, .98)
+    fb = np.where((np.arange(S) // 40) % 3 == 0, 1 - f, f)
+    enc = np.array([3., 0., -3.])
+    av, bv = enc[rng.binomial(2, f[:, None], size=(S, asize))], enc[rng.binomial(2, fb[:, None], size=(S, bsize))]
+    av[rng.random(av.shape) < .02] = -10000
+    bv[rng.random(bv.shape) < .02] = -10000
+    return pos, av.ravel().copy(), bv.ravel().copy()
+
+
+def _pack(emu, av, bv, S, asize, bsize):
+    m = asize + bsize
+    planes = np.zeros(((S + 31) // 32) * 2 * m, dtype=np.uint32)
+    emu.emu_css_pack_f64(dptr(av), dptr(bv), ll(S), asize, bsize, 2, 3, vp(planes))
+    return planes
+
+
+def test_css_pack_kernel(emu):
+    asize, bsize, S = 5, 6, 100
+    pos, av, bv = _css_input(5, asize, bsize, S, 5000)
+    m = asize + bsize
+    P = _pack(emu, av, bv, S, asize, bsize).reshape(-1, 2, m)
+    G = np.concatenate([av.reshape(S, asize), bv.reshape(S, bsize)], 1)
+    for k in range(S):
+        w, b = divmod(k, 32)
+        assert np.array_equal((P[w, 0] >> b) & 1, (G[k] == 3).astype(np.uint32))
+        assert np.array_equal((P[w, 1] >> b) & 1, (G[k] == -3).astype(np.uint32))
+    a8 = np.where(av == -10000, -128, av).astype(np.int8)
+    b8 = np.where(bv == -10000, -128, bv).astype(np.int8)
+    P8 = np.zeros_like(P.reshape(-1))
+    emu.emu_css_pack_i8(vp(a8), vp(b8), ll(S), asize, bsize, 2, 3, vp(P8))
+    assert np.array_equal(P8, P.reshape(-1))
+
+
+@pytest.mark.parametrize("kernel", ["warp", "cta", "cta_global"])
+def test_css_mds_kernels(emu, oracle, kernel):
+    asize, bsize, S, L, wsize, wstep = 6, 5, 220, 20000, 2500, 500
+    m = asize + bsize
+    pos, av, bv = _css_input(6, asize, bsize, S, L)
+    planes = _pack(emu, av, bv, S, asize, bsize)
+    n = L // wstep
+    wl, wr = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    emu.emu_window_table(iptr(pos), ll(S), ll(0), ll(n), L, wsize, wstep, 0, iptr(wl), iptr(wr))
+    X, ev, st = np.zeros((n, m, 2)), np.zeros((n, 3)), np.zeros(n, dtype=np.uint8)
+    if kernel == "warp":
+        emu.emu_css_mds_warp(vp(planes), None, m, iptr(wl), iptr(wr), ll(n), 4, 2, 3, dptr(X), dptr(ev), vp(st))
+    else:
+        emu.emu_css_mds(vp(planes), None, m, iptr(wl), iptr(wr), ll(n), 4, 1 if kernel == "cta" else 0, 3, dptr(X), dptr(ev), vp(st))
+    scored = 0
+    for w in range(n):
+        l, r = int(wl[w]), int(wr[w])
+        if r <= l:
+            assert st[w] == 0
+            continue
+        D = np.zeros((m, m))
+        oracle.fpt_oracle_compare_all(dptr(av[l * asize:r * asize].copy()), dptr(bv[l * bsize:r * bsize].copy()), asize, bsize, r - l, dptr(D))
+        keep = oracle.fpt_oracle_fill_averages(dptr(D), m)
+        assert st[w] == (2 if keep else 1)
+        if not keep:
+            continue
+        Xo, evo = np.zeros((m, 2)), np.zeros(3)
+        oracle.fpt_oracle_cmds(dptr(D), m, dptr(Xo), dptr(evo))
+        assert np.allclose(ev[w, :2], evo[:2], rtol=1e-10, atol=1e-10 * abs(evo[0]))
+        do, dg = np.zeros((m, m)), np.zeros((m, m))
+        oracle.fpt_oracle_calc_dist(dptr(Xo), m, dptr(do))
+        oracle.fpt_oracle_calc_dist(dptr(X[w].copy()), m, dptr(dg))
+        if np.isfinite(do).all() and np.isfinite(dg).all() and evo[1] - evo[2] > 1e-8 * evo[0]:
+            assert np.allclose(do, dg, rtol=1e-9, atol=1e-10 * do.max())
+            scored += 1
+    assert scored >= 10
+
+
+@pytest.mark.parametrize("mds", [1, 2])
+def test_css_smacof_and_perm_kernels(emu, oracle, mds):
+    asize, bsize, S, L, wsize, wstep = 4, 4, 90, 6000, 2500, 500
+    m = asize + bsize
+    pos, av, bv = _css_input(7, asize, bsize, S, L)
+    apos, bpos = np.repeat(pos, asize).astype(np.int32), np.repeat(pos, bsize).astype(np.int32)
+    planes = _pack(emu, av, bv, S, asize, bsize)
+    n = L // wstep
+    wl, wr = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    emu.emu_window_table(iptr(pos), ll(S), ll(0), ll(n), L, wsize, wstep, 0, iptr(wl), iptr(wr))
+    X, ev, st = np.zeros((n, m, 2)), np.zeros((n, 3)), np.zeros(n, dtype=np.uint8)
+    seed = 99
+    if mds == 2:
+        emu.emu_css_mds_warp(vp(planes), None, m, iptr(wl), iptr(wr), ll(n), 4, 2, 2, dptr(X), dptr(ev), vp(st))
+        Xr, sg, it = np.zeros((n, 1, m, 2)), np.zeros(n), np.zeros(n, dtype=np.int32)
+        emu.emu_css_smacof(vp(planes), None, m, iptr(wl), iptr(wr), ll(0), ll(n), 4, 1, 3, 1, 0, C.c_uint64(seed), None, 300,
+                           C.c_double(1e-6), dptr(X), dptr(Xr), dptr(sg), iptr(it), vp(st))
+        X = Xr[:, 0].copy()
+    else:
+        Xr, sg, it = np.zeros((n, 4, m, 2)), np.zeros(n * 4), np.zeros(n * 4, dtype=np.int32)
+        emu.emu_css_smacof(vp(planes), None, m, iptr(wl), iptr(wr), ll(0), ll(n), 4, 1, 3, 4, 1, C.c_uint64(seed), None, 300,
+                           C.c_double(1e-6), None, dptr(Xr), dptr(sg), iptr(it), vp(st))
+        emu.emu_css_pick(dptr(Xr), dptr(sg), m, 4, ll(n), vp(st), dptr(X))
+    sc, p, hits, nn = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    emu.emu_css_perm(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), 7, 150, C.c_uint64(seed), None, 1, 1, 64, 2, 0, dptr(sc), dptr(p),
+                     iptr(hits), iptr(nn))
+    so, po = np.zeros(n), np.zeros(n)
+    oracle.fpt_oracle_css_scan(dptr(av), dptr(bv), iptr(apos), iptr(bpos), 0, L, wsize, wstep, av.size, bv.size, 7, 150, 0, mds,
+                               dptr(so), dptr(po), 0, seed)
+    scored = st == 2
+    assert np.array_equal(scored, po != 0) and scored.sum() >= 5
+    ok = scored & np.isfinite(so)
+    np.testing.assert_allclose(sc[ok], so[ok], rtol=1e-6, atol=1e-9)
+    if mds == 1:
+        assert np.array_equal(sc[ok], so[ok])        # random starts: the whole chain is the reference's arithmetic order
+        assert np.array_equal(p[ok], po[ok])
+
+
+def test_css_perm_kernel_chunks_early_stop_and_scratch_paths(emu, oracle):
+    """several chunks per window (runs > threads), early stop inside a chunk, 16-bit labels, global-memory scratch"""
+    rng = np.random.default_rng(8)
+    asize, bsize, n = 5, 6, 6
+    m = asize + bsize
+    X = rng.normal(size=(n, m, 2))
+    X[:, :asize, 0] += np.linspace(0.0, 1.5, n)[:, None]          # windows from "no separation" to "clear separation"
+    st = np.full(n, 2, dtype=np.uint8)
+    states = (np.arange(n, dtype=np.uint64) * 7919 + 13)
+    for tres, runs in ((5, 200), (1000, 100), (1, 70)):
+        want_p, want_h, want_n = [], [], []
+        for w in range(n):
+            dist = np.zeros((m, m))
+            oracle.fpt_oracle_calc_dist(dptr(X[w].copy()), m, dptr(dist))
+            tr = np.arange(m, dtype=np.int32)
+            score = oracle.fpt_oracle_css(dptr(dist), m, iptr(tr), iptr(tr[asize:]), asize, bsize)
+            s64, h, nn = C.c_uint64(int(states[w])), C.c_int(), C.c_int()
+            want_p.append(oracle.fpt_oracle_significance(dptr(dist), m, iptr(tr), asize, bsize, score, tres, runs, C.byref(s64), C.byref(h), C.byref(nn)))
+            want_h.append(h.value)
+            want_n.append(nn.value)
+        for dist_smem, tracks_smem, wide in ((1, 1, 0), (0, 0, 1), (1, 0, 0)):
+            sc, p, hits, nn = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+            emu.emu_css_perm(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), tres, runs, C.c_uint64(0), vp(states), dist_smem, tracks_smem,
+                             32, 2, wide, dptr(sc), dptr(p), iptr(hits), iptr(nn))
+            assert list(hits) == want_h and list(nn) == want_n and list(p) == want_p

@@ -1,0 +1,120 @@
+"""Multi-rank host logic on the CPU: contiguous window ranges + halo SNPs per rank, world_size-2 gloo gather, and
+the invariant that the gathered result does not depend on the number of ranks (random streams are keyed by the global
+window index). The compute function is injected: here the oracle stands in for the CUDA path, which the GPU suite
+exercises with the same sharding code."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_fet(a, b, pos, asize, bsize, regend, wsize, wstep, perc, semantics=0, window_begin=None, window_end=None, seed=None):
+    import checkers
+    from checkers import dptr, iptr
+    o = checkers.load_oracle()
+    a, b = np.ascontiguousarray(a, dtype=np.float64), np.ascontiguousarray(b, dtype=np.float64)
+    apos, bpos = np.repeat(pos, asize).astype(np.int32), np.repeat(pos, bsize).astype(np.int32)
+    n = regend // wstep
+    s, d = np.zeros(n), np.zeros(n)
+    if pos.size:
+        assert o.fpt_oracle_fet_scan(dptr(a), dptr(b), iptr(apos), iptr(bpos), 0, regend, wsize, wstep, a.size, b.size, perc,
+                                     dptr(s), dptr(d), semantics, seed) == 0
+    return s[window_begin:window_end].copy(), d[window_begin:window_end].copy(), None
+
+
+def _oracle_css(a, b, pos, asize, bsize, regend, wsize, wstep, treshold, runs, drosophila=0, mds=0, semantics=0, window_begin=None,
+                window_end=None, seed=None):
+    import checkers
+    from checkers import dptr, iptr
+    o = checkers.load_oracle()
+    a, b = np.ascontiguousarray(a, dtype=np.float64), np.ascontiguousarray(b, dtype=np.float64)
+    apos, bpos = np.repeat(pos, asize).astype(np.int32), np.repeat(pos, bsize).astype(np.int32)
+    n = regend // wstep
+    s, p = np.zeros(n), np.zeros(n)
+    if pos.size:
+        assert o.fpt_oracle_css_scan(dptr(a), dptr(b), iptr(apos), iptr(bpos), 0, regend, wsize, wstep, a.size, b.size, treshold, runs,
+                                     drosophila, mds, dptr(s), dptr(p), semantics, seed) == 0
+    return s[window_begin:window_end].copy(), p[window_begin:window_end].copy(), None
+
+
+def _data():
+    import fpt_b200.synth as synth
+    ch = synth.chromosome(77, 80000, 1600, 6, 5)
+    av, bv, _, _ = synth.reference_layout(ch)
+    return ch, av, bv
+
+
+def test_partition_and_halo():
+    from fpt_b200.sharding import partition_windows, snp_slice
+    for nwin, world in ((160, 1), (160, 2), (161, 4), (7, 8), (0, 3)):
+        r = partition_windows(nwin, world)
+        assert len(r) == world and r[0][0] == 0 and r[-1][1] == nwin
+        assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+        assert max(e - b for b, e in r) - min(e - b for b, e in r) <= 1
+    pos = np.array([0, 499, 500, 2999, 3000, 3001, 9000], dtype=np.int32)
+    assert snp_slice(pos, 0, 1, 2500, 500) == (0, 3)              # window 0 = [0, 2500]
+    assert snp_slice(pos, 1, 2, 2500, 500) == (2, 5)              # window 1 = [500, 3000], right edge inclusive
+    assert snp_slice(pos, 3, 3, 2500, 500) == (0, 0)
+
+
+def test_single_process_sharding_is_rank_count_invariant():
+    from fpt_b200.sharding import css_scan_sharded, fet_scan_sharded, partition_windows
+    ch, av, bv = _data()
+    regend, wsize, wstep = 80000, 2500, 500
+    full_s, full_d = fet_scan_sharded(av, bv, ch["pos"], 6, 5, regend, wsize, wstep, 0.95, 0, 1, seed=5, compute=_oracle_fet)
+    for world in (2, 3):
+        ranges = partition_windows(regend // wstep, world)
+        s_cat, d_cat = [], []
+        for rank in range(world):          # emulate the ranks one after the other (no process group: gather is the identity)
+            from fpt_b200 import sharding
+            wb, we = ranges[rank]
+            lo, hi = sharding.snp_slice(ch["pos"], wb, we, wsize, wstep)
+            s, d, _ = _oracle_fet(av[lo * 6:hi * 6], bv[lo * 5:hi * 5], ch["pos"][lo:hi], 6, 5, regend, wsize, wstep, 0.95,
+                                  window_begin=wb, window_end=we, seed=5)
+            s_cat.append(s)
+            d_cat.append(d)
+        assert np.array_equal(np.concatenate(s_cat), full_s) and np.array_equal(np.concatenate(d_cat), full_d)
+    cs, cp = css_scan_sharded(av, bv, ch["pos"], 6, 5, regend, wsize, wstep, 5, 40, 0, 1, seed=5, compute=_oracle_css)
+    assert (cp != 0).sum() > 50 and cs.size == regend // wstep
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from fpt_b200.sharding import css_scan_sharded, fet_scan_sharded
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        ch, av, bv = _data()
+        s, d = fet_scan_sharded(av, bv, ch["pos"], 6, 5, 80000, 2500, 500, 0.95, rank, world, seed=5, compute=_oracle_fet)
+        cs, cp = css_scan_sharded(av, bv, ch["pos"], 6, 5, 80000, 2500, 500, 5, 40, rank, world, seed=5, compute=_oracle_css)
+        q.put((rank, s, d, cs, cp))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_gather_matches_single_rank():
+    import torch.multiprocessing as mp
+    from fpt_b200.sharding import css_scan_sharded, fet_scan_sharded
+    ch, av, bv = _data()
+    s1, d1 = fet_scan_sharded(av, bv, ch["pos"], 6, 5, 80000, 2500, 500, 0.95, 0, 1, seed=5, compute=_oracle_fet)
+    c1, p1 = css_scan_sharded(av, bv, ch["pos"], 6, 5, 80000, 2500, 500, 5, 40, 0, 1, seed=5, compute=_oracle_css)
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, s, d, cs, cp in got:            # every rank ends up with the full, identical result
+        assert np.array_equal(s, s1) and np.array_equal(d, d1)
+        assert np.array_equal(cs, c1, equal_nan=True) and np.array_equal(cp, p1)
