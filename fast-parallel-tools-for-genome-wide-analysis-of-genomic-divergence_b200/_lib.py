@@ -44,6 +44,9 @@ SYMBOLS = {
     "fpt_set_device": (_I, [_I]),
     "fpt_set_seed": (None, [C.c_uint64]),
     "fpt_get_seed": (C.c_uint64, []),
+    "fpt_set_perm_mode": (None, [_I]),
+    "fpt_get_perm_mode": (_I, []),
+    "fpt_css_perm_rechecks": (C.c_longlong, []),
     "fpt_release": (None, []),
     "fpt_window_state": (C.c_uint64, [C.c_uint64, C.c_int64, _I]),
     "fpt_profile_enable": (_I, [_I]),

@@ -10,7 +10,7 @@ from ._lib import (FPT_SCAN_SERIAL, FPT_SCAN_THREADED, FPT_WIN_DISCARDED, FPT_WI
                    FptError, Genotypes, ScanRange)
 
 __all__ = ["FptError", "FPT_SCAN_SERIAL", "FPT_SCAN_THREADED", "FPT_WIN_EMPTY", "FPT_WIN_DISCARDED", "FPT_WIN_SCORED",
-           "device_count", "set_device", "set_seed", "get_seed", "window_state", "window_count", "fet_scan", "css_scan",
+           "device_count", "set_device", "set_seed", "get_seed", "set_perm_mode", "get_perm_mode", "css_perm_rechecks", "window_state", "window_count", "fet_scan", "css_scan",
            "fet_per_snp", "fet_tables"]
 
 
@@ -28,6 +28,19 @@ def set_seed(seed):
 
 def get_seed():
     return int(_lib.load().fpt_get_seed())
+
+
+def set_perm_mode(chain):
+    """CSS label shuffles: False = independent per permutation (default), True = the reference's chained label array"""
+    _lib.load().fpt_set_perm_mode(1 if chain else 0)
+
+
+def get_perm_mode():
+    return bool(_lib.load().fpt_get_perm_mode())
+
+
+def css_perm_rechecks():
+    return int(_lib.load().fpt_css_perm_rechecks())
 
 
 def window_state(seed, window, stream=0):

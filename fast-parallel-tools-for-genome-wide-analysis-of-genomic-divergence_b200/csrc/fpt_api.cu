@@ -22,6 +22,7 @@
 #include "../../include/fpt_b200.h"
 #include "fpt_css.cuh"
 #include "fpt_css_eig.cuh"
+#include "fpt_css_perm.cuh"
 #include "fpt_fet.cuh"
 #include "fpt_rt.cuh"
 #include "fpt_tables.h"
@@ -30,6 +31,7 @@
 static thread_local char g_err[512] = "";
 static uint64_t g_seed = 20261018ULL;
 static int g_device = -1;               /* -1: whatever device is current */
+static int g_perm_chain = 0;            /* CSS label shuffles: 0 = independent per permutation, 1 = the reference's chain */
 
 static int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -58,6 +60,7 @@ struct DeviceCtx {
     unsigned long long *binom = nullptr;
     double *lf = nullptr;
     int lf_maxn = -1;
+    unsigned long long *rechecks = nullptr;
     bool pool_ready = false;
 };
 static DeviceCtx g_ctx[64];
@@ -85,6 +88,8 @@ static int get_ctx(DeviceCtx **out) {
         std::vector<unsigned long long> b = fpt_build_binom_table();
         CU(cudaMalloc(&c.binom, b.size() * sizeof(unsigned long long)));
         CU(cudaMemcpy(c.binom, b.data(), b.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&c.rechecks, sizeof(unsigned long long)));
+        CU(cudaMemset(c.rechecks, 0, sizeof(unsigned long long)));
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             unsigned long long keep = ~0ULL;                 /* keep freed blocks cached between calls */
@@ -236,6 +241,21 @@ extern "C" int fpt_set_device(int device) {
     return FPT_OK;
 }
 
+extern "C" void fpt_set_perm_mode(int chain) { g_perm_chain = chain != 0; }
+extern "C" int fpt_get_perm_mode(void) { return g_perm_chain; }
+
+/* exact re-evaluations the permutation kernel needed since the last call (its integer surrogate could not
+   decide `permuted >= observed`); synchronises the device */
+extern "C" long long fpt_css_perm_rechecks(void) {
+    DeviceCtx *c;
+    if (get_ctx(&c) != FPT_OK) return -1;
+    unsigned long long v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, c->rechecks, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    cudaMemset(c->rechecks, 0, sizeof v);
+    return (long long)v;
+}
+
 extern "C" void fpt_set_seed(uint64_t seed) { g_seed = seed; }
 extern "C" uint64_t fpt_get_seed(void) { return g_seed; }
 extern "C" uint64_t fpt_window_state(uint64_t seed, int64_t window, int stream) {
@@ -251,6 +271,7 @@ extern "C" void fpt_release(void) {
         cudaDeviceSynchronize();
         if (c.binom) cudaFree(c.binom);
         if (c.lf) cudaFree(c.lf);
+        if (c.rechecks) cudaFree(c.rechecks);
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
         c = DeviceCtx();
@@ -425,6 +446,8 @@ struct CssPlan {
     size_t smem_mds_warp;
     int perm_threads, wide_tracks, dist_in_smem, tracks_in_smem;
     size_t smem_perm, perm_scratch_per_cta;
+    int perm2, qbits;                /* second-generation permutation kernel (labels in bytes, everything in smem) */
+    size_t smem_perm2;
     int max_ctas;                    /* upper bound on persistent CTAs (sizes the global scratch) */
 };
 
@@ -448,6 +471,9 @@ static CssPlan css_plan(const DeviceCtx *c, int m) {
     size_t per = (p.dist_in_smem ? 0 : (size_t)m * m * 8) + (p.tracks_in_smem ? 0 : (size_t)2 * p.perm_threads * m * tb);
     p.perm_scratch_per_cta = (per + 255) & ~(size_t)255;
     p.max_ctas = c->sms * 16;
+    p.smem_perm2 = fpt_css_perm2_smem_bytes(m, p.perm_threads, g_perm_chain);
+    p.perm2 = m <= 250 && p.smem_perm2 <= budget;
+    p.qbits = 8;
     return p;
 }
 
@@ -496,7 +522,7 @@ static int launch_perm(DeviceCtx *c, const CssPlan &p, const CssWorkspace &ws, i
     CHECK(persistent_grid(c, fpt_css_perm_kernel<TrackT>, p.perm_threads, p.smem_perm, nwin, &grid));
     grid = std::min(grid, p.max_ctas);
     { ProfScope ps_("css_perm", st); fpt_css_perm_kernel<TrackT><<<grid, p.perm_threads, p.smem_perm, st>>>(
-        ws.X, p.m, asize, bsize, wbase, nwin, status, treshold, runs, seed, states, p.dist_in_smem, p.tracks_in_smem,
+        ws.X, p.m, asize, bsize, wbase, nwin, status, treshold, runs, seed, states, g_perm_chain, p.dist_in_smem, p.tracks_in_smem,
         (double *)ws.perm_scratch, p.perm_scratch_per_cta, scores, pv, hits, nperm); }
     CU(cudaGetLastError());
     return FPT_OK;
@@ -552,7 +578,17 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
         CU(cudaGetLastError());
     }
     int *hits = probes ? probes->hits : nullptr, *nperm = probes ? probes->nperm : nullptr;
-    if (p.wide_tracks)
+    if (p.perm2) {
+        /* quantisation width: |smaller group| * m * 2^qbits must stay below 2^31 (integer surrogate sums) */
+        const long long terms = (long long)std::min(asize, bsize) * m + 1;
+        int qb = 22;
+        while (qb > 4 && (terms << qb) >= (1LL << 31)) qb--;
+        CHECK(persistent_grid(c, fpt_css_perm2_kernel, p.perm_threads, p.smem_perm2, nwin, &grid));
+        { ProfScope ps_("css_perm", st); fpt_css_perm2_kernel<<<grid, p.perm_threads, p.smem_perm2, st>>>(
+              ws.X, m, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, g_perm_chain, qb, scores, pv,
+              hits, nperm, c->rechecks); }
+        CU(cudaGetLastError());
+    } else if (p.wide_tracks)
         CHECK(launch_perm<unsigned short>(c, p, ws, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed,
                                           st_perm, scores, pv, hits, nperm, st));
     else

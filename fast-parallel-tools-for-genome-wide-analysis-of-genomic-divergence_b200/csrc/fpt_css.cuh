@@ -509,7 +509,7 @@ template <typename TrackT>
 __global__ void __launch_bounds__(256)
 fpt_css_perm_kernel(const double *__restrict__ Xall, int m, int asize, int bsize, long long wbase, long long nwin,
                     const unsigned char *__restrict__ status, int treshold, int runs, uint64_t seed,
-                    const uint64_t *__restrict__ state_override, int dist_in_smem, int tracks_in_smem,
+                    const uint64_t *__restrict__ state_override, int chain, int dist_in_smem, int tracks_in_smem,
                     double *__restrict__ gscratch, size_t gscratch_per_cta, double *__restrict__ out_score,
                     double *__restrict__ out_p, int *__restrict__ out_hits, int *__restrict__ out_n) {
     FPT_DYN_SMEM(smem);
@@ -562,7 +562,9 @@ fpt_css_perm_kernel(const double *__restrict__ Xall, int m, int asize, int bsize
             for (;;) {                                          /* generate; repair offsets after rejections */
                 int used = 0;
                 if (tid < nvalid) {
-                    uint64_t st = fpt_lcg_skip(st_win, (uint64_t)(stream_pos + offs[tid]));
+                    /* chain: stream consumed sequentially; independent: permutation k starts k*(m-1) draws in */
+                    uint64_t st = fpt_lcg_skip(st_win, chain ? (uint64_t)(stream_pos + offs[tid])
+                                                             : (uint64_t)(ndone + tid) * (uint64_t)draws);
                     for (int e = 0; e < m; e++) mine[e] = (TrackT)e;
                     for (int i = m - 1; i > 0; i--) {
                         const int rr = (int)fpt_randint((uint32_t)(i + 1), st, used);
@@ -572,7 +574,7 @@ fpt_css_perm_kernel(const double *__restrict__ Xall, int m, int asize, int bsize
                 int total = 0;
                 const int incl = fpt_block_scan_incl(used, scan, &total);
                 const int want = incl - used;
-                const int bad = (tid < nvalid && want != offs[tid]) ? 1 : 0;
+                const int bad = (chain && tid < nvalid && want != offs[tid]) ? 1 : 0;
                 if (bad) offs[tid] = want;
                 cons[tid] = total;
                 if (!__syncthreads_or(bad)) break;
@@ -580,7 +582,7 @@ fpt_css_perm_kernel(const double *__restrict__ Xall, int m, int asize, int bsize
             const int chunk_draws = cons[0];
             /* inclusive scan under composition: G_k = s_1 o ... o s_k, (f o g)[pos] = f[g[pos]] */
             TrackT *src = buf0, *dst = buf1;
-            for (int d = 1; d < nvalid; d <<= 1) {
+            for (int d = 1; chain && d < nvalid; d <<= 1) {
                 __syncthreads();
                 if (tid < nvalid) {
                     const TrackT *g = src + (size_t)tid * m;
@@ -599,7 +601,8 @@ fpt_css_perm_kernel(const double *__restrict__ Xall, int m, int asize, int bsize
             if (tid < nvalid) {
                 const TrackT *g = src + (size_t)tid * m;
                 TrackT *o = dst + (size_t)tid * m;                /* labels after permutation ndone+tid+1 */
-                for (int e = 0; e < m; e++) o[e] = carry[g[e]];
+                if (chain) for (int e = 0; e < m; e++) o[e] = carry[g[e]];
+                else for (int e = 0; e < m; e++) o[e] = g[e];  /* fresh identity labels every time */
                 hit = fpt_css_score<TrackT>(dist, m, o, o + asize, asize, bsize) >= score ? 1 : 0;
             }
             int chunk_hits = 0;

@@ -1,0 +1,292 @@
+/*
+ * fpt_css_perm.cuh — score + Monte-Carlo permutation test, second generation
+ * (reference: calc_dist css/css.c:573-587, css css.c:608-647, random_shuffle css.c:700-706,
+ *  significance_treshold css.c:727-752).
+ *
+ * One CTA per window, embedding distances in shared memory, PP consecutive permutations per thread.
+ *
+ * Exactness without paying for it. The reference decides `permuted score >= observed score` on sums
+ * accumulated in one fixed order; reproducing that order costs asize*bsize + m - 2 dependent fp64
+ * adds fed by 8-byte shared-memory gathers per permutation (the first-generation kernel,
+ * fpt_css_perm_kernel, does exactly that and is shared-memory-wavefront bound). Here every permutation is
+ * first scored with a cheap, order-independent surrogate:
+ *     distances quantised to integers q = round(d * S) (4-byte gathers, integer adds, no rounding at all),
+ *     between-group sum through the identity  sum_{A'xB'} q = sum_{i in G} rowsum_q(i) - 2 sum_{i<j in G} q_ij
+ *     (G = the smaller group; exact in integers), i.e. |G| + |G|(|G|-1)/2 gathers instead of asize*bsize.
+ * The surrogate differs from the true score by at most E (quantisation bound + fp bound, derived below); only when
+ * |surrogate - observed| <= E — a handful of permutations per thousand windows — is the score recomputed in the
+ * reference's order. Decisions, hence hits, early-stop index and p, are those of the reference arithmetic.
+ *
+ * Shuffles. mode 0 (default): permutation k is the reference's Fisher-Yates shuffle applied to FRESH identity
+ * labels with the window's nrand48 stream positioned at k*(m-1) draws (counter-based: any permutation can be
+ * regenerated on its own). mode 1 ("chain"): the reference's exact semantics — one persistent label array
+ * shuffled again and again, stream consumed sequentially with rejections: thread blocks of PP permutations are
+ * shuffled from identity to get the block's net permutation, a prefix scan under composition gives every block
+ * its starting labels, and the block is replayed from there (bit-identical to significance_treshold run from
+ * the same 48-bit state on identity labels).
+ */
+#ifndef FPT_CSS_PERM_CUH
+#define FPT_CSS_PERM_CUH
+
+#include "fpt_css.cuh"
+
+#define FPT_PERM_PP 4                     /* permutations per thread per chunk */
+
+FPT_HD int fpt_perm_row_stride(int m) {   /* bytes; a multiple of 4 whose word count is odd: conflict-free rows */
+    int w = (m + 3) >> 2;
+    if ((w & 1) == 0) w++;
+    return w << 2;
+}
+
+FPT_HD size_t fpt_css_perm2_smem_bytes(int m, int nthreads, int chain) {
+    size_t off = (size_t)m * m * 8;                       /* dist */
+    off += (size_t)m * m * 4;                             /* q */
+    off += (size_t)m * 4;                                 /* rowsum_q */
+    off += (size_t)2 * m * 8;                             /* X */
+    off += (size_t)nthreads * 4 * 2;                      /* offs, used */
+    off += 33 * 4 + 12;
+    off = (off + 15) & ~(size_t)15;
+    off += (size_t)fpt_perm_row_stride(m);                /* carry */
+    off = (off + 15) & ~(size_t)15;
+    off += (size_t)nthreads * fpt_perm_row_stride(m) * (chain ? 2 : 1);
+    return off;
+}
+
+/* reference-order score on byte labels (same as fpt_css_score<unsigned char>) is reused for the rare recheck */
+
+/* Fisher-Yates on a byte row, css.c:700-706 */
+FPT_D void fpt_shuffle_row(unsigned char *row, int m, uint64_t &st, int &used) {
+    for (int i = m - 1; i > 0; i--) {
+        const int rr = (int)fpt_randint((uint32_t)(i + 1), st, used);
+        const unsigned char t = row[i]; row[i] = row[rr]; row[rr] = t;
+    }
+}
+
+FPT_D void fpt_identity_row(unsigned char *row, int m) {
+    /* 4 labels per store; the row is 4-byte aligned and padded to a multiple of 4 */
+    unsigned *r4 = reinterpret_cast<unsigned *>(row);
+    for (int e = 0; e < m; e += 4) r4[e >> 2] = (unsigned)e * 0x01010101u + 0x03020100u;
+}
+
+/* integer surrogate of the score for labels `row`: returns sum over A'xB' of q and the two adjacent-pair sums */
+FPT_D void fpt_surrogate(const unsigned *q, const int *rowsum, int m, const unsigned char *row, int asize, int bsize,
+                         int use_a, long long &bet, int &wa, int &wb) {
+    const unsigned char *g = use_a ? row : row + asize;
+    const int ng = use_a ? asize : bsize;
+    int rs = 0, pr = 0;
+    for (int i = 0; i < ng; i++) {
+        const int gi = g[i];
+        rs += rowsum[gi];
+        const unsigned *qi = q + gi * m;
+        for (int j = i + 1; j < ng; j++) pr += (int)qi[g[j]];
+    }
+    bet = (long long)rs - 2LL * (long long)pr;
+    int a = 0, b = 0;
+    for (int i = 0; i + 1 < asize; i++) a += (int)q[row[i] * m + row[i + 1]];
+    for (int i = 0; i + 1 < bsize; i++) b += (int)q[row[asize + i] * m + row[asize + i + 1]];
+    wa = a; wb = b;
+}
+
+__global__ void __launch_bounds__(256, 4)
+fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsize, long long wbase, long long nwin,
+                     const unsigned char *__restrict__ status, int treshold, int runs, uint64_t seed,
+                     const uint64_t *__restrict__ state_override, int chain, int qbits,
+                     double *__restrict__ out_score, double *__restrict__ out_p, int *__restrict__ out_hits,
+                     int *__restrict__ out_n, unsigned long long *__restrict__ recheck_counter) {
+    FPT_DYN_SMEM(smem);
+    const int T = blockDim.x, tid = threadIdx.x, RS = fpt_perm_row_stride(m);
+    size_t off = 0;
+    double *dist = (double *)(smem + off); off += (size_t)m * m * 8;
+    unsigned *q = (unsigned *)(smem + off); off += (size_t)m * m * 4;
+    int *rowsum = (int *)(smem + off); off += (size_t)m * 4;
+    double *X = (double *)(smem + off); off += (size_t)2 * m * 8;
+    int *offs = (int *)(smem + off); off += (size_t)T * 4;
+    int *usedv = (int *)(smem + off); off += (size_t)T * 4;
+    int *scan = (int *)(smem + off); off += 33 * 4 + 12;
+    off = (off + 15) & ~(size_t)15;
+    unsigned char *carry = smem + off; off += (size_t)RS;
+    off = (off + 15) & ~(size_t)15;
+    unsigned char *rows = smem + off;
+    unsigned char *rows2 = rows + (size_t)T * RS;          /* chain mode only */
+    __shared__ double s_score, s_dmax;
+    __shared__ int s_flag;
+    unsigned char *mine = rows + (size_t)tid * RS;
+    const int use_a = asize <= bsize;
+    const int draws = m - 1;
+    unsigned long long rechecks = 0;
+
+    for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
+        if (status[w] != FPT_WIN_SCORED) continue;
+        for (int e = tid; e < 2 * m; e += T) X[e] = Xall[(size_t)w * 2 * m + e];
+        __syncthreads();
+        double dmax = 0.0;
+        for (int e = tid; e < m * m; e += T) {              /* calc_dist, css.c:573-587 */
+            const int i = e / m, j = e - i * m;
+            if (j < i) {
+                const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
+                const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                dist[e] = d; dist[j * m + i] = d;
+                dmax = fmax(dmax, d);                       /* NaN distances: fmax ignores them, see `usable` */
+            } else if (j == i) dist[e] = 0.0;
+        }
+        for (int e = tid; e < RS; e += T) carry[e] = (unsigned char)e;
+        for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(FPT_FULL_MASK, dmax, o));
+        double *wmax = reinterpret_cast<double *>(offs);    /* T ints = T/2 doubles >= T/32 warp maxima; 8-byte aligned */
+        if ((tid & 31) == 0) wmax[tid >> 5] = dmax;
+        __syncthreads();
+        if (tid == 0) {
+            double mx = 0.0;
+            for (int k = 0; k < (T >> 5); k++) mx = fmax(mx, wmax[k]);
+            s_dmax = mx;
+            s_score = fpt_css_score<unsigned char>(dist, m, carry, carry + asize, asize, bsize);
+        }
+        __syncthreads();
+        const double score = s_score;
+        dmax = s_dmax;
+        /* quantisation: q = rint(d * S), S = 2^qbits / dmax  =>  q <= 2^qbits, |q/S - d| <= 0.5/S.
+           The surrogate is only usable for finite, positive distances and a finite observed score. */
+        const bool usable = (dmax > 0.0) && (dmax < 1e300) && (score == score) && (fabs(score) < 1e300);
+        const double S = usable ? (double)(1u << qbits) / dmax : 0.0;
+        int bad = 0;
+        for (int e = tid; e < m * m; e += T) {
+            const double d = dist[e];
+            if (!(d == d)) bad = 1;
+            q[e] = usable && d == d ? (unsigned)__double2ll_rn(d * S) : 0u;
+        }
+        const bool use_surrogate = usable && !__syncthreads_or(bad);
+        for (int i = tid; i < m; i += T) {
+            int s = 0;
+            for (int j = 0; j < m; j++) s += (int)q[i * m + j];
+            rowsum[i] = s;
+        }
+        __syncthreads();
+        /* |surrogate - reference score| <= E:  quantisation  (0.5/S)(1 + (a+b)(1/a^2 + 1/b^2))  on the three
+           means, plus a generous bound on the fp64 rounding of both evaluations */
+        const double a_ = (double)asize, b_ = (double)bsize;
+        const double wterm = (asize > 1 ? 1.0 / (a_ * a_) : 0.0) + (bsize > 1 ? 1.0 / (b_ * b_) : 0.0);
+        const double E = use_surrogate ? (0.5 / S) * (1.0 + (a_ + b_) * wterm) * 1.0000001 + 1e-11 * dmax * (1.0 + (a_ + b_)) : 0.0;
+        const double invS = use_surrogate ? 1.0 / S : 0.0;
+        const double c_bet = invS / (a_ * b_);
+        const double c_wa = asize > 1 ? invS / (a_ * a_ * (a_ - 1.0)) : 0.0;
+        const double c_wb = bsize > 1 ? invS / (b_ * b_ * (b_ - 1.0)) : 0.0;
+
+        const uint64_t st_win = state_override ? state_override[w] : fpt_stream_state(seed, wbase + w, FPT_STREAM_RESAMPLE);
+        long long stream_pos = 0;                           /* chain mode: draws consumed by finished chunks */
+        int hits = 0, ndone = 0;
+        bool stopped = false;
+        while (!stopped && hits < treshold && ndone < runs) {
+            const int nvalid = min(T * FPT_PERM_PP, runs - ndone);
+            const int first = tid * FPT_PERM_PP;            /* my permutations: first .. first+PP-1 of this chunk */
+            const int mycount = max(0, min(FPT_PERM_PP, nvalid - first));
+            uint64_t st = 0;
+            if (chain) {
+                /* pass 1: net permutation of my block from identity; repair stream offsets after rejections */
+                offs[tid] = first * draws;
+                __syncthreads();
+                for (;;) {
+                    int used = 0;
+                    if (mycount > 0) {
+                        fpt_identity_row(mine, m);
+                        uint64_t s1 = fpt_lcg_skip(st_win, (uint64_t)(stream_pos + offs[tid]));
+                        for (int j = 0; j < mycount; j++) fpt_shuffle_row(mine, m, s1, used);
+                    }
+                    int total = 0;
+                    const int incl = fpt_block_scan_incl(used, scan, &total);
+                    const int want = incl - used;
+                    const int wrong = (mycount > 0 && want != offs[tid]) ? 1 : 0;
+                    if (wrong) offs[tid] = want;
+                    usedv[tid] = total;
+                    if (!__syncthreads_or(wrong)) break;
+                }
+                /* exclusive scan under composition over the thread blocks: (f o g)[pos] = f[g[pos]] */
+                const int nblk = (nvalid + FPT_PERM_PP - 1) / FPT_PERM_PP;
+                unsigned char *src = rows, *dst = rows2;
+                for (int d = 1; d < nblk; d <<= 1) {
+                    __syncthreads();
+                    if (tid < nblk) {
+                        const unsigned char *g = src + (size_t)tid * RS;
+                        unsigned char *o = dst + (size_t)tid * RS;
+                        if (tid >= d) {
+                            const unsigned char *f = src + (size_t)(tid - d) * RS;
+                            for (int e = 0; e < m; e++) o[e] = f[g[e]];
+                        } else {
+                            for (int e = 0; e < m; e++) o[e] = g[e];
+                        }
+                    }
+                    unsigned char *tmp = src; src = dst; dst = tmp;
+                }
+                __syncthreads();
+                /* my starting labels: carry o (inclusive scan up to block tid-1); my block is replayed from there */
+                unsigned char *start = dst + (size_t)tid * RS;
+                if (mycount > 0) {
+                    if (tid == 0) { for (int e = 0; e < m; e++) start[e] = carry[e]; }
+                    else { const unsigned char *g = src + (size_t)(tid - 1) * RS; for (int e = 0; e < m; e++) start[e] = carry[g[e]]; }
+                }
+                __syncthreads();
+                mine = start;
+                st = fpt_lcg_skip(st_win, (uint64_t)(stream_pos + offs[tid]));
+            }
+            /* pass 2 (the only pass without the chain): shuffle, score, decide */
+            int myhits = 0, hitmask = 0;
+            bool resync = false;
+            for (int j = 0; j < mycount; j++) {
+                int used = 0;
+                if (!chain) {
+                    fpt_identity_row(mine, m);
+                    /* the stream of permutation k starts k*(m-1) draws in; after a shuffle without a rejected draw the
+                       state already sits at the next permutation's start */
+                    if (j == 0 || resync) st = fpt_lcg_skip(st_win, (uint64_t)(ndone + first + j) * (uint64_t)draws);
+                }
+                fpt_shuffle_row(mine, m, st, used);
+                resync = used != draws;
+                int hit;
+                bool exact = !use_surrogate;
+                if (use_surrogate) {
+                    long long bet; int wa, wb;
+                    fpt_surrogate(q, rowsum, m, mine, asize, bsize, use_a, bet, wa, wb);
+                    const double approx = (double)bet * c_bet - (a_ + b_) * ((double)wa * c_wa + (double)wb * c_wb);
+                    const double diff = approx - score;
+                    hit = diff > 0.0;
+                    exact = !(fabs(diff) > E);
+                }
+                if (exact) {
+                    hit = fpt_css_score<unsigned char>(dist, m, mine, mine + asize, asize, bsize) >= score ? 1 : 0;
+                    rechecks++;
+                }
+                myhits += hit; hitmask |= hit << j;
+            }
+            int chunk_hits = 0;
+            const int hincl = fpt_block_scan_incl(myhits, scan, &chunk_hits);
+            if (tid == 0) s_flag = -1;
+            __syncthreads();
+            if (myhits > 0 && hits + hincl >= treshold && hits + hincl - myhits < treshold) {
+                /* the treshold-th hit is one of mine: find which permutation */
+                int need = treshold - (hits + hincl - myhits);
+                for (int j = 0; j < FPT_PERM_PP; j++) if ((hitmask >> j) & 1) { if (--need == 0) { s_flag = first + j; break; } }
+            }
+            __syncthreads();
+            if (s_flag >= 0) {
+                ndone += s_flag + 1; hits = treshold; stopped = true;
+            } else {
+                hits += chunk_hits; ndone += nvalid;
+                if (chain) {
+                    const int lastblk = (nvalid - 1) / FPT_PERM_PP;
+                    if (tid == lastblk) for (int e = 0; e < m; e++) carry[e] = mine[e];
+                    stream_pos += usedv[0];
+                }
+            }
+            __syncthreads();
+            mine = rows + (size_t)tid * RS;
+        }
+        if (tid == 0) {
+            out_score[w] = score;
+            out_p[w] = __ddiv_rn(__dmul_rn((double)(hits + 1), 1.0), (double)(ndone + 1));
+            if (out_hits) out_hits[w] = hits;
+            if (out_n) out_n[w] = ndone;
+        }
+        __syncthreads();
+    }
+    if (recheck_counter && rechecks) atomicAdd(recheck_counter, rechecks);
+}
+
+#endif

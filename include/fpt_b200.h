@@ -52,6 +52,15 @@ int fpt_device_count(void);                 /* number of CUDA devices, 0 if none
 int fpt_set_device(int device);             /* device used by the host entry points of this process */
 void fpt_set_seed(uint64_t seed);           /* seed of the window-keyed random streams (default 20261018) */
 uint64_t fpt_get_seed(void);
+/* CSS label shuffles. 0 (default): permutation k of a window is the reference's Fisher-Yates shuffle (css/css.c:700-706)
+   of fresh identity labels, its nrand48 stream positioned k*(m-1) draws into the window's stream (counter-based).
+   1: the reference's exact chain — one persistent label array shuffled again and again (css/css.c:727-752), bit-identical
+   to significance_treshold() run on identity labels from the same 48-bit state. */
+void fpt_set_perm_mode(int chain);
+int fpt_get_perm_mode(void);
+/* number of permutations since the last call whose integer surrogate score could not decide `permuted >= observed` and
+   were re-scored in the reference's summation order (diagnostic; synchronises the device); -1 on error */
+long long fpt_css_perm_rechecks(void);
 void fpt_release(void);                     /* free cached device/pinned buffers */
 /* 48-bit LCG state of (seed, global window index, stream); stream 0 = bootstrap / label shuffles
    (nrand48 draws), 1 = SMACOF starts (drand48 draws). Pure host arithmetic. */

@@ -617,6 +617,44 @@ double fpt_oracle_significance(const double *dist, int m, int *tracks, int asize
     return (hits + 1) * 1.0 / (n + 1);
 }
 
+/* state after n further draws of the LCG (square-and-multiply on the affine map) */
+uint64_t fpt_oracle_lcg_skip(uint64_t s, uint64_t n) {
+    uint64_t ra = 1, rc = 0, ba = LCG_A, bc = LCG_C;
+    while (n) {
+        if (n & 1) { rc = (ba * rc + bc) & MASK48; ra = (ba * ra) & MASK48; }
+        bc = (ba * bc + bc) & MASK48;
+        ba = (ba * ba) & MASK48;
+        n >>= 1;
+    }
+    return (ra * s + rc) & MASK48;
+}
+
+/* permutation test in "independent" mode (the product's default): permutation k is the reference's Fisher-Yates
+   shuffle (css.c:700-706) of FRESH identity labels with the window's nrand48 stream positioned k*(m-1) draws in;
+   scoring, hit counting, early stop and p exactly as css.c:727-752 */
+double fpt_oracle_significance_indep(const double *dist, int m, int asize, int bsize, double score, int treshold,
+                                     int runs, uint64_t state, int *hits_out, int *n_out) {
+    int hits = 0, n = 0;
+    int *tracks = (int *)malloc((size_t)m * sizeof(int));
+    while (hits < treshold && n < runs) {
+        uint64_t st = fpt_oracle_lcg_skip(state, (uint64_t)n * (uint64_t)(m - 1));
+        for (int i = 0; i < m; i++) tracks[i] = i;
+        for (int i = m - 1; i > 0; i--) {
+            int r = (int)fpt_oracle_randint(i + 1, &st);
+            int t = tracks[i]; tracks[i] = tracks[r]; tracks[r] = t;
+        }
+        if (fpt_oracle_css(dist, m, tracks, tracks + asize, asize, bsize) >= score) hits++;
+        n++;
+    }
+    free(tracks);
+    if (hits_out) *hits_out = hits;
+    if (n_out) *n_out = n;
+    return (hits + 1) * 1.0 / (n + 1);
+}
+
+static int g_perm_chain = 0;    /* 0 = independent shuffles (product default), 1 = the reference's chained label array */
+void fpt_oracle_set_perm_mode(int chain) { g_perm_chain = chain != 0; }
+
 double fpt_oracle_css_window(const double *avals, const double *bvals, int asize, int bsize, int npos,
                              int drosophila, int mds, int treshold, int runs, uint64_t state_perm,
                              uint64_t state_init, double *p_out, double *X_out, double evals_out[3]) {
@@ -637,8 +675,9 @@ double fpt_oracle_css_window(const double *avals, const double *bvals, int asize
         fpt_oracle_calc_dist(X, m, dist);
         for (int i = 0; i < m; i++) tracks[i] = i;
         score = fpt_oracle_css(dist, m, tracks, tracks + asize, asize, bsize);
-        if (p_out) *p_out = fpt_oracle_significance(dist, m, tracks, asize, bsize, score, treshold, runs,
-                                                    &state_perm, NULL, NULL);
+        if (p_out) *p_out = g_perm_chain
+            ? fpt_oracle_significance(dist, m, tracks, asize, bsize, score, treshold, runs, &state_perm, NULL, NULL)
+            : fpt_oracle_significance_indep(dist, m, asize, bsize, score, treshold, runs, state_perm, NULL, NULL);
         if (X_out) memcpy(X_out, X, (size_t)m * 2 * sizeof(double));
         if (evals_out) memcpy(evals_out, ev, sizeof ev);
     }

@@ -74,6 +74,10 @@ void   fpt_oracle_calc_dist(const double *X, int m, double *dist);
 double fpt_oracle_css(const double *dist, int m, const int *atracks, const int *btracks, int asize, int bsize);
 double fpt_oracle_significance(const double *dist, int m, int *tracks, int asize, int bsize, double score,
                                int treshold, int runs, uint64_t *state, int *hits_out, int *n_out);
+uint64_t fpt_oracle_lcg_skip(uint64_t state, uint64_t n);
+double fpt_oracle_significance_indep(const double *dist, int m, int asize, int bsize, double score, int treshold,
+                                     int runs, uint64_t state, int *hits_out, int *n_out);
+void   fpt_oracle_set_perm_mode(int chain);   /* scans: 0 = independent shuffles (default), 1 = chained labels */
 /* one window end to end; returns the score or -1 (discarded); *p_out untouched when discarded */
 double fpt_oracle_css_window(const double *avals, const double *bvals, int asize, int bsize, int npos,
                              int drosophila, int mds, int treshold, int runs, uint64_t state_perm,

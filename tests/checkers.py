@@ -98,6 +98,13 @@ def load_oracle():
     o.fpt_oracle_significance.restype = C.c_double
     o.fpt_oracle_significance.argtypes = [c_double_p, C.c_int, c_int_p, C.c_int, C.c_int, C.c_double, C.c_int,
                                           C.c_int, c_u64_p, c_int_p, c_int_p]
+    o.fpt_oracle_lcg_skip.restype = C.c_uint64
+    o.fpt_oracle_lcg_skip.argtypes = [C.c_uint64, C.c_uint64]
+    o.fpt_oracle_significance_indep.restype = C.c_double
+    o.fpt_oracle_significance_indep.argtypes = [c_double_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint64,
+                                                c_int_p, c_int_p]
+    o.fpt_oracle_set_perm_mode.restype = None
+    o.fpt_oracle_set_perm_mode.argtypes = [C.c_int]
     o.fpt_oracle_css_window.restype = C.c_double
     o.fpt_oracle_css_window.argtypes = [c_double_p, c_double_p] + [C.c_int] * 7 + [C.c_uint64, C.c_uint64,
                                                                                   c_double_p, c_double_p, c_double_p]

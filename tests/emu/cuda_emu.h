@@ -113,6 +113,7 @@ static inline double __dsqrt_rn(double a) { return sqrt(a); }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline double __ull2double_rn(unsigned long long v) { return (double)v; }
 static inline double __int2double_rn(int v) { return (double)v; }
+static inline long long __double2ll_rn(double v) { return llrint(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }

@@ -11,6 +11,7 @@ FPT_EMU_DEFINE_GLOBALS
 #include "fpt_fet.cuh"
 #include "fpt_css.cuh"
 #include "fpt_css_eig.cuh"
+#include "fpt_css_perm.cuh"
 #include "fpt_tables.h"
 
 template <class F>
@@ -128,7 +129,7 @@ void emu_css_pick(const double *Xruns, const double *sigma_runs, int m, int nrun
 
 void emu_css_perm(const double *Xall, int m, int asize, int bsize, long long wbase, long long nwin, const unsigned char *status,
                   int treshold, int runs, uint64_t seed, const uint64_t *state_override, int dist_in_smem,
-                  int tracks_in_smem, int nthreads, int grid, int wide_tracks, double *out_score, double *out_p,
+                  int tracks_in_smem, int nthreads, int grid, int wide_tracks, int chain, double *out_score, double *out_p,
                   int *out_hits, int *out_n) {
     int tb = wide_tracks ? 2 : 1;
     size_t smem = fpt_css_perm_smem_bytes(m, nthreads, tb, dist_in_smem, tracks_in_smem);
@@ -138,14 +139,27 @@ void emu_css_perm(const double *Xall, int m, int asize, int bsize, long long wba
     double *gp = per_cta ? gs.data() : 0;
     if (wide_tracks)
         run_grid(grid, nthreads, smem, [=]() {
-            fpt_css_perm_kernel<unsigned short>(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override,
+            fpt_css_perm_kernel<unsigned short>(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override, chain,
                                                 dist_in_smem, tracks_in_smem, gp, per_cta, out_score, out_p, out_hits, out_n);
         });
     else
         run_grid(grid, nthreads, smem, [=]() {
-            fpt_css_perm_kernel<unsigned char>(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override,
+            fpt_css_perm_kernel<unsigned char>(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override, chain,
                                                dist_in_smem, tracks_in_smem, gp, per_cta, out_score, out_p, out_hits, out_n);
         });
+}
+
+unsigned long long emu_css_perm2(const double *Xall, int m, int asize, int bsize, long long wbase, long long nwin,
+                                 const unsigned char *status, int treshold, int runs, uint64_t seed, const uint64_t *state_override,
+                                 int chain, int qbits, int nthreads, int grid, double *out_score, double *out_p, int *out_hits,
+                                 int *out_n) {
+    size_t smem = fpt_css_perm2_smem_bytes(m, nthreads, chain);
+    unsigned long long rechecks = 0, *pr = &rechecks;
+    run_grid(grid, nthreads, smem, [=]() {
+        fpt_css_perm2_kernel(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override, chain, qbits,
+                             out_score, out_p, out_hits, out_n, pr);
+    });
+    return rechecks;
 }
 
 }  // extern "C"

@@ -214,11 +214,13 @@ def test_css_smacof_and_perm_kernels(emu, oracle, mds):
                            C.c_double(1e-6), None, dptr(Xr), dptr(sg), iptr(it), vp(st))
         emu.emu_css_pick(dptr(Xr), dptr(sg), m, 4, ll(n), vp(st), dptr(X))
     sc, p, hits, nn = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
-    emu.emu_css_perm(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), 7, 150, C.c_uint64(seed), None, 1, 1, 64, 2, 0, dptr(sc), dptr(p),
+    emu.emu_css_perm(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), 7, 150, C.c_uint64(seed), None, 1, 1, 64, 2, 0, 1, dptr(sc), dptr(p),
                      iptr(hits), iptr(nn))
     so, po = np.zeros(n), np.zeros(n)
+    oracle.fpt_oracle_set_perm_mode(1)
     oracle.fpt_oracle_css_scan(dptr(av), dptr(bv), iptr(apos), iptr(bpos), 0, L, wsize, wstep, av.size, bv.size, 7, 150, 0, mds,
                                dptr(so), dptr(po), 0, seed)
+    oracle.fpt_oracle_set_perm_mode(0)
     scored = st == 2
     assert np.array_equal(scored, po != 0) and scored.sum() >= 5
     ok = scored & np.isfinite(so)
@@ -228,28 +230,43 @@ def test_css_smacof_and_perm_kernels(emu, oracle, mds):
         assert np.array_equal(p[ok], po[ok])
 
 
-def test_css_perm_kernel_chunks_early_stop_and_scratch_paths(emu, oracle):
-    """several chunks per window (runs > threads), early stop inside a chunk, 16-bit labels, global-memory scratch"""
+@pytest.mark.parametrize("chain", [0, 1])
+def test_css_perm_kernels_chunks_early_stop_and_scratch_paths(emu, oracle, chain):
+    """both permutation kernels, both shuffle modes: several chunks per window (runs > permutations per chunk), early
+    stop inside a chunk, 16-bit labels, global-memory scratch, the integer surrogate with forced ties (rechecks)"""
+    import math
+    emu.emu_css_perm2.restype = C.c_ulonglong
     rng = np.random.default_rng(8)
-    asize, bsize, n = 5, 6, 6
-    m = asize + bsize
-    X = rng.normal(size=(n, m, 2))
-    X[:, :asize, 0] += np.linspace(0.0, 1.5, n)[:, None]          # windows from "no separation" to "clear separation"
-    st = np.full(n, 2, dtype=np.uint8)
-    states = (np.arange(n, dtype=np.uint64) * 7919 + 13)
-    for tres, runs in ((5, 200), (1000, 100), (1, 70)):
-        want_p, want_h, want_n = [], [], []
-        for w in range(n):
-            dist = np.zeros((m, m))
-            oracle.fpt_oracle_calc_dist(dptr(X[w].copy()), m, dptr(dist))
-            tr = np.arange(m, dtype=np.int32)
-            score = oracle.fpt_oracle_css(dptr(dist), m, iptr(tr), iptr(tr[asize:]), asize, bsize)
-            s64, h, nn = C.c_uint64(int(states[w])), C.c_int(), C.c_int()
-            want_p.append(oracle.fpt_oracle_significance(dptr(dist), m, iptr(tr), asize, bsize, score, tres, runs, C.byref(s64), C.byref(h), C.byref(nn)))
-            want_h.append(h.value)
-            want_n.append(nn.value)
-        for dist_smem, tracks_smem, wide in ((1, 1, 0), (0, 0, 1), (1, 0, 0)):
+    for asize, bsize, n in ((5, 6, 6), (2, 2, 4), (1, 4, 3)):
+        m = asize + bsize
+        X = rng.normal(size=(n, m, 2))
+        X[:, :asize, 0] += np.linspace(0.0, 1.5, n)[:, None]      # windows from "no separation" to "clear separation"
+        if m == 4:
+            X[1] = np.round(X[1])                                  # exact ties between permuted and observed scores
+        st = np.full(n, 2, dtype=np.uint8)
+        states = (np.arange(n, dtype=np.uint64) * 7919 + 13)
+        qbits = min(22, int(math.floor(math.log2(2 ** 31 / (min(asize, bsize) * m + 1)))))
+        for tres, runs in ((5, 300), (1000, 100), (1, 70)):
+            want_p, want_h, want_n = [], [], []
+            for w in range(n):
+                dist = np.zeros((m, m))
+                oracle.fpt_oracle_calc_dist(dptr(X[w].copy()), m, dptr(dist))
+                tr = np.arange(m, dtype=np.int32)
+                score = oracle.fpt_oracle_css(dptr(dist), m, iptr(tr), iptr(tr[asize:]), asize, bsize)
+                h, nn = C.c_int(), C.c_int()
+                if chain:
+                    s64 = C.c_uint64(int(states[w]))
+                    want_p.append(oracle.fpt_oracle_significance(dptr(dist), m, iptr(tr), asize, bsize, score, tres, runs, C.byref(s64), C.byref(h), C.byref(nn)))
+                else:
+                    want_p.append(oracle.fpt_oracle_significance_indep(dptr(dist), m, asize, bsize, score, tres, runs, int(states[w]), C.byref(h), C.byref(nn)))
+                want_h.append(h.value)
+                want_n.append(nn.value)
+            for dist_smem, tracks_smem, wide in ((1, 1, 0), (0, 0, 1), (1, 0, 0)):
+                sc, p, hits, nn = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+                emu.emu_css_perm(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), tres, runs, C.c_uint64(0), vp(states), dist_smem, tracks_smem,
+                                 32, 2, wide, chain, dptr(sc), dptr(p), iptr(hits), iptr(nn))
+                assert list(hits) == want_h and list(nn) == want_n and list(p) == want_p
             sc, p, hits, nn = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
-            emu.emu_css_perm(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), tres, runs, C.c_uint64(0), vp(states), dist_smem, tracks_smem,
-                             32, 2, wide, dptr(sc), dptr(p), iptr(hits), iptr(nn))
+            emu.emu_css_perm2(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), tres, runs, C.c_uint64(0), vp(states), chain, qbits, 32, 2,
+                              dptr(sc), dptr(p), iptr(hits), iptr(nn))
             assert list(hits) == want_h and list(nn) == want_n and list(p) == want_p

@@ -206,13 +206,17 @@ def test_css_dropin_matches_reference(fpt, ref_css):
 
 
 def test_css_significance_matches_reference_stream(fpt, ref_css, oracle):
-    """per window, explicit state: p equals the reference's significance_treshold run on fresh identity labels"""
+    """chain mode, per window, explicit state: p equals the reference's significance_treshold run on fresh identity labels"""
     asize, bsize, wsize, wstep, regend, nsnp = 12, 9, 5000, 5000, 40000, 900
     m = asize + bsize
     ch, (av, bv, apos, bpos) = _synth(81, regend, nsnp, asize, bsize)
     n = regend // wstep
     states = np.array([0x5EED0000 + 977 * i for i in range(n)], dtype=np.uint64)
-    s_g, p_g, wr, pr = fpt.css_scan(av, bv, ch["pos"], asize, bsize, regend, wsize, wstep, 5, 400, mds=0, states_perm=states, probes=True)
+    fpt.set_perm_mode(True)
+    try:
+        s_g, p_g, wr, pr = fpt.css_scan(av, bv, ch["pos"], asize, bsize, regend, wsize, wstep, 5, 1400, mds=0, states_perm=states, probes=True)
+    finally:
+        fpt.set_perm_mode(False)
     checked = 0
     for w in range(n):
         if not wr[w]:
@@ -224,8 +228,41 @@ def test_css_significance_matches_reference_stream(fpt, ref_css, oracle):
         score = ref_css.css(dist.pp, iptr(tracks), iptr(tracks[asize:]), asize, bsize)
         assert score == s_g[w]                       # same embedding -> bit-identical score arithmetic
         st = checkers.state_to_ushort3(int(states[w]))
-        p_ref = ref_css.significance_treshold(dist.pp, iptr(tracks), asize, bsize, score, 5, 400, st)
+        p_ref = ref_css.significance_treshold(dist.pp, iptr(tracks), asize, bsize, score, 5, 1400, st)
         assert p_ref == p_g[w]
+        checked += 1
+    assert checked >= 4
+
+
+def test_css_independent_shuffles_match_reference_functions(fpt, ref_css, oracle):
+    """default mode: permutation k = the reference's random_shuffle on fresh identity labels, stream k*(m-1) draws in;
+    hits / permutations drawn / p recomputed with the reference's own random_shuffle + css, per window"""
+    asize, bsize, wsize, wstep, regend, nsnp = 20, 20, 5000, 5000, 50000, 1200
+    m = asize + bsize
+    ch, (av, bv, apos, bpos) = _synth(83, regend, nsnp, asize, bsize)
+    n = regend // wstep
+    states = np.array([0xC0FFEE00 + 7919 * i for i in range(n)], dtype=np.uint64)
+    tres, runs = 6, 600
+    s_g, p_g, wr, pr = fpt.css_scan(av, bv, ch["pos"], asize, bsize, regend, wsize, wstep, tres, runs, mds=0, states_perm=states, probes=True)
+    checked = 0
+    for w in range(n):
+        if not wr[w]:
+            continue
+        X = checkers.RefMatrix(m, 2, pr["X"][w])
+        dist = checkers.RefMatrix(m, m)
+        ref_css.calc_dist(X.pp, dist.pp, m)
+        ident = np.arange(m, dtype=np.int32)
+        score = ref_css.css(dist.pp, iptr(ident), iptr(ident[asize:]), asize, bsize)
+        assert score == s_g[w]
+        hits = k = 0
+        while hits < tres and k < runs:
+            st = checkers.state_to_ushort3(oracle.fpt_oracle_lcg_skip(int(states[w]), k * (m - 1)))
+            tr = np.arange(m, dtype=np.int32)
+            ref_css.random_shuffle(iptr(tr), m, st)
+            hits += ref_css.css(dist.pp, iptr(tr), iptr(tr[asize:]), asize, bsize) >= score
+            k += 1
+        assert (hits, k) == (pr["hits"][w], pr["nperm"][w])
+        assert p_g[w] == (hits + 1) * 1.0 / (k + 1)
         checked += 1
     assert checked >= 4
 
