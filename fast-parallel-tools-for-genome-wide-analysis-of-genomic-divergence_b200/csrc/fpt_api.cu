@@ -556,7 +556,8 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
         if (p.mds_warps > 0) {
             const int block = 32 * p.mds_warps;
             CHECK(persistent_grid(c, fpt_css_mds_warp_kernel, block, p.smem_mds_warp, (nwin + p.mds_warps - 1) / p.mds_warps, &grid));
-            { ProfScope ps_("css_mds", st); fpt_css_mds_warp_kernel<<<grid, block, p.smem_mds_warp, st>>>(planes, absdiff, m, wleft, wright, nwin, 4, ws.X, ws.evals, status); }
+            { ProfScope ps_("css_mds", st); fpt_css_mds_warp_kernel<<<grid, block, p.smem_mds_warp, st>>>(planes, absdiff, m, wleft, wright, nwin, 4, ws.X,
+                                                                                          (probes && probes->evals) ? ws.evals : nullptr, status); }
         } else {                                           /* cohorts too large for a warp's shared-memory slice */
             CHECK(persistent_grid(c, fpt_css_mds_kernel, 128, p.smem_win, nwin, &grid));
             grid = std::min(grid, p.max_ctas);

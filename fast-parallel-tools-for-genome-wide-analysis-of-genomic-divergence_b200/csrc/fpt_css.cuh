@@ -273,7 +273,11 @@ FPT_D void fpt_css_cmds(double *A, double *V, int m, double *X, double *evals3, 
     }
     __syncthreads();
     const int i1 = top[0], i2 = top[1];
-    const double s1 = sqrt(A[i1 * m + i1]), s2 = i2 >= 0 ? sqrt(A[i2 * m + i2]) : 0.0;
+    double l1 = A[i1 * m + i1], l2 = i2 >= 0 ? A[i2 * m + i2] : 0.0;
+    /* an eigenvalue that is zero up to rounding is clamped to zero (see fpt_css_eig.cuh); truly negative -> NaN */
+    if (l1 < 0.0 && -l1 <= 1e-13 * fabs(l1)) l1 = 0.0;
+    if (l2 < 0.0 && -l2 <= 1e-13 * fabs(l1)) l2 = 0.0;
+    const double s1 = sqrt(l1), s2 = i2 >= 0 ? sqrt(l2) : 0.0;
     for (int j = threadIdx.x; j < m; j += blockDim.x) {
         X[2 * j] = V[j * m + i1] * s1;
         X[2 * j + 1] = i2 >= 0 ? V[j * m + i2] * s2 : 0.0;

@@ -53,6 +53,18 @@ struct FptEigWork {
 
 FPT_HD int fpt_eig_ld(int m) { return m | 1; }
 
+/* e / m for 0 <= e < m*m, m <= 4096, without an integer division: magic = ceil(2^32 / m) */
+FPT_HD unsigned fpt_div_magic(int m) { return (unsigned)((0x100000000ULL + (unsigned)m - 1) / (unsigned)m); }
+FPT_D int fpt_fastdiv(int e, unsigned magic) { return (int)__umulhi((unsigned)e, magic); }
+
+/* 1/q to full double precision from the single-precision reciprocal and two Newton steps (|q| within float range) */
+FPT_D double fpt_fast_rcp(double q) {
+    double r = (double)(1.0f / (float)q);
+    r = fma(r, fma(-q, r, 1.0), r);
+    r = fma(r, fma(-q, r, 1.0), r);
+    return r;
+}
+
 FPT_HD size_t fpt_eig_work_bytes(int m, int wch) {
     size_t doubles = (size_t)m * fpt_eig_ld(m) + (size_t)5 * m + (size_t)2 * m + (size_t)6 * m;
     size_t bytes = doubles * 8 + (size_t)wch * 2 * m * 4;
@@ -79,13 +91,14 @@ FPT_D FptEigWork fpt_eig_carve(unsigned char *base, int m, int wch) {
 /* ---- step 1a: D (full, mirrored, zero diagonal) from the bit-planes of SNPs [l, r); warp-level twin of fpt_css_counts */
 FPT_D void fpt_warp_counts(const unsigned *__restrict__ planes, int m, int l, int r, const FptEigWork &w) {
     const int lane = threadIdx.x & 31, ld = w.ld;
+    const unsigned magic = fpt_div_magic(m);
     const int w0 = l >> 5, w1 = (r - 1) >> 5, mm = m * m;
-    for (int e = lane; e < mm; e += 32) { const int i = e / m, j = e - i * m; w.A[i * ld + j] = 0.0; }
+    for (int e = lane; e < mm; e += 32) { const int i = fpt_fastdiv(e, magic), j = e - i * m; w.A[i * ld + j] = 0.0; }
     for (int wc = w0; wc <= w1; wc += w.wch) {
         const int nw = min(w.wch, w1 - wc + 1);
         __syncwarp();
         for (int e = lane; e < nw * 2 * m; e += 32) {
-            const int ww = wc + e / (2 * m);
+            const int ww = wc + (e >= 2 * m ? fpt_fastdiv(e, magic) >> 1 : 0);
             unsigned mask = 0xffffffffu;
             if (ww == w0) mask &= 0xffffffffu << (l & 31);
             if (ww == w1) mask &= 0xffffffffu >> (31 - ((r - 1) & 31));
@@ -93,7 +106,7 @@ FPT_D void fpt_warp_counts(const unsigned *__restrict__ planes, int m, int l, in
         }
         __syncwarp();
         for (int e = lane; e < mm; e += 32) {
-            const int i = e / m, j = e - i * m;
+            const int i = fpt_fastdiv(e, magic), j = e - i * m;
             if (j < i) {
                 int cnt = 0;
                 for (int q = 0; q < nw; q++) {
@@ -106,7 +119,7 @@ FPT_D void fpt_warp_counts(const unsigned *__restrict__ planes, int m, int l, in
     }
     __syncwarp();
     for (int e = lane; e < mm; e += 32) {
-        const int i = e / m, j = e - i * m;
+        const int i = fpt_fastdiv(e, magic), j = e - i * m;
         if (j > i) w.A[i * ld + j] = w.A[j * ld + i];
     }
     __syncwarp();
@@ -115,10 +128,11 @@ FPT_D void fpt_warp_counts(const unsigned *__restrict__ planes, int m, int l, in
 /* ---- step 1b: fill_averages (css.c:337-366); returns 1 to keep the window */
 FPT_D int fpt_warp_fill(int m, const FptEigWork &w) {
     const int lane = threadIdx.x & 31, ld = w.ld, mm = m * m;
+    const unsigned magic = fpt_div_magic(m);
     long long blanks = 0;
     double sum = 0.0;
     for (int e = lane; e < mm; e += 32) {
-        const int i = e / m, j = e - i * m;
+        const int i = fpt_fastdiv(e, magic), j = e - i * m;
         const double v = w.A[i * ld + j];
         if (v < 0.00001) blanks++; else sum += v;
     }
@@ -127,20 +141,21 @@ FPT_D int fpt_warp_fill(int m, const FptEigWork &w) {
     if (blanks > (long long)(mm / 2)) return 0;
     const double avg = __ddiv_rn(sum, (double)mm);
     for (int e = lane; e < mm; e += 32) {
-        const int i = e / m, j = e - i * m;
+        const int i = fpt_fastdiv(e, magic), j = e - i * m;
         if (w.A[i * ld + j] < 0.00001) w.A[i * ld + j] = avg;
     }
     __syncwarp();
     return 1;
 }
 
-/* number of eigenvalues of the tridiagonal (d, e2 = e^2) below x: negative pivots of T - xI (LAPACK dstebz scheme) */
+/* number of eigenvalues of the tridiagonal (d, e2 = e^2) below x: negative pivots of T - xI (LAPACK dstebz scheme).
+   Works on the matrix scaled to unit norm, so every pivot is inside single-precision range for the fast reciprocal. */
 FPT_D int fpt_sturm_count(const double *d, const double *e2, int n, double x, double pivmin) {
     double q = d[0] - x;
     int cnt = q < 0.0 ? 1 : 0;
     for (int i = 1; i < n; i++) {
         if (fabs(q) < pivmin) q = -pivmin;
-        q = d[i] - x - e2[i - 1] / q;
+        q = (d[i] - x) - e2[i - 1] * fpt_fast_rcp(q);
         cnt += q < 0.0 ? 1 : 0;
     }
     return cnt;
@@ -149,6 +164,7 @@ FPT_D int fpt_sturm_count(const double *d, const double *e2, int n, double x, do
 /* ---- steps 1c-5. A holds the filled D on entry; X (2m doubles) and evals3 are written by the warp. */
 FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, int want_third) {
     const int lane = threadIdx.x & 31, ld = w.ld, mm = m * m;
+    const unsigned magic = fpt_div_magic(m);
     double *A = w.A;
     if (m == 1) {
         if (lane == 0) { X[0] = 0.0; X[1] = 0.0; if (evals3) { evals3[0] = 0.0; evals3[1] = 0.0; evals3[2] = 0.0; } }
@@ -156,7 +172,7 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
         return;
     }
     /* double centring */
-    for (int e = lane; e < mm; e += 32) { const int i = e / m, j = e - i * m; const double v = A[i * ld + j]; A[i * ld + j] = v * v; }
+    for (int e = lane; e < mm; e += 32) { const int i = fpt_fastdiv(e, magic), j = e - i * m; const double v = A[i * ld + j]; A[i * ld + j] = v * v; }
     __syncwarp();
     for (int i = lane; i < m; i += 32) {
         double s = 0.0;
@@ -168,11 +184,11 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
     for (int i = 0; i < m; i++) g += w.pv[i];
     g /= m;
     for (int e = lane; e < mm; e += 32) {
-        const int i = e / m, j = e - i * m;
+        const int i = fpt_fastdiv(e, magic), j = e - i * m;
         if (j <= i) A[i * ld + j] = -0.5 * (((A[i * ld + j] - w.pv[i]) - w.pv[j]) + g);
     }
     __syncwarp();
-    for (int e = lane; e < mm; e += 32) { const int i = e / m, j = e - i * m; if (j > i) A[i * ld + j] = A[j * ld + i]; }
+    for (int e = lane; e < mm; e += 32) { const int i = fpt_fastdiv(e, magic), j = e - i * m; if (j > i) A[i * ld + j] = A[j * ld + i]; }
     __syncwarp();
 
     /* Householder tridiagonalisation, lower form: H_k = I - tau v v', v(k+1) = 1, v(k+2:) stored in column k */
@@ -224,28 +240,41 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
     }
     __syncwarp();
 
-    /* Gershgorin bounds, squared off-diagonals (into wv), pivot floor */
-    double glo = 1e300, ghi = -1e300, emax = 0.0;
+    /* Gershgorin bounds and the norm used to scale T to O(1): the searches below run on d/tnorm, (e/tnorm)^2 (kept in
+       pv / wv), which keeps every Sturm pivot inside single-precision range for the fast reciprocal */
+    double glo = 1e300, ghi = -1e300;
     for (int i = lane; i < m; i += 32) {
         const double el = i > 0 ? fabs(w.e[i - 1]) : 0.0, er = i < m - 1 ? fabs(w.e[i]) : 0.0;
         glo = fmin(glo, w.d[i] - el - er);
         ghi = fmax(ghi, w.d[i] + el + er);
-        if (i < m - 1) { w.wv[i] = w.e[i] * w.e[i]; emax = fmax(emax, w.wv[i]); }
     }
-    glo = fpt_warp_min(glo); ghi = fpt_warp_max(ghi); emax = fpt_warp_max(emax);
-    __syncwarp();
+    glo = fpt_warp_min(glo); ghi = fpt_warp_max(ghi);
     const double tnorm = fmax(fabs(glo), fabs(ghi));
-    const double pivmin = 2.2250738585072014e-308 * fmax(1.0, emax);
-    const double pad = 2.0 * tnorm * 2.220446049250313e-16 * m + 2.0 * pivmin;
-    glo -= pad; ghi += pad;
+    if (!(tnorm > 0.0) || !(tnorm < 1e300)) {              /* B = 0 (all dissimilarities equal) or not finite */
+        const double v = tnorm == 0.0 ? 0.0 : tnorm - tnorm;   /* 0, or NaN when the input was not finite */
+        for (int j = lane; j < 2 * m; j += 32) X[j] = v;
+        if (lane == 0 && evals3) { evals3[0] = v; evals3[1] = v; evals3[2] = v; }
+        __syncwarp();
+        return;
+    }
+    const double rnorm = 1.0 / tnorm;
+    for (int i = lane; i < m; i += 32) {
+        w.pv[i] = w.d[i] * rnorm;
+        if (i < m - 1) { const double es = w.e[i] * rnorm; w.wv[i] = es * es; }
+    }
+    __syncwarp();
+    const double pivmin = 1e-30;
+    const double pad = 4.0 * 2.220446049250313e-16 * m + 2.0 * pivmin;
+    glo = glo * rnorm - pad; ghi = ghi * rnorm + pad;
 
-    /* two largest eigenvalues at once: lanes 0-15 bracket index m-1, lanes 16-31 index m-2; 17-section */
+    /* two largest eigenvalues at once: lanes 0-15 bracket index m-1, lanes 16-31 index m-2; 17-section.
+       11 rounds shrink the bracket by 17^11 = 3.4e13; the Rayleigh quotient of the converged vector supplies the rest. */
     const int half = lane >> 4, hl = lane & 15;
     const int want = m - 1 - half;                         /* ascending index searched by this half-warp */
     double lo = glo, hi = ghi;
-    for (int round = 0; round < 14; round++) {
+    for (int round = 0; round < 11; round++) {
         const double x = lo + (hi - lo) * ((double)(hl + 1) / 17.0);
-        const int flag = fpt_sturm_count(w.d, w.wv, m, x, pivmin) >= want + 1;
+        const int flag = fpt_sturm_count(w.pv, w.wv, m, x, pivmin) >= want + 1;
         const unsigned bal = (__ballot_sync(FPT_FULL_MASK, flag) >> (16 * half)) & 0xffffu;
         int js = 16;                                       /* first probe already above the eigenvalue */
         for (int b = 0; b < 16; b++) if ((bal >> b) & 1u) { js = b; break; }
@@ -254,15 +283,15 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
         if (js > 0) lo = xl;
         if (js < 16) hi = xh;
     }
-    const double lam_mine = 0.5 * (lo + hi);
-    const double lam1 = __shfl_sync(FPT_FULL_MASK, lam_mine, 0);
-    const double lam2 = __shfl_sync(FPT_FULL_MASK, lam_mine, 16);
+    const double lam_mine = 0.5 * (lo + hi);               /* scaled units */
+    double lam1 = __shfl_sync(FPT_FULL_MASK, lam_mine, 0);
+    double lam2 = __shfl_sync(FPT_FULL_MASK, lam_mine, 16);
     double lam3 = 0.0;
     if (want_third && m >= 3) {                            /* diagnostics only: 33-section, 7 rounds */
         double l3 = glo, h3 = ghi;
         for (int round = 0; round < 7; round++) {
             const double x = l3 + (h3 - l3) * ((double)(lane + 1) / 33.0);
-            const int flag = fpt_sturm_count(w.d, w.wv, m, x, pivmin) >= m - 2;
+            const int flag = fpt_sturm_count(w.pv, w.wv, m, x, pivmin) >= m - 2;
             const unsigned bal = __ballot_sync(FPT_FULL_MASK, flag);
             int js = 32;
             for (int b = 0; b < 32; b++) if ((bal >> b) & 1u) { js = b; break; }
@@ -271,60 +300,71 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
             if (js > 0) l3 = xl;
             if (js < 32) h3 = xh;
         }
-        lam3 = 0.5 * (l3 + h3);
+        lam3 = 0.5 * (l3 + h3) * tnorm;
     }
 
-    /* eigenvectors of T by inverse iteration: lane c (0, 1) owns vector c and its solver arrays */
-    const double epsT = 2.220446049250313e-16 * fmax(tnorm, 1e-300);
+    /* eigenvectors of T (unscaled) by inverse iteration. Lane c (0, 1) owns vector c: T - lam I is factored ONCE
+       (LAPACK dgttrf scheme: partial pivoting, multipliers and swap flags kept, pivots stored as reciprocals), then
+       three solves; the second vector is kept orthogonal to the first; the eigenvalue is polished by the Rayleigh
+       quotient of the converged vector. Per vector: 1/pivot, du, du2 in `lu`, the multipliers in pv / wv (a multiplier of an
+       interchanged row is stored as f + 4). */
+    const double epsT = 2.220446049250313e-16 * tnorm;
+    if (lane < 2) {
+        const int c = lane;
+        const double lam = (c == 0 ? lam1 : lam2) * tnorm;
+        double *dd = w.lu + (size_t)c * 3 * m, *du = dd + m, *du2 = du + m;
+        double *dl = (c == 0 ? w.pv : w.wv);               /* the scaled copies are no longer needed */
+        double *y = w.y + (size_t)c * m;
+        for (int i = 0; i < m; i++) {
+            dd[i] = w.d[i] - lam;
+            if (i < m - 1) { du[i] = w.e[i]; dl[i] = w.e[i]; }
+            du2[i] = 0.0;
+            const unsigned hsh = ((unsigned)i * 2654435761u + (unsigned)c * 40503u + 12345u) >> 8;
+            y[i] = ((double)(hsh & 0xffffu) / 65536.0) - 0.5 + (c == 0 ? 1.0 : 0.0);
+        }
+        for (int i = 0; i < m - 1; i++) {
+            if (fabs(dd[i]) >= fabs(dl[i])) {               /* no interchange */
+                if (dd[i] == 0.0) dd[i] = epsT;
+                const double f = dl[i] / dd[i];
+                dl[i] = f;                                  /* |f| <= 1 */
+                dd[i + 1] -= f * du[i];
+            } else {                                        /* interchange rows i and i+1 */
+                const double f = dd[i] / dl[i];
+                dd[i] = dl[i];
+                dl[i] = f + 4.0;                            /* |f| < 1: a stored value above 2 flags the interchange */
+                const double t = du[i];
+                du[i] = dd[i + 1];
+                dd[i + 1] = t - f * dd[i + 1];
+                if (i < m - 2) { du2[i] = du[i + 1]; du[i + 1] = -f * du[i + 1]; }
+            }
+        }
+        if (dd[m - 1] == 0.0) dd[m - 1] = epsT;
+        for (int i = 0; i < m; i++) dd[i] = 1.0 / dd[i];    /* pivots are only ever divided by */
+    }
+    __syncwarp();
     for (int iter = 0; iter < 3; iter++) {
         if (lane < 2) {
             const int c = lane;
-            const double lam = c == 0 ? lam1 : lam2;
-            double *dd = w.lu + (size_t)c * 3 * m, *du = dd + m, *dl = du + m, *y = w.y + (size_t)c * m;
-            for (int i = 0; i < m; i++) {
-                dd[i] = w.d[i] - lam;
-                if (i < m - 1) { du[i] = w.e[i]; dl[i] = w.e[i]; }
-                if (iter == 0) {
-                    const unsigned hsh = ((unsigned)i * 2654435761u + (unsigned)c * 40503u + 12345u) >> 8;
-                    y[i] = ((double)(hsh & 0xffffu) / 65536.0) - 0.5 + (c == 0 ? 1.0 : 0.0);
-                }
+            const double *rdd = w.lu + (size_t)c * 3 * m, *du = rdd + m, *du2 = du + m;
+            const double *dl = (c == 0 ? w.pv : w.wv);
+            double *y = w.y + (size_t)c * m;
+            for (int i = 0; i < m - 1; i++) {              /* forward: replay interchanges and multipliers (dgtts2) */
+                const double f = dl[i];
+                if (f > 2.0) { const double t = y[i]; y[i] = y[i + 1]; y[i + 1] = t - (f - 4.0) * y[i]; }
+                else y[i + 1] -= f * y[i];
             }
-            /* LAPACK dgtsv elimination with partial pivoting; dl becomes the second super-diagonal */
-            for (int i = 0; i < m - 1; i++) {
-                if (fabs(dd[i]) >= fabs(dl[i])) {
-                    if (dd[i] == 0.0) dd[i] = epsT;
-                    const double f = dl[i] / dd[i];
-                    dd[i + 1] -= f * du[i];
-                    y[i + 1] -= f * y[i];
-                    dl[i] = 0.0;
-                } else {
-                    const double f = dd[i] / dl[i];
-                    dd[i] = dl[i];
-                    double t = dd[i + 1];
-                    dd[i + 1] = du[i] - f * t;
-                    if (i < m - 2) { dl[i] = du[i + 1]; du[i + 1] = -f * dl[i]; } else dl[i] = 0.0;
-                    du[i] = t;
-                    t = y[i]; y[i] = y[i + 1]; y[i + 1] = t - f * y[i + 1];
-                }
-            }
-            if (dd[m - 1] == 0.0) dd[m - 1] = epsT;
-            y[m - 1] /= dd[m - 1];
-            if (m > 1) {
-                if (dd[m - 2] == 0.0) dd[m - 2] = epsT;
-                y[m - 2] = (y[m - 2] - du[m - 2] * y[m - 1]) / dd[m - 2];
-            }
-            for (int i = m - 3; i >= 0; i--) {
-                if (dd[i] == 0.0) dd[i] = epsT;
-                y[i] = (y[i] - du[i] * y[i + 1] - dl[i] * y[i + 2]) / dd[i];
-            }
+            y[m - 1] *= rdd[m - 1];
+            if (m > 1) y[m - 2] = (y[m - 2] - du[m - 2] * y[m - 1]) * rdd[m - 2];
+            for (int i = m - 3; i >= 0; i--) y[i] = (y[i] - du[i] * y[i + 1] - du2[i] * y[i + 2]) * rdd[i];
             double mx = 0.0;
             for (int i = 0; i < m; i++) mx = fmax(mx, fabs(y[i]));
             if (!(mx > 0.0) || !(mx < 1e300)) {            /* overflow / breakdown: restart from a unit vector */
                 for (int i = 0; i < m; i++) y[i] = i == c ? 1.0 : 0.0;
                 mx = 1.0;
             }
+            const double rm = 1.0 / mx;
             double nn = 0.0;
-            for (int i = 0; i < m; i++) { y[i] /= mx; nn += y[i] * y[i]; }
+            for (int i = 0; i < m; i++) { y[i] *= rm; nn += y[i] * y[i]; }
             nn = 1.0 / sqrt(nn);
             for (int i = 0; i < m; i++) y[i] *= nn;
         }
@@ -338,6 +378,16 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
             if (nn > 0.0) { nn = 1.0 / sqrt(nn); for (int i = 0; i < m; i++) y1[i] *= nn; }
         }
         __syncwarp();
+    }
+    {   /* Rayleigh quotients y'Ty of the unit vectors: the eigenvalues to working precision */
+        double rq = 0.0;
+        if (lane < 2) {
+            const double *y = w.y + (size_t)lane * m;
+            for (int i = 0; i < m; i++) rq += w.d[i] * y[i] * y[i];
+            for (int i = 0; i < m - 1; i++) rq += 2.0 * w.e[i] * y[i] * y[i + 1];
+        }
+        lam1 = __shfl_sync(FPT_FULL_MASK, rq, 0);
+        lam2 = __shfl_sync(FPT_FULL_MASK, rq, 1);
     }
 
     /* back-transform: z = H_0 H_1 ... H_{m-3} y, applied last reflector first */
@@ -356,7 +406,12 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
         }
         __syncwarp();
     }
-    const double r1 = sqrt(lam1), r2 = sqrt(lam2);         /* negative eigenvalue -> NaN, as in css.c:558 */
+    /* css.c:558 takes sqrt of the eigenvalues unguarded: a genuinely negative one gives NaN coordinates, as in the
+       reference. An eigenvalue that is zero up to rounding (rank-deficient B, e.g. always with two tracks) is clamped
+       to zero instead of letting the sign of the last bit decide between 0 and NaN. */
+    if (lam1 < 0.0 && -lam1 <= 1e-13 * tnorm) lam1 = 0.0;
+    if (lam2 < 0.0 && -lam2 <= 1e-13 * fmax(fabs(lam1), tnorm * 1e-3)) lam2 = 0.0;
+    const double r1 = sqrt(lam1), r2 = sqrt(lam2);
     for (int j = lane; j < m; j += 32) { X[2 * j] = w.y[j] * r1; X[2 * j + 1] = w.y[m + j] * r2; }
     if (lane == 0 && evals3) { evals3[0] = lam1; evals3[1] = lam2; evals3[2] = lam3; }
     __syncwarp();

@@ -495,6 +495,10 @@ void fpt_oracle_cmds(const double *D, int m, double *X, double evals[3]) {
         else if (i3 < 0 || e > B[i3 * m + i3]) { i3 = i; }
     }
     double l1 = B[i1 * m + i1], l2 = i2 >= 0 ? B[i2 * m + i2] : 0.0, l3 = i3 >= 0 ? B[i3 * m + i3] : 0.0;
+    /* css.c:558 takes these square roots unguarded (negative eigenvalue -> NaN coordinates). Deviation, shared with the
+       product: an eigenvalue that is zero up to rounding (rank-deficient B) is clamped to zero instead of letting the
+       sign of its last bit decide between 0 and NaN. */
+    if (l2 < 0 && -l2 <= 1e-13 * fabs(l1)) l2 = 0.0;
     double s1 = sqrt(l1), s2 = sqrt(l2);
     for (int j = 0; j < m; j++) {
         X[2 * j] = V[j * m + i1] * s1;

@@ -117,6 +117,7 @@ static inline long long __double2ll_rn(double v) { return llrint(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
     return (unsigned long long)(((unsigned __int128)a * b) >> 64);
 }
