@@ -62,6 +62,8 @@ struct DeviceCtx {
     int lf_maxn = -1;
     unsigned long long *rechecks = nullptr;
     bool pool_ready = false;
+    void *pinned[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   /* grow-only host staging */
+    size_t pinned_bytes[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 };
 static DeviceCtx g_ctx[64];
 static std::mutex g_mu;
@@ -115,6 +117,21 @@ static int ensure_lf(DeviceCtx *c, int maxn) {
     if (c->lf) { CU(cudaDeviceSynchronize()); cudaFree(c->lf); }
     c->lf = d;
     c->lf_maxn = want;
+    return FPT_OK;
+}
+
+/* page-locked staging buffers are expensive to create (cudaMallocHost pins pages), so the host entry points keep a few
+   per device and only ever grow them; host entry points are not re-entrant per device (neither is the reference) */
+static int pinned_slot(DeviceCtx *c, int slot, size_t bytes, void **out) {
+    if (bytes > c->pinned_bytes[slot]) {
+        if (c->pinned[slot]) cudaFreeHost(c->pinned[slot]);
+        c->pinned[slot] = nullptr; c->pinned_bytes[slot] = 0;
+        size_t want = std::max<size_t>(bytes + bytes / 4, 1 << 16);
+        cudaError_t e = cudaMallocHost(&c->pinned[slot], want);
+        if (e != cudaSuccess) return fail(FPT_ERR_CUDA, "cudaMallocHost(%zu bytes): %s", want, cudaGetErrorString(e));
+        c->pinned_bytes[slot] = want;
+    }
+    *out = c->pinned[slot];
     return FPT_OK;
 }
 
@@ -272,6 +289,7 @@ extern "C" void fpt_release(void) {
         if (c.binom) cudaFree(c.binom);
         if (c.lf) cudaFree(c.lf);
         if (c.rechecks) cudaFree(c.rechecks);
+        for (int k = 0; k < 8; k++) if (c.pinned[k]) cudaFreeHost(c.pinned[k]);
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
         c = DeviceCtx();
@@ -707,6 +725,45 @@ static int scan_front(Arena &ar, const fpt_genotypes *g, const fpt_scan_range *r
     return FPT_OK;
 }
 
+/* everything after the genotype upload has been enqueued on ar.st */
+static int fet_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const DevGenotypes &d, const fpt_scan_range *r,
+                         double perc, double *scores, double *stddev, uint8_t *written) {
+    cudaStream_t st = ar.st;
+    long long nwin;
+    CHECK(check_range(r, &nwin));
+    ScanFront f;
+    CHECK(scan_front(ar, g, r, &f));
+    int32_t *d_tab = nullptr; double *d_snp = nullptr, *d_sc = nullptr, *d_sd = nullptr; uint8_t *d_fl = nullptr;
+    uint64_t *d_states = nullptr;
+    CHECK(ar.get(&d_tab, (size_t)g->nsnp * 4));
+    CHECK(ar.get(&d_snp, (size_t)g->nsnp));
+    CHECK(ar.get(&d_sc, (size_t)nwin)); CHECK(ar.get(&d_sd, (size_t)nwin)); CHECK(ar.get(&d_fl, (size_t)nwin));
+    if (r->states_resample) {
+        CHECK(ar.get(&d_states, (size_t)nwin));
+        CU(cudaMemcpyAsync(d_states, r->states_resample, (size_t)nwin * 8, cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemsetAsync(d_fl, 0, (size_t)nwin, st));
+    if (d.a64) CHECK(fpt_dev_fet_count_f64(d.a64, d.b64, g->nsnp, g->asize, g->bsize, d_tab, st));
+    else CHECK(fpt_dev_fet_count_i8((const int8_t *)d.a8, (const int8_t *)d.b8, g->nsnp, g->asize, g->bsize, d_tab, st));
+    CHECK(fpt_dev_fet_score(d_tab, g->nsnp, g->asize + g->bsize, 0, d_snp, st));
+    CU(cudaMemcpyAsync(&f.max_npos, f.d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CHECK(fpt_dev_fet_windows(d_snp, f.d_wl, f.d_wr, r, f.max_npos, perc, d_states, d_sc, d_sd, d_fl, st));
+    void *h0, *h1, *h2;
+    CHECK(pinned_slot(c, 0, (size_t)nwin * 8, &h0)); CHECK(pinned_slot(c, 1, (size_t)nwin * 8, &h1));
+    CHECK(pinned_slot(c, 2, (size_t)nwin, &h2));
+    double *h_sc = (double *)h0, *h_sd = (double *)h1; uint8_t *h_fl = (uint8_t *)h2;
+    CU(cudaMemcpyAsync(h_sc, d_sc, (size_t)nwin * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_sd, d_sd, (size_t)nwin * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_fl, d_fl, (size_t)nwin, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (long long w = 0; w < nwin; w++) {                  /* un-scored windows stay as the caller left them */
+        if (h_fl[w]) { scores[w] = h_sc[w]; stddev[w] = h_sd[w]; }
+        if (written) written[w] = h_fl[w];
+    }
+    return FPT_OK;
+}
+
 extern "C" int fpt_fet_scan(const fpt_genotypes *g, const fpt_scan_range *r, double perc, double *scores,
                             double *stddev, uint8_t *written) {
     DeviceCtx *c;
@@ -719,37 +776,83 @@ extern "C" int fpt_fet_scan(const fpt_genotypes *g, const fpt_scan_range *r, dou
     HostStream hs;
     CHECK(hs.make());
     Arena ar(hs.st);
-    ScanFront f;
-    CHECK(scan_front(ar, g, r, &f));                       /* small copies first: the table overlaps the big upload */
     DevGenotypes d;
     CHECK(upload_genotypes(ar, g, &d));
-    int32_t *d_tab; double *d_snp, *d_sc, *d_sd; uint8_t *d_fl; uint64_t *d_states = nullptr;
-    CHECK(ar.get(&d_tab, (size_t)g->nsnp * 4));
-    CHECK(ar.get(&d_snp, (size_t)g->nsnp));
-    CHECK(ar.get(&d_sc, (size_t)nwin)); CHECK(ar.get(&d_sd, (size_t)nwin)); CHECK(ar.get(&d_fl, (size_t)nwin));
-    if (r->states_resample) {
-        CHECK(ar.get(&d_states, (size_t)nwin));
-        CU(cudaMemcpyAsync(d_states, r->states_resample, (size_t)nwin * 8, cudaMemcpyHostToDevice, hs.st));
+    return fet_scan_core(c, ar, g, d, r, perc, scores, stddev, written);
+}
+
+static int css_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const DevGenotypes &d, const fpt_scan_range *r,
+                         int treshold, int runs, int drosophila, int mds, double *scores, double *p, uint8_t *written,
+                         const fpt_css_probes *probes) {
+    cudaStream_t st = ar.st;
+    long long nwin;
+    CHECK(check_range(r, &nwin));
+    const int m = g->asize + g->bsize;
+    ScanFront f;
+    CHECK(scan_front(ar, g, r, &f));
+    uint32_t *d_planes = nullptr; double *d_abs = nullptr;
+    if (drosophila) {
+        CHECK(ar.get(&d_abs, (size_t)g->nsnp));
+        CHECK(fpt_dev_css_absdiff(d.a64, d.b64, g->nsnp, d_abs, st));
+    } else {
+        CHECK(ar.get(&d_planes, fpt_dev_css_planes_bytes(g->nsnp, m) / 4));
+        if (d.a64) CHECK(fpt_dev_css_pack_f64(d.a64, d.b64, g->nsnp, g->asize, g->bsize, d_planes, st));
+        else CHECK(fpt_dev_css_pack_i8((const int8_t *)d.a8, (const int8_t *)d.b8, g->nsnp, g->asize, g->bsize, d_planes, st));
     }
-    CU(cudaMemsetAsync(d_fl, 0, (size_t)nwin, hs.st));
-    if (d.a64) CHECK(fpt_dev_fet_count_f64(d.a64, d.b64, g->nsnp, g->asize, g->bsize, d_tab, hs.st));
-    else CHECK(fpt_dev_fet_count_i8((const int8_t *)d.a8, (const int8_t *)d.b8, g->nsnp, g->asize, g->bsize, d_tab, hs.st));
-    CHECK(fpt_dev_fet_score(d_tab, g->nsnp, g->asize + g->bsize, 0, d_snp, hs.st));
-    CU(cudaMemcpyAsync(&f.max_npos, f.d_max, sizeof(int), cudaMemcpyDeviceToHost, hs.st));
-    CU(cudaStreamSynchronize(hs.st));
-    CHECK(fpt_dev_fet_windows(d_snp, f.d_wl, f.d_wr, r, f.max_npos, perc, d_states, d_sc, d_sd, d_fl, hs.st));
-    double *h_sc, *h_sd; uint8_t *h_fl;
-    CHECK(ar.host(&h_sc, (size_t)nwin)); CHECK(ar.host(&h_sd, (size_t)nwin)); CHECK(ar.host(&h_fl, (size_t)nwin));
-    CU(cudaMemcpyAsync(h_sc, d_sc, (size_t)nwin * 8, cudaMemcpyDeviceToHost, hs.st));
-    CU(cudaMemcpyAsync(h_sd, d_sd, (size_t)nwin * 8, cudaMemcpyDeviceToHost, hs.st));
-    CU(cudaMemcpyAsync(h_fl, d_fl, (size_t)nwin, cudaMemcpyDeviceToHost, hs.st));
-    CU(cudaStreamSynchronize(hs.st));
-    for (long long w = 0; w < nwin; w++) {                  /* un-scored windows stay as the caller left them */
-        if (h_fl[w]) { scores[w] = h_sc[w]; stddev[w] = h_sd[w]; }
-        if (written) written[w] = h_fl[w];
+    const int nruns = mds == 1 ? 4 : (mds == 2 ? 1 : 0);
+    size_t ws_bytes = fpt_dev_css_workspace_bytes(m, nwin, mds);
+    unsigned char *d_ws; double *d_sc, *d_p; uint8_t *d_st;
+    CHECK(ar.get(&d_ws, ws_bytes));
+    CHECK(ar.get(&d_sc, (size_t)nwin)); CHECK(ar.get(&d_p, (size_t)nwin)); CHECK(ar.get(&d_st, (size_t)nwin));
+    CU(cudaMemsetAsync(d_st, 0, (size_t)nwin, st));
+    fpt_scan_range rd = *r;
+    uint64_t *d_s0 = nullptr, *d_s1 = nullptr;
+    if (r->states_resample) { CHECK(ar.get(&d_s0, (size_t)nwin)); CU(cudaMemcpyAsync(d_s0, r->states_resample, (size_t)nwin * 8, cudaMemcpyHostToDevice, st)); }
+    if (r->states_init) { CHECK(ar.get(&d_s1, (size_t)nwin)); CU(cudaMemcpyAsync(d_s1, r->states_init, (size_t)nwin * 8, cudaMemcpyHostToDevice, st)); }
+    rd.states_resample = d_s0; rd.states_init = d_s1;
+    fpt_css_probes dp;
+    memset(&dp, 0, sizeof dp);
+    if (probes) {
+        if (probes->X) CHECK(ar.get(&dp.X, (size_t)nwin * 2 * m));
+        if (probes->evals) CHECK(ar.get(&dp.evals, (size_t)nwin * 3));
+        if (probes->hits) CHECK(ar.get(&dp.hits, (size_t)nwin));
+        if (probes->nperm) CHECK(ar.get(&dp.nperm, (size_t)nwin));
+        if (probes->smacof_iters && nruns) CHECK(ar.get(&dp.smacof_iters, (size_t)nwin * nruns));
+        if (probes->smacof_sigma && nruns) CHECK(ar.get(&dp.smacof_sigma, (size_t)nwin * nruns));
+        if (dp.hits) CU(cudaMemsetAsync(dp.hits, 0, (size_t)nwin * 4, st));
+        if (dp.nperm) CU(cudaMemsetAsync(dp.nperm, 0, (size_t)nwin * 4, st));
+        if (dp.X) CU(cudaMemsetAsync(dp.X, 0, (size_t)nwin * 2 * m * 8, st));
+    }
+    CHECK(fpt_dev_css_windows(d_planes, d_abs, g->asize, g->bsize, f.d_wl, f.d_wr, &rd, treshold, runs, mds, d_ws, ws_bytes,
+                              d_sc, d_p, d_st, probes ? &dp : nullptr, st));
+    double *h_sc, *h_p; uint8_t *h_st;
+    void *h0, *h1, *h2;
+    CHECK(pinned_slot(c, 0, (size_t)nwin * 8, &h0)); CHECK(pinned_slot(c, 1, (size_t)nwin * 8, &h1));
+    CHECK(pinned_slot(c, 2, (size_t)nwin, &h2));
+    h_sc = (double *)h0; h_p = (double *)h1; h_st = (uint8_t *)h2;
+    CU(cudaMemcpyAsync(h_sc, d_sc, (size_t)nwin * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_p, d_p, (size_t)nwin * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_st, d_st, (size_t)nwin, cudaMemcpyDeviceToHost, st));
+    if (probes) {
+        if (probes->X) CU(cudaMemcpyAsync(probes->X, dp.X, (size_t)nwin * 2 * m * 8, cudaMemcpyDeviceToHost, st));
+        if (probes->evals) CU(cudaMemcpyAsync(probes->evals, dp.evals, (size_t)nwin * 3 * 8, cudaMemcpyDeviceToHost, st));
+        if (probes->hits) CU(cudaMemcpyAsync(probes->hits, dp.hits, (size_t)nwin * 4, cudaMemcpyDeviceToHost, st));
+        if (probes->nperm) CU(cudaMemcpyAsync(probes->nperm, dp.nperm, (size_t)nwin * 4, cudaMemcpyDeviceToHost, st));
+        if (probes->smacof_iters && nruns) CU(cudaMemcpyAsync(probes->smacof_iters, dp.smacof_iters, (size_t)nwin * nruns * 4, cudaMemcpyDeviceToHost, st));
+        if (probes->smacof_sigma && nruns) CU(cudaMemcpyAsync(probes->smacof_sigma, dp.smacof_sigma, (size_t)nwin * nruns * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    for (long long w = 0; w < nwin; w++) {
+        /* css.c:126-132: score and p are stored only when the scorer did not return -1. -1 is the reference's
+           "window discarded" sentinel, so a window whose score happens to BE exactly -1.0 is dropped too. */
+        const bool store = h_st[w] == FPT_WIN_SCORED && h_sc[w] != -1.0;
+        if (store) { scores[w] = h_sc[w]; p[w] = h_p[w]; }
+        if (written) written[w] = store;
+        if (probes && probes->status) probes->status[w] = h_st[w];
     }
     return FPT_OK;
 }
+
 
 extern "C" int fpt_css_scan(const fpt_genotypes *g, const fpt_scan_range *r, int treshold, int runs, int drosophila,
                             int mds, double *scores, double *p, uint8_t *written, const fpt_css_probes *probes) {
@@ -768,70 +871,12 @@ extern "C" int fpt_css_scan(const fpt_genotypes *g, const fpt_scan_range *r, int
     if (mds < 0 || mds > 2) return fail(FPT_ERR_ARG, "css: mds must be 0, 1 or 2 (got %d)", mds);
     if (nwin == 0 || g->nsnp == 0) return FPT_OK;
     if (!g->pos || !scores || !p) return fail(FPT_ERR_ARG, "css_scan: positions and both outputs are required");
-    const int m = g->asize + g->bsize;
     HostStream hs;
     CHECK(hs.make());
     Arena ar(hs.st);
-    ScanFront f;
-    CHECK(scan_front(ar, g, r, &f));
     DevGenotypes d;
     CHECK(upload_genotypes(ar, g, &d));
-    uint32_t *d_planes = nullptr; double *d_abs = nullptr;
-    if (drosophila) {
-        CHECK(ar.get(&d_abs, (size_t)g->nsnp));
-        CHECK(fpt_dev_css_absdiff(d.a64, d.b64, g->nsnp, d_abs, hs.st));
-    } else {
-        CHECK(ar.get(&d_planes, fpt_dev_css_planes_bytes(g->nsnp, m) / 4));
-        if (d.a64) CHECK(fpt_dev_css_pack_f64(d.a64, d.b64, g->nsnp, g->asize, g->bsize, d_planes, hs.st));
-        else CHECK(fpt_dev_css_pack_i8((const int8_t *)d.a8, (const int8_t *)d.b8, g->nsnp, g->asize, g->bsize, d_planes, hs.st));
-    }
-    const int nruns = mds == 1 ? 4 : (mds == 2 ? 1 : 0);
-    size_t ws_bytes = fpt_dev_css_workspace_bytes(m, nwin, mds);
-    unsigned char *d_ws; double *d_sc, *d_p; uint8_t *d_st;
-    CHECK(ar.get(&d_ws, ws_bytes));
-    CHECK(ar.get(&d_sc, (size_t)nwin)); CHECK(ar.get(&d_p, (size_t)nwin)); CHECK(ar.get(&d_st, (size_t)nwin));
-    CU(cudaMemsetAsync(d_st, 0, (size_t)nwin, hs.st));
-    fpt_scan_range rd = *r;
-    uint64_t *d_s0 = nullptr, *d_s1 = nullptr;
-    if (r->states_resample) { CHECK(ar.get(&d_s0, (size_t)nwin)); CU(cudaMemcpyAsync(d_s0, r->states_resample, (size_t)nwin * 8, cudaMemcpyHostToDevice, hs.st)); }
-    if (r->states_init) { CHECK(ar.get(&d_s1, (size_t)nwin)); CU(cudaMemcpyAsync(d_s1, r->states_init, (size_t)nwin * 8, cudaMemcpyHostToDevice, hs.st)); }
-    rd.states_resample = d_s0; rd.states_init = d_s1;
-    fpt_css_probes dp;
-    memset(&dp, 0, sizeof dp);
-    if (probes) {
-        if (probes->X) CHECK(ar.get(&dp.X, (size_t)nwin * 2 * m));
-        if (probes->evals) CHECK(ar.get(&dp.evals, (size_t)nwin * 3));
-        if (probes->hits) CHECK(ar.get(&dp.hits, (size_t)nwin));
-        if (probes->nperm) CHECK(ar.get(&dp.nperm, (size_t)nwin));
-        if (probes->smacof_iters && nruns) CHECK(ar.get(&dp.smacof_iters, (size_t)nwin * nruns));
-        if (probes->smacof_sigma && nruns) CHECK(ar.get(&dp.smacof_sigma, (size_t)nwin * nruns));
-        if (dp.hits) CU(cudaMemsetAsync(dp.hits, 0, (size_t)nwin * 4, hs.st));
-        if (dp.nperm) CU(cudaMemsetAsync(dp.nperm, 0, (size_t)nwin * 4, hs.st));
-        if (dp.X) CU(cudaMemsetAsync(dp.X, 0, (size_t)nwin * 2 * m * 8, hs.st));
-    }
-    CHECK(fpt_dev_css_windows(d_planes, d_abs, g->asize, g->bsize, f.d_wl, f.d_wr, &rd, treshold, runs, mds, d_ws, ws_bytes,
-                              d_sc, d_p, d_st, probes ? &dp : nullptr, hs.st));
-    double *h_sc, *h_p; uint8_t *h_st;
-    CHECK(ar.host(&h_sc, (size_t)nwin)); CHECK(ar.host(&h_p, (size_t)nwin)); CHECK(ar.host(&h_st, (size_t)nwin));
-    CU(cudaMemcpyAsync(h_sc, d_sc, (size_t)nwin * 8, cudaMemcpyDeviceToHost, hs.st));
-    CU(cudaMemcpyAsync(h_p, d_p, (size_t)nwin * 8, cudaMemcpyDeviceToHost, hs.st));
-    CU(cudaMemcpyAsync(h_st, d_st, (size_t)nwin, cudaMemcpyDeviceToHost, hs.st));
-    if (probes) {
-        if (probes->X) CU(cudaMemcpyAsync(probes->X, dp.X, (size_t)nwin * 2 * m * 8, cudaMemcpyDeviceToHost, hs.st));
-        if (probes->evals) CU(cudaMemcpyAsync(probes->evals, dp.evals, (size_t)nwin * 3 * 8, cudaMemcpyDeviceToHost, hs.st));
-        if (probes->hits) CU(cudaMemcpyAsync(probes->hits, dp.hits, (size_t)nwin * 4, cudaMemcpyDeviceToHost, hs.st));
-        if (probes->nperm) CU(cudaMemcpyAsync(probes->nperm, dp.nperm, (size_t)nwin * 4, cudaMemcpyDeviceToHost, hs.st));
-        if (probes->smacof_iters && nruns) CU(cudaMemcpyAsync(probes->smacof_iters, dp.smacof_iters, (size_t)nwin * nruns * 4, cudaMemcpyDeviceToHost, hs.st));
-        if (probes->smacof_sigma && nruns) CU(cudaMemcpyAsync(probes->smacof_sigma, dp.smacof_sigma, (size_t)nwin * nruns * 8, cudaMemcpyDeviceToHost, hs.st));
-    }
-    CU(cudaStreamSynchronize(hs.st));
-    for (long long w = 0; w < nwin; w++) {
-        /* css.c:126-132: score and p are stored only when the scorer did not return -1 */
-        if (h_st[w] == FPT_WIN_SCORED) { scores[w] = h_sc[w]; p[w] = h_p[w]; }
-        if (written) written[w] = h_st[w] == FPT_WIN_SCORED;
-        if (probes && probes->status) probes->status[w] = h_st[w];
-    }
-    return FPT_OK;
+    return css_scan_core(c, ar, g, d, r, treshold, runs, drosophila, mds, scores, p, written, probes);
 }
 
 /* ------------------------------------------------------------------------------------------------ drop-ins */
@@ -843,20 +888,12 @@ static int population_size(const int *pos, int len) {
     return n;
 }
 
-/* reference layout -> one position per SNP; verifies that A and B describe the same SNPs */
-static int unique_positions(const int *apos, const int *bpos, int alen, int blen, int *asize, int *bsize,
-                            std::vector<int32_t> *pos) {
-    if (alen <= 0 || blen <= 0 || !apos || !bpos) return fail(FPT_ERR_ARG, "empty position arrays");
-    *asize = population_size(apos, alen);
-    *bsize = population_size(bpos, blen);
-    const long long na = alen / *asize, nb = blen / *bsize;
-    if (na != nb)
-        return fail(FPT_ERR_POSITIONS, "population A has %lld SNPs (%d individuals), B has %lld (%d individuals)", na, *asize, nb, *bsize);
-    pos->resize((size_t)na);
-    for (long long k = 0; k < na; k++) {
-        const int pa = apos[k * *asize];
-        if (pa != bpos[k * *bsize]) return fail(FPT_ERR_POSITIONS, "SNP %lld: position %d in A but %d in B", k, pa, bpos[k * *bsize]);
-        (*pos)[(size_t)k] = pa;
+/* reference layout -> one position per SNP (into pinned staging); verifies that A and B describe the same SNPs */
+static int gather_positions(const int *apos, const int *bpos, int asize, int bsize, long long nsnp, int32_t *pos) {
+    for (long long k = 0; k < nsnp; k++) {
+        const int pa = apos[k * asize];
+        if (pa != bpos[k * bsize]) return fail(FPT_ERR_POSITIONS, "SNP %lld: position %d in A but %d in B", k, pa, bpos[k * bsize]);
+        pos[k] = pa;
     }
     return FPT_OK;
 }
@@ -871,28 +908,50 @@ static fpt_scan_range full_range(int regend, int wsize, int wstep, int semantics
     return r;
 }
 
-static int fet_dropin(double *avals, double *bvals, int *apos, int *bpos, int regend, int wsize, int wstep, int alen,
-                      int blen, double perc, double *scores, double *stddev, int semantics) {
+/* Shared by the four drop-ins: population sizes from the run length of the first position (get_population_size,
+   comparative.c:25-34), the float64 genotype upload enqueued FIRST so that the host-side gather of one position per
+   SNP (and the A/B consistency check) overlaps the DMA, then the scan proper. */
+static int dropin(int css, double *avals, double *bvals, int *apos, int *bpos, int regend, int wsize, int wstep, int alen,
+                  int blen, double perc, int treshold, int runs, int drosophila, int mds, double *out0, double *out1,
+                  int semantics) {
+    DeviceCtx *c;
+    CHECK(get_ctx(&c));
     if (wsize <= 0 || wstep <= 0) return fail(FPT_ERR_ARG, "bad window geometry wsize=%d wstep=%d", wsize, wstep);
+    if (alen <= 0 || blen <= 0 || !apos || !bpos || !avals || !bvals || !out0 || !out1) return fail(FPT_ERR_ARG, "empty or NULL arrays");
     fpt_genotypes g;
     memset(&g, 0, sizeof g);
-    std::vector<int32_t> pos;
-    CHECK(unique_positions(apos, bpos, alen, blen, &g.asize, &g.bsize, &pos));
-    g.avals = avals; g.bvals = bvals; g.pos = pos.data(); g.nsnp = (int64_t)pos.size();
+    g.asize = population_size(apos, alen);
+    g.bsize = population_size(bpos, blen);
+    const long long na = alen / g.asize, nb = blen / g.bsize;
+    if (na != nb)
+        return fail(FPT_ERR_POSITIONS, "population A has %lld SNPs (%d individuals), B has %lld (%d individuals)", na, g.asize, nb, g.bsize);
+    if (css && drosophila && (g.asize != 1 || g.bsize != 1))
+        return fail(FPT_ERR_ARG, "the frequency metric takes one track per population (got %d+%d)", g.asize, g.bsize);
+    g.avals = avals; g.bvals = bvals; g.nsnp = na;
     fpt_scan_range r = full_range(regend, wsize, wstep, semantics);
-    return fpt_fet_scan(&g, &r, perc, scores, stddev, nullptr);
+    if (r.window_end == 0) return FPT_OK;
+    HostStream hs;
+    CHECK(hs.make());
+    Arena ar(hs.st);
+    DevGenotypes d;
+    CHECK(upload_genotypes(ar, &g, &d));                   /* asynchronous when the caller's arrays are page-locked */
+    void *hpos;
+    CHECK(pinned_slot(c, 3, (size_t)na * sizeof(int32_t), &hpos));
+    CHECK(gather_positions(apos, bpos, g.asize, g.bsize, na, (int32_t *)hpos));
+    g.pos = (const int32_t *)hpos;
+    if (css) return css_scan_core(c, ar, &g, d, &r, treshold, runs, drosophila, mds, out0, out1, nullptr, nullptr);
+    return fet_scan_core(c, ar, &g, d, &r, perc, out0, out1, nullptr);
+}
+
+static int fet_dropin(double *avals, double *bvals, int *apos, int *bpos, int regend, int wsize, int wstep, int alen,
+                      int blen, double perc, double *scores, double *stddev, int semantics) {
+    return dropin(0, avals, bvals, apos, bpos, regend, wsize, wstep, alen, blen, perc, 0, 0, 0, 0, scores, stddev, semantics);
 }
 
 static int css_dropin(double *avals, double *bvals, int *apos, int *bpos, int regend, int wsize, int wstep, int alen,
                       int blen, int treshold, int runs, int drosophila, int mds, double *scores, double *p, int semantics) {
-    if (wsize <= 0 || wstep <= 0) return fail(FPT_ERR_ARG, "bad window geometry wsize=%d wstep=%d", wsize, wstep);
-    fpt_genotypes g;
-    memset(&g, 0, sizeof g);
-    std::vector<int32_t> pos;
-    CHECK(unique_positions(apos, bpos, alen, blen, &g.asize, &g.bsize, &pos));
-    g.avals = avals; g.bvals = bvals; g.pos = pos.data(); g.nsnp = (int64_t)pos.size();
-    fpt_scan_range r = full_range(regend, wsize, wstep, semantics);
-    return fpt_css_scan(&g, &r, treshold, runs, drosophila, mds, scores, p, nullptr, nullptr);
+    if (mds < 0 || mds > 2) return fail(FPT_ERR_ARG, "css: mds must be 0, 1 or 2 (got %d)", mds);
+    return dropin(1, avals, bvals, apos, bpos, regend, wsize, wstep, alen, blen, 0.0, treshold, runs, drosophila, mds, scores, p, semantics);
 }
 
 /* regstart is accepted and ignored, as in the reference (windows always start at 0) */
