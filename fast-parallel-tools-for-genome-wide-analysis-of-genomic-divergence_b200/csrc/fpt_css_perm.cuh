@@ -38,8 +38,11 @@ FPT_HD int fpt_perm_row_stride(int m) {   /* bytes; a multiple of 4 whose word c
     return w << 2;
 }
 
+FPT_HD int fpt_css_perm2_uses_mma(int m) { return m >= 8 && m <= 64; }
+
 FPT_HD size_t fpt_css_perm2_smem_bytes(int m, int nthreads, int chain) {
     size_t off = (size_t)m * m * 8;                       /* dist */
+    if (fpt_css_perm2_uses_mma(m)) off += (size_t)3 * (((m + 7) >> 3) << 3) * 80;   /* digit matrices, FPT_QD_STRIDE */
     off += (size_t)m * m * 4;                             /* q */
     off += (size_t)m * 4;                                 /* rowsum_q */
     off += (size_t)2 * m * 8;                             /* X */
@@ -87,6 +90,99 @@ FPT_D void fpt_surrogate(const unsigned *q, const int *rowsum, int m, const unsi
     wa = a; wb = b;
 }
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Tensor-core form of the between-group sum (cohorts of up to 64 individuals).
+ *
+ * For 16 permutations at a time,  R = Z Q  with Z (16 x m) the 0/1 membership of the smaller group G and Q the m x m
+ * matrix of quantised distances, then  sum_{A'xB'} q = sum_j (1 - z_j) R_j.  Q is split into three base-256 digits
+ * so that the product runs on the integer tensor cores (mma.sync m16n8k32, u8 x u8 -> s32) and stays EXACT — the
+ * surrogate keeps its "no rounding at all" property. This replaces |G| + |G|(|G|-1)/2 scattered shared-memory gathers
+ * per permutation by ~4 conflict-free fragment loads and 2 MMAs.
+ *
+ * Fragment layout (PTX ISA, m16n8k32 with 8-bit operands; g = lane/4, t = lane%4):
+ *   A (16x32, row): a0 = row g,   cols 4t..4t+3;  a1 = row g+8, cols 4t..4t+3;  a2/a3 = same rows, cols 16+4t..
+ *   B (32x8,  col): b0 = rows 4t..4t+3 of column g;  b1 = rows 16+4t.. of column g
+ *   C (16x8):       c0,c1 = row g, cols 2t,2t+1;     c2,c3 = row g+8, cols 2t,2t+1
+ */
+#define FPT_QD_STRIDE 80          /* bytes per digit row: 64 + 16 padding -> the 8 column groups hit disjoint banks */
+
+#ifndef FPT_EMU
+FPT_D void fpt_mma_u8(int (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+#else
+/* CPU emulation of the warp-wide MMA with the layout documented above (tests/emu) */
+static inline void fpt_mma_u8(int (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    const uint32_t regs[6] = { a[0], a[1], a[2], a[3], b0, b1 };
+    const uint32_t (*all)[8] = emu_warp_publish(regs, 6);
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int i = 0; i < 4; i++) {
+        const int row = g + 8 * (i >> 1), col = 2 * t + (i & 1);
+        int acc = c[i];
+        for (int k = 0; k < 32; k++) {
+            /* A(row, k): register (row>>3) + 2*(k>>4) of lane (row&7)*4 + ((k&15)>>2), byte k&3 */
+            const int av = (int)((all[(row & 7) * 4 + ((k & 15) >> 2)][(row >> 3) + 2 * (k >> 4)] >> (8 * (k & 3))) & 0xffu);
+            /* B(k, col): register 4 + (k>>4) of lane col*4 + ((k&15)>>2), byte k&3 */
+            const int bv = (int)((all[col * 4 + ((k & 15) >> 2)][4 + (k >> 4)] >> (8 * (k & 3))) & 0xffu);
+            acc += av * bv;
+        }
+        c[i] = acc;
+    }
+    emu_warp_release();
+}
+#endif
+
+/* four membership bits -> four 0/1 bytes */
+FPT_D unsigned fpt_nibble_to_bytes(unsigned nib) { return ((nib & 0xfu) * 0x00204081u) & 0x01010101u; }
+
+/* sum over A'xB' of q for the permutation owned by THIS lane, computed cooperatively by the warp.
+   gmask = membership mask of the smaller group for this lane's permutation (0 for an idle lane);
+   qd = digit matrices [3][nrows][FPT_QD_STRIDE], nrows = m rounded up to 8. */
+FPT_D int fpt_bet_mma(unsigned long long gmask, const unsigned char *qd, int m) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int ntiles = (m + 7) >> 3, nrows = ntiles << 3, ksteps = (m + 31) >> 5;
+    int mine = 0;
+    for (int tile = 0; tile < 2; tile++) {              /* permutations of lanes 16*tile .. 16*tile+15 */
+        const unsigned long long m1 = __shfl_sync(FPT_FULL_MASK, gmask, 16 * tile + g);
+        const unsigned long long m2 = __shfl_sync(FPT_FULL_MASK, gmask, 16 * tile + g + 8);
+        unsigned a[2][4];
+        for (int ks = 0; ks < 2; ks++) {
+            a[ks][0] = fpt_nibble_to_bytes((unsigned)(m1 >> (32 * ks + 4 * t)));
+            a[ks][1] = fpt_nibble_to_bytes((unsigned)(m2 >> (32 * ks + 4 * t)));
+            a[ks][2] = fpt_nibble_to_bytes((unsigned)(m1 >> (32 * ks + 16 + 4 * t)));
+            a[ks][3] = fpt_nibble_to_bytes((unsigned)(m2 >> (32 * ks + 16 + 4 * t)));
+        }
+        int s1 = 0, s2 = 0;                             /* masked row sums of rows g and g+8 */
+        for (int nt = 0; nt < ntiles; nt++) {
+            int r[4] = { 0, 0, 0, 0 };
+            for (int d = 2; d >= 0; d--) {
+                int c[4] = { 0, 0, 0, 0 };
+                const unsigned char *row = qd + ((size_t)d * nrows + (size_t)(8 * nt + g)) * FPT_QD_STRIDE + 4 * t;
+                for (int ks = 0; ks < ksteps; ks++) {
+                    const unsigned b0 = *reinterpret_cast<const unsigned *>(row + 32 * ks);
+                    const unsigned b1 = *reinterpret_cast<const unsigned *>(row + 32 * ks + 16);
+                    fpt_mma_u8(c, a[ks], b0, b1);
+                }
+                for (int i = 0; i < 4; i++) r[i] = (r[i] << 8) + c[i];
+            }
+            const int j0 = 8 * nt + 2 * t;                 /* columns held by this lane; padded columns are zero */
+            if (!((m1 >> j0) & 1ULL)) s1 += r[0];
+            if (!((m1 >> (j0 + 1)) & 1ULL)) s1 += r[1];
+            if (!((m2 >> j0) & 1ULL)) s2 += r[2];
+            if (!((m2 >> (j0 + 1)) & 1ULL)) s2 += r[3];
+        }
+        s1 += __shfl_xor_sync(FPT_FULL_MASK, s1, 1); s1 += __shfl_xor_sync(FPT_FULL_MASK, s1, 2);
+        s2 += __shfl_xor_sync(FPT_FULL_MASK, s2, 1); s2 += __shfl_xor_sync(FPT_FULL_MASK, s2, 2);
+        const int myrow = lane & 15;                        /* my permutation's row inside its tile */
+        const int v1 = __shfl_sync(FPT_FULL_MASK, s1, 4 * (myrow & 7));
+        const int v2 = __shfl_sync(FPT_FULL_MASK, s2, 4 * (myrow & 7));
+        if ((lane >> 4) == tile) mine = myrow < 8 ? v1 : v2;
+    }
+    return mine;
+}
+
 __global__ void __launch_bounds__(256, 4)
 fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsize, long long wbase, long long nwin,
                      const unsigned char *__restrict__ status, int treshold, int runs, uint64_t seed,
@@ -97,6 +193,9 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
     const int T = blockDim.x, tid = threadIdx.x, RS = fpt_perm_row_stride(m);
     size_t off = 0;
     double *dist = (double *)(smem + off); off += (size_t)m * m * 8;
+    const int use_mma = fpt_css_perm2_uses_mma(m);
+    const int qd_rows = ((m + 7) >> 3) << 3;
+    unsigned char *qd = smem + off; if (use_mma) off += (size_t)3 * qd_rows * FPT_QD_STRIDE;
     unsigned *q = (unsigned *)(smem + off); off += (size_t)m * m * 4;
     int *rowsum = (int *)(smem + off); off += (size_t)m * 4;
     double *X = (double *)(smem + off); off += (size_t)2 * m * 8;
@@ -154,6 +253,18 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
             q[e] = usable && d == d ? (unsigned)__double2ll_rn(d * S) : 0u;
         }
         const bool use_surrogate = usable && !__syncthreads_or(bad);
+        if (use_mma) {                                      /* base-256 digits of q, zero padded to 8-row / 64-column tiles */
+            for (int e = tid; e < 3 * qd_rows * 16; e += T) {
+                const int d = e / (qd_rows * 16), rem = e - d * qd_rows * 16, n = rem >> 4, k4 = (rem & 15) << 2;
+                unsigned wv = 0;
+                for (int b = 0; b < 4; b++) {
+                    const int k = k4 + b;
+                    const unsigned v = (n < m && k < m) ? ((q[n * m + k] >> (8 * d)) & 0xffu) : 0u;
+                    wv |= v << (8 * b);
+                }
+                *reinterpret_cast<unsigned *>(qd + ((size_t)d * qd_rows + n) * FPT_QD_STRIDE + k4) = wv;
+            }
+        }
         for (int i = tid; i < m; i += T) {
             int s = 0;
             for (int j = 0; j < m; j++) s += (int)q[i * m + j];
@@ -229,25 +340,45 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
             /* pass 2 (the only pass without the chain): shuffle, score, decide */
             int myhits = 0, hitmask = 0;
             bool resync = false;
-            for (int j = 0; j < mycount; j++) {
+            /* warps whose 32 x PP permutations all lie beyond the chunk skip the loop; inside, every lane runs every
+               iteration because the tensor-core path is a warp-wide operation (idle lanes contribute empty masks) */
+            const bool warp_active = (tid & ~31) * FPT_PERM_PP < nvalid;
+            for (int j = 0; warp_active && j < FPT_PERM_PP; j++) {
+                const bool valid = j < mycount;
                 int used = 0;
-                if (!chain) {
-                    fpt_identity_row(mine, m);
-                    /* the stream of permutation k starts k*(m-1) draws in; after a shuffle without a rejected draw the
-                       state already sits at the next permutation's start */
-                    if (j == 0 || resync) st = fpt_lcg_skip(st_win, (uint64_t)(ndone + first + j) * (uint64_t)draws);
+                if (valid) {
+                    if (!chain) {
+                        fpt_identity_row(mine, m);
+                        /* the stream of permutation k starts k*(m-1) draws in; after a shuffle without a rejected draw the
+                           state already sits at the next permutation's start */
+                        if (j == 0 || resync) st = fpt_lcg_skip(st_win, (uint64_t)(ndone + first + j) * (uint64_t)draws);
+                    }
+                    fpt_shuffle_row(mine, m, st, used);
+                    resync = used != draws;
                 }
-                fpt_shuffle_row(mine, m, st, used);
-                resync = used != draws;
-                int hit;
-                bool exact = !use_surrogate;
+                int hit = 0;
+                bool exact = valid && !use_surrogate;
                 if (use_surrogate) {
-                    long long bet; int wa, wb;
-                    fpt_surrogate(q, rowsum, m, mine, asize, bsize, use_a, bet, wa, wb);
-                    const double approx = (double)bet * c_bet - (a_ + b_) * ((double)wa * c_wa + (double)wb * c_wb);
-                    const double diff = approx - score;
-                    hit = diff > 0.0;
-                    exact = !(fabs(diff) > E);
+                    long long bet = 0; int wa = 0, wb = 0;
+                    if (use_mma) {
+                        unsigned long long gmask = 0ULL;
+                        if (valid) {
+                            const unsigned char *gr = use_a ? mine : mine + asize;
+                            const int ng = use_a ? asize : bsize;
+                            for (int i = 0; i < ng; i++) gmask |= 1ULL << gr[i];
+                            for (int i = 0; i + 1 < asize; i++) wa += (int)q[mine[i] * m + mine[i + 1]];
+                            for (int i = 0; i + 1 < bsize; i++) wb += (int)q[mine[asize + i] * m + mine[asize + i + 1]];
+                        }
+                        bet = (long long)fpt_bet_mma(gmask, qd, m);
+                    } else if (valid) {
+                        fpt_surrogate(q, rowsum, m, mine, asize, bsize, use_a, bet, wa, wb);
+                    }
+                    if (valid) {
+                        const double approx = (double)bet * c_bet - (a_ + b_) * ((double)wa * c_wa + (double)wb * c_wb);
+                        const double diff = approx - score;
+                        hit = diff > 0.0;
+                        exact = !(fabs(diff) > E);
+                    }
                 }
                 if (exact) {
                     hit = fpt_css_score<unsigned char>(dist, m, mine, mine + asize, asize, bsize) >= score ? 1 : 0;

@@ -40,6 +40,7 @@ struct Cta {
     pthread_barrier_t bar;
     pthread_barrier_t *warp_bar;
     uint64_t (*slots)[32];
+    uint32_t (*wide)[32][8];     /* one 8-register record per lane: warp-wide publish for emulated MMA */
     unsigned nthreads;
 };
 extern Cta *g_cta;
@@ -81,6 +82,15 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d) {
 template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d) {
     int l = emu::t_threadIdx.x % 32; return emu_exchange(v, l - d >= 0 ? l - d : l);
 }
+/* every lane publishes n <= 8 registers; returns a pointer to the warp's [32][8] table (valid until emu_warp_release) */
+static inline const uint32_t (*emu_warp_publish(const uint32_t *regs, int n))[8] {
+    unsigned w = emu::t_threadIdx.x / 32, l = emu::t_threadIdx.x % 32;
+    for (int i = 0; i < n; i++) emu::g_cta->wide[w][l][i] = regs[i];
+    pthread_barrier_wait(&emu::g_cta->warp_bar[w]);
+    return emu::g_cta->wide[w];
+}
+static inline void emu_warp_release() { pthread_barrier_wait(&emu::g_cta->warp_bar[emu::t_threadIdx.x / 32]); }
+
 static inline unsigned __ballot_sync(unsigned, int pred) {
     unsigned w = emu::t_threadIdx.x / 32, l = emu::t_threadIdx.x % 32;
     emu::g_cta->slots[w][l] = pred ? 1 : 0;
@@ -191,6 +201,7 @@ inline void launch(unsigned nblocks, unsigned nthreads, size_t dyn_smem, void (*
         pthread_barrier_init(&cta.warp_bar[w], 0, cnt);
     }
     cta.slots = (uint64_t(*)[32])calloc(nwarps, sizeof(uint64_t[32]));
+    cta.wide = (uint32_t(*)[32][8])calloc(nwarps, sizeof(uint32_t[32][8]));
     g_cta = &cta;
     g_blockDim = dim3(nthreads, 1, 1);
     g_gridDim = dim3(nblocks, 1, 1);
@@ -213,7 +224,7 @@ inline void launch(unsigned nblocks, unsigned nthreads, size_t dyn_smem, void (*
     pthread_barrier_destroy(&ctx.gate);
     pthread_barrier_destroy(&cta.bar);
     for (unsigned w = 0; w < nwarps; w++) pthread_barrier_destroy(&cta.warp_bar[w]);
-    free(cta.warp_bar); free(cta.slots); free(g_dyn_smem);
+    free(cta.warp_bar); free(cta.slots); free(cta.wide); free(g_dyn_smem);
     g_cta = 0; g_dyn_smem = 0;
 }
 

@@ -157,8 +157,11 @@ def test_css_scan_matches_oracle(fpt, oracle, mds, shape):
     s_o, p_o = _css_oracle_scan(oracle, av, bv, apos, bpos, regend, wsize, wstep, 10, 200, mds, 0, seed)
     s_g, p_g, wr, pr = fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 10, 200, mds=mds,
                                     seed=seed, probes=True)
-    assert np.array_equal(wr == 1, p_o != 0)                     # same windows scored / discarded
-    finite = np.isfinite(s_o) & np.isfinite(s_g)
+    # same windows scored / discarded — except where the score is the reference's own "discarded" sentinel -1.0
+    # (css.c:126: `if (result != -1)`), which a 2+2 toy cohort can hit exactly and where the last bit decides
+    near_sentinel = (pr["status"] == 2) & (np.abs(np.where(wr == 1, s_g, -1.0) + 1.0) < 1e-9)
+    assert np.array_equal((wr == 1) | near_sentinel, (p_o != 0) | near_sentinel)
+    finite = np.isfinite(s_o) & np.isfinite(s_g) & ~near_sentinel
     if mds != 1:
         # with lambda2 ~ lambda3 the embedding depends on the eigensolver's arbitrary basis
         ev = pr["evals"]
