@@ -45,6 +45,8 @@ FPT_HD size_t fpt_css_perm2_smem_bytes(int m, int nthreads, int chain) {
     if (fpt_css_perm2_uses_mma(m)) off += (size_t)3 * (((m + 7) >> 3) << 3) * 80;   /* digit matrices, FPT_QD_STRIDE */
     off += (size_t)m * m * 4;                             /* q */
     off += (size_t)m * 4;                                 /* rowsum_q */
+    off = (off + 7) & ~(size_t)7;
+    off += (size_t)(m + 1) * 8;                           /* per-n (limit, magic) of the shuffle draws */
     off += (size_t)2 * m * 8;                             /* X */
     off += (size_t)nthreads * 4 * 2;                      /* offs, used */
     off += 33 * 4 + 12;
@@ -58,9 +60,10 @@ FPT_HD size_t fpt_css_perm2_smem_bytes(int m, int nthreads, int chain) {
 /* reference-order score on byte labels (same as fpt_css_score<unsigned char>) is reused for the rare recheck */
 
 /* Fisher-Yates on a byte row, css.c:700-706 */
-FPT_D void fpt_shuffle_row(unsigned char *row, int m, uint64_t &st, int &used) {
+FPT_D void fpt_shuffle_row(unsigned char *row, int m, const uint2 *rtab, uint64_t &st, int &used) {
     for (int i = m - 1; i > 0; i--) {
-        const int rr = (int)fpt_randint((uint32_t)(i + 1), st, used);
+        const uint2 lm = rtab[i + 1];                       /* (limit, magic) of n = i + 1, same for every thread */
+        const int rr = (int)fpt_randint_fast((uint32_t)(i + 1), lm.x, lm.y, st, used);
         const unsigned char t = row[i]; row[i] = row[rr]; row[rr] = t;
     }
 }
@@ -147,24 +150,28 @@ FPT_D int fpt_bet_mma(unsigned long long gmask, const unsigned char *qd, int m) 
     for (int tile = 0; tile < 2; tile++) {              /* permutations of lanes 16*tile .. 16*tile+15 */
         const unsigned long long m1 = __shfl_sync(FPT_FULL_MASK, gmask, 16 * tile + g);
         const unsigned long long m2 = __shfl_sync(FPT_FULL_MASK, gmask, 16 * tile + g + 8);
-        unsigned a[2][4];
-        for (int ks = 0; ks < 2; ks++) {
-            a[ks][0] = fpt_nibble_to_bytes((unsigned)(m1 >> (32 * ks + 4 * t)));
-            a[ks][1] = fpt_nibble_to_bytes((unsigned)(m2 >> (32 * ks + 4 * t)));
-            a[ks][2] = fpt_nibble_to_bytes((unsigned)(m1 >> (32 * ks + 16 + 4 * t)));
-            a[ks][3] = fpt_nibble_to_bytes((unsigned)(m2 >> (32 * ks + 16 + 4 * t)));
-        }
+        unsigned a0[4], a1[4];                          /* A fragments of k-step 0 (individuals 0..31) and 1 (32..63) */
+        a0[0] = fpt_nibble_to_bytes((unsigned)(m1 >> (4 * t)));
+        a0[1] = fpt_nibble_to_bytes((unsigned)(m2 >> (4 * t)));
+        a0[2] = fpt_nibble_to_bytes((unsigned)(m1 >> (16 + 4 * t)));
+        a0[3] = fpt_nibble_to_bytes((unsigned)(m2 >> (16 + 4 * t)));
+        a1[0] = fpt_nibble_to_bytes((unsigned)(m1 >> (32 + 4 * t)));
+        a1[1] = fpt_nibble_to_bytes((unsigned)(m2 >> (32 + 4 * t)));
+        a1[2] = fpt_nibble_to_bytes((unsigned)(m1 >> (48 + 4 * t)));
+        a1[3] = fpt_nibble_to_bytes((unsigned)(m2 >> (48 + 4 * t)));
         int s1 = 0, s2 = 0;                             /* masked row sums of rows g and g+8 */
+        const unsigned char *colbase = qd + (size_t)g * FPT_QD_STRIDE + 4 * t;
+        const size_t dstride = (size_t)nrows * FPT_QD_STRIDE;
         for (int nt = 0; nt < ntiles; nt++) {
             int r[4] = { 0, 0, 0, 0 };
+#pragma unroll
             for (int d = 2; d >= 0; d--) {
                 int c[4] = { 0, 0, 0, 0 };
-                const unsigned char *row = qd + ((size_t)d * nrows + (size_t)(8 * nt + g)) * FPT_QD_STRIDE + 4 * t;
-                for (int ks = 0; ks < ksteps; ks++) {
-                    const unsigned b0 = *reinterpret_cast<const unsigned *>(row + 32 * ks);
-                    const unsigned b1 = *reinterpret_cast<const unsigned *>(row + 32 * ks + 16);
-                    fpt_mma_u8(c, a[ks], b0, b1);
-                }
+                const unsigned char *row = colbase + (size_t)d * dstride + (size_t)(8 * nt) * FPT_QD_STRIDE;
+                fpt_mma_u8(c, a0, *reinterpret_cast<const unsigned *>(row), *reinterpret_cast<const unsigned *>(row + 16));
+                if (ksteps > 1)
+                    fpt_mma_u8(c, a1, *reinterpret_cast<const unsigned *>(row + 32), *reinterpret_cast<const unsigned *>(row + 48));
+#pragma unroll
                 for (int i = 0; i < 4; i++) r[i] = (r[i] << 8) + c[i];
             }
             const int j0 = 8 * nt + 2 * t;                 /* columns held by this lane; padded columns are zero */
@@ -198,6 +205,8 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
     unsigned char *qd = smem + off; if (use_mma) off += (size_t)3 * qd_rows * FPT_QD_STRIDE;
     unsigned *q = (unsigned *)(smem + off); off += (size_t)m * m * 4;
     int *rowsum = (int *)(smem + off); off += (size_t)m * 4;
+    off = (off + 7) & ~(size_t)7;
+    uint2 *rtab = (uint2 *)(smem + off); off += (size_t)(m + 1) * 8;
     double *X = (double *)(smem + off); off += (size_t)2 * m * 8;
     int *offs = (int *)(smem + off); off += (size_t)T * 4;
     int *usedv = (int *)(smem + off); off += (size_t)T * 4;
@@ -213,6 +222,12 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
     const int use_a = asize <= bsize;
     const int draws = m - 1;
     unsigned long long rechecks = 0;
+    for (int n = tid; n <= m; n += T) {
+        uint2 lm;
+        lm.x = n > 0 ? fpt_randint_limit((uint32_t)n) : 0u; lm.y = n > 0 ? fpt_randint_magic((uint32_t)n) : 0u;
+        rtab[n] = lm;
+    }
+    __syncthreads();
 
     for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
         if (status[w] != FPT_WIN_SCORED) continue;
@@ -299,7 +314,7 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
                     if (mycount > 0) {
                         fpt_identity_row(mine, m);
                         uint64_t s1 = fpt_lcg_skip(st_win, (uint64_t)(stream_pos + offs[tid]));
-                        for (int j = 0; j < mycount; j++) fpt_shuffle_row(mine, m, s1, used);
+                        for (int j = 0; j < mycount; j++) fpt_shuffle_row(mine, m, rtab, s1, used);
                     }
                     int total = 0;
                     const int incl = fpt_block_scan_incl(used, scan, &total);
@@ -353,7 +368,7 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
                            state already sits at the next permutation's start */
                         if (j == 0 || resync) st = fpt_lcg_skip(st_win, (uint64_t)(ndone + first + j) * (uint64_t)draws);
                     }
-                    fpt_shuffle_row(mine, m, st, used);
+                    fpt_shuffle_row(mine, m, rtab, st, used);
                     resync = used != draws;
                 }
                 int hit = 0;

@@ -380,18 +380,19 @@ FPT_D void fpt_bitonic_sort(double *x, int npad) {
 /* order statistics k and k+1 (0-based, k+1 optional) of replicate draws, by bisection on the index
    value with the draws regenerated on every pass: O(1) memory, used for very large windows */
 FPT_D void fpt_select_by_regeneration(uint64_t st0, int n, int k, bool need_next, int &v0, int &v1, int &used) {
+    const uint32_t lim = fpt_randint_limit((uint32_t)n), mag = fpt_randint_magic((uint32_t)n);
     int lo = 0, hi = n - 1;
     while (lo < hi) {                                    /* smallest v with #(draw <= v) >= k+1 */
         int mid = (lo + hi) >> 1, cnt = 0;
         uint64_t st = st0; used = 0;
-        for (int i = 0; i < n; i++) cnt += ((int)fpt_randint((uint32_t)n, st, used) <= mid);
+        for (int i = 0; i < n; i++) cnt += ((int)fpt_randint_fast((uint32_t)n, lim, mag, st, used) <= mid);
         if (cnt >= k + 1) hi = mid; else lo = mid + 1;
     }
     v0 = lo; v1 = lo;
     uint64_t st = st0; used = 0;
     int cnt = 0, nxt = n;
     for (int i = 0; i < n; i++) {
-        int r = (int)fpt_randint((uint32_t)n, st, used);
+        int r = (int)fpt_randint_fast((uint32_t)n, lim, mag, st, used);
         cnt += (r <= lo);
         if (r > lo && r < nxt) nxt = r;
     }
@@ -426,6 +427,7 @@ fpt_fet_window_kernel(const double *__restrict__ snp_scores, const int *__restri
         const double h = __dmul_rn((double)(n - 1), perc);
         const double delta = __dsub_rn(h, (double)k);
         const bool need_next = k + 1 < n;
+        const uint32_t lim = fpt_randint_limit((uint32_t)n), mag = fpt_randint_magic((uint32_t)n);
         const int s = threadIdx.x;
         if (s < FPT_FET_NSAMPLES) offs[s] = s * n;
         __syncthreads();
@@ -436,7 +438,7 @@ fpt_fet_window_kernel(const double *__restrict__ snp_scores, const int *__restri
                 if (use_hist) {
                     unsigned short *hrow = hist + (size_t)s * n;
                     for (int i = 0; i < n; i++) hrow[i] = 0;
-                    for (int i = 0; i < n; i++) hrow[fpt_randint((uint32_t)n, st, used)]++;
+                    for (int i = 0; i < n; i++) hrow[fpt_randint_fast((uint32_t)n, lim, mag, st, used)]++;
                     int cum = 0, v = 0;
                     for (; v < n; v++) { cum += hrow[v]; if (cum > k) break; }
                     v0 = v; v1 = v;

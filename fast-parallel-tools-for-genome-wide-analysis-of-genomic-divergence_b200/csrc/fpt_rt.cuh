@@ -69,6 +69,24 @@ FPT_HD uint32_t fpt_randint(uint32_t n, uint64_t &s, int &used) {
     return r % n;
 }
 
+/* the same draw with the two per-n constants precomputed: limit = RAND_MAX - (RAND_MAX+1) % n and
+   magic = floor(2^32 / n), which turns r % n (r < 2^31) into one multiply-high and a conditional subtract:
+   floor(r * magic / 2^32) is floor(r / n) or one less, because r * (2^32 mod n) / (n 2^32) < 1/2 */
+FPT_HD uint32_t fpt_randint_limit(uint32_t n) { return 2147483647u - (2147483648u % n); }
+FPT_HD uint32_t fpt_randint_magic(uint32_t n) {            /* floor(2^32 / n) in 32-bit arithmetic */
+    if (n <= 1) return 0u;
+    const uint32_t q = 0xFFFFFFFFu / n, r = 0xFFFFFFFFu - q * n;
+    return r == n - 1 ? q + 1 : q;
+}
+FPT_D uint32_t fpt_randint_fast(uint32_t n, uint32_t limit, uint32_t magic, uint64_t &s, int &used) {
+    uint32_t r = (uint32_t)(fpt_lcg_next(s) >> 17);
+    used++;
+    while (r > limit) { r = (uint32_t)(fpt_lcg_next(s) >> 17); used++; }
+    uint32_t rem = r - __umulhi(r, magic) * n;
+    if (rem >= n) rem -= n;
+    return n > 1 ? rem : 0u;
+}
+
 FPT_HD double fpt_drand48(uint64_t &s) {
     /* X / 2^48: X < 2^48 converts exactly, the power-of-two scale is exact */
     return (double)(long long)fpt_lcg_next(s) * 3.5527136788005009e-15;   /* 2^-48 */
