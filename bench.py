@@ -442,13 +442,13 @@ def css_config():
             "windows_per_step_per_gpu": CSS["chromosomes"] * (CSS["length"] // CSS["wstep"]), "sharding": "one genome per GPU (weak)"}
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, out):
     if rank != 0:
         return
     ncores = os.cpu_count() or 1
     probe = cpu_css(2000)                                 # calibrate the sample to a few minutes in total
     if probe is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_css.so not built (reference tree absent at build time)"}))
+        out.emit({"impl": "reference", "unavailable": "oracle/_ref/libref_css.so not built (reference tree absent at build time)"})
         return
     rate = probe["windows"] / probe["seconds"][0]
     budget = 150.0 / max(1, args.steps + args.warmup)
@@ -465,10 +465,25 @@ def run_reference(args, rank):
                              "note": "unmodified reference threadcompute (64 pthreads hard-wired), css.c linked against the "
                                      "header-only GSL stand-in of oracle/gsl_shim"},
             "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    out.emit(line)
+
+
+class OneLineStdout:
+    """everything any library prints to stdout while the benchmark runs (NCCL banners, reference printf()s) goes to
+    stderr; the single JSON line is written to the real stdout at the end"""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.write(self.real, (json.dumps(obj) + "\n").encode())
 
 
 def main():
+    out = OneLineStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -489,7 +504,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, out)
         return
     import torch
     import fpt_b200._lib as lib_mod
@@ -583,7 +598,7 @@ def main():
                                                cf["snps"], n, cf["seconds"]),
                                            "parity_vs_gpu": {"score_max_abs_diff": float(np.max(np.abs(s_host[:n - 8] - cf["scores"][:n - 8])))}}
             line["fet"] = fet
-        print(json.dumps(line))
+        out.emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -442,7 +442,8 @@ static void jacobi_eig(double *A, double *V, int n) {
             dia += A[i * n + i] * A[i * n + i];
             for (int j = i + 1; j < n; j++) off += A[i * n + j] * A[i * n + j];
         }
-        if (off <= 1e-300 || off <= 1e-34 * dia) break;
+        /* quadratic convergence; the rounding floor of off/dia sits near 1e-29, so 1e-26 is reached one sweep after 1e-13 */
+        if (off <= 1e-300 || off <= 1e-26 * (dia + off)) break;
         for (int p = 0; p < n - 1; p++)
             for (int q = p + 1; q < n; q++) {
                 double apq = A[p * n + q];

@@ -9,8 +9,8 @@
  *   - gsl_blas_dgemm: row-major, NoTrans/NoTrans only, i-k-j accumulation; when beta == 0 the
  *     destination is overwritten without being read (the reference hands in uninitialised
  *     malloc memory as C).
- *   - gsl_eigen_symmv: cyclic two-sided Jacobi in fp64, eigenvectors in the COLUMNS of evec,
- *     input matrix is destroyed (as in GSL).
+ *   - gsl_eigen_symmv: Householder tridiagonalisation + implicit QL in fp64 (the algorithm family GSL itself
+ *     uses), eigenvectors in the COLUMNS of evec, input matrix is destroyed (as in GSL).
  *   - gsl_eigen_symmv_sort: descending by eigenvalue, permuting the columns along.
  */
 #ifndef FPT_GSL_SHIM_H
@@ -81,47 +81,109 @@ static inline gsl_eigen_symmv_workspace *gsl_eigen_symmv_alloc(size_t n) {
 }
 static inline void gsl_eigen_symmv_free(gsl_eigen_symmv_workspace *w) { free(w); }
 
-/* cyclic Jacobi; A (n x n, symmetric) is overwritten, eval gets the diagonal, evec the rotations */
+/* Symmetric eigensolver of the same family as GSL's gsl_eigen_symmv: Householder reduction to tridiagonal form
+   followed by implicit-shift QL iterations with the transformations accumulated (the classic tred2 / tql2 pair, written
+   here from the textbook algorithm). A is destroyed, eigenvalues go to eval (unsorted), eigenvectors to the COLUMNS of
+   evec. O(n^3) with a small constant, so the CPU baseline is not handicapped by the stand-in. */
 static inline int gsl_eigen_symmv(gsl_matrix *A, gsl_vector *eval, gsl_matrix *evec, gsl_eigen_symmv_workspace *w) {
     (void)w;
-    size_t n = A->size1, lda = A->tda, ldv = evec->tda;
-    double *a = A->data, *v = evec->data;
-    for (size_t i = 0; i < n; i++)
-        for (size_t j = 0; j < n; j++) v[i * ldv + j] = (i == j) ? 1.0 : 0.0;
-    for (int sweep = 0; sweep < 100; sweep++) {
-        double off = 0.0, diag = 0.0;
-        for (size_t i = 0; i < n; i++) {
-            diag += a[i * lda + i] * a[i * lda + i];
-            for (size_t j = i + 1; j < n; j++) off += a[i * lda + j] * a[i * lda + j];
-        }
-        if (off <= 1e-300 || off <= 1e-34 * diag) break;
-        for (size_t p = 0; p + 1 < n; p++) {
-            for (size_t q = p + 1; q < n; q++) {
-                double apq = a[p * lda + q];
-                if (apq == 0.0) continue;
-                double app = a[p * lda + p], aqq = a[q * lda + q];
-                double theta = (aqq - app) / (2.0 * apq);
-                double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (size_t k = 0; k < n; k++) {           /* columns p,q */
-                    double akp = a[k * lda + p], akq = a[k * lda + q];
-                    a[k * lda + p] = c * akp - s * akq;
-                    a[k * lda + q] = s * akp + c * akq;
-                }
-                for (size_t k = 0; k < n; k++) {           /* rows p,q */
-                    double apk = a[p * lda + k], aqk = a[q * lda + k];
-                    a[p * lda + k] = c * apk - s * aqk;
-                    a[q * lda + k] = s * apk + c * aqk;
-                }
-                for (size_t k = 0; k < n; k++) {
-                    double vkp = v[k * ldv + p], vkq = v[k * ldv + q];
-                    v[k * ldv + p] = c * vkp - s * vkq;
-                    v[k * ldv + q] = s * vkp + c * vkq;
-                }
+    const int n = (int)A->size1;
+    const size_t lda = A->tda, ldv = evec->tda;
+    double *V = evec->data;
+    double *d = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    double *e = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+#define VV(i, j) V[(size_t)(i) * ldv + (size_t)(j)]
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) VV(i, j) = A->data[(size_t)i * lda + j];
+    /* ---- Householder tridiagonalisation */
+    for (int j = 0; j < n; j++) d[j] = VV(n - 1, j);
+    for (int i = n - 1; i > 0; i--) {
+        double scale = 0.0, h = 0.0;
+        for (int k = 0; k < i; k++) scale += fabs(d[k]);
+        if (scale == 0.0) {
+            e[i] = d[i - 1];
+            for (int j = 0; j < i; j++) { d[j] = VV(i - 1, j); VV(i, j) = 0.0; VV(j, i) = 0.0; }
+        } else {
+            for (int k = 0; k < i; k++) { d[k] /= scale; h += d[k] * d[k]; }
+            double f = d[i - 1], g = sqrt(h);
+            if (f > 0) g = -g;
+            e[i] = scale * g; h -= f * g; d[i - 1] = f - g;
+            for (int j = 0; j < i; j++) e[j] = 0.0;
+            for (int j = 0; j < i; j++) {
+                f = d[j]; VV(j, i) = f; g = e[j] + VV(j, j) * f;
+                for (int k = j + 1; k <= i - 1; k++) { g += VV(k, j) * d[k]; e[k] += VV(k, j) * f; }
+                e[j] = g;
+            }
+            f = 0.0;
+            for (int j = 0; j < i; j++) { e[j] /= h; f += e[j] * d[j]; }
+            const double hh = f / (h + h);
+            for (int j = 0; j < i; j++) e[j] -= hh * d[j];
+            for (int j = 0; j < i; j++) {
+                f = d[j]; g = e[j];
+                for (int k = j; k <= i - 1; k++) VV(k, j) -= (f * e[k] + g * d[k]);
+                d[j] = VV(i - 1, j); VV(i, j) = 0.0;
             }
         }
+        d[i] = h;
     }
-    for (size_t i = 0; i < n; i++) eval->data[i * eval->stride] = a[i * lda + i];
+    for (int i = 0; i < n - 1; i++) {
+        VV(n - 1, i) = VV(i, i); VV(i, i) = 1.0;
+        const double h = d[i + 1];
+        if (h != 0.0) {
+            for (int k = 0; k <= i; k++) d[k] = VV(k, i + 1) / h;
+            for (int j = 0; j <= i; j++) {
+                double g = 0.0;
+                for (int k = 0; k <= i; k++) g += VV(k, i + 1) * VV(k, j);
+                for (int k = 0; k <= i; k++) VV(k, j) -= g * d[k];
+            }
+        }
+        for (int k = 0; k <= i; k++) VV(k, i + 1) = 0.0;
+    }
+    for (int j = 0; j < n; j++) { d[j] = VV(n - 1, j); VV(n - 1, j) = 0.0; }
+    if (n > 0) { VV(n - 1, n - 1) = 1.0; e[0] = 0.0; }
+    /* ---- implicit QL on the tridiagonal, rotations applied to V */
+    for (int i = 1; i < n; i++) e[i - 1] = e[i];
+    if (n > 0) e[n - 1] = 0.0;
+    double f = 0.0, tst1 = 0.0;
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < n; l++) {
+        tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
+        int m = l;
+        while (m < n) { if (fabs(e[m]) <= eps * tst1) break; m++; }
+        if (m > l) {
+            int iter = 0;
+            do {
+                iter++;
+                double g = d[l], p = (d[l + 1] - g) / (2.0 * e[l]), r = hypot(p, 1.0);
+                if (p < 0) r = -r;
+                d[l] = e[l] / (p + r); d[l + 1] = e[l] * (p + r);
+                const double dl1 = d[l + 1];
+                double h = g - d[l];
+                for (int i = l + 2; i < n; i++) d[i] -= h;
+                f += h;
+                p = d[m];
+                double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0;
+                const double el1 = e[l + 1];
+                for (int i = m - 1; i >= l; i--) {
+                    c3 = c2; c2 = c; s2 = s;
+                    g = c * e[i]; h = c * p; r = hypot(p, e[i]);
+                    e[i + 1] = s * r; s = e[i] / r; c = p / r;
+                    p = c * d[i] - s * g; d[i + 1] = h + s * (c * g + s * d[i]);
+                    for (int k = 0; k < n; k++) {
+                        h = VV(k, i + 1);
+                        VV(k, i + 1) = s * VV(k, i) + c * h;
+                        VV(k, i) = c * VV(k, i) - s * h;
+                    }
+                }
+                p = -s * s2 * c3 * el1 * e[l] / dl1;
+                e[l] = s * p; d[l] = c * p;
+            } while (fabs(e[l]) > eps * tst1 && iter < 200);
+        }
+        d[l] = d[l] + f;
+        e[l] = 0.0;
+    }
+#undef VV
+    for (int i = 0; i < n; i++) eval->data[(size_t)i * eval->stride] = d[i];
+    free(d); free(e);
     return 0;
 }
 

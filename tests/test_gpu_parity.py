@@ -270,6 +270,19 @@ def test_css_independent_shuffles_match_reference_functions(fpt, ref_css, oracle
     assert checked >= 4
 
 
+@pytest.mark.parametrize("asize,bsize", [(36, 36), (70, 60), (150, 140)])
+def test_css_larger_cohorts_take_the_fallback_paths(fpt, oracle, asize, bsize):
+    """72: one warp per CTA for classical MDS, gather surrogate; 130: gather surrogate, bigger tiles; 290: Jacobi and
+    first-generation permutation kernel with 16-bit labels and global-memory scratch"""
+    regend, wsize, wstep, nsnp, seed = 12000, 3000, 1500, 500, 3
+    ch, (av, bv, apos, bpos) = _synth(100 + asize, regend, nsnp, asize, bsize)
+    s_o, p_o = _css_oracle_scan(oracle, av, bv, apos, bpos, regend, wsize, wstep, 5, 60, 0, 0, seed)
+    s_g, p_g, wr, pr = fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 5, 60, mds=0, seed=seed, probes=True)
+    assert np.array_equal(wr == 1, p_o != 0) and (wr == 1).sum() >= 4
+    np.testing.assert_allclose(s_g, s_o, rtol=CSS_RTOL, atol=1e-12)
+    assert np.array_equal(p_g, p_o)
+
+
 def test_css_frequency_metric(fpt, oracle):
     """drosophila = 1: two frequency tracks, m = 2 (compare_freq)"""
     rng = np.random.default_rng(3)

@@ -200,3 +200,30 @@ def test_css_scan_scores_match_reference_compute(oracle, ref_css, mds):
     assert np.array_equal(p_o != 0, p_r[:n] != 0)
     ok = np.isfinite(s_r[:n])
     np.testing.assert_allclose(s_o[ok], s_r[:n][ok], rtol=1e-9, atol=1e-12)
+
+
+def test_gsl_standin_eigensolver_matches_numpy(ref_css, oracle):
+    """the GSL stand-in behind the compiled reference (oracle/gsl_shim) and the oracle's own Jacobi against
+    numpy.linalg.eigh: classical-MDS distances of random configurations, including repeated and integer distances"""
+    rng = np.random.default_rng(0)
+    for m in (2, 3, 5, 17, 40, 41, 100):
+        for rep in range(4):
+            pts = rng.normal(size=(m, 3))
+            D = np.sqrt(((pts[:, None] - pts[None]) ** 2).sum(-1))
+            if rep == 3:
+                D = np.round(D * 2)
+            Dm = RefMatrix(m, m, D.copy())
+            X, B, Z, T, L, Q = RefMatrix(m, 2), RefMatrix(m, m), RefMatrix(m, m), RefMatrix(m, m), RefMatrix(2, 2), RefMatrix(m, 2)
+            ref_css.cmds(Dm.pp, X.pp, 2, m, B.pp, Z.pp, T.pp, L.pp, Q.pp)
+            Xo, evo = np.zeros((m, 2)), np.zeros(3)
+            oracle.fpt_oracle_cmds(dptr(np.ascontiguousarray(D)), m, dptr(Xo), dptr(evo))
+            J = np.eye(m) - 1.0 / m
+            ev, evec = np.linalg.eigh(-0.5 * J @ (D * D) @ J)
+            order = np.argsort(ev)[::-1]
+            if ev[order[1]] <= 0 or (m > 2 and ev[order[1]] - ev[order[2]] < 1e-8 * ev[order[0]]):
+                continue
+            Xn = evec[:, order[:2]] * np.sqrt(ev[order[:2]])
+            dn = np.sqrt(((Xn[:, None] - Xn[None]) ** 2).sum(-1))
+            for Xc in (X.a, Xo):
+                dc = np.sqrt(((Xc[:, None] - Xc[None]) ** 2).sum(-1))
+                assert np.abs(dc - dn).max() <= 1e-10 * dn.max()
