@@ -478,7 +478,7 @@ static CssPlan css_plan(const DeviceCtx *c, int m) {
     if (!p.mats_in_smem && fpt_css_smem_bytes(m, p.wch, 0) > budget) p.wch = 1;
     p.smem_win = fpt_css_smem_bytes(m, p.wch, p.mats_in_smem);
     const size_t per_warp = fpt_eig_work_bytes(m, 4);
-    p.mds_warps = 4 * per_warp <= budget / 2 ? 4 : (per_warp <= budget ? 1 : 0);
+    p.mds_warps = 2 * per_warp <= 32 * 1024 ? 2 : (per_warp <= budget ? 1 : 0);   /* small CTAs: many resident warps */
     p.smem_mds_warp = per_warp * (p.mds_warps > 0 ? p.mds_warps : 1);
     p.perm_threads = 256;
     p.wide_tracks = m > 256;

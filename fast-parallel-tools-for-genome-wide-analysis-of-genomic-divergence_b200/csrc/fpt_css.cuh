@@ -210,8 +210,7 @@ FPT_D void fpt_css_cmds(double *A, double *V, int m, double *X, double *evals3, 
            ~eps^2 behind), so the first sweep that lands below 1e-24 is already at that floor */
         if (off <= 1e-300 || off <= 1e-24 * (dia + off)) break;
         for (int round = 0; round < n - 1; round++) {
-            if ((int)threadIdx.x < half) {
-                const int t = threadIdx.x;
+            for (int t = threadIdx.x; t < half; t += blockDim.x) {     /* one rotation per disjoint pair of this round */
                 int a, b;
                 if (t == 0) { a = n - 1; b = round; }
                 else { a = (round + t) % (n - 1); b = (round - t + (n - 1)) % (n - 1); }

@@ -14,7 +14,8 @@
  *   5. back-transformation through the stored reflectors, X = [v1 v2] diag(sqrt l1, sqrt l2)
  *
  * No __syncthreads anywhere: each warp of the CTA owns its own window and its own slice of shared
- * memory. Rows are padded to an odd number of doubles so that "lane = row" accesses are conflict-free.
+ * memory. The symmetric matrix is kept as its packed lower triangle (half the shared memory of a square
+ * array, hence more resident warps for a latency-bound kernel, and only one triangle to update).
  */
 #ifndef FPT_CSS_EIG_CUH
 #define FPT_CSS_EIG_CUH
@@ -40,8 +41,7 @@ FPT_D double fpt_warp_min(double v) {
 
 /* per-warp shared-memory work area */
 struct FptEigWork {
-    double *A;        /* m x ld, ld odd */
-    int ld;
+    double *A;        /* symmetric matrix, lower triangle packed by rows: element (i, j <= i) at i(i+1)/2 + j */
     double *d, *e;    /* tridiagonal: m diagonal, m-1 off-diagonal (e2 overwrites nothing: kept in tau2) */
     double *tau;      /* m reflector scales */
     double *pv, *wv;  /* m each: Householder work vectors */
@@ -51,7 +51,7 @@ struct FptEigWork {
     int wch;
 };
 
-FPT_HD int fpt_eig_ld(int m) { return m | 1; }
+FPT_HD int fpt_tri(int i) { return (i * (i + 1)) >> 1; }
 
 /* e / m for 0 <= e < m*m, m <= 4096, without an integer division: magic = ceil(2^32 / m) */
 FPT_HD unsigned fpt_div_magic(int m) { return (unsigned)((0x100000000ULL + (unsigned)m - 1) / (unsigned)m); }
@@ -66,7 +66,7 @@ FPT_D double fpt_fast_rcp(double q) {
 }
 
 FPT_HD size_t fpt_eig_work_bytes(int m, int wch) {
-    size_t doubles = (size_t)m * fpt_eig_ld(m) + (size_t)5 * m + (size_t)2 * m + (size_t)6 * m;
+    size_t doubles = (size_t)fpt_tri(m) + (size_t)5 * m + (size_t)2 * m + (size_t)6 * m;
     size_t bytes = doubles * 8 + (size_t)wch * 2 * m * 4;
     return (bytes + 15) & ~(size_t)15;
 }
@@ -74,8 +74,7 @@ FPT_HD size_t fpt_eig_work_bytes(int m, int wch) {
 FPT_D FptEigWork fpt_eig_carve(unsigned char *base, int m, int wch) {
     FptEigWork w;
     double *p = (double *)base;
-    w.ld = fpt_eig_ld(m);
-    w.A = p; p += (size_t)m * w.ld;
+    w.A = p; p += (size_t)fpt_tri(m);
     w.d = p; p += m;
     w.e = p; p += m;
     w.tau = p; p += m;
@@ -88,12 +87,13 @@ FPT_D FptEigWork fpt_eig_carve(unsigned char *base, int m, int wch) {
     return w;
 }
 
-/* ---- step 1a: D (full, mirrored, zero diagonal) from the bit-planes of SNPs [l, r); warp-level twin of fpt_css_counts */
+/* ---- step 1a: D (packed lower triangle, zero diagonal) from the bit-planes of SNPs [l, r); warp-level twin of
+   fpt_css_counts. Lane = column j of row i, so the plane words of a row are read as consecutive addresses. */
 FPT_D void fpt_warp_counts(const unsigned *__restrict__ planes, int m, int l, int r, const FptEigWork &w) {
-    const int lane = threadIdx.x & 31, ld = w.ld;
+    const int lane = threadIdx.x & 31;
     const unsigned magic = fpt_div_magic(m);
-    const int w0 = l >> 5, w1 = (r - 1) >> 5, mm = m * m;
-    for (int e = lane; e < mm; e += 32) { const int i = fpt_fastdiv(e, magic), j = e - i * m; w.A[i * ld + j] = 0.0; }
+    const int w0 = l >> 5, w1 = (r - 1) >> 5;
+    for (int e = lane; e < fpt_tri(m); e += 32) w.A[e] = 0.0;
     for (int wc = w0; wc <= w1; wc += w.wch) {
         const int nw = min(w.wch, w1 - wc + 1);
         __syncwarp();
@@ -105,45 +105,36 @@ FPT_D void fpt_warp_counts(const unsigned *__restrict__ planes, int m, int l, in
             w.wbuf[e] = planes[(size_t)wc * 2 * m + e] & mask;
         }
         __syncwarp();
-        for (int e = lane; e < mm; e += 32) {
-            const int i = fpt_fastdiv(e, magic), j = e - i * m;
-            if (j < i) {
+        for (int i = 1; i < m; i++) {
+            for (int j = lane; j < i; j += 32) {
                 int cnt = 0;
                 for (int q = 0; q < nw; q++) {
                     const unsigned *row = w.wbuf + (size_t)q * 2 * m;
                     cnt += __popc(row[i] & row[m + j]) + __popc(row[m + i] & row[j]);
                 }
-                w.A[i * ld + j] += (double)cnt;
+                w.A[fpt_tri(i) + j] += (double)cnt;
             }
         }
     }
     __syncwarp();
-    for (int e = lane; e < mm; e += 32) {
-        const int i = fpt_fastdiv(e, magic), j = e - i * m;
-        if (j > i) w.A[i * ld + j] = w.A[j * ld + i];
-    }
-    __syncwarp();
 }
 
-/* ---- step 1b: fill_averages (css.c:337-366); returns 1 to keep the window */
+/* ---- step 1b: fill_averages (css.c:337-366) on the packed triangle; returns 1 to keep the window. Every off-diagonal
+   entry stands for two of the m*m entries the reference visits, the diagonal (always blank before filling) for one. */
 FPT_D int fpt_warp_fill(int m, const FptEigWork &w) {
-    const int lane = threadIdx.x & 31, ld = w.ld, mm = m * m;
-    const unsigned magic = fpt_div_magic(m);
+    const int lane = threadIdx.x & 31, mm = m * m;
     long long blanks = 0;
     double sum = 0.0;
-    for (int e = lane; e < mm; e += 32) {
-        const int i = fpt_fastdiv(e, magic), j = e - i * m;
-        const double v = w.A[i * ld + j];
-        if (v < 0.00001) blanks++; else sum += v;
-    }
-    blanks = fpt_warp_sum_i64(blanks);
+    for (int i = 1; i < m; i++)
+        for (int j = lane; j < i; j += 32) {
+            const double v = w.A[fpt_tri(i) + j];
+            if (v < 0.00001) blanks += 2; else sum += 2.0 * v;
+        }
+    blanks = fpt_warp_sum_i64(blanks) + m;
     sum = fpt_warp_sum(sum);
     if (blanks > (long long)(mm / 2)) return 0;
     const double avg = __ddiv_rn(sum, (double)mm);
-    for (int e = lane; e < mm; e += 32) {
-        const int i = fpt_fastdiv(e, magic), j = e - i * m;
-        if (w.A[i * ld + j] < 0.00001) w.A[i * ld + j] = avg;
-    }
+    for (int e = lane; e < fpt_tri(m); e += 32) if (w.A[e] < 0.00001) w.A[e] = avg;
     __syncwarp();
     return 1;
 }
@@ -163,41 +154,42 @@ FPT_D int fpt_sturm_count(const double *d, const double *e2, int n, double x, do
 
 /* ---- steps 1c-5. A holds the filled D on entry; X (2m doubles) and evals3 are written by the warp. */
 FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, int want_third) {
-    const int lane = threadIdx.x & 31, ld = w.ld, mm = m * m;
-    const unsigned magic = fpt_div_magic(m);
+    const int lane = threadIdx.x & 31;
     double *A = w.A;
     if (m == 1) {
         if (lane == 0) { X[0] = 0.0; X[1] = 0.0; if (evals3) { evals3[0] = 0.0; evals3[1] = 0.0; evals3[2] = 0.0; } }
         __syncwarp();
         return;
     }
-    /* double centring */
-    for (int e = lane; e < mm; e += 32) { const int i = fpt_fastdiv(e, magic), j = e - i * m; const double v = A[i * ld + j]; A[i * ld + j] = v * v; }
+    /* double centring on the packed triangle; a row sum visits j < i in the row, the diagonal, then j > i down the column */
+    for (int e = lane; e < fpt_tri(m); e += 32) { const double v = A[e]; A[e] = v * v; }
     __syncwarp();
     for (int i = lane; i < m; i += 32) {
         double s = 0.0;
-        for (int j = 0; j < m; j++) s += A[i * ld + j];
+        const double *row = A + fpt_tri(i);
+        for (int j = 0; j <= i; j++) s += row[j];
+        for (int j = i + 1; j < m; j++) s += A[fpt_tri(j) + i];
         w.pv[i] = s / m;
     }
     __syncwarp();
     double g = 0.0;
     for (int i = 0; i < m; i++) g += w.pv[i];
     g /= m;
-    for (int e = lane; e < mm; e += 32) {
-        const int i = fpt_fastdiv(e, magic), j = e - i * m;
-        if (j <= i) A[i * ld + j] = -0.5 * (((A[i * ld + j] - w.pv[i]) - w.pv[j]) + g);
+    for (int i = 0; i < m; i++) {
+        const double ri = w.pv[i];
+        double *row = A + fpt_tri(i);
+        for (int j = lane; j <= i; j += 32) row[j] = -0.5 * (((row[j] - ri) - w.pv[j]) + g);
     }
     __syncwarp();
-    for (int e = lane; e < mm; e += 32) { const int i = fpt_fastdiv(e, magic), j = e - i * m; if (j > i) A[i * ld + j] = A[j * ld + i]; }
-    __syncwarp();
 
-    /* Householder tridiagonalisation, lower form: H_k = I - tau v v', v(k+1) = 1, v(k+2:) stored in column k */
+    /* Householder tridiagonalisation (LAPACK dsytd2, lower): H_k = I - tau v v', v(k+1) = 1, v(k+2:) stored in column k.
+       Only the lower triangle is referenced and updated. Lane = row. */
     for (int k = 0; k + 2 < m; k++) {
-        const double x0 = A[(k + 1) * ld + k];
+        const double x0 = A[fpt_tri(k + 1) + k];
         double s2 = 0.0;
-        for (int i = k + 2 + lane; i < m; i += 32) { const double x = A[i * ld + k]; s2 += x * x; }
+        for (int i = k + 2 + lane; i < m; i += 32) { const double x = A[fpt_tri(i) + k]; s2 += x * x; }
         s2 = fpt_warp_sum(s2);
-        if (lane == 0) w.d[k] = A[k * ld + k];
+        if (lane == 0) w.d[k] = A[fpt_tri(k) + k];
         if (s2 == 0.0) {                                  /* column already tridiagonal: H = I */
             if (lane == 0) { w.e[k] = x0; w.tau[k] = 0.0; }
             __syncwarp();
@@ -207,35 +199,36 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
         const double alpha = x0 >= 0.0 ? -nrm : nrm;
         const double tau = (alpha - x0) / alpha;
         const double scal = 1.0 / (x0 - alpha);
-        for (int i = k + 2 + lane; i < m; i += 32) A[i * ld + k] *= scal;
-        if (lane == 0) { A[(k + 1) * ld + k] = 1.0; w.e[k] = alpha; w.tau[k] = tau; }
+        for (int i = k + 2 + lane; i < m; i += 32) A[fpt_tri(i) + k] *= scal;
+        if (lane == 0) { A[fpt_tri(k + 1) + k] = 1.0; w.e[k] = alpha; w.tau[k] = tau; }
         __syncwarp();
-        /* p = tau * A22 v */
+        /* p = tau * A22 v, A22 symmetric and stored as its lower triangle: row part, then column part */
         double pvdot = 0.0;
         for (int i = k + 1 + lane; i < m; i += 32) {
-            const double *row = A + (size_t)i * ld;
+            const double *row = A + fpt_tri(i);
             double s = 0.0;
-            for (int j = k + 1; j < m; j++) s += row[j] * A[j * ld + k];
+            for (int j = k + 1; j <= i; j++) s += row[j] * A[fpt_tri(j) + k];
+            for (int j = i + 1; j < m; j++) s += A[fpt_tri(j) + i] * A[fpt_tri(j) + k];
             s *= tau;
             w.pv[i] = s;
-            pvdot += s * A[i * ld + k];
+            pvdot += s * row[k];
         }
         pvdot = fpt_warp_sum(pvdot);
         const double K = -0.5 * tau * pvdot;
-        for (int i = k + 1 + lane; i < m; i += 32) w.wv[i] = w.pv[i] + K * A[i * ld + k];
+        for (int i = k + 1 + lane; i < m; i += 32) w.wv[i] = w.pv[i] + K * A[fpt_tri(i) + k];
         __syncwarp();
-        /* A22 -= v w' + w v' */
+        /* A22 -= v w' + w v' on the lower triangle */
         for (int i = k + 1 + lane; i < m; i += 32) {
-            double *row = A + (size_t)i * ld;
+            double *row = A + fpt_tri(i);
             const double vi = row[k], wi = w.wv[i];
-            for (int j = k + 1; j < m; j++) row[j] -= vi * w.wv[j] + wi * A[j * ld + k];
+            for (int j = k + 1; j <= i; j++) row[j] -= vi * w.wv[j] + wi * A[fpt_tri(j) + k];
         }
         __syncwarp();
     }
     if (lane == 0) {
-        w.d[m - 2] = A[(m - 2) * ld + (m - 2)];
-        w.e[m - 2] = A[(m - 1) * ld + (m - 2)];
-        w.d[m - 1] = A[(m - 1) * ld + (m - 1)];
+        w.d[m - 2] = A[fpt_tri(m - 2) + (m - 2)];
+        w.e[m - 2] = A[fpt_tri(m - 1) + (m - 2)];
+        w.d[m - 1] = A[fpt_tri(m - 1) + (m - 1)];
         if (m == 2) w.tau[0] = 0.0;
     }
     __syncwarp();
@@ -396,12 +389,12 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
         if (tau == 0.0) continue;
         double s0 = 0.0, s1 = 0.0;
         for (int i = k + 1 + lane; i < m; i += 32) {
-            const double v = A[i * ld + k];
+            const double v = A[fpt_tri(i) + k];
             s0 += v * w.y[i]; s1 += v * w.y[m + i];
         }
         s0 = tau * fpt_warp_sum(s0); s1 = tau * fpt_warp_sum(s1);
         for (int i = k + 1 + lane; i < m; i += 32) {
-            const double v = A[i * ld + k];
+            const double v = A[fpt_tri(i) + k];
             w.y[i] -= s0 * v; w.y[m + i] -= s1 * v;
         }
         __syncwarp();
@@ -434,7 +427,7 @@ fpt_css_mds_warp_kernel(const unsigned *__restrict__ planes, const double *__res
                 double s = 0.0;
                 for (int i = r; i-- > l;) s = __dadd_rn(s, absdiff[i]);
                 s = __ddiv_rn(s, (double)(r - l));
-                w.A[0] = 0.0; w.A[1] = s; w.A[w.ld] = s; w.A[w.ld + 1] = 0.0;
+                w.A[0] = 0.0; w.A[1] = s; w.A[2] = 0.0;          /* packed: (0,0), (1,0), (1,1) */
             }
             __syncwarp();
         } else {
