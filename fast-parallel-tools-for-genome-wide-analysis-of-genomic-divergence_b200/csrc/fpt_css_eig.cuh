@@ -199,29 +199,31 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
         const double alpha = x0 >= 0.0 ? -nrm : nrm;
         const double tau = (alpha - x0) / alpha;
         const double scal = 1.0 / (x0 - alpha);
-        for (int i = k + 2 + lane; i < m; i += 32) A[fpt_tri(i) + k] *= scal;
-        if (lane == 0) { A[fpt_tri(k + 1) + k] = 1.0; w.e[k] = alpha; w.tau[k] = tau; }
+        double *vv = w.y;                                 /* the reflector as a contiguous vector (y is free until step 4) */
+        for (int i = k + 2 + lane; i < m; i += 32) { const double v = A[fpt_tri(i) + k] * scal; A[fpt_tri(i) + k] = v; vv[i] = v; }
+        if (lane == 0) { A[fpt_tri(k + 1) + k] = 1.0; vv[k + 1] = 1.0; w.e[k] = alpha; w.tau[k] = tau; }
         __syncwarp();
-        /* p = tau * A22 v, A22 symmetric and stored as its lower triangle: row part, then column part */
+        /* p = tau * A22 v, A22 symmetric and stored as its lower triangle: row part, then down the column (index grows by j+1) */
         double pvdot = 0.0;
         for (int i = k + 1 + lane; i < m; i += 32) {
             const double *row = A + fpt_tri(i);
             double s = 0.0;
-            for (int j = k + 1; j <= i; j++) s += row[j] * A[fpt_tri(j) + k];
-            for (int j = i + 1; j < m; j++) s += A[fpt_tri(j) + i] * A[fpt_tri(j) + k];
+            for (int j = k + 1; j <= i; j++) s += row[j] * vv[j];
+            int idx = fpt_tri(i + 1) + i;
+            for (int j = i + 1; j < m; j++) { s += A[idx] * vv[j]; idx += j + 1; }
             s *= tau;
             w.pv[i] = s;
-            pvdot += s * row[k];
+            pvdot += s * vv[i];
         }
         pvdot = fpt_warp_sum(pvdot);
         const double K = -0.5 * tau * pvdot;
-        for (int i = k + 1 + lane; i < m; i += 32) w.wv[i] = w.pv[i] + K * A[fpt_tri(i) + k];
+        for (int i = k + 1 + lane; i < m; i += 32) w.wv[i] = w.pv[i] + K * vv[i];
         __syncwarp();
         /* A22 -= v w' + w v' on the lower triangle */
         for (int i = k + 1 + lane; i < m; i += 32) {
             double *row = A + fpt_tri(i);
-            const double vi = row[k], wi = w.wv[i];
-            for (int j = k + 1; j <= i; j++) row[j] -= vi * w.wv[j] + wi * A[fpt_tri(j) + k];
+            const double vi = vv[i], wi = w.wv[i];
+            for (int j = k + 1; j <= i; j++) row[j] -= vi * w.wv[j] + wi * vv[j];
         }
         __syncwarp();
     }

@@ -147,18 +147,18 @@ FPT_D int fpt_bet_mma(unsigned long long gmask, const unsigned char *qd, int m) 
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntiles = (m + 7) >> 3, nrows = ntiles << 3, ksteps = (m + 31) >> 5;
     int mine = 0;
+    const unsigned glo = (unsigned)gmask, ghi = (unsigned)(gmask >> 32);      /* 32-bit halves: cheap shifts and shuffles */
     for (int tile = 0; tile < 2; tile++) {              /* permutations of lanes 16*tile .. 16*tile+15 */
-        const unsigned long long m1 = __shfl_sync(FPT_FULL_MASK, gmask, 16 * tile + g);
-        const unsigned long long m2 = __shfl_sync(FPT_FULL_MASK, gmask, 16 * tile + g + 8);
-        unsigned a0[4], a1[4];                          /* A fragments of k-step 0 (individuals 0..31) and 1 (32..63) */
-        a0[0] = fpt_nibble_to_bytes((unsigned)(m1 >> (4 * t)));
-        a0[1] = fpt_nibble_to_bytes((unsigned)(m2 >> (4 * t)));
-        a0[2] = fpt_nibble_to_bytes((unsigned)(m1 >> (16 + 4 * t)));
-        a0[3] = fpt_nibble_to_bytes((unsigned)(m2 >> (16 + 4 * t)));
-        a1[0] = fpt_nibble_to_bytes((unsigned)(m1 >> (32 + 4 * t)));
-        a1[1] = fpt_nibble_to_bytes((unsigned)(m2 >> (32 + 4 * t)));
-        a1[2] = fpt_nibble_to_bytes((unsigned)(m1 >> (48 + 4 * t)));
-        a1[3] = fpt_nibble_to_bytes((unsigned)(m2 >> (48 + 4 * t)));
+        const unsigned lo1 = __shfl_sync(FPT_FULL_MASK, glo, 16 * tile + g), lo2 = __shfl_sync(FPT_FULL_MASK, glo, 16 * tile + g + 8);
+        unsigned hi1 = 0u, hi2 = 0u;
+        if (ksteps > 1) { hi1 = __shfl_sync(FPT_FULL_MASK, ghi, 16 * tile + g); hi2 = __shfl_sync(FPT_FULL_MASK, ghi, 16 * tile + g + 8); }
+        /* A fragments of k-step 0 (individuals 0..31) and 1 (32..63): nibbles t and t+4 of each half */
+        unsigned a0[4], a1[4];
+        const unsigned l1 = lo1 >> (4 * t), l2 = lo2 >> (4 * t), h1 = hi1 >> (4 * t), h2 = hi2 >> (4 * t);
+        a0[0] = fpt_nibble_to_bytes(l1); a0[1] = fpt_nibble_to_bytes(l2);
+        a0[2] = fpt_nibble_to_bytes(l1 >> 16); a0[3] = fpt_nibble_to_bytes(l2 >> 16);
+        a1[0] = fpt_nibble_to_bytes(h1); a1[1] = fpt_nibble_to_bytes(h2);
+        a1[2] = fpt_nibble_to_bytes(h1 >> 16); a1[3] = fpt_nibble_to_bytes(h2 >> 16);
         int s1 = 0, s2 = 0;                             /* masked row sums of rows g and g+8 */
         const unsigned char *colbase = qd + (size_t)g * FPT_QD_STRIDE + 4 * t;
         const size_t dstride = (size_t)nrows * FPT_QD_STRIDE;
@@ -174,11 +174,14 @@ FPT_D int fpt_bet_mma(unsigned long long gmask, const unsigned char *qd, int m) 
 #pragma unroll
                 for (int i = 0; i < 4; i++) r[i] = (r[i] << 8) + c[i];
             }
-            const int j0 = 8 * nt + 2 * t;                 /* columns held by this lane; padded columns are zero */
-            if (!((m1 >> j0) & 1ULL)) s1 += r[0];
-            if (!((m1 >> (j0 + 1)) & 1ULL)) s1 += r[1];
-            if (!((m2 >> j0) & 1ULL)) s2 += r[2];
-            if (!((m2 >> (j0 + 1)) & 1ULL)) s2 += r[3];
+            /* columns 8nt + 2t, +1 held by this lane: keep those outside the group (padded columns are zero anyway) */
+            const unsigned w1 = nt < 4 ? lo1 : hi1, w2 = nt < 4 ? lo2 : hi2;
+            const int sh = ((8 * nt) & 31) + 2 * t;
+            const unsigned b1 = w1 >> sh, b2 = w2 >> sh;
+            if (!(b1 & 1u)) s1 += r[0];
+            if (!(b1 & 2u)) s1 += r[1];
+            if (!(b2 & 1u)) s2 += r[2];
+            if (!(b2 & 2u)) s2 += r[3];
         }
         s1 += __shfl_xor_sync(FPT_FULL_MASK, s1, 1); s1 += __shfl_xor_sync(FPT_FULL_MASK, s1, 2);
         s2 += __shfl_xor_sync(FPT_FULL_MASK, s2, 1); s2 += __shfl_xor_sync(FPT_FULL_MASK, s2, 2);
