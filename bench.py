@@ -214,6 +214,7 @@ def bench_css(lib_mod, args, rank, world, dist):
     lib.fpt_profile_enable(0)
     prof = json.loads(buf.value.decode())
     scored = int(sum(int((st == 2).sum().item()) for st in out_st))
+    rechecks = int(lib.fpt_css_perm_rechecks())             # exact re-scorings since the library was loaded (all steps so far)
     windows_per_step = len(chroms) * nout                # window slots visited per rank and step
 
     # end to end through the drop-in host call
@@ -232,7 +233,7 @@ def bench_css(lib_mod, args, rank, world, dist):
     h2d = sum(av[1].nbytes + bv[1].nbytes + 4 * nsnp for (av, bv, apos, bpos) in host)
     d2h = len(chroms) * nout * 17
     return dict(ms=ms, ms_e2e=ms_e2e, windows_per_step=windows_per_step, scored=scored, scored_e2e=scored_e2e, prof=prof,
-                launches=launches_per_step * args.steps, h2d=h2d, d2h=d2h, clocks=clk.summary(),
+                launches=launches_per_step * args.steps, h2d=h2d, d2h=d2h, rechecks=rechecks, clocks=clk.summary(),
                 sample=(chroms[0], host[0], out_s[0].cpu().numpy(), out_p[0].cpu().numpy()))
 
 
@@ -541,6 +542,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": css_config(),
             "windows_scored_per_step_per_gpu": css["scored"],
+            "perm_rechecks": {"exact_rescorings": css["rechecks"],
+                              "permutations_scored": css["scored"] * 1024 * (args.steps + args.warmup),
+                              "note": "permutations whose integer surrogate score was too close to the observed score to decide "
+                                      "`>=` and were re-scored in the reference's summation order"},
             "e2e": {"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": css["h2d"], "d2h_bytes_per_step": css["d2h"],
                     "api": "fpt_css_compute (drop-in, host float64 arrays in pinned memory), one call per chromosome",
                     "windows_scored": css["scored_e2e"]},

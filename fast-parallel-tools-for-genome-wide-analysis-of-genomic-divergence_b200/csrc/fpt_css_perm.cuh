@@ -142,58 +142,75 @@ FPT_D unsigned fpt_nibble_to_bytes(unsigned nib) { return ((nib & 0xfu) * 0x0020
 
 /* sum over A'xB' of q for the permutation owned by THIS lane, computed cooperatively by the warp.
    gmask = membership mask of the smaller group for this lane's permutation (0 for an idle lane);
-   qd = digit matrices [3][nrows][FPT_QD_STRIDE], nrows = m rounded up to 8. */
-FPT_D int fpt_bet_mma(unsigned long long gmask, const unsigned char *qd, int m) {
+   qd = digit matrices [ndigits][nrows][FPT_QD_STRIDE], nrows = m rounded up to 8.
+   The warp's 32 permutations form two 16-row tiles; every B fragment is loaded once and used by both. */
+FPT_D int fpt_bet_mma(unsigned long long gmask, const unsigned char *qd, int m, int ndigits) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntiles = (m + 7) >> 3, nrows = ntiles << 3, ksteps = (m + 31) >> 5;
-    int mine = 0;
     const unsigned glo = (unsigned)gmask, ghi = (unsigned)(gmask >> 32);      /* 32-bit halves: cheap shifts and shuffles */
-    for (int tile = 0; tile < 2; tile++) {              /* permutations of lanes 16*tile .. 16*tile+15 */
-        const unsigned lo1 = __shfl_sync(FPT_FULL_MASK, glo, 16 * tile + g), lo2 = __shfl_sync(FPT_FULL_MASK, glo, 16 * tile + g + 8);
-        unsigned hi1 = 0u, hi2 = 0u;
-        if (ksteps > 1) { hi1 = __shfl_sync(FPT_FULL_MASK, ghi, 16 * tile + g); hi2 = __shfl_sync(FPT_FULL_MASK, ghi, 16 * tile + g + 8); }
-        /* A fragments of k-step 0 (individuals 0..31) and 1 (32..63): nibbles t and t+4 of each half */
-        unsigned a0[4], a1[4];
-        const unsigned l1 = lo1 >> (4 * t), l2 = lo2 >> (4 * t), h1 = hi1 >> (4 * t), h2 = hi2 >> (4 * t);
-        a0[0] = fpt_nibble_to_bytes(l1); a0[1] = fpt_nibble_to_bytes(l2);
-        a0[2] = fpt_nibble_to_bytes(l1 >> 16); a0[3] = fpt_nibble_to_bytes(l2 >> 16);
-        a1[0] = fpt_nibble_to_bytes(h1); a1[1] = fpt_nibble_to_bytes(h2);
-        a1[2] = fpt_nibble_to_bytes(h1 >> 16); a1[3] = fpt_nibble_to_bytes(h2 >> 16);
-        int s1 = 0, s2 = 0;                             /* masked row sums of rows g and g+8 */
-        const unsigned char *colbase = qd + (size_t)g * FPT_QD_STRIDE + 4 * t;
-        const size_t dstride = (size_t)nrows * FPT_QD_STRIDE;
-        for (int nt = 0; nt < ntiles; nt++) {
-            int r[4] = { 0, 0, 0, 0 };
+    /* masks of my four rows: tile 0 rows g, g+8 (lanes g, g+8) and tile 1 rows g, g+8 (lanes 16+g, 24+g) */
+    unsigned lo[4], hi[4] = { 0u, 0u, 0u, 0u };
 #pragma unroll
-            for (int d = 2; d >= 0; d--) {
-                int c[4] = { 0, 0, 0, 0 };
-                const unsigned char *row = colbase + (size_t)d * dstride + (size_t)(8 * nt) * FPT_QD_STRIDE;
-                fpt_mma_u8(c, a0, *reinterpret_cast<const unsigned *>(row), *reinterpret_cast<const unsigned *>(row + 16));
-                if (ksteps > 1)
-                    fpt_mma_u8(c, a1, *reinterpret_cast<const unsigned *>(row + 32), *reinterpret_cast<const unsigned *>(row + 48));
+    for (int r = 0; r < 4; r++) lo[r] = __shfl_sync(FPT_FULL_MASK, glo, 8 * r + g);
+    if (ksteps > 1) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) r[i] = (r[i] << 8) + c[i];
-            }
-            /* columns 8nt + 2t, +1 held by this lane: keep those outside the group (padded columns are zero anyway) */
-            const unsigned w1 = nt < 4 ? lo1 : hi1, w2 = nt < 4 ? lo2 : hi2;
-            const int sh = ((8 * nt) & 31) + 2 * t;
-            const unsigned b1 = w1 >> sh, b2 = w2 >> sh;
-            if (!(b1 & 1u)) s1 += r[0];
-            if (!(b1 & 2u)) s1 += r[1];
-            if (!(b2 & 1u)) s2 += r[2];
-            if (!(b2 & 2u)) s2 += r[3];
-        }
-        s1 += __shfl_xor_sync(FPT_FULL_MASK, s1, 1); s1 += __shfl_xor_sync(FPT_FULL_MASK, s1, 2);
-        s2 += __shfl_xor_sync(FPT_FULL_MASK, s2, 1); s2 += __shfl_xor_sync(FPT_FULL_MASK, s2, 2);
-        const int myrow = lane & 15;                        /* my permutation's row inside its tile */
-        const int v1 = __shfl_sync(FPT_FULL_MASK, s1, 4 * (myrow & 7));
-        const int v2 = __shfl_sync(FPT_FULL_MASK, s2, 4 * (myrow & 7));
-        if ((lane >> 4) == tile) mine = myrow < 8 ? v1 : v2;
+        for (int r = 0; r < 4; r++) hi[r] = __shfl_sync(FPT_FULL_MASK, ghi, 8 * r + g);
     }
-    return mine;
+    /* A fragments: k-step 0 = individuals 0..31 (nibbles t, t+4 of the low half), k-step 1 = 32..63 (high half) */
+    unsigned a0[2][4], a1[2][4];
+#pragma unroll
+    for (int tile = 0; tile < 2; tile++) {
+        const unsigned l1 = lo[2 * tile] >> (4 * t), l2 = lo[2 * tile + 1] >> (4 * t);
+        const unsigned h1 = hi[2 * tile] >> (4 * t), h2 = hi[2 * tile + 1] >> (4 * t);
+        a0[tile][0] = fpt_nibble_to_bytes(l1); a0[tile][1] = fpt_nibble_to_bytes(l2);
+        a0[tile][2] = fpt_nibble_to_bytes(l1 >> 16); a0[tile][3] = fpt_nibble_to_bytes(l2 >> 16);
+        a1[tile][0] = fpt_nibble_to_bytes(h1); a1[tile][1] = fpt_nibble_to_bytes(h2);
+        a1[tile][2] = fpt_nibble_to_bytes(h1 >> 16); a1[tile][3] = fpt_nibble_to_bytes(h2 >> 16);
+    }
+    int sum[4] = { 0, 0, 0, 0 };                        /* masked row sums: tile 0 rows g, g+8; tile 1 rows g, g+8 */
+    const unsigned char *colbase = qd + (size_t)g * FPT_QD_STRIDE + 4 * t;
+    const size_t dstride = (size_t)nrows * FPT_QD_STRIDE;
+    for (int nt = 0; nt < ntiles; nt++) {
+        int r0[4] = { 0, 0, 0, 0 }, r1[4] = { 0, 0, 0, 0 };
+        for (int d = ndigits - 1; d >= 0; d--) {
+            const unsigned char *row = colbase + (size_t)d * dstride + (size_t)(8 * nt) * FPT_QD_STRIDE;
+            int c0[4] = { 0, 0, 0, 0 }, c1[4] = { 0, 0, 0, 0 };
+            const unsigned b0 = *reinterpret_cast<const unsigned *>(row), b1 = *reinterpret_cast<const unsigned *>(row + 16);
+            fpt_mma_u8(c0, a0[0], b0, b1);
+            fpt_mma_u8(c1, a0[1], b0, b1);
+            if (ksteps > 1) {
+                const unsigned b2 = *reinterpret_cast<const unsigned *>(row + 32), b3 = *reinterpret_cast<const unsigned *>(row + 48);
+                fpt_mma_u8(c0, a1[0], b2, b3);
+                fpt_mma_u8(c1, a1[1], b2, b3);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) { r0[i] = (r0[i] << 8) + c0[i]; r1[i] = (r1[i] << 8) + c1[i]; }
+        }
+        /* columns 8nt + 2t, +1 held by this lane: keep those outside the group (padded columns are zero anyway) */
+        const int sh = ((8 * nt) & 31) + 2 * t;
+        const bool upper = nt >= 4;
+        const unsigned m00 = (upper ? hi[0] : lo[0]) >> sh, m01 = (upper ? hi[1] : lo[1]) >> sh;
+        const unsigned m10 = (upper ? hi[2] : lo[2]) >> sh, m11 = (upper ? hi[3] : lo[3]) >> sh;
+        if (!(m00 & 1u)) sum[0] += r0[0];
+        if (!(m00 & 2u)) sum[0] += r0[1];
+        if (!(m01 & 1u)) sum[1] += r0[2];
+        if (!(m01 & 2u)) sum[1] += r0[3];
+        if (!(m10 & 1u)) sum[2] += r1[0];
+        if (!(m10 & 2u)) sum[2] += r1[1];
+        if (!(m11 & 1u)) sum[3] += r1[2];
+        if (!(m11 & 2u)) sum[3] += r1[3];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) { sum[r] += __shfl_xor_sync(FPT_FULL_MASK, sum[r], 1); sum[r] += __shfl_xor_sync(FPT_FULL_MASK, sum[r], 2); }
+    /* lane L owns row L%16 of tile L/16: that row sits in the quad of lanes 4*(L%8).. as sum[2*tile + (L%16 >= 8)] */
+    const int src = 4 * (lane & 7);
+    const int v0 = __shfl_sync(FPT_FULL_MASK, sum[0], src), v1 = __shfl_sync(FPT_FULL_MASK, sum[1], src);
+    const int v2 = __shfl_sync(FPT_FULL_MASK, sum[2], src), v3 = __shfl_sync(FPT_FULL_MASK, sum[3], src);
+    const int sel = ((lane >> 4) << 1) | ((lane >> 3) & 1);
+    return sel == 0 ? v0 : (sel == 1 ? v1 : (sel == 2 ? v2 : v3));
 }
 
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsize, long long wbase, long long nwin,
                      const unsigned char *__restrict__ status, int treshold, int runs, uint64_t seed,
                      const uint64_t *__restrict__ state_override, int chain, int qbits,
@@ -204,6 +221,7 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
     size_t off = 0;
     double *dist = (double *)(smem + off); off += (size_t)m * m * 8;
     const int use_mma = fpt_css_perm2_uses_mma(m);
+    const int ndigits = (qbits + 8) >> 3;                  /* q <= 2^qbits */
     const int qd_rows = ((m + 7) >> 3) << 3;
     unsigned char *qd = smem + off; if (use_mma) off += (size_t)3 * qd_rows * FPT_QD_STRIDE;
     unsigned *q = (unsigned *)(smem + off); off += (size_t)m * m * 4;
@@ -272,7 +290,7 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
         }
         const bool use_surrogate = usable && !__syncthreads_or(bad);
         if (use_mma) {                                      /* base-256 digits of q, zero padded to 8-row / 64-column tiles */
-            for (int e = tid; e < 3 * qd_rows * 16; e += T) {
+            for (int e = tid; e < ndigits * qd_rows * 16; e += T) {
                 const int d = e / (qd_rows * 16), rem = e - d * qd_rows * 16, n = rem >> 4, k4 = (rem & 15) << 2;
                 unsigned wv = 0;
                 for (int b = 0; b < 4; b++) {
@@ -387,7 +405,7 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
                             for (int i = 0; i + 1 < asize; i++) wa += (int)q[mine[i] * m + mine[i + 1]];
                             for (int i = 0; i + 1 < bsize; i++) wb += (int)q[mine[asize + i] * m + mine[asize + i + 1]];
                         }
-                        bet = (long long)fpt_bet_mma(gmask, qd, m);
+                        bet = (long long)fpt_bet_mma(gmask, qd, m, ndigits);
                     } else if (valid) {
                         fpt_surrogate(q, rowsum, m, mine, asize, bsize, use_a, bet, wa, wb);
                     }

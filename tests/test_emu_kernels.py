@@ -245,7 +245,7 @@ def test_css_perm_kernels_chunks_early_stop_and_scratch_paths(emu, oracle, chain
             X[1] = np.round(X[1])                                  # exact ties between permuted and observed scores
         st = np.full(n, 2, dtype=np.uint8)
         states = (np.arange(n, dtype=np.uint64) * 7919 + 13)
-        qbits = min(22, int(math.floor(math.log2(2 ** 31 / (min(asize, bsize) * m + 1)))))
+        qbits = min(15 if 8 <= m <= 64 else 22, int(math.floor(math.log2(2 ** 31 / (min(asize, bsize) * m + 1)))))
         for tres, runs in ((5, 300), (1000, 100), (1, 70)):
             want_p, want_h, want_n = [], [], []
             for w in range(n):
