@@ -600,7 +600,7 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
     if (p.perm2) {
         /* quantisation width: |smaller group| * m * 2^qbits must stay below 2^31 (integer surrogate sums) */
         const long long terms = (long long)std::min(asize, bsize) * m + 1;
-        int qb = fpt_css_perm2_uses_mma(m) ? 15 : 22;     /* tensor-core path: two base-256 digits (q <= 2^15) */
+        int qb = fpt_css_perm2_uses_mma(m) ? 23 : 22;     /* tensor-core path: three base-256 digits (q <= 2^23 fits 24 bits) */
         while (qb > 4 && (terms << qb) >= (1LL << 31)) qb--;
         CHECK(persistent_grid(c, fpt_css_perm2_kernel, p.perm_threads, p.smem_perm2, nwin, &grid));
         { ProfScope ps_("css_perm", st); fpt_css_perm2_kernel<<<grid, p.perm_threads, p.smem_perm2, st>>>(

@@ -93,10 +93,13 @@ FPT_D void fpt_warp_counts(const unsigned *__restrict__ planes, int m, int l, in
     const int lane = threadIdx.x & 31;
     const unsigned magic = fpt_div_magic(m);
     const int w0 = l >> 5, w1 = (r - 1) >> 5;
+    #pragma unroll 1
     for (int e = lane; e < fpt_tri(m); e += 32) w.A[e] = 0.0;
+    #pragma unroll 1
     for (int wc = w0; wc <= w1; wc += w.wch) {
         const int nw = min(w.wch, w1 - wc + 1);
         __syncwarp();
+        #pragma unroll 1
         for (int e = lane; e < nw * 2 * m; e += 32) {
             const int ww = wc + (e >= 2 * m ? fpt_fastdiv(e, magic) >> 1 : 0);
             unsigned mask = 0xffffffffu;
@@ -105,9 +108,12 @@ FPT_D void fpt_warp_counts(const unsigned *__restrict__ planes, int m, int l, in
             w.wbuf[e] = planes[(size_t)wc * 2 * m + e] & mask;
         }
         __syncwarp();
+        #pragma unroll 1
         for (int i = 1; i < m; i++) {
+            #pragma unroll 1
             for (int j = lane; j < i; j += 32) {
                 int cnt = 0;
+                #pragma unroll 1
                 for (int q = 0; q < nw; q++) {
                     const unsigned *row = w.wbuf + (size_t)q * 2 * m;
                     cnt += __popc(row[i] & row[m + j]) + __popc(row[m + i] & row[j]);
@@ -125,7 +131,9 @@ FPT_D int fpt_warp_fill(int m, const FptEigWork &w) {
     const int lane = threadIdx.x & 31, mm = m * m;
     long long blanks = 0;
     double sum = 0.0;
+    #pragma unroll 1
     for (int i = 1; i < m; i++)
+        #pragma unroll 1
         for (int j = lane; j < i; j += 32) {
             const double v = w.A[fpt_tri(i) + j];
             if (v < 0.00001) blanks += 2; else sum += 2.0 * v;
@@ -134,6 +142,7 @@ FPT_D int fpt_warp_fill(int m, const FptEigWork &w) {
     sum = fpt_warp_sum(sum);
     if (blanks > (long long)(mm / 2)) return 0;
     const double avg = __ddiv_rn(sum, (double)mm);
+    #pragma unroll 1
     for (int e = lane; e < fpt_tri(m); e += 32) if (w.A[e] < 0.00001) w.A[e] = avg;
     __syncwarp();
     return 1;
@@ -144,6 +153,7 @@ FPT_D int fpt_warp_fill(int m, const FptEigWork &w) {
 FPT_D int fpt_sturm_count(const double *d, const double *e2, int n, double x, double pivmin) {
     double q = d[0] - x;
     int cnt = q < 0.0 ? 1 : 0;
+    #pragma unroll 1
     for (int i = 1; i < n; i++) {
         if (fabs(q) < pivmin) q = -pivmin;
         q = (d[i] - x) - e2[i - 1] * fpt_fast_rcp(q);
@@ -162,31 +172,40 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
         return;
     }
     /* double centring on the packed triangle; a row sum visits j < i in the row, the diagonal, then j > i down the column */
+    #pragma unroll 1
     for (int e = lane; e < fpt_tri(m); e += 32) { const double v = A[e]; A[e] = v * v; }
     __syncwarp();
+    #pragma unroll 1
     for (int i = lane; i < m; i += 32) {
         double s = 0.0;
         const double *row = A + fpt_tri(i);
+        #pragma unroll 1
         for (int j = 0; j <= i; j++) s += row[j];
+        #pragma unroll 1
         for (int j = i + 1; j < m; j++) s += A[fpt_tri(j) + i];
         w.pv[i] = s / m;
     }
     __syncwarp();
     double g = 0.0;
+    #pragma unroll 1
     for (int i = 0; i < m; i++) g += w.pv[i];
     g /= m;
+    #pragma unroll 1
     for (int i = 0; i < m; i++) {
         const double ri = w.pv[i];
         double *row = A + fpt_tri(i);
+        #pragma unroll 1
         for (int j = lane; j <= i; j += 32) row[j] = -0.5 * (((row[j] - ri) - w.pv[j]) + g);
     }
     __syncwarp();
 
     /* Householder tridiagonalisation (LAPACK dsytd2, lower): H_k = I - tau v v', v(k+1) = 1, v(k+2:) stored in column k.
        Only the lower triangle is referenced and updated. Lane = row. */
+    #pragma unroll 1
     for (int k = 0; k + 2 < m; k++) {
         const double x0 = A[fpt_tri(k + 1) + k];
         double s2 = 0.0;
+        #pragma unroll 1
         for (int i = k + 2 + lane; i < m; i += 32) { const double x = A[fpt_tri(i) + k]; s2 += x * x; }
         s2 = fpt_warp_sum(s2);
         if (lane == 0) w.d[k] = A[fpt_tri(k) + k];
@@ -200,16 +219,20 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
         const double tau = (alpha - x0) / alpha;
         const double scal = 1.0 / (x0 - alpha);
         double *vv = w.y;                                 /* the reflector as a contiguous vector (y is free until step 4) */
+        #pragma unroll 1
         for (int i = k + 2 + lane; i < m; i += 32) { const double v = A[fpt_tri(i) + k] * scal; A[fpt_tri(i) + k] = v; vv[i] = v; }
         if (lane == 0) { A[fpt_tri(k + 1) + k] = 1.0; vv[k + 1] = 1.0; w.e[k] = alpha; w.tau[k] = tau; }
         __syncwarp();
         /* p = tau * A22 v, A22 symmetric and stored as its lower triangle: row part, then down the column (index grows by j+1) */
         double pvdot = 0.0;
+        #pragma unroll 1
         for (int i = k + 1 + lane; i < m; i += 32) {
             const double *row = A + fpt_tri(i);
             double s = 0.0;
+            #pragma unroll 1
             for (int j = k + 1; j <= i; j++) s += row[j] * vv[j];
             int idx = fpt_tri(i + 1) + i;
+            #pragma unroll 1
             for (int j = i + 1; j < m; j++) { s += A[idx] * vv[j]; idx += j + 1; }
             s *= tau;
             w.pv[i] = s;
@@ -217,12 +240,15 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
         }
         pvdot = fpt_warp_sum(pvdot);
         const double K = -0.5 * tau * pvdot;
+        #pragma unroll 1
         for (int i = k + 1 + lane; i < m; i += 32) w.wv[i] = w.pv[i] + K * vv[i];
         __syncwarp();
         /* A22 -= v w' + w v' on the lower triangle */
+        #pragma unroll 1
         for (int i = k + 1 + lane; i < m; i += 32) {
             double *row = A + fpt_tri(i);
             const double vi = vv[i], wi = w.wv[i];
+            #pragma unroll 1
             for (int j = k + 1; j <= i; j++) row[j] -= vi * w.wv[j] + wi * vv[j];
         }
         __syncwarp();
@@ -238,6 +264,7 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
     /* Gershgorin bounds and the norm used to scale T to O(1): the searches below run on d/tnorm, (e/tnorm)^2 (kept in
        pv / wv), which keeps every Sturm pivot inside single-precision range for the fast reciprocal */
     double glo = 1e300, ghi = -1e300;
+    #pragma unroll 1
     for (int i = lane; i < m; i += 32) {
         const double el = i > 0 ? fabs(w.e[i - 1]) : 0.0, er = i < m - 1 ? fabs(w.e[i]) : 0.0;
         glo = fmin(glo, w.d[i] - el - er);
@@ -247,12 +274,14 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
     const double tnorm = fmax(fabs(glo), fabs(ghi));
     if (!(tnorm > 0.0) || !(tnorm < 1e300)) {              /* B = 0 (all dissimilarities equal) or not finite */
         const double v = tnorm == 0.0 ? 0.0 : tnorm - tnorm;   /* 0, or NaN when the input was not finite */
+        #pragma unroll 1
         for (int j = lane; j < 2 * m; j += 32) X[j] = v;
         if (lane == 0 && evals3) { evals3[0] = v; evals3[1] = v; evals3[2] = v; }
         __syncwarp();
         return;
     }
     const double rnorm = 1.0 / tnorm;
+    #pragma unroll 1
     for (int i = lane; i < m; i += 32) {
         w.pv[i] = w.d[i] * rnorm;
         if (i < m - 1) { const double es = w.e[i] * rnorm; w.wv[i] = es * es; }
@@ -267,11 +296,13 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
     const int half = lane >> 4, hl = lane & 15;
     const int want = m - 1 - half;                         /* ascending index searched by this half-warp */
     double lo = glo, hi = ghi;
+    #pragma unroll 1
     for (int round = 0; round < 11; round++) {
         const double x = lo + (hi - lo) * ((double)(hl + 1) / 17.0);
         const int flag = fpt_sturm_count(w.pv, w.wv, m, x, pivmin) >= want + 1;
         const unsigned bal = (__ballot_sync(FPT_FULL_MASK, flag) >> (16 * half)) & 0xffffu;
         int js = 16;                                       /* first probe already above the eigenvalue */
+        #pragma unroll 1
         for (int b = 0; b < 16; b++) if ((bal >> b) & 1u) { js = b; break; }
         const double xl = __shfl_sync(FPT_FULL_MASK, x, 16 * half + (js > 0 ? js - 1 : 0));
         const double xh = __shfl_sync(FPT_FULL_MASK, x, 16 * half + (js < 16 ? js : 15));
@@ -284,11 +315,13 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
     double lam3 = 0.0;
     if (want_third && m >= 3) {                            /* diagnostics only: 33-section, 7 rounds */
         double l3 = glo, h3 = ghi;
+        #pragma unroll 1
         for (int round = 0; round < 7; round++) {
             const double x = l3 + (h3 - l3) * ((double)(lane + 1) / 33.0);
             const int flag = fpt_sturm_count(w.pv, w.wv, m, x, pivmin) >= m - 2;
             const unsigned bal = __ballot_sync(FPT_FULL_MASK, flag);
             int js = 32;
+            #pragma unroll 1
             for (int b = 0; b < 32; b++) if ((bal >> b) & 1u) { js = b; break; }
             const double xl = __shfl_sync(FPT_FULL_MASK, x, js > 0 ? js - 1 : 0);
             const double xh = __shfl_sync(FPT_FULL_MASK, x, js < 32 ? js : 31);
@@ -310,6 +343,7 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
         double *dd = w.lu + (size_t)c * 3 * m, *du = dd + m, *du2 = du + m;
         double *dl = (c == 0 ? w.pv : w.wv);               /* the scaled copies are no longer needed */
         double *y = w.y + (size_t)c * m;
+        #pragma unroll 1
         for (int i = 0; i < m; i++) {
             dd[i] = w.d[i] - lam;
             if (i < m - 1) { du[i] = w.e[i]; dl[i] = w.e[i]; }
@@ -317,6 +351,7 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
             const unsigned hsh = ((unsigned)i * 2654435761u + (unsigned)c * 40503u + 12345u) >> 8;
             y[i] = ((double)(hsh & 0xffffu) / 65536.0) - 0.5 + (c == 0 ? 1.0 : 0.0);
         }
+        #pragma unroll 1
         for (int i = 0; i < m - 1; i++) {
             if (fabs(dd[i]) >= fabs(dl[i])) {               /* no interchange */
                 if (dd[i] == 0.0) dd[i] = epsT;
@@ -334,15 +369,18 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
             }
         }
         if (dd[m - 1] == 0.0) dd[m - 1] = epsT;
+        #pragma unroll 1
         for (int i = 0; i < m; i++) dd[i] = 1.0 / dd[i];    /* pivots are only ever divided by */
     }
     __syncwarp();
+    #pragma unroll 1
     for (int iter = 0; iter < 3; iter++) {
         if (lane < 2) {
             const int c = lane;
             const double *rdd = w.lu + (size_t)c * 3 * m, *du = rdd + m, *du2 = du + m;
             const double *dl = (c == 0 ? w.pv : w.wv);
             double *y = w.y + (size_t)c * m;
+            #pragma unroll 1
             for (int i = 0; i < m - 1; i++) {              /* forward: replay interchanges and multipliers (dgtts2) */
                 const double f = dl[i];
                 if (f > 2.0) { const double t = y[i]; y[i] = y[i + 1]; y[i + 1] = t - (f - 4.0) * y[i]; }
@@ -350,25 +388,32 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
             }
             y[m - 1] *= rdd[m - 1];
             if (m > 1) y[m - 2] = (y[m - 2] - du[m - 2] * y[m - 1]) * rdd[m - 2];
+            #pragma unroll 1
             for (int i = m - 3; i >= 0; i--) y[i] = (y[i] - du[i] * y[i + 1] - du2[i] * y[i + 2]) * rdd[i];
             double mx = 0.0;
+            #pragma unroll 1
             for (int i = 0; i < m; i++) mx = fmax(mx, fabs(y[i]));
             if (!(mx > 0.0) || !(mx < 1e300)) {            /* overflow / breakdown: restart from a unit vector */
+                #pragma unroll 1
                 for (int i = 0; i < m; i++) y[i] = i == c ? 1.0 : 0.0;
                 mx = 1.0;
             }
             const double rm = 1.0 / mx;
             double nn = 0.0;
+            #pragma unroll 1
             for (int i = 0; i < m; i++) { y[i] *= rm; nn += y[i] * y[i]; }
             nn = 1.0 / sqrt(nn);
+            #pragma unroll 1
             for (int i = 0; i < m; i++) y[i] *= nn;
         }
         __syncwarp();
         if (lane == 1) {                                   /* keep the second vector orthogonal to the first */
             double *y0 = w.y, *y1 = w.y + m;
             double dot = 0.0;
+            #pragma unroll 1
             for (int i = 0; i < m; i++) dot += y0[i] * y1[i];
             double nn = 0.0;
+            #pragma unroll 1
             for (int i = 0; i < m; i++) { y1[i] -= dot * y0[i]; nn += y1[i] * y1[i]; }
             if (nn > 0.0) { nn = 1.0 / sqrt(nn); for (int i = 0; i < m; i++) y1[i] *= nn; }
         }
@@ -378,7 +423,9 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
         double rq = 0.0;
         if (lane < 2) {
             const double *y = w.y + (size_t)lane * m;
+            #pragma unroll 1
             for (int i = 0; i < m; i++) rq += w.d[i] * y[i] * y[i];
+            #pragma unroll 1
             for (int i = 0; i < m - 1; i++) rq += 2.0 * w.e[i] * y[i] * y[i + 1];
         }
         lam1 = __shfl_sync(FPT_FULL_MASK, rq, 0);
@@ -386,15 +433,18 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
     }
 
     /* back-transform: z = H_0 H_1 ... H_{m-3} y, applied last reflector first */
+    #pragma unroll 1
     for (int k = m - 3; k >= 0; k--) {
         const double tau = w.tau[k];
         if (tau == 0.0) continue;
         double s0 = 0.0, s1 = 0.0;
+        #pragma unroll 1
         for (int i = k + 1 + lane; i < m; i += 32) {
             const double v = A[fpt_tri(i) + k];
             s0 += v * w.y[i]; s1 += v * w.y[m + i];
         }
         s0 = tau * fpt_warp_sum(s0); s1 = tau * fpt_warp_sum(s1);
+        #pragma unroll 1
         for (int i = k + 1 + lane; i < m; i += 32) {
             const double v = A[fpt_tri(i) + k];
             w.y[i] -= s0 * v; w.y[m + i] -= s1 * v;
@@ -407,6 +457,7 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
     if (lam1 < 0.0 && -lam1 <= 1e-13 * tnorm) lam1 = 0.0;
     if (lam2 < 0.0 && -lam2 <= 1e-13 * fmax(fabs(lam1), tnorm * 1e-3)) lam2 = 0.0;
     const double r1 = sqrt(lam1), r2 = sqrt(lam2);
+    #pragma unroll 1
     for (int j = lane; j < m; j += 32) { X[2 * j] = w.y[j] * r1; X[2 * j + 1] = w.y[m + j] * r2; }
     if (lane == 0 && evals3) { evals3[0] = lam1; evals3[1] = lam2; evals3[2] = lam3; }
     __syncwarp();
@@ -421,12 +472,14 @@ fpt_css_mds_warp_kernel(const unsigned *__restrict__ planes, const double *__res
     FPT_DYN_SMEM(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const FptEigWork w = fpt_eig_carve(smem + (size_t)warp * fpt_eig_work_bytes(m, wch), m, wch);
+    #pragma unroll 1
     for (long long win = (long long)blockIdx.x * nwarp + warp; win < nwin; win += (long long)gridDim.x * nwarp) {
         const int l = wleft[win], r = wright[win];
         if (r <= l) { if (lane == 0) status[win] = 0; continue; }
         if (absdiff) {
             if (lane == 0) {                               /* compare_freq, css.c:245-264 */
                 double s = 0.0;
+                #pragma unroll 1
                 for (int i = r; i-- > l;) s = __dadd_rn(s, absdiff[i]);
                 s = __ddiv_rn(s, (double)(r - l));
                 w.A[0] = 0.0; w.A[1] = s; w.A[2] = 0.0;          /* packed: (0,0), (1,0), (1,1) */
