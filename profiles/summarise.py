@@ -20,7 +20,11 @@ KEYS = [
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-    "lts__t_bytes.sum", "sm__cycles_elapsed.max",
+    "lts__t_bytes.sum", "sm__cycles_elapsed.max", "sm__inst_executed_pipe_tensor.sum",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
 ]
 UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
 
@@ -60,7 +64,7 @@ def main():
         md.append("")
         try:
             rd, wr = vals["dram__bytes_read.sum"], vals["dram__bytes_write.sum"]
-            traffic[k] = float(rd[0].replace(",", "")) * UNIT.get(rd[1], 1.0) + float(wr[0].replace(",", "")) * UNIT.get(wr[1], 1.0)
+            traffic[{'css_perm2': 'css_perm', 'css_mds_warp': 'css_mds'}.get(k, k)] = float(rd[0].replace(",", "")) * UNIT.get(rd[1], 1.0) + float(wr[0].replace(",", "")) * UNIT.get(wr[1], 1.0)
         except Exception:
             pass
     with open(os.path.join(OUT, "%s_ncu_summary.md" % tag), "w") as f:
