@@ -176,7 +176,7 @@ def bench_css(lib_mod, args, rank, world, dist):
             local = torch.cat([torch.cat(out_s), torch.cat(out_p)])
             dist.all_gather_into_tensor(gathered, local)
 
-    launches_per_step = len(chroms) * 4                  # pack, window table, mds, permutations
+    launches_per_step = len(chroms) * 5                  # pack, window table, tridiagonalisation, eigenvectors, permutations
 
     def step_e2e():
         total = 0
@@ -241,7 +241,11 @@ def css_kernel_bytes(name, windows, nsnp_total, m):
     """algorithmic HBM bytes of one step, per kernel (DESIGN.md section 'Kernels and rooflines')"""
     if name == "css_perm":      # embedding in (16 m), status in (1), score + p out (16)
         return windows * (16 * m + 17)
-    if name == "css_mds":       # the window's bit-plane slab in (~2 words x 2 planes x m x 4), window bounds (8), X + evals + status out
+    if name == "css_tridiag":   # the window's bit-plane slab in, window bounds (8); tridiagonal (24 m) + reflectors (4 m (m-1)) + status out
+        return windows * (2 * 2 * m * 4 + 8 + 24 * m + 4 * m * (m - 1) + 1)
+    if name == "css_eigvec":    # tridiagonal + reflectors + status in, embedding (16 m) out
+        return windows * (24 * m + 4 * m * (m - 1) + 1 + 16 * m)
+    if name == "css_mds":       # fallback Jacobi kernel
         return windows * (2 * 2 * m * 4 + 8 + 16 * m + 25)
     if name == "css_pack":      # float64 genotypes in, two bit-planes out
         return nsnp_total * m * 8 + nsnp_total * m // 4

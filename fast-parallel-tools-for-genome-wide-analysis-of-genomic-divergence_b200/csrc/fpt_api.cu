@@ -477,7 +477,7 @@ static CssPlan css_plan(const DeviceCtx *c, int m) {
     p.mats_in_smem = fpt_css_smem_bytes(m, p.wch, 1) <= budget;
     if (!p.mats_in_smem && fpt_css_smem_bytes(m, p.wch, 0) > budget) p.wch = 1;
     p.smem_win = fpt_css_smem_bytes(m, p.wch, p.mats_in_smem);
-    const size_t per_warp = fpt_eig_work_bytes(m, 4);
+    const size_t per_warp = fpt_tridiag_work_bytes(m, 4);
     p.mds_warps = 2 * per_warp <= 32 * 1024 ? 2 : (per_warp <= budget ? 1 : 0);   /* small CTAs: many resident warps */
     p.smem_mds_warp = per_warp * (p.mds_warps > 0 ? p.mds_warps : 1);
     p.perm_threads = 256;
@@ -496,7 +496,7 @@ static CssPlan css_plan(const DeviceCtx *c, int m) {
 }
 
 struct CssWorkspace {
-    double *X, *Xruns, *sigma, *evals, *gscratch;
+    double *X, *Xruns, *sigma, *evals, *gscratch, *tri, *refl;
     int *iters;
     unsigned char *perm_scratch;
     size_t total;
@@ -515,12 +515,16 @@ static CssWorkspace css_carve(const CssPlan &p, long long nwin, int mds, unsigne
     size_t oI = take((size_t)nwin * nruns * 4);
     size_t oG = take(p.mats_in_smem ? 0 : (size_t)p.max_ctas * 2 * p.m * p.m * 8);
     size_t oP = take((size_t)p.max_ctas * p.perm_scratch_per_cta);
+    const bool warp_mds = p.mds_warps > 0 && mds != 1;      /* tridiagonal + reflectors handed from phase A to phase B */
+    size_t oT = take(warp_mds ? (size_t)nwin * 3 * p.m * 8 : 0);
+    size_t oR = take(warp_mds ? (size_t)nwin * ((size_t)p.m * (p.m - 1) / 2) * 8 : 0);
     w.total = off + 256;
     if (base) {
         w.X = (double *)(base + oX); w.Xruns = (double *)(base + oXr); w.sigma = (double *)(base + oS);
         w.evals = (double *)(base + oE); w.iters = (int *)(base + oI);
         w.gscratch = p.mats_in_smem ? nullptr : (double *)(base + oG);
         w.perm_scratch = p.perm_scratch_per_cta ? base + oP : nullptr;
+        w.tri = (double *)(base + oT); w.refl = (double *)(base + oR);
     }
     return w;
 }
@@ -573,9 +577,13 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
     if (mds == 0 || mds == 2) {
         if (p.mds_warps > 0) {
             const int block = 32 * p.mds_warps;
-            CHECK(persistent_grid(c, fpt_css_mds_warp_kernel, block, p.smem_mds_warp, (nwin + p.mds_warps - 1) / p.mds_warps, &grid));
-            { ProfScope ps_("css_mds", st); fpt_css_mds_warp_kernel<<<grid, block, p.smem_mds_warp, st>>>(planes, absdiff, m, wleft, wright, nwin, 4, ws.X,
-                                                                                          (probes && probes->evals) ? ws.evals : nullptr, status); }
+            CHECK(persistent_grid(c, fpt_css_tridiag_kernel, block, p.smem_mds_warp, (nwin + p.mds_warps - 1) / p.mds_warps, &grid));
+            { ProfScope ps_("css_tridiag", st); fpt_css_tridiag_kernel<<<grid, block, p.smem_mds_warp, st>>>(planes, absdiff, m, wleft, wright, nwin, 4, ws.tri, ws.refl, status); }
+            CU(cudaGetLastError());
+            const size_t smem_b = fpt_eigvec_work_bytes(m) * 4;
+            CHECK(persistent_grid(c, fpt_css_eigvec_kernel, 128, smem_b, (nwin + 3) / 4, &grid));
+            { ProfScope ps_("css_eigvec", st); fpt_css_eigvec_kernel<<<grid, 128, smem_b, st>>>(m, nwin, ws.tri, ws.refl, status, ws.X,
+                                                                                                (probes && probes->evals) ? ws.evals : nullptr); }
         } else {                                           /* cohorts too large for a warp's shared-memory slice */
             CHECK(persistent_grid(c, fpt_css_mds_kernel, 128, p.smem_win, nwin, &grid));
             grid = std::min(grid, p.max_ctas);

@@ -5,6 +5,9 @@
  * The reference needs only the two largest eigenvalues BY VALUE and their vectors, so a full
  * diagonalisation is two orders of magnitude more work than necessary. Per window this file does:
  *
+ * Two kernels (the first needs the m x m matrix in shared memory, the second only O(m) vectors and therefore runs
+ * with twice the resident warps — it is a chain of dependent fp64 operations — and each fits the instruction cache):
+ *
  *   1. pairwise opposite-homozygote counts from the window's bit-plane slab, fill_averages,
  *      double centring  B = -1/2 (S - r 1' - 1 r' + g),  S = D.D                     (O(m^2))
  *   2. Householder reduction of B to tridiagonal T (LAPACK dsytd2 scheme, lower)       (4/3 m^3 flops)
@@ -63,28 +66,6 @@ FPT_D double fpt_fast_rcp(double q) {
     r = fma(r, fma(-q, r, 1.0), r);
     r = fma(r, fma(-q, r, 1.0), r);
     return r;
-}
-
-FPT_HD size_t fpt_eig_work_bytes(int m, int wch) {
-    size_t doubles = (size_t)fpt_tri(m) + (size_t)5 * m + (size_t)2 * m + (size_t)6 * m;
-    size_t bytes = doubles * 8 + (size_t)wch * 2 * m * 4;
-    return (bytes + 15) & ~(size_t)15;
-}
-
-FPT_D FptEigWork fpt_eig_carve(unsigned char *base, int m, int wch) {
-    FptEigWork w;
-    double *p = (double *)base;
-    w.A = p; p += (size_t)fpt_tri(m);
-    w.d = p; p += m;
-    w.e = p; p += m;
-    w.tau = p; p += m;
-    w.pv = p; p += m;
-    w.wv = p; p += m;
-    w.y = p; p += 2 * m;
-    w.lu = p; p += 6 * m;
-    w.wbuf = (unsigned *)p;
-    w.wch = wch;
-    return w;
 }
 
 /* ---- step 1a: D (packed lower triangle, zero diagonal) from the bit-planes of SNPs [l, r); warp-level twin of
@@ -162,12 +143,17 @@ FPT_D int fpt_sturm_count(const double *d, const double *e2, int n, double x, do
     return cnt;
 }
 
-/* ---- steps 1c-5. A holds the filled D on entry; X (2m doubles) and evals3 are written by the warp. */
-FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, int want_third) {
+/* start of column k of the reflector store: strictly-lower part of the matrix, column by column, so that a reflector is one
+   contiguous run (coalesced for lane = row): column k holds rows k+1 .. m-1 */
+FPT_HD int fpt_refl_col(int m, int k) { return (k * (2 * m - k - 1)) >> 1; }
+
+/* ---- steps 1c-2 (phase A). A holds the filled D on entry. Leaves the tridiagonal (d, e) and reflector scales (tau) in the
+   work area and writes the reflectors to `refl` (global, m(m-1)/2 doubles, layout fpt_refl_col). */
+FPT_D void fpt_warp_tridiag(int m, const FptEigWork &w, double *__restrict__ refl) {
     const int lane = threadIdx.x & 31;
     double *A = w.A;
     if (m == 1) {
-        if (lane == 0) { X[0] = 0.0; X[1] = 0.0; if (evals3) { evals3[0] = 0.0; evals3[1] = 0.0; evals3[2] = 0.0; } }
+        if (lane == 0) { w.d[0] = 0.0; w.e[0] = 0.0; w.tau[0] = 0.0; }
         __syncwarp();
         return;
     }
@@ -220,8 +206,9 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
         const double scal = 1.0 / (x0 - alpha);
         double *vv = w.y;                                 /* the reflector as a contiguous vector (y is free until step 4) */
         #pragma unroll 1
-        for (int i = k + 2 + lane; i < m; i += 32) { const double v = A[fpt_tri(i) + k] * scal; A[fpt_tri(i) + k] = v; vv[i] = v; }
-        if (lane == 0) { A[fpt_tri(k + 1) + k] = 1.0; vv[k + 1] = 1.0; w.e[k] = alpha; w.tau[k] = tau; }
+        double *rcol = refl + fpt_refl_col(m, k) - (k + 1);   /* rcol[i] = v_i, i = k+1 .. m-1 */
+        for (int i = k + 2 + lane; i < m; i += 32) { const double v = A[fpt_tri(i) + k] * scal; vv[i] = v; rcol[i] = v; }
+        if (lane == 0) { vv[k + 1] = 1.0; rcol[k + 1] = 1.0; w.e[k] = alpha; w.tau[k] = tau; }
         __syncwarp();
         /* p = tau * A22 v, A22 symmetric and stored as its lower triangle: row part, then down the column (index grows by j+1) */
         double pvdot = 0.0;
@@ -260,7 +247,17 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
         if (m == 2) w.tau[0] = 0.0;
     }
     __syncwarp();
+}
 
+/* ---- steps 3-5 (phase B): the two largest eigenpairs of the tridiagonal in the work area (d, e, tau), back-transformed
+   through the reflectors in `refl`; X (2m doubles) and evals3 are written by the warp. Needs no m x m storage. */
+FPT_D void fpt_warp_eig(int m, const FptEigWork &w, const double *__restrict__ refl, double *X, double *evals3, int want_third) {
+    const int lane = threadIdx.x & 31;
+    if (m == 1) {
+        if (lane == 0) { X[0] = 0.0; X[1] = 0.0; if (evals3) { evals3[0] = 0.0; evals3[1] = 0.0; evals3[2] = 0.0; } }
+        __syncwarp();
+        return;
+    }
     /* Gershgorin bounds and the norm used to scale T to O(1): the searches below run on d/tnorm, (e/tnorm)^2 (kept in
        pv / wv), which keeps every Sturm pivot inside single-precision range for the fast reciprocal */
     double glo = 1e300, ghi = -1e300;
@@ -437,16 +434,17 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
     for (int k = m - 3; k >= 0; k--) {
         const double tau = w.tau[k];
         if (tau == 0.0) continue;
+        const double *rcol = refl + fpt_refl_col(m, k) - (k + 1);
         double s0 = 0.0, s1 = 0.0;
         #pragma unroll 1
         for (int i = k + 1 + lane; i < m; i += 32) {
-            const double v = A[fpt_tri(i) + k];
+            const double v = rcol[i];
             s0 += v * w.y[i]; s1 += v * w.y[m + i];
         }
         s0 = tau * fpt_warp_sum(s0); s1 = tau * fpt_warp_sum(s1);
         #pragma unroll 1
         for (int i = k + 1 + lane; i < m; i += 32) {
-            const double v = A[fpt_tri(i) + k];
+            const double v = rcol[i];
             w.y[i] -= s0 * v; w.y[m + i] -= s1 * v;
         }
         __syncwarp();
@@ -463,15 +461,46 @@ FPT_D void fpt_warp_cmds(int m, const FptEigWork &w, double *X, double *evals3, 
     __syncwarp();
 }
 
-/* mds 0 and the first half of mds 2: one WARP per window; warps of a CTA work on different windows.
-   Dynamic shared memory: (blockDim.x/32) work areas of fpt_eig_work_bytes(m, wch). */
+/* work areas: phase A needs the packed matrix, phase B only O(m) vectors — which is why they are separate kernels:
+   the eigen-solve is a chain of dependent fp64 operations and wants as many resident warps as possible */
+FPT_HD size_t fpt_tridiag_work_bytes(int m, int wch) {
+    size_t bytes = ((size_t)fpt_tri(m) + (size_t)7 * m) * 8 + (size_t)wch * 2 * m * 4;
+    return (bytes + 15) & ~(size_t)15;
+}
+FPT_D FptEigWork fpt_tridiag_carve(unsigned char *base, int m, int wch) {
+    FptEigWork w;
+    double *p = (double *)base;
+    w.A = p; p += (size_t)fpt_tri(m);
+    w.d = p; p += m; w.e = p; p += m; w.tau = p; p += m;
+    w.pv = p; p += m; w.wv = p; p += m;
+    w.y = p; p += 2 * m;                                   /* first half doubles as the contiguous reflector */
+    w.lu = 0;
+    w.wbuf = (unsigned *)p;
+    w.wch = wch;
+    return w;
+}
+FPT_HD size_t fpt_eigvec_work_bytes(int m) { return (size_t)13 * m * 8; }
+FPT_D FptEigWork fpt_eigvec_carve(unsigned char *base, int m) {
+    FptEigWork w;
+    double *p = (double *)base;
+    w.A = 0;
+    w.d = p; p += m; w.e = p; p += m; w.tau = p; p += m;
+    w.pv = p; p += m; w.wv = p; p += m;
+    w.y = p; p += 2 * m;
+    w.lu = p; p += 6 * m;
+    w.wbuf = 0; w.wch = 0;
+    return w;
+}
+
+/* phase A kernel: one WARP per window. tri_out: 3m doubles per window (d, e, tau); refl_out: m(m-1)/2 per window. */
 __global__ void __launch_bounds__(128)
-fpt_css_mds_warp_kernel(const unsigned *__restrict__ planes, const double *__restrict__ absdiff, int m,
-                        const int *__restrict__ wleft, const int *__restrict__ wright, long long nwin, int wch,
-                        double *__restrict__ Xout, double *__restrict__ evals_out, unsigned char *__restrict__ status) {
+fpt_css_tridiag_kernel(const unsigned *__restrict__ planes, const double *__restrict__ absdiff, int m,
+                       const int *__restrict__ wleft, const int *__restrict__ wright, long long nwin, int wch,
+                       double *__restrict__ tri_out, double *__restrict__ refl_out, unsigned char *__restrict__ status) {
     FPT_DYN_SMEM(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    const FptEigWork w = fpt_eig_carve(smem + (size_t)warp * fpt_eig_work_bytes(m, wch), m, wch);
+    const FptEigWork w = fpt_tridiag_carve(smem + (size_t)warp * fpt_tridiag_work_bytes(m, wch), m, wch);
+    const size_t nrefl = (size_t)m * (m - 1) / 2;
     #pragma unroll 1
     for (long long win = (long long)blockIdx.x * nwarp + warp; win < nwin; win += (long long)gridDim.x * nwarp) {
         const int l = wleft[win], r = wright[win];
@@ -489,8 +518,31 @@ fpt_css_mds_warp_kernel(const unsigned *__restrict__ planes, const double *__res
             fpt_warp_counts(planes, m, l, r, w);
         }
         if (!fpt_warp_fill(m, w)) { if (lane == 0) status[win] = 1; __syncwarp(); continue; }
-        fpt_warp_cmds(m, w, Xout + (size_t)win * 2 * m, evals_out ? evals_out + 3 * win : 0, evals_out != 0);
+        fpt_warp_tridiag(m, w, refl_out + (size_t)win * nrefl);
+        double *t = tri_out + (size_t)win * 3 * m;
+        #pragma unroll 1
+        for (int i = lane; i < m; i += 32) { t[i] = w.d[i]; t[m + i] = i < m - 1 ? w.e[i] : 0.0; t[2 * m + i] = i < m - 2 ? w.tau[i] : 0.0; }
         if (lane == 0) status[win] = 2;
+        __syncwarp();
+    }
+}
+
+/* phase B kernel: one WARP per kept window, O(m) shared memory per warp */
+__global__ void __launch_bounds__(128)
+fpt_css_eigvec_kernel(int m, long long nwin, const double *__restrict__ tri_in, const double *__restrict__ refl_in,
+                      const unsigned char *__restrict__ status, double *__restrict__ Xout, double *__restrict__ evals_out) {
+    FPT_DYN_SMEM(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const FptEigWork w = fpt_eigvec_carve(smem + (size_t)warp * fpt_eigvec_work_bytes(m), m);
+    const size_t nrefl = (size_t)m * (m - 1) / 2;
+    #pragma unroll 1
+    for (long long win = (long long)blockIdx.x * nwarp + warp; win < nwin; win += (long long)gridDim.x * nwarp) {
+        if (status[win] != 2) continue;
+        const double *t = tri_in + (size_t)win * 3 * m;
+        #pragma unroll 1
+        for (int i = lane; i < m; i += 32) { w.d[i] = t[i]; w.e[i] = t[m + i]; w.tau[i] = t[2 * m + i]; }
+        __syncwarp();
+        fpt_warp_eig(m, w, refl_in + (size_t)win * nrefl, Xout + (size_t)win * 2 * m, evals_out ? evals_out + 3 * win : 0, evals_out != 0);
         __syncwarp();
     }
 }

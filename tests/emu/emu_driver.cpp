@@ -103,9 +103,14 @@ void emu_css_mds(const unsigned *planes, const double *absdiff, int m, const int
 
 void emu_css_mds_warp(const unsigned *planes, const double *absdiff, int m, const int *wleft, const int *wright,
                       long long nwin, int wch, int warps, int grid, double *X, double *evals, unsigned char *status) {
-    size_t smem = fpt_eig_work_bytes(m, wch) * warps;
-    run_grid(grid, 32 * warps, smem, [=]() {
-        fpt_css_mds_warp_kernel(planes, absdiff, m, wleft, wright, nwin, wch, X, evals, status);
+    /* phase A (tridiagonalisation) then phase B (eigenvectors), as the library launches them */
+    std::vector<double> tri((size_t)nwin * 3 * m + 1), refl((size_t)nwin * ((size_t)m * (m - 1) / 2) + 1);
+    double *pt = tri.data(), *pr = refl.data();
+    run_grid(grid, 32 * warps, fpt_tridiag_work_bytes(m, wch) * warps, [=]() {
+        fpt_css_tridiag_kernel(planes, absdiff, m, wleft, wright, nwin, wch, pt, pr, status);
+    });
+    run_grid(grid, 32 * warps, fpt_eigvec_work_bytes(m) * warps, [=]() {
+        fpt_css_eigvec_kernel(m, nwin, pt, pr, status, X, evals);
     });
 }
 
