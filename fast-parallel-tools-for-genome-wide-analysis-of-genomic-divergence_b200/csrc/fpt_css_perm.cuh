@@ -68,32 +68,6 @@ FPT_D void fpt_shuffle_row(unsigned char *row, int m, const uint2 *rtab, uint64_
     }
 }
 
-/* The same shuffle, harvesting what the surrogate needs on the way. After step i, position i is final: its label is the
-   value just moved there, still in a register. So the membership mask of the smaller group and the two adjacent-pair sums
-   (pairs (i, i+1) inside A' = positions 0..asize-1 and inside B' = asize..m-1) are accumulated without re-reading the row. */
-FPT_D void fpt_shuffle_row_harvest(unsigned char *row, int m, const uint2 *rtab, uint64_t &st, int &used, const unsigned *q,
-                                   int asize, int use_a, unsigned long long &gmask, int &wa, int &wb) {
-    unsigned glo = 0u, ghi = 0u;
-    int sa = 0, sb = 0;
-    int next = -1;                                          /* label at position i + 1 (final) */
-    for (int i = m - 1; i > 0; i--) {
-        const uint2 lm = rtab[i + 1];
-        const int rr = (int)fpt_randint_fast((uint32_t)(i + 1), lm.x, lm.y, st, used);
-        const unsigned char t = row[i];
-        const int cur = row[rr];                            /* becomes the final label of position i */
-        row[i] = (unsigned char)cur; row[rr] = t;
-        const bool in_a = i < asize;
-        if (in_a == (use_a != 0)) { if (cur < 32) glo |= 1u << cur; else ghi |= 1u << (cur - 32); }
-        if (next >= 0 && i + 1 != asize) { const int v = (int)q[cur * m + next]; if (in_a) sa += v; else sb += v; }
-        next = cur;
-    }
-    const int cur = row[0];                                 /* position 0 is whatever is left */
-    if ((0 < asize) == (use_a != 0)) { if (cur < 32) glo |= 1u << cur; else ghi |= 1u << (cur - 32); }
-    if (next >= 0 && 1 != asize) { const int v = (int)q[cur * m + next]; if (0 < asize) sa += v; else sb += v; }
-    gmask = ((unsigned long long)ghi << 32) | glo;
-    wa = sa; wb = sb;
-}
-
 FPT_D void fpt_identity_row(unsigned char *row, int m) {
     /* 4 labels per store; the row is 4-byte aligned and padded to a multiple of 4 */
     unsigned *r4 = reinterpret_cast<unsigned *>(row);
@@ -407,8 +381,7 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
             const bool warp_active = (tid & ~31) * FPT_PERM_PP < nvalid;
             for (int j = 0; warp_active && j < FPT_PERM_PP; j++) {
                 const bool valid = j < mycount;
-                int used = 0, wa = 0, wb = 0;
-                unsigned long long gmask = 0ULL;
+                int used = 0;
                 if (valid) {
                     if (!chain) {
                         fpt_identity_row(mine, m);
@@ -416,15 +389,22 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
                            state already sits at the next permutation's start */
                         if (j == 0 || resync) st = fpt_lcg_skip(st_win, (uint64_t)(ndone + first + j) * (uint64_t)draws);
                     }
-                    if (use_surrogate && use_mma) fpt_shuffle_row_harvest(mine, m, rtab, st, used, q, asize, use_a, gmask, wa, wb);
-                    else fpt_shuffle_row(mine, m, rtab, st, used);
+                    fpt_shuffle_row(mine, m, rtab, st, used);
                     resync = used != draws;
                 }
                 int hit = 0;
                 bool exact = valid && !use_surrogate;
                 if (use_surrogate) {
-                    long long bet = 0;
+                    long long bet = 0; int wa = 0, wb = 0;
                     if (use_mma) {
+                        unsigned long long gmask = 0ULL;
+                        if (valid) {
+                            const unsigned char *gr = use_a ? mine : mine + asize;
+                            const int ng = use_a ? asize : bsize;
+                            for (int i = 0; i < ng; i++) gmask |= 1ULL << gr[i];
+                            for (int i = 0; i + 1 < asize; i++) wa += (int)q[mine[i] * m + mine[i + 1]];
+                            for (int i = 0; i + 1 < bsize; i++) wb += (int)q[mine[asize + i] * m + mine[asize + i + 1]];
+                        }
                         bet = (long long)fpt_bet_mma(gmask, qd, m, ndigits);
                     } else if (valid) {
                         fpt_surrogate(q, rowsum, m, mine, asize, bsize, use_a, bet, wa, wb);
