@@ -217,6 +217,32 @@ def bench_css(lib_mod, args, rank, world, dist):
     rechecks = int(lib.fpt_css_perm_rechecks())             # exact re-scorings since the library was loaded (all steps so far)
     windows_per_step = len(chroms) * nout                # window slots visited per rank and step
 
+    # the other two MDS variants of BASELINE configs[2], on chromosome 0 only (device-resident, one warm-up + one timed pass each)
+    variants = {}
+    if not args.small or True:
+        da, db, dpos = resident[0]
+        check(lib.fpt_dev_css_pack_f64(da.data_ptr(), db.data_ptr(), nsnp, asize, bsize, planes.data_ptr(), sp))
+        mx.zero_()
+        check(lib.fpt_dev_window_table(dpos.data_ptr(), nsnp, C.byref(r), wl.data_ptr(), wr.data_ptr(), mx.data_ptr(), sp))
+        for mds_v in (1, 2):
+            wsb = lib.fpt_dev_css_workspace_bytes(m, nout, mds_v)
+            wsv = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            sv, pv, stv = (torch.zeros(nout, dtype=torch.float64, device=dev), torch.zeros(nout, dtype=torch.float64, device=dev),
+                           torch.zeros(nout, dtype=torch.uint8, device=dev))
+            for it in range(2):
+                stv.zero_()
+                torch.cuda.synchronize()
+                e0.record(stream)
+                check(lib.fpt_dev_css_windows(planes.data_ptr(), None, asize, bsize, wl.data_ptr(), wr.data_ptr(), C.byref(r),
+                                              CSS["mct"], CSS["mcr"], mds_v, wsv.data_ptr(), wsb, sv.data_ptr(), pv.data_ptr(),
+                                              stv.data_ptr(), None, sp))
+                e1.record(stream)
+                torch.cuda.synchronize()
+            variants["mds%d" % mds_v] = {"windows_per_s": nout / (e0.elapsed_time(e1) * 1e-3), "ms_per_chromosome": e0.elapsed_time(e1),
+                                         "windows_scored": int((stv == 2).sum().item())}
+            del wsv
+    lib.fpt_profile_summary(buf, 4096)                   # drop the variants' launches from the per-kernel record
+
     # end to end through the drop-in host call
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
@@ -233,7 +259,7 @@ def bench_css(lib_mod, args, rank, world, dist):
     h2d = sum(av[1].nbytes + bv[1].nbytes + 4 * nsnp for (av, bv, apos, bpos) in host)
     d2h = len(chroms) * nout * 17
     return dict(ms=ms, ms_e2e=ms_e2e, windows_per_step=windows_per_step, scored=scored, scored_e2e=scored_e2e, prof=prof,
-                launches=launches_per_step * args.steps, h2d=h2d, d2h=d2h, rechecks=rechecks, clocks=clk.summary(),
+                launches=launches_per_step * args.steps, h2d=h2d, d2h=d2h, rechecks=rechecks, variants=variants, clocks=clk.summary(),
                 sample=(chroms[0], host[0], out_s[0].cpu().numpy(), out_p[0].cpu().numpy()))
 
 
@@ -562,6 +588,8 @@ def main():
                                  "(1000 x 438 gathers per window, reference summation order kept for bit-identical p-values); "
                                  "its HBM traffic is ~0.7 KB per window, so the HBM fraction is small by construction"},
             "clocks": css["clocks"],
+            "mds_variants": {"note": "same workload, chromosome 0 only, device-resident: mds=1 is SMACOF from 4 random starts, mds=2 is "
+                                     "classical MDS followed by SMACOF (css.c:208-218)", **css["variants"]},
         }
         # algorithmic shared-memory traffic of the permutation kernel against the SM-clock-scaled smem peak
         if "css_perm" in prof and css["clocks"].get("sm_mhz"):
