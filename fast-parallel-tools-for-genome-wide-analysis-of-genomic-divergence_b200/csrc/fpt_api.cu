@@ -513,7 +513,7 @@ static CssWorkspace css_carve(const CssPlan &p, long long nwin, int mds, unsigne
     size_t oS = take((size_t)nwin * nruns * 8);
     size_t oE = take((size_t)nwin * 3 * 8);
     size_t oI = take((size_t)nwin * nruns * 4);
-    size_t oG = take(p.mats_in_smem ? 0 : (size_t)p.max_ctas * 2 * p.m * p.m * 8);
+    size_t oG = take(p.mats_in_smem ? 0 : (size_t)p.max_ctas * fpt_css_mats_doubles(p.m) * 8);
     size_t oP = take((size_t)p.max_ctas * p.perm_scratch_per_cta);
     const bool warp_mds = p.mds_warps > 0 && mds != 1;      /* tridiagonal + reflectors handed from phase A to phase B */
     size_t oT = take(warp_mds ? (size_t)nwin * 3 * p.m * 8 : 0);

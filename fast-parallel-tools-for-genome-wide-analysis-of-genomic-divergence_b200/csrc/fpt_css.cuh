@@ -292,11 +292,14 @@ struct FptCssSmem {
     FptJacobiScratch js;
 };
 
+/* doubles taken by the two matrices of a window: M0 is m x m, M1 is m x (m|1) (SMACOF keeps B with an odd leading dimension) */
+FPT_HD size_t fpt_css_mats_doubles(int m) { return (size_t)2 * m * m + (size_t)m; }
+
 FPT_D FptCssSmem fpt_css_carve(unsigned char *smem, int m, int wch, int mats_in_smem, double *gscratch) {
     FptCssSmem s;
     size_t off = 0;
     const size_t mm = (size_t)m * m;
-    if (mats_in_smem) { s.M0 = (double *)(smem + off); off += mm * 8; s.M1 = (double *)(smem + off); off += mm * 8; }
+    if (mats_in_smem) { s.M0 = (double *)(smem + off); off += mm * 8; s.M1 = (double *)(smem + off); off += (mm + m) * 8; }
     else { s.M0 = gscratch; s.M1 = gscratch + mm; }
     s.X = (double *)(smem + off); off += (size_t)2 * m * 8;
     s.Z = (double *)(smem + off); off += (size_t)2 * m * 8;
@@ -317,7 +320,7 @@ FPT_D FptCssSmem fpt_css_carve(unsigned char *smem, int m, int wch, int mats_in_
 FPT_HD size_t fpt_css_smem_bytes(int m, int wch, int mats_in_smem) {
     const size_t mm = (size_t)m * m;
     const int half = ((m + 1) >> 1) + 1;
-    size_t off = (mats_in_smem ? 2 * mm * 8 : 0) + (size_t)4 * m * 8 + (size_t)m * 8 + (size_t)2 * half * 8 + 66 * 8 +
+    size_t off = (mats_in_smem ? (2 * mm + m) * 8 : 0) + (size_t)4 * m * 8 + (size_t)m * 8 + (size_t)2 * half * 8 + 66 * 8 +
                  (size_t)2 * half * 4;
     off = (off + 15) & ~(size_t)15;
     return off + (size_t)wch * 2 * m * 4;
@@ -330,7 +333,7 @@ fpt_css_mds_kernel(const unsigned *__restrict__ planes, const double *__restrict
                    int mats_in_smem, double *__restrict__ gscratch, double *__restrict__ Xout,
                    double *__restrict__ evals_out, unsigned char *__restrict__ status) {
     FPT_DYN_SMEM(smem);
-    FptCssSmem s = fpt_css_carve(smem, m, wch, mats_in_smem, gscratch ? gscratch + (size_t)blockIdx.x * 2 * m * m : 0);
+    FptCssSmem s = fpt_css_carve(smem, m, wch, mats_in_smem, gscratch ? gscratch + (size_t)blockIdx.x * fpt_css_mats_doubles(m) : 0);
     for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
         const int l = wleft[w], r = wright[w];
         if (r <= l) { if (threadIdx.x == 0) status[w] = FPT_WIN_EMPTY; continue; }
@@ -344,53 +347,58 @@ fpt_css_mds_kernel(const unsigned *__restrict__ planes, const double *__restrict
 }
 
 /* ============================================================================================
- * SMACOF (css.c:907-938). Per iteration, exactly the reference's sequence: B(Z) from the current
- * distances (b_ij = -delta_ij/d_ij, 0 when d_ij < 1e-5; b_ii = -sum_j b_ij accumulated with j counting
- * down), X = B Z / m with the products accumulated over ascending j (dgemm order), new distances,
- * stress, Z = X; loop while first pass or (stress drop > eps and k <= max_iters). Distances and B are
- * symmetric, so each pair is evaluated once and mirrored. The only departure from the reference's
- * operation order is the stress sum, which is a fixed-order parallel tree instead of one running sum.
+ * SMACOF (css.c:907-938). Per iteration, the reference's sequence: B(Z) from the current distances
+ * (b_ij = -delta_ij/d_ij, 0 when d_ij < 1e-5; b_ii = -sum_j b_ij accumulated with j counting down), X = B Z / m with the
+ * products accumulated over ascending j (dgemm order), new distances, stress, Z = X; loop while first pass or
+ * (stress drop > eps and k <= max_iters).
+ *
+ * One pass over the m(m-1)/2 pairs per iteration does all the pair work: distance of the NEW configuration (IEEE sqrt,
+ * same expression as calc_dist), its contribution to the stress, and b_ij for the NEXT Guttman transform — distances and B
+ * are symmetric, so each pair is evaluated once and mirrored, and the distance matrix itself is never stored. B lives in a
+ * matrix with an odd leading dimension, so the row pass (thread = one row and coordinate, the reference's exact operation
+ * order) reads it without bank conflicts. The only departure from the reference's operation order is the stress sum, which
+ * is a fixed-order parallel tree instead of one running sum.
  */
-FPT_D double fpt_css_dist_stress(const double *X, const double *delta, double *Dm, int m, const FptCssScratch &sc) {
-    const int mm = m * m;
-    double part = 0.0;
-    for (int e = threadIdx.x; e < mm; e += blockDim.x) {
-        const int i = e / m, j = e - i * m;
-        if (j < i) {
-            const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
-            const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-            Dm[e] = d; Dm[j * m + i] = d;
-            const double err = __dsub_rn(d, delta[e]);
-            part = __dadd_rn(part, __dmul_rn(err, err));
-        } else if (j == i) {
-            Dm[e] = 0.0;
-        }
-    }
-    return fpt_block_sum(part, sc.red);      /* has the barriers that publish Dm */
+FPT_HD int fpt_css_ldb(int m) { return m | 1; }
+
+FPT_D void fpt_pair_of(int p, int &i, int &j) {             /* p = i(i-1)/2 + j, 0 <= j < i */
+    int r = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+    while ((r * (r - 1)) / 2 > p) r--;
+    while (((r + 1) * r) / 2 <= p) r++;
+    i = r; j = p - (r * (r - 1)) / 2;
 }
 
-FPT_D double fpt_css_smacof(const double *delta, double *Dm, int m, double *X, double *Z, int max_iters, double eps,
+/* stress of configuration X against delta; leaves B(X) (off-diagonal) in Bm */
+FPT_D double fpt_css_pairs_pass(const double *X, const double *delta, double *Bm, int m, const FptCssScratch &sc) {
+    const int npairs = (m * (m - 1)) >> 1, ldb = fpt_css_ldb(m);
+    double part = 0.0;
+    for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+        int i, j;
+        fpt_pair_of(p, i, j);
+        const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
+        const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        const double dl = delta[i * m + j];
+        const double err = __dsub_rn(d, dl);
+        part = __dadd_rn(part, __dmul_rn(err, err));
+        const double b = d < 0.00001 ? 0.0 : __ddiv_rn(__dmul_rn(-1.0, dl), d);
+        Bm[i * ldb + j] = b; Bm[j * ldb + i] = b;
+    }
+    return fpt_block_sum(part, sc.red);                     /* has the barriers that publish Bm */
+}
+
+FPT_D double fpt_css_smacof(const double *delta, double *Bm, int m, double *X, double *Z, int max_iters, double eps,
                             const FptCssScratch &sc, int *iters_out) {
-    const int mm = m * m;
+    const int ldb = fpt_css_ldb(m);
     for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) Z[e] = X[e];
     __syncthreads();
-    double sigma = fpt_css_dist_stress(X, delta, Dm, m, sc), prev = 0.0;
+    double sigma = fpt_css_pairs_pass(X, delta, Bm, m, sc), prev = 0.0;
     int k = 0;
     while (k == 0 || (__dsub_rn(prev, sigma) > eps && k <= max_iters)) {
         prev = sigma;
         k++;
-        for (int e = threadIdx.x; e < mm; e += blockDim.x) {             /* Dm: distances -> B off-diagonal */
-            const int i = e / m, j = e - i * m;
-            if (j < i) {
-                const double d = Dm[e];
-                const double b = d < 0.00001 ? 0.0 : __ddiv_rn(__dmul_rn(-1.0, delta[e]), d);
-                Dm[e] = b; Dm[j * m + i] = b;
-            }
-        }
-        __syncthreads();
         for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {           /* one (row, coordinate) per thread */
             const int i = e >> 1, c = e & 1;
-            const double *brow = Dm + (size_t)i * m;
+            const double *brow = Bm + (size_t)i * ldb;
             double dsum = 0.0;
             for (int j = m; j--;) if (j != i) dsum = __dadd_rn(dsum, brow[j]);
             const double bii = __dmul_rn(-1.0, dsum);
@@ -399,7 +407,7 @@ FPT_D double fpt_css_smacof(const double *delta, double *Dm, int m, double *X, d
             X[e] = __ddiv_rn(acc, (double)m);
         }
         __syncthreads();
-        sigma = fpt_css_dist_stress(X, delta, Dm, m, sc);
+        sigma = fpt_css_pairs_pass(X, delta, Bm, m, sc);
         for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) Z[e] = X[e];
         __syncthreads();
     }
@@ -416,7 +424,7 @@ fpt_css_smacof_kernel(const unsigned *__restrict__ planes, const double *__restr
                       const double *__restrict__ Xin, double *__restrict__ Xruns, double *__restrict__ sigma_runs,
                       int *__restrict__ iters_runs, unsigned char *__restrict__ status) {
     FPT_DYN_SMEM(smem);
-    FptCssSmem s = fpt_css_carve(smem, m, wch, mats_in_smem, gscratch ? gscratch + (size_t)blockIdx.x * 2 * m * m : 0);
+    FptCssSmem s = fpt_css_carve(smem, m, wch, mats_in_smem, gscratch ? gscratch + (size_t)blockIdx.x * fpt_css_mats_doubles(m) : 0);
     const long long nitems = nwin * nruns;
     for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
         const long long w = it / nruns;

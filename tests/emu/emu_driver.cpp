@@ -94,7 +94,7 @@ void emu_css_absdiff(const double *a, const double *b, long long n, double *out)
 void emu_css_mds(const unsigned *planes, const double *absdiff, int m, const int *wleft, const int *wright,
                  long long nwin, int wch, int mats_in_smem, int grid, double *X, double *evals, unsigned char *status) {
     size_t smem = fpt_css_smem_bytes(m, wch, mats_in_smem);
-    std::vector<double> gs(mats_in_smem ? 1 : (size_t)grid * 2 * m * m);
+    std::vector<double> gs(mats_in_smem ? 1 : (size_t)grid * fpt_css_mats_doubles(m));
     double *gp = mats_in_smem ? 0 : gs.data();
     run_grid(grid, 128, smem, [=]() {
         fpt_css_mds_kernel(planes, absdiff, m, wleft, wright, nwin, wch, mats_in_smem, gp, X, evals, status);
@@ -119,7 +119,7 @@ void emu_css_smacof(const unsigned *planes, const double *absdiff, int m, const 
                     const uint64_t *state_override, int max_iters, double eps, const double *Xin, double *Xruns,
                     double *sigma_runs, int *iters_runs, unsigned char *status) {
     size_t smem = fpt_css_smem_bytes(m, wch, mats_in_smem);
-    std::vector<double> gs(mats_in_smem ? 1 : (size_t)grid * 2 * m * m);
+    std::vector<double> gs(mats_in_smem ? 1 : (size_t)grid * fpt_css_mats_doubles(m));
     double *gp = mats_in_smem ? 0 : gs.data();
     run_grid(grid, 128, smem, [=]() {
         fpt_css_smacof_kernel(planes, absdiff, m, wleft, wright, wbase, nwin, wch, mats_in_smem, gp, nruns, random_start, seed,
