@@ -431,10 +431,11 @@ fpt_fet_window_kernel(const double *__restrict__ snp_scores, const int *__restri
         const int s = threadIdx.x;
         if (s < FPT_FET_NSAMPLES) offs[s] = s * n;
         __syncthreads();
-        for (;;) {
+        for (int pass = 0;; pass++) {
+            int used = 0;
             if (s < FPT_FET_NSAMPLES) {
                 uint64_t st = fpt_lcg_skip(st_win, (uint64_t)offs[s]);
-                int used = 0, v0 = 0, v1 = 0;
+                int v0 = 0, v1 = 0;
                 if (use_hist) {
                     unsigned short *hrow = hist + (size_t)s * n;
                     for (int i = 0; i < n; i++) hrow[i] = 0;
@@ -451,6 +452,8 @@ fpt_fet_window_kernel(const double *__restrict__ snp_scores, const int *__restri
                 reps[s] = val;
                 cons[s] = used;
             }
+            /* common case: no replicate had a rejected draw, so the assumed offsets s*n were right */
+            if (pass == 0 && !__syncthreads_or(s < FPT_FET_NSAMPLES && used != n)) break;
             if (threadIdx.x == 0) changed = 0;
             __syncthreads();
             if (threadIdx.x == 0) {                      /* replicate s starts after the draws of 0..s-1 */
