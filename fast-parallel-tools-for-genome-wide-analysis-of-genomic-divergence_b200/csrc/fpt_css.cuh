@@ -399,21 +399,11 @@ FPT_D double fpt_css_smacof(const double *delta, double *Bm, int m, double *X, d
         for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {           /* one (row, coordinate) per thread */
             const int i = e >> 1, c = e & 1;
             const double *brow = Bm + (size_t)i * ldb;
-            const double *zc = Z + c;
-            /* b_ii = -sum_{j != i} b_ij, j counting down (css.c:814-826): two plain loops around the diagonal */
             double dsum = 0.0;
-#pragma unroll 4
-            for (int j = m - 1; j > i; j--) dsum = __dadd_rn(dsum, brow[j]);
-#pragma unroll 4
-            for (int j = i - 1; j >= 0; j--) dsum = __dadd_rn(dsum, brow[j]);
+            for (int j = m; j--;) if (j != i) dsum = __dadd_rn(dsum, brow[j]);
             const double bii = __dmul_rn(-1.0, dsum);
-            /* row i of B times column c of Z, j ascending (dgemm order), the diagonal term in its place */
             double acc = 0.0;
-#pragma unroll 4
-            for (int j = 0; j < i; j++) acc = __dadd_rn(acc, __dmul_rn(brow[j], zc[2 * j]));
-            acc = __dadd_rn(acc, __dmul_rn(bii, zc[2 * i]));
-#pragma unroll 4
-            for (int j = i + 1; j < m; j++) acc = __dadd_rn(acc, __dmul_rn(brow[j], zc[2 * j]));
+            for (int j = 0; j < m; j++) acc = __dadd_rn(acc, __dmul_rn(j == i ? bii : brow[j], Z[2 * j + c]));
             X[e] = __ddiv_rn(acc, (double)m);
         }
         __syncthreads();
