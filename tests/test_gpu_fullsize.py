@@ -1,0 +1,174 @@
+"""Parity at BASELINE.json's full sizes, where the CPU oracle cannot re-run everything: size-independent properties over
+the whole output (independent recount of every contingency table, symmetry of the test under swapping populations / alleles,
+idempotence, layout independence, sharded == unsharded) plus oracle spot checks on random SNPs and windows, and the device-
+resident API against the host API."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import checkers
+from checkers import dptr, iptr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c1():
+    """BASELINE configs[0]: 1 M SNPs over 100 Mb, 20+20 individuals"""
+    import fpt_b200.synth as synth
+    return synth.chromosome_fast(20261018, 100_000_000, 1_000_000, 20, 20)
+
+
+@pytest.fixture(scope="module")
+def c3():
+    """one chromosome of BASELINE configs[2]: 214 285 SNPs over 21.4 Mb, 20+20 individuals"""
+    import fpt_b200.synth as synth
+    return synth.chromosome_fast(20261020, 21_428_500, 214_285, 20, 20)
+
+
+def test_fet_full_size_tables_scores_and_symmetry(fpt, oracle, c1):
+    a, b = c1["acodes"].reshape(-1, 20), c1["bcodes"].reshape(-1, 20)
+    tab, sc = fpt.fet_per_snp(c1["acodes"], c1["bcodes"], 20, 20)
+    want = np.stack([(a == 3).sum(1), (a == -3).sum(1), (b == 3).sum(1), (b == -3).sum(1)], 1).astype(np.int32)
+    assert np.array_equal(tab, want)                                  # every one of the 1 M tables, recounted independently
+    assert np.all(np.isfinite(sc)) and np.all(sc >= 0)
+    # the test is symmetric under swapping the populations and under swapping the alleles
+    swap_pop, swap_all = fpt.fet_tables(tab[:, [2, 3, 0, 1]]), fpt.fet_tables(tab[:, [1, 0, 3, 2]])
+    for other in (swap_pop, swap_all):
+        np.testing.assert_allclose(other, sc, rtol=1e-11, atol=1e-13)
+        assert np.array_equal(other == 0, sc == 0)
+    rng = np.random.default_rng(0)
+    idx = rng.choice(tab.shape[0], size=20000, replace=False)
+    t = np.ascontiguousarray(tab[idx])
+    so = np.zeros(idx.size)
+    oracle.fpt_oracle_fet_tables(iptr(t), idx.size, dptr(so))
+    np.testing.assert_allclose(sc[idx], so, rtol=1e-9, atol=1e-13)
+
+
+def test_fet_full_size_scan_spot_checks_and_sharding(fpt, oracle, c1):
+    regend, wsize, wstep, seed = 100_000_000, 2500, 500, 77
+    pos = c1["pos"]
+    s, d, w = fpt.fet_scan(c1["acodes"], c1["bcodes"], pos, 20, 20, regend, wsize, wstep, 0.95, seed=seed)
+    n = regend // wstep
+    assert w.sum() > 0.9 * n
+    s2, d2, w2 = fpt.fet_scan(c1["acodes"], c1["bcodes"], pos, 20, 20, regend, wsize, wstep, 0.95, seed=seed)
+    assert np.array_equal(s, s2) and np.array_equal(d, d2)            # idempotent
+    tab, snp = fpt.fet_per_snp(c1["acodes"], c1["bcodes"], 20, 20, want_tables=False)
+    rng = np.random.default_rng(1)
+    for wi in rng.choice(np.nonzero(w)[0], size=300, replace=False):
+        l = int(np.searchsorted(pos, wi * wstep, "left"))
+        r = int(np.searchsorted(pos, wi * wstep + wsize, "right"))
+        buf = snp[l:r].copy()
+        out = np.zeros(2)
+        oracle.fpt_oracle_fet_window(dptr(buf), r - l, 0.95, 100, oracle.fpt_oracle_window_state(seed, int(wi), 0), dptr(out))
+        assert out[0] == s[wi] and out[1] == pytest.approx(d[wi], rel=1e-12, abs=1e-15)
+    from fpt_b200.sharding import partition_windows, snp_slice
+    parts = []
+    for wb, we in partition_windows(n, 3):
+        lo, hi = snp_slice(pos, wb, we, wsize, wstep)
+        parts.append(fpt.fet_scan(c1["acodes"][lo * 20:hi * 20], c1["bcodes"][lo * 20:hi * 20], pos[lo:hi], 20, 20, regend, wsize, wstep,
+                                  0.95, seed=seed, window_begin=wb, window_end=we))
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), s) and np.array_equal(np.concatenate([p[1] for p in parts]), d)
+
+
+def test_fet_genome_scale_tables_symmetry_and_spot_checks(fpt, oracle):
+    """BASELINE configs[3] shape (coverage up to 500), 4 M tables: log-space arithmetic"""
+    import fpt_b200.synth as synth
+    T = synth.coverage_tables(11, 4_000_000, 20, 500)
+    sc = fpt.fet_tables(T)
+    assert np.all(np.isfinite(sc)) and np.all(sc >= 0)
+    np.testing.assert_allclose(fpt.fet_tables(np.ascontiguousarray(T[:, [2, 3, 0, 1]])), sc, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(fpt.fet_tables(np.ascontiguousarray(T[:, [1, 0, 3, 2]])), sc, rtol=1e-9, atol=1e-11)
+    idx = np.random.default_rng(2).choice(T.shape[0], size=20000, replace=False)
+    t = np.ascontiguousarray(T[idx])
+    so = np.zeros(idx.size)
+    oracle.fpt_oracle_fet_tables(iptr(t), idx.size, dptr(so))
+    np.testing.assert_allclose(sc[idx], so, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("mds", [0, 2])
+def test_css_full_size_spot_checks_layouts_and_sharding(fpt, oracle, c3, mds):
+    import fpt_b200.synth as synth
+    regend, wsize, wstep, seed, mct, mcr = 21_428_500, 2500, 500, 5, 1000, 1000
+    pos = c3["pos"]
+    n = regend // wstep
+    s, p, w = fpt.css_scan(c3["acodes"], c3["bcodes"], pos, 20, 20, regend, wsize, wstep, mct, mcr, mds=mds, seed=seed)
+    assert w.sum() > 0.8 * n and np.all((p[w == 1] > 0) & (p[w == 1] <= 1))
+    av, bv, _, _ = synth.reference_layout(c3)
+    if mds == 0:
+        s2, p2, w2 = fpt.css_scan(av, bv, pos, 20, 20, regend, wsize, wstep, mct, mcr, mds=mds, seed=seed)
+        assert np.array_equal(s, s2, equal_nan=True) and np.array_equal(p, p2)         # float64 layout == int8 codes, idempotent
+    rng = np.random.default_rng(3)
+    bad = 0
+    picks = rng.choice(np.nonzero(w)[0], size=60 if mds == 0 else 25, replace=False)
+    for wi in picks:
+        l = int(np.searchsorted(pos, wi * wstep, "left"))
+        r = int(np.searchsorted(pos, wi * wstep + wsize, "right"))
+        pv = np.zeros(1)
+        so = oracle.fpt_oracle_css_window(dptr(av[l * 20:r * 20].copy()), dptr(bv[l * 20:r * 20].copy()), 20, 20, r - l, 0, mds, mct, mcr,
+                                          oracle.fpt_oracle_window_state(seed, int(wi), 0), oracle.fpt_oracle_window_state(seed, int(wi), 1),
+                                          dptr(pv), None, None)
+        if abs(s[wi] - so) <= 1e-5 * abs(so):
+            assert p[wi] == pv[0]
+        else:
+            bad += 1
+    assert bad <= (0 if mds == 0 else 1)
+    from fpt_b200.sharding import partition_windows, snp_slice
+    if mds == 0:
+        parts = []
+        for wb, we in partition_windows(n, 4):
+            lo, hi = snp_slice(pos, wb, we, wsize, wstep)
+            parts.append(fpt.css_scan(c3["acodes"][lo * 20:hi * 20], c3["bcodes"][lo * 20:hi * 20], pos[lo:hi], 20, 20, regend, wsize, wstep,
+                                      mct, mcr, mds=mds, seed=seed, window_begin=wb, window_end=we))
+        assert np.array_equal(np.concatenate([q[0] for q in parts]), s, equal_nan=True)
+        assert np.array_equal(np.concatenate([q[1] for q in parts]), p)
+
+
+def test_device_resident_api_matches_host_api(fpt, c3):
+    """the path bench.py times (`value`): device pointers + the caller's stream"""
+    import torch
+    import fpt_b200._lib as L
+    from fpt_b200._lib import ScanRange, check
+    lib = L.load()
+    dev = torch.device("cuda", 0)
+    nsnp = 60000
+    regend, wsize, wstep, seed = int(c3["pos"][nsnp - 1]) // 500 * 500, 2500, 500, 9
+    pos = c3["pos"][:nsnp]
+    a8, b8 = c3["acodes"][:nsnp * 20], c3["bcodes"][:nsnp * 20]
+    n = regend // wstep
+    r = ScanRange()
+    r.regend, r.wsize, r.wstep, r.semantics, r.window_begin, r.window_end, r.seed = regend, wsize, wstep, 0, 0, n, seed
+    st = torch.cuda.Stream()
+    sp = C.c_void_p(st.cuda_stream)
+    with torch.cuda.stream(st):
+        da, db, dpos = torch.from_numpy(a8).to(dev), torch.from_numpy(b8).to(dev), torch.from_numpy(pos).to(dev)
+        wl, wr = torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.int32, device=dev)
+        mx = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(lib.fpt_dev_window_table(dpos.data_ptr(), nsnp, C.byref(r), wl.data_ptr(), wr.data_ptr(), mx.data_ptr(), sp))
+        # FET
+        tab = torch.empty(nsnp * 4, dtype=torch.int32, device=dev)
+        snp = torch.empty(nsnp, dtype=torch.float64, device=dev)
+        check(lib.fpt_dev_fet_count_i8(da.data_ptr(), db.data_ptr(), nsnp, 20, 20, tab.data_ptr(), sp))
+        check(lib.fpt_dev_fet_score(tab.data_ptr(), nsnp, 40, 0, snp.data_ptr(), sp))
+        fs, fd = torch.zeros(n, dtype=torch.float64, device=dev), torch.zeros(n, dtype=torch.float64, device=dev)
+        ff = torch.zeros(n, dtype=torch.uint8, device=dev)
+        check(lib.fpt_dev_fet_windows(snp.data_ptr(), wl.data_ptr(), wr.data_ptr(), C.byref(r), int(mx.item()), 0.95, None, fs.data_ptr(),
+                                      fd.data_ptr(), ff.data_ptr(), sp))
+        # CSS
+        planes = torch.empty(lib.fpt_dev_css_planes_bytes(nsnp, 40) // 4, dtype=torch.int32, device=dev)
+        check(lib.fpt_dev_css_pack_i8(da.data_ptr(), db.data_ptr(), nsnp, 20, 20, planes.data_ptr(), sp))
+        wsb = lib.fpt_dev_css_workspace_bytes(40, n, 0)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        cs, cp = torch.zeros(n, dtype=torch.float64, device=dev), torch.zeros(n, dtype=torch.float64, device=dev)
+        cst = torch.zeros(n, dtype=torch.uint8, device=dev)
+        check(lib.fpt_dev_css_windows(planes.data_ptr(), None, 20, 20, wl.data_ptr(), wr.data_ptr(), C.byref(r), 100, 100, 0, ws.data_ptr(), wsb,
+                                      cs.data_ptr(), cp.data_ptr(), cst.data_ptr(), None, sp))
+    st.synchronize()
+    hs, hd, hw = fpt.fet_scan(a8, b8, pos, 20, 20, regend, wsize, wstep, 0.95, seed=seed)
+    assert np.array_equal(ff.cpu().numpy(), hw)
+    assert np.array_equal(np.where(hw == 1, fs.cpu().numpy(), 0), hs) and np.array_equal(np.where(hw == 1, fd.cpu().numpy(), 0), hd)
+    hcs, hcp, hcw = fpt.css_scan(a8, b8, pos, 20, 20, regend, wsize, wstep, 100, 100, mds=0, seed=seed)
+    scored = cst.cpu().numpy() == 2
+    assert np.array_equal(scored & (cs.cpu().numpy() != -1.0), hcw == 1)
+    assert np.array_equal(np.where(hcw == 1, cs.cpu().numpy(), 0), hcs, equal_nan=True) and np.array_equal(np.where(hcw == 1, cp.cpu().numpy(), 0), hcp)
