@@ -33,11 +33,16 @@ def test_fet_full_size_tables_scores_and_symmetry(fpt, oracle, c1):
     want = np.stack([(a == 3).sum(1), (a == -3).sum(1), (b == 3).sum(1), (b == -3).sum(1)], 1).astype(np.int32)
     assert np.array_equal(tab, want)                                  # every one of the 1 M tables, recounted independently
     assert np.all(np.isfinite(sc)) and np.all(sc >= 0)
-    # the test is symmetric under swapping the populations and under swapping the alleles
-    swap_pop, swap_all = fpt.fet_tables(tab[:, [2, 3, 0, 1]]), fpt.fet_tables(tab[:, [1, 0, 3, 2]])
+    # The reference's two-tailed rule walks its FIRST tail towards the first minimum cell in clockwise order, so
+    # it is symmetric under swapping the populations / the alleles only when that minimum is unique; there it must be.
+    srt = np.sort(tab, axis=1)
+    uniq = srt[:, 0] < srt[:, 1]
+    assert uniq.mean() > 0.3
+    swap_pop = fpt.fet_tables(np.ascontiguousarray(tab[:, [2, 3, 0, 1]]))
+    swap_all = fpt.fet_tables(np.ascontiguousarray(tab[:, [1, 0, 3, 2]]))
     for other in (swap_pop, swap_all):
-        np.testing.assert_allclose(other, sc, rtol=1e-11, atol=1e-13)
-        assert np.array_equal(other == 0, sc == 0)
+        np.testing.assert_allclose(other[uniq], sc[uniq], rtol=1e-11, atol=1e-13)
+        assert np.array_equal(other[uniq] == 0, sc[uniq] == 0)
     rng = np.random.default_rng(0)
     idx = rng.choice(tab.shape[0], size=20000, replace=False)
     t = np.ascontiguousarray(tab[idx])
@@ -78,8 +83,12 @@ def test_fet_genome_scale_tables_symmetry_and_spot_checks(fpt, oracle):
     T = synth.coverage_tables(11, 4_000_000, 20, 500)
     sc = fpt.fet_tables(T)
     assert np.all(np.isfinite(sc)) and np.all(sc >= 0)
-    np.testing.assert_allclose(fpt.fet_tables(np.ascontiguousarray(T[:, [2, 3, 0, 1]])), sc, rtol=1e-9, atol=1e-11)
-    np.testing.assert_allclose(fpt.fet_tables(np.ascontiguousarray(T[:, [1, 0, 3, 2]])), sc, rtol=1e-9, atol=1e-11)
+    srt = np.sort(T, axis=1)
+    # symmetric only where the minimum cell is unique and, for N <= 67, where the reference's rounding-dependent
+    # `P2 < P0` ties do not interfere (that domain is pinned bit-for-bit against the reference elsewhere)
+    uniq = (srt[:, 0] < srt[:, 1]) & (T.sum(1) > 67)
+    np.testing.assert_allclose(fpt.fet_tables(np.ascontiguousarray(T[:, [2, 3, 0, 1]]))[uniq], sc[uniq], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(fpt.fet_tables(np.ascontiguousarray(T[:, [1, 0, 3, 2]]))[uniq], sc[uniq], rtol=1e-9, atol=1e-11)
     idx = np.random.default_rng(2).choice(T.shape[0], size=20000, replace=False)
     t = np.ascontiguousarray(T[idx])
     so = np.zeros(idx.size)
