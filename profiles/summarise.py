@@ -64,7 +64,7 @@ def main():
         md.append("")
         try:
             rd, wr = vals["dram__bytes_read.sum"], vals["dram__bytes_write.sum"]
-            traffic[{'css_perm2': 'css_perm', 'css_mds_warp': 'css_mds'}.get(k, k)] = float(rd[0].replace(",", "")) * UNIT.get(rd[1], 1.0) + float(wr[0].replace(",", "")) * UNIT.get(wr[1], 1.0)
+            traffic[{'css_perm2': 'css_perm'}.get(k, k)] = float(rd[0].replace(",", "")) * UNIT.get(rd[1], 1.0) + float(wr[0].replace(",", "")) * UNIT.get(wr[1], 1.0)
         except Exception:
             pass
     with open(os.path.join(OUT, "%s_ncu_summary.md" % tag), "w") as f:
