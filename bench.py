@@ -49,10 +49,11 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel):
-    """per-launch DRAM bytes of `kernel` from the committed ncu capture, if one has been summarised"""
+def ncu_traffic(kernel, what="traffic"):
+    """per-launch DRAM bytes (or warp instructions, what="inst") of `kernel` from the committed ncu capture, if one has
+    been summarised"""
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "ncu_%s.json" % what)) as f:
             return json.load(f).get(kernel)
     except Exception:
         return None
@@ -584,20 +585,24 @@ def main():
                          "peak_source": hbm_src, "traffic": ncu_traffic(dom),
                          "share_of_step": {k: round(v["ms"] / tot, 4) for k, v in prof.items()},
                          "kernel_ms_per_launch": {k: v["ms"] / v["launches"] for k, v in prof.items()},
-                         "note": "the permutation kernel is bound by shared-memory gathers feeding a dependent fp64 add chain "
-                                 "(1000 x 438 gathers per window, reference summation order kept for bit-identical p-values); "
-                                 "its HBM traffic is ~0.7 KB per window, so the HBM fraction is small by construction"},
+                         "note": "the permutation kernel is instruction-issue bound (48-bit LCG label shuffles, u8 IMMA between-group "
+                                 "sums over a quantised distance matrix held in shared memory, exact fp64 re-scoring of near ties); "
+                                 "it reads ~0.7 KB per window from HBM, so the HBM fraction is small by construction; see "
+                                 "roofline_issue for the bound that applies"},
             "clocks": css["clocks"],
             "mds_variants": {"note": "same workload, chromosome 0 only, device-resident: mds=1 is SMACOF from 4 random starts, mds=2 is "
                                      "classical MDS followed by SMACOF (css.c:208-218)", **css["variants"]},
         }
-        # algorithmic shared-memory traffic of the permutation kernel against the SM-clock-scaled smem peak
-        if "css_perm" in prof and css["clocks"].get("sm_mhz"):
-            gathers = nout * CSS["mcr"] * (CSS["asize"] * CSS["bsize"] + m - 2)
-            smem_peak = 128.0 * 148 * css["clocks"]["sm_mhz"] * 1e6 / 1e9
-            smem_ach = gathers * 8 / (prof["css_perm"]["ms"] / prof["css_perm"]["launches"] * 1e-3) / 1e9
-            line["roofline_smem"] = {"kernel": "css_perm", "bound": "smem", "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s",
-                                     "frac": smem_ach / smem_peak, "peak_source": "128 B/clk/SM x 148 SMs x sampled SM clock"}
+        # issue-slot roofline of the dominant kernel: warp instructions of one launch (ncu capture of the same workload,
+        # profiles/ncu_inst.json) over the live launch time, against 4 schedulers x 148 SMs x the sampled SM clock
+        n_inst = ncu_traffic(dom, "inst")
+        if n_inst and css["clocks"].get("sm_mhz"):
+            issue_peak = 4 * 148 * css["clocks"]["sm_mhz"] * 1e6 / 1e9
+            issue_ach = n_inst / (per_launch_ms * 1e-3) / 1e9
+            line["roofline_issue"] = {"kernel": dom, "bound": "issue", "achieved": issue_ach, "peak": issue_peak,
+                                      "unit": "Gwarp-inst/s", "frac": issue_ach / issue_peak,
+                                      "peak_source": "1 warp-inst/clk/scheduler x 4 x 148 SMs x sampled SM clock",
+                                      "inst_per_launch": n_inst}
         if world == 1 and not args.skip_cpu:
             cb = cpu_css(1000)
             if cb is not None:                           # scale the sample to roughly 15 s of CPU wall time

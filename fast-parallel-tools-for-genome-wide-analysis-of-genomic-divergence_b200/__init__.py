@@ -11,6 +11,11 @@ Modules mirror the reference's Cython extension modules, so its Statistic classe
 ``api``                         extended entry points: compact inputs, window ranges, probes, device API
 ``sharding``                    contiguous genome-range sharding over the GPUs of one node
 ``synth``                       synthetic genotype generator of SURVEY.md section 8(d)
+``regions``                     significant-region calling (tools/SignificantCSSRegions.py, tools/FilterFisherScores.py)
+``ingest``                      VCF / GTrack text -> genotype arrays (tools/VCFConvert.py), native scanner
+``results``                     result-file writers / readers of the runner tools, Python-2 number formatting
+``stat_shims``                  Python-3 stand-ins for FisherExactScoreStat / CategoryClusterSeparationStat `_compute`
+``tools``                       per-chromosome drivers (tools/FisherExactTestSNPTool.py, tools/ClusterSeparationScore.py)
 ==============================  ==========================================================================
 
 All compute goes through ``libfpt_b200.so`` (hand-written CUDA behind the C ABI of ``include/fpt_b200.h``).

@@ -28,6 +28,10 @@ class ScanRange(C.Structure):
                 ("states_resample", C.c_void_p), ("states_init", C.c_void_p)]
 
 
+class ChromRun(C.Structure):
+    _fields_ = [("name_off", C.c_int64), ("name_len", C.c_int32), ("reserved", C.c_int32), ("first_record", C.c_int64)]
+
+
 class CssProbes(C.Structure):
     _fields_ = [("status", C.c_void_p), ("X", C.c_void_p), ("evals", C.c_void_p), ("hits", C.c_void_p),
                 ("nperm", C.c_void_p), ("smacof_iters", C.c_void_p), ("smacof_sigma", C.c_void_p)]
@@ -71,6 +75,11 @@ SYMBOLS = {
     "fpt_dev_css_workspace_bytes": (C.c_size_t, [_I, C.c_int64, _I]),
     "fpt_dev_css_windows": (_I, [_P, _P, _I, _I, _P, _P, C.POINTER(ScanRange), _I, _I, _I, _P, C.c_size_t, _P, _P, _P,
                                  C.POINTER(CssProbes), _P]),
+    "fpt_vcf_scan": (_I, [C.c_char_p, C.c_size_t, _P, _P, _P]),
+    "fpt_vcf_parse": (_I, [C.c_char_p, C.c_size_t, C.c_int64, _I, _I, _I, _P, _I, C.c_int64, _P, _P, _P, C.c_int64, _P]),
+    "fpt_gtrack_scan": (_I, [C.c_char_p, C.c_size_t, _P]),
+    "fpt_gtrack_parse": (_I, [C.c_char_p, C.c_size_t, _I, _I, _I, C.c_int64, _P, _P, _P, C.c_int64, _P]),
+    "fpt_compact_codes": (_I, [_P, C.c_int64, _P]),
 }
 
 _lib = None

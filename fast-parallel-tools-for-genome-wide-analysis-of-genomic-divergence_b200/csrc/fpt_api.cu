@@ -985,3 +985,6 @@ extern "C" int fpt_css_compute(double *avals, double *bvals, int *apos, int *bpo
     (void)regstart;
     return css_dropin(avals, bvals, apos, bpos, regend, wsize, wstep, alen, blen, treshold, runs, drosophila, mds, scores, p, FPT_SCAN_SERIAL);
 }
+
+/* ================================================================================================ text ingest */
+#include "fpt_ingest.h"

@@ -181,6 +181,32 @@ int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff, int asize
                         void *workspace, size_t workspace_bytes, double *scores, double *p, uint8_t *status,
                         const fpt_css_probes *probes, void *stream);
 
+/* ================================================================================================
+ * Text ingest (host only). VCF and GTrack "valued points" text -> positions plus one int8 code per
+ * individual and SNP (3 / 0 / -3, -128 for the reference's -10000), i.e. the `fpt_genotypes` compact layout.
+ * Replaces tools/VCFConvert.py:5-89 (GT table, "#CHROM" header, GT slot taken from the first record's FORMAT, one point
+ * per record and selected individual) and the reading loop of statistics/fisher/testFisher.c:193-227.
+ * Chromosomes come back as runs of consecutive records that share a CHROM / seqid string.
+ */
+typedef struct fpt_chrom_run {
+    int64_t name_off;       /* byte offset of the name inside the text buffer */
+    int32_t name_len;
+    int32_t reserved;
+    int64_t first_record;   /* index of the run's first record */
+} fpt_chrom_run;
+
+int fpt_vcf_scan(const char *buf, size_t len, int64_t *header_off, int64_t *body_off, int64_t *nrecords);
+/* codes: nrecords * nsamples int8, record-major, sample order = sample_cols (0-based VCF column numbers).
+   A genotype outside the reference's table (a KeyError there) gives FPT_ERR_ARG naming record and column. */
+int fpt_vcf_parse(const char *buf, size_t len, int64_t body_off, int chrom_col, int pos_col, int format_col,
+                  const int32_t *sample_cols, int nsamples, int64_t nrecords, int8_t *codes, int32_t *pos,
+                  fpt_chrom_run *runs, int64_t max_runs, int64_t *nruns);
+int fpt_gtrack_scan(const char *buf, size_t len, int64_t *nrecords);
+int fpt_gtrack_parse(const char *buf, size_t len, int seqid_col, int start_col, int value_col, int64_t nrecords,
+                     int32_t *pos, double *vals, fpt_chrom_run *runs, int64_t max_runs, int64_t *nruns);
+/* reference-layout float64 values -> compact codes */
+int fpt_compact_codes(const double *vals, int64_t n, int8_t *codes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -467,6 +467,86 @@ static void jacobi_eig(double *A, double *V, int n) {
     }
 }
 
+
+/* Householder tridiagonalisation + implicit-shift QL for cohorts where cyclic Jacobi would take minutes (m > 128).
+   Same contract as jacobi_eig: eigenvalues on A's diagonal, eigenvectors in V's columns. The rotations are applied to the
+   transposed eigenvector matrix so that the inner loops run over contiguous memory. */
+static void tridiag_ql_eig(double *A, double *V, int n) {
+    double *d = (double *)calloc((size_t)n + 1, sizeof(double)), *e = (double *)calloc((size_t)n + 1, sizeof(double));
+    double *Q = (double *)malloc((size_t)n * n * sizeof(double));   /* rows = basis vectors (Q^T) */
+    double *u = (double *)malloc((size_t)n * sizeof(double)), *w = (double *)malloc((size_t)n * sizeof(double));
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) Q[(size_t)i * n + j] = i == j;
+    /* reduce from the top: step k annihilates A[k+2.., k] with H = I - beta u u' acting on indices k+1..n-1 */
+    for (int k = 0; k + 2 < n; k++) {
+        double sigma = 0;
+        for (int i = k + 2; i < n; i++) sigma += A[(size_t)i * n + k] * A[(size_t)i * n + k];
+        double x0 = A[(size_t)(k + 1) * n + k];
+        if (sigma == 0.0) continue;
+        double norm = sqrt(x0 * x0 + sigma), alpha = x0 > 0 ? -norm : norm;
+        u[k + 1] = x0 - alpha;
+        for (int i = k + 2; i < n; i++) u[i] = A[(size_t)i * n + k];
+        double beta = 1.0 / (norm * (norm + fabs(x0)));           /* 2 / u'u */
+        /* w = beta A u ; K = beta/2 u'w ; w -= K u ; A -= u w' + w u' (trailing block) */
+        for (int i = k + 1; i < n; i++) {
+            double acc = 0; const double *row = A + (size_t)i * n;
+            for (int j = k + 1; j < n; j++) acc += row[j] * u[j];
+            w[i] = beta * acc;
+        }
+        double kk = 0;
+        for (int i = k + 1; i < n; i++) kk += u[i] * w[i];
+        kk *= 0.5 * beta;
+        for (int i = k + 1; i < n; i++) w[i] -= kk * u[i];
+        for (int i = k + 1; i < n; i++) {
+            double *row = A + (size_t)i * n; const double ui = u[i], wi = w[i];
+            for (int j = k + 1; j < n; j++) row[j] -= ui * w[j] + wi * u[j];
+        }
+        A[(size_t)(k + 1) * n + k] = A[(size_t)k * n + k + 1] = alpha;
+        for (int i = k + 2; i < n; i++) A[(size_t)i * n + k] = A[(size_t)k * n + i] = 0.0;
+        /* Q^T <- Q^T H: every row r of Q gets r -= beta (r.u) u */
+        for (int r = 0; r < n; r++) {
+            double *row = Q + (size_t)r * n; double acc = 0;
+            for (int j = k + 1; j < n; j++) acc += row[j] * u[j];
+            acc *= beta;
+            for (int j = k + 1; j < n; j++) row[j] -= acc * u[j];
+        }
+    }
+    /* Q currently holds the product H1 H2 ... as a matrix whose COLUMNS are the tridiagonal basis; transpose into rows */
+    for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) {
+        double t = Q[(size_t)i * n + j]; Q[(size_t)i * n + j] = Q[(size_t)j * n + i]; Q[(size_t)j * n + i] = t;
+    }
+    for (int i = 0; i < n; i++) { d[i] = A[(size_t)i * n + i]; e[i] = i + 1 < n ? A[(size_t)(i + 1) * n + i] : 0.0; }
+    /* implicit QL; rotation (i, i+1) mixes rows i and i+1 of Q */
+    for (int l = 0; l < n; l++) {
+        for (int iter = 0; iter < 300; iter++) {
+            int mm = l;
+            for (; mm + 1 < n; mm++) {
+                double dd = fabs(d[mm]) + fabs(d[mm + 1]);
+                if (fabs(e[mm]) <= 2.220446049250313e-16 * dd) break;
+            }
+            if (mm == l) break;
+            double g = (d[l + 1] - d[l]) / (2.0 * e[l]), r = hypot(g, 1.0);
+            g = d[mm] - d[l] + e[l] / (g + (g >= 0 ? fabs(r) : -fabs(r)));
+            double s = 1.0, c = 1.0, p = 0.0; int i;
+            for (i = mm - 1; i >= l; i--) {
+                double f = s * e[i], b = c * e[i];
+                r = hypot(f, g); e[i + 1] = r;
+                if (r == 0.0) { d[i + 1] -= p; e[mm] = 0.0; break; }
+                s = f / r; c = g / r; g = d[i + 1] - p;
+                r = (d[i] - g) * s + 2.0 * c * b; p = s * r; d[i + 1] = g + p; g = c * r - b;
+                double *r0 = Q + (size_t)i * n, *r1 = Q + (size_t)(i + 1) * n;
+                for (int k = 0; k < n; k++) { double f1 = r1[k]; r1[k] = s * r0[k] + c * f1; r0[k] = c * r0[k] - s * f1; }
+            }
+            if (r == 0.0 && i >= l) continue;
+            d[l] -= p; e[l] = g; e[mm] = 0.0;
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        A[(size_t)i * n + i] = d[i];
+        for (int j = 0; j < n; j++) V[(size_t)j * n + i] = Q[(size_t)i * n + j];
+    }
+    free(d); free(e); free(Q); free(u); free(w);
+}
+
 void fpt_oracle_cmds(const double *D, int m, double *X, double evals[3]) {
     /* css.c:505-560: B = -1/2 Z (D.D) Z with Z = I - 11'/m, formed by the same two products
        (Z*(D.D) then *Z); the two largest eigenvalues by value; X = Q sqrt(L), no guard on L < 0 */
@@ -475,19 +555,22 @@ void fpt_oracle_cmds(const double *D, int m, double *X, double evals[3]) {
     double *B = (double *)malloc(mm * sizeof(double)), *V = (double *)malloc(mm * sizeof(double));
     double zo = -1.0 / m, zd = (m - 1) / (m * 1.0);
     for (size_t i = 0; i < mm; i++) S[i] = D[i] * D[i];
-    for (int i = 0; i < m; i++)
-        for (int j = 0; j < m; j++) {
-            double acc = 0;
-            for (int k = 0; k < m; k++) acc += (i == k ? zd : zo) * S[k * m + j];
-            T[i * m + j] = acc;
+    /* k-outer accumulation: every T[i][j] still sums k = 0..m-1 in order (bit-identical), the loads are contiguous */
+    for (int i = 0; i < m; i++) {
+        double *Ti = T + (size_t)i * m;
+        for (int j = 0; j < m; j++) Ti[j] = 0;
+        for (int k = 0; k < m; k++) {
+            const double z = i == k ? zd : zo; const double *Sk = S + (size_t)k * m;
+            for (int j = 0; j < m; j++) Ti[j] += z * Sk[j];
         }
+    }
     for (int i = 0; i < m; i++)
         for (int j = 0; j < m; j++) {
             double acc = 0;
             for (int k = 0; k < m; k++) acc += T[i * m + k] * (k == j ? zd : zo);
             B[i * m + j] = acc * -0.5;
         }
-    jacobi_eig(B, V, m);
+    if (m > 128) tridiag_ql_eig(B, V, m); else jacobi_eig(B, V, m);
     int i1 = -1, i2 = -1, i3 = -1;                  /* top three by value */
     for (int i = 0; i < m; i++) {
         double e = B[i * m + i];

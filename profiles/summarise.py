@@ -43,6 +43,7 @@ def main():
           "`gpurun` on a B200 from `python bench.py --chromosomes 2 --steps 1 --warmup 1 --skip-cpu`; raw metric tables in",
           "`%s_<kernel>_raw.csv`. Times under ncu are serialised and cold-cache: compare shares, not absolutes." % tag, ""]
     traffic = {}
+    insts = {}
     for k in kernels:
         rep = os.path.join(SRC, "prof_%s.ncu-rep" % k)
         if not os.path.exists(rep):
@@ -67,6 +68,8 @@ def main():
             traffic[{'css_perm2': 'css_perm'}.get(k, k)] = float(rd[0].replace(",", "")) * UNIT.get(rd[1], 1.0) + float(wr[0].replace(",", "")) * UNIT.get(wr[1], 1.0)
         except Exception:
             pass
+        if "smsp__inst_executed.sum" in vals:
+            insts[{'css_perm2': 'css_perm'}.get(k, k)] = float(vals["smsp__inst_executed.sum"][0].replace(",", ""))
     with open(os.path.join(OUT, "%s_ncu_summary.md" % tag), "w") as f:
         f.write("\n".join(md) + "\n")
     tpath = os.path.join(OUT, "ncu_traffic.json")
@@ -75,6 +78,10 @@ def main():
         old = json.load(open(tpath))
     old.update(traffic)
     json.dump(old, open(tpath, "w"), indent=1, sort_keys=True)
+    ipath = os.path.join(OUT, "ncu_inst.json")          # warp instructions per launch, for the issue-slot roofline
+    old = json.load(open(ipath)) if os.path.exists(ipath) else {}
+    old.update(insts)
+    json.dump(old, open(ipath, "w"), indent=1, sort_keys=True)
     # launch list -> per-kernel totals and shares
     for fn in sorted(os.listdir(SRC)):
         if fn.startswith("launches_%s" % tag) and fn.endswith(".csv"):

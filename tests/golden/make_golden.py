@@ -120,7 +120,36 @@ def css_fixture():
     np.savez_compressed(os.path.join(HERE, "css_golden.npz"), **out)
 
 
+def vcf_fixture():
+    """small.vcf (synthetic, two chromosomes, phased and unphased calls, missing calls, extra FORMAT slots) and the GTrack
+    text the reference's own converter (tools/VCFConvert.py, Python 2: its print statements are rewritten as calls, nothing
+    else is touched) makes of it for two populations; one requested individual is absent from the header."""
+    import re
+    src = open("/root/reference/tools/VCFConvert.py").read()
+    src = re.sub(r"^(\s*)print (.*?);?\s*$", r"\1print(\2)", src, flags=re.M)
+    ns = {"__name__": "vcfconvert_reference"}
+    exec(compile(src, "VCFConvert.py", "exec"), ns)
+    rng = np.random.default_rng(11)
+    names = ["ind%02d" % i for i in range(9)]
+    gts = ["0/0", "0|0", "0/1", "1/0", "0|1", "1|0", "1/1", "1|1", "./.", ".|."]
+    lines = ["##fileformat=VCFv4.1", "##source=fpt_b200 tests/golden/make_golden.py",
+             "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names)]
+    for chrom, n in (("chrI", 40), ("chrII", 25)):
+        for pos in np.sort(rng.choice(20000, size=n, replace=False)):
+            calls = ["%d:%s:%d" % (rng.integers(1, 60), gts[rng.integers(0, len(gts))], rng.integers(0, 99)) for _ in names]
+            lines.append("%s\t%d\t.\tA\tC\t50\tPASS\t.\tDP:GT:GQ\t%s" % (chrom, pos, "\t".join(calls)))
+    vcf = "\n".join(lines) + "\n"
+    open(os.path.join(HERE, "small.vcf"), "w").write(vcf)
+    pops = {"A": ["ind00", "ind02", "ind04", "ind07", "nobody"], "B": ["ind08", "ind01", "ind03", "ind05"]}
+    for tag, pop in pops.items():
+        with checkers.silence_stdout():
+            text = ns["addHeader"]("test") + ns["convertToGtrackFile"](vcf, list(pop), "test")
+        open(os.path.join(HERE, "small_pop%s.gtrack" % tag), "w").write(text)
+
+
 if __name__ == "__main__":
+    if os.path.exists("/root/reference/tools/VCFConvert.py"):
+        vcf_fixture()
     if not checkers.ref_available():
         raise SystemExit("oracle/_ref is not built: run `make -C oracle ref` where /root/reference exists")
     fet_fixture()

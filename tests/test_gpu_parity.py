@@ -283,6 +283,19 @@ def test_css_larger_cohorts_take_the_fallback_paths(fpt, oracle, asize, bsize):
     assert np.array_equal(p_g, p_o)
 
 
+def test_css_large_cohort_500_plus_500(fpt, oracle):
+    """BASELINE configs[4] cohort size (500+500 individuals, 50 kb windows) on a handful of windows: the generic fallback
+    kernels (Jacobi eigensolver and first-generation permutation kernel, matrices in per-CTA global scratch, 16-bit labels)"""
+    asize = bsize = 500
+    regend, wsize, wstep, nsnp, seed = 150000, 50000, 50000, 500, 4
+    ch, (av, bv, apos, bpos) = _synth(500, regend, nsnp, asize, bsize)
+    s_o, p_o = _css_oracle_scan(oracle, av, bv, apos, bpos, regend, wsize, wstep, 3, 40, 0, 0, seed)
+    s_g, p_g, wr = fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 3, 40, mds=0, seed=seed)
+    assert np.array_equal(wr == 1, p_o != 0) and (wr == 1).sum() == 3
+    np.testing.assert_allclose(s_g, s_o, rtol=CSS_RTOL, atol=1e-12)
+    assert np.array_equal(p_g, p_o)
+
+
 def test_css_frequency_metric(fpt, oracle):
     """drosophila = 1: two frequency tracks, m = 2 (compare_freq)"""
     rng = np.random.default_rng(3)
@@ -304,3 +317,54 @@ def test_position_mismatch_is_an_error(fpt):
     with pytest.raises(fpt.FptError) as e:
         serial.fisher_exact_tester(av, bv, apos, bpos, 0, 50000, 2500, 500, av.size, bv.size, 0.95, np.zeros(100), np.zeros(100))
     assert e.value.code == -3
+
+
+# ------------------------------------------------------------------------------------------------ whole pipeline
+def test_pipeline_vcf_to_region_calls(fpt, oracle):
+    """SURVEY 8(f) rows 1-4 around the CUDA path: VCF text -> native ingest -> Statistic stand-ins -> drop-in scorers (GPU)
+    -> result files -> region callers, against the same pipeline with the oracle behind the drop-in argument lists."""
+    from collections import OrderedDict
+    import fpt_b200.synth as synth
+    from fpt_b200 import ingest, results, tools
+    asize, bsize, length, nsnp, seed = 6, 5, 70000, 1800, fpt.get_seed()
+    names = ["a%d" % i for i in range(asize)] + ["b%d" % i for i in range(bsize)]
+    gt = {3: "0/0", 0: "0|1", -3: "1/1", -128: "./."}
+    lines = ["##fileformat=VCFv4.1", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names)]
+    lens = OrderedDict()
+    for c in range(2):
+        ch = synth.chromosome(700 + c, length, nsnp, asize, bsize)
+        lens["chr%d" % (c + 1)] = length
+        codes = np.concatenate([ch["acodes"].reshape(-1, asize), ch["bcodes"].reshape(-1, bsize)], axis=1)
+        for p, row in zip(ch["pos"], codes):
+            lines.append("chr%d\t%d\t.\tA\tC\t.\t.\t.\tGT:DP\t%s" % (c + 1, p, "\t".join(gt[int(v)] + ":9" for v in row)))
+    genome, info = ingest.read_vcf("\n".join(lines) + "\n", names[:asize], names[asize:])
+    assert info["records"] == 2 * nsnp and list(genome) == list(lens)
+    ta = OrderedDict((k, v.reference_layout()[0]) for k, v in genome.items())
+    tb = OrderedDict((k, v.reference_layout()[1]) for k, v in genome.items())
+    fet_text = tools.fisher_exact_test_snp_tool(ta, tb, lens, 2500, 500, 0.95, number=results.str_exact)
+    css_text = tools.cluster_separation_score_tool(ta, tb, lens, mds=0, mc_treshold=10, mc_runs=200, number=results.str_exact)
+    # the oracle behind the same host code
+    want_fet, want_css = [results.FET_HEADER], [results.CSS_HEADER]
+    for name in lens:
+        a, b = ta[name], tb[name]
+        n = length // 500
+        s, d, cs, cp = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+        oracle.fpt_oracle_fet_scan(dptr(a.vals), dptr(b.vals), iptr(a.starts), iptr(b.starts), 0, length, 2500, 500, a.vals.size,
+                                   b.vals.size, 0.95, dptr(s), dptr(d), 1, seed)
+        oracle.fpt_oracle_css_scan(dptr(a.vals), dptr(b.vals), iptr(a.starts), iptr(b.starts), 0, length, 2500, 500, a.vals.size,
+                                   b.vals.size, 10, 200, 0, 0, dptr(cs), dptr(cp), 1, seed)
+        want_fet.append(results.format_windows(name, 500, s, d, results.str_exact))
+        want_css.append(results.format_windows(name, 500, cs, cp, results.str_exact))
+    for got, want, rtol in ((fet_text, "".join(want_fet), FET_RTOL), (css_text, "".join(want_css), CSS_RTOL)):
+        gc, gs, g2, g3 = results.read_scan(got)
+        wc, ws, w2, w3 = results.read_scan(want)
+        assert gc == wc and np.array_equal(gs, ws) and len(gc) > 200        # same windows written, same order
+        np.testing.assert_allclose(g2, w2, rtol=rtol, atol=1e-12)
+        np.testing.assert_allclose(g3, w3, rtol=1e-9 if rtol == FET_RTOL else 0, atol=1e-12 if rtol == FET_RTOL else 0)
+    # region calls from the GPU-written files equal those from the oracle-written files
+    assert (results.significant_css_regions_file(css_text, 2500, lens, fdr=0.2)
+            == results.significant_css_regions_file("".join(want_css), 2500, lens, fdr=0.2))
+    assert (results.significant_css_regions_file(css_text, 2500, lens, num_top=10)
+            == results.significant_css_regions_file("".join(want_css), 2500, lens, num_top=10))
+    assert (results.filter_fisher_scores_file(fet_text, 2500, lens, 0.95, 75.0)
+            == results.filter_fisher_scores_file("".join(want_fet), 2500, lens, 0.95, 75.0))
