@@ -54,6 +54,7 @@ FPT_HD size_t fpt_css_perm2_smem_bytes(int m, int nthreads, int chain) {
     off += (size_t)fpt_perm_row_stride(m);                /* carry */
     off = (off + 15) & ~(size_t)15;
     off += (size_t)nthreads * fpt_perm_row_stride(m) * (chain ? 2 : 1);
+    if (fpt_css_perm2_uses_mma(m)) { off = (off + 15) & ~(size_t)15; off += (size_t)nthreads * 80; }   /* membership rows, FPT_IND_STRIDE */
     return off;
 }
 
@@ -137,35 +138,39 @@ static inline void fpt_mma_u8(int (&c)[4], const unsigned (&a)[4], unsigned b0, 
 }
 #endif
 
-/* four membership bits -> four 0/1 bytes */
-FPT_D unsigned fpt_nibble_to_bytes(unsigned nib) { return ((nib & 0xfu) * 0x00204081u) & 0x01010101u; }
+/* Membership rows: ind[lane][individual] = 1 when the individual belongs to the smaller group of the permutation owned by
+   that lane, else 0; 64 bytes used per row, rows FPT_IND_STRIDE = 80 bytes (20 words) apart so that the eight rows times
+   four words of one fragment load fall into 32 different banks. The rows ARE the A operand of the u8 MMA. */
+#define FPT_IND_STRIDE 80
+
+FPT_D void fpt_ind_row_build(unsigned char *myrow, const unsigned char *group, int ng) {
+    uint4 *z = reinterpret_cast<uint4 *>(myrow);
+    z[0] = z[1] = z[2] = z[3] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < ng; i++) myrow[group[i]] = 1;
+}
 
 /* sum over A'xB' of q for the permutation owned by THIS lane, computed cooperatively by the warp.
-   gmask = membership mask of the smaller group for this lane's permutation (0 for an idle lane);
+   ind = the warp's 32 membership rows (written by their lanes, __syncwarp()ed by the caller);
    qd = digit matrices [ndigits][nrows][FPT_QD_STRIDE], nrows = m rounded up to 8.
    The warp's 32 permutations form two 16-row tiles; every B fragment is loaded once and used by both. */
-FPT_D int fpt_bet_mma(unsigned long long gmask, const unsigned char *qd, int m, int ndigits) {
+FPT_D int fpt_bet_mma(const unsigned char *ind, const unsigned char *qd, int m, int ndigits) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int ntiles = (m + 7) >> 3, nrows = ntiles << 3, ksteps = (m + 31) >> 5;
-    const unsigned glo = (unsigned)gmask, ghi = (unsigned)(gmask >> 32);      /* 32-bit halves: cheap shifts and shuffles */
-    /* masks of my four rows: tile 0 rows g, g+8 (lanes g, g+8) and tile 1 rows g, g+8 (lanes 16+g, 24+g) */
-    unsigned lo[4], hi[4] = { 0u, 0u, 0u, 0u };
-#pragma unroll
-    for (int r = 0; r < 4; r++) lo[r] = __shfl_sync(FPT_FULL_MASK, glo, 8 * r + g);
-    if (ksteps > 1) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) hi[r] = __shfl_sync(FPT_FULL_MASK, ghi, 8 * r + g);
-    }
-    /* A fragments: k-step 0 = individuals 0..31 (nibbles t, t+4 of the low half), k-step 1 = 32..63 (high half) */
-    unsigned a0[2][4], a1[2][4];
+    /* my four rows: tile 0 rows g, g+8 (lanes g, g+8) and tile 1 rows g, g+8 (lanes 16+g, 24+g) */
+    const unsigned char *myrows = ind + (size_t)g * FPT_IND_STRIDE;
+    /* A fragments of m16n8k32: reg 0 = (row g, k 4t..4t+3), 1 = (row g+8, same k), 2 / 3 = the same rows at k + 16;
+       a0 = k-step 0 (individuals 0..31), a1 = k-step 1 (32..63) */
+    unsigned a0[2][4], a1[2][4] = { { 0u, 0u, 0u, 0u }, { 0u, 0u, 0u, 0u } };
 #pragma unroll
     for (int tile = 0; tile < 2; tile++) {
-        const unsigned l1 = lo[2 * tile] >> (4 * t), l2 = lo[2 * tile + 1] >> (4 * t);
-        const unsigned h1 = hi[2 * tile] >> (4 * t), h2 = hi[2 * tile + 1] >> (4 * t);
-        a0[tile][0] = fpt_nibble_to_bytes(l1); a0[tile][1] = fpt_nibble_to_bytes(l2);
-        a0[tile][2] = fpt_nibble_to_bytes(l1 >> 16); a0[tile][3] = fpt_nibble_to_bytes(l2 >> 16);
-        a1[tile][0] = fpt_nibble_to_bytes(h1); a1[tile][1] = fpt_nibble_to_bytes(h2);
-        a1[tile][2] = fpt_nibble_to_bytes(h1 >> 16); a1[tile][3] = fpt_nibble_to_bytes(h2 >> 16);
+        const unsigned char *lo_row = myrows + (size_t)(16 * tile) * FPT_IND_STRIDE + 4 * t;
+        const unsigned char *hi_row = lo_row + 8 * FPT_IND_STRIDE;
+        a0[tile][0] = *reinterpret_cast<const unsigned *>(lo_row);      a0[tile][1] = *reinterpret_cast<const unsigned *>(hi_row);
+        a0[tile][2] = *reinterpret_cast<const unsigned *>(lo_row + 16); a0[tile][3] = *reinterpret_cast<const unsigned *>(hi_row + 16);
+        if (ksteps > 1) {
+            a1[tile][0] = *reinterpret_cast<const unsigned *>(lo_row + 32); a1[tile][1] = *reinterpret_cast<const unsigned *>(hi_row + 32);
+            a1[tile][2] = *reinterpret_cast<const unsigned *>(lo_row + 48); a1[tile][3] = *reinterpret_cast<const unsigned *>(hi_row + 48);
+        }
     }
     int sum[4] = { 0, 0, 0, 0 };                        /* masked row sums: tile 0 rows g, g+8; tile 1 rows g, g+8 */
     const unsigned char *colbase = qd + (size_t)g * FPT_QD_STRIDE + 4 * t;
@@ -187,18 +192,19 @@ FPT_D int fpt_bet_mma(unsigned long long gmask, const unsigned char *qd, int m, 
             for (int i = 0; i < 4; i++) { r0[i] = (r0[i] << 8) + c0[i]; r1[i] = (r1[i] << 8) + c1[i]; }
         }
         /* columns 8nt + 2t, +1 held by this lane: keep those outside the group (padded columns are zero anyway) */
-        const int sh = ((8 * nt) & 31) + 2 * t;
-        const bool upper = nt >= 4;
-        const unsigned m00 = (upper ? hi[0] : lo[0]) >> sh, m01 = (upper ? hi[1] : lo[1]) >> sh;
-        const unsigned m10 = (upper ? hi[2] : lo[2]) >> sh, m11 = (upper ? hi[3] : lo[3]) >> sh;
-        if (!(m00 & 1u)) sum[0] += r0[0];
-        if (!(m00 & 2u)) sum[0] += r0[1];
-        if (!(m01 & 1u)) sum[1] += r0[2];
-        if (!(m01 & 2u)) sum[1] += r0[3];
-        if (!(m10 & 1u)) sum[2] += r1[0];
-        if (!(m10 & 2u)) sum[2] += r1[1];
-        if (!(m11 & 1u)) sum[3] += r1[2];
-        if (!(m11 & 2u)) sum[3] += r1[3];
+        const unsigned char *mcol = myrows + 8 * nt + 2 * t;
+        const unsigned m00 = *reinterpret_cast<const unsigned short *>(mcol);
+        const unsigned m01 = *reinterpret_cast<const unsigned short *>(mcol + 8 * FPT_IND_STRIDE);
+        const unsigned m10 = *reinterpret_cast<const unsigned short *>(mcol + 16 * FPT_IND_STRIDE);
+        const unsigned m11 = *reinterpret_cast<const unsigned short *>(mcol + 24 * FPT_IND_STRIDE);
+        if (!(m00 & 0x00ffu)) sum[0] += r0[0];
+        if (!(m00 & 0xff00u)) sum[0] += r0[1];
+        if (!(m01 & 0x00ffu)) sum[1] += r0[2];
+        if (!(m01 & 0xff00u)) sum[1] += r0[3];
+        if (!(m10 & 0x00ffu)) sum[2] += r1[0];
+        if (!(m10 & 0xff00u)) sum[2] += r1[1];
+        if (!(m11 & 0x00ffu)) sum[3] += r1[2];
+        if (!(m11 & 0xff00u)) sum[3] += r1[3];
     }
 #pragma unroll
     for (int r = 0; r < 4; r++) { sum[r] += __shfl_xor_sync(FPT_FULL_MASK, sum[r], 1); sum[r] += __shfl_xor_sync(FPT_FULL_MASK, sum[r], 2); }
@@ -237,6 +243,8 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
     off = (off + 15) & ~(size_t)15;
     unsigned char *rows = smem + off;
     unsigned char *rows2 = rows + (size_t)T * RS;          /* chain mode only */
+    unsigned char *ind = smem + ((off + (size_t)T * RS * (chain ? 2 : 1) + 15) & ~(size_t)15);   /* MMA path only */
+    unsigned char *myind = ind + (size_t)tid * FPT_IND_STRIDE, *warpind = ind + (size_t)(tid & ~31) * FPT_IND_STRIDE;
     __shared__ double s_score, s_dmax;
     __shared__ int s_flag;
     unsigned char *mine = rows + (size_t)tid * RS;
@@ -397,15 +405,14 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
                 if (use_surrogate) {
                     long long bet = 0; int wa = 0, wb = 0;
                     if (use_mma) {
-                        unsigned long long gmask = 0ULL;
+                        fpt_ind_row_build(myind, use_a ? mine : mine + asize, valid ? (use_a ? asize : bsize) : 0);
+                        __syncwarp();
                         if (valid) {
-                            const unsigned char *gr = use_a ? mine : mine + asize;
-                            const int ng = use_a ? asize : bsize;
-                            for (int i = 0; i < ng; i++) gmask |= 1ULL << gr[i];
                             for (int i = 0; i + 1 < asize; i++) wa += (int)q[mine[i] * m + mine[i + 1]];
                             for (int i = 0; i + 1 < bsize; i++) wb += (int)q[mine[asize + i] * m + mine[asize + i + 1]];
                         }
-                        bet = (long long)fpt_bet_mma(gmask, qd, m, ndigits);
+                        bet = (long long)fpt_bet_mma(warpind, qd, m, ndigits);
+                        __syncwarp();
                     } else if (valid) {
                         fpt_surrogate(q, rowsum, m, mine, asize, bsize, use_a, bet, wa, wb);
                     }

@@ -161,6 +161,7 @@ struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
 struct double2 { double x, y; };
 static inline int4 make_int4(int a, int b, int c, int d) { int4 r = { a, b, c, d }; return r; }
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r = { a, b, c, d }; return r; }
 static inline int2 make_int2(int a, int b) { int2 r = { a, b }; return r; }
 static inline double2 make_double2(double a, double b) { double2 r = { a, b }; return r; }
 
