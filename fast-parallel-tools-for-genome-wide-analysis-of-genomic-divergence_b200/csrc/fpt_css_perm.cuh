@@ -55,6 +55,8 @@ FPT_HD size_t fpt_css_perm2_smem_bytes(int m, int nthreads, int chain) {
     off = (off + 15) & ~(size_t)15;
     off += (size_t)nthreads * fpt_perm_row_stride(m) * (chain ? 2 : 1);
     if (fpt_css_perm2_uses_mma(m)) { off = (off + 15) & ~(size_t)15; off += (size_t)nthreads * 80; }   /* membership rows, FPT_IND_STRIDE */
+    off = (off + 15) & ~(size_t)15;
+    off += (size_t)(nthreads + 1) * 16;                   /* affine skip-ahead maps: one per thread, one per chunk */
     return off;
 }
 
@@ -67,6 +69,25 @@ FPT_D void fpt_shuffle_row(unsigned char *row, int m, const uint2 *rtab, uint64_
         const int rr = (int)fpt_randint_fast((uint32_t)(i + 1), lm.x, lm.y, st, used);
         const unsigned char t = row[i]; row[i] = row[rr]; row[rr] = t;
     }
+}
+
+/* The same Fisher-Yates, optimistic: a draw is rejected with probability < n / 2^31, so the loop only REMEMBERS whether one
+   was (no branch, no draw counter). Returns true and advances `st` by m - 1 draws when none was; otherwise `st` is left
+   alone and the caller replays the permutation on the exact path above. */
+FPT_D bool fpt_shuffle_row_optimistic(unsigned char *row, int m, const uint2 *rtab, uint64_t &st) {
+    uint64_t s = st;
+    bool rejected = false;
+    for (int i = m - 1; i > 0; i--) {
+        const uint2 lm = rtab[i + 1];
+        const uint32_t n = (uint32_t)(i + 1);
+        const uint32_t r = (uint32_t)(fpt_lcg_next(s) >> 17);
+        rejected |= r > lm.x;
+        uint32_t rem = r - __umulhi(r, lm.y) * n;
+        if (rem >= n) rem -= n;
+        const unsigned char t = row[i]; row[i] = row[rem]; row[rem] = t;
+    }
+    if (!rejected) st = s;
+    return !rejected;
 }
 
 FPT_D void fpt_identity_row(unsigned char *row, int m) {
@@ -143,10 +164,9 @@ static inline void fpt_mma_u8(int (&c)[4], const unsigned (&a)[4], unsigned b0, 
    four words of one fragment load fall into 32 different banks. The rows ARE the A operand of the u8 MMA. */
 #define FPT_IND_STRIDE 80
 
-FPT_D void fpt_ind_row_build(unsigned char *myrow, const unsigned char *group, int ng) {
+FPT_D void fpt_ind_row_clear(unsigned char *myrow) {
     uint4 *z = reinterpret_cast<uint4 *>(myrow);
     z[0] = z[1] = z[2] = z[3] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = 0; i < ng; i++) myrow[group[i]] = 1;
 }
 
 /* sum over A'xB' of q for the permutation owned by THIS lane, computed cooperatively by the warp.
@@ -245,12 +265,27 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
     unsigned char *rows2 = rows + (size_t)T * RS;          /* chain mode only */
     unsigned char *ind = smem + ((off + (size_t)T * RS * (chain ? 2 : 1) + 15) & ~(size_t)15);   /* MMA path only */
     unsigned char *myind = ind + (size_t)tid * FPT_IND_STRIDE, *warpind = ind + (size_t)(tid & ~31) * FPT_IND_STRIDE;
+    /* independent shuffles: permutation k of a window starts k (m-1) draws into the window's stream. Thread t's first
+       permutation of chunk c is (c T + t) PP, so its start is  skip_t( skip_chunk^c (window state) )  with two affine maps
+       x -> a x + b (mod 2^48) that do not depend on the window: computed once here, applied with two multiplies per chunk */
+    ulonglong2 *skipmap = (ulonglong2 *)(smem + (((size_t)(ind - smem) + (use_mma ? (size_t)T * FPT_IND_STRIDE : 0) + 15) & ~(size_t)15));
     __shared__ double s_score, s_dmax;
     __shared__ int s_flag;
     unsigned char *mine = rows + (size_t)tid * RS;
     const int use_a = asize <= bsize;
     const int draws = m - 1;
     unsigned long long rechecks = 0;
+    {
+        /* a = A^n, b = skip(0, n): skip(x, n) = a x + b */
+        const uint64_t n_t = (uint64_t)tid * FPT_PERM_PP * (uint64_t)(m - 1);
+        const uint64_t b_t = fpt_lcg_skip(0ULL, n_t);
+        skipmap[tid] = make_ulonglong2((fpt_lcg_skip(1ULL, n_t) - b_t) & FPT_MASK48, b_t);
+        if (tid == 0) {
+            const uint64_t n_c = (uint64_t)T * FPT_PERM_PP * (uint64_t)(m - 1);
+            const uint64_t b_c = fpt_lcg_skip(0ULL, n_c);
+            skipmap[T] = make_ulonglong2((fpt_lcg_skip(1ULL, n_c) - b_c) & FPT_MASK48, b_c);
+        }
+    }
     for (int n = tid; n <= m; n += T) {
         uint2 lm;
         lm.x = n > 0 ? fpt_randint_limit((uint32_t)n) : 0u; lm.y = n > 0 ? fpt_randint_magic((uint32_t)n) : 0u;
@@ -327,6 +362,7 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
 
         const uint64_t st_win = state_override ? state_override[w] : fpt_stream_state(seed, wbase + w, FPT_STREAM_RESAMPLE);
         long long stream_pos = 0;                           /* chain mode: draws consumed by finished chunks */
+        uint64_t st_chunk = st_win;                         /* independent mode: window state advanced by the finished chunks */
         int hits = 0, ndone = 0;
         bool stopped = false;
         while (!stopped && hits < treshold && ndone < runs) {
@@ -395,22 +431,41 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
                         fpt_identity_row(mine, m);
                         /* the stream of permutation k starts k*(m-1) draws in; after a shuffle without a rejected draw the
                            state already sits at the next permutation's start */
-                        if (j == 0 || resync) st = fpt_lcg_skip(st_win, (uint64_t)(ndone + first + j) * (uint64_t)draws);
+                        if (j == 0) { const ulonglong2 sk = skipmap[tid]; st = (sk.x * st_chunk + sk.y) & FPT_MASK48; }
+                        else if (resync) st = fpt_lcg_skip(st_win, (uint64_t)(ndone + first + j) * (uint64_t)draws);
+                        resync = !fpt_shuffle_row_optimistic(mine, m, rtab, st);
+                        if (resync) {                       /* a rejected draw: replay this permutation exactly */
+                            fpt_identity_row(mine, m);
+                            fpt_shuffle_row(mine, m, rtab, st, used);
+                        }
+                    } else {
+                        fpt_shuffle_row(mine, m, rtab, st, used);
                     }
-                    fpt_shuffle_row(mine, m, rtab, st, used);
-                    resync = used != draws;
                 }
                 int hit = 0;
                 bool exact = valid && !use_surrogate;
                 if (use_surrogate) {
                     long long bet = 0; int wa = 0, wb = 0;
                     if (use_mma) {
-                        fpt_ind_row_build(myind, use_a ? mine : mine + asize, valid ? (use_a ? asize : bsize) : 0);
-                        __syncwarp();
+                        /* one walk over the labels: membership row of the smaller group + both adjacent-pair sums */
+                        fpt_ind_row_clear(myind);
                         if (valid) {
-                            for (int i = 0; i + 1 < asize; i++) wa += (int)q[mine[i] * m + mine[i + 1]];
-                            for (int i = 0; i + 1 < bsize; i++) wb += (int)q[mine[asize + i] * m + mine[asize + i + 1]];
+                            int prev = mine[0];
+                            if (use_a) myind[prev] = 1;
+                            for (int i = 1; i < asize; i++) {
+                                const int c = mine[i];
+                                if (use_a) myind[c] = 1;
+                                wa += (int)q[prev * m + c]; prev = c;
+                            }
+                            prev = mine[asize];
+                            if (!use_a) myind[prev] = 1;
+                            for (int i = 1; i < bsize; i++) {
+                                const int c = mine[asize + i];
+                                if (!use_a) myind[c] = 1;
+                                wb += (int)q[prev * m + c]; prev = c;
+                            }
                         }
+                        __syncwarp();
                         bet = (long long)fpt_bet_mma(warpind, qd, m, ndigits);
                         __syncwarp();
                     } else if (valid) {
@@ -443,6 +498,7 @@ fpt_css_perm2_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
                 ndone += s_flag + 1; hits = treshold; stopped = true;
             } else {
                 hits += chunk_hits; ndone += nvalid;
+                { const ulonglong2 sk = skipmap[T]; st_chunk = (sk.x * st_chunk + sk.y) & FPT_MASK48; }
                 if (chain) {
                     const int lastblk = (nvalid - 1) / FPT_PERM_PP;
                     if (tid == lastblk) for (int e = 0; e < m; e++) carry[e] = mine[e];

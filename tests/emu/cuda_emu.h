@@ -159,6 +159,8 @@ struct int4 { int x, y, z, w; };
 struct int2 { int x, y; };
 struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
+struct ulonglong2 { unsigned long long x, y; };
+static inline ulonglong2 make_ulonglong2(unsigned long long a, unsigned long long b) { ulonglong2 r = { a, b }; return r; }
 struct double2 { double x, y; };
 static inline int4 make_int4(int a, int b, int c, int d) { int4 r = { a, b, c, d }; return r; }
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r = { a, b, c, d }; return r; }

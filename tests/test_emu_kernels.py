@@ -245,6 +245,19 @@ def test_css_perm_kernels_chunks_early_stop_and_scratch_paths(emu, oracle, chain
             X[1] = np.round(X[1])                                  # exact ties between permuted and observed scores
         st = np.full(n, 2, dtype=np.uint8)
         states = (np.arange(n, dtype=np.uint64) * 7919 + 13)
+        if m == 11:
+            # window 0: the very first draw (n = 11) comes out as 2^31 - 1 > limit, i.e. is rejected and redrawn; window 1:
+            # the same for the first draw of permutation 3 (independent mode) -> optimistic shuffle, replay, resync
+            A, Cc, M48 = 0x5DEECE66D, 0xB, (1 << 48) - 1
+            ainv = pow(A, -1, 1 << 48)
+            target = (0x7FFFFFFF << 17) | 0x1ABCD
+            states[0] = ((target - Cc) * ainv) & M48
+            s = states[0].item()
+            assert ((s * A + Cc) & M48) >> 17 == 0x7FFFFFFF
+            back = (target - Cc) * ainv & M48
+            for _ in range(3 * (m - 1)):
+                back = ((back - Cc) * ainv) & M48
+            states[1] = back
         qbits = min(15 if 8 <= m <= 64 else 22, int(math.floor(math.log2(2 ** 31 / (min(asize, bsize) * m + 1)))))
         for tres, runs in ((5, 300), (1000, 100), (1, 70)):
             want_p, want_h, want_n = [], [], []
