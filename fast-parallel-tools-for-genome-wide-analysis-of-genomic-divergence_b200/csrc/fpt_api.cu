@@ -22,6 +22,7 @@
 #include "../../include/fpt_b200.h"
 #include "fpt_css.cuh"
 #include "fpt_css_eig.cuh"
+#include "fpt_css_lanczos.cuh"
 #include "fpt_css_perm.cuh"
 #include "fpt_fet.cuh"
 #include "fpt_rt.cuh"
@@ -459,7 +460,8 @@ extern "C" int fpt_dev_css_absdiff(const double *a, const double *b, int64_t nsn
 /* launch geometry of the per-window CSS kernels for a cohort of m individuals */
 struct CssPlan {
     int m, wch, mats_in_smem;
-    size_t smem_win;                 /* CTA-per-window kernels (SMACOF, Jacobi fallback) */
+    size_t smem_win;                 /* CTA-per-window kernels (SMACOF) */
+    size_t smem_large; int wch_large; /* large cohorts: Lanczos kernel, one 512-thread CTA per window */
     int mds_warps;                   /* > 0: classical MDS runs one warp per window, this many warps per CTA */
     size_t smem_mds_warp;
     int perm_threads, wide_tracks, dist_in_smem, tracks_in_smem;
@@ -488,7 +490,10 @@ static CssPlan css_plan(const DeviceCtx *c, int m) {
     p.smem_perm = fpt_css_perm_smem_bytes(m, p.perm_threads, tb, p.dist_in_smem, p.tracks_in_smem);
     size_t per = (p.dist_in_smem ? 0 : (size_t)m * m * 8) + (p.tracks_in_smem ? 0 : (size_t)2 * p.perm_threads * m * tb);
     p.perm_scratch_per_cta = (per + 255) & ~(size_t)255;
-    p.max_ctas = c->sms * 16;
+    /* cohorts beyond the one-warp path keep two m x m matrices per CTA in global scratch: bound the persistent grid */
+    p.max_ctas = p.mds_warps > 0 ? c->sms * 16 : c->sms * 2;
+    p.wch_large = 2;
+    p.smem_large = fpt_lanczos_smem_bytes(m, p.wch_large);
     p.smem_perm2 = fpt_css_perm2_smem_bytes(m, p.perm_threads, g_perm_chain);
     p.perm2 = m <= 250 && p.smem_perm2 <= budget;
     p.qbits = 8;
@@ -513,7 +518,8 @@ static CssWorkspace css_carve(const CssPlan &p, long long nwin, int mds, unsigne
     size_t oS = take((size_t)nwin * nruns * 8);
     size_t oE = take((size_t)nwin * 3 * 8);
     size_t oI = take((size_t)nwin * nruns * 4);
-    size_t oG = take(p.mats_in_smem ? 0 : (size_t)p.max_ctas * fpt_css_mats_doubles(p.m) * 8);
+    const bool need_g = !p.mats_in_smem || p.mds_warps == 0;
+    size_t oG = take(need_g ? (size_t)p.max_ctas * fpt_css_mats_doubles(p.m) * 8 : 0);
     size_t oP = take((size_t)p.max_ctas * p.perm_scratch_per_cta);
     const bool warp_mds = p.mds_warps > 0 && mds != 1;      /* tridiagonal + reflectors handed from phase A to phase B */
     size_t oT = take(warp_mds ? (size_t)nwin * 3 * p.m * 8 : 0);
@@ -522,7 +528,7 @@ static CssWorkspace css_carve(const CssPlan &p, long long nwin, int mds, unsigne
     if (base) {
         w.X = (double *)(base + oX); w.Xruns = (double *)(base + oXr); w.sigma = (double *)(base + oS);
         w.evals = (double *)(base + oE); w.iters = (int *)(base + oI);
-        w.gscratch = p.mats_in_smem ? nullptr : (double *)(base + oG);
+        w.gscratch = need_g ? (double *)(base + oG) : nullptr;
         w.perm_scratch = p.perm_scratch_per_cta ? base + oP : nullptr;
         w.tri = (double *)(base + oT); w.refl = (double *)(base + oR);
     }
@@ -584,11 +590,13 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
             CHECK(persistent_grid(c, fpt_css_eigvec_kernel, 128, smem_b, (nwin + 3) / 4, &grid));
             { ProfScope ps_("css_eigvec", st); fpt_css_eigvec_kernel<<<grid, 128, smem_b, st>>>(m, nwin, ws.tri, ws.refl, status, ws.X,
                                                                                                 (probes && probes->evals) ? ws.evals : nullptr); }
-        } else {                                           /* cohorts too large for a warp's shared-memory slice */
-            CHECK(persistent_grid(c, fpt_css_mds_kernel, 128, p.smem_win, nwin, &grid));
+        } else {                                           /* cohorts too large for a warp's shared-memory slice: Lanczos, CTA per window */
+            if (p.smem_large > (size_t)c->smem_optin)
+                return fail(FPT_ERR_ARG, "cohort of %d individuals does not fit the large-cohort kernel's shared memory", m);
+            CHECK(persistent_grid(c, fpt_css_mds_large_kernel, 512, p.smem_large, nwin, &grid));
             grid = std::min(grid, p.max_ctas);
-            { ProfScope ps_("css_mds", st); fpt_css_mds_kernel<<<grid, 128, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, nwin, p.wch, p.mats_in_smem,
-                                                             ws.gscratch, ws.X, ws.evals, status); }
+            { ProfScope ps_("css_mds_large", st); fpt_css_mds_large_kernel<<<grid, 512, p.smem_large, st>>>(planes, absdiff, m, wleft, wright, nwin, p.wch_large,
+                                                             ws.gscratch, ws.X, ws.evals, status, nullptr); }
         }
         CU(cudaGetLastError());
     }

@@ -260,15 +260,13 @@ FPT_D void fpt_warp_tridiag(int m, const FptEigWork &w, double *__restrict__ ref
     __syncwarp();
 }
 
-/* ---- steps 3-5 (phase B): the two largest eigenpairs of the tridiagonal in the work area (d, e, tau), back-transformed
-   through the reflectors in `refl`; X (2m doubles) and evals3 are written by the warp. Needs no m x m storage. */
-FPT_D void fpt_warp_eig(int m, const FptEigWork &w, const double *__restrict__ refl, double *X, double *evals3, int want_third) {
+/* ---- steps 3-4: the two largest eigenpairs (and optionally the third eigenvalue) of the symmetric tridiagonal (w.d, w.e)
+   of order m >= 2, by one warp. On return w.y[0..m) and w.y[m..2m) hold the unit eigenvectors; out1..out3 the eigenvalues
+   (out3 = 0 unless want_third), tnorm_out the Gershgorin norm of T. Returns 0 when T is zero or not finite (nothing
+   else is written then; tnorm_out tells which). Used by the Householder path below and by the Lanczos path for large
+   cohorts (fpt_css_lanczos.cuh). Needs w.d, w.e, w.pv, w.wv, w.y (2m), w.lu (6m). */
+FPT_D int fpt_warp_tri_eig(int m, const FptEigWork &w, int want_third, double &out1, double &out2, double &out3, double &tnorm_out) {
     const int lane = threadIdx.x & 31;
-    if (m == 1) {
-        if (lane == 0) { X[0] = 0.0; X[1] = 0.0; if (evals3) { evals3[0] = 0.0; evals3[1] = 0.0; evals3[2] = 0.0; } }
-        __syncwarp();
-        return;
-    }
     /* Gershgorin bounds and the norm used to scale T to O(1): the searches below run on d/tnorm, (e/tnorm)^2 (kept in
        pv / wv), which keeps every Sturm pivot inside single-precision range for the fast reciprocal */
     double glo = 1e300, ghi = -1e300;
@@ -280,14 +278,8 @@ FPT_D void fpt_warp_eig(int m, const FptEigWork &w, const double *__restrict__ r
     }
     glo = fpt_warp_min(glo); ghi = fpt_warp_max(ghi);
     const double tnorm = fmax(fabs(glo), fabs(ghi));
-    if (!(tnorm > 0.0) || !(tnorm < 1e300)) {              /* B = 0 (all dissimilarities equal) or not finite */
-        const double v = tnorm == 0.0 ? 0.0 : tnorm - tnorm;   /* 0, or NaN when the input was not finite */
-        #pragma unroll 1
-        for (int j = lane; j < 2 * m; j += 32) X[j] = v;
-        if (lane == 0 && evals3) { evals3[0] = v; evals3[1] = v; evals3[2] = v; }
-        __syncwarp();
-        return;
-    }
+    tnorm_out = tnorm;
+    if (!(tnorm > 0.0) || !(tnorm < 1e300)) return 0;      /* B = 0 (all dissimilarities equal) or not finite */
     const double rnorm = 1.0 / tnorm;
     #pragma unroll 1
     for (int i = lane; i < m; i += 32) {
@@ -438,6 +430,28 @@ FPT_D void fpt_warp_eig(int m, const FptEigWork &w, const double *__restrict__ r
         }
         lam1 = __shfl_sync(FPT_FULL_MASK, rq, 0);
         lam2 = __shfl_sync(FPT_FULL_MASK, rq, 1);
+    }
+    out1 = lam1; out2 = lam2; out3 = lam3;
+    return 1;
+}
+
+/* ---- steps 3-5 (phase B): the two largest eigenpairs of the tridiagonal in the work area (d, e, tau), back-transformed
+   through the reflectors in `refl`; X (2m doubles) and evals3 are written by the warp. Needs no m x m storage. */
+FPT_D void fpt_warp_eig(int m, const FptEigWork &w, const double *__restrict__ refl, double *X, double *evals3, int want_third) {
+    const int lane = threadIdx.x & 31;
+    if (m == 1) {
+        if (lane == 0) { X[0] = 0.0; X[1] = 0.0; if (evals3) { evals3[0] = 0.0; evals3[1] = 0.0; evals3[2] = 0.0; } }
+        __syncwarp();
+        return;
+    }
+    double lam1 = 0.0, lam2 = 0.0, lam3 = 0.0, tnorm = 0.0;
+    if (!fpt_warp_tri_eig(m, w, want_third, lam1, lam2, lam3, tnorm)) {
+        const double v = tnorm == 0.0 ? 0.0 : tnorm - tnorm;   /* 0, or NaN when the input was not finite */
+        #pragma unroll 1
+        for (int j = lane; j < 2 * m; j += 32) X[j] = v;
+        if (lane == 0 && evals3) { evals3[0] = v; evals3[1] = v; evals3[2] = v; }
+        __syncwarp();
+        return;
     }
 
     /* back-transform: z = H_0 H_1 ... H_{m-3} y, applied last reflector first */

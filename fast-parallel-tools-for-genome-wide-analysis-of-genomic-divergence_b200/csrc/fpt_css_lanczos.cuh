@@ -1,0 +1,260 @@
+/*
+ * fpt_css_lanczos.cuh — classical MDS of one window for LARGE cohorts (m beyond the one-warp path of fpt_css_eig.cuh),
+ * one CTA per window (reference: cmds, css/css.c:505-560 — GSL's dense symmetric eigensolver, two largest eigenpairs kept).
+ *
+ * At m = 1000 (BASELINE configs[4]) a full reduction of the 8 MB matrix re-reads it ~m times; the reference only wants the
+ * two largest eigenpairs, and those are the ones a Krylov method finds first. So:
+ *
+ *   1. B = -1/2 (S - r 1' - 1 r' + g), S = D.D, formed once in the CTA's global scratch (read-only afterwards)
+ *   2. Lanczos with FULL re-orthogonalisation (classical Gram-Schmidt applied twice) against every previous vector:
+ *      w = B q_j (one coalesced pass over B, a warp per row), h = Q'w, w -= Q h, twice; alpha_j = h_j, beta_j = |w|
+ *   3. every FPT_LANCZOS_CHECK steps warp 0 solves the j x j tridiagonal (fpt_warp_tri_eig: Sturm multisection + inverse
+ *      iteration) and the residual bounds beta_j |y_c[j-1]| of the two leading Ritz pairs decide: stop once both are
+ *      below 1e-9 of their spectral gap (eigenvector error ~ residual / gap), or at 1e-14 of the norm, or at the cap
+ *   4. X = [Q y_1, Q y_2] diag(sqrt l1, sqrt l2)
+ *
+ * With full re-orthogonalisation the recurrence is numerically a Householder reduction stopped early: no ghost
+ * eigenvalues, and at j = m it is complete. Traffic per window: (steps) x 8 m^2 bytes for the products (HBM/L2, coalesced)
+ * plus ~16 m j bytes per step for the basis — against ~4 m^3 bytes for a reduction in place.
+ */
+#ifndef FPT_CSS_LANCZOS_CUH
+#define FPT_CSS_LANCZOS_CUH
+
+#include "fpt_css.cuh"
+#include "fpt_css_eig.cuh"
+
+#define FPT_LANCZOS_CHECK 8
+#define FPT_LANCZOS_FIRST_CHECK 16
+
+FPT_HD int fpt_lanczos_cap(int m) { return m < 384 ? m : 384; }
+
+struct FptLanczosSmem {
+    double *q;        /* m: current Lanczos vector (read by every row of the product) */
+    double *w;        /* m: B q and its orthogonalised remainder */
+    double *alpha;    /* cap */
+    double *beta;     /* cap */
+    double *h;        /* cap: projections on the basis */
+    double *rmean;    /* m */
+    FptEigWork ew;    /* tridiagonal eigen-solve of order <= cap, warp 0 */
+    FptCssScratch sc; /* reductions + bit-plane words of the dissimilarity stage */
+};
+
+FPT_HD size_t fpt_lanczos_smem_bytes(int m, int wch) {
+    const int cap = fpt_lanczos_cap(m);
+    size_t off = (size_t)3 * m * 8 + (size_t)3 * cap * 8 + (size_t)13 * cap * 8 + 66 * 8;
+    off = (off + 15) & ~(size_t)15;
+    return off + (size_t)wch * 2 * m * 4;
+}
+
+FPT_D FptLanczosSmem fpt_lanczos_carve(unsigned char *smem, int m, int wch) {
+    FptLanczosSmem s;
+    const int cap = fpt_lanczos_cap(m);
+    double *p = (double *)smem;
+    s.q = p; p += m; s.w = p; p += m; s.rmean = p; p += m;
+    s.alpha = p; p += cap; s.beta = p; p += cap; s.h = p; p += cap;
+    s.ew.A = 0;
+    s.ew.d = p; p += cap; s.ew.e = p; p += cap; s.ew.tau = p; p += cap;
+    s.ew.pv = p; p += cap; s.ew.wv = p; p += cap;
+    s.ew.y = p; p += 2 * cap;
+    s.ew.lu = p; p += 6 * cap;
+    s.ew.wbuf = 0; s.ew.wch = 0;
+    s.sc.red = p; p += 33;
+    s.sc.redi = (long long *)p; p += 33;
+    size_t off = (size_t)((unsigned char *)p - smem);
+    off = (off + 15) & ~(size_t)15;
+    s.sc.wbuf = (unsigned *)(smem + off);
+    s.sc.wch = wch;
+    return s;
+}
+
+/* y = B x for a symmetric m x m matrix in global memory: a warp per row, lanes across the row (coalesced), two rows in
+   flight per warp; x and y in shared memory */
+FPT_D void fpt_cta_symv(const double *__restrict__ B, int m, const double *x, double *y) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int i = 2 * warp; i < m; i += 2 * nwarp) {
+        const double *r0 = B + (size_t)i * m;
+        const bool two = i + 1 < m;
+        const double *r1 = two ? r0 + m : r0;
+        double s0 = 0.0, s1 = 0.0;
+        for (int j = lane; j < m; j += 32) { const double xv = x[j]; s0 += r0[j] * xv; s1 += r1[j] * xv; }
+        s0 = fpt_warp_sum(s0); s1 = fpt_warp_sum(s1);
+        if (lane == 0) { y[i] = s0; if (two) y[i + 1] = s1; }
+    }
+}
+
+/* one classical Gram-Schmidt pass of w against the nq basis vectors Q[0..nq) (rows of length m in global memory);
+   the projections are ADDED to h so that two passes accumulate the exact coefficients */
+FPT_D void fpt_cta_cgs_pass(const double *__restrict__ Q, int nq, int m, double *w, double *h, double *hpass) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int i = warp; i < nq; i += nwarp) {
+        const double *qi = Q + (size_t)i * m;
+        double s = 0.0;
+        for (int e = lane; e < m; e += 32) s += qi[e] * w[e];
+        s = fpt_warp_sum(s);
+        if (lane == 0) { hpass[i] = s; h[i] += s; }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < m; e += blockDim.x) {
+        double acc = w[e];
+        for (int i = 0; i < nq; i++) acc -= hpass[i] * Q[(size_t)i * m + e];
+        w[e] = acc;
+    }
+    __syncthreads();
+}
+
+/* A (m x m, global) holds the filled dissimilarities on entry and B on exit; Q (>= cap x m doubles, global) receives the
+   Lanczos basis. X: 2m doubles (shared or global) written by the CTA; evals3 optional. All threads of the CTA take part. */
+FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *evals3, const FptLanczosSmem &s, int *steps_out) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int cap = fpt_lanczos_cap(m);
+    const size_t mm = (size_t)m * m;
+    __shared__ double sh_val[4];
+    __shared__ int sh_flag;
+    /* ---- 1. double centring in place (same closed form as the small-cohort paths) */
+    for (size_t e = tid; e < mm; e += T) { const double d = A[e]; A[e] = d * d; }
+    __syncthreads();
+    {
+        const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+        for (int i = warp; i < m; i += nwarp) {                /* row sums, coalesced */
+            const double *row = A + (size_t)i * m;
+            double acc = 0.0;
+            for (int j = lane; j < m; j += 32) acc += row[j];
+            acc = fpt_warp_sum(acc);
+            if (lane == 0) s.rmean[i] = acc / m;
+        }
+    }
+    __syncthreads();
+    double g = 0.0;
+    for (int i = tid; i < m; i += T) g += s.rmean[i];
+    g = fpt_block_sum(g, s.sc.red) / m;
+    for (size_t e = tid; e < mm; e += T) {
+        const int i = (int)(e / m), j = (int)(e - (size_t)i * m);
+        A[e] = -0.5 * (((A[e] - s.rmean[i]) - s.rmean[j]) + g);
+    }
+    __syncthreads();
+
+    /* ---- 2. Lanczos. Start vector: fixed pseudo-random signs and magnitudes (any vector with a component along the
+       leading eigenvectors works; a fixed one keeps runs reproducible) */
+    double nn = 0.0;
+    for (int e = tid; e < m; e += T) {
+        const unsigned hsh = ((unsigned)e * 2654435761u + 40503u) >> 7;
+        const double v = ((double)(hsh & 0xffffu) / 65536.0) - 0.5;
+        s.w[e] = v; nn += v * v;
+    }
+    nn = fpt_block_sum(nn, s.sc.red);
+    const double rn0 = 1.0 / sqrt(nn);
+    for (int e = tid; e < m; e += T) { const double v = s.w[e] * rn0; s.q[e] = v; Q[e] = v; }
+    __syncthreads();
+
+    int nvec = 0;                       /* order of T when the iteration stops */
+    int have = 0;                       /* 1: a converged (or final) tridiagonal solve sits in s.ew.y */
+    double lam1 = 0.0, lam2 = 0.0, lam3 = 0.0, bnorm = 0.0;
+    int degenerate = 0;                 /* 1: B q0 = 0 or non-finite */
+    for (int j = 0; j < cap; j++) {
+        fpt_cta_symv(A, m, s.q, s.w);
+        for (int i = tid; i <= j; i += T) s.h[i] = 0.0;
+        __syncthreads();
+        fpt_cta_cgs_pass(Q, j + 1, m, s.w, s.h, s.ew.lu);            /* lu is free between tridiagonal solves */
+        fpt_cta_cgs_pass(Q, j + 1, m, s.w, s.h, s.ew.lu);
+        double b2 = 0.0;
+        for (int e = tid; e < m; e += T) b2 += s.w[e] * s.w[e];
+        b2 = fpt_block_sum(b2, s.sc.red);
+        const double bj = sqrt(b2);
+        if (tid == 0) { s.alpha[j] = s.h[j]; s.beta[j] = bj; }
+        __syncthreads();
+        nvec = j + 1;
+        bnorm = fmax(bnorm, fabs(s.alpha[j]) + bj + (j > 0 ? s.beta[j - 1] : 0.0));
+        if (!(bnorm < 1e300)) { degenerate = 2; break; }          /* NaN / Inf in the input */
+        if (j == 0 && bnorm == 0.0) { degenerate = 1; break; }    /* B q0 = 0: B = 0 (all dissimilarities equal) */
+        const bool breakdown = !(bj > 1e-14 * bnorm);             /* invariant subspace: T_j is exact */
+        const bool check = breakdown || nvec == cap || (nvec >= FPT_LANCZOS_FIRST_CHECK && (nvec % FPT_LANCZOS_CHECK) == 0) || nvec == m;
+        if (check && nvec >= 2) {
+            if (tid < 32) {
+                for (int i = tid; i < nvec; i += 32) { s.ew.d[i] = s.alpha[i]; s.ew.e[i] = i < nvec - 1 ? s.beta[i] : 0.0; }
+                __syncwarp();
+                double l1 = 0.0, l2 = 0.0, l3 = 0.0, tn = 0.0;
+                const int ok = fpt_warp_tri_eig(nvec, s.ew, nvec >= 3, l1, l2, l3, tn);
+                if (tid == 0) {
+                    int done = 0;
+                    if (ok) {
+                        const double r1 = bj * fabs(s.ew.y[nvec - 1]), r2 = bj * fabs(s.ew.y[2 * nvec - 1]);
+                        const double gap1 = l1 - l2, gap2 = fmin(l1 - l2, nvec >= 3 ? l2 - l3 : l1 - l2);
+                        const double floor_ = 1e-14 * tn;
+                        done = (r1 <= fmax(1e-9 * gap1, floor_)) && (r2 <= fmax(1e-9 * gap2, floor_));
+                    }
+                    sh_val[0] = l1; sh_val[1] = l2; sh_val[2] = l3; sh_val[3] = tn;
+                    sh_flag = ok ? (done ? 2 : 1) : 0;
+                }
+            }
+            __syncthreads();
+            lam1 = sh_val[0]; lam2 = sh_val[1]; lam3 = sh_val[2];
+            const int flag = sh_flag;
+            __syncthreads();
+            have = flag != 0;
+            if (flag == 0) { degenerate = sh_val[3] == 0.0 ? 1 : 2; break; }
+            if (flag == 2 || breakdown || nvec == cap || nvec == m) break;
+        } else if (breakdown || nvec == m) {
+            break;                                                  /* nvec == 1 */
+        }
+        /* next vector */
+        const double rb = 1.0 / bj;
+        double *qn = Q + (size_t)(j + 1) * m;
+        for (int e = tid; e < m; e += T) { const double v = s.w[e] * rb; s.q[e] = v; qn[e] = v; }
+        __syncthreads();
+    }
+    if (steps_out && tid == 0) *steps_out = nvec;
+
+    /* ---- 3. coordinates */
+    if (degenerate || !have) {
+        /* B = 0 gives X = 0 as the one-warp path does; non-finite input gives NaN; a 1 x 1 Krylov space (m == 1, or q0 an
+           eigenvector) has one Ritz pair: alpha_0 along q0 */
+        double v = degenerate == 2 ? bnorm - bnorm : 0.0;
+        if (!degenerate && nvec == 1) {
+            double a0 = s.alpha[0];
+            if (a0 < 0.0 && -a0 <= 1e-13 * bnorm) a0 = 0.0;
+            const double r = sqrt(a0);
+            for (int e = tid; e < m; e += T) { X[2 * e] = s.q[e] * r; X[2 * e + 1] = 0.0; }
+            if (tid == 0 && evals3) { evals3[0] = s.alpha[0]; evals3[1] = 0.0; evals3[2] = 0.0; }
+        } else {
+            for (int e = tid; e < 2 * m; e += T) X[e] = v;
+            if (tid == 0 && evals3) { evals3[0] = v; evals3[1] = v; evals3[2] = v; }
+        }
+        __syncthreads();
+        return;
+    }
+    const double tnorm = sh_val[3];
+    if (lam1 < 0.0 && -lam1 <= 1e-13 * tnorm) lam1 = 0.0;
+    if (lam2 < 0.0 && -lam2 <= 1e-13 * fmax(fabs(lam1), tnorm * 1e-3)) lam2 = 0.0;
+    const double r1 = sqrt(lam1), r2 = sqrt(lam2);
+    const double *y0 = s.ew.y, *y1 = s.ew.y + nvec;
+    for (int e = tid; e < m; e += T) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int i = 0; i < nvec; i++) { const double qv = Q[(size_t)i * m + e]; a0 += qv * y0[i]; a1 += qv * y1[i]; }
+        X[2 * e] = a0 * r1; X[2 * e + 1] = a1 * r2;
+    }
+    if (tid == 0 && evals3) { evals3[0] = lam1; evals3[1] = lam2; evals3[2] = lam3; }
+    __syncthreads();
+}
+
+/* mds 0 (and the first half of mds 2) for large cohorts: one CTA walks windows blockIdx.x, +gridDim.x, ...;
+   gscratch: per CTA fpt_css_mats_doubles(m) doubles (B, then the Lanczos basis) */
+__global__ void __launch_bounds__(512, 2)
+fpt_css_mds_large_kernel(const unsigned *__restrict__ planes, const double *__restrict__ absdiff, int m,
+                         const int *__restrict__ wleft, const int *__restrict__ wright, long long nwin, int wch,
+                         double *__restrict__ gscratch, double *__restrict__ Xout, double *__restrict__ evals_out,
+                         unsigned char *__restrict__ status, int *__restrict__ steps_out) {
+    FPT_DYN_SMEM(smem);
+    const FptLanczosSmem s = fpt_lanczos_carve(smem, m, wch);
+    double *M0 = gscratch + (size_t)blockIdx.x * fpt_css_mats_doubles(m), *M1 = M0 + (size_t)m * m;
+    for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
+        const int l = wleft[w], r = wright[w];
+        if (r <= l) { if (threadIdx.x == 0) status[w] = FPT_WIN_EMPTY; continue; }
+        const int keep = fpt_css_dissimilarity(planes, absdiff, m, l, r, M0, s.sc);
+        if (!keep) { if (threadIdx.x == 0) status[w] = FPT_WIN_DISCARDED; __syncthreads(); continue; }
+        fpt_css_cmds_lanczos(M0, M1, m, Xout + (size_t)w * 2 * m, evals_out ? evals_out + 3 * w : 0, s, steps_out ? steps_out + w : 0);
+        if (threadIdx.x == 0) status[w] = FPT_WIN_SCORED;
+        __syncthreads();
+    }
+}
+
+#endif

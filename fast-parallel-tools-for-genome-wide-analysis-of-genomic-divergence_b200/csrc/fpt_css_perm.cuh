@@ -76,16 +76,17 @@ FPT_D void fpt_shuffle_row(unsigned char *row, int m, const uint2 *rtab, uint64_
    alone and the caller replays the permutation on the exact path above. */
 FPT_D bool fpt_shuffle_row_optimistic(unsigned char *row, int m, const uint2 *rtab, uint64_t &st) {
     uint64_t s = st;
-    bool rejected = false;
+    uint32_t over = 0u;                                     /* bit 31 set once some r > limit (both are < 2^31) */
     for (int i = m - 1; i > 0; i--) {
         const uint2 lm = rtab[i + 1];
         const uint32_t n = (uint32_t)(i + 1);
         const uint32_t r = (uint32_t)(fpt_lcg_next(s) >> 17);
-        rejected |= r > lm.x;
+        over |= lm.x - r;
         uint32_t rem = r - __umulhi(r, lm.y) * n;
         if (rem >= n) rem -= n;
         const unsigned char t = row[i]; row[i] = row[rem]; row[rem] = t;
     }
+    const bool rejected = (over >> 31) != 0u;
     if (!rejected) st = s;
     return !rejected;
 }

@@ -1,0 +1,18 @@
+import sys, time, json, numpy as np
+sys.path.insert(0, '/root/repo')
+import fpt_b200.api as api, fpt_b200.synth as synth
+from fpt_b200 import _lib
+import ctypes as C
+lib=_lib.load()
+asize=bsize=500
+nwin=int(sys.argv[1]) if len(sys.argv)>1 else 148
+regend=50000*nwin
+ch=synth.chromosome_fast(3, regend, 167*nwin, asize, bsize, wstep=50000)
+lib.fpt_profile_enable(1)
+for runs in (1000,):
+    t=time.time()
+    s,p,wr=api.css_scan(ch["acodes"],ch["bcodes"],ch["pos"],asize,bsize,regend,50000,50000,1000,runs,mds=0,seed=1)
+    dt=time.time()-t
+    buf=C.create_string_buffer(8192); lib.fpt_profile_summary(buf,8192)
+    print(runs, 'windows', nwin, 'scored', int((wr==1).sum()) if wr is not None else None, 'sec', round(dt,2), buf.value.decode())
+    print(s[:4], p[:4])

@@ -11,6 +11,7 @@ FPT_EMU_DEFINE_GLOBALS
 #include "fpt_fet.cuh"
 #include "fpt_css.cuh"
 #include "fpt_css_eig.cuh"
+#include "fpt_css_lanczos.cuh"
 #include "fpt_css_perm.cuh"
 #include "fpt_tables.h"
 
@@ -98,6 +99,15 @@ void emu_css_mds(const unsigned *planes, const double *absdiff, int m, const int
     double *gp = mats_in_smem ? 0 : gs.data();
     run_grid(grid, 128, smem, [=]() {
         fpt_css_mds_kernel(planes, absdiff, m, wleft, wright, nwin, wch, mats_in_smem, gp, X, evals, status);
+    });
+}
+
+void emu_css_mds_large(const unsigned *planes, const double *absdiff, int m, const int *wleft, const int *wright,
+                       long long nwin, int wch, int threads, int grid, double *X, double *evals, unsigned char *status, int *steps) {
+    std::vector<double> gs((size_t)grid * fpt_css_mats_doubles(m));
+    double *gp = gs.data();
+    run_grid(grid, threads, fpt_lanczos_smem_bytes(m, wch), [=]() {
+        fpt_css_mds_large_kernel(planes, absdiff, m, wleft, wright, nwin, wch, gp, X, evals, status, steps);
     });
 }
 

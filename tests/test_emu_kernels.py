@@ -190,6 +190,47 @@ def test_css_mds_kernels(emu, oracle, kernel):
     assert scored >= 10
 
 
+@pytest.mark.parametrize("shape", [(6, 5, 220, 20000), (30, 34, 260, 12000), (1, 1, 60, 6000)])
+def test_css_mds_large_cohort_kernel(emu, oracle, shape):
+    """the Lanczos kernel used beyond the one-warp path, run here on small and medium cohorts (it is size-agnostic): early
+    stop by the residual test (m = 64), complete Krylov space (m = 11, 2), windows discarded by fill_averages"""
+    asize, bsize, S, L = shape
+    wsize, wstep = 2500, 500
+    m = asize + bsize
+    pos, av, bv = _css_input(6, asize, bsize, S, L)
+    planes = _pack(emu, av, bv, S, asize, bsize)
+    n = L // wstep
+    wl, wr = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    emu.emu_window_table(iptr(pos), ll(S), ll(0), ll(n), L, wsize, wstep, 0, iptr(wl), iptr(wr))
+    X, ev, st, steps = np.zeros((n, m, 2)), np.zeros((n, 3)), np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.int32)
+    emu.emu_css_mds_large(vp(planes), None, m, iptr(wl), iptr(wr), ll(n), 2, 64, 2, dptr(X), dptr(ev), vp(st), iptr(steps))
+    scored = 0
+    for w in range(n):
+        l, r = int(wl[w]), int(wr[w])
+        if r <= l:
+            assert st[w] == 0
+            continue
+        D = np.zeros((m, m))
+        oracle.fpt_oracle_compare_all(dptr(av[l * asize:r * asize].copy()), dptr(bv[l * bsize:r * bsize].copy()), asize, bsize, r - l, dptr(D))
+        keep = oracle.fpt_oracle_fill_averages(dptr(D), m)
+        assert st[w] == (2 if keep else 1)
+        if not keep:
+            continue
+        assert 1 <= steps[w] <= m
+        Xo, evo = np.zeros((m, 2)), np.zeros(3)
+        oracle.fpt_oracle_cmds(dptr(D), m, dptr(Xo), dptr(evo))
+        assert np.allclose(ev[w, :2], evo[:2], rtol=1e-9, atol=1e-10 * abs(evo[0]))
+        do, dg = np.zeros((m, m)), np.zeros((m, m))
+        oracle.fpt_oracle_calc_dist(dptr(Xo), m, dptr(do))
+        oracle.fpt_oracle_calc_dist(dptr(X[w].copy()), m, dptr(dg))
+        if np.isfinite(do).all() and np.isfinite(dg).all() and (m < 3 or evo[1] - evo[2] > 1e-6 * evo[0]):
+            assert np.allclose(do, dg, rtol=1e-6, atol=1e-8 * do.max())
+            scored += 1
+    assert scored >= (10 if m > 2 else 5)
+    if m == 64:
+        assert steps[st == 2].max() < m          # the residual test stops well before the Krylov space is complete
+
+
 @pytest.mark.parametrize("mds", [1, 2])
 def test_css_smacof_and_perm_kernels(emu, oracle, mds):
     asize, bsize, S, L, wsize, wstep = 4, 4, 90, 6000, 2500, 500

@@ -296,6 +296,20 @@ def test_css_large_cohort_500_plus_500(fpt, oracle):
     assert np.array_equal(p_g, p_o)
 
 
+@pytest.mark.parametrize("mds", [0, 2])
+def test_css_cohort_beyond_the_warp_path(fpt, oracle, mds):
+    """150+150 individuals: classical MDS by the Lanczos kernel (CTA per window, matrices in global scratch), permutations by
+    the first-generation kernel with 16-bit labels"""
+    asize = bsize = 150
+    regend, wsize, wstep, nsnp, seed = 400000, 20000, 10000, 4000, 9
+    ch, (av, bv, apos, bpos) = _synth(77, regend, nsnp, asize, bsize, wstep=wstep)
+    s_o, p_o = _css_oracle_scan(oracle, av, bv, apos, bpos, regend, wsize, wstep, 5, 60, mds, 0, seed)
+    s_g, p_g, wr = fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 5, 60, mds=mds, seed=seed)
+    assert np.array_equal(wr == 1, p_o != 0) and (wr == 1).sum() >= 30
+    np.testing.assert_allclose(s_g, s_o, rtol=CSS_RTOL, atol=1e-12)
+    assert np.array_equal(p_g, p_o)
+
+
 def test_css_frequency_metric(fpt, oracle):
     """drosophila = 1: two frequency tracks, m = 2 (compare_freq)"""
     rng = np.random.default_rng(3)
