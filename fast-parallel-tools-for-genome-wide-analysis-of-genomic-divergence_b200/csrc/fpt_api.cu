@@ -24,6 +24,7 @@
 #include "fpt_css_eig.cuh"
 #include "fpt_css_lanczos.cuh"
 #include "fpt_css_perm.cuh"
+#include "fpt_css_perm_large.cuh"
 #include "fpt_fet.cuh"
 #include "fpt_rt.cuh"
 #include "fpt_tables.h"
@@ -464,7 +465,7 @@ struct CssPlan {
     size_t smem_large; int wch_large; /* large cohorts: Lanczos kernel, one 512-thread CTA per window */
     int mds_warps;                   /* > 0: classical MDS runs one warp per window, this many warps per CTA */
     size_t smem_mds_warp;
-    int perm_threads, wide_tracks, dist_in_smem, tracks_in_smem;
+    int perm_threads, wide_tracks, dist_in_smem, tracks_in_smem, perm_sur;
     size_t smem_perm, perm_scratch_per_cta;
     int perm2, qbits;                /* second-generation permutation kernel (labels in bytes, everything in smem) */
     size_t smem_perm2;
@@ -486,9 +487,15 @@ static CssPlan css_plan(const DeviceCtx *c, int m) {
     p.wide_tracks = m > 256;
     const int tb = p.wide_tracks ? 2 : 1;
     p.dist_in_smem = (size_t)m * m * 8 + (size_t)4 * 1024 <= budget;
-    p.tracks_in_smem = fpt_css_perm_smem_bytes(m, p.perm_threads, tb, p.dist_in_smem, 1) <= budget;
-    p.smem_perm = fpt_css_perm_smem_bytes(m, p.perm_threads, tb, p.dist_in_smem, p.tracks_in_smem);
-    size_t per = (p.dist_in_smem ? 0 : (size_t)m * m * 8) + (p.tracks_in_smem ? 0 : (size_t)2 * p.perm_threads * m * tb);
+    /* general kernel: with the distance matrix in global memory the exact evaluation is a quarter of a million scattered
+       loads per permutation, so the integer surrogate goes on (its membership rows want 128-thread CTAs) */
+    p.perm_sur = !p.dist_in_smem && fpt_css_perm_smem_bytes(m, 128, tb, 0, 0, 1) <= budget;
+    if (p.perm_sur) p.perm_threads = 128;
+    p.tracks_in_smem = fpt_css_perm_smem_bytes(m, p.perm_threads, tb, p.dist_in_smem, 1, p.perm_sur) <= budget;
+    p.smem_perm = fpt_css_perm_smem_bytes(m, p.perm_threads, tb, p.dist_in_smem, p.tracks_in_smem, p.perm_sur);
+    size_t per = (p.dist_in_smem ? 0 : (size_t)m * m * 8) +
+                 (p.tracks_in_smem ? 0 : (((size_t)2 * p.perm_threads * m * tb + 15) & ~(size_t)15)) +
+                 (p.perm_sur ? fpt_perm_large_sur_scratch(m) : 0);
     p.perm_scratch_per_cta = (per + 255) & ~(size_t)255;
     /* cohorts beyond the one-warp path keep two m x m matrices per CTA in global scratch: bound the persistent grid */
     p.max_ctas = p.mds_warps > 0 ? c->sms * 16 : c->sms * 2;
@@ -551,7 +558,7 @@ static int launch_perm(DeviceCtx *c, const CssPlan &p, const CssWorkspace &ws, i
     grid = std::min(grid, p.max_ctas);
     { ProfScope ps_("css_perm", st); fpt_css_perm_kernel<TrackT><<<grid, p.perm_threads, p.smem_perm, st>>>(
         ws.X, p.m, asize, bsize, wbase, nwin, status, treshold, runs, seed, states, g_perm_chain, p.dist_in_smem, p.tracks_in_smem,
-        (double *)ws.perm_scratch, p.perm_scratch_per_cta, scores, pv, hits, nperm); }
+        (double *)ws.perm_scratch, p.perm_scratch_per_cta, p.perm_sur ? 23 : 0, scores, pv, hits, nperm, c->rechecks); }
     CU(cudaGetLastError());
     return FPT_OK;
 }

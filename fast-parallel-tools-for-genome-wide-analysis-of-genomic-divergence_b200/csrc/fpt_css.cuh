@@ -504,142 +504,4 @@ FPT_D double fpt_css_score(const double *dist, int m, const TrackT *at, const Tr
     return __dsub_rn(bet, __dmul_rn((double)(asize + bsize), __dadd_rn(wa, wb)));
 }
 
-FPT_HD size_t fpt_css_perm_smem_bytes(int m, int nthreads, int track_bytes, int dist_in_smem, int tracks_in_smem) {
-    size_t off = dist_in_smem ? (size_t)m * m * 8 : 0;
-    off += (size_t)2 * m * 8;                                   /* X */
-    off += (size_t)nthreads * 4 * 2;                            /* offs, cons */
-    off += 33 * 4 + 16;
-    off = (off + 15) & ~(size_t)15;
-    off += (size_t)m * track_bytes;                             /* carry */
-    off = (off + 15) & ~(size_t)15;
-    if (tracks_in_smem) off += (size_t)2 * nthreads * m * track_bytes;
-    return off;
-}
-
-template <typename TrackT>
-__global__ void __launch_bounds__(256)
-fpt_css_perm_kernel(const double *__restrict__ Xall, int m, int asize, int bsize, long long wbase, long long nwin,
-                    const unsigned char *__restrict__ status, int treshold, int runs, uint64_t seed,
-                    const uint64_t *__restrict__ state_override, int chain, int dist_in_smem, int tracks_in_smem,
-                    double *__restrict__ gscratch, size_t gscratch_per_cta, double *__restrict__ out_score,
-                    double *__restrict__ out_p, int *__restrict__ out_hits, int *__restrict__ out_n) {
-    FPT_DYN_SMEM(smem);
-    const int T = blockDim.x, tid = threadIdx.x;
-    size_t off = 0;
-    unsigned char *gs = gscratch ? (unsigned char *)gscratch + (size_t)blockIdx.x * gscratch_per_cta : 0;
-    double *dist;
-    if (dist_in_smem) { dist = (double *)(smem + off); off += (size_t)m * m * 8; }
-    else { dist = (double *)gs; gs += (size_t)m * m * 8; }
-    double *X = (double *)(smem + off); off += (size_t)2 * m * 8;
-    int *offs = (int *)(smem + off); off += (size_t)T * 4;
-    int *cons = (int *)(smem + off); off += (size_t)T * 4;
-    int *scan = (int *)(smem + off); off += 33 * 4 + 16;
-    off = (off + 15) & ~(size_t)15;
-    TrackT *carry = (TrackT *)(smem + off); off += (size_t)m * sizeof(TrackT);
-    off = (off + 15) & ~(size_t)15;
-    TrackT *buf0, *buf1;
-    if (tracks_in_smem) { buf0 = (TrackT *)(smem + off); buf1 = buf0 + (size_t)T * m; }
-    else { buf0 = (TrackT *)gs; buf1 = buf0 + (size_t)T * m; }
-    __shared__ double s_score;
-    __shared__ int s_flag;
-
-    for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
-        if (status[w] != FPT_WIN_SCORED) continue;
-        for (int e = tid; e < 2 * m; e += T) X[e] = Xall[(size_t)w * 2 * m + e];
-        __syncthreads();
-        for (int e = tid; e < m * m; e += T) {                  /* calc_dist, css.c:573-587 */
-            const int i = e / m, j = e - i * m;
-            if (j < i) {
-                const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
-                const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-                dist[e] = d; dist[j * m + i] = d;
-            } else if (j == i) dist[e] = 0.0;
-        }
-        for (int e = tid; e < m; e += T) carry[e] = (TrackT)e;
-        __syncthreads();
-        if (tid == 0) s_score = fpt_css_score<TrackT>(dist, m, carry, carry + asize, asize, bsize);
-        __syncthreads();
-        const double score = s_score;
-        const uint64_t st_win = state_override ? state_override[w] : fpt_stream_state(seed, wbase + w, FPT_STREAM_RESAMPLE);
-        const int draws = m - 1;
-        long long stream_pos = 0;                               /* draws consumed by finished chunks */
-        int hits = 0, ndone = 0;
-        bool stopped = false;
-        while (!stopped && hits < treshold && ndone < runs) {
-            const int nvalid = min(T, runs - ndone);
-            offs[tid] = tid * draws;
-            __syncthreads();
-            TrackT *mine = buf0 + (size_t)tid * m;
-            for (;;) {                                          /* generate; repair offsets after rejections */
-                int used = 0;
-                if (tid < nvalid) {
-                    /* chain: stream consumed sequentially; independent: permutation k starts k*(m-1) draws in */
-                    uint64_t st = fpt_lcg_skip(st_win, chain ? (uint64_t)(stream_pos + offs[tid])
-                                                             : (uint64_t)(ndone + tid) * (uint64_t)draws);
-                    for (int e = 0; e < m; e++) mine[e] = (TrackT)e;
-                    for (int i = m - 1; i > 0; i--) {
-                        const int rr = (int)fpt_randint((uint32_t)(i + 1), st, used);
-                        const TrackT t = mine[i]; mine[i] = mine[rr]; mine[rr] = t;
-                    }
-                }
-                int total = 0;
-                const int incl = fpt_block_scan_incl(used, scan, &total);
-                const int want = incl - used;
-                const int bad = (chain && tid < nvalid && want != offs[tid]) ? 1 : 0;
-                if (bad) offs[tid] = want;
-                cons[tid] = total;
-                if (!__syncthreads_or(bad)) break;
-            }
-            const int chunk_draws = cons[0];
-            /* inclusive scan under composition: G_k = s_1 o ... o s_k, (f o g)[pos] = f[g[pos]] */
-            TrackT *src = buf0, *dst = buf1;
-            for (int d = 1; chain && d < nvalid; d <<= 1) {
-                __syncthreads();
-                if (tid < nvalid) {
-                    const TrackT *g = src + (size_t)tid * m;
-                    TrackT *o = dst + (size_t)tid * m;
-                    if (tid >= d) {
-                        const TrackT *f = src + (size_t)(tid - d) * m;
-                        for (int e = 0; e < m; e++) o[e] = f[g[e]];
-                    } else {
-                        for (int e = 0; e < m; e++) o[e] = g[e];
-                    }
-                }
-                TrackT *tmp = src; src = dst; dst = tmp;
-            }
-            __syncthreads();
-            int hit = 0;
-            if (tid < nvalid) {
-                const TrackT *g = src + (size_t)tid * m;
-                TrackT *o = dst + (size_t)tid * m;                /* labels after permutation ndone+tid+1 */
-                if (chain) for (int e = 0; e < m; e++) o[e] = carry[g[e]];
-                else for (int e = 0; e < m; e++) o[e] = g[e];  /* fresh identity labels every time */
-                hit = fpt_css_score<TrackT>(dist, m, o, o + asize, asize, bsize) >= score ? 1 : 0;
-            }
-            int chunk_hits = 0;
-            const int hincl = fpt_block_scan_incl(hit, scan, &chunk_hits);
-            if (tid == 0) s_flag = -1;
-            __syncthreads();
-            if (hit && hits + hincl == treshold) s_flag = tid;  /* the permutation at which the loop exits */
-            __syncthreads();
-            if (s_flag >= 0) {
-                ndone += s_flag + 1; hits = treshold; stopped = true;
-            } else {
-                hits += chunk_hits; ndone += nvalid;
-                const TrackT *last = dst + (size_t)(nvalid - 1) * m;
-                for (int e = tid; e < m; e += T) carry[e] = last[e];
-                stream_pos += chunk_draws;
-            }
-            __syncthreads();
-        }
-        if (tid == 0) {
-            out_score[w] = score;
-            out_p[w] = __ddiv_rn(__dmul_rn((double)(hits + 1), 1.0), (double)(ndone + 1));
-            if (out_hits) out_hits[w] = hits;
-            if (out_n) out_n[w] = ndone;
-        }
-        __syncthreads();
-    }
-}
-
 #endif

@@ -13,6 +13,7 @@ FPT_EMU_DEFINE_GLOBALS
 #include "fpt_css_eig.cuh"
 #include "fpt_css_lanczos.cuh"
 #include "fpt_css_perm.cuh"
+#include "fpt_css_perm_large.cuh"
 #include "fpt_tables.h"
 
 template <class F>
@@ -142,26 +143,46 @@ void emu_css_pick(const double *Xruns, const double *sigma_runs, int m, int nrun
     run_grid(2, 64, 0, [=]() { fpt_css_pick_kernel(Xruns, sigma_runs, m, nruns, nwin, status, Xout); });
 }
 
-void emu_css_perm(const double *Xall, int m, int asize, int bsize, long long wbase, long long nwin, const unsigned char *status,
+static unsigned long long emu_css_perm_impl(const double *Xall, int m, int asize, int bsize, long long wbase, long long nwin, const unsigned char *status,
                   int treshold, int runs, uint64_t seed, const uint64_t *state_override, int dist_in_smem,
-                  int tracks_in_smem, int nthreads, int grid, int wide_tracks, int chain, double *out_score, double *out_p,
+                  int tracks_in_smem, int nthreads, int grid, int wide_tracks, int chain, int qbits, double *out_score, double *out_p,
                   int *out_hits, int *out_n) {
     int tb = wide_tracks ? 2 : 1;
-    size_t smem = fpt_css_perm_smem_bytes(m, nthreads, tb, dist_in_smem, tracks_in_smem);
-    size_t per_cta = (dist_in_smem ? 0 : (size_t)m * m * 8) + (tracks_in_smem ? 0 : (size_t)2 * nthreads * m * tb);
+    size_t smem = fpt_css_perm_smem_bytes(m, nthreads, tb, dist_in_smem, tracks_in_smem, qbits > 0);
+    size_t per_cta = (dist_in_smem ? 0 : (size_t)m * m * 8) + (tracks_in_smem ? 0 : (((size_t)2 * nthreads * m * tb + 15) & ~(size_t)15));
+    if (qbits > 0) per_cta += fpt_perm_large_sur_scratch(m);
     per_cta = (per_cta + 15) & ~(size_t)15;
     std::vector<double> gs(per_cta ? (size_t)grid * per_cta / 8 + 2 : 1);
     double *gp = per_cta ? gs.data() : 0;
+    unsigned long long rechecks = 0, *pr = &rechecks;
     if (wide_tracks)
         run_grid(grid, nthreads, smem, [=]() {
             fpt_css_perm_kernel<unsigned short>(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override, chain,
-                                                dist_in_smem, tracks_in_smem, gp, per_cta, out_score, out_p, out_hits, out_n);
+                                                dist_in_smem, tracks_in_smem, gp, per_cta, qbits, out_score, out_p, out_hits, out_n, pr);
         });
     else
         run_grid(grid, nthreads, smem, [=]() {
             fpt_css_perm_kernel<unsigned char>(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override, chain,
-                                               dist_in_smem, tracks_in_smem, gp, per_cta, out_score, out_p, out_hits, out_n);
+                                               dist_in_smem, tracks_in_smem, gp, per_cta, qbits, out_score, out_p, out_hits, out_n, pr);
         });
+    return rechecks;
+}
+
+void emu_css_perm(const double *Xall, int m, int asize, int bsize, long long wbase, long long nwin, const unsigned char *status,
+                  int treshold, int runs, uint64_t seed, const uint64_t *state_override, int dist_in_smem,
+                  int tracks_in_smem, int nthreads, int grid, int wide_tracks, int chain, double *out_score, double *out_p,
+                  int *out_hits, int *out_n) {
+    emu_css_perm_impl(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override, dist_in_smem, tracks_in_smem,
+                      nthreads, grid, wide_tracks, chain, 0, out_score, out_p, out_hits, out_n);
+}
+
+/* the general kernel with the integer surrogate on (q and digit matrices in global scratch) */
+unsigned long long emu_css_perm_sur(const double *Xall, int m, int asize, int bsize, long long wbase, long long nwin, const unsigned char *status,
+                  int treshold, int runs, uint64_t seed, const uint64_t *state_override, int dist_in_smem,
+                  int tracks_in_smem, int nthreads, int grid, int wide_tracks, int chain, int qbits, double *out_score, double *out_p,
+                  int *out_hits, int *out_n) {
+    return emu_css_perm_impl(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override, dist_in_smem, tracks_in_smem,
+                             nthreads, grid, wide_tracks, chain, qbits, out_score, out_p, out_hits, out_n);
 }
 
 unsigned long long emu_css_perm2(const double *Xall, int m, int asize, int bsize, long long wbase, long long nwin,

@@ -320,7 +320,47 @@ def test_css_perm_kernels_chunks_early_stop_and_scratch_paths(emu, oracle, chain
                 emu.emu_css_perm(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), tres, runs, C.c_uint64(0), vp(states), dist_smem, tracks_smem,
                                  32, 2, wide, chain, dptr(sc), dptr(p), iptr(hits), iptr(nn))
                 assert list(hits) == want_h and list(nn) == want_n and list(p) == want_p
+            # the general kernel with the large-cohort surrogate (q, digit matrices, labels in global scratch; u8 MMA)
+            emu.emu_css_perm_sur.restype = C.c_ulonglong
+            for wide, qb in ((1, 23), (0, 9)):
+                sc, p, hits, nn = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+                rechecks = emu.emu_css_perm_sur(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), tres, runs, C.c_uint64(0), vp(states), 0, 0,
+                                                32, 2, wide, chain, qb, dptr(sc), dptr(p), iptr(hits), iptr(nn))
+                assert list(hits) == want_h and list(nn) == want_n and list(p) == want_p
+                if m == 4:
+                    assert rechecks > 0                            # the tie window cannot be decided by the surrogate
             sc, p, hits, nn = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
             emu.emu_css_perm2(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), tres, runs, C.c_uint64(0), vp(states), chain, qbits, 32, 2,
                               dptr(sc), dptr(p), iptr(hits), iptr(nn))
             assert list(hits) == want_h and list(nn) == want_n and list(p) == want_p
+
+
+def test_css_perm_surrogate_many_tiles(emu, oracle):
+    """the large-cohort surrogate over several 32-deep k-steps and 8-wide column tiles (m = 70: 3 k-steps, 9 tiles, ragged)"""
+    emu.emu_css_perm_sur.restype = C.c_ulonglong
+    rng = np.random.default_rng(21)
+    asize, bsize, n = 33, 37, 2
+    m = asize + bsize
+    X = rng.normal(size=(n, m, 2))
+    X[1, :asize, 0] += 0.6
+    st = np.full(n, 2, dtype=np.uint8)
+    states = np.array([5, 77], dtype=np.uint64)
+    for chain in (0, 1):
+        want = []
+        for w in range(n):
+            dist = np.zeros((m, m))
+            oracle.fpt_oracle_calc_dist(dptr(X[w].copy()), m, dptr(dist))
+            tr = np.arange(m, dtype=np.int32)
+            score = oracle.fpt_oracle_css(dptr(dist), m, iptr(tr), iptr(tr[asize:]), asize, bsize)
+            h, nn = C.c_int(), C.c_int()
+            if chain:
+                s64 = C.c_uint64(int(states[w]))
+                pv = oracle.fpt_oracle_significance(dptr(dist), m, iptr(tr), asize, bsize, score, 1000, 48, C.byref(s64), C.byref(h), C.byref(nn))
+            else:
+                pv = oracle.fpt_oracle_significance_indep(dptr(dist), m, asize, bsize, score, 1000, 48, int(states[w]), C.byref(h), C.byref(nn))
+            want.append((pv, h.value, nn.value))
+        sc, p, hits, nn = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        emu.emu_css_perm_sur(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), 1000, 48, C.c_uint64(0), vp(states), 0, 0, 32, 2, 1, chain, 23,
+                             dptr(sc), dptr(p), iptr(hits), iptr(nn))
+        assert [(p[w], hits[w], nn[w]) for w in range(n)] == want
+        assert 0 < hits[0] < 48                                   # a window where the decisions actually vary
