@@ -558,7 +558,7 @@ static int launch_perm(DeviceCtx *c, const CssPlan &p, const CssWorkspace &ws, i
     grid = std::min(grid, p.max_ctas);
     { ProfScope ps_("css_perm", st); fpt_css_perm_kernel<TrackT><<<grid, p.perm_threads, p.smem_perm, st>>>(
         ws.X, p.m, asize, bsize, wbase, nwin, status, treshold, runs, seed, states, g_perm_chain, p.dist_in_smem, p.tracks_in_smem,
-        (double *)ws.perm_scratch, p.perm_scratch_per_cta, p.perm_sur ? 23 : 0, scores, pv, hits, nperm, c->rechecks); }
+        (double *)ws.perm_scratch, p.perm_scratch_per_cta, p.perm_sur ? 31 : 0, scores, pv, hits, nperm, c->rechecks); }
     CU(cudaGetLastError());
     return FPT_OK;
 }

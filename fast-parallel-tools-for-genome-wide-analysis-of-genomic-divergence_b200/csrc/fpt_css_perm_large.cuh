@@ -24,14 +24,16 @@
    that consecutive rows start in different banks / sectors */
 FPT_HD int fpt_perm_large_kpad(int m) { return ((m + 31) >> 5) << 5; }
 FPT_HD int fpt_perm_large_stride(int m) { return fpt_perm_large_kpad(m) + 16; }
-FPT_HD size_t fpt_perm_large_sur_scratch(int m) {            /* q (u32 m x m) + three digit matrices */
+#define FPT_LARGE_DIGITS 4        /* base-256 digits of q: qbits <= 31 */
+FPT_HD size_t fpt_perm_large_sur_scratch(int m) {            /* q (u32 m x m) + the digit matrices */
     const size_t nrows = (size_t)(((m + 7) >> 3) << 3);
-    size_t b = (size_t)m * m * 4 + 3 * nrows * fpt_perm_large_stride(m);
+    size_t b = (size_t)m * m * 4 + FPT_LARGE_DIGITS * nrows * fpt_perm_large_stride(m);
     return (b + 255) & ~(size_t)255;
 }
 
 /* sum over A'xB' of q for the 32 permutations of a warp (lane L owns permutation L), any m.
-   ind: the warp's 32 membership rows (stride zs bytes, shared memory); qd: digit matrices [3][nrows][qs] in global memory.
+   ind: the warp's 32 membership rows (stride zs bytes, shared memory); qd: digit matrices [FPT_LARGE_DIGITS][nrows][qs] in
+   global memory.
    Per 8-column tile and 32-deep k-step: 8 fragment loads of A (shared), 2 of B per digit (global, L1/L2), 2 MMAs per digit. */
 FPT_D long long fpt_bet_mma_large(const unsigned char *ind, int zs, const unsigned char *__restrict__ qd, int qs, int m) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -40,9 +42,9 @@ FPT_D long long fpt_bet_mma_large(const unsigned char *ind, int zs, const unsign
     const size_t dstride = (size_t)nrows * qs;
     long long sum[4] = { 0, 0, 0, 0 };                  /* masked row sums: tile 0 rows g, g+8; tile 1 rows g, g+8 */
     for (int nt = 0; nt < ntiles; nt++) {
-        int c0[3][4], c1[3][4];
+        int c0[FPT_LARGE_DIGITS][4], c1[FPT_LARGE_DIGITS][4];
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
+        for (int d = 0; d < FPT_LARGE_DIGITS; d++) {
 #pragma unroll
             for (int i = 0; i < 4; i++) { c0[d][i] = 0; c1[d][i] = 0; }
         }
@@ -55,7 +57,7 @@ FPT_D long long fpt_bet_mma_large(const unsigned char *ind, int zs, const unsign
             a1[0] = *reinterpret_cast<const unsigned *>(ar + 16 * zs);      a1[1] = *reinterpret_cast<const unsigned *>(ar + 24 * zs);
             a1[2] = *reinterpret_cast<const unsigned *>(ar + 16 * zs + 16); a1[3] = *reinterpret_cast<const unsigned *>(ar + 24 * zs + 16);
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
+            for (int d = 0; d < FPT_LARGE_DIGITS; d++) {
                 const unsigned char *bp = brow + (size_t)d * dstride + 32 * ks;
                 const unsigned b0 = *reinterpret_cast<const unsigned *>(bp), b1 = *reinterpret_cast<const unsigned *>(bp + 16);
                 fpt_mma_u8(c0[d], a0, b0, b1);
@@ -70,8 +72,9 @@ FPT_D long long fpt_bet_mma_large(const unsigned char *ind, int zs, const unsign
         const unsigned m11 = *reinterpret_cast<const unsigned short *>(mcol + 24 * zs);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const long long r0 = (long long)c0[0][i] + ((long long)c0[1][i] << 8) + ((long long)c0[2][i] << 16);
-            const long long r1 = (long long)c1[0][i] + ((long long)c1[1][i] << 8) + ((long long)c1[2][i] << 16);
+            long long r0 = 0, r1 = 0;
+#pragma unroll
+            for (int d = FPT_LARGE_DIGITS; d--;) { r0 = (r0 << 8) + c0[d][i]; r1 = (r1 << 8) + c1[d][i]; }
             const unsigned bytemask = (i & 1) ? 0xff00u : 0x00ffu;
             const unsigned mk0 = (i < 2) ? m00 : m01, mk1 = (i < 2) ? m10 : m11;
             if (!(mk0 & bytemask)) sum[i >> 1] += r0;
@@ -87,6 +90,62 @@ FPT_D long long fpt_bet_mma_large(const unsigned char *ind, int zs, const unsign
     return sel == 0 ? v0 : (sel == 1 ? v1 : (sel == 2 ? v2 : v3));
 }
 
+/* observed score (identity labels), all threads of the CTA: bit-identical to fpt_css_score on labels 0..m-1.
+   The between-group sum runs over rows asize-1..0 and, inside a row, columns m-1..asize: contiguous memory. */
+FPT_D double fpt_css_score_identity(const double *dist, int m, int asize, int bsize, double *buf, int bufdoubles) {
+    __shared__ double s_val;
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int rows_per_tile = bufdoubles / bsize;
+    double bet = 0.0;
+    if (rows_per_tile < 1) {
+        if (tid == 0) {
+            for (int i = asize; i--;) { const double *row = dist + (size_t)i * m + asize; for (int j = bsize; j--;) bet = __dadd_rn(bet, row[j]); }
+        }
+    } else {
+        for (int ihi = asize - 1; ihi >= 0; ihi -= rows_per_tile) {
+            const int ilo = ihi - rows_per_tile + 1 > 0 ? ihi - rows_per_tile + 1 : 0, nr = ihi - ilo + 1;
+            for (int r = 0; r < nr; r++) {
+                const double *src = dist + (size_t)(ilo + r) * m + asize;
+                double *dst = buf + (size_t)r * bsize;
+                for (int j = tid; j < bsize; j += T) dst[j] = src[j];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int r = nr; r--;) { const double *row = buf + (size_t)r * bsize; for (int j = bsize; j--;) bet = __dadd_rn(bet, row[j]); }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        bet = __ddiv_rn(bet, (double)((long long)asize * bsize));
+        double wa = 0.0, wb = 0.0;
+        if (asize > 1) {
+            for (int i = asize - 1; i--;) wa = __dadd_rn(wa, dist[(size_t)i * m + i + 1]);
+            wa = __ddiv_rn(wa, (double)((long long)asize * asize * (asize - 1)));
+        }
+        if (bsize > 1) {
+            for (int i = bsize - 1; i--;) wb = __dadd_rn(wb, dist[(size_t)(asize + i) * m + asize + i + 1]);
+            wb = __ddiv_rn(wb, (double)((long long)bsize * bsize * (bsize - 1)));
+        }
+        s_val = __dsub_rn(bet, __dmul_rn((double)(asize + bsize), __dadd_rn(wa, wb)));
+    }
+    __syncthreads();
+    const double v = s_val;
+    __syncthreads();
+    return v;
+}
+
+template <typename TrackT>
+FPT_D double fpt_css_score_one_thread(const double *dist, int m, const TrackT *labels, int asize, int bsize) {
+    __shared__ double s_val;
+    __syncthreads();
+    if (threadIdx.x == 0) s_val = fpt_css_score<TrackT>(dist, m, labels, labels + asize, asize, bsize);
+    __syncthreads();
+    const double v = s_val;
+    __syncthreads();
+    return v;
+}
+
 FPT_HD size_t fpt_css_perm_smem_bytes(int m, int nthreads, int track_bytes, int dist_in_smem, int tracks_in_smem, int surrogate) {
     size_t off = dist_in_smem ? (size_t)m * m * 8 : 0;
     off += (size_t)2 * m * 8;                                   /* X */
@@ -97,11 +156,13 @@ FPT_HD size_t fpt_css_perm_smem_bytes(int m, int nthreads, int track_bytes, int 
     off = (off + 15) & ~(size_t)15;
     if (tracks_in_smem) off += (size_t)2 * nthreads * m * track_bytes;
     if (surrogate) { off = (off + 15) & ~(size_t)15; off += (size_t)nthreads * fpt_perm_large_stride(m); }   /* membership rows */
+    off = (off + 15) & ~(size_t)15;
+    off += (size_t)(m + 1) * 8;                                 /* per-n (limit, magic) of the shuffle draws */
     return off;
 }
 
 template <typename TrackT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 fpt_css_perm_kernel(const double *__restrict__ Xall, int m, int asize, int bsize, long long wbase, long long nwin,
                     const unsigned char *__restrict__ status, int treshold, int runs, uint64_t seed,
                     const uint64_t *__restrict__ state_override, int chain, int dist_in_smem, int tracks_in_smem,
@@ -133,66 +194,107 @@ fpt_css_perm_kernel(const double *__restrict__ Xall, int m, int asize, int bsize
         off = (off + 15) & ~(size_t)15;
         ind = smem + off;
     }
+    off = (off + 15) & ~(size_t)15;
+    if (qbits > 0) off += (size_t)T * zs;
+    off = (off + 15) & ~(size_t)15;
+    uint2 *rtab = (uint2 *)(smem + off);
+    for (int n = tid; n <= m; n += T) {
+        uint2 lm;
+        lm.x = n > 0 ? fpt_randint_limit((uint32_t)n) : 0u; lm.y = n > 0 ? fpt_randint_magic((uint32_t)n) : 0u;
+        rtab[n] = lm;
+    }
+    __syncthreads();
     unsigned long long rechecks = 0;
-    __shared__ double s_score, s_dmax;
+    __shared__ double s_dmax;
     __shared__ int s_flag;
 
     for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
         if (status[w] != FPT_WIN_SCORED) continue;
         for (int e = tid; e < 2 * m; e += T) X[e] = Xall[(size_t)w * 2 * m + e];
         __syncthreads();
-        double dmax = 0.0;
-        for (int e = tid; e < m * m; e += T) {                  /* calc_dist, css.c:573-587 */
-            const int i = e / m, j = e - i * m;
-            if (j < i) {
-                const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
-                const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-                dist[e] = d; dist[j * m + i] = d;
-                dmax = fmax(dmax, d);                           /* fmax ignores NaN distances: see `usable` */
-            } else if (j == i) dist[e] = 0.0;
-        }
         for (int e = tid; e < m; e += T) carry[e] = (TrackT)e;
-        for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(FPT_FULL_MASK, dmax, o));
-        double *wmax = reinterpret_cast<double *>(offs);        /* T ints = T/2 doubles >= T/32 warp maxima */
-        if ((tid & 31) == 0) wmax[tid >> 5] = dmax;
+        /* Surrogate scale from the bounding box of the embedding: dub >= every distance, at most sqrt(2) above the largest,
+           and it is known BEFORE the distances are, so one pass writes dist, q and the three digit matrices together. */
+        double xlo = 1e308, xhi = -1e308, ylo = 1e308, yhi = -1e308;
+        for (int e = tid; e < m; e += T) {
+            const double x = X[2 * e], y = X[2 * e + 1];
+            xlo = fmin(xlo, x); xhi = fmax(xhi, x); ylo = fmin(ylo, y); yhi = fmax(yhi, y);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            xlo = fmin(xlo, __shfl_xor_sync(FPT_FULL_MASK, xlo, o)); xhi = fmax(xhi, __shfl_xor_sync(FPT_FULL_MASK, xhi, o));
+            ylo = fmin(ylo, __shfl_xor_sync(FPT_FULL_MASK, ylo, o)); yhi = fmax(yhi, __shfl_xor_sync(FPT_FULL_MASK, yhi, o));
+        }
+        double *wbox = reinterpret_cast<double *>(offs);        /* 2T ints (offs, cons) = T doubles >= 4 per warp */
+        if ((tid & 31) == 0) { double *b4 = wbox + 4 * (tid >> 5); b4[0] = xlo; b4[1] = xhi; b4[2] = ylo; b4[3] = yhi; }
         __syncthreads();
         if (tid == 0) {
-            double mx = 0.0;
-            for (int k = 0; k < (T >> 5); k++) mx = fmax(mx, wmax[k]);
-            s_dmax = mx;
-            s_score = fpt_css_score<TrackT>(dist, m, carry, carry + asize, asize, bsize);
+            for (int k = 1; k < (T >> 5); k++) {
+                xlo = fmin(xlo, wbox[4 * k]); xhi = fmax(xhi, wbox[4 * k + 1]); ylo = fmin(ylo, wbox[4 * k + 2]); yhi = fmax(yhi, wbox[4 * k + 3]);
+            }
+            const double ex = xhi - xlo, ey = yhi - ylo;
+            s_dmax = sqrt(ex * ex + ey * ey) * 1.000000000001;
         }
         __syncthreads();
-        const double score = s_score;
-        dmax = s_dmax;
-        /* surrogate set-up, as in fpt_css_perm2_kernel: q = rint(d S), S = 2^qbits / dmax; error bound E */
-        const bool usable = qbits > 0 && (dmax > 0.0) && (dmax < 1e300) && (score == score) && (fabs(score) < 1e300);
-        const double S = usable ? (double)(1u << qbits) / dmax : 0.0;
-        bool use_surrogate = false;
+        const double dmax = s_dmax;
+        const bool scale_ok = qbits > 0 && (dmax > 0.0) && (dmax < 1e300);
+        const double S = scale_ok ? (double)(1u << qbits) / dmax : 0.0;
+        int bad = 0;
         if (qbits > 0) {
-            int bad = 0;
-            for (int e = tid; e < m * m; e += T) {
-                const double d = dist[e];
-                if (!(d == d)) bad = 1;
-                q[e] = usable && d == d ? (unsigned)__double2ll_rn(d * S) : 0u;
-            }
-            use_surrogate = usable && !__syncthreads_or(bad);
-            const int words = zs >> 2;                          /* digit rows, zero padded, 4 bytes per store */
-            for (int e = tid; e < 3 * qd_rows * words; e += T) {
-                const int d = e / (qd_rows * words), rem = e - d * qd_rows * words, n = rem / words, k4 = (rem - n * words) << 2;
-                unsigned wv = 0;
-                for (int b = 0; b < 4; b++) {
-                    const int k = k4 + b;
-                    const unsigned v = (n < m && k < m) ? ((q[(size_t)n * m + k] >> (8 * d)) & 0xffu) : 0u;
-                    wv |= v << (8 * b);
+            const int words = zs >> 2;
+            for (int e = tid; e < qd_rows * words; e += T) {    /* row n, columns k4 .. k4+3 */
+                const int n = e / words, k4 = (e - n * words) << 2;
+                unsigned w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                if (n < m && k4 < m) {
+                    const double xn = X[2 * n], yn = X[2 * n + 1];
+                    for (int b = 0; b < 4; b++) {
+                        const int k = k4 + b;
+                        if (k >= m) break;
+                        double d = 0.0;
+                        if (k != n) {                           /* calc_dist, css.c:573-587 (symmetric bit for bit) */
+                            const double dx = __dsub_rn(xn, X[2 * k]), dy = __dsub_rn(yn, X[2 * k + 1]);
+                            d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                        }
+                        dist[(size_t)n * m + k] = d;
+                        if (!(d == d)) bad = 1;
+                        const unsigned qv = (scale_ok && d == d) ? (unsigned)__double2ll_rn(d * S) : 0u;
+                        q[(size_t)n * m + k] = qv;
+                        w0 |= (qv & 0xffu) << (8 * b); w1 |= ((qv >> 8) & 0xffu) << (8 * b);
+                        w2 |= ((qv >> 16) & 0xffu) << (8 * b); w3 |= (qv >> 24) << (8 * b);
+                    }
                 }
-                *reinterpret_cast<unsigned *>(qd + ((size_t)d * qd_rows + n) * zs + k4) = wv;
+                {
+                    unsigned char *p0 = qd + (size_t)n * zs + k4;
+                    const size_t ds = (size_t)qd_rows * zs;
+                    *reinterpret_cast<unsigned *>(p0) = w0;
+                    *reinterpret_cast<unsigned *>(p0 + ds) = w1;
+                    *reinterpret_cast<unsigned *>(p0 + 2 * ds) = w2;
+                    *reinterpret_cast<unsigned *>(p0 + 3 * ds) = w3;
+                }
             }
-            __syncthreads();
+        } else {
+            for (int e = tid; e < m * m; e += T) {              /* calc_dist, css.c:573-587 */
+                const int i = e / m, j = e - i * m;
+                if (j < i) {
+                    const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
+                    const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                    dist[e] = d; dist[j * m + i] = d;
+                } else if (j == i) dist[e] = 0.0;
+            }
         }
+        bad = __syncthreads_or(bad);
+        /* observed score in the reference's summation order: with identity labels the rows it walks are contiguous, so the
+           CTA stages them through shared memory (the membership rows' space) and one thread adds them up in order */
+        const double score = (qbits > 0) ? fpt_css_score_identity(dist, m, asize, bsize, reinterpret_cast<double *>(ind), (T * zs) >> 3)
+                                         : fpt_css_score_one_thread<TrackT>(dist, m, carry, asize, bsize);
+        const bool use_surrogate = scale_ok && !bad && (score == score) && (fabs(score) < 1e300);
         const double a_ = (double)asize, b_ = (double)bsize;
         const double wterm = (asize > 1 ? 1.0 / (a_ * a_) : 0.0) + (bsize > 1 ? 1.0 / (b_ * b_) : 0.0);
-        const double E = use_surrogate ? (0.5 / S) * (1.0 + (a_ + b_) * wterm) * 1.0000001 + 1e-11 * dmax * (1.0 + (a_ + b_)) : 0.0;
+        /* |surrogate - reference score| <= E: quantisation (0.5/S)(1 + (a+b)(1/a^2 + 1/b^2)) on the three means, plus the
+           rounding of the two fp64 evaluations: a recursive sum of n terms <= dmax is off by at most (n-1) u n dmax, i.e.
+           (n-1) u dmax on the mean (u = 2^-53); the two adjacent-pair means contribute less than (a+b) u dmax each. Taken
+           eight times over. */
+        const double E = use_surrogate ? (0.5 / S) * (1.0 + (a_ + b_) * wterm) * 1.0000001 +
+                                         8.0 * 1.2e-16 * dmax * (a_ * b_ + 2.0 * (a_ + b_)) : 0.0;
         const double invS = use_surrogate ? 1.0 / S : 0.0;
         const double c_bet = invS / (a_ * b_);
         const double c_wa = asize > 1 ? invS / (a_ * a_ * (a_ - 1.0)) : 0.0;
@@ -215,9 +317,27 @@ fpt_css_perm_kernel(const double *__restrict__ Xall, int m, int asize, int bsize
                     uint64_t st = fpt_lcg_skip(st_win, chain ? (uint64_t)(stream_pos + offs[tid])
                                                              : (uint64_t)(ndone + tid) * (uint64_t)draws);
                     for (int e = 0; e < m; e++) mine[e] = (TrackT)e;
+                    /* optimistic pass: a draw is rejected with probability < n / 2^31; remember, do not branch */
+                    uint64_t s2 = st;
+                    uint32_t over = 0u;
                     for (int i = m - 1; i > 0; i--) {
-                        const int rr = (int)fpt_randint((uint32_t)(i + 1), st, used);
-                        const TrackT t = mine[i]; mine[i] = mine[rr]; mine[rr] = t;
+                        const uint2 lm = rtab[i + 1];
+                        const uint32_t n = (uint32_t)(i + 1);
+                        const uint32_t r = (uint32_t)(fpt_lcg_next(s2) >> 17);
+                        over |= lm.x - r;
+                        uint32_t rem = r - __umulhi(r, lm.y) * n;
+                        if (rem >= n) rem -= n;
+                        const TrackT t = mine[i]; mine[i] = mine[rem]; mine[rem] = t;
+                    }
+                    used = draws;
+                    if (over >> 31) {                           /* replay exactly, counting the draws */
+                        used = 0;
+                        for (int e = 0; e < m; e++) mine[e] = (TrackT)e;
+                        for (int i = m - 1; i > 0; i--) {
+                            const uint2 lm = rtab[i + 1];
+                            const int rr = (int)fpt_randint_fast((uint32_t)(i + 1), lm.x, lm.y, st, used);
+                            const TrackT t = mine[i]; mine[i] = mine[rr]; mine[rr] = t;
+                        }
                     }
                 }
                 int total = 0;
@@ -250,11 +370,9 @@ fpt_css_perm_kernel(const double *__restrict__ Xall, int m, int asize, int bsize
             {
                 const bool valid = tid < nvalid;
                 const TrackT *g = src + (size_t)tid * m;
-                TrackT *o = dst + (size_t)tid * m;                /* labels after permutation ndone+tid+1 */
-                if (valid) {
-                    if (chain) for (int e = 0; e < m; e++) o[e] = carry[g[e]];
-                    else for (int e = 0; e < m; e++) o[e] = g[e];  /* fresh identity labels every time */
-                }
+                TrackT *oc = dst + (size_t)tid * m;
+                if (valid && chain) for (int e = 0; e < m; e++) oc[e] = carry[g[e]];   /* labels after permutation ndone+tid+1 */
+                const TrackT *o = chain ? oc : g;               /* independent: fresh identity labels every time */
                 bool exact = valid && !use_surrogate;
                 const bool warp_active = (tid & ~31) < nvalid;  /* the tensor-core sum is a warp-wide operation */
                 if (use_surrogate && warp_active) {
@@ -303,8 +421,10 @@ fpt_css_perm_kernel(const double *__restrict__ Xall, int m, int asize, int bsize
                 ndone += s_flag + 1; hits = treshold; stopped = true;
             } else {
                 hits += chunk_hits; ndone += nvalid;
-                const TrackT *last = dst + (size_t)(nvalid - 1) * m;
-                for (int e = tid; e < m; e += T) carry[e] = last[e];
+                if (chain) {
+                    const TrackT *last = dst + (size_t)(nvalid - 1) * m;
+                    for (int e = tid; e < m; e += T) carry[e] = last[e];
+                }
                 stream_pos += chunk_draws;
             }
             __syncthreads();
