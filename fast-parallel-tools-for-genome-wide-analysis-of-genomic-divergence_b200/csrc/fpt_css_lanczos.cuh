@@ -67,18 +67,27 @@ FPT_D FptLanczosSmem fpt_lanczos_carve(unsigned char *smem, int m, int wch) {
     return s;
 }
 
-/* y = B x for a symmetric m x m matrix in global memory: a warp per row, lanes across the row (coalesced), two rows in
-   flight per warp; x and y in shared memory */
+/* y = B x for a symmetric m x m matrix in global memory: a warp per row, lanes across the row (coalesced), four rows in
+   flight per warp and two column strides per trip so that enough loads are outstanding to cover the HBM latency;
+   x and y in shared memory */
 FPT_D void fpt_cta_symv(const double *__restrict__ B, int m, const double *x, double *y) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int i = 2 * warp; i < m; i += 2 * nwarp) {
+    for (int i = 4 * warp; i < m; i += 4 * nwarp) {
+        const int nr = m - i < 4 ? m - i : 4;
         const double *r0 = B + (size_t)i * m;
-        const bool two = i + 1 < m;
-        const double *r1 = two ? r0 + m : r0;
-        double s0 = 0.0, s1 = 0.0;
-        for (int j = lane; j < m; j += 32) { const double xv = x[j]; s0 += r0[j] * xv; s1 += r1[j] * xv; }
-        s0 = fpt_warp_sum(s0); s1 = fpt_warp_sum(s1);
-        if (lane == 0) { y[i] = s0; if (two) y[i + 1] = s1; }
+        const double *r1 = nr > 1 ? r0 + m : r0, *r2 = nr > 2 ? r0 + 2 * (size_t)m : r0, *r3 = nr > 3 ? r0 + 3 * (size_t)m : r0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int j = lane;
+        for (; j + 32 < m; j += 64) {
+            const double xa = x[j], xb = x[j + 32];
+            const double a0 = r0[j], a1 = r1[j], a2 = r2[j], a3 = r3[j];
+            const double b0 = r0[j + 32], b1 = r1[j + 32], b2 = r2[j + 32], b3 = r3[j + 32];
+            s0 += a0 * xa; s1 += a1 * xa; s2 += a2 * xa; s3 += a3 * xa;
+            s0 += b0 * xb; s1 += b1 * xb; s2 += b2 * xb; s3 += b3 * xb;
+        }
+        if (j < m) { const double xa = x[j]; s0 += r0[j] * xa; s1 += r1[j] * xa; s2 += r2[j] * xa; s3 += r3[j] * xa; }
+        s0 = fpt_warp_sum(s0); s1 = fpt_warp_sum(s1); s2 = fpt_warp_sum(s2); s3 = fpt_warp_sum(s3);
+        if (lane == 0) { y[i] = s0; if (nr > 1) y[i + 1] = s1; if (nr > 2) y[i + 2] = s2; if (nr > 3) y[i + 3] = s3; }
     }
 }
 
