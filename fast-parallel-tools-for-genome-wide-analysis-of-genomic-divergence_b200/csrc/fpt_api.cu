@@ -13,10 +13,13 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/fpt_b200.h"
@@ -911,12 +914,32 @@ static int population_size(const int *pos, int len) {
     return n;
 }
 
-/* reference layout -> one position per SNP (into pinned staging); verifies that A and B describe the same SNPs */
+/* reference layout -> one position per SNP (into pinned staging); verifies that A and B describe the same SNPs.
+   The reads are strided (one int per asize / bsize), i.e. one cache line per SNP and population: on a genome-sized call
+   this is ~128 bytes of host memory traffic per SNP, so it is split over a few threads to stay behind the DMA it overlaps. */
 static int gather_positions(const int *apos, const int *bpos, int asize, int bsize, long long nsnp, int32_t *pos) {
-    for (long long k = 0; k < nsnp; k++) {
-        const int pa = apos[k * asize];
-        if (pa != bpos[k * bsize]) return fail(FPT_ERR_POSITIONS, "SNP %lld: position %d in A but %d in B", k, pa, bpos[k * bsize]);
-        pos[k] = pa;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nt = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(8, hw ? hw : 1), nsnp / 32768));
+    std::vector<long long> bad((size_t)nt, -1);
+    auto work = [&](int t) {
+        const long long lo = nsnp * t / nt, hi = nsnp * (t + 1) / nt;
+        for (long long k = lo; k < hi; k++) {
+            const int pa = apos[k * asize];
+            if (pa != bpos[k * bsize]) { bad[(size_t)t] = k; return; }
+            pos[k] = pa;
+        }
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
+    }
+    for (int t = 0; t < nt; t++) {
+        const long long k = bad[(size_t)t];
+        if (k >= 0) return fail(FPT_ERR_POSITIONS, "SNP %lld: position %d in A but %d in B", k, apos[k * asize], bpos[k * bsize]);
     }
     return FPT_OK;
 }
@@ -953,17 +976,29 @@ static int dropin(int css, double *avals, double *bvals, int *apos, int *bpos, i
     g.avals = avals; g.bvals = bvals; g.nsnp = na;
     fpt_scan_range r = full_range(regend, wsize, wstep, semantics);
     if (r.window_end == 0) return FPT_OK;
+    static const bool trace = getenv("FPT_TRACE") != nullptr;     /* host-side phase times on stderr */
+    const auto t0 = std::chrono::steady_clock::now();
     HostStream hs;
     CHECK(hs.make());
     Arena ar(hs.st);
     DevGenotypes d;
     CHECK(upload_genotypes(ar, &g, &d));                   /* asynchronous when the caller's arrays are page-locked */
+    const auto t1 = std::chrono::steady_clock::now();
     void *hpos;
     CHECK(pinned_slot(c, 3, (size_t)na * sizeof(int32_t), &hpos));
     CHECK(gather_positions(apos, bpos, g.asize, g.bsize, na, (int32_t *)hpos));
     g.pos = (const int32_t *)hpos;
-    if (css) return css_scan_core(c, ar, &g, d, &r, treshold, runs, drosophila, mds, out0, out1, nullptr, nullptr);
-    return fet_scan_core(c, ar, &g, d, &r, perc, out0, out1, nullptr);
+    const auto t2 = std::chrono::steady_clock::now();
+    const int rc = css ? css_scan_core(c, ar, &g, d, &r, treshold, runs, drosophila, mds, out0, out1, nullptr, nullptr)
+                       : fet_scan_core(c, ar, &g, d, &r, perc, out0, out1, nullptr);
+    if (trace) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[fpt] %s drop-in: enqueue upload %.3f ms, gather positions %.3f ms, scan %.3f ms\n", css ? "css" : "fet",
+                ms(t0, t1), ms(t1, t2), ms(t2, t3));
+    }
+    return rc;
 }
 
 static int fet_dropin(double *avals, double *bvals, int *apos, int *bpos, int regend, int wsize, int wstep, int alen,
