@@ -155,6 +155,15 @@ FPT_D int fpt_css_dissimilarity(const unsigned *__restrict__ planes, const doubl
     return fpt_css_fill(D, m, sc);
 }
 
+struct FptJacobiScratch {
+    double *rmean;   /* m */
+    double *rc;      /* ceil(m/2)+1 rotation cosines */
+    double *rs;      /* sines */
+    int *rp, *rq;    /* pair indices */
+};
+
+#ifdef FPT_EMU   /* the library launches fpt_css_eig.cuh / fpt_css_lanczos.cuh instead; this dense Jacobi solver is kept for the
+                    CPU-emulator tests as an independent third eigen-solver (tests/test_emu_kernels.py) */
 /* ============================================================================================
  * Classical MDS. B = -1/2 Z (D.D) Z, Z = I - 11'/m, written in its closed double-centred form
  * b_ij = -1/2 (s_ij - r_i - r_j + g) (the reference forms the same matrix with two dgemm calls);
@@ -163,12 +172,6 @@ FPT_D int fpt_css_dissimilarity(const unsigned *__restrict__ planes, const doubl
  * with no guard against negative ones (css.c:543-558: sqrt gives NaN, as in the reference).
  * A holds D on entry and is destroyed; V receives the eigenvectors (columns).
  */
-struct FptJacobiScratch {
-    double *rmean;   /* m */
-    double *rc;      /* ceil(m/2)+1 rotation cosines */
-    double *rs;      /* sines */
-    int *rp, *rq;    /* pair indices */
-};
 
 FPT_D void fpt_css_cmds(double *A, double *V, int m, double *X, double *evals3, const FptJacobiScratch &js,
                         const FptCssScratch &sc) {
@@ -284,6 +287,8 @@ FPT_D void fpt_css_cmds(double *A, double *V, int m, double *X, double *evals3, 
     __syncthreads();
 }
 
+#endif
+
 /* dynamic shared memory carve-up shared by the window kernels */
 struct FptCssSmem {
     double *M0, *M1;          /* two m x m matrices (or global scratch when m is too large) */
@@ -326,6 +331,7 @@ FPT_HD size_t fpt_css_smem_bytes(int m, int wch, int mats_in_smem) {
     return off + (size_t)wch * 2 * m * 4;
 }
 
+#ifdef FPT_EMU
 /* mds 0 and the first half of mds 2: one CTA walks windows blockIdx.x, +gridDim.x, ... */
 __global__ void __launch_bounds__(128)
 fpt_css_mds_kernel(const unsigned *__restrict__ planes, const double *__restrict__ absdiff, int m,
@@ -345,6 +351,8 @@ fpt_css_mds_kernel(const unsigned *__restrict__ planes, const double *__restrict
         __syncthreads();
     }
 }
+
+#endif
 
 /* ============================================================================================
  * SMACOF (css.c:907-938). Per iteration, the reference's sequence: B(Z) from the current distances
