@@ -665,22 +665,86 @@ static int check_genotypes(const fpt_genotypes *g) {
 /* copy both populations to the device in the layout the caller has them */
 struct DevGenotypes { const double *a64 = nullptr, *b64 = nullptr; const signed char *a8 = nullptr, *b8 = nullptr; };
 
-static int upload_genotypes(Arena &ar, const fpt_genotypes *g, DevGenotypes *d) {
-    const size_t na = (size_t)g->nsnp * g->asize, nb = (size_t)g->nsnp * g->bsize;
-    if (g->avals) {
-        double *a, *b;
-        CHECK(ar.get(&a, na)); CHECK(ar.get(&b, nb));
-        CU(cudaMemcpyAsync(a, g->avals, na * sizeof(double), cudaMemcpyHostToDevice, ar.st));
-        CU(cudaMemcpyAsync(b, g->bvals, nb * sizeof(double), cudaMemcpyHostToDevice, ar.st));
-        d->a64 = a; d->b64 = b;
-    } else {
-        signed char *a, *b;
-        CHECK(ar.get(&a, na)); CHECK(ar.get(&b, nb));
-        CU(cudaMemcpyAsync(a, g->acodes, na, cudaMemcpyHostToDevice, ar.st));
-        CU(cudaMemcpyAsync(b, g->bcodes, nb, cudaMemcpyHostToDevice, ar.st));
-        d->a8 = a; d->b8 = b;
+/* The genotype upload is cut into SNP chunks on a copy stream of its own, one event per chunk, so that the per-SNP
+   kernels (counting / packing) and every window whose SNPs have all arrived can run while later chunks are still on the
+   bus. Chunk boundaries are multiples of 4096 SNPs (whole bit-plane words, whole staging tiles). */
+#define FPT_MAX_CHUNKS 8
+#define FPT_CHUNK_BYTES_FET ((size_t)16 << 20)    /* the copy dominates a FET scan: many chunks, windows released early */
+#define FPT_CHUNK_BYTES_CSS ((size_t)96 << 20)    /* compute dominates a CSS scan: sub-range launches cost more in tails than the
+                                                     copy they hide until the input is several hundred MB */
+struct UploadPlan {
+    int n = 0;                                   /* chunks */
+    int queued = 0;                              /* chunks already handed to the copy stream */
+    long long snp_end[FPT_MAX_CHUNKS];           /* exclusive end of chunk c */
+    cudaEvent_t ev[FPT_MAX_CHUNKS];
+    cudaStream_t cs = nullptr;
+    char *da = nullptr, *db = nullptr;           /* device arrays */
+    const char *ha = nullptr, *hb = nullptr;     /* host arrays */
+    size_t rowa = 0, rowb = 0;                   /* bytes per SNP */
+    ~UploadPlan() {
+        if (cs) cudaStreamSynchronize(cs);       /* error paths: no copy may outlive the buffers it writes */
+        for (int c = 0; c < n; c++) cudaEventDestroy(ev[c]);
+        if (cs) cudaStreamDestroy(cs);
+    }
+};
+
+/* hand chunks [queued, upto) to the copy stream */
+static int upload_enqueue(UploadPlan *p, int upto) {
+    for (; p->queued < upto && p->queued < p->n; p->queued++) {
+        const long long s0 = p->queued ? p->snp_end[p->queued - 1] : 0, s1 = p->snp_end[p->queued];
+        CU(cudaMemcpyAsync(p->da + (size_t)s0 * p->rowa, p->ha + (size_t)s0 * p->rowa, (size_t)(s1 - s0) * p->rowa, cudaMemcpyHostToDevice, p->cs));
+        CU(cudaMemcpyAsync(p->db + (size_t)s0 * p->rowb, p->hb + (size_t)s0 * p->rowb, (size_t)(s1 - s0) * p->rowb, cudaMemcpyHostToDevice, p->cs));
+        CU(cudaEventRecord(p->ev[p->queued], p->cs));
     }
     return FPT_OK;
+}
+
+/* Allocates the device arrays, lays out the chunks and starts the first quarter of them. The caller enqueues whatever small
+   host->device copies the scan needs early (positions) and then calls upload_enqueue(plan, plan->n): copies are served in
+   enqueue order by the DMA engine, so anything enqueued after the last chunk would wait for the whole genome. */
+static int upload_genotypes(Arena &ar, const fpt_genotypes *g, DevGenotypes *d, UploadPlan *plan, size_t chunk_bytes) {
+    const size_t na = (size_t)g->nsnp * g->asize, nb = (size_t)g->nsnp * g->bsize;
+    const size_t esz = g->avals ? sizeof(double) : 1;
+    if (g->avals) { double *pa, *pb; CHECK(ar.get(&pa, na)); CHECK(ar.get(&pb, nb)); plan->da = (char *)pa; plan->db = (char *)pb; d->a64 = pa; d->b64 = pb; }
+    else { signed char *pa, *pb; CHECK(ar.get(&pa, na)); CHECK(ar.get(&pb, nb)); plan->da = (char *)pa; plan->db = (char *)pb; d->a8 = pa; d->b8 = pb; }
+    plan->ha = g->avals ? (const char *)g->avals : (const char *)g->acodes;
+    plan->hb = g->avals ? (const char *)g->bvals : (const char *)g->bcodes;
+    plan->rowa = (size_t)g->asize * esz; plan->rowb = (size_t)g->bsize * esz;
+    /* one chunk per `chunk_bytes` (FPT_UPLOAD_CHUNK_BYTES overrides: tests use it to cut small inputs), at most FPT_MAX_CHUNKS */
+    const size_t bytes = (na + nb) * esz;
+    if (const char *e = getenv("FPT_UPLOAD_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) chunk_bytes = (size_t)v; }
+    const int want = (int)std::min<size_t>(FPT_MAX_CHUNKS, std::max<size_t>(1, bytes / chunk_bytes));
+    long long per = ((g->nsnp + want - 1) / want + 4095) & ~4095LL;
+    if (per <= 0) per = 4096;
+    CU(cudaStreamCreateWithFlags(&plan->cs, cudaStreamNonBlocking));
+    cudaEvent_t ready;                           /* the copy stream starts once the stream-ordered allocations exist */
+    CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CU(cudaEventRecord(ready, ar.st));
+    CU(cudaStreamWaitEvent(plan->cs, ready, 0));
+    CU(cudaEventDestroy(ready));
+    for (long long s0 = 0; s0 < g->nsnp && plan->n < FPT_MAX_CHUNKS;) {
+        const long long s1 = (plan->n == FPT_MAX_CHUNKS - 1) ? g->nsnp : std::min<long long>(g->nsnp, s0 + per);
+        CU(cudaEventCreateWithFlags(&plan->ev[plan->n], cudaEventDisableTiming));
+        plan->snp_end[plan->n++] = s1;
+        s0 = s1;
+    }
+    return upload_enqueue(plan, (plan->n + 3) / 4);       /* a quarter now: the DMA stays busy while the host prepares the rest */
+}
+
+/* positions ascending? (the windows-as-they-arrive schedule needs it; unsorted input falls back to one pass at the end) */
+static bool positions_sorted(const int32_t *pos, long long n) {
+    for (long long k = 1; k < n; k++) if (pos[k] < pos[k - 1]) return false;
+    return true;
+}
+
+/* windows [0, returned) of the range have every SNP among the first `s1` ones (positions ascending): window gw covers
+   positions <= gw*wstep + wsize (fpt_window_table_kernel), so it is complete iff that is below pos[s1] */
+static long long windows_complete(const fpt_genotypes *g, const fpt_scan_range *r, long long nwin, long long s1) {
+    if (s1 >= g->nsnp) return nwin;
+    const long long lim = (long long)g->pos[s1] - r->wsize - 1;
+    if (lim < 0) return 0;
+    const long long gw_excl = lim / r->wstep + 1;
+    return std::max<long long>(0, std::min<long long>(nwin, gw_excl - r->window_begin));
 }
 
 struct HostStream {
@@ -698,7 +762,10 @@ extern "C" int fpt_fet_per_snp(const fpt_genotypes *g, int32_t *tables, double *
     CHECK(hs.make());
     Arena ar(hs.st);
     DevGenotypes d;
-    CHECK(upload_genotypes(ar, g, &d));
+    UploadPlan plan;
+    CHECK(upload_genotypes(ar, g, &d, &plan, FPT_CHUNK_BYTES_FET));
+    CHECK(upload_enqueue(&plan, plan.n));
+    CU(cudaStreamWaitEvent(hs.st, plan.ev[plan.n - 1], 0));
     int32_t *d_tab; double *d_sc;
     CHECK(ar.get(&d_tab, (size_t)g->nsnp * 4));
     CHECK(ar.get(&d_sc, (size_t)g->nsnp));
@@ -751,9 +818,10 @@ static int scan_front(Arena &ar, const fpt_genotypes *g, const fpt_scan_range *r
     return FPT_OK;
 }
 
-/* everything after the genotype upload has been enqueued on ar.st */
-static int fet_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const DevGenotypes &d, const fpt_scan_range *r,
-                         double perc, double *scores, double *stddev, uint8_t *written) {
+/* The genotype upload is in flight on plan.cs. Per chunk: wait for it, count + score its SNPs, then run every window whose
+   SNPs have all arrived (positions ascending; otherwise all windows after the last chunk). */
+static int fet_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const DevGenotypes &d, UploadPlan &plan,
+                         const fpt_scan_range *r, double perc, double *scores, double *stddev, uint8_t *written) {
     cudaStream_t st = ar.st;
     long long nwin;
     CHECK(check_range(r, &nwin));
@@ -768,13 +836,31 @@ static int fet_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const 
         CHECK(ar.get(&d_states, (size_t)nwin));
         CU(cudaMemcpyAsync(d_states, r->states_resample, (size_t)nwin * 8, cudaMemcpyHostToDevice, st));
     }
+    /* the small host->device copies above (positions, stream states) are now ahead of the remaining chunks in the DMA queue */
+    CHECK(upload_enqueue(&plan, plan.n));
     CU(cudaMemsetAsync(d_fl, 0, (size_t)nwin, st));
-    if (d.a64) CHECK(fpt_dev_fet_count_f64(d.a64, d.b64, g->nsnp, g->asize, g->bsize, d_tab, st));
-    else CHECK(fpt_dev_fet_count_i8((const int8_t *)d.a8, (const int8_t *)d.b8, g->nsnp, g->asize, g->bsize, d_tab, st));
-    CHECK(fpt_dev_fet_score(d_tab, g->nsnp, g->asize + g->bsize, 0, d_snp, st));
     CU(cudaMemcpyAsync(&f.max_npos, f.d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    CHECK(fpt_dev_fet_windows(d_snp, f.d_wl, f.d_wr, r, f.max_npos, perc, d_states, d_sc, d_sd, d_fl, st));
+    CU(cudaStreamSynchronize(st));                          /* positions and window table only: the genotypes are on plan.cs */
+    const bool stream_windows = plan.n > 1 && positions_sorted(g->pos, g->nsnp);
+    long long wdone = 0, s0 = 0;
+    for (int k = 0; k < plan.n; k++) {
+        const long long s1 = plan.snp_end[k];
+        CU(cudaStreamWaitEvent(st, plan.ev[k], 0));
+        if (d.a64) CHECK(fpt_dev_fet_count_f64(d.a64 + (size_t)s0 * g->asize, d.b64 + (size_t)s0 * g->bsize, s1 - s0, g->asize, g->bsize, d_tab + 4 * s0, st));
+        else CHECK(fpt_dev_fet_count_i8((const int8_t *)d.a8 + (size_t)s0 * g->asize, (const int8_t *)d.b8 + (size_t)s0 * g->bsize, s1 - s0, g->asize,
+                                        g->bsize, d_tab + 4 * s0, st));
+        CHECK(fpt_dev_fet_score(d_tab + 4 * s0, s1 - s0, g->asize + g->bsize, 0, d_snp + s0, st));
+        const long long wav = (k == plan.n - 1) ? nwin : (stream_windows ? windows_complete(g, r, nwin, s1) : 0);
+        if (wav > wdone) {
+            fpt_scan_range sub = *r;
+            sub.window_begin = r->window_begin + wdone;
+            sub.window_end = r->window_begin + wav;
+            CHECK(fpt_dev_fet_windows(d_snp, f.d_wl + wdone, f.d_wr + wdone, &sub, f.max_npos, perc, d_states ? d_states + wdone : nullptr,
+                                      d_sc + wdone, d_sd + wdone, d_fl + wdone, st));
+            wdone = wav;
+        }
+        s0 = s1;
+    }
     void *h0, *h1, *h2;
     CHECK(pinned_slot(c, 0, (size_t)nwin * 8, &h0)); CHECK(pinned_slot(c, 1, (size_t)nwin * 8, &h1));
     CHECK(pinned_slot(c, 2, (size_t)nwin, &h2));
@@ -803,13 +889,14 @@ extern "C" int fpt_fet_scan(const fpt_genotypes *g, const fpt_scan_range *r, dou
     CHECK(hs.make());
     Arena ar(hs.st);
     DevGenotypes d;
-    CHECK(upload_genotypes(ar, g, &d));
-    return fet_scan_core(c, ar, g, d, r, perc, scores, stddev, written);
+    UploadPlan plan;
+    CHECK(upload_genotypes(ar, g, &d, &plan, FPT_CHUNK_BYTES_FET));
+    return fet_scan_core(c, ar, g, d, plan, r, perc, scores, stddev, written);
 }
 
-static int css_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const DevGenotypes &d, const fpt_scan_range *r,
-                         int treshold, int runs, int drosophila, int mds, double *scores, double *p, uint8_t *written,
-                         const fpt_css_probes *probes) {
+static int css_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const DevGenotypes &d, UploadPlan &plan,
+                         const fpt_scan_range *r, int treshold, int runs, int drosophila, int mds, double *scores, double *p,
+                         uint8_t *written, const fpt_css_probes *probes) {
     cudaStream_t st = ar.st;
     long long nwin;
     CHECK(check_range(r, &nwin));
@@ -817,25 +904,17 @@ static int css_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const 
     ScanFront f;
     CHECK(scan_front(ar, g, r, &f));
     uint32_t *d_planes = nullptr; double *d_abs = nullptr;
-    if (drosophila) {
-        CHECK(ar.get(&d_abs, (size_t)g->nsnp));
-        CHECK(fpt_dev_css_absdiff(d.a64, d.b64, g->nsnp, d_abs, st));
-    } else {
-        CHECK(ar.get(&d_planes, fpt_dev_css_planes_bytes(g->nsnp, m) / 4));
-        if (d.a64) CHECK(fpt_dev_css_pack_f64(d.a64, d.b64, g->nsnp, g->asize, g->bsize, d_planes, st));
-        else CHECK(fpt_dev_css_pack_i8((const int8_t *)d.a8, (const int8_t *)d.b8, g->nsnp, g->asize, g->bsize, d_planes, st));
-    }
+    if (drosophila) CHECK(ar.get(&d_abs, (size_t)g->nsnp));
+    else CHECK(ar.get(&d_planes, fpt_dev_css_planes_bytes(g->nsnp, m) / 4));
     const int nruns = mds == 1 ? 4 : (mds == 2 ? 1 : 0);
     size_t ws_bytes = fpt_dev_css_workspace_bytes(m, nwin, mds);
     unsigned char *d_ws; double *d_sc, *d_p; uint8_t *d_st;
     CHECK(ar.get(&d_ws, ws_bytes));
     CHECK(ar.get(&d_sc, (size_t)nwin)); CHECK(ar.get(&d_p, (size_t)nwin)); CHECK(ar.get(&d_st, (size_t)nwin));
     CU(cudaMemsetAsync(d_st, 0, (size_t)nwin, st));
-    fpt_scan_range rd = *r;
     uint64_t *d_s0 = nullptr, *d_s1 = nullptr;
     if (r->states_resample) { CHECK(ar.get(&d_s0, (size_t)nwin)); CU(cudaMemcpyAsync(d_s0, r->states_resample, (size_t)nwin * 8, cudaMemcpyHostToDevice, st)); }
     if (r->states_init) { CHECK(ar.get(&d_s1, (size_t)nwin)); CU(cudaMemcpyAsync(d_s1, r->states_init, (size_t)nwin * 8, cudaMemcpyHostToDevice, st)); }
-    rd.states_resample = d_s0; rd.states_init = d_s1;
     fpt_css_probes dp;
     memset(&dp, 0, sizeof dp);
     if (probes) {
@@ -849,8 +928,42 @@ static int css_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const 
         if (dp.nperm) CU(cudaMemsetAsync(dp.nperm, 0, (size_t)nwin * 4, st));
         if (dp.X) CU(cudaMemsetAsync(dp.X, 0, (size_t)nwin * 2 * m * 8, st));
     }
-    CHECK(fpt_dev_css_windows(d_planes, d_abs, g->asize, g->bsize, f.d_wl, f.d_wr, &rd, treshold, runs, mds, d_ws, ws_bytes,
-                              d_sc, d_p, d_st, probes ? &dp : nullptr, st));
+    /* the small host->device copies above (positions, stream states) are now ahead of the remaining chunks in the DMA queue */
+    CHECK(upload_enqueue(&plan, plan.n));
+    /* per upload chunk: pack its SNPs, then score every window whose SNPs have all arrived (see fet_scan_core) */
+    const bool stream_windows = plan.n > 1 && positions_sorted(g->pos, g->nsnp);
+    long long wdone = 0, s0 = 0;
+    for (int k = 0; k < plan.n; k++) {
+        const long long s1 = plan.snp_end[k];
+        CU(cudaStreamWaitEvent(st, plan.ev[k], 0));
+        if (drosophila) CHECK(fpt_dev_css_absdiff(d.a64 + s0, d.b64 + s0, s1 - s0, d_abs + s0, st));
+        else {
+            uint32_t *pl = d_planes + (size_t)(s0 / 32) * 2 * m;        /* chunk starts are multiples of 32 SNPs */
+            if (d.a64) CHECK(fpt_dev_css_pack_f64(d.a64 + (size_t)s0 * g->asize, d.b64 + (size_t)s0 * g->bsize, s1 - s0, g->asize, g->bsize, pl, st));
+            else CHECK(fpt_dev_css_pack_i8((const int8_t *)d.a8 + (size_t)s0 * g->asize, (const int8_t *)d.b8 + (size_t)s0 * g->bsize, s1 - s0, g->asize,
+                                           g->bsize, pl, st));
+        }
+        const long long wav = (k == plan.n - 1) ? nwin : (stream_windows ? windows_complete(g, r, nwin, s1) : 0);
+        if (wav > wdone) {
+            const long long nw = wav - wdone;
+            fpt_scan_range sub = *r;
+            sub.window_begin = r->window_begin + wdone;
+            sub.window_end = r->window_begin + wav;
+            sub.states_resample = d_s0 ? d_s0 + wdone : nullptr;
+            sub.states_init = d_s1 ? d_s1 + wdone : nullptr;
+            fpt_css_probes dq = dp;
+            if (dq.X) dq.X += (size_t)wdone * 2 * m;
+            if (dq.evals) dq.evals += (size_t)wdone * 3;
+            if (dq.hits) dq.hits += wdone;
+            if (dq.nperm) dq.nperm += wdone;
+            if (dq.smacof_iters) dq.smacof_iters += (size_t)wdone * nruns;
+            if (dq.smacof_sigma) dq.smacof_sigma += (size_t)wdone * nruns;
+            CHECK(fpt_dev_css_windows(d_planes, d_abs, g->asize, g->bsize, f.d_wl + wdone, f.d_wr + wdone, &sub, treshold, runs, mds, d_ws,
+                                      fpt_dev_css_workspace_bytes(m, nw, mds), d_sc + wdone, d_p + wdone, d_st + wdone, probes ? &dq : nullptr, st));
+            wdone = wav;
+        }
+        s0 = s1;
+    }
     double *h_sc, *h_p; uint8_t *h_st;
     void *h0, *h1, *h2;
     CHECK(pinned_slot(c, 0, (size_t)nwin * 8, &h0)); CHECK(pinned_slot(c, 1, (size_t)nwin * 8, &h1));
@@ -901,8 +1014,9 @@ extern "C" int fpt_css_scan(const fpt_genotypes *g, const fpt_scan_range *r, int
     CHECK(hs.make());
     Arena ar(hs.st);
     DevGenotypes d;
-    CHECK(upload_genotypes(ar, g, &d));
-    return css_scan_core(c, ar, g, d, r, treshold, runs, drosophila, mds, scores, p, written, probes);
+    UploadPlan plan;
+    CHECK(upload_genotypes(ar, g, &d, &plan, FPT_CHUNK_BYTES_CSS));
+    return css_scan_core(c, ar, g, d, plan, r, treshold, runs, drosophila, mds, scores, p, written, probes);
 }
 
 /* ------------------------------------------------------------------------------------------------ drop-ins */
@@ -982,15 +1096,16 @@ static int dropin(int css, double *avals, double *bvals, int *apos, int *bpos, i
     CHECK(hs.make());
     Arena ar(hs.st);
     DevGenotypes d;
-    CHECK(upload_genotypes(ar, &g, &d));                   /* asynchronous when the caller's arrays are page-locked */
+    UploadPlan plan;
+    CHECK(upload_genotypes(ar, &g, &d, &plan, css ? FPT_CHUNK_BYTES_CSS : FPT_CHUNK_BYTES_FET));            /* asynchronous when the caller's arrays are page-locked */
     const auto t1 = std::chrono::steady_clock::now();
     void *hpos;
     CHECK(pinned_slot(c, 3, (size_t)na * sizeof(int32_t), &hpos));
     CHECK(gather_positions(apos, bpos, g.asize, g.bsize, na, (int32_t *)hpos));
     g.pos = (const int32_t *)hpos;
     const auto t2 = std::chrono::steady_clock::now();
-    const int rc = css ? css_scan_core(c, ar, &g, d, &r, treshold, runs, drosophila, mds, out0, out1, nullptr, nullptr)
-                       : fet_scan_core(c, ar, &g, d, &r, perc, out0, out1, nullptr);
+    const int rc = css ? css_scan_core(c, ar, &g, d, plan, &r, treshold, runs, drosophila, mds, out0, out1, nullptr, nullptr)
+                       : fet_scan_core(c, ar, &g, d, plan, &r, perc, out0, out1, nullptr);
     if (trace) {
         const auto t3 = std::chrono::steady_clock::now();
         auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {

@@ -382,3 +382,33 @@ def test_pipeline_vcf_to_region_calls(fpt, oracle):
             == results.significant_css_regions_file("".join(want_css), 2500, lens, num_top=10))
     assert (results.filter_fisher_scores_file(fet_text, 2500, lens, 0.95, 75.0)
             == results.filter_fisher_scores_file("".join(want_fet), 2500, lens, 0.95, 75.0))
+
+
+# ------------------------------------------------------------------------------------------------ chunked upload
+@pytest.mark.parametrize("semantics", [0, 1])
+def test_scans_with_chunked_upload_match_single_pass(fpt, oracle, monkeypatch, semantics):
+    """the host entry points cut the genotype upload into chunks and score windows as their SNPs arrive; forced here on
+    a small input (8 chunks of 4096 SNPs) and compared with the single-pass result and the oracle, both layouts"""
+    asize, bsize, regend, wsize, wstep, nsnp = 9, 8, 900000, 2500, 500, 30000
+    ch, (av, bv, apos, bpos) = _synth(321, regend, nsnp, asize, bsize)
+    n = regend // wstep
+    res = {}
+    for tag, chunk in (("one", None), ("many", "4096")):
+        if chunk is None:
+            monkeypatch.delenv("FPT_UPLOAD_CHUNK_BYTES", raising=False)
+        else:
+            monkeypatch.setenv("FPT_UPLOAD_CHUNK_BYTES", chunk)
+        f64 = fpt.fet_scan(av, bv, ch["pos"], asize, bsize, regend, wsize, wstep, 0.95, semantics=semantics, seed=77)
+        i8 = fpt.fet_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 0.95, semantics=semantics, seed=77)
+        css = fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 5, 60, mds=0, semantics=semantics, seed=77)
+        res[tag] = (f64, i8, css)
+    for a, b in zip(res["one"], res["many"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    s_o, d_o = np.zeros(n), np.zeros(n)
+    oracle.fpt_oracle_fet_scan(dptr(av), dptr(bv), iptr(apos), iptr(bpos), 0, regend, wsize, wstep, av.size, bv.size, 0.95, dptr(s_o), dptr(d_o),
+                               semantics, 77)
+    s_g, d_g, wr = res["many"][0]
+    assert np.array_equal(wr == 1, s_o != 0) and (wr == 1).sum() > 1000
+    np.testing.assert_allclose(s_g, s_o, rtol=FET_RTOL, atol=1e-13)
+    np.testing.assert_allclose(d_g, d_o, rtol=1e-9, atol=1e-12)
