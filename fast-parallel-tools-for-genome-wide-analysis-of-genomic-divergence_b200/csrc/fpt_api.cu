@@ -72,6 +72,7 @@ struct DeviceCtx {
 };
 static DeviceCtx g_ctx[64];
 static std::mutex g_mu;
+static std::mutex g_host_mu[64];         /* host entry points that use a device's staging buffers run one at a time */
 
 static int get_ctx(DeviceCtx **out) {
     int n = 0;
@@ -126,7 +127,8 @@ static int ensure_lf(DeviceCtx *c, int maxn) {
 }
 
 /* page-locked staging buffers are expensive to create (cudaMallocHost pins pages), so the host entry points keep a few
-   per device and only ever grow them; host entry points are not re-entrant per device (neither is the reference) */
+   per device and only ever grow them; the host entry points that use them hold g_host_mu[device] for the whole call, so
+   concurrent callers serialise per device (the reference's own entry points share global state and are not re-entrant) */
 static int pinned_slot(DeviceCtx *c, int slot, size_t bytes, void **out) {
     if (bytes > c->pinned_bytes[slot]) {
         if (c->pinned[slot]) cudaFreeHost(c->pinned[slot]);
@@ -889,6 +891,7 @@ extern "C" int fpt_fet_scan(const fpt_genotypes *g, const fpt_scan_range *r, dou
     CHECK(check_range(r, &nwin));
     if (nwin == 0 || g->nsnp == 0) return FPT_OK;
     if (!g->pos || !scores || !stddev) return fail(FPT_ERR_ARG, "fet_scan: positions and both outputs are required");
+    std::lock_guard<std::mutex> host_lock(g_host_mu[c->device]);
     HostStream hs;
     CHECK(hs.make());
     Arena ar(hs.st);
@@ -1014,6 +1017,7 @@ extern "C" int fpt_css_scan(const fpt_genotypes *g, const fpt_scan_range *r, int
     if (mds < 0 || mds > 2) return fail(FPT_ERR_ARG, "css: mds must be 0, 1 or 2 (got %d)", mds);
     if (nwin == 0 || g->nsnp == 0) return FPT_OK;
     if (!g->pos || !scores || !p) return fail(FPT_ERR_ARG, "css_scan: positions and both outputs are required");
+    std::lock_guard<std::mutex> host_lock(g_host_mu[c->device]);
     HostStream hs;
     CHECK(hs.make());
     Arena ar(hs.st);
@@ -1094,6 +1098,7 @@ static int dropin(int css, double *avals, double *bvals, int *apos, int *bpos, i
     g.avals = avals; g.bvals = bvals; g.nsnp = na;
     fpt_scan_range r = full_range(regend, wsize, wstep, semantics);
     if (r.window_end == 0) return FPT_OK;
+    std::lock_guard<std::mutex> host_lock(g_host_mu[c->device]);
     static const bool trace = getenv("FPT_TRACE") != nullptr;     /* host-side phase times on stderr */
     const auto t0 = std::chrono::steady_clock::now();
     HostStream hs;

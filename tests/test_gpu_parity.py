@@ -412,3 +412,31 @@ def test_scans_with_chunked_upload_match_single_pass(fpt, oracle, monkeypatch, s
     assert np.array_equal(wr == 1, s_o != 0) and (wr == 1).sum() > 1000
     np.testing.assert_allclose(s_g, s_o, rtol=FET_RTOL, atol=1e-13)
     np.testing.assert_allclose(d_g, d_o, rtol=1e-9, atol=1e-12)
+
+
+def test_concurrent_host_calls_serialise(fpt):
+    """two Python threads (ctypes drops the GIL) scanning at once: the host entry points share per-device staging buffers and
+    must therefore take turns; results equal the ones of back-to-back calls"""
+    import threading
+    asize, bsize, regend, wsize, wstep, nsnp = 8, 8, 400000, 2500, 500, 12000
+    ch, _ = _synth(55, regend, nsnp, asize, bsize)
+    ch2, _ = _synth(56, regend, nsnp, asize, bsize)
+    want = [fpt.fet_scan(c["acodes"], c["bcodes"], c["pos"], asize, bsize, regend, wsize, wstep, 0.95, seed=3) for c in (ch, ch2)]
+    want_css = fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 10, 100, seed=3)
+    got = {}
+
+    def run(tag, fn):
+        got[tag] = [fn() for _ in range(6)]
+
+    th = [threading.Thread(target=run, args=("a", lambda: fpt.fet_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 0.95, seed=3))),
+          threading.Thread(target=run, args=("b", lambda: fpt.fet_scan(ch2["acodes"], ch2["bcodes"], ch2["pos"], asize, bsize, regend, wsize, wstep, 0.95, seed=3))),
+          threading.Thread(target=run, args=("c", lambda: fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 10, 100, seed=3)))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for tag, w in (("a", want[0]), ("b", want[1]), ("c", want_css)):
+        assert len(got[tag]) == 6
+        for res in got[tag]:
+            for x, y in zip(res, w):
+                assert np.array_equal(x, y)
