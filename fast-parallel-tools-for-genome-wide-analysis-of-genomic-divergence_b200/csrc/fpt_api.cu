@@ -937,8 +937,10 @@ static int css_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const 
     }
     /* the small host->device copies above (positions, stream states) are now ahead of the remaining chunks in the DMA queue */
     CHECK(upload_enqueue(&plan, plan.n));
-    /* per upload chunk: pack its SNPs, then score every window whose SNPs have all arrived (see fet_scan_core) */
-    const bool stream_windows = plan.n > 1 && positions_sorted(g->pos, g->nsnp);
+    /* per upload chunk: pack its SNPs, then score every window whose SNPs have all arrived (see fet_scan_core). Only where
+       a sub-range still fills the GPU many times over: the CTA-per-window kernels of large cohorts run a few hundred windows
+       at a time, and a short extra launch costs them a whole wave. */
+    const bool stream_windows = plan.n > 1 && nwin >= 8192 && css_plan(c, m).mds_warps > 0 && positions_sorted(g->pos, g->nsnp);
     long long wdone = 0, s0 = 0;
     for (int k = 0; k < plan.n; k++) {
         const long long s1 = plan.snp_end[k];
