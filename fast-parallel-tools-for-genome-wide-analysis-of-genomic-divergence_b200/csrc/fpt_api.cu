@@ -1043,7 +1043,7 @@ static int population_size(const int *pos, int len) {
    this is ~128 bytes of host memory traffic per SNP, so it is split over a few threads to stay behind the DMA it overlaps. */
 static int gather_positions(const int *apos, const int *bpos, int asize, int bsize, long long nsnp, int32_t *pos) {
     const unsigned hw = std::thread::hardware_concurrency();
-    const int nt = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(8, hw ? hw : 1), nsnp / 32768));
+    const int nt = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(12, hw ? hw : 1), nsnp / 16384));
     std::vector<long long> bad((size_t)nt, -1);
     auto work = [&](int t) {
         const long long lo = nsnp * t / nt, hi = nsnp * (t + 1) / nt;

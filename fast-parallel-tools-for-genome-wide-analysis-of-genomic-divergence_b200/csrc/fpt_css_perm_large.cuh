@@ -104,14 +104,23 @@ FPT_D double fpt_css_score_identity(const double *dist, int m, int asize, int bs
     } else {
         for (int ihi = asize - 1; ihi >= 0; ihi -= rows_per_tile) {
             const int ilo = ihi - rows_per_tile + 1 > 0 ? ihi - rows_per_tile + 1 : 0, nr = ihi - ilo + 1;
-            for (int r = 0; r < nr; r++) {
-                const double *src = dist + (size_t)(ilo + r) * m + asize;
-                double *dst = buf + (size_t)r * bsize;
-                for (int j = tid; j < bsize; j += T) dst[j] = src[j];
+            for (int e = tid; e < nr * bsize; e += T) {         /* one flat sweep: many loads in flight per thread */
+                const int r = e / bsize, j = e - r * bsize;
+                buf[e] = dist[(size_t)(ilo + r) * m + asize + j];
             }
             __syncthreads();
-            if (tid == 0) {
-                for (int r = nr; r--;) { const double *row = buf + (size_t)r * bsize; for (int j = bsize; j--;) bet = __dadd_rn(bet, row[j]); }
+            if (tid == 0) {                                   /* loads run ahead, the additions stay one chain in order */
+                for (int r = nr; r--;) {
+                    const double *row = buf + (size_t)r * bsize;
+                    int j = bsize;
+                    for (; j >= 8; j -= 8) {
+                        const double x7 = row[j - 1], x6 = row[j - 2], x5 = row[j - 3], x4 = row[j - 4];
+                        const double x3 = row[j - 5], x2 = row[j - 6], x1 = row[j - 7], x0 = row[j - 8];
+                        bet = __dadd_rn(bet, x7); bet = __dadd_rn(bet, x6); bet = __dadd_rn(bet, x5); bet = __dadd_rn(bet, x4);
+                        bet = __dadd_rn(bet, x3); bet = __dadd_rn(bet, x2); bet = __dadd_rn(bet, x1); bet = __dadd_rn(bet, x0);
+                    }
+                    for (; j--;) bet = __dadd_rn(bet, row[j]);
+                }
             }
             __syncthreads();
         }
@@ -159,6 +168,36 @@ FPT_HD size_t fpt_css_perm_smem_bytes(int m, int nthreads, int track_bytes, int 
     off = (off + 15) & ~(size_t)15;
     off += (size_t)(m + 1) * 8;                                 /* per-n (limit, magic) of the shuffle draws */
     return off;
+}
+
+/* Fisher-Yates of fresh identity labels into `row` (shared or global memory), css.c:700-706. Optimistic first: a draw is
+   rejected with probability < n / 2^31, so the loop only remembers whether one was and the permutation is replayed exactly
+   (counting the draws) when it happened. `st` is the stream state at the permutation's first draw; returns the draws used. */
+template <typename TrackT>
+FPT_D int fpt_generate_labels(TrackT *row, int m, const uint2 *rtab, uint64_t st) {
+    for (int e = 0; e < m; e++) row[e] = (TrackT)e;
+    uint64_t s2 = st;
+    uint32_t over = 0u;
+    for (int i = m - 1; i > 0; i--) {
+        const uint2 lm = rtab[i + 1];
+        const uint32_t n = (uint32_t)(i + 1);
+        const uint32_t r = (uint32_t)(fpt_lcg_next(s2) >> 17);
+        over |= lm.x - r;
+        uint32_t rem = r - __umulhi(r, lm.y) * n;
+        if (rem >= n) rem -= n;
+        const TrackT t = row[i]; row[i] = row[rem]; row[rem] = t;
+    }
+    int used = m - 1;
+    if (over >> 31) {
+        used = 0;
+        for (int e = 0; e < m; e++) row[e] = (TrackT)e;
+        for (int i = m - 1; i > 0; i--) {
+            const uint2 lm = rtab[i + 1];
+            const int rr = (int)fpt_randint_fast((uint32_t)(i + 1), lm.x, lm.y, st, used);
+            const TrackT t = row[i]; row[i] = row[rr]; row[rr] = t;
+        }
+    }
+    return used;
 }
 
 template <typename TrackT>
@@ -310,43 +349,42 @@ fpt_css_perm_kernel(const double *__restrict__ Xall, int m, int asize, int bsize
             offs[tid] = tid * draws;
             __syncthreads();
             TrackT *mine = buf0 + (size_t)tid * m;
-            for (;;) {                                          /* generate; repair offsets after rejections */
-                int used = 0;
-                if (tid < nvalid) {
-                    /* chain: stream consumed sequentially; independent: permutation k starts k*(m-1) draws in */
-                    uint64_t st = fpt_lcg_skip(st_win, chain ? (uint64_t)(stream_pos + offs[tid])
-                                                             : (uint64_t)(ndone + tid) * (uint64_t)draws);
-                    for (int e = 0; e < m; e++) mine[e] = (TrackT)e;
-                    /* optimistic pass: a draw is rejected with probability < n / 2^31; remember, do not branch */
-                    uint64_t s2 = st;
-                    uint32_t over = 0u;
-                    for (int i = m - 1; i > 0; i--) {
-                        const uint2 lm = rtab[i + 1];
-                        const uint32_t n = (uint32_t)(i + 1);
-                        const uint32_t r = (uint32_t)(fpt_lcg_next(s2) >> 17);
-                        over |= lm.x - r;
-                        uint32_t rem = r - __umulhi(r, lm.y) * n;
-                        if (rem >= n) rem -= n;
-                        const TrackT t = mine[i]; mine[i] = mine[rem]; mine[rem] = t;
+            if (!chain && ind) {
+                /* independent shuffles: permutation k starts k*(m-1) draws in, nothing to repair. The swaps are random
+                   accesses, so the labels are generated in SHARED memory — the membership rows' space, free until the
+                   scoring below — as many rows at a time as fit, and then copied out to the global rows in one sweep. */
+                const int rbytes = (int)((((size_t)m * sizeof(TrackT) + 3) >> 2) | 1) << 2;      /* odd word count: conflict-free rows */
+                const int rows_fit = (int)(((size_t)T * zs) / rbytes);
+                for (int base = 0; base < nvalid; base += rows_fit) {
+                    const int nb = min(rows_fit, nvalid - base);
+                    if (tid >= base && tid < base + nb)
+                        fpt_generate_labels<TrackT>(reinterpret_cast<TrackT *>(ind + (size_t)(tid - base) * rbytes), m, rtab,
+                                                    fpt_lcg_skip(st_win, (uint64_t)(ndone + tid) * (uint64_t)draws));
+                    __syncthreads();
+                    for (int e = tid; e < nb * m; e += T) {
+                        const int rr = e / m, col = e - rr * m;
+                        buf0[(size_t)(base + rr) * m + col] = reinterpret_cast<const TrackT *>(ind + (size_t)rr * rbytes)[col];
                     }
-                    used = draws;
-                    if (over >> 31) {                           /* replay exactly, counting the draws */
-                        used = 0;
-                        for (int e = 0; e < m; e++) mine[e] = (TrackT)e;
-                        for (int i = m - 1; i > 0; i--) {
-                            const uint2 lm = rtab[i + 1];
-                            const int rr = (int)fpt_randint_fast((uint32_t)(i + 1), lm.x, lm.y, st, used);
-                            const TrackT t = mine[i]; mine[i] = mine[rr]; mine[rr] = t;
-                        }
-                    }
+                    __syncthreads();
                 }
-                int total = 0;
-                const int incl = fpt_block_scan_incl(used, scan, &total);
-                const int want = incl - used;
-                const int bad = (chain && tid < nvalid && want != offs[tid]) ? 1 : 0;
-                if (bad) offs[tid] = want;
-                cons[tid] = total;
-                if (!__syncthreads_or(bad)) break;
+                cons[tid] = 0;
+                __syncthreads();
+            } else {
+                for (;;) {                                      /* generate; repair offsets after rejections */
+                    int used = 0;
+                    if (tid < nvalid) {
+                        /* chain: stream consumed sequentially; independent: permutation k starts k*(m-1) draws in */
+                        used = fpt_generate_labels<TrackT>(mine, m, rtab, fpt_lcg_skip(st_win, chain ? (uint64_t)(stream_pos + offs[tid])
+                                                                                                    : (uint64_t)(ndone + tid) * (uint64_t)draws));
+                    }
+                    int total = 0;
+                    const int incl = fpt_block_scan_incl(used, scan, &total);
+                    const int want = incl - used;
+                    const int bad = (chain && tid < nvalid && want != offs[tid]) ? 1 : 0;
+                    if (bad) offs[tid] = want;
+                    cons[tid] = total;
+                    if (!__syncthreads_or(bad)) break;
+                }
             }
             const int chunk_draws = cons[0];
             /* inclusive scan under composition: G_k = s_1 o ... o s_k, (f o g)[pos] = f[g[pos]] */
