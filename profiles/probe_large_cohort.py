@@ -1,5 +1,5 @@
 import sys, time, json, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import fpt_b200.api as api, fpt_b200.synth as synth
 from fpt_b200 import _lib
 import ctypes as C
