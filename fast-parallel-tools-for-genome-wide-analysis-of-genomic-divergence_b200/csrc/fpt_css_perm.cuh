@@ -1,5 +1,5 @@
 /*
- * fpt_css_perm.cuh — score + Monte-Carlo permutation test, second generation
+ * fpt_css_perm.cuh — score + Monte-Carlo permutation test for cohorts that fit shared memory (m <= 250)
  * (reference: calc_dist css/css.c:573-587, css css.c:608-647, random_shuffle css.c:700-706,
  *  significance_treshold css.c:727-752).
  *
@@ -7,12 +7,13 @@
  *
  * Exactness without paying for it. The reference decides `permuted score >= observed score` on sums
  * accumulated in one fixed order; reproducing that order costs asize*bsize + m - 2 dependent fp64
- * adds fed by 8-byte shared-memory gathers per permutation (the first-generation kernel,
- * fpt_css_perm_kernel, does exactly that and is shared-memory-wavefront bound). Here every permutation is
- * first scored with a cheap, order-independent surrogate:
+ * adds fed by 8-byte shared-memory gathers per permutation (shared-memory-wavefront bound: 30 ms per chromosome of
+ * BASELINE configs[2] against 5.6 ms now). Here every permutation is first scored with a cheap, order-independent
+ * surrogate:
  *     distances quantised to integers q = round(d * S) (4-byte gathers, integer adds, no rounding at all),
  *     between-group sum through the identity  sum_{A'xB'} q = sum_{i in G} rowsum_q(i) - 2 sum_{i<j in G} q_ij
- *     (G = the smaller group; exact in integers), i.e. |G| + |G|(|G|-1)/2 gathers instead of asize*bsize.
+ *     (G = the smaller group; exact in integers), i.e. |G| + |G|(|G|-1)/2 gathers instead of asize*bsize — or, for
+ *     8 <= m <= 64, as a u8 tensor-core product of the 0/1 membership rows with the base-256 digits of q (below).
  * The surrogate differs from the true score by at most E (quantisation bound + fp bound, derived below); only when
  * |surrogate - observed| <= E — a handful of permutations per thousand windows — is the score recomputed in the
  * reference's order. Decisions, hence hits, early-stop index and p, are those of the reference arithmetic.

@@ -272,8 +272,8 @@ def test_css_independent_shuffles_match_reference_functions(fpt, ref_css, oracle
 
 @pytest.mark.parametrize("asize,bsize", [(36, 36), (70, 60), (150, 140)])
 def test_css_larger_cohorts_take_the_fallback_paths(fpt, oracle, asize, bsize):
-    """72: one warp per CTA for classical MDS, gather surrogate; 130: gather surrogate, bigger tiles; 290: Jacobi and
-    first-generation permutation kernel with 16-bit labels and global-memory scratch"""
+    """72: one warp per CTA for classical MDS, gather surrogate; 130: gather surrogate, bigger tiles; 290: Lanczos classical
+    MDS and the general permutation kernel (16-bit labels, global-memory scratch, tensor-core surrogate)"""
     regend, wsize, wstep, nsnp, seed = 12000, 3000, 1500, 500, 3
     ch, (av, bv, apos, bpos) = _synth(100 + asize, regend, nsnp, asize, bsize)
     s_o, p_o = _css_oracle_scan(oracle, av, bv, apos, bpos, regend, wsize, wstep, 5, 60, 0, 0, seed)
@@ -284,8 +284,8 @@ def test_css_larger_cohorts_take_the_fallback_paths(fpt, oracle, asize, bsize):
 
 
 def test_css_large_cohort_500_plus_500(fpt, oracle):
-    """BASELINE configs[4] cohort size (500+500 individuals, 50 kb windows) on a handful of windows: the generic fallback
-    kernels (Jacobi eigensolver and first-generation permutation kernel, matrices in per-CTA global scratch, 16-bit labels)"""
+    """BASELINE configs[4] cohort size (500+500 individuals, 50 kb windows) on a handful of windows: the large-cohort kernels
+    (Lanczos classical MDS; general permutation kernel with matrices in per-CTA global scratch, 16-bit labels, surrogate)"""
     asize = bsize = 500
     regend, wsize, wstep, nsnp, seed = 150000, 50000, 50000, 500, 4
     ch, (av, bv, apos, bpos) = _synth(500, regend, nsnp, asize, bsize)
@@ -299,7 +299,7 @@ def test_css_large_cohort_500_plus_500(fpt, oracle):
 @pytest.mark.parametrize("mds", [0, 2])
 def test_css_cohort_beyond_the_warp_path(fpt, oracle, mds):
     """150+150 individuals: classical MDS by the Lanczos kernel (CTA per window, matrices in global scratch), permutations by
-    the first-generation kernel with 16-bit labels"""
+    the general kernel with 16-bit labels and the tensor-core surrogate"""
     asize = bsize = 150
     regend, wsize, wstep, nsnp, seed = 400000, 20000, 10000, 4000, 9
     ch, (av, bv, apos, bpos) = _synth(77, regend, nsnp, asize, bsize, wstep=wstep)
