@@ -83,6 +83,7 @@ struct FptCssScratch {
     long long *redi;        /* 33 int64 */
     unsigned *wbuf;         /* wch * 2 * m words */
     int wch;
+    int *pairs;             /* SMACOF: pair index p -> (i << 16 | j), or NULL when the table does not fit shared memory */
 };
 
 FPT_D void fpt_css_counts(const unsigned *__restrict__ planes, int m, int l, int r, double *D, const FptCssScratch &sc) {
@@ -317,6 +318,8 @@ FPT_D FptCssSmem fpt_css_carve(unsigned char *smem, int m, int wch, int mats_in_
     s.js.rp = (int *)(smem + off); off += (size_t)half * 4;
     s.js.rq = (int *)(smem + off); off += (size_t)half * 4;
     off = (off + 15) & ~(size_t)15;
+    s.sc.pairs = 0;
+    if (mats_in_smem) { s.sc.pairs = (int *)(smem + off); off += (((size_t)m * (m - 1) / 2) * 4 + 15) & ~(size_t)15; }
     s.sc.wbuf = (unsigned *)(smem + off);
     s.sc.wch = wch;
     return s;
@@ -328,6 +331,7 @@ FPT_HD size_t fpt_css_smem_bytes(int m, int wch, int mats_in_smem) {
     size_t off = (mats_in_smem ? (2 * mm + m) * 8 : 0) + (size_t)4 * m * 8 + (size_t)m * 8 + (size_t)2 * half * 8 + 66 * 8 +
                  (size_t)2 * half * 4;
     off = (off + 15) & ~(size_t)15;
+    if (mats_in_smem) off += (((size_t)m * (m - 1) / 2) * 4 + 15) & ~(size_t)15;   /* SMACOF pair table */
     return off + (size_t)wch * 2 * m * 4;
 }
 
@@ -382,7 +386,8 @@ FPT_D double fpt_css_pairs_pass(const double *X, const double *delta, double *Bm
     double part = 0.0;
     for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
         int i, j;
-        fpt_pair_of(p, i, j);
+        if (sc.pairs) { const int pk = sc.pairs[p]; i = pk >> 16; j = pk & 0xffff; }
+        else fpt_pair_of(p, i, j);
         const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
         const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
         const double dl = delta[i * m + j];
@@ -404,14 +409,19 @@ FPT_D double fpt_css_smacof(const double *delta, double *Bm, int m, double *X, d
     while (k == 0 || (__dsub_rn(prev, sigma) > eps && k <= max_iters)) {
         prev = sigma;
         k++;
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {               /* b_ii = -sum_{j != i} b_ij, j counting down */
+            double *brow = Bm + (size_t)i * ldb;
+            double dsum = 0.0;
+            for (int j = m; --j > i;) dsum = __dadd_rn(dsum, brow[j]);
+            for (int j = i; j--;) dsum = __dadd_rn(dsum, brow[j]);
+            brow[i] = __dmul_rn(-1.0, dsum);
+        }
+        __syncthreads();
         for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {           /* one (row, coordinate) per thread */
             const int i = e >> 1, c = e & 1;
             const double *brow = Bm + (size_t)i * ldb;
-            double dsum = 0.0;
-            for (int j = m; j--;) if (j != i) dsum = __dadd_rn(dsum, brow[j]);
-            const double bii = __dmul_rn(-1.0, dsum);
             double acc = 0.0;
-            for (int j = 0; j < m; j++) acc = __dadd_rn(acc, __dmul_rn(j == i ? bii : brow[j], Z[2 * j + c]));
+            for (int j = 0; j < m; j++) acc = __dadd_rn(acc, __dmul_rn(brow[j], Z[2 * j + c]));
             X[e] = __ddiv_rn(acc, (double)m);
         }
         __syncthreads();
@@ -433,6 +443,10 @@ fpt_css_smacof_kernel(const unsigned *__restrict__ planes, const double *__restr
                       int *__restrict__ iters_runs, unsigned char *__restrict__ status) {
     FPT_DYN_SMEM(smem);
     FptCssSmem s = fpt_css_carve(smem, m, wch, mats_in_smem, gscratch ? gscratch + (size_t)blockIdx.x * fpt_css_mats_doubles(m) : 0);
+    if (s.sc.pairs) {                                     /* the pair decode is the same for every window and iteration */
+        for (int p = threadIdx.x; p < (m * (m - 1)) >> 1; p += blockDim.x) { int i, j; fpt_pair_of(p, i, j); s.sc.pairs[p] = (i << 16) | j; }
+        __syncthreads();
+    }
     const long long nitems = nwin * nruns;
     for (long long it = blockIdx.x; it < nitems; it += gridDim.x) {
         const long long w = it / nruns;

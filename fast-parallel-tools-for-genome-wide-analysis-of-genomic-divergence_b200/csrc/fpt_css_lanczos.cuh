@@ -64,6 +64,7 @@ FPT_D FptLanczosSmem fpt_lanczos_carve(unsigned char *smem, int m, int wch) {
     off = (off + 15) & ~(size_t)15;
     s.sc.wbuf = (unsigned *)(smem + off);
     s.sc.wch = wch;
+    s.sc.pairs = 0;
     return s;
 }
 
