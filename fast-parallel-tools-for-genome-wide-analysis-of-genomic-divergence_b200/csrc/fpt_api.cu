@@ -614,9 +614,20 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
     }
     if (mds == 1 || mds == 2) {
         const int nruns = mds == 1 ? 4 : 1;
-        CHECK(persistent_grid(c, fpt_css_smacof_kernel, 128, p.smem_win, nwin * nruns, &grid));
+        /* block size: the pair pass runs ceil(npairs / threads) rounds, so pick the multiple of 32 (64..256) that wastes
+           the fewest thread-rounds (m = 40: 780 pairs -> 160 threads x 5 rounds instead of 128 x 7) */
+        int sthreads = 128;
+        {
+            const long long npairs = (long long)m * (m - 1) / 2;
+            long long best = -1;
+            for (int t = 64; t <= 256; t += 32) {
+                const long long cost = ((npairs + t - 1) / t) * t;
+                if (best < 0 || cost < best) { best = cost; sthreads = t; }
+            }
+        }
+        CHECK(persistent_grid(c, fpt_css_smacof_kernel, sthreads, p.smem_win, nwin * nruns, &grid));
         grid = std::min(grid, p.max_ctas);
-        { ProfScope ps_("css_smacof", st); fpt_css_smacof_kernel<<<grid, 128, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, r->window_begin, nwin, p.wch,
+        { ProfScope ps_("css_smacof", st); fpt_css_smacof_kernel<<<grid, sthreads, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, r->window_begin, nwin, p.wch,
                                                             p.mats_in_smem, ws.gscratch, nruns, mds == 1, r->seed, st_init,
                                                             300, 0.000001, ws.X, ws.Xruns, ws.sigma, ws.iters, status); }
         CU(cudaGetLastError());

@@ -434,7 +434,7 @@ FPT_D double fpt_css_smacof(const double *delta, double *Bm, int m, double *X, d
 }
 
 /* one CTA per (window, start). nruns = 4 random starts (mds 1) or 1 start from Xin (mds 2). */
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 fpt_css_smacof_kernel(const unsigned *__restrict__ planes, const double *__restrict__ absdiff, int m,
                       const int *__restrict__ wleft, const int *__restrict__ wright, long long wbase, long long nwin,
                       int wch, int mats_in_smem, double *__restrict__ gscratch, int nruns, int random_start, uint64_t seed,
