@@ -292,12 +292,13 @@ FPT_D int fpt_warp_tri_eig(int m, const FptEigWork &w, int want_third, double &o
     glo = glo * rnorm - pad; ghi = ghi * rnorm + pad;
 
     /* two largest eigenvalues at once: lanes 0-15 bracket index m-1, lanes 16-31 index m-2; 17-section.
-       11 rounds shrink the bracket by 17^11 = 3.4e13; the Rayleigh quotient of the converged vector supplies the rest. */
+       8 rounds shrink the bracket by 17^8 = 7e9 (1.4e-10 of the spectrum width); three inverse-iteration solves with that
+       shift and the Rayleigh quotient of the converged vector supply the rest. */
     const int half = lane >> 4, hl = lane & 15;
     const int want = m - 1 - half;                         /* ascending index searched by this half-warp */
     double lo = glo, hi = ghi;
     #pragma unroll 1
-    for (int round = 0; round < 11; round++) {
+    for (int round = 0; round < 8; round++) {
         const double x = lo + (hi - lo) * ((double)(hl + 1) / 17.0);
         const int flag = fpt_sturm_count(w.pv, w.wv, m, x, pivmin) >= want + 1;
         const unsigned bal = (__ballot_sync(FPT_FULL_MASK, flag) >> (16 * half)) & 0xffffu;
