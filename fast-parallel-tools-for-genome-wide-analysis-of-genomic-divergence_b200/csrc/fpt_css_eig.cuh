@@ -391,46 +391,65 @@ FPT_D int fpt_warp_tri_eig(int m, const FptEigWork &w, int want_third, double &o
             if (m > 1) y[m - 2] = (y[m - 2] - du[m - 2] * y[m - 1]) * rdd[m - 2];
             #pragma unroll 1
             for (int i = m - 3; i >= 0; i--) y[i] = (y[i] - du[i] * y[i + 1] - du2[i] * y[i + 2]) * rdd[i];
+        }
+        __syncwarp();
+        /* the solves above are recurrences (one lane each); everything else on the vectors is data-parallel: lanes 0-15 work
+           on vector 0, lanes 16-31 on vector 1 */
+        {
+            const int c = lane >> 4, hl = lane & 15;
+            double *y = w.y + (size_t)c * m;
             double mx = 0.0;
             #pragma unroll 1
-            for (int i = 0; i < m; i++) mx = fmax(mx, fabs(y[i]));
-            if (!(mx > 0.0) || !(mx < 1e300)) {            /* overflow / breakdown: restart from a unit vector */
+            for (int i = hl; i < m; i += 16) mx = fmax(mx, fabs(y[i]));
+            for (int o = 8; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FPT_FULL_MASK, mx, o));
+            const bool broke = !(mx > 0.0) || !(mx < 1e300);   /* overflow / breakdown: restart from a unit vector */
+            if (broke) {
                 #pragma unroll 1
-                for (int i = 0; i < m; i++) y[i] = i == c ? 1.0 : 0.0;
+                for (int i = hl; i < m; i += 16) y[i] = i == c ? 1.0 : 0.0;
                 mx = 1.0;
             }
+            __syncwarp();
             const double rm = 1.0 / mx;
             double nn = 0.0;
             #pragma unroll 1
-            for (int i = 0; i < m; i++) { y[i] *= rm; nn += y[i] * y[i]; }
+            for (int i = hl; i < m; i += 16) { const double v = y[i] * rm; y[i] = v; nn += v * v; }
+            for (int o = 8; o > 0; o >>= 1) nn += __shfl_xor_sync(FPT_FULL_MASK, nn, o);
             nn = 1.0 / sqrt(nn);
             #pragma unroll 1
-            for (int i = 0; i < m; i++) y[i] *= nn;
+            for (int i = hl; i < m; i += 16) y[i] *= nn;
         }
         __syncwarp();
-        if (lane == 1) {                                   /* keep the second vector orthogonal to the first */
+        {   /* keep the second vector orthogonal to the first */
             double *y0 = w.y, *y1 = w.y + m;
             double dot = 0.0;
             #pragma unroll 1
-            for (int i = 0; i < m; i++) dot += y0[i] * y1[i];
+            for (int i = lane; i < m; i += 32) dot += y0[i] * y1[i];
+            dot = fpt_warp_sum(dot);
             double nn = 0.0;
             #pragma unroll 1
-            for (int i = 0; i < m; i++) { y1[i] -= dot * y0[i]; nn += y1[i] * y1[i]; }
-            if (nn > 0.0) { nn = 1.0 / sqrt(nn); for (int i = 0; i < m; i++) y1[i] *= nn; }
+            for (int i = lane; i < m; i += 32) { const double v = y1[i] - dot * y0[i]; y1[i] = v; nn += v * v; }
+            nn = fpt_warp_sum(nn);
+            if (nn > 0.0) {
+                nn = 1.0 / sqrt(nn);
+                #pragma unroll 1
+                for (int i = lane; i < m; i += 32) y1[i] *= nn;
+            }
         }
         __syncwarp();
     }
-    {   /* Rayleigh quotients y'Ty of the unit vectors: the eigenvalues to working precision */
+    {   /* Rayleigh quotients y'Ty of the unit vectors: the eigenvalues to working precision (half a warp per vector) */
+        const int c = lane >> 4, hl = lane & 15;
+        const double *y = w.y + (size_t)c * m;
         double rq = 0.0;
-        if (lane < 2) {
-            const double *y = w.y + (size_t)lane * m;
-            #pragma unroll 1
-            for (int i = 0; i < m; i++) rq += w.d[i] * y[i] * y[i];
-            #pragma unroll 1
-            for (int i = 0; i < m - 1; i++) rq += 2.0 * w.e[i] * y[i] * y[i + 1];
+        #pragma unroll 1
+        for (int i = hl; i < m; i += 16) {
+            const double yi = y[i];
+            rq += w.d[i] * yi * yi;
+            if (i < m - 1) rq += 2.0 * w.e[i] * yi * y[i + 1];
         }
+        for (int o = 8; o > 0; o >>= 1) rq += __shfl_xor_sync(FPT_FULL_MASK, rq, o);
         lam1 = __shfl_sync(FPT_FULL_MASK, rq, 0);
-        lam2 = __shfl_sync(FPT_FULL_MASK, rq, 1);
+        lam2 = __shfl_sync(FPT_FULL_MASK, rq, 16);
     }
     out1 = lam1; out2 = lam2; out3 = lam3;
     return 1;
