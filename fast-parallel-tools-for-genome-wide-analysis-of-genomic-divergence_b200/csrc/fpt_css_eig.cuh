@@ -338,20 +338,27 @@ FPT_D int fpt_warp_tri_eig(int m, const FptEigWork &w, int want_third, double &o
        quotient of the converged vector. Per vector: 1/pivot, du, du2 in `lu`, the multipliers in pv / wv (a multiplier of an
        interchanged row is stored as f + 4). */
     const double epsT = 2.220446049250313e-16 * tnorm;
-    if (lane < 2) {
-        const int c = lane;
+    {   /* set-up, half a warp per vector */
+        const int c = lane >> 4, hl = lane & 15;
         const double lam = (c == 0 ? lam1 : lam2) * tnorm;
         double *dd = w.lu + (size_t)c * 3 * m, *du = dd + m, *du2 = du + m;
         double *dl = (c == 0 ? w.pv : w.wv);               /* the scaled copies are no longer needed */
         double *y = w.y + (size_t)c * m;
+        __syncwarp();
         #pragma unroll 1
-        for (int i = 0; i < m; i++) {
+        for (int i = hl; i < m; i += 16) {
             dd[i] = w.d[i] - lam;
             if (i < m - 1) { du[i] = w.e[i]; dl[i] = w.e[i]; }
             du2[i] = 0.0;
             const unsigned hsh = ((unsigned)i * 2654435761u + (unsigned)c * 40503u + 12345u) >> 8;
             y[i] = ((double)(hsh & 0xffffu) / 65536.0) - 0.5 + (c == 0 ? 1.0 : 0.0);
         }
+    }
+    __syncwarp();
+    if (lane < 2) {                                        /* the elimination itself is a recurrence: one lane per vector */
+        const int c = lane;
+        double *dd = w.lu + (size_t)c * 3 * m, *du = dd + m, *du2 = du + m;
+        double *dl = (c == 0 ? w.pv : w.wv);
         #pragma unroll 1
         for (int i = 0; i < m - 1; i++) {
             if (fabs(dd[i]) >= fabs(dl[i])) {               /* no interchange */
@@ -370,8 +377,12 @@ FPT_D int fpt_warp_tri_eig(int m, const FptEigWork &w, int want_third, double &o
             }
         }
         if (dd[m - 1] == 0.0) dd[m - 1] = epsT;
+    }
+    __syncwarp();
+    {   /* pivots are only ever divided by: reciprocals, half a warp per vector */
+        double *dd = w.lu + (size_t)(lane >> 4) * 3 * m;
         #pragma unroll 1
-        for (int i = 0; i < m; i++) dd[i] = 1.0 / dd[i];    /* pivots are only ever divided by */
+        for (int i = lane & 15; i < m; i += 16) dd[i] = 1.0 / dd[i];
     }
     __syncwarp();
     #pragma unroll 1
