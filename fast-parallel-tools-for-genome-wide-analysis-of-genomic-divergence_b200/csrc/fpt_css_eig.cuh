@@ -520,18 +520,22 @@ FPT_D void fpt_warp_eig(int m, const FptEigWork &w, const double *__restrict__ r
 /* work areas: phase A needs the packed matrix, phase B only O(m) vectors — which is why they are separate kernels:
    the eigen-solve is a chain of dependent fp64 operations and wants as many resident warps as possible */
 FPT_HD size_t fpt_tridiag_work_bytes(int m, int wch) {
-    size_t bytes = ((size_t)fpt_tri(m) + (size_t)7 * m) * 8 + (size_t)wch * 2 * m * 4;
+    /* packed matrix + six vectors (d, e, tau, pv, wv, the contiguous reflector); the bit-plane words of the counting stage
+       live in the vectors' space, which is idle until the reduction starts (shared memory per warp decides how many warps
+       an SM holds, and this kernel runs on latency hiding) */
+    const size_t vec = (size_t)6 * m * 8, words = (size_t)wch * 2 * m * 4;
+    size_t bytes = (size_t)fpt_tri(m) * 8 + (words > vec ? words : vec);
     return (bytes + 15) & ~(size_t)15;
 }
 FPT_D FptEigWork fpt_tridiag_carve(unsigned char *base, int m, int wch) {
     FptEigWork w;
     double *p = (double *)base;
     w.A = p; p += (size_t)fpt_tri(m);
+    w.wbuf = (unsigned *)p;                                /* aliases the vectors below */
     w.d = p; p += m; w.e = p; p += m; w.tau = p; p += m;
     w.pv = p; p += m; w.wv = p; p += m;
-    w.y = p; p += 2 * m;                                   /* first half doubles as the contiguous reflector */
+    w.y = p; p += m;                                       /* the contiguous reflector (phase B has its own 2m) */
     w.lu = 0;
-    w.wbuf = (unsigned *)p;
     w.wch = wch;
     return w;
 }
