@@ -485,7 +485,7 @@ static CssPlan css_plan(const DeviceCtx *c, int m) {
     p.mats_in_smem = fpt_css_smem_bytes(m, p.wch, 1) <= budget;
     if (!p.mats_in_smem && fpt_css_smem_bytes(m, p.wch, 0) > budget) p.wch = 1;
     p.smem_win = fpt_css_smem_bytes(m, p.wch, p.mats_in_smem);
-    const size_t per_warp = fpt_tridiag_work_bytes(m, 4);
+    const size_t per_warp = fpt_tridiag_work_bytes(m, 3);   /* three 32-SNP words per pass fill the vectors' space exactly */
     p.mds_warps = 2 * per_warp <= 32 * 1024 ? 2 : (per_warp <= budget ? 1 : 0);   /* small CTAs: many resident warps */
     p.smem_mds_warp = per_warp * (p.mds_warps > 0 ? p.mds_warps : 1);
     p.perm_threads = 256;
@@ -596,7 +596,7 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
         if (p.mds_warps > 0) {
             const int block = 32 * p.mds_warps;
             CHECK(persistent_grid(c, fpt_css_tridiag_kernel, block, p.smem_mds_warp, (nwin + p.mds_warps - 1) / p.mds_warps, &grid));
-            { ProfScope ps_("css_tridiag", st); fpt_css_tridiag_kernel<<<grid, block, p.smem_mds_warp, st>>>(planes, absdiff, m, wleft, wright, nwin, 4, ws.tri, ws.refl, status); }
+            { ProfScope ps_("css_tridiag", st); fpt_css_tridiag_kernel<<<grid, block, p.smem_mds_warp, st>>>(planes, absdiff, m, wleft, wright, nwin, 3, ws.tri, ws.refl, status); }
             CU(cudaGetLastError());
             const size_t smem_b = fpt_eigvec_work_bytes(m) * 4;
             CHECK(persistent_grid(c, fpt_css_eigvec_kernel, 128, smem_b, (nwin + 3) / 4, &grid));

@@ -520,10 +520,10 @@ FPT_D void fpt_warp_eig(int m, const FptEigWork &w, const double *__restrict__ r
 /* work areas: phase A needs the packed matrix, phase B only O(m) vectors — which is why they are separate kernels:
    the eigen-solve is a chain of dependent fp64 operations and wants as many resident warps as possible */
 FPT_HD size_t fpt_tridiag_work_bytes(int m, int wch) {
-    /* packed matrix + six vectors (d, e, tau, pv, wv, the contiguous reflector); the bit-plane words of the counting stage
-       live in the vectors' space, which is idle until the reduction starts (shared memory per warp decides how many warps
-       an SM holds, and this kernel runs on latency hiding) */
-    const size_t vec = (size_t)6 * m * 8, words = (size_t)wch * 2 * m * 4;
+    /* packed matrix + three vectors (pv, wv, the contiguous reflector); d, e and tau go straight to global memory (one
+       scalar store per step), and the bit-plane words of the counting stage live in the vectors' space, which is idle until
+       the reduction starts. Shared memory per warp decides how many warps an SM holds, and this kernel runs on latency hiding. */
+    const size_t vec = (size_t)3 * m * 8, words = (size_t)wch * 2 * m * 4;
     size_t bytes = (size_t)fpt_tri(m) * 8 + (words > vec ? words : vec);
     return (bytes + 15) & ~(size_t)15;
 }
@@ -532,9 +532,9 @@ FPT_D FptEigWork fpt_tridiag_carve(unsigned char *base, int m, int wch) {
     double *p = (double *)base;
     w.A = p; p += (size_t)fpt_tri(m);
     w.wbuf = (unsigned *)p;                                /* aliases the vectors below */
-    w.d = p; p += m; w.e = p; p += m; w.tau = p; p += m;
     w.pv = p; p += m; w.wv = p; p += m;
     w.y = p; p += m;                                       /* the contiguous reflector (phase B has its own 2m) */
+    w.d = 0; w.e = 0; w.tau = 0;                           /* set per window: the window's slot of the hand-over buffer */
     w.lu = 0;
     w.wch = wch;
     return w;
@@ -578,11 +578,16 @@ fpt_css_tridiag_kernel(const unsigned *__restrict__ planes, const double *__rest
             fpt_warp_counts(planes, m, l, r, w);
         }
         if (!fpt_warp_fill(m, w)) { if (lane == 0) status[win] = 1; __syncwarp(); continue; }
-        fpt_warp_tridiag(m, w, refl_out + (size_t)win * nrefl);
+        FptEigWork ww = w;                                   /* d, e, tau: written in place in the hand-over buffer */
         double *t = tri_out + (size_t)win * 3 * m;
-        #pragma unroll 1
-        for (int i = lane; i < m; i += 32) { t[i] = w.d[i]; t[m + i] = i < m - 1 ? w.e[i] : 0.0; t[2 * m + i] = i < m - 2 ? w.tau[i] : 0.0; }
-        if (lane == 0) status[win] = 2;
+        ww.d = t; ww.e = t + m; ww.tau = t + 2 * m;
+        fpt_warp_tridiag(m, ww, refl_out + (size_t)win * nrefl);
+        if (lane == 0) {                                     /* entries the reduction does not produce */
+            t[m + m - 1] = 0.0;
+            t[2 * m + m - 1] = 0.0;
+            if (m >= 2) t[2 * m + m - 2] = 0.0;
+            status[win] = 2;
+        }
         __syncwarp();
     }
 }
