@@ -385,6 +385,10 @@ FPT_D int fpt_warp_tri_eig(int m, const FptEigWork &w, int want_third, double &o
         for (int i = lane & 15; i < m; i += 16) dd[i] = 1.0 / dd[i];
     }
     __syncwarp();
+    /* at most three solves; the loop stops as soon as the Rayleigh quotients of both vectors have settled (a vector error e
+       moves the quotient by ~e^2, so a change below 1e-12 of the norm means the previous iterate was already good to ~1e-6
+       and the current one far better). With the bracket above two solves are the rule. */
+    double rq_prev = 0.0;
     #pragma unroll 1
     for (int iter = 0; iter < 3; iter++) {
         if (lane < 2) {
@@ -447,8 +451,7 @@ FPT_D int fpt_warp_tri_eig(int m, const FptEigWork &w, int want_third, double &o
             }
         }
         __syncwarp();
-    }
-    {   /* Rayleigh quotients y'Ty of the unit vectors: the eigenvalues to working precision (half a warp per vector) */
+        /* Rayleigh quotients y'Ty of the unit vectors: the eigenvalues to working precision (half a warp per vector) */
         const int c = lane >> 4, hl = lane & 15;
         const double *y = w.y + (size_t)c * m;
         double rq = 0.0;
@@ -461,6 +464,9 @@ FPT_D int fpt_warp_tri_eig(int m, const FptEigWork &w, int want_third, double &o
         for (int o = 8; o > 0; o >>= 1) rq += __shfl_xor_sync(FPT_FULL_MASK, rq, o);
         lam1 = __shfl_sync(FPT_FULL_MASK, rq, 0);
         lam2 = __shfl_sync(FPT_FULL_MASK, rq, 16);
+        const int settled = iter > 0 && fabs(rq - rq_prev) <= 1e-12 * tnorm;
+        rq_prev = rq;
+        if (__all_sync(FPT_FULL_MASK, settled)) break;
     }
     out1 = lam1; out2 = lam2; out3 = lam3;
     return 1;
