@@ -39,6 +39,11 @@ def get_perm_mode():
     return bool(_lib.load().fpt_get_perm_mode())
 
 
+def set_perm_large_kernel(tensor_memory):
+    """Large cohorts (m > 250): True = tcgen05 permutation kernel (default), False = the general kernel. Same results."""
+    _lib.load().fpt_set_perm_large_kernel(1 if tensor_memory else 0)
+
+
 def css_perm_rechecks():
     return int(_lib.load().fpt_css_perm_rechecks())
 

@@ -28,6 +28,7 @@
 #include "fpt_css_lanczos.cuh"
 #include "fpt_css_perm.cuh"
 #include "fpt_css_perm_large.cuh"
+#include "fpt_css_perm_umma.cuh"
 #include "fpt_fet.cuh"
 #include "fpt_rt.cuh"
 #include "fpt_tables.h"
@@ -36,6 +37,7 @@
 static thread_local char g_err[512] = "";
 static uint64_t g_seed = 20261018ULL;
 static int g_device = -1;               /* -1: whatever device is current */
+static int g_perm_umma = 1;             /* large cohorts: 1 = tcgen05 permutation kernel, 0 = the general (mma.sync) kernel */
 static int g_perm_chain = 0;            /* CSS label shuffles: 0 = independent per permutation, 1 = the reference's chain */
 
 static int fail(int code, const char *fmt, ...) {
@@ -267,6 +269,7 @@ extern "C" int fpt_set_device(int device) {
 
 extern "C" void fpt_set_perm_mode(int chain) { g_perm_chain = chain != 0; }
 extern "C" int fpt_get_perm_mode(void) { return g_perm_chain; }
+extern "C" void fpt_set_perm_large_kernel(int tensor_memory) { g_perm_umma = tensor_memory != 0; }
 
 /* exact re-evaluations the permutation kernel needed since the last call (its integer surrogate could not
    decide `permuted >= observed`); synchronises the device */
@@ -474,6 +477,7 @@ struct CssPlan {
     size_t smem_perm, perm_scratch_per_cta;
     int perm2, qbits;                /* second-generation permutation kernel (labels in bytes, everything in smem) */
     size_t smem_perm2;
+    int perm_umma; size_t smem_umma; /* large cohorts, independent shuffles: tcgen05 contraction, one CTA per SM */
     int max_ctas;                    /* upper bound on persistent CTAs (sizes the global scratch) */
 };
 
@@ -509,6 +513,9 @@ static CssPlan css_plan(const DeviceCtx *c, int m) {
     p.smem_perm2 = fpt_css_perm2_smem_bytes(m, p.perm_threads, g_perm_chain);
     p.perm2 = m <= 250 && p.smem_perm2 <= budget;
     p.qbits = 8;
+    p.smem_umma = fpt_umma_smem_bytes(m);
+    p.perm_umma = !p.perm2 && p.perm_sur && !g_perm_chain && g_perm_umma && m <= 1024 && p.smem_umma <= budget;
+    if (p.perm_umma) p.perm_scratch_per_cta = std::max(p.perm_scratch_per_cta, (fpt_umma_scratch_bytes(m) + 1023) & ~(size_t)1023);
     return p;
 }
 
@@ -564,6 +571,18 @@ static int launch_perm(DeviceCtx *c, const CssPlan &p, const CssWorkspace &ws, i
     { ProfScope ps_("css_perm", st); fpt_css_perm_kernel<TrackT><<<grid, p.perm_threads, p.smem_perm, st>>>(
         ws.X, p.m, asize, bsize, wbase, nwin, status, treshold, runs, seed, states, g_perm_chain, p.dist_in_smem, p.tracks_in_smem,
         (double *)ws.perm_scratch, p.perm_scratch_per_cta, p.perm_sur ? 31 : 0, scores, pv, hits, nperm, c->rechecks); }
+    CU(cudaGetLastError());
+    return FPT_OK;
+}
+
+static int launch_perm_umma(DeviceCtx *c, const CssPlan &p, const CssWorkspace &ws, int asize, int bsize, long long wbase,
+                            long long nwin, const uint8_t *status, int treshold, int runs, uint64_t seed, const uint64_t *states,
+                            double *scores, double *pv, int *hits, int *nperm, cudaStream_t st) {
+    CU(cudaFuncSetAttribute(fpt_css_perm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_umma));
+    const int grid = (int)std::max(1LL, std::min<long long>(std::min(c->sms, p.max_ctas), nwin));   /* all of tensor memory: one CTA per SM */
+    { ProfScope ps_("css_perm", st); fpt_css_perm_umma_kernel<<<grid, FPT_UMMA_THREADS, p.smem_umma, st>>>(
+        ws.X, p.m, asize, bsize, wbase, nwin, status, treshold, runs, seed, states, ws.perm_scratch, p.perm_scratch_per_cta, 31,
+        scores, pv, hits, nperm, c->rechecks); }
     CU(cudaGetLastError());
     return FPT_OK;
 }
@@ -646,6 +665,9 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
               ws.X, m, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, g_perm_chain, qb, scores, pv,
               hits, nperm, c->rechecks); }
         CU(cudaGetLastError());
+    } else if (p.perm_umma) {
+        CHECK(launch_perm_umma(c, p, ws, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, scores, pv,
+                               hits, nperm, st));
     } else if (p.wide_tracks)
         CHECK(launch_perm<unsigned short>(c, p, ws, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed,
                                           st_perm, scores, pv, hits, nperm, st));

@@ -58,6 +58,10 @@ uint64_t fpt_get_seed(void);
    to significance_treshold() run on identity labels from the same 48-bit state. */
 void fpt_set_perm_mode(int chain);
 int fpt_get_perm_mode(void);
+/* Cohorts too large for the all-in-shared-memory permutation kernel (m > 250), independent shuffles: 1 (default) scores a
+   batch of 128 permutations as one u8 contraction on tcgen05 / tensor memory (csrc/fpt_css_perm_umma.cuh, m <= 1024),
+   0 keeps the general kernel (csrc/fpt_css_perm_large.cuh). Same decisions either way; the switch exists for the parity tests. */
+void fpt_set_perm_large_kernel(int tensor_memory);
 /* number of permutations since the last call whose integer surrogate score could not decide `permuted >= observed` and
    were re-scored in the reference's summation order (diagnostic; synchronises the device); -1 on error */
 long long fpt_css_perm_rechecks(void);

@@ -296,6 +296,28 @@ def test_css_large_cohort_500_plus_500(fpt, oracle):
     assert np.array_equal(p_g, p_o)
 
 
+@pytest.mark.parametrize("asize,bsize,mct,mcr", [(500, 500, 300, 300), (400, 300, 7, 400), (130, 170, 1000, 1000), (513, 511, 140, 140)])
+def test_css_tensor_memory_permutation_kernel_matches_general_kernel(fpt, asize, bsize, mct, mcr):
+    """Large cohorts: the tcgen05 / tensor-memory permutation kernel (csrc/fpt_css_perm_umma.cuh) takes the same decisions as
+    the general kernel (csrc/fpt_css_perm_large.cuh) — hits, permutations drawn, p and score identical — over several batches
+    of 128 permutations, ragged last batches, unequal groups, early stops and K / N padding (m = 300, 700, 1000, 1024)."""
+    from fpt_b200 import api
+    regend, wsize, wstep, nsnp, seed = 200000, 50000, 50000, 600, 11
+    ch, _ = _synth(300 + asize, regend, nsnp, asize, bsize)
+    out = []
+    try:
+        for tm in (True, False):
+            api.set_perm_large_kernel(tm)
+            out.append(fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, mct, mcr, mds=0, seed=seed, probes=True))
+    finally:
+        api.set_perm_large_kernel(True)
+    (s1, p1, w1, pr1), (s0, p0, w0, pr0) = out
+    assert (w1 == 1).sum() == 4 and np.array_equal(w1, w0)
+    assert np.array_equal(s1, s0, equal_nan=True) and np.array_equal(p1, p0)
+    assert np.array_equal(pr1["hits"], pr0["hits"]) and np.array_equal(pr1["nperm"], pr0["nperm"])
+    assert pr1["nperm"][w1 == 1].max() > 0
+
+
 @pytest.mark.parametrize("mds", [0, 2])
 def test_css_cohort_beyond_the_warp_path(fpt, oracle, mds):
     """150+150 individuals: classical MDS by the Lanczos kernel (CTA per window, matrices in global scratch), permutations by
