@@ -40,8 +40,9 @@ def get_perm_mode():
 
 
 def set_perm_large_kernel(tensor_memory):
-    """Large cohorts (m > 250): True = tcgen05 permutation kernel (default), False = the general kernel. Same results."""
-    _lib.load().fpt_set_perm_large_kernel(1 if tensor_memory else 0)
+    """Large cohorts (m > 250): 1 / True = tcgen05 permutation kernel (default), 0 / False = the general kernel, 2 = tcgen05
+    kernel with a coarse (10-bit) surrogate that forces many exact re-scorings. Same results in every mode."""
+    _lib.load().fpt_set_perm_large_kernel(int(tensor_memory))
 
 
 def css_perm_rechecks():

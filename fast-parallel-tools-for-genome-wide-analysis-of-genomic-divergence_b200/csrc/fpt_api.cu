@@ -269,7 +269,13 @@ extern "C" int fpt_set_device(int device) {
 
 extern "C" void fpt_set_perm_mode(int chain) { g_perm_chain = chain != 0; }
 extern "C" int fpt_get_perm_mode(void) { return g_perm_chain; }
-extern "C" void fpt_set_perm_large_kernel(int tensor_memory) { g_perm_umma = tensor_memory != 0; }
+extern "C" void fpt_set_perm_large_kernel(int tensor_memory) { g_perm_umma = tensor_memory; }
+extern "C" int fpt_debug_umma_phases(unsigned long long *out8) {
+    unsigned long long zero[8] = { 0 };
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(out8, fpt_umma_phase_cycles, sizeof zero) != cudaSuccess ||
+        cudaMemcpyToSymbol(fpt_umma_phase_cycles, zero, sizeof zero) != cudaSuccess) return FPT_ERR_CUDA;
+    return FPT_OK;
+}
 
 /* exact re-evaluations the permutation kernel needed since the last call (its integer surrogate could not
    decide `permuted >= observed`); synchronises the device */
@@ -578,11 +584,18 @@ static int launch_perm(DeviceCtx *c, const CssPlan &p, const CssWorkspace &ws, i
 static int launch_perm_umma(DeviceCtx *c, const CssPlan &p, const CssWorkspace &ws, int asize, int bsize, long long wbase,
                             long long nwin, const uint8_t *status, int treshold, int runs, uint64_t seed, const uint64_t *states,
                             double *scores, double *pv, int *hits, int *nperm, cudaStream_t st) {
+    /* observed scores first: one warp per window, its result handed over in `scores` */
+    const size_t smem_obs = fpt_css_observed_smem_bytes(p.m);
+    int grid_obs;
+    CHECK(persistent_grid(c, fpt_css_observed_kernel, FPT_OBS_WARPS * 32, smem_obs, (nwin + FPT_OBS_WARPS - 1) / FPT_OBS_WARPS, &grid_obs));
+    { ProfScope ps_("css_observed", st); fpt_css_observed_kernel<<<grid_obs, FPT_OBS_WARPS * 32, smem_obs, st>>>(
+        ws.X, p.m, asize, bsize, nwin, status, scores); }
+    CU(cudaGetLastError());
     CU(cudaFuncSetAttribute(fpt_css_perm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_umma));
     const int grid = (int)std::max(1LL, std::min<long long>(std::min(c->sms, p.max_ctas), nwin));   /* all of tensor memory: one CTA per SM */
     { ProfScope ps_("css_perm", st); fpt_css_perm_umma_kernel<<<grid, FPT_UMMA_THREADS, p.smem_umma, st>>>(
-        ws.X, p.m, asize, bsize, wbase, nwin, status, treshold, runs, seed, states, ws.perm_scratch, p.perm_scratch_per_cta, 31,
-        scores, pv, hits, nperm, c->rechecks); }
+        ws.X, p.m, asize, bsize, wbase, nwin, status, treshold, runs, seed, states, ws.perm_scratch, p.perm_scratch_per_cta,
+        g_perm_umma == 2 ? 10 : 31, scores, pv, hits, nperm, c->rechecks); }
     CU(cudaGetLastError());
     return FPT_OK;
 }

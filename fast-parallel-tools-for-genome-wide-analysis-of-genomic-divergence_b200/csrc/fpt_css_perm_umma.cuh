@@ -36,10 +36,9 @@ FPT_HD int fpt_umma_kp(int m) { return ((m + FPT_UMMA_KC - 1) / FPT_UMMA_KC) * F
 FPT_HD int fpt_umma_np(int m) { return ((m + FPT_UMMA_NT - 1) / FPT_UMMA_NT) * FPT_UMMA_NT; }
 FPT_HD int fpt_umma_rbytes(int m) { return (int)((((size_t)m * 2 + 3) >> 2) | 1) << 2; }     /* label row, odd word count */
 
-/* per-CTA global scratch: dist (f64 m x m), q (u32 m x m), digit matrices in tile layout, label rows of one batch */
+/* per-CTA global scratch: digit matrices in tile layout, label rows of one batch */
 FPT_HD size_t fpt_umma_scratch_bytes(int m) {
-    size_t b = (((size_t)m * m * 8 + 255) & ~(size_t)255) + (((size_t)m * m * 4 + 255) & ~(size_t)255);
-    b += (size_t)FPT_UMMA_DIGITS * fpt_umma_np(m) * fpt_umma_kp(m);
+    size_t b = (size_t)FPT_UMMA_DIGITS * fpt_umma_np(m) * fpt_umma_kp(m);
     b += ((size_t)FPT_UMMA_BATCH * m * 2 + 255) & ~(size_t)255;
     return b;
 }
@@ -49,9 +48,132 @@ FPT_HD size_t fpt_umma_smem_bytes(int m) {
     off += (size_t)2 * m * 8;                                   /* X */
     off += (size_t)(m + 1) * 8;                                 /* per-n (limit, magic) of the shuffle draws */
     off += (size_t)2 * FPT_UMMA_BATCH * 8;                      /* adjacent-pair sums */
+    off += (size_t)(FPT_UMMA_THREADS / 32) * 32 * 8;            /* per-warp staging of the exact re-scoring */
     off += (size_t)FPT_UMMA_BATCH * 4 + 33 * 4 + 16;            /* hits, scan */
     return (off + 15) & ~(size_t)15;
 }
+
+
+/* quantised distance between individuals i and j of the embedding X: the value the distance pass stores for (i, j) */
+FPT_D unsigned fpt_umma_q(const double *X, int i, int j, double S) {
+    const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
+    const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    return (unsigned)__double2ll_rn(d * S);
+}
+
+/* Fisher-Yates of fresh identity labels (css.c:700-706) like fpt_generate_labels, four draws ahead of the swaps: the draws
+   do not depend on the labels, so the generator's chain and the swaps' load-store chain run side by side */
+FPT_D void fpt_umma_shuffle(unsigned short *row, int m, const uint2 *rtab, uint64_t st) {
+    for (int e = 0; e < m; e++) row[e] = (unsigned short)e;
+    uint64_t s2 = st;
+    uint32_t over = 0u;
+    int i = m - 1;
+    for (; i >= 4; i -= 4) {
+        uint32_t rem[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t n = (uint32_t)(i - u + 1);
+            const uint2 lm = rtab[n];
+            const uint32_t r = (uint32_t)(fpt_lcg_next(s2) >> 17);
+            over |= lm.x - r;
+            uint32_t rm = r - __umulhi(r, lm.y) * n;
+            if (rm >= n) rm -= n;
+            rem[u] = rm;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned short t = row[i - u], x = row[rem[u]];
+            row[i - u] = x; row[rem[u]] = t;
+        }
+    }
+    for (; i > 0; i--) {
+        const uint32_t n = (uint32_t)(i + 1);
+        const uint2 lm = rtab[n];
+        const uint32_t r = (uint32_t)(fpt_lcg_next(s2) >> 17);
+        over |= lm.x - r;
+        uint32_t rm = r - __umulhi(r, lm.y) * n;
+        if (rm >= n) rm -= n;
+        const unsigned short t = row[i], x = row[rm];
+        row[i] = x; row[rm] = t;
+    }
+    if (over >> 31) fpt_generate_labels<unsigned short>(row, m, rtab, st);     /* a rejected draw: exact replay */
+}
+
+/* Observed score of every window (identity labels) in the reference's summation order, css.c:608-647: a quarter of a million
+   dependent fp64 additions per window at m = 1000, i.e. latency, so ONE WARP per window and many windows per SM. The lanes
+   compute the next 32 distances (calc_dist, css.c:573-587) while lane 0 adds the previous 32 in order. Bit-identical to
+   fpt_css_score_identity on the stored distance matrix. */
+#define FPT_OBS_WARPS 4
+FPT_HD size_t fpt_css_observed_smem_bytes(int m) { return (size_t)FPT_OBS_WARPS * ((size_t)2 * m * 8 + 32 * 8); }
+
+/* kind 0: between-group pairs (i from asize-1 down, j from m-1 down to asize); 1: adjacent pairs of the first group;
+   2: of the second group — each in the order the reference adds them */
+FPT_D double fpt_observed_chain(const double *X, double *stage, int kind, int asize, int bsize, int lane,
+                                const unsigned short *lab = nullptr) {
+    const int total = kind == 0 ? asize * bsize : (kind == 1 ? asize - 1 : bsize - 1);     /* m <= 1024: fits an int */
+    double acc = 0.0;
+    auto dist_of = [&](int e) -> double {
+        int i, j;
+        if (kind == 0) { const int r = e / bsize; i = asize - 1 - r; j = asize + bsize - 1 - (e - r * bsize); }
+        else if (kind == 1) { i = asize - 2 - e; j = i + 1; }
+        else { i = asize + bsize - 2 - e; j = i + 1; }
+        if (lab) { i = lab[i]; j = lab[j]; }                    /* a permutation's labels instead of the identity */
+        const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
+        return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    };
+    double dcur = lane < total ? dist_of(lane) : 0.0;
+    for (int base = 0; base < total; base += 32) {
+        stage[lane] = dcur;
+        __syncwarp();
+        const int nxt = base + 32 + lane;
+        const double dnext = nxt < total ? dist_of(nxt) : 0.0;
+        if (lane == 0) {
+            const int cnt = total - base < 32 ? total - base : 32;
+            if (cnt == 32) {
+#pragma unroll
+                for (int t = 0; t < 32; t++) acc = __dadd_rn(acc, stage[t]);
+            } else {
+                for (int t = 0; t < cnt; t++) acc = __dadd_rn(acc, stage[t]);
+            }
+        }
+        __syncwarp();
+        dcur = dnext;
+    }
+    return acc;                                                 /* lane 0 holds the sum */
+}
+
+/* css() of css.c:608-647 for one label row by a whole warp, reference summation order; every lane returns the score */
+FPT_D double fpt_warp_css_score(const double *X, double *stage, const unsigned short *lab, int asize, int bsize, int lane) {
+    double bet = fpt_observed_chain(X, stage, 0, asize, bsize, lane, lab);
+    const double wa0 = asize > 1 ? fpt_observed_chain(X, stage, 1, asize, bsize, lane, lab) : 0.0;
+    const double wb0 = bsize > 1 ? fpt_observed_chain(X, stage, 2, asize, bsize, lane, lab) : 0.0;
+    bet = __ddiv_rn(bet, (double)((long long)asize * bsize));
+    const double wa = asize > 1 ? __ddiv_rn(wa0, (double)((long long)asize * asize * (asize - 1))) : 0.0;
+    const double wb = bsize > 1 ? __ddiv_rn(wb0, (double)((long long)bsize * bsize * (bsize - 1))) : 0.0;
+    return __shfl_sync(FPT_FULL_MASK, __dsub_rn(bet, __dmul_rn((double)(asize + bsize), __dadd_rn(wa, wb))), 0);
+}
+
+__global__ void __launch_bounds__(FPT_OBS_WARPS * 32)
+fpt_css_observed_kernel(const double *__restrict__ Xall, int m, int asize, int bsize, long long nwin,
+                        const unsigned char *__restrict__ status, double *__restrict__ out_score) {
+    FPT_DYN_SMEM(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *X = reinterpret_cast<double *>(smem) + (size_t)warp * (2 * m + 32);
+    double *stage = X + 2 * m;
+    for (long long w = (long long)blockIdx.x * FPT_OBS_WARPS + warp; w < nwin; w += (long long)gridDim.x * FPT_OBS_WARPS) {
+        if (status[w] != FPT_WIN_SCORED) continue;
+        __syncwarp();
+        for (int e = lane; e < 2 * m; e += 32) X[e] = Xall[(size_t)w * 2 * m + e];
+        __syncwarp();
+        const double sc = fpt_warp_css_score(X, stage, nullptr, asize, bsize, lane);
+        if (lane == 0) out_score[w] = sc;
+    }
+}
+
+/* diagnostic: SM cycles thread 0 spent per phase, summed over CTAs and windows (distance pass, observed score, shuffles,
+   membership rows, contraction, decisions); read and reset by fpt_debug_umma_phases() */
+__device__ unsigned long long fpt_umma_phase_cycles[8];
+#define FPT_UMMA_MARK(slot) do { if (tid == 0) { const long long now_ = clock64(); atomicAdd(&fpt_umma_phase_cycles[slot], (unsigned long long)(now_ - t_mark)); t_mark = now_; } } while (0)
 
 __global__ void __launch_bounds__(FPT_UMMA_THREADS, 1)
 fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int bsize, long long wbase, long long nwin,
@@ -74,11 +196,10 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
     double *X = (double *)(smem + off); off += (size_t)2 * m * 8;
     uint2 *rtab = (uint2 *)(smem + off); off += (size_t)(m + 1) * 8;
     long long *wsum = (long long *)(smem + off); off += (size_t)2 * FPT_UMMA_BATCH * 8;
+    double *stage = (double *)(smem + off) + 32 * warp; off += (size_t)(FPT_UMMA_THREADS / 32) * 32 * 8;
     int *hit_s = (int *)(smem + off); off += (size_t)FPT_UMMA_BATCH * 4;
     int *scan = (int *)(smem + off);
     unsigned char *gs = gscratch + (size_t)blockIdx.x * gscratch_per_cta;
-    double *dist = (double *)gs; gs += ((size_t)m * m * 8 + 255) & ~(size_t)255;
-    unsigned *q = (unsigned *)gs; gs += ((size_t)m * m * 4 + 255) & ~(size_t)255;
     unsigned char *qd = gs; gs += (size_t)FPT_UMMA_DIGITS * np * kp;
     unsigned short *labels = (unsigned short *)gs;
     const size_t qd_digit = (size_t)np * kp;
@@ -105,10 +226,11 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
     unsigned long long rechecks = 0;
     const int rbytes = fpt_umma_rbytes(m);
     const int rows_fit = min(FPT_UMMA_BATCH, (int)(shuf_bytes / (size_t)rbytes));
-    const int myrow = lane * 8 + warp;                          /* shuffle rows dealt over all eight warps */
+    const int myrow = tid;                                      /* shuffle rows: consecutive lanes, rows an odd word count apart */
 
     for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
         if (status[w] != FPT_WIN_SCORED) continue;
+        long long t_mark = clock64();
         for (int e = tid; e < 2 * m; e += T) X[e] = Xall[(size_t)w * 2 * m + e];
         __syncthreads();
         /* surrogate scale from the bounding box of the embedding (known before the distances are) */
@@ -134,8 +256,7 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
         const double dmax = s_dmax;
         const bool scale_ok = (dmax > 0.0) && (dmax < 1e300);
         const double S = scale_ok ? (double)(1u << qbits) / dmax : 0.0;
-        /* one pass: distances (symmetric bit for bit, written transposed so that a warp stores consecutive addresses),
-           q, and the four digit matrices in the tile layout. Thread order: 4 bytes of k, then the row n, then 16 bytes of k:
+        /* one pass: distances (calc_dist) and the four digit matrices of their quantised values in the tile layout. Thread order: 4 bytes of k, then the row n, then 16 bytes of k:
            a warp fills one 128-byte core matrix per digit. */
         int bad = 0;
         const int nquads = (kp >> 4) * np * 4;
@@ -152,10 +273,8 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
                         const double dx = __dsub_rn(xn, X[2 * k]), dy = __dsub_rn(yn, X[2 * k + 1]);
                         d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
                     }
-                    dist[(size_t)k * m + n] = d;
                     if (!(d == d)) bad = 1;
                     const unsigned qv = (scale_ok && d == d) ? (unsigned)__double2ll_rn(d * S) : 0u;
-                    q[(size_t)k * m + n] = qv;
                     w0 |= (qv & 0xffu) << (8 * b); w1 |= ((qv >> 8) & 0xffu) << (8 * b);
                     w2 |= ((qv >> 16) & 0xffu) << (8 * b); w3 |= (qv >> 24) << (8 * b);
                 }
@@ -169,7 +288,9 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
         }
         fpt_fence_proxy_async();                                /* the digit matrices are read back by bulk copies */
         bad = __syncthreads_or(bad);
-        const double score = fpt_css_score_identity(dist, m, asize, bsize, reinterpret_cast<double *>(tileA), (int)(shuf_bytes >> 3));
+        FPT_UMMA_MARK(0);
+        const double score = out_score[w];                      /* fpt_css_observed_kernel ran before this kernel */
+        FPT_UMMA_MARK(1);
         const bool use_surrogate = scale_ok && !bad && (score == score) && (fabs(score) < 1e300);
         const double a_ = (double)asize, b_ = (double)bsize;
         const double wterm = (asize > 1 ? 1.0 / (a_ * a_) : 0.0) + (bsize > 1 ? 1.0 / (b_ * b_) : 0.0);
@@ -192,39 +313,52 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
             for (int base = 0; base < nvalid; base += rows_fit) {
                 const int nb = min(rows_fit, nvalid - base);
                 if (myrow < nb)
-                    fpt_generate_labels<unsigned short>(reinterpret_cast<unsigned short *>(tileA + (size_t)myrow * rbytes), m, rtab,
-                                                        fpt_lcg_skip(st_win, (uint64_t)(ndone + base + myrow) * (uint64_t)draws));
+                    fpt_umma_shuffle(reinterpret_cast<unsigned short *>(tileA + (size_t)myrow * rbytes), m, rtab,
+                                     fpt_lcg_skip(st_win, (uint64_t)(ndone + base + myrow) * (uint64_t)draws));
                 __syncthreads();
-                for (int e = tid; e < nb * m; e += T) {
-                    const int rr = e / m, col = e - rr * m;
-                    labels[(size_t)(base + rr) * m + col] = reinterpret_cast<const unsigned short *>(tileA + (size_t)rr * rbytes)[col];
+                /* one warp per row: labels out to the batch's global rows, and the two adjacent-pair sums of the surrogate
+                   from the embedding itself (the same quantised values the distance pass stores, no gathers) */
+                for (int rr = warp; rr < nb; rr += T >> 5) {
+                    const unsigned short *row = reinterpret_cast<const unsigned short *>(tileA + (size_t)rr * rbytes);
+                    unsigned short *orow = labels + (size_t)(base + rr) * m;
+                    long long sa = 0, sb = 0;
+#pragma unroll 4
+                    for (int col = lane; col < m; col += 32) {
+                        const int c = row[col], pc = row[col > 0 ? col - 1 : 0];
+                        orow[col] = (unsigned short)c;
+                        const long long qv = use_surrogate ? (long long)fpt_umma_q(X, c, pc, S) : 0;
+                        sa += (col != 0 && col < asize) ? qv : 0;
+                        sb += (col > asize) ? qv : 0;
+                    }
+                    for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(FPT_FULL_MASK, sa, o); sb += __shfl_xor_sync(FPT_FULL_MASK, sb, o); }
+                    if (lane == 0) { wsum[base + rr] = sa; wsum[FPT_UMMA_BATCH + base + rr] = sb; }
                 }
                 __syncthreads();
             }
-            /* membership rows of the smaller group (A operand) and the two adjacent-pair sums: thread (p, half) walks the
-               first or the second group of permutation p */
+            FPT_UMMA_MARK(2);
+            /* membership rows of the smaller group (the A operand): one sweep over its labels, a byte store each */
             for (int e = tid; e < (FPT_UMMA_BATCH * kp) >> 4; e += T) reinterpret_cast<uint4 *>(tileA)[e] = make_uint4(0u, 0u, 0u, 0u);
+            if (tid < FPT_UMMA_BATCH) hit_s[tid] = 0;
             __syncthreads();
-            {
-                const int p = tid & (FPT_UMMA_BATCH - 1), half = tid >> 7;
-                long long sum = 0;
-                if (p < nvalid) {
-                    const unsigned short *o = labels + (size_t)p * m + (half ? asize : 0);
-                    const int cnt = half ? bsize : asize;
-                    const bool mark = use_surrogate && ((half == 0) == (use_a != 0));
-                    int prev = o[0];
-                    if (mark) tileA[fpt_umma_tile_off(FPT_UMMA_BATCH, p, prev)] = 1;
-                    for (int i = 1; i < cnt; i++) {
-                        const int c = o[i];
-                        if (mark) tileA[fpt_umma_tile_off(FPT_UMMA_BATCH, p, c)] = 1;
-                        sum += (long long)q[(size_t)prev * m + c]; prev = c;
+            if (use_surrogate) {
+                const int lo = use_a ? 0 : asize, cnt = use_a ? asize : bsize;
+                const int total = nvalid * cnt;
+                for (int e0 = tid; e0 < total; e0 += 8 * T) {
+                    int pp[8], cc[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int e = e0 + u * T;
+                        pp[u] = e < total ? e / cnt : -1;
+                        cc[u] = e < total ? (int)labels[(size_t)pp[u] * m + lo + (e - pp[u] * cnt)] : 0;
                     }
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (pp[u] >= 0) tileA[fpt_umma_tile_off(FPT_UMMA_BATCH, pp[u], cc[u])] = 1;
                 }
-                wsum[half * FPT_UMMA_BATCH + p] = sum;
-                if (tid < FPT_UMMA_BATCH) hit_s[tid] = 0;
             }
             fpt_fence_proxy_async();                            /* rows and ring space: generic writes before async reads / writes */
             __syncthreads();
+            FPT_UMMA_MARK(3);
             if (use_surrogate) {
                 if (warp == 0) {
                     if (lane == 0) {                            /* producer: digit tiles into the ring */
@@ -298,26 +432,30 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
                             acc_it++;
                         }
                     }
-                    if (p < nvalid) {
-                        long long bet = 0;
+                    long long bet = 0;
 #pragma unroll
-                        for (int d = FPT_UMMA_DIGITS; d--;) bet = (bet << 8) + (long long)acc[d];
-                        const double approx = (double)bet * c_bet - (a_ + b_) * ((double)wsum[p] * c_wa + (double)wsum[FPT_UMMA_BATCH + p] * c_wb);
-                        const double diff = approx - score;
-                        int hit = diff > 0.0;
-                        if (!(fabs(diff) > E)) {
-                            const unsigned short *o = labels + (size_t)p * m;
-                            hit = fpt_css_score<unsigned short>(dist, m, o, o + asize, asize, bsize) >= score ? 1 : 0;
-                            rechecks++;
-                        }
-                        hit_s[p] = hit;
+                    for (int d = FPT_UMMA_DIGITS; d--;) bet = (bet << 8) + (long long)acc[d];
+                    const double approx = (double)bet * c_bet - (a_ + b_) * ((double)wsum[p] * c_wa + (double)wsum[FPT_UMMA_BATCH + p] * c_wb);
+                    const double diff = approx - score;
+                    int hit = diff > 0.0;
+                    /* within E of the observed score: the whole warp re-scores that permutation in the reference's order */
+                    unsigned need = __ballot_sync(FPT_FULL_MASK, p < nvalid && !(fabs(diff) > E));
+                    while (need) {
+                        const int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        const double sc = fpt_warp_css_score(X, stage, labels + (size_t)(wq * 32 + src) * m, asize, bsize, lane);
+                        if (lane == src) { hit = sc >= score ? 1 : 0; rechecks++; }
                     }
+                    if (p < nvalid) hit_s[p] = hit;
                 }
-            } else if (tid < nvalid) {
-                const unsigned short *o = labels + (size_t)tid * m;
-                hit_s[tid] = fpt_css_score<unsigned short>(dist, m, o, o + asize, asize, bsize) >= score ? 1 : 0;
+            } else {                                            /* no surrogate (NaN embedding ...): every permutation exactly */
+                for (int p = warp; p < nvalid; p += T >> 5) {
+                    const double sc = fpt_warp_css_score(X, stage, labels + (size_t)p * m, asize, bsize, lane);
+                    if (lane == 0) hit_s[p] = sc >= score ? 1 : 0;
+                }
             }
             __syncthreads();
+            FPT_UMMA_MARK(4);
             const int hit = tid < FPT_UMMA_BATCH ? hit_s[tid] : 0;
             int chunk_hits = 0;
             const int hincl = fpt_block_scan_incl(hit, scan, &chunk_hits);
@@ -328,6 +466,7 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
             if (s_flag >= 0) { ndone += s_flag + 1; hits = treshold; stopped = true; }
             else { hits += chunk_hits; ndone += nvalid; }
             __syncthreads();
+            FPT_UMMA_MARK(5);
         }
         if (tid == 0) {
             out_score[w] = score;

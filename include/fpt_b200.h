@@ -60,8 +60,13 @@ void fpt_set_perm_mode(int chain);
 int fpt_get_perm_mode(void);
 /* Cohorts too large for the all-in-shared-memory permutation kernel (m > 250), independent shuffles: 1 (default) scores a
    batch of 128 permutations as one u8 contraction on tcgen05 / tensor memory (csrc/fpt_css_perm_umma.cuh, m <= 1024),
-   0 keeps the general kernel (csrc/fpt_css_perm_large.cuh). Same decisions either way; the switch exists for the parity tests. */
+   0 keeps the general kernel (csrc/fpt_css_perm_large.cuh), 2 is the tensor-memory kernel with a 10-bit surrogate, which sends
+   a large share of the permutations through the exact re-scoring. Same decisions in every mode; the switch exists for the
+   parity tests. */
 void fpt_set_perm_large_kernel(int tensor_memory);
+/* diagnostic: SM cycles per phase of the tensor-memory permutation kernel since the last call, summed over CTAs and windows
+   (0 distance pass, 1 observed score, 2 shuffles, 3 membership rows, 4 contraction, 5 decisions); synchronises the device */
+int fpt_debug_umma_phases(unsigned long long *out8);
 /* number of permutations since the last call whose integer surrogate score could not decide `permuted >= observed` and
    were re-scored in the reference's summation order (diagnostic; synchronises the device); -1 on error */
 long long fpt_css_perm_rechecks(void);

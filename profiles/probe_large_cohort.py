@@ -16,3 +16,7 @@ for runs in (1000,):
     buf=C.create_string_buffer(8192); lib.fpt_profile_summary(buf,8192)
     print(runs, 'windows', nwin, 'scored', int((wr==1).sum()) if wr is not None else None, 'sec', round(dt,2), buf.value.decode())
     print(s[:4], p[:4])
+    ph=(C.c_ulonglong*8)()
+    if lib.fpt_debug_umma_phases(ph)==0:
+        tot=sum(ph) or 1
+        print('umma phase share (dist, observed, shuffle, rows, contraction, decide):', [round(x/tot,3) for x in ph][:6], 'Mcycles per window', round(tot/1e6/max(1,nwin),2))
