@@ -54,11 +54,24 @@ FPT_HD size_t fpt_umma_smem_bytes(int m) {
 }
 
 
+/* Distance for the SURROGATE only (the exact paths use the IEEE square root): single-precision reciprocal square root,
+   one Newton step on it and one Heron step on the root — eight fp64 operations instead of the ~30 of __dsqrt_rn. Relative
+   error against the reference's distance below 2^-50 (the squared length by one fma: 1.5 ulp; the root after the Heron step:
+   the square of 1.5 * 2^-42 plus two roundings), which the error bound E accounts for. Symmetric in its two points bit for
+   bit (only squares of the differences enter), so every stage that needs q(i, j) computes the same integer. */
+FPT_D double fpt_umma_dist(double xi, double yi, double xj, double yj) {
+    const double dx = xi - xj, dy = yi - yj;
+    const double x = fma(dx, dx, dy * dy);
+    if (!(x > 1e-30 && x < 1e30)) return __dsqrt_rn(x);         /* zero, denormal-ish, huge, NaN: the IEEE path */
+    double y = (double)rsqrtf((float)x);
+    const double e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    const double g = x * y;
+    return fma(0.5 * y, fma(-g, g, x), g);
+}
 /* quantised distance between individuals i and j of the embedding X: the value the distance pass stores for (i, j) */
 FPT_D unsigned fpt_umma_q(const double *X, int i, int j, double S) {
-    const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
-    const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-    return (unsigned)__double2ll_rn(d * S);
+    return (unsigned)__double2ll_rn(fpt_umma_dist(X[2 * i], X[2 * i + 1], X[2 * j], X[2 * j + 1]) * S);
 }
 
 /* Fisher-Yates of fresh identity labels (css.c:700-706) like fpt_generate_labels, four draws ahead of the swaps: the draws
@@ -226,7 +239,6 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
     unsigned long long rechecks = 0;
     const int rbytes = fpt_umma_rbytes(m);
     const int rows_fit = min(FPT_UMMA_BATCH, (int)(shuf_bytes / (size_t)rbytes));
-    const int myrow = tid;                                      /* shuffle rows: consecutive lanes, rows an odd word count apart */
 
     for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
         if (status[w] != FPT_WIN_SCORED) continue;
@@ -256,7 +268,7 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
         const double dmax = s_dmax;
         const bool scale_ok = (dmax > 0.0) && (dmax < 1e300);
         const double S = scale_ok ? (double)(1u << qbits) / dmax : 0.0;
-        /* one pass: distances (calc_dist) and the four digit matrices of their quantised values in the tile layout. Thread order: 4 bytes of k, then the row n, then 16 bytes of k:
+        /* one pass: surrogate distances and the four digit matrices of their quantised values in the tile layout. Thread order: 4 bytes of k, then the row n, then 16 bytes of k:
            a warp fills one 128-byte core matrix per digit. */
         int bad = 0;
         const int nquads = (kp >> 4) * np * 4;
@@ -268,11 +280,7 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
                 for (int b = 0; b < 4; b++) {
                     const int k = k4 + b;
                     if (k >= m) break;
-                    double d = 0.0;
-                    if (k != n) {                               /* calc_dist, css.c:573-587 */
-                        const double dx = __dsub_rn(xn, X[2 * k]), dy = __dsub_rn(yn, X[2 * k + 1]);
-                        d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-                    }
+                    const double d = k != n ? fpt_umma_dist(xn, yn, X[2 * k], X[2 * k + 1]) : 0.0;
                     if (!(d == d)) bad = 1;
                     const unsigned qv = (scale_ok && d == d) ? (unsigned)__double2ll_rn(d * S) : 0u;
                     w0 |= (qv & 0xffu) << (8 * b); w1 |= ((qv >> 8) & 0xffu) << (8 * b);
@@ -294,8 +302,9 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
         const bool use_surrogate = scale_ok && !bad && (score == score) && (fabs(score) < 1e300);
         const double a_ = (double)asize, b_ = (double)bsize;
         const double wterm = (asize > 1 ? 1.0 / (a_ * a_) : 0.0) + (bsize > 1 ? 1.0 / (b_ * b_) : 0.0);
-        /* |surrogate - reference score| <= E, see fpt_css_perm_large.cuh */
-        const double E = use_surrogate ? (0.5 / S) * (1.0 + (a_ + b_) * wterm) * 1.0000001 +
+        /* |surrogate - reference score| <= E, see fpt_css_perm_large.cuh; here q is the rounding of a distance that is itself
+           within 2^-50 of the reference's, i.e. |q / S - d| <= (0.5 + 2^-19) / S: the factor 1.00001 covers it */
+        const double E = use_surrogate ? (0.5 / S) * (1.0 + (a_ + b_) * wterm) * 1.00001 +
                                          8.0 * 1.2e-16 * dmax * (a_ * b_ + 2.0 * (a_ + b_)) : 0.0;
         const double invS = use_surrogate ? 1.0 / S : 0.0;
         const double c_bet = invS / (a_ * b_);
@@ -312,10 +321,14 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
                memory: as many label rows at a time as the tile space holds, copied out to the batch's global rows. */
             for (int base = 0; base < nvalid; base += rows_fit) {
                 const int nb = min(rows_fit, nvalid - base);
+                /* rows dealt over all eight warps, consecutive lanes on consecutive rows (an odd word count apart: no bank
+                   conflicts on equal indices); two half-empty warps per scheduler hide each other's latency */
+                const int rpw = (nb + (T >> 5) - 1) / (T >> 5), myrow = lane < rpw ? warp * rpw + lane : nb;
                 if (myrow < nb)
                     fpt_umma_shuffle(reinterpret_cast<unsigned short *>(tileA + (size_t)myrow * rbytes), m, rtab,
                                      fpt_lcg_skip(st_win, (uint64_t)(ndone + base + myrow) * (uint64_t)draws));
                 __syncthreads();
+                FPT_UMMA_MARK(2);
                 /* one warp per row: labels out to the batch's global rows, and the two adjacent-pair sums of the surrogate
                    from the embedding itself (the same quantised values the distance pass stores, no gathers) */
                 for (int rr = warp; rr < nb; rr += T >> 5) {
@@ -335,7 +348,7 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
                 }
                 __syncthreads();
             }
-            FPT_UMMA_MARK(2);
+            FPT_UMMA_MARK(6);
             /* membership rows of the smaller group (the A operand): one sweep over its labels, a byte store each */
             for (int e = tid; e < (FPT_UMMA_BATCH * kp) >> 4; e += T) reinterpret_cast<uint4 *>(tileA)[e] = make_uint4(0u, 0u, 0u, 0u);
             if (tid < FPT_UMMA_BATCH) hit_s[tid] = 0;

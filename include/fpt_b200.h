@@ -65,7 +65,8 @@ int fpt_get_perm_mode(void);
    parity tests. */
 void fpt_set_perm_large_kernel(int tensor_memory);
 /* diagnostic: SM cycles per phase of the tensor-memory permutation kernel since the last call, summed over CTAs and windows
-   (0 distance pass, 1 observed score, 2 shuffles, 3 membership rows, 4 contraction, 5 decisions); synchronises the device */
+   (0 distance pass, 1 hand-over of the observed score, 2 shuffles, 3 membership rows, 4 contraction, 5 decisions, 6 label copy-out
+   and adjacent-pair sums); synchronises the device */
 int fpt_debug_umma_phases(unsigned long long *out8);
 /* number of permutations since the last call whose integer surrogate score could not decide `permuted >= observed` and
    were re-scored in the reference's summation order (diagnostic; synchronises the device); -1 on error */

@@ -19,4 +19,4 @@ for runs in (1000,):
     ph=(C.c_ulonglong*8)()
     if lib.fpt_debug_umma_phases(ph)==0:
         tot=sum(ph) or 1
-        print('umma phase share (dist, observed, shuffle, rows, contraction, decide):', [round(x/tot,3) for x in ph][:6], 'Mcycles per window', round(tot/1e6/max(1,nwin),2))
+        print('umma phase share (dist, observed, shuffle, rows, contraction, decide, sweep):', [round(x/tot,3) for x in ph][:7], 'Mcycles per window', round(tot/1e6/max(1,nwin),2))
