@@ -519,7 +519,8 @@ LARGE = dict(seed0=900, asize=500, bsize=500, windows=592, wsize=50_000, wstep=5
 
 def bench_large_cohort(lib_mod, args):
     """BASELINE configs[4] cohort (500+500 individuals, 50 kb windows, ~167 SNPs per window) on a slice of windows: the
-    large-cohort kernels (Lanczos classical MDS, general permutation kernel with the tensor-core surrogate). Timed through
+    large-cohort kernels (Lanczos classical MDS; observed scores by a warp per window; permutation test with the between-group
+    sums of 128 permutations as one tcgen05 u8 contraction, accumulators in tensor memory). Timed through
     the host scan entry with compact int8 inputs; the per-kernel split comes from the library's own CUDA events."""
     import ctypes as C
     import fpt_b200.api as api
@@ -542,7 +543,25 @@ def bench_large_cohort(lib_mod, args):
     lib.fpt_profile_enable(0)
     scored = int((wr == 1).sum())
     dev_ms = sum(v["ms"] for v in prof.values())
-    return {"metric": "css_windows_per_sec_1000perms", "unit": "windows/s", "value": scored / (dev_ms * 1e-3),
+    # the permutation kernel's contraction (csrc/fpt_css_perm_umma.cuh): per window ceil(mcr / 128) batches of a
+    # 128 x Np x Kp u8 product per base-256 digit (4 digits), Np / Kp = m padded to 256 / 128
+    m = LARGE["asize"] + LARGE["bsize"]
+    npad, kpad, batches = -(-m // 256) * 256, -(-m // 128) * 128, -(-LARGE["mcr"] // 128)
+    macs = float(scored) * batches * 128 * npad * kpad * 4
+    perm_ms = prof.get("css_perm", {}).get("ms", 0.0)
+    # kind::i8 rate on this part, from the ncu capture of this kernel (profiles/r1_css_perm_umma_raw.csv): the imma sub-pipe is
+    # busy 512 cycles per 128 x 256 x 32 instruction = 2048 MAC/clk/SM (half the bf16 rate), times 148 SMs at the maximum SM clock
+    i8_peak = 2048.0 * 2.0 * 148 * 1.965e9 / 1e12
+    tensor = {"kernel": "css_perm (fpt_css_perm_umma_kernel)", "bound": "tensor", "unit": "TOP/s (u8 x u8 -> s32)",
+              "achieved": 2.0 * macs / (perm_ms * 1e-3) / 1e12 if perm_ms > 0 else None,
+              "peak": i8_peak,
+              "peak_source": "tcgen05 kind::i8 issue rate measured with ncu on this kernel (512 pipe cycles per 128x256x32 MMA = 2048 MAC/clk/SM) x 148 SMs x 1965 MHz; "
+                             "MEASURED_PEAKS.json has no 8-bit figure",
+              "note": "whole-kernel time: the contraction is ~20 % of it and runs with the imma sub-pipe busy throughout (tensor-pipe bound); the rest is SIMT "
+                      "work (surrogate distance pass, label shuffles, adjacent-pair sweep, membership rows)"}
+    if tensor["achieved"] is not None:
+        tensor["frac"] = tensor["achieved"] / tensor["peak"]
+    return {"metric": "css_windows_per_sec_1000perms", "unit": "windows/s", "value": scored / (dev_ms * 1e-3), "roofline_tensor": tensor,
             "e2e": {"value": scored / min(secs[1:]), "unit": "windows/s", "api": "fpt_css_scan (host int8 codes)",
                     "h2d_bytes_per_step": int(ch["acodes"].nbytes + ch["bcodes"].nbytes + ch["pos"].nbytes)},
             "config": {"workload": "CSS scan, %d windows of BASELINE configs[4]: 500+500 individuals, 50 kb windows, ~%d SNPs per window, "

@@ -92,6 +92,44 @@ FPT_D void fpt_cta_symv(const double *__restrict__ B, int m, const double *x, do
     }
 }
 
+/* The same product from the COMPACT form of B (a quarter of the bytes): B = -1/2 (S - r 1' - 1 r' + g) and S = D.D holds only
+   squares of small integers (counts of opposite homozygotes) plus one repeated real (the fill_averages value, css.c:337-366),
+   so the matrix streamed per Lanczos step is 16-bit codes — c >= 1: S = c^2, c = 0: S = v2 — and
+       y = -1/2 ( S x - r (1'x) - 1 (r'x) + g (1'x) ).
+   The integer c^2 becomes a double by the 2^52 trick (one fp64 add instead of a conversion instruction). A warp per row,
+   four rows in flight, each lane four consecutive codes (8-byte loads; m % 4 == 0). sx = 1'x and rx = r'x are given. */
+FPT_D void fpt_cta_symv_codes(const unsigned short *__restrict__ C, int m, const double *x, double *y, const double *rmean,
+                              double g, double v2, double sx, double rx) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int i = 4 * warp; i < m; i += 4 * nwarp) {
+        const int nr = m - i < 4 ? m - i : 4;
+        const unsigned short *r0 = C + (size_t)i * m;
+        const unsigned short *rr[4] = { r0, nr > 1 ? r0 + m : r0, nr > 2 ? r0 + 2 * (size_t)m : r0, nr > 3 ? r0 + 3 * (size_t)m : r0 };
+        double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
+        for (int j = 4 * lane; j < m; j += 128) {
+            uint2 cc[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) cc[r] = *reinterpret_cast<const uint2 *>(rr[r] + j);
+            const double2 xa = *reinterpret_cast<const double2 *>(x + j), xb = *reinterpret_cast<const double2 *>(x + j + 2);
+            const double xs[4] = { xa.x, xa.y, xb.x, xb.y };
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const unsigned cw[4] = { cc[r].x & 0xffffu, cc[r].x >> 16, cc[r].y & 0xffffu, cc[r].y >> 16 };
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const double sq = __hiloint2double(0x43300000, (int)(cw[k] * cw[k])) - 4503599627370496.0;
+                    acc[r] = fma(cw[k] ? sq : v2, xs[k], acc[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) acc[r] = fpt_warp_sum(acc[r]);
+        if (lane == 0) {
+            for (int r = 0; r < nr; r++) y[i + r] = -0.5 * (((acc[r] - rmean[i + r] * sx) - rx) + g * sx);
+        }
+    }
+}
+
 /* one classical Gram-Schmidt pass of w against the nq basis vectors Q[0..nq) (rows of length m in global memory);
    the projections are ADDED to h so that two passes accumulate the exact coefficients */
 FPT_D void fpt_cta_cgs_pass(const double *__restrict__ Q, int nq, int m, double *w, double *h, double *hpass) {
@@ -120,26 +158,50 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
     const size_t mm = (size_t)m * m;
     __shared__ double sh_val[4];
     __shared__ int sh_flag;
-    /* ---- 1. double centring in place (same closed form as the small-cohort paths) */
-    for (size_t e = tid; e < mm; e += T) { const double d = A[e]; A[e] = d * d; }
-    __syncthreads();
+    /* ---- 1. row means of S = D.D and the grand mean (same closed form as the small-cohort paths); on the way, whether
+       the matrix has the compact form: every entry a count in 1..65535 or the fill value v0 (the diagonal always is) */
+    const double v0 = A[0];
+    int compact = (m & 3) == 0;
     {
         const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
         for (int i = warp; i < m; i += nwarp) {                /* row sums, coalesced */
             const double *row = A + (size_t)i * m;
             double acc = 0.0;
-            for (int j = lane; j < m; j += 32) acc += row[j];
+            for (int j = lane; j < m; j += 32) {
+                const double d = row[j];
+                acc += d * d;
+                if (!(d == v0 || (d >= 1.0 && d <= 65535.0 && d == floor(d)))) compact = 0;
+            }
             acc = fpt_warp_sum(acc);
             if (lane == 0) s.rmean[i] = acc / m;
         }
     }
-    __syncthreads();
+    compact = __syncthreads_and(compact);
     double g = 0.0;
     for (int i = tid; i < m; i += T) g += s.rmean[i];
     g = fpt_block_sum(g, s.sc.red) / m;
-    for (size_t e = tid; e < mm; e += T) {
-        const int i = (int)(e / m), j = (int)(e - (size_t)i * m);
-        A[e] = -0.5 * (((A[e] - s.rmean[i]) - s.rmean[j]) + g);
+    unsigned short *codes = reinterpret_cast<unsigned short *>(A);
+    const double v2 = v0 * v0;
+    if (compact) {
+        /* in place: the codes of a block of 8 T entries land in the first quarter of the bytes those entries occupied,
+           which only the block itself has still to read — hence the barrier between its loads and its stores */
+        for (size_t base = 0; base < mm; base += (size_t)8 * T) {
+            double d[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const size_t e = base + tid + (size_t)u * T; d[u] = e < mm ? A[e] : 0.0; }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const size_t e = base + tid + (size_t)u * T;
+                if (e < mm) codes[e] = (d[u] >= 1.0 && d[u] == floor(d[u])) ? (unsigned short)d[u] : (unsigned short)0;
+            }
+        }
+    } else {
+        for (size_t e = tid; e < mm; e += T) {
+            const int i = (int)(e / m), j = (int)(e - (size_t)i * m);
+            const double d = A[e];
+            A[e] = -0.5 * (((d * d - s.rmean[i]) - s.rmean[j]) + g);
+        }
     }
     __syncthreads();
 
@@ -161,7 +223,15 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
     double lam1 = 0.0, lam2 = 0.0, lam3 = 0.0, bnorm = 0.0;
     int degenerate = 0;                 /* 1: B q0 = 0 or non-finite */
     for (int j = 0; j < cap; j++) {
-        fpt_cta_symv(A, m, s.q, s.w);
+        if (compact) {
+            double sx = 0.0, rx = 0.0;
+            for (int e = tid; e < m; e += T) { const double v = s.q[e]; sx += v; rx += s.rmean[e] * v; }
+            sx = fpt_block_sum(sx, s.sc.red);
+            rx = fpt_block_sum(rx, s.sc.red);
+            fpt_cta_symv_codes(codes, m, s.q, s.w, s.rmean, g, v2, sx, rx);
+        } else {
+            fpt_cta_symv(A, m, s.q, s.w);
+        }
         for (int i = tid; i <= j; i += T) s.h[i] = 0.0;
         __syncthreads();
         fpt_cta_cgs_pass(Q, j + 1, m, s.w, s.h, s.ew.lu);            /* lu is free between tridiagonal solves */

@@ -114,6 +114,14 @@ static inline int __syncthreads_or(int p) {
     return r;
 }
 
+static inline int __syncthreads_and(int p) { return !__syncthreads_or(!p); }
+static inline double __hiloint2double(int hi, int lo) {
+    unsigned long long bits = ((unsigned long long)(unsigned)hi << 32) | (unsigned long long)(unsigned)lo;
+    double d;
+    memcpy(&d, &bits, 8);
+    return d;
+}
+
 /* arithmetic intrinsics (the emu build uses -ffp-contract=off, so plain operators round once) */
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
