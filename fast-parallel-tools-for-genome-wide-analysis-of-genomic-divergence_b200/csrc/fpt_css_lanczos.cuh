@@ -97,28 +97,34 @@ FPT_D void fpt_cta_symv(const double *__restrict__ B, int m, const double *x, do
    so the matrix streamed per Lanczos step is 16-bit codes — c >= 1: S = c^2, c = 0: S = v2 — and
        y = -1/2 ( S x - r (1'x) - 1 (r'x) + g (1'x) ).
    The integer c^2 becomes a double by the 2^52 trick (one fp64 add instead of a conversion instruction). A warp per row,
-   four rows in flight, each lane four consecutive codes (8-byte loads; m % 4 == 0). sx = 1'x and rx = r'x are given. */
-FPT_D void fpt_cta_symv_codes(const unsigned short *__restrict__ C, int m, const double *x, double *y, const double *rmean,
+   four rows in flight, each lane one 8-byte load of consecutive codes: four 16-bit ones (m % 4 == 0) or, when no count exceeds
+   255, eight 8-bit ones (m % 8 == 0). sx = 1'x and rx = r'x are given. */
+template <typename CodeT>
+FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, const double *x, double *y, const double *rmean,
                               double g, double v2, double sx, double rx) {
+    constexpr int PER = 8 / (int)sizeof(CodeT);                 /* codes per 8-byte load: 4 or 8 */
+    constexpr int BITS = 8 * (int)sizeof(CodeT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int i = 4 * warp; i < m; i += 4 * nwarp) {
         const int nr = m - i < 4 ? m - i : 4;
-        const unsigned short *r0 = C + (size_t)i * m;
-        const unsigned short *rr[4] = { r0, nr > 1 ? r0 + m : r0, nr > 2 ? r0 + 2 * (size_t)m : r0, nr > 3 ? r0 + 3 * (size_t)m : r0 };
+        const CodeT *r0 = C + (size_t)i * m;
+        const CodeT *rr[4] = { r0, nr > 1 ? r0 + m : r0, nr > 2 ? r0 + 2 * (size_t)m : r0, nr > 3 ? r0 + 3 * (size_t)m : r0 };
         double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
-        for (int j = 4 * lane; j < m; j += 128) {
+        for (int j = PER * lane; j < m; j += 32 * PER) {
             uint2 cc[4];
 #pragma unroll
             for (int r = 0; r < 4; r++) cc[r] = *reinterpret_cast<const uint2 *>(rr[r] + j);
-            const double2 xa = *reinterpret_cast<const double2 *>(x + j), xb = *reinterpret_cast<const double2 *>(x + j + 2);
-            const double xs[4] = { xa.x, xa.y, xb.x, xb.y };
+            double xs[PER];
+#pragma unroll
+            for (int k = 0; k < PER; k += 2) { const double2 xv = *reinterpret_cast<const double2 *>(x + j + k); xs[k] = xv.x; xs[k + 1] = xv.y; }
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                const unsigned cw[4] = { cc[r].x & 0xffffu, cc[r].x >> 16, cc[r].y & 0xffffu, cc[r].y >> 16 };
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const double sq = __hiloint2double(0x43300000, (int)(cw[k] * cw[k])) - 4503599627370496.0;
-                    acc[r] = fma(cw[k] ? sq : v2, xs[k], acc[r]);
+                for (int k = 0; k < PER; k++) {
+                    const unsigned word = (k * BITS) < 32 ? cc[r].x : cc[r].y;
+                    const unsigned c = (word >> ((k * BITS) & 31)) & ((1u << BITS) - 1u);
+                    const double sq = __hiloint2double(0x43300000, (int)(c * c)) - 4503599627370496.0;
+                    acc[r] = fma(c ? sq : v2, xs[k], acc[r]);
                 }
             }
         }
@@ -161,7 +167,7 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
     /* ---- 1. row means of S = D.D and the grand mean (same closed form as the small-cohort paths); on the way, whether
        the matrix has the compact form: every entry a count in 1..65535 or the fill value v0 (the diagonal always is) */
     const double v0 = A[0];
-    int compact = (m & 3) == 0;
+    int compact = (m & 3) == 0, narrow = (m & 7) == 0;          /* narrow: every count fits a byte */
     {
         const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
         for (int i = warp; i < m; i += nwarp) {                /* row sums, coalesced */
@@ -171,16 +177,19 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
                 const double d = row[j];
                 acc += d * d;
                 if (!(d == v0 || (d >= 1.0 && d <= 65535.0 && d == floor(d)))) compact = 0;
+                if (d > 255.0) narrow = 0;
             }
             acc = fpt_warp_sum(acc);
             if (lane == 0) s.rmean[i] = acc / m;
         }
     }
     compact = __syncthreads_and(compact);
+    narrow = __syncthreads_and(narrow);
     double g = 0.0;
     for (int i = tid; i < m; i += T) g += s.rmean[i];
     g = fpt_block_sum(g, s.sc.red) / m;
     unsigned short *codes = reinterpret_cast<unsigned short *>(A);
+    unsigned char *codes8 = reinterpret_cast<unsigned char *>(A);
     const double v2 = v0 * v0;
     if (compact) {
         /* in place: the codes of a block of 8 T entries land in the first quarter of the bytes those entries occupied,
@@ -193,7 +202,10 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const size_t e = base + tid + (size_t)u * T;
-                if (e < mm) codes[e] = (d[u] >= 1.0 && d[u] == floor(d[u])) ? (unsigned short)d[u] : (unsigned short)0;
+                if (e < mm) {
+                    const unsigned c = (d[u] >= 1.0 && d[u] == floor(d[u])) ? (unsigned)d[u] : 0u;
+                    if (narrow) codes8[e] = (unsigned char)c; else codes[e] = (unsigned short)c;
+                }
             }
         }
     } else {
@@ -228,7 +240,8 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
             for (int e = tid; e < m; e += T) { const double v = s.q[e]; sx += v; rx += s.rmean[e] * v; }
             sx = fpt_block_sum(sx, s.sc.red);
             rx = fpt_block_sum(rx, s.sc.red);
-            fpt_cta_symv_codes(codes, m, s.q, s.w, s.rmean, g, v2, sx, rx);
+            if (narrow) fpt_cta_symv_codes<unsigned char>(codes8, m, s.q, s.w, s.rmean, g, v2, sx, rx);
+            else fpt_cta_symv_codes<unsigned short>(codes, m, s.q, s.w, s.rmean, g, v2, sx, rx);
         } else {
             fpt_cta_symv(A, m, s.q, s.w);
         }
