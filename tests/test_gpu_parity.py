@@ -296,6 +296,18 @@ def test_css_large_cohort_500_plus_500(fpt, oracle):
     assert np.array_equal(p_g, p_o)
 
 
+def test_tcgen05_plumbing_against_a_host_product():
+    """csrc/fpt_umma.cuh on its own: bulk TMA copies into shared memory, shared-memory descriptors of the K-major core-matrix
+    layout, `tcgen05.mma kind::i8` into tensor memory, `tcgen05.ld` back — a 128 x 256 x 128 u8 product equal to the host's."""
+    import os
+    import subprocess
+    probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "probes", "umma_probe")
+    if not os.path.exists(probe):
+        pytest.skip("tests/probes/umma_probe not built (__graft_entry__.build() compiles it)")
+    r = subprocess.run([probe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "UMMA_PROBE OK" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("asize,bsize,mct,mcr", [(500, 500, 300, 300), (400, 300, 7, 400), (130, 170, 1000, 1000), (513, 511, 140, 140)])
 def test_css_tensor_memory_permutation_kernel_matches_general_kernel(fpt, asize, bsize, mct, mcr):
     """Large cohorts: the tcgen05 / tensor-memory permutation kernel (csrc/fpt_css_perm_umma.cuh) takes the same decisions as
