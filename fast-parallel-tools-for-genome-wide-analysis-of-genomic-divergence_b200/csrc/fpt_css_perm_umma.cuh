@@ -269,30 +269,40 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
         const bool scale_ok = (dmax > 0.0) && (dmax < 1e300);
         const double S = scale_ok ? (double)(1u << qbits) / dmax : 0.0;
         /* one pass: surrogate distances and the four digit matrices of their quantised values in the tile layout. Thread order: 4 bytes of k, then the row n, then 16 bytes of k:
-           a warp fills one 128-byte core matrix per digit. */
+           a warp fills one 128-byte core matrix per digit; no divisions, the four k-side points stay in registers. */
         int bad = 0;
-        const int nquads = (kp >> 4) * np * 4;
-        for (int e = tid; e < nquads; e += T) {
-            const int kq = e & 3, n = (e >> 2) % np, kg = (e >> 2) / np, k4 = (kg << 4) + (kq << 2);
-            unsigned w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-            if (n < m && k4 < m) {
-                const double xn = X[2 * n], yn = X[2 * n + 1];
-                for (int b = 0; b < 4; b++) {
-                    const int k = k4 + b;
-                    if (k >= m) break;
-                    const double d = k != n ? fpt_umma_dist(xn, yn, X[2 * k], X[2 * k + 1]) : 0.0;
-                    if (!(d == d)) bad = 1;
-                    const unsigned qv = (scale_ok && d == d) ? (unsigned)__double2ll_rn(d * S) : 0u;
-                    w0 |= (qv & 0xffu) << (8 * b); w1 |= ((qv >> 8) & 0xffu) << (8 * b);
-                    w2 |= ((qv >> 16) & 0xffu) << (8 * b); w3 |= (qv >> 24) << (8 * b);
+        {
+            const int kq = tid & 3, nfirst = tid >> 2;          /* T = 256: 64 rows per sweep, np is a multiple of 64 */
+            for (int kg = 0; kg < (kp >> 4); kg++) {
+                const int k4 = (kg << 4) + (kq << 2);
+                double xk[4], yk[4];
+#pragma unroll
+                for (int b = 0; b < 4; b++) { const int k = k4 + b < m ? k4 + b : 0; xk[b] = X[2 * k]; yk[b] = X[2 * k + 1]; }
+                /* tile (n / 256, k / 128) of digit d at ((d * ntn + nt) * nkc + kc) * 32 KB */
+                const size_t kpart = (size_t)(k4 >> 7) * FPT_UMMA_STAGE + (size_t)((k4 & 127) >> 4) * (FPT_UMMA_NT * 16) + (size_t)(k4 & 15);
+                for (int n = nfirst; n < np; n += T >> 2) {
+                    unsigned w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                    if (n < m && k4 < m) {
+                        const double xn = X[2 * n], yn = X[2 * n + 1];
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const int k = k4 + b;
+                            if (k < m) {
+                                const double d = k != n ? fpt_umma_dist(xn, yn, xk[b], yk[b]) : 0.0;
+                                if (!(d == d)) bad = 1;
+                                const unsigned qv = (scale_ok && d == d) ? (unsigned)__double2ll_rn(d * S) : 0u;
+                                w0 |= (qv & 0xffu) << (8 * b); w1 |= ((qv >> 8) & 0xffu) << (8 * b);
+                                w2 |= ((qv >> 16) & 0xffu) << (8 * b); w3 |= (qv >> 24) << (8 * b);
+                            }
+                        }
+                    }
+                    const size_t toff = (size_t)(n >> 8) * nkc * FPT_UMMA_STAGE + (size_t)((n & 255) >> 3) * 128 + (size_t)(n & 7) * 16 + kpart;
+                    *reinterpret_cast<unsigned *>(qd + toff) = w0;
+                    *reinterpret_cast<unsigned *>(qd + qd_digit + toff) = w1;
+                    *reinterpret_cast<unsigned *>(qd + 2 * qd_digit + toff) = w2;
+                    *reinterpret_cast<unsigned *>(qd + 3 * qd_digit + toff) = w3;
                 }
             }
-            /* tile (n / 256, k / 128) of digit d at ((d * ntn + nt) * nkc + kc) * 32 KB */
-            const size_t toff = ((size_t)(n >> 8) * nkc + (size_t)(k4 >> 7)) * FPT_UMMA_STAGE + fpt_umma_tile_off(FPT_UMMA_NT, n & 255, k4 & 127);
-            *reinterpret_cast<unsigned *>(qd + toff) = w0;
-            *reinterpret_cast<unsigned *>(qd + qd_digit + toff) = w1;
-            *reinterpret_cast<unsigned *>(qd + 2 * qd_digit + toff) = w2;
-            *reinterpret_cast<unsigned *>(qd + 3 * qd_digit + toff) = w3;
         }
         fpt_fence_proxy_async();                                /* the digit matrices are read back by bulk copies */
         bad = __syncthreads_or(bad);
