@@ -25,7 +25,7 @@
 #include "fpt_css_perm_large.cuh"
 #include "fpt_umma.cuh"
 
-#define FPT_UMMA_THREADS 256
+#define FPT_UMMA_THREADS 512
 #define FPT_UMMA_BATCH 128                 /* permutations per contraction = MMA M */
 #define FPT_UMMA_NT 256                    /* MMA N: columns of one accumulator */
 #define FPT_UMMA_KC 128                    /* bytes of K per ring stage */
@@ -74,40 +74,44 @@ FPT_D unsigned fpt_umma_q(const double *X, int i, int j, double S) {
     return (unsigned)__double2ll_rn(fpt_umma_dist(X[2 * i], X[2 * i + 1], X[2 * j], X[2 * j + 1]) * S);
 }
 
-/* Fisher-Yates of fresh identity labels (css.c:700-706) like fpt_generate_labels, four draws ahead of the swaps: the draws
-   do not depend on the labels, so the generator's chain and the swaps' load-store chain run side by side */
+/* Fisher-Yates of fresh identity labels (css.c:700-706) like fpt_generate_labels, software-pipelined: the draws do not depend on
+   the labels, so the four draws of the NEXT group (table loads, generator steps, modulo) are issued before the four swaps of the
+   current one and the two dependency chains run side by side */
 FPT_D void fpt_umma_shuffle(unsigned short *row, int m, const uint2 *rtab, uint64_t st) {
     for (int e = 0; e < m; e++) row[e] = (unsigned short)e;
     uint64_t s2 = st;
     uint32_t over = 0u;
-    int i = m - 1;
-    for (; i >= 4; i -= 4) {
-        uint32_t rem[4];
+    /* the swap positions of steps i, i-1, i-2, i-3 (n = i+1 .. i-2); positions of a step below 1 are never used */
+    auto draw4 = [&](int i, uint32_t *rem) {
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const uint32_t n = (uint32_t)(i - u + 1);
+            const int iu = i - u;
+            const uint32_t n = (uint32_t)(iu > 0 ? iu + 1 : 2);
             const uint2 lm = rtab[n];
-            const uint32_t r = (uint32_t)(fpt_lcg_next(s2) >> 17);
-            over |= lm.x - r;
-            uint32_t rm = r - __umulhi(r, lm.y) * n;
-            if (rm >= n) rm -= n;
-            rem[u] = rm;
+            if (iu > 0) {
+                const uint32_t r = (uint32_t)(fpt_lcg_next(s2) >> 17);
+                over |= lm.x - r;
+                uint32_t rm = r - __umulhi(r, lm.y) * n;
+                if (rm >= n) rm -= n;
+                rem[u] = rm;
+            } else {
+                rem[u] = 0u;
+            }
         }
+    };
+    uint32_t cur[4], nxt[4];
+    draw4(m - 1, cur);
+    for (int i = m - 1; i > 0; i -= 4) {
+        draw4(i - 4, nxt);                                      /* the next group's draws go out ahead of this group's swaps */
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const unsigned short t = row[i - u], x = row[rem[u]];
-            row[i - u] = x; row[rem[u]] = t;
+            if (i - u > 0) {
+                const unsigned short t = row[i - u], x = row[cur[u]];
+                row[i - u] = x; row[cur[u]] = t;
+            }
         }
-    }
-    for (; i > 0; i--) {
-        const uint32_t n = (uint32_t)(i + 1);
-        const uint2 lm = rtab[n];
-        const uint32_t r = (uint32_t)(fpt_lcg_next(s2) >> 17);
-        over |= lm.x - r;
-        uint32_t rm = r - __umulhi(r, lm.y) * n;
-        if (rm >= n) rm -= n;
-        const unsigned short t = row[i], x = row[rm];
-        row[i] = x; row[rm] = t;
+#pragma unroll
+        for (int u = 0; u < 4; u++) cur[u] = nxt[u];
     }
     if (over >> 31) fpt_generate_labels<unsigned short>(row, m, rtab, st);     /* a rejected draw: exact replay */
 }
@@ -272,7 +276,7 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
            a warp fills one 128-byte core matrix per digit; no divisions, the four k-side points stay in registers. */
         int bad = 0;
         {
-            const int kq = tid & 3, nfirst = tid >> 2;          /* T = 256: 64 rows per sweep, np is a multiple of 64 */
+            const int kq = tid & 3, nfirst = tid >> 2;          /* T / 4 rows per sweep; np is a multiple of 256 */
             for (int kg = 0; kg < (kp >> 4); kg++) {
                 const int k4 = (kg << 4) + (kq << 2);
                 double xk[4], yk[4];
@@ -331,9 +335,9 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
                memory: as many label rows at a time as the tile space holds, copied out to the batch's global rows. */
             for (int base = 0; base < nvalid; base += rows_fit) {
                 const int nb = min(rows_fit, nvalid - base);
-                /* rows dealt over all eight warps, consecutive lanes on consecutive rows (an odd word count apart: no bank
-                   conflicts on equal indices); two half-empty warps per scheduler hide each other's latency */
-                const int rpw = (nb + (T >> 5) - 1) / (T >> 5), myrow = lane < rpw ? warp * rpw + lane : nb;
+                /* one row per thread on the first warps: consecutive lanes on consecutive rows (an odd word count apart: no
+                   bank conflicts on equal indices), full warps so that the chain's instructions are issued once per 32 rows */
+                const int myrow = tid;
                 if (myrow < nb)
                     fpt_umma_shuffle(reinterpret_cast<unsigned short *>(tileA + (size_t)myrow * rbytes), m, rtab,
                                      fpt_lcg_skip(st_win, (uint64_t)(ndone + base + myrow) * (uint64_t)draws));
@@ -420,7 +424,7 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
                             acc_it++;
                         }
                     }
-                } else if (warp >= 4) {                         /* drain: lane p of the accumulator = permutation p */
+                } else if (warp >= 4 && warp < 8) {             /* drain: lane p of the accumulator = permutation p */
                     const int wq = warp - 4, p = wq * 32 + lane;
                     const unsigned char *mrow = tileA + (size_t)(p >> 3) * 128 + (size_t)(p & 7) * 16;
                     uint32_t acc[FPT_UMMA_DIGITS] = { 0u, 0u, 0u, 0u };
