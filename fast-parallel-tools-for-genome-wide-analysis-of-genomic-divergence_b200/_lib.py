@@ -52,6 +52,8 @@ SYMBOLS = {
     "fpt_get_perm_mode": (_I, []),
     "fpt_set_perm_large_kernel": (None, [_I]),
     "fpt_debug_umma_phases": (_I, [_P]),
+    "fpt_debug_lanczos_phases": (_I, [_P]),
+    "fpt_set_lanczos_form": (None, [_I]),
     "fpt_css_perm_rechecks": (C.c_longlong, []),
     "fpt_release": (None, []),
     "fpt_window_state": (C.c_uint64, [C.c_uint64, C.c_int64, _I]),

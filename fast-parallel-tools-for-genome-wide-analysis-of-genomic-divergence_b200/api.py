@@ -39,6 +39,11 @@ def get_perm_mode():
     return bool(_lib.load().fpt_get_perm_mode())
 
 
+def set_lanczos_form(max_form):
+    """Large-cohort MDS: highest matrix form the Lanczos product may stream (3 squares + fill list, 2 / 1 count codes, 0 fp64)."""
+    _lib.load().fpt_set_lanczos_form(int(max_form))
+
+
 def set_perm_large_kernel(tensor_memory):
     """Large cohorts (m > 250): 1 / True = tcgen05 permutation kernel (default), 0 / False = the general kernel, 2 = tcgen05
     kernel with a coarse (10-bit) surrogate that forces many exact re-scorings. Same results in every mode."""

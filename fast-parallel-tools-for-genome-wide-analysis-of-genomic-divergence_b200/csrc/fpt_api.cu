@@ -37,6 +37,7 @@
 static thread_local char g_err[512] = "";
 static uint64_t g_seed = 20261018ULL;
 static int g_device = -1;               /* -1: whatever device is current */
+static int g_lanczos_form = 2;          /* large-cohort MDS: highest product form allowed (3 squares + fill list ... 0 fp64 matrix) */
 static int g_perm_umma = 1;             /* large cohorts: 1 = tcgen05 permutation kernel, 0 = the general (mma.sync) kernel */
 static int g_perm_chain = 0;            /* CSS label shuffles: 0 = independent per permutation, 1 = the reference's chain */
 
@@ -270,6 +271,13 @@ extern "C" int fpt_set_device(int device) {
 extern "C" void fpt_set_perm_mode(int chain) { g_perm_chain = chain != 0; }
 extern "C" int fpt_get_perm_mode(void) { return g_perm_chain; }
 extern "C" void fpt_set_perm_large_kernel(int tensor_memory) { g_perm_umma = tensor_memory; }
+extern "C" void fpt_set_lanczos_form(int max_form) { g_lanczos_form = max_form < 0 ? 0 : (max_form > 3 ? 3 : max_form); }
+extern "C" int fpt_debug_lanczos_phases(unsigned long long *out8) {
+    unsigned long long zero[8] = { 0 };
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(out8, fpt_lanczos_phase_cycles, sizeof zero) != cudaSuccess ||
+        cudaMemcpyToSymbol(fpt_lanczos_phase_cycles, zero, sizeof zero) != cudaSuccess) return FPT_ERR_CUDA;
+    return FPT_OK;
+}
 extern "C" int fpt_debug_umma_phases(unsigned long long *out8) {
     unsigned long long zero[8] = { 0 };
     if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(out8, fpt_umma_phase_cycles, sizeof zero) != cudaSuccess ||
@@ -640,7 +648,7 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
             CHECK(persistent_grid(c, fpt_css_mds_large_kernel, 512, p.smem_large, nwin, &grid));
             grid = std::min(grid, p.max_ctas);
             { ProfScope ps_("css_mds_large", st); fpt_css_mds_large_kernel<<<grid, 512, p.smem_large, st>>>(planes, absdiff, m, wleft, wright, nwin, p.wch_large,
-                                                             ws.gscratch, ws.X, ws.evals, status, nullptr); }
+                                                             ws.gscratch, ws.X, ws.evals, status, nullptr, g_lanczos_form); }
         }
         CU(cudaGetLastError());
     }

@@ -68,6 +68,13 @@ void fpt_set_perm_large_kernel(int tensor_memory);
    (0 distance pass, 1 hand-over of the observed score, 2 shuffles, 3 membership rows, 4 contraction, 5 decisions, 6 label copy-out
    and adjacent-pair sums); synchronises the device */
 int fpt_debug_umma_phases(unsigned long long *out8);
+/* the same for the large-cohort MDS kernel (0 unused, 1 row means + code conversion, 2 products, 3 Gram-Schmidt, 4 tridiagonal
+   solves, 5 norms / next vector, 6 coordinates) */
+int fpt_debug_lanczos_phases(unsigned long long *out8);
+/* Large-cohort classical MDS (csrc/fpt_css_lanczos.cuh): the highest form of the matrix the Lanczos product may stream —
+   3 (default) 16-bit squares of the counts + a list of the fill entries, 2 8-bit count codes, 1 16-bit count codes, 0 the fp64
+   matrix B. Every window takes the highest form it qualifies for; lower settings exist for the parity tests. */
+void fpt_set_lanczos_form(int max_form);
 /* number of permutations since the last call whose integer surrogate score could not decide `permuted >= observed` and
    were re-scored in the reference's summation order (diagnostic; synchronises the device); -1 on error */
 long long fpt_css_perm_rechecks(void);

@@ -20,3 +20,6 @@ for runs in (1000,):
     if lib.fpt_debug_umma_phases(ph)==0:
         tot=sum(ph) or 1
         print('umma phase share (dist, observed, shuffle, rows, contraction, decide, sweep):', [round(x/tot,3) for x in ph][:7], 'Mcycles per window', round(tot/1e6/max(1,nwin),2))
+    if lib.fpt_debug_lanczos_phases(ph)==0:
+        tot=sum(ph) or 1
+        print('lanczos phase share (-, means+codes, products, gram-schmidt, tri-solves, norms, coordinates):', [round(x/tot,3) for x in ph][:7], 'Mcycles per window', round(tot/1e6/max(1,nwin),2))
