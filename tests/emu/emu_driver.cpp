@@ -14,6 +14,7 @@ FPT_EMU_DEFINE_GLOBALS
 #include "fpt_css_lanczos.cuh"
 #include "fpt_css_perm.cuh"
 #include "fpt_css_perm_large.cuh"
+#include "fpt_css_observed.cuh"
 #include "fpt_tables.h"
 
 template <class F>
@@ -196,6 +197,50 @@ unsigned long long emu_css_perm2(const double *Xall, int m, int asize, int bsize
                              out_score, out_p, out_hits, out_n, pr);
     });
     return rechecks;
+}
+
+/* fpt_css_observed.cuh: the observed-score kernel (a warp per window) */
+void emu_css_observed(const double *Xall, int m, int asize, int bsize, long long nwin, const unsigned char *status, int grid,
+                      double *out_score) {
+    run_grid(grid, FPT_OBS_WARPS * 32, fpt_css_observed_smem_bytes(m), [=]() {
+        fpt_css_observed_kernel(Xall, m, asize, bsize, nwin, status, out_score);
+    });
+}
+
+/* the pipelined shuffle next to fpt_generate_labels from the same stream positions, and the warp-wide css() of the shuffled
+   labels: one warp, permutation p on lane p % 32; labels_fast / labels_ref: nperm x m, scores: nperm */
+void emu_umma_shuffle_and_score(const double *X, int m, int asize, int bsize, uint64_t state, int nperm,
+                                unsigned short *labels_fast, unsigned short *labels_ref, double *scores) {
+    std::vector<uint2> rtab(m + 1);
+    for (int n = 0; n <= m; n++) { rtab[n].x = n > 0 ? fpt_randint_limit((uint32_t)n) : 0u; rtab[n].y = n > 0 ? fpt_randint_magic((uint32_t)n) : 0u; }
+    const uint2 *rt = rtab.data();
+    run_grid(1, 32, 32 * 8, [=]() {
+        const int lane = threadIdx.x;
+        double *stage = (double *)emu::g_dyn_smem;
+        for (int p0 = 0; p0 < nperm; p0 += 32) {
+            const int p = p0 + lane;
+            if (p < nperm) {
+                const uint64_t st = fpt_lcg_skip(state, (uint64_t)p * (uint64_t)(m - 1));
+                fpt_umma_shuffle(labels_fast + (size_t)p * m, m, rt, st);
+                fpt_generate_labels<unsigned short>(labels_ref + (size_t)p * m, m, rt, st);
+            }
+            __syncwarp();
+            for (int q = p0; q < p0 + 32 && q < nperm; q++) {
+                const double sc = fpt_warp_css_score(X, stage, labels_fast + (size_t)q * m, asize, bsize, lane);
+                if (lane == 0) scores[q] = sc;
+            }
+        }
+    });
+}
+
+/* surrogate distance of fpt_css_observed.cuh for n point pairs, both orders */
+void emu_umma_dist(const double *xi, const double *yi, const double *xj, const double *yj, int n, double *d_ij, double *d_ji) {
+    run_grid(1, 32, 0, [=]() {
+        for (int e = threadIdx.x; e < n; e += 32) {
+            d_ij[e] = fpt_umma_dist(xi[e], yi[e], xj[e], yj[e]);
+            d_ji[e] = fpt_umma_dist(xj[e], yj[e], xi[e], yi[e]);
+        }
+    });
 }
 
 }  // extern "C"

@@ -364,3 +364,49 @@ def test_css_perm_surrogate_many_tiles(emu, oracle):
                              dptr(sc), dptr(p), iptr(hits), iptr(nn))
         assert [(p[w], hits[w], nn[w]) for w in range(n)] == want
         assert 0 < hits[0] < 48                                   # a window where the decisions actually vary
+
+
+def test_large_cohort_observed_score_shuffle_and_surrogate_distance(emu, oracle):
+    """csrc/fpt_css_observed.cuh, the SIMT half of the tensor-memory permutation path: (1) the warp-per-window observed-score
+    kernel equals css() of the reference's calc_dist matrix bit for bit; (2) the software-pipelined Fisher-Yates produces the
+    labels of fpt_generate_labels (the reference's random_shuffle on its nrand48 stream) and the warp-wide css() of those labels
+    equals the oracle's; (3) the Newton/Heron surrogate distance is symmetric bit for bit and within 2^-50 of the exact root."""
+    rng = np.random.default_rng(5)
+    for asize, bsize in ((37, 30), (5, 64), (1, 3)):
+        m, nwin = asize + bsize, 5
+        X = rng.normal(size=(nwin, m, 2)) * rng.uniform(0.1, 50.0, size=(nwin, 1, 1))
+        status = np.full(nwin, 2, dtype=np.uint8)
+        status[3] = 1
+        got = np.zeros(nwin)
+        emu.emu_css_observed(dptr(X), m, asize, bsize, ll(nwin), vp(status), 2, dptr(got))
+        at, bt = np.arange(asize, dtype=np.int32), np.arange(asize, m, dtype=np.int32)
+        for w in range(nwin):
+            if status[w] != 2:
+                assert got[w] == 0.0
+                continue
+            dist = np.zeros((m, m))
+            oracle.fpt_oracle_calc_dist(dptr(X[w].copy()), m, dptr(dist))
+            assert got[w] == oracle.fpt_oracle_css(dptr(dist), m, iptr(at), iptr(bt), asize, bsize)
+        # shuffles and permuted scores
+        nperm = 40
+        lf, lr = np.zeros((nperm, m), dtype=np.uint16), np.zeros((nperm, m), dtype=np.uint16)
+        sc = np.zeros(nperm)
+        Xw = X[0].copy()
+        emu.emu_umma_shuffle_and_score(dptr(Xw), m, asize, bsize, C.c_uint64(0x1234ABCD5678), nperm, vp(lf), vp(lr), dptr(sc))
+        assert np.array_equal(lf, lr)
+        assert all(sorted(row) == list(range(m)) for row in lf.tolist())
+        dist = np.zeros((m, m))
+        oracle.fpt_oracle_calc_dist(dptr(Xw), m, dptr(dist))
+        for k in range(nperm):
+            tr = lf[k].astype(np.int32)
+            assert sc[k] == oracle.fpt_oracle_css(dptr(dist), m, iptr(tr[:asize].copy()), iptr(tr[asize:].copy()), asize, bsize)
+    n = 4000
+    pts = [rng.normal(size=n) * 10.0 ** rng.uniform(-3, 3, size=n) for _ in range(4)]
+    pts[2][:5], pts[3][:5] = pts[0][:5], pts[1][:5]                  # coincident points: distance 0
+    dij, dji = np.zeros(n), np.zeros(n)
+    emu.emu_umma_dist(dptr(pts[0]), dptr(pts[1]), dptr(pts[2]), dptr(pts[3]), n, dptr(dij), dptr(dji))
+    assert np.array_equal(dij, dji)
+    exact = np.hypot(pts[0] - pts[2], pts[1] - pts[3])
+    assert np.all(dij[:5] == 0.0)
+    rel = np.abs(dij[5:] - exact[5:]) / exact[5:]
+    assert rel.max() < 2.0 ** -50
