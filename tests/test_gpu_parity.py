@@ -296,30 +296,6 @@ def test_css_large_cohort_500_plus_500(fpt, oracle):
     assert np.array_equal(p_g, p_o)
 
 
-@pytest.mark.parametrize("asize,bsize,nsnp", [(500, 500, 600), (200, 200, 600), (200, 200, 40), (152, 148, 60)])
-def test_css_large_cohort_mds_forms_agree(fpt, asize, bsize, nsnp):
-    """Large-cohort classical MDS: the Lanczos product from 16-bit squares + fill list, from 8- or 16-bit count codes and from the
-    fp64 matrix B give the same embedding up to rounding (dense windows, and sparse ones where many pairs never differ and take
-    the fill value), hence the same scores to 1e-9 and the same permutation p-values."""
-    from fpt_b200 import api
-    regend, wsize, wstep, seed = 200000, 50000, 50000, 21
-    ch, _ = _synth(400 + nsnp, regend, nsnp, asize, bsize)
-    out = []
-    try:
-        for form in (3, 2, 1, 0):
-            api.set_lanczos_form(form)
-            out.append(fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 20, 100, mds=0, seed=seed, probes=True))
-    finally:
-        api.set_lanczos_form(3)
-    s3, p3, w3, pr3 = out[0]
-    assert (w3 == 1).sum() >= 3
-    for s_f, p_f, w_f, pr_f in out[1:]:
-        assert np.array_equal(w_f, w3)
-        np.testing.assert_allclose(s_f, s3, rtol=1e-9, atol=1e-12)
-        assert np.array_equal(p_f, p3)
-        np.testing.assert_allclose(pr_f["evals"], pr3["evals"], rtol=1e-10, atol=1e-9)
-
-
 def test_tcgen05_plumbing_against_a_host_product():
     """csrc/fpt_umma.cuh on its own: bulk TMA copies into shared memory, shared-memory descriptors of the K-major core-matrix
     layout, `tcgen05.mma kind::i8` into tensor memory, `tcgen05.ld` back — a 128 x 256 x 128 u8 product equal to the host's."""
@@ -504,3 +480,27 @@ def test_concurrent_host_calls_serialise(fpt):
         for res in got[tag]:
             for x, y in zip(res, w):
                 assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("asize,bsize,nsnp", [(500, 500, 600), (200, 200, 600), (200, 200, 40), (152, 148, 60)])
+def test_css_large_cohort_mds_forms_agree(fpt, asize, bsize, nsnp):
+    """Large-cohort classical MDS: the Lanczos product from 16-bit squares + fill list, from 8- or 16-bit count codes and from the
+    fp64 matrix B give the same embedding up to rounding (dense windows, and sparse ones where many pairs never differ and take
+    the fill value), hence the same scores to 1e-9 and the same permutation p-values."""
+    from fpt_b200 import api
+    regend, wsize, wstep, seed = 200000, 50000, 50000, 21
+    ch, _ = _synth(400 + nsnp, regend, nsnp, asize, bsize)
+    out = []
+    try:
+        for form in (3, 2, 1, 0):
+            api.set_lanczos_form(form)
+            out.append(fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 20, 100, mds=0, seed=seed, probes=True))
+    finally:
+        api.set_lanczos_form(3)
+    s3, p3, w3, pr3 = out[0]
+    assert (w3 == 1).sum() >= 3
+    for s_f, p_f, w_f, pr_f in out[1:]:
+        assert np.array_equal(w_f, w3)
+        np.testing.assert_allclose(s_f, s3, rtol=1e-9, atol=1e-12)
+        assert np.array_equal(p_f, p3)
+        np.testing.assert_allclose(pr_f["evals"], pr3["evals"], rtol=1e-10, atol=1e-9)
