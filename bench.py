@@ -272,8 +272,8 @@ def css_kernel_bytes(name, windows, nsnp_total, m):
         return windows * (2 * 2 * m * 4 + 8 + 24 * m + 4 * m * (m - 1) + 1)
     if name == "css_eigvec":    # tridiagonal + reflectors + status in, embedding (16 m) out
         return windows * (24 * m + 4 * m * (m - 1) + 1 + 16 * m)
-    if name == "css_mds_large":  # Lanczos kernel: ~80 passes over the m x m matrix in global scratch
-        return windows * (80 * 8 * m * m)
+    if name == "css_mds_large":  # Lanczos kernel, ~80 steps: the matrix as 8-bit codes per step + four passes over the growing basis
+        return windows * (80 * m * m + 4 * 8 * m * (80 * 81 // 2))
     if name == "css_pack":      # float64 genotypes in, two bit-planes out
         return nsnp_total * m * 8 + nsnp_total * m // 4
     if name == "window_table":  # positions are binary-searched (L2 resident); two int32 out
