@@ -40,7 +40,7 @@ def get_perm_mode():
 
 
 def set_lanczos_form(max_form):
-    """Large-cohort MDS: highest matrix form the Lanczos product may stream (3 squares + fill list, 2 / 1 count codes, 0 fp64)."""
+    """Large-cohort MDS: highest matrix form the Lanczos product may stream (2 8-bit / 1 16-bit count codes, 0 fp64 matrix)."""
     _lib.load().fpt_set_lanczos_form(int(max_form))
 
 

@@ -37,7 +37,7 @@
 static thread_local char g_err[512] = "";
 static uint64_t g_seed = 20261018ULL;
 static int g_device = -1;               /* -1: whatever device is current */
-static int g_lanczos_form = 2;          /* large-cohort MDS: highest product form allowed (3 squares + fill list ... 0 fp64 matrix) */
+static int g_lanczos_form = 2;          /* large-cohort MDS: highest product form allowed (2 8-bit codes, 1 16-bit codes, 0 fp64 matrix) */
 static int g_perm_umma = 1;             /* large cohorts: 1 = tcgen05 permutation kernel, 0 = the general (mma.sync) kernel */
 static int g_perm_chain = 0;            /* CSS label shuffles: 0 = independent per permutation, 1 = the reference's chain */
 
@@ -271,7 +271,7 @@ extern "C" int fpt_set_device(int device) {
 extern "C" void fpt_set_perm_mode(int chain) { g_perm_chain = chain != 0; }
 extern "C" int fpt_get_perm_mode(void) { return g_perm_chain; }
 extern "C" void fpt_set_perm_large_kernel(int tensor_memory) { g_perm_umma = tensor_memory; }
-extern "C" void fpt_set_lanczos_form(int max_form) { g_lanczos_form = max_form < 0 ? 0 : (max_form > 3 ? 3 : max_form); }
+extern "C" void fpt_set_lanczos_form(int max_form) { g_lanczos_form = max_form < 0 ? 0 : (max_form > 2 ? 2 : max_form); }
 extern "C" int fpt_debug_lanczos_phases(unsigned long long *out8) {
     unsigned long long zero[8] = { 0 };
     if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(out8, fpt_lanczos_phase_cycles, sizeof zero) != cudaSuccess ||

@@ -35,7 +35,6 @@ __device__ unsigned long long fpt_lanczos_phase_cycles[8];
 #define FPT_LZ_START() do { } while (0)
 #endif
 
-#define FPT_LZ_ZCAP 512                     /* off-diagonal fill entries the "squares" product can carry as a list */
 #define FPT_LANCZOS_CHECK 8
 #define FPT_LANCZOS_FIRST_CHECK 16
 
@@ -48,15 +47,13 @@ struct FptLanczosSmem {
     double *beta;     /* cap */
     double *h;        /* cap: projections on the basis */
     double *rmean;    /* m */
-    unsigned *zlist;  /* FPT_LZ_ZCAP: (row << 16 | column) of the off-diagonal fill entries, sorted */
-    int *zcnt;
     FptEigWork ew;    /* tridiagonal eigen-solve of order <= cap, warp 0 */
     FptCssScratch sc; /* reductions + bit-plane words of the dissimilarity stage */
 };
 
 FPT_HD size_t fpt_lanczos_smem_bytes(int m, int wch) {
     const int cap = fpt_lanczos_cap(m);
-    size_t off = (size_t)3 * m * 8 + (size_t)3 * cap * 8 + (size_t)13 * cap * 8 + 66 * 8 + (size_t)(FPT_LZ_ZCAP / 2 + 1) * 8;
+    size_t off = (size_t)3 * m * 8 + (size_t)3 * cap * 8 + (size_t)13 * cap * 8 + 66 * 8;
     off = (off + 15) & ~(size_t)15;
     return off + (size_t)wch * 2 * m * 4;
 }
@@ -75,8 +72,6 @@ FPT_D FptLanczosSmem fpt_lanczos_carve(unsigned char *smem, int m, int wch) {
     s.ew.wbuf = 0; s.ew.wch = 0;
     s.sc.red = p; p += 33;
     s.sc.redi = (long long *)p; p += 33;
-    s.zlist = (unsigned *)p; p += FPT_LZ_ZCAP / 2;
-    s.zcnt = (int *)p; p += 1;
     size_t off = (size_t)((unsigned char *)p - smem);
     off = (off + 15) & ~(size_t)15;
     s.sc.wbuf = (unsigned *)(smem + off);
@@ -153,54 +148,6 @@ FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, const double *
     }
 }
 
-/* The leanest form, for windows whose counts all fit a byte and whose fill value sits on the diagonal and at most FPT_LZ_ZCAP
-   other places: the matrix streamed is S itself as 16-bit integers (c^2 <= 65025; 0 where the fill value belongs), so an
-   element costs one extraction, one fp64 add (the 2^52 trick) and one fma; the fill entries are added afterwards — the
-   diagonal in the row's epilogue, the others from the sorted list, each row's entries by one thread in list order
-   (deterministic). */
-FPT_D void fpt_cta_symv_squares(const unsigned short *__restrict__ Sq, int m, const double *x, double *y, const double *rmean,
-                                double g, double v2, double sx, double rx, int diag_fill, const unsigned *zlist, int nz) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int i = 4 * warp; i < m; i += 4 * nwarp) {
-        const int nr = m - i < 4 ? m - i : 4;
-        const unsigned short *r0 = Sq + (size_t)i * m;
-        const unsigned short *rr[4] = { r0, nr > 1 ? r0 + m : r0, nr > 2 ? r0 + 2 * (size_t)m : r0, nr > 3 ? r0 + 3 * (size_t)m : r0 };
-        double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
-        for (int j = 4 * lane; j < m; j += 128) {
-            uint2 cc[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++) cc[r] = *reinterpret_cast<const uint2 *>(rr[r] + j);
-            const double2 xa = *reinterpret_cast<const double2 *>(x + j), xb = *reinterpret_cast<const double2 *>(x + j + 2);
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                acc[r] = fma(__hiloint2double(0x43300000, (int)(cc[r].x & 0xffffu)) - 4503599627370496.0, xa.x, acc[r]);
-                acc[r] = fma(__hiloint2double(0x43300000, (int)(cc[r].x >> 16)) - 4503599627370496.0, xa.y, acc[r]);
-                acc[r] = fma(__hiloint2double(0x43300000, (int)(cc[r].y & 0xffffu)) - 4503599627370496.0, xb.x, acc[r]);
-                acc[r] = fma(__hiloint2double(0x43300000, (int)(cc[r].y >> 16)) - 4503599627370496.0, xb.y, acc[r]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 4; r++) acc[r] = fpt_warp_sum(acc[r]);
-        if (lane == 0) {
-            for (int r = 0; r < nr; r++) {
-                const double a = diag_fill ? acc[r] + v2 * x[i + r] : acc[r];
-                y[i + r] = -0.5 * (((a - rmean[i + r] * sx) - rx) + g * sx);
-            }
-        }
-    }
-    if (nz > 0) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < nz; t += blockDim.x) {
-            const unsigned z = zlist[t];
-            if (t == 0 || (zlist[t - 1] >> 16) != (z >> 16)) {  /* first entry of its row: this thread adds the row's entries */
-                double sum = 0.0;
-                for (int u = t; u < nz && (zlist[u] >> 16) == (z >> 16); u++) sum += x[zlist[u] & 0xffffu];
-                y[z >> 16] += -0.5 * (v2 * sum);
-            }
-        }
-    }
-}
-
 /* one classical Gram-Schmidt pass of w against the nq basis vectors Q[0..nq) (rows of length m in global memory);
    the projections are ADDED to h so that two passes accumulate the exact coefficients */
 FPT_D void fpt_cta_cgs_pass(const double *__restrict__ Q, int nq, int m, double *w, double *h, double *hpass) {
@@ -224,7 +171,7 @@ FPT_D void fpt_cta_cgs_pass(const double *__restrict__ Q, int nq, int m, double 
 /* A (m x m, global) holds the filled dissimilarities on entry and B on exit; Q (>= cap x m doubles, global) receives the
    Lanczos basis. X: 2m doubles (shared or global) written by the CTA; evals3 optional. All threads of the CTA take part. */
 FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *evals3, const FptLanczosSmem &s, int *steps_out,
-                                int max_form = 3) {
+                                int max_form = 2) {
     const int T = blockDim.x, tid = threadIdx.x;
     const int cap = fpt_lanczos_cap(m);
     const size_t mm = (size_t)m * m;
@@ -235,8 +182,6 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
        the matrix has the compact form: every entry a count in 1..65535 or the fill value v0 (the diagonal always is) */
     const double v0 = A[0];
     int compact = (m & 3) == 0, narrow = 1;                     /* narrow: every count fits a byte */
-    int nfill = 0;                                              /* entries that take the fill value, off the diagonal */
-    if (tid == 0) s.zcnt[0] = 0;
     {
         const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
         for (int i = warp; i < m; i += nwarp) {                /* row sums, coalesced */
@@ -247,7 +192,6 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
                 acc += d * d;
                 if (!(d == v0 || (d >= 1.0 && d <= 65535.0 && d == floor(d)))) compact = 0;
                 if (d > 255.0) narrow = 0;
-                if (j != i && !(d >= 1.0 && d == floor(d))) nfill++;
             }
             acc = fpt_warp_sum(acc);
             if (lane == 0) s.rmean[i] = acc / m;
@@ -255,13 +199,11 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
     }
     compact = __syncthreads_and(compact);
     narrow = __syncthreads_and(narrow);
-    nfill = (int)fpt_block_sum_i64((long long)nfill, s.sc.redi);
-    /* product form: 3 squares + fill list, 2 8-bit codes, 1 16-bit codes, 0 fp64 matrix; `max_form` caps it (parity tests) */
-    const int ok3 = compact && narrow && nfill <= FPT_LZ_ZCAP, ok2 = compact && narrow && (m & 7) == 0, ok1 = compact;
-    const int form = (ok3 && max_form >= 3) ? 3 : ((ok2 && max_form >= 2) ? 2 : ((ok1 && max_form >= 1) ? 1 : 0));
+    /* product form: 2 8-bit codes, 1 16-bit codes, 0 fp64 matrix; `max_form` caps it (parity tests) */
+    const int ok2 = compact && narrow && (m & 7) == 0, ok1 = compact;
+    const int form = (ok2 && max_form >= 2) ? 2 : ((ok1 && max_form >= 1) ? 1 : 0);
     narrow = form == 2;
     compact = form > 0;
-    const int diag_fill = !(v0 >= 1.0 && v0 == floor(v0));
     double g = 0.0;
     for (int i = tid; i < m; i += T) g += s.rmean[i];
     g = fpt_block_sum(g, s.sc.red) / m;
@@ -281,14 +223,7 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
                 const size_t e = base + tid + (size_t)u * T;
                 if (e < mm) {
                     const unsigned c = (d[u] >= 1.0 && d[u] == floor(d[u])) ? (unsigned)d[u] : 0u;
-                    if (form == 3) {
-                        codes[e] = (unsigned short)(c * c);
-                        if (c == 0u) {
-                            const unsigned i = (unsigned)(e / m), j = (unsigned)(e - (size_t)i * m);
-                            if (i != j) s.zlist[atomicAdd(&s.zcnt[0], 1)] = (i << 16) | j;
-                        }
-                    } else if (narrow) codes8[e] = (unsigned char)c;
-                    else codes[e] = (unsigned short)c;
+                    if (narrow) codes8[e] = (unsigned char)c; else codes[e] = (unsigned short)c;
                 }
             }
         }
@@ -300,22 +235,6 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
         }
     }
     __syncthreads();
-    if (form == 3 && nfill > 0) {                               /* the list in (row, column) order: bitonic sort, padded */
-        for (int t = tid; t < FPT_LZ_ZCAP; t += T) if (t >= nfill) s.zlist[t] = 0xffffffffu;
-        __syncthreads();
-        for (int k = 2; k <= FPT_LZ_ZCAP; k <<= 1)
-            for (int jj = k >> 1; jj > 0; jj >>= 1) {
-                for (int t = tid; t < FPT_LZ_ZCAP; t += T) {
-                    const int o = t ^ jj;
-                    if (o > t) {
-                        const unsigned a = s.zlist[t], b = s.zlist[o];
-                        if (((t & k) == 0) ? (a > b) : (a < b)) { s.zlist[t] = b; s.zlist[o] = a; }
-                    }
-                }
-                __syncthreads();
-            }
-    }
-
     FPT_LZ_MARK(1);
     /* ---- 2. Lanczos. Start vector: fixed pseudo-random signs and magnitudes (any vector with a component along the
        leading eigenvectors works; a fixed one keeps runs reproducible) */
@@ -340,8 +259,7 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
             for (int e = tid; e < m; e += T) { const double v = s.q[e]; sx += v; rx += s.rmean[e] * v; }
             sx = fpt_block_sum(sx, s.sc.red);
             rx = fpt_block_sum(rx, s.sc.red);
-            if (form == 3) fpt_cta_symv_squares(codes, m, s.q, s.w, s.rmean, g, v2, sx, rx, diag_fill, s.zlist, nfill);
-            else if (narrow) fpt_cta_symv_codes<unsigned char>(codes8, m, s.q, s.w, s.rmean, g, v2, sx, rx);
+            if (narrow) fpt_cta_symv_codes<unsigned char>(codes8, m, s.q, s.w, s.rmean, g, v2, sx, rx);
             else fpt_cta_symv_codes<unsigned short>(codes, m, s.q, s.w, s.rmean, g, v2, sx, rx);
         } else {
             fpt_cta_symv(A, m, s.q, s.w);
@@ -442,7 +360,7 @@ __global__ void __launch_bounds__(512, 2)
 fpt_css_mds_large_kernel(const unsigned *__restrict__ planes, const double *__restrict__ absdiff, int m,
                          const int *__restrict__ wleft, const int *__restrict__ wright, long long nwin, int wch,
                          double *__restrict__ gscratch, double *__restrict__ Xout, double *__restrict__ evals_out,
-                         unsigned char *__restrict__ status, int *__restrict__ steps_out, int max_form = 3) {
+                         unsigned char *__restrict__ status, int *__restrict__ steps_out, int max_form = 2) {
     FPT_DYN_SMEM(smem);
     const FptLanczosSmem s = fpt_lanczos_carve(smem, m, wch);
     double *M0 = gscratch + (size_t)blockIdx.x * fpt_css_mats_doubles(m), *M1 = M0 + (size_t)m * m;

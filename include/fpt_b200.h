@@ -72,8 +72,8 @@ int fpt_debug_umma_phases(unsigned long long *out8);
    solves, 5 norms / next vector, 6 coordinates) */
 int fpt_debug_lanczos_phases(unsigned long long *out8);
 /* Large-cohort classical MDS (csrc/fpt_css_lanczos.cuh): the highest form of the matrix the Lanczos product may stream —
-   3 (default) 16-bit squares of the counts + a list of the fill entries, 2 8-bit count codes, 1 16-bit count codes, 0 the fp64
-   matrix B. Every window takes the highest form it qualifies for; lower settings exist for the parity tests. */
+   2 (default) 8-bit count codes, 1 16-bit count codes, 0 the fp64 matrix B. Every window takes the highest form it qualifies
+   for; lower settings exist for the parity tests. */
 void fpt_set_lanczos_form(int max_form);
 /* number of permutations since the last call whose integer surrogate score could not decide `permuted >= observed` and
    were re-scored in the reference's summation order (diagnostic; synchronises the device); -1 on error */
