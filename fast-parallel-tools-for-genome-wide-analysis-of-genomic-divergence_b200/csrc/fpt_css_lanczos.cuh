@@ -109,41 +109,46 @@ FPT_D void fpt_cta_symv(const double *__restrict__ B, int m, const double *x, do
    so the matrix streamed per Lanczos step is 16-bit codes — c >= 1: S = c^2, c = 0: S = v2 — and
        y = -1/2 ( S x - r (1'x) - 1 (r'x) + g (1'x) ).
    The integer c^2 becomes a double by the 2^52 trick (one fp64 add instead of a conversion instruction). A warp per row,
-   four rows in flight, each lane one 8-byte load of consecutive codes: four 16-bit ones (m % 4 == 0) or, when no count exceeds
+   ROWS rows in flight (eight with 8-bit codes: 2 KB of loads outstanding per warp), each lane one 8-byte load of consecutive codes: four 16-bit ones (m % 4 == 0) or, when no count exceeds
    255, eight 8-bit ones (m % 8 == 0). sx = 1'x and rx = r'x are given. */
-template <typename CodeT>
+template <typename CodeT, int ROWS>
 FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, const double *x, double *y, const double *rmean,
                               double g, double v2, double sx, double rx) {
     constexpr int PER = 8 / (int)sizeof(CodeT);                 /* codes per 8-byte load: 4 or 8 */
     constexpr int BITS = 8 * (int)sizeof(CodeT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int i = 4 * warp; i < m; i += 4 * nwarp) {
-        const int nr = m - i < 4 ? m - i : 4;
+    for (int i = ROWS * warp; i < m; i += ROWS * nwarp) {
+        const int nr = m - i < ROWS ? m - i : ROWS;
         const CodeT *r0 = C + (size_t)i * m;
-        const CodeT *rr[4] = { r0, nr > 1 ? r0 + m : r0, nr > 2 ? r0 + 2 * (size_t)m : r0, nr > 3 ? r0 + 3 * (size_t)m : r0 };
-        double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
+        double acc[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) acc[r] = 0.0;
         for (int j = PER * lane; j < m; j += 32 * PER) {
-            uint2 cc[4];
+            uint2 cc[ROWS];                                     /* ROWS 8-byte loads in flight per lane */
 #pragma unroll
-            for (int r = 0; r < 4; r++) cc[r] = *reinterpret_cast<const uint2 *>(rr[r] + j);
-            double xs[PER];
+            for (int r = 0; r < ROWS; r++) cc[r] = *reinterpret_cast<const uint2 *>(r0 + (size_t)(r < nr ? r : 0) * m + j);
 #pragma unroll
-            for (int k = 0; k < PER; k += 2) { const double2 xv = *reinterpret_cast<const double2 *>(x + j + k); xs[k] = xv.x; xs[k + 1] = xv.y; }
+            for (int k = 0; k < PER; k += 2) {
+                const double2 xv = *reinterpret_cast<const double2 *>(x + j + k);
 #pragma unroll
-            for (int r = 0; r < 4; r++) {
+                for (int kk = 0; kk < 2; kk++) {
+                    const double xk = kk ? xv.y : xv.x;
 #pragma unroll
-                for (int k = 0; k < PER; k++) {
-                    const unsigned word = (k * BITS) < 32 ? cc[r].x : cc[r].y;
-                    const unsigned c = (word >> ((k * BITS) & 31)) & ((1u << BITS) - 1u);
-                    const double sq = __hiloint2double(0x43300000, (int)(c * c)) - 4503599627370496.0;
-                    acc[r] = fma(c ? sq : v2, xs[k], acc[r]);
+                    for (int r = 0; r < ROWS; r++) {
+                        const unsigned word = ((k + kk) * BITS) < 32 ? cc[r].x : cc[r].y;
+                        const unsigned c = (word >> (((k + kk) * BITS) & 31)) & ((1u << BITS) - 1u);
+                        const double sq = __hiloint2double(0x43300000, (int)(c * c)) - 4503599627370496.0;
+                        acc[r] = fma(c ? sq : v2, xk, acc[r]);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int r = 0; r < 4; r++) acc[r] = fpt_warp_sum(acc[r]);
+        for (int r = 0; r < ROWS; r++) acc[r] = fpt_warp_sum(acc[r]);
         if (lane == 0) {
-            for (int r = 0; r < nr; r++) y[i + r] = -0.5 * (((acc[r] - rmean[i + r] * sx) - rx) + g * sx);
+#pragma unroll
+            for (int r = 0; r < ROWS; r++)
+                if (r < nr) y[i + r] = -0.5 * (((acc[r] - rmean[i + r] * sx) - rx) + g * sx);
         }
     }
 }
@@ -259,8 +264,8 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
             for (int e = tid; e < m; e += T) { const double v = s.q[e]; sx += v; rx += s.rmean[e] * v; }
             sx = fpt_block_sum(sx, s.sc.red);
             rx = fpt_block_sum(rx, s.sc.red);
-            if (narrow) fpt_cta_symv_codes<unsigned char>(codes8, m, s.q, s.w, s.rmean, g, v2, sx, rx);
-            else fpt_cta_symv_codes<unsigned short>(codes, m, s.q, s.w, s.rmean, g, v2, sx, rx);
+            if (narrow) fpt_cta_symv_codes<unsigned char, 8>(codes8, m, s.q, s.w, s.rmean, g, v2, sx, rx);
+            else fpt_cta_symv_codes<unsigned short, 4>(codes, m, s.q, s.w, s.rmean, g, v2, sx, rx);
         } else {
             fpt_cta_symv(A, m, s.q, s.w);
         }
