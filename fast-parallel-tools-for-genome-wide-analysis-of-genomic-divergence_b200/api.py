@@ -6,6 +6,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
+from ._dropin import _arr
 from ._lib import (FPT_SCAN_SERIAL, FPT_SCAN_THREADED, FPT_WIN_DISCARDED, FPT_WIN_EMPTY, FPT_WIN_SCORED, CssProbes,
                    FptError, Genotypes, ScanRange)
 
@@ -100,6 +101,16 @@ def _range(regend, wsize, wstep, semantics, window_begin, window_end, seed, stat
     return r, n
 
 
+def _out(name, a, n):
+    """caller-supplied output array: float64, 1-d, C-contiguous, writable, at least one entry per window of the range"""
+    if a is None:
+        return np.zeros(n)
+    _arr(name, a, np.float64, writable=True)
+    if a.size < n:
+        raise ValueError("'%s' holds %d entries but the window range has %d" % (name, a.size, n))
+    return a
+
+
 def fet_scan(a, b, pos, asize, bsize, regend, wsize, wstep, perc, semantics=FPT_SCAN_SERIAL, window_begin=None,
              window_end=None, seed=None, states=None, scores=None, stddev=None):
     """Windowed FET scan. ``a``/``b``: float64 values or int8 codes, SNP-major; ``pos``: one position per SNP.
@@ -107,8 +118,7 @@ def fet_scan(a, b, pos, asize, bsize, regend, wsize, wstep, perc, semantics=FPT_
     keep = []
     g = _genotypes(a, b, pos, asize, bsize, keep)
     r, n = _range(regend, wsize, wstep, semantics, window_begin, window_end, seed, states, None, keep)
-    scores = np.zeros(n) if scores is None else scores
-    stddev = np.zeros(n) if stddev is None else stddev
+    scores, stddev = _out("scores", scores, n), _out("stddev", stddev, n)
     written = np.zeros(n, dtype=np.uint8)
     _lib.check(_lib.load().fpt_fet_scan(C.byref(g), C.byref(r), float(perc), scores.ctypes.data, stddev.ctypes.data,
                                         written.ctypes.data))
@@ -124,8 +134,7 @@ def css_scan(a, b, pos, asize, bsize, regend, wsize, wstep, treshold, runs, dros
     g = _genotypes(a, b, pos, asize, bsize, keep)
     r, n = _range(regend, wsize, wstep, semantics, window_begin, window_end, seed, states_perm, states_init, keep)
     m = asize + bsize
-    scores = np.zeros(n) if scores is None else scores
-    p = np.zeros(n) if p is None else p
+    scores, p = _out("scores", scores, n), _out("p", p, n)
     written = np.zeros(n, dtype=np.uint8)
     pr, out = None, None
     if probes:

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <mutex>
 #include <thread>
@@ -35,11 +36,16 @@
 
 /* ================================================================================================ state */
 static thread_local char g_err[512] = "";
-static uint64_t g_seed = 20261018ULL;
-static int g_device = -1;               /* -1: whatever device is current */
-static int g_lanczos_form = 2;          /* large-cohort MDS: highest product form allowed (2 8-bit codes, 1 16-bit codes, 0 fp64 matrix) */
-static int g_perm_umma = 1;             /* large cohorts: 1 = tcgen05 permutation kernel, 0 = the general (mma.sync) kernel */
-static int g_perm_chain = 0;            /* CSS label shuffles: 0 = independent per permutation, 1 = the reference's chain */
+/* Process-wide settings. They are atomics, and every entry point takes ONE snapshot of them when it starts (struct Knobs):
+   a setter racing a scan in another thread affects the next call, never the kernel route of a call in flight. */
+static std::atomic<uint64_t> g_seed{20261018ULL};
+static std::atomic<int> g_device{-1};           /* -1: whatever device is current */
+static std::atomic<int> g_lanczos_form{2};      /* large-cohort MDS: highest product form allowed (2 8-bit codes, 1 16-bit codes, 0 fp64 matrix) */
+static std::atomic<int> g_perm_umma{1};         /* large cohorts: 1 = tcgen05 permutation kernel, 0 = the general (mma.sync) kernel */
+static std::atomic<int> g_perm_chain{0};        /* CSS label shuffles: 0 = independent per permutation, 1 = the reference's chain */
+
+struct Knobs { int lanczos_form, perm_umma, perm_chain; };
+static Knobs knobs_now() { Knobs k; k.lanczos_form = g_lanczos_form.load(); k.perm_umma = g_perm_umma.load(); k.perm_chain = g_perm_chain.load(); return k; }
 
 static int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -68,6 +74,7 @@ struct DeviceCtx {
     unsigned long long *binom = nullptr;
     double *lf = nullptr;
     int lf_maxn = -1;
+    std::vector<double *> lf_retired;
     unsigned long long *rechecks = nullptr;
     bool pool_ready = false;
     void *pinned[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   /* grow-only host staging */
@@ -85,8 +92,8 @@ static int get_ctx(DeviceCtx **out) {
         return fail(FPT_ERR_NO_DEVICE, "no CUDA device available (%s); libfpt_b200 has no CPU path",
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     }
-    int dev = 0;
-    if (g_device >= 0) { CU(cudaSetDevice(g_device)); dev = g_device; }
+    int dev = g_device.load();
+    if (dev >= 0) CU(cudaSetDevice(dev));
     else CU(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return fail(FPT_ERR_ARG, "device index %d out of range", dev);
     std::lock_guard<std::mutex> lk(g_mu);
@@ -115,17 +122,20 @@ static int get_ctx(DeviceCtx **out) {
 }
 
 /* log-factorial table, grown on demand (rare: once per process for a given coverage) */
-static int ensure_lf(DeviceCtx *c, int maxn) {
+static int ensure_lf(DeviceCtx *c, int maxn, const double **table) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (maxn <= c->lf_maxn) return FPT_OK;
+    if (maxn <= c->lf_maxn) { *table = c->lf; return FPT_OK; }
     int want = std::max(maxn, 1024);
     std::vector<double> t = fpt_build_lfact_table(want);
     double *d = nullptr;
     CU(cudaMalloc(&d, t.size() * sizeof(double)));
     CU(cudaMemcpy(d, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
-    if (c->lf) { CU(cudaDeviceSynchronize()); cudaFree(c->lf); }
+    /* grow-only and never freed before fpt_release(): a launch in flight on another stream (or another thread that read the
+       pointer a moment ago) keeps a valid table; the old one is a prefix of the new one */
+    if (c->lf) c->lf_retired.push_back(c->lf);
     c->lf = d;
     c->lf_maxn = want;
+    *table = d;
     return FPT_OK;
 }
 
@@ -200,13 +210,17 @@ static int persistent_grid(DeviceCtx *c, K kernel, int block, size_t smem, long 
  * summed device time per kernel. Used by bench.py for the roofline of the dominant kernel.
  */
 struct ProfRec { const char *name; cudaEvent_t a, b; };
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;                    /* guards the two vectors */
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_prof_free;
 
 static cudaEvent_t prof_event() {
     cudaEvent_t e;
-    if (!g_prof_free.empty()) { e = g_prof_free.back(); g_prof_free.pop_back(); return e; }
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (!g_prof_free.empty()) { e = g_prof_free.back(); g_prof_free.pop_back(); return e; }
+    }
     cudaEventCreate(&e);
     return e;
 }
@@ -217,7 +231,7 @@ struct ProfScope {
         if (g_prof_on) { a = prof_event(); cudaEventRecord(a, st); }
     }
     ~ProfScope() {
-        if (a) { cudaEvent_t b = prof_event(); cudaEventRecord(b, st); g_prof.push_back({ name, a, b }); }
+        if (a) { cudaEvent_t b = prof_event(); cudaEventRecord(b, st); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back({ name, a, b }); }
     }
 };
 
@@ -229,6 +243,7 @@ extern "C" int fpt_profile_enable(int on) {
 extern "C" int fpt_profile_summary(char *buf, size_t buflen) {
     struct Acc { const char *name; double ms; long n; };
     std::vector<Acc> acc;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (ProfRec &r : g_prof) {
         cudaEventSynchronize(r.b);
         float ms = 0.f;
@@ -263,15 +278,15 @@ extern "C" int fpt_device_count(void) {
 extern "C" int fpt_set_device(int device) {
     int n = fpt_device_count();
     if (device < 0 || device >= n) return fail(FPT_ERR_ARG, "device %d not in [0,%d)", device, n);
-    g_device = device;
+    g_device.store(device);
     CU(cudaSetDevice(device));
     return FPT_OK;
 }
 
-extern "C" void fpt_set_perm_mode(int chain) { g_perm_chain = chain != 0; }
-extern "C" int fpt_get_perm_mode(void) { return g_perm_chain; }
-extern "C" void fpt_set_perm_large_kernel(int tensor_memory) { g_perm_umma = tensor_memory; }
-extern "C" void fpt_set_lanczos_form(int max_form) { g_lanczos_form = max_form < 0 ? 0 : (max_form > 2 ? 2 : max_form); }
+extern "C" void fpt_set_perm_mode(int chain) { g_perm_chain.store(chain != 0); }
+extern "C" int fpt_get_perm_mode(void) { return g_perm_chain.load(); }
+extern "C" void fpt_set_perm_large_kernel(int tensor_memory) { g_perm_umma.store(tensor_memory); }
+extern "C" void fpt_set_lanczos_form(int max_form) { g_lanczos_form.store(max_form < 0 ? 0 : (max_form > 2 ? 2 : max_form)); }
 extern "C" int fpt_debug_lanczos_phases(unsigned long long *out8) {
     unsigned long long zero[8] = { 0 };
     if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(out8, fpt_lanczos_phase_cycles, sizeof zero) != cudaSuccess ||
@@ -297,8 +312,8 @@ extern "C" long long fpt_css_perm_rechecks(void) {
     return (long long)v;
 }
 
-extern "C" void fpt_set_seed(uint64_t seed) { g_seed = seed; }
-extern "C" uint64_t fpt_get_seed(void) { return g_seed; }
+extern "C" void fpt_set_seed(uint64_t seed) { g_seed.store(seed); }
+extern "C" uint64_t fpt_get_seed(void) { return g_seed.load(); }
 extern "C" uint64_t fpt_window_state(uint64_t seed, int64_t window, int stream) {
     return fpt_stream_state(seed, (long long)window, stream);
 }
@@ -312,6 +327,7 @@ extern "C" void fpt_release(void) {
         cudaDeviceSynchronize();
         if (c.binom) cudaFree(c.binom);
         if (c.lf) cudaFree(c.lf);
+        for (double *q : c.lf_retired) cudaFree(q);
         if (c.rechecks) cudaFree(c.rechecks);
         for (int k = 0; k < 8; k++) if (c.pinned[k]) cudaFreeHost(c.pinned[k]);
         cudaMemPool_t pool;
@@ -377,13 +393,14 @@ extern "C" int fpt_dev_fet_score(const int32_t *tables, int64_t n, int max_n, in
         CU(cudaStreamSynchronize(st));
         CU(cudaFreeAsync(d_max, st));
     }
-    CHECK(ensure_lf(c, max_n));
+    const double *lf = nullptr;
+    CHECK(ensure_lf(c, max_n, &lf));
     size_t lf_bytes = ((size_t)max_n + 1) * sizeof(double);
     int lf_in_smem = lf_bytes <= 96 * 1024;
     size_t smem = FPT_BINOM_ENTRIES * sizeof(unsigned long long) + (lf_in_smem ? lf_bytes : 0);
     int grid;
     CHECK(persistent_grid(c, fpt_fet_score_kernel, 256, smem, (n + 255) / 256, &grid));
-    { ProfScope ps_("fet_score", st); fpt_fet_score_kernel<<<grid, 256, smem, st>>>((const int4 *)tables, n, c->binom, c->lf, max_n, lf_in_smem, force_log, out); }
+    { ProfScope ps_("fet_score", st); fpt_fet_score_kernel<<<grid, 256, smem, st>>>((const int4 *)tables, n, c->binom, lf, max_n, lf_in_smem, force_log, out); }
     CU(cudaGetLastError());
     return FPT_OK;
 }
@@ -423,7 +440,7 @@ extern "C" int fpt_dev_fet_windows(const double *snp_scores, const int32_t *wlef
     int npad = 2;
     while (npad < max_npos) npad <<= 1;
     int use_hist = max_npos <= FPT_FET_HIST_MAX_NPOS;
-    size_t smem = (size_t)npad * sizeof(double) + (use_hist ? (size_t)FPT_FET_NSAMPLES * max_npos * sizeof(unsigned short) : 0);
+    size_t smem = (size_t)npad * sizeof(double) + (use_hist ? (size_t)FPT_FET_HIST_LD * max_npos * sizeof(unsigned short) : 0);
     if ((int)smem > c->smem_optin)
         return fail(FPT_ERR_WINDOW_TOO_LARGE, "a window holds %d SNPs; at most %d fit one CTA's shared memory", max_npos,
                     c->smem_optin / 8);
@@ -495,7 +512,7 @@ struct CssPlan {
     int max_ctas;                    /* upper bound on persistent CTAs (sizes the global scratch) */
 };
 
-static CssPlan css_plan(const DeviceCtx *c, int m) {
+static CssPlan css_plan(const DeviceCtx *c, int m, const Knobs &kn) {
     CssPlan p;
     p.m = m;
     p.wch = 8;
@@ -524,11 +541,11 @@ static CssPlan css_plan(const DeviceCtx *c, int m) {
     p.max_ctas = p.mds_warps > 0 ? c->sms * 16 : c->sms * 2;
     p.wch_large = 2;
     p.smem_large = fpt_lanczos_smem_bytes(m, p.wch_large);
-    p.smem_perm2 = fpt_css_perm2_smem_bytes(m, p.perm_threads, g_perm_chain);
+    p.smem_perm2 = fpt_css_perm2_smem_bytes(m, p.perm_threads, kn.perm_chain);
     p.perm2 = m <= 250 && p.smem_perm2 <= budget;
     p.qbits = 8;
     p.smem_umma = fpt_umma_smem_bytes(m);
-    p.perm_umma = !p.perm2 && p.perm_sur && !g_perm_chain && g_perm_umma && m <= 1024 && p.smem_umma <= budget;
+    p.perm_umma = !p.perm2 && p.perm_sur && !kn.perm_chain && kn.perm_umma && m <= 1024 && p.smem_umma <= budget;
     if (p.perm_umma) p.perm_scratch_per_cta = std::max(p.perm_scratch_per_cta, (fpt_umma_scratch_bytes(m) + 1023) & ~(size_t)1023);
     return p;
 }
@@ -571,25 +588,33 @@ static CssWorkspace css_carve(const CssPlan &p, long long nwin, int mds, unsigne
 extern "C" size_t fpt_dev_css_workspace_bytes(int m, int64_t nwin, int mds) {
     DeviceCtx *c;
     if (get_ctx(&c) != FPT_OK || m <= 0 || nwin < 0) return 0;
-    CssPlan p = css_plan(c, m);
-    return css_carve(p, nwin, mds, nullptr).total;
+    /* the largest layout over the kernel routes the process-wide switches can select, so that a workspace sized before
+       fpt_set_perm_mode / fpt_set_perm_large_kernel is still accepted afterwards */
+    size_t total = 0;
+    for (int chain = 0; chain < 2; chain++)
+        for (int umma = 0; umma < 2; umma++) {
+            Knobs kn = knobs_now();
+            kn.perm_chain = chain; kn.perm_umma = umma;
+            total = std::max(total, css_carve(css_plan(c, m, kn), nwin, mds, nullptr).total);
+        }
+    return total;
 }
 
 template <typename TrackT>
-static int launch_perm(DeviceCtx *c, const CssPlan &p, const CssWorkspace &ws, int asize, int bsize, long long wbase,
+static int launch_perm(DeviceCtx *c, const Knobs &kn, const CssPlan &p, const CssWorkspace &ws, int asize, int bsize, long long wbase,
                        long long nwin, const uint8_t *status, int treshold, int runs, uint64_t seed, const uint64_t *states,
                        double *scores, double *pv, int *hits, int *nperm, cudaStream_t st) {
     int grid;
     CHECK(persistent_grid(c, fpt_css_perm_kernel<TrackT>, p.perm_threads, p.smem_perm, nwin, &grid));
     grid = std::min(grid, p.max_ctas);
     { ProfScope ps_("css_perm", st); fpt_css_perm_kernel<TrackT><<<grid, p.perm_threads, p.smem_perm, st>>>(
-        ws.X, p.m, asize, bsize, wbase, nwin, status, treshold, runs, seed, states, g_perm_chain, p.dist_in_smem, p.tracks_in_smem,
+        ws.X, p.m, asize, bsize, wbase, nwin, status, treshold, runs, seed, states, kn.perm_chain, p.dist_in_smem, p.tracks_in_smem,
         (double *)ws.perm_scratch, p.perm_scratch_per_cta, p.perm_sur ? 31 : 0, scores, pv, hits, nperm, c->rechecks); }
     CU(cudaGetLastError());
     return FPT_OK;
 }
 
-static int launch_perm_umma(DeviceCtx *c, const CssPlan &p, const CssWorkspace &ws, int asize, int bsize, long long wbase,
+static int launch_perm_umma(DeviceCtx *c, const Knobs &kn, const CssPlan &p, const CssWorkspace &ws, int asize, int bsize, long long wbase,
                             long long nwin, const uint8_t *status, int treshold, int runs, uint64_t seed, const uint64_t *states,
                             double *scores, double *pv, int *hits, int *nperm, cudaStream_t st) {
     /* observed scores first: one warp per window, its result handed over in `scores` */
@@ -599,19 +624,26 @@ static int launch_perm_umma(DeviceCtx *c, const CssPlan &p, const CssWorkspace &
     { ProfScope ps_("css_observed", st); fpt_css_observed_kernel<<<grid_obs, FPT_OBS_WARPS * 32, smem_obs, st>>>(
         ws.X, p.m, asize, bsize, nwin, status, scores); }
     CU(cudaGetLastError());
-    CU(cudaFuncSetAttribute(fpt_css_perm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_umma));
-    const int grid = (int)std::max(1LL, std::min<long long>(std::min(c->sms, p.max_ctas), nwin));   /* all of tensor memory: one CTA per SM */
-    { ProfScope ps_("css_perm", st); fpt_css_perm_umma_kernel<<<grid, FPT_UMMA_THREADS, p.smem_umma, st>>>(
+    /* The kernel allocates all 512 columns of tensor memory, so two of its CTAs must never share an SM (the second would
+       sit in tcgen05.alloc until the first exits — also across streams). Enforced here, not assumed: the dynamic shared
+       memory request is padded above half of an SM's capacity, which makes co-residency impossible whatever m is. */
+    const size_t smem_launch = std::max(p.smem_umma, (size_t)c->smem_optin / 2 + 2048);
+    CU(cudaFuncSetAttribute(fpt_css_perm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpt_css_perm_umma_kernel, FPT_UMMA_THREADS, smem_launch));
+    if (per_sm != 1) return fail(FPT_ERR_CUDA, "tensor-memory permutation kernel: %d CTAs per SM (exactly 1 required)", per_sm);
+    const int grid = (int)std::max(1LL, std::min<long long>(std::min(c->sms, p.max_ctas), nwin));
+    { ProfScope ps_("css_perm", st); fpt_css_perm_umma_kernel<<<grid, FPT_UMMA_THREADS, smem_launch, st>>>(
         ws.X, p.m, asize, bsize, wbase, nwin, status, treshold, runs, seed, states, ws.perm_scratch, p.perm_scratch_per_cta,
-        g_perm_umma == 2 ? 10 : 31, scores, pv, hits, nperm, c->rechecks); }
+        kn.perm_umma == 2 ? 10 : 31, scores, pv, hits, nperm, c->rechecks); }
     CU(cudaGetLastError());
     return FPT_OK;
 }
 
-extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff, int asize, int bsize,
-                                   const int32_t *wleft, const int32_t *wright, const fpt_scan_range *r, int treshold,
-                                   int runs, int mds, void *workspace, size_t workspace_bytes, double *scores, double *pv,
-                                   uint8_t *status, const fpt_css_probes *probes, void *stream) {
+static int dev_css_windows(const Knobs &kn, const uint32_t *planes, const double *absdiff, int asize, int bsize,
+                           const int32_t *wleft, const int32_t *wright, const fpt_scan_range *r, int treshold,
+                           int runs, int mds, void *workspace, size_t workspace_bytes, double *scores, double *pv,
+                           uint8_t *status, const fpt_css_probes *probes, void *stream) {
     DeviceCtx *c;
     CHECK(get_ctx(&c));
     cudaStream_t st = (cudaStream_t)stream;
@@ -623,7 +655,7 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
     if (!absdiff && !planes) return fail(FPT_ERR_ARG, "css: neither bit-planes nor frequency differences given");
     if (nwin == 0) return FPT_OK;
     const int m = asize + bsize;
-    CssPlan p = css_plan(c, m);
+    CssPlan p = css_plan(c, m, kn);
     if (p.smem_win > (size_t)c->smem_optin || p.smem_perm > (size_t)c->smem_optin)
         return fail(FPT_ERR_ARG, "cohort of %d individuals does not fit the kernels' shared-memory plan", m);
     CssWorkspace ws = css_carve(p, nwin, mds, (unsigned char *)workspace);
@@ -648,7 +680,7 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
             CHECK(persistent_grid(c, fpt_css_mds_large_kernel, 512, p.smem_large, nwin, &grid));
             grid = std::min(grid, p.max_ctas);
             { ProfScope ps_("css_mds_large", st); fpt_css_mds_large_kernel<<<grid, 512, p.smem_large, st>>>(planes, absdiff, m, wleft, wright, nwin, p.wch_large,
-                                                             ws.gscratch, ws.X, ws.evals, status, nullptr, g_lanczos_form); }
+                                                             ws.gscratch, ws.X, ws.evals, status, nullptr, kn.lanczos_form); }
         }
         CU(cudaGetLastError());
     }
@@ -683,17 +715,17 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
         while (qb > 4 && (terms << qb) >= (1LL << 31)) qb--;
         CHECK(persistent_grid(c, fpt_css_perm2_kernel, p.perm_threads, p.smem_perm2, nwin, &grid));
         { ProfScope ps_("css_perm", st); fpt_css_perm2_kernel<<<grid, p.perm_threads, p.smem_perm2, st>>>(
-              ws.X, m, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, g_perm_chain, qb, scores, pv,
+              ws.X, m, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, kn.perm_chain, qb, scores, pv,
               hits, nperm, c->rechecks); }
         CU(cudaGetLastError());
     } else if (p.perm_umma) {
-        CHECK(launch_perm_umma(c, p, ws, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, scores, pv,
+        CHECK(launch_perm_umma(c, kn, p, ws, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, scores, pv,
                                hits, nperm, st));
     } else if (p.wide_tracks)
-        CHECK(launch_perm<unsigned short>(c, p, ws, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed,
+        CHECK(launch_perm<unsigned short>(c, kn, p, ws, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed,
                                           st_perm, scores, pv, hits, nperm, st));
     else
-        CHECK(launch_perm<unsigned char>(c, p, ws, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed,
+        CHECK(launch_perm<unsigned char>(c, kn, p, ws, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed,
                                          st_perm, scores, pv, hits, nperm, st));
     if (probes) {
         const int nruns = mds == 1 ? 4 : (mds == 2 ? 1 : 0);
@@ -706,6 +738,14 @@ extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff
         if (probes->smacof_sigma && nruns) CU(cudaMemcpyAsync(probes->smacof_sigma, ws.sigma, (size_t)nwin * nruns * 8, cudaMemcpyDeviceToDevice, st));
     }
     return FPT_OK;
+}
+
+extern "C" int fpt_dev_css_windows(const uint32_t *planes, const double *absdiff, int asize, int bsize,
+                                   const int32_t *wleft, const int32_t *wright, const fpt_scan_range *r, int treshold,
+                                   int runs, int mds, void *workspace, size_t workspace_bytes, double *scores, double *pv,
+                                   uint8_t *status, const fpt_css_probes *probes, void *stream) {
+    return dev_css_windows(knobs_now(), planes, absdiff, asize, bsize, wleft, wright, r, treshold, runs, mds, workspace, workspace_bytes,
+                           scores, pv, status, probes, stream);
 }
 
 /* ================================================================================================ host entry points */
@@ -962,6 +1002,7 @@ static int css_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const 
     long long nwin;
     CHECK(check_range(r, &nwin));
     const int m = g->asize + g->bsize;
+    const Knobs kn = knobs_now();                 /* one snapshot for every launch of this call */
     ScanFront f;
     CHECK(scan_front(ar, g, r, &f));
     uint32_t *d_planes = nullptr; double *d_abs = nullptr;
@@ -994,7 +1035,7 @@ static int css_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const 
     /* per upload chunk: pack its SNPs, then score every window whose SNPs have all arrived (see fet_scan_core). Only where
        a sub-range still fills the GPU many times over: the CTA-per-window kernels of large cohorts run a few hundred windows
        at a time, and a short extra launch costs them a whole wave. */
-    const bool stream_windows = plan.n > 1 && nwin >= 8192 && css_plan(c, m).mds_warps > 0 && positions_sorted(g->pos, g->nsnp);
+    const bool stream_windows = plan.n > 1 && nwin >= 8192 && css_plan(c, m, kn).mds_warps > 0 && positions_sorted(g->pos, g->nsnp);
     long long wdone = 0, s0 = 0;
     for (int k = 0; k < plan.n; k++) {
         const long long s1 = plan.snp_end[k];
@@ -1021,7 +1062,7 @@ static int css_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const 
             if (dq.nperm) dq.nperm += wdone;
             if (dq.smacof_iters) dq.smacof_iters += (size_t)wdone * nruns;
             if (dq.smacof_sigma) dq.smacof_sigma += (size_t)wdone * nruns;
-            CHECK(fpt_dev_css_windows(d_planes, d_abs, g->asize, g->bsize, f.d_wl + wdone, f.d_wr + wdone, &sub, treshold, runs, mds, d_ws,
+            CHECK(dev_css_windows(kn, d_planes, d_abs, g->asize, g->bsize, f.d_wl + wdone, f.d_wr + wdone, &sub, treshold, runs, mds, d_ws,
                                       fpt_dev_css_workspace_bytes(m, nw, mds), d_sc + wdone, d_p + wdone, d_st + wdone, probes ? &dq : nullptr, st));
             wdone = wav;
         }
@@ -1128,7 +1169,7 @@ static fpt_scan_range full_range(int regend, int wsize, int wstep, int semantics
     r.regend = regend; r.wsize = wsize; r.wstep = wstep; r.semantics = semantics;
     r.window_begin = 0;
     r.window_end = wstep > 0 ? regend / wstep : 0;       /* length of the caller's output arrays (Q17) */
-    r.seed = g_seed;
+    r.seed = g_seed.load();
     return r;
 }
 

@@ -3,9 +3,10 @@
  *
  *   fpt_css_pack_kernel     genotype codes -> two bit-planes per individual ("is 3", "is -3"),
  *                           32 SNPs per word, word-major so a window is one contiguous slab
- *   fpt_css_mds_kernel      per window: pairwise opposite-homozygote counts (compare_all,
+ *   fpt_css_dissimilarity   per window: pairwise opposite-homozygote counts (compare_all,
  *                           css/css.c:277-327) or frequency difference (compare_freq, css.c:245-264),
- *                           fill_averages (css.c:337-366), classical MDS (cmds, css.c:505-560)
+ *                           fill_averages (css.c:337-366); classical MDS (cmds, css.c:505-560) lives in
+ *                           fpt_css_eig.cuh (one warp per window) and fpt_css_lanczos.cuh (large cohorts)
  *   fpt_css_smacof_kernel   per (window, start): SMACOF majorisation (smacof / guttman_transform /
  *                           stress, css.c:767-938) from a random start (smacof_runs, css.c:852-884)
  *                           or from the classical-MDS solution (css.c:216-217)
@@ -156,146 +157,11 @@ FPT_D int fpt_css_dissimilarity(const unsigned *__restrict__ planes, const doubl
     return fpt_css_fill(D, m, sc);
 }
 
-struct FptJacobiScratch {
-    double *rmean;   /* m */
-    double *rc;      /* ceil(m/2)+1 rotation cosines */
-    double *rs;      /* sines */
-    int *rp, *rq;    /* pair indices */
-};
-
-#ifdef FPT_EMU   /* the library launches fpt_css_eig.cuh / fpt_css_lanczos.cuh instead; this dense Jacobi solver is kept for the
-                    CPU-emulator tests as an independent third eigen-solver (tests/test_emu_kernels.py) */
-/* ============================================================================================
- * Classical MDS. B = -1/2 Z (D.D) Z, Z = I - 11'/m, written in its closed double-centred form
- * b_ij = -1/2 (s_ij - r_i - r_j + g) (the reference forms the same matrix with two dgemm calls);
- * eigen-decomposition by two-sided Jacobi with a round-robin ordering so that m/2 disjoint rotations
- * run concurrently; X = [v1 v2] diag(sqrt(l1), sqrt(l2)) for the two largest eigenvalues BY VALUE,
- * with no guard against negative ones (css.c:543-558: sqrt gives NaN, as in the reference).
- * A holds D on entry and is destroyed; V receives the eigenvectors (columns).
- */
-
-FPT_D void fpt_css_cmds(double *A, double *V, int m, double *X, double *evals3, const FptJacobiScratch &js,
-                        const FptCssScratch &sc) {
-    const int mm = m * m;
-    for (int e = threadIdx.x; e < mm; e += blockDim.x) { double d = A[e]; A[e] = d * d; }
-    __syncthreads();
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {        /* column sums = row sums (symmetric), conflict-free */
-        double s = 0.0;
-        for (int j = 0; j < m; j++) s += A[j * m + i];
-        js.rmean[i] = s / m;
-    }
-    __syncthreads();
-    double g = 0.0;
-    for (int i = 0; i < m; i++) g += js.rmean[i];
-    g /= m;
-    for (int e = threadIdx.x; e < mm; e += blockDim.x) {       /* lower triangle and diagonal in place */
-        const int i = e / m, j = e - i * m;
-        V[e] = (i == j) ? 1.0 : 0.0;
-        if (j <= i) A[e] = -0.5 * (((A[e] - js.rmean[i]) - js.rmean[j]) + g);
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < mm; e += blockDim.x) {       /* mirror: B is exactly symmetric */
-        const int i = e / m, j = e - i * m;
-        if (j > i) A[e] = A[j * m + i];
-    }
-    __syncthreads();
-
-    const int n = (m + 1) & ~1, half = n >> 1;
-    for (int sweep = 0; sweep < 40; sweep++) {
-        double off = 0.0, dia = 0.0;
-        for (int e = threadIdx.x; e < mm; e += blockDim.x) {
-            const int i = e / m, j = e - i * m;
-            const double v = A[e];
-            if (i == j) dia += v * v; else if (j > i) off += v * v;
-        }
-        off = fpt_block_sum(off, sc.red);
-        dia = fpt_block_sum(dia, sc.red);
-        /* Jacobi converges quadratically and its rounding floor sits near 1e-29 (m^2/2 rotations each leaving
-           ~eps^2 behind), so the first sweep that lands below 1e-24 is already at that floor */
-        if (off <= 1e-300 || off <= 1e-24 * (dia + off)) break;
-        for (int round = 0; round < n - 1; round++) {
-            for (int t = threadIdx.x; t < half; t += blockDim.x) {     /* one rotation per disjoint pair of this round */
-                int a, b;
-                if (t == 0) { a = n - 1; b = round; }
-                else { a = (round + t) % (n - 1); b = (round - t + (n - 1)) % (n - 1); }
-                const int p = a < b ? a : b, q = a < b ? b : a;
-                double c = 1.0, s = 0.0;
-                if (q < m) {
-                    const double apq = A[p * m + q];
-                    if (apq != 0.0) {
-                        const double th = (A[q * m + q] - A[p * m + p]) / (2.0 * apq);
-                        const double tt = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
-                        c = 1.0 / sqrt(tt * tt + 1.0);
-                        s = tt * c;
-                    }
-                }
-                js.rp[t] = p; js.rq[t] = q < m ? q : p;      /* a bye rotates p with itself by the identity */
-                js.rc[t] = c; js.rs[t] = s;
-            }
-            __syncthreads();
-            for (int e = threadIdx.x; e < m * half; e += blockDim.x) {      /* columns p,q of A and V */
-                const int k = e / half, t = e - k * half;
-                const double c = js.rc[t], s = js.rs[t];
-                if (s != 0.0) {
-                    const int p = js.rp[t], q = js.rq[t];
-                    double x = A[k * m + p], y = A[k * m + q];
-                    A[k * m + p] = c * x - s * y; A[k * m + q] = s * x + c * y;
-                    x = V[k * m + p]; y = V[k * m + q];
-                    V[k * m + p] = c * x - s * y; V[k * m + q] = s * x + c * y;
-                }
-            }
-            __syncthreads();
-            for (int e = threadIdx.x; e < m * half; e += blockDim.x) {      /* rows p,q of A */
-                const int t = e / m, k = e - t * m;
-                const double c = js.rc[t], s = js.rs[t];
-                if (s != 0.0) {
-                    const int p = js.rp[t], q = js.rq[t];
-                    const double x = A[p * m + k], y = A[q * m + k];
-                    A[p * m + k] = c * x - s * y; A[q * m + k] = s * x + c * y;
-                }
-            }
-            __syncthreads();
-        }
-    }
-    /* two (three, for diagnostics) largest eigenvalues by value; earliest index wins ties */
-    __shared__ int top[3];
-    if (threadIdx.x == 0) {
-        int i1 = -1, i2 = -1, i3 = -1;
-        for (int i = 0; i < m; i++) {
-            const double e = A[i * m + i];
-            if (i1 < 0 || e > A[i1 * m + i1]) { i3 = i2; i2 = i1; i1 = i; }
-            else if (i2 < 0 || e > A[i2 * m + i2]) { i3 = i2; i2 = i; }
-            else if (i3 < 0 || e > A[i3 * m + i3]) { i3 = i; }
-        }
-        top[0] = i1; top[1] = i2; top[2] = i3;
-        if (evals3) {
-            evals3[0] = A[i1 * m + i1];
-            evals3[1] = i2 >= 0 ? A[i2 * m + i2] : 0.0;
-            evals3[2] = i3 >= 0 ? A[i3 * m + i3] : 0.0;
-        }
-    }
-    __syncthreads();
-    const int i1 = top[0], i2 = top[1];
-    double l1 = A[i1 * m + i1], l2 = i2 >= 0 ? A[i2 * m + i2] : 0.0;
-    /* an eigenvalue that is zero up to rounding is clamped to zero (see fpt_css_eig.cuh); truly negative -> NaN */
-    if (l1 < 0.0 && -l1 <= 1e-13 * fabs(l1)) l1 = 0.0;
-    if (l2 < 0.0 && -l2 <= 1e-13 * fabs(l1)) l2 = 0.0;
-    const double s1 = sqrt(l1), s2 = i2 >= 0 ? sqrt(l2) : 0.0;
-    for (int j = threadIdx.x; j < m; j += blockDim.x) {
-        X[2 * j] = V[j * m + i1] * s1;
-        X[2 * j + 1] = i2 >= 0 ? V[j * m + i2] * s2 : 0.0;
-    }
-    __syncthreads();
-}
-
-#endif
-
 /* dynamic shared memory carve-up shared by the window kernels */
 struct FptCssSmem {
     double *M0, *M1;          /* two m x m matrices (or global scratch when m is too large) */
-    double *X, *Z;            /* m x 2 each */
+    double *X, *Z, *Zold;     /* m x 2 each: X^k, its copy for the next transform, and X^(k-1) (exact stress of the previous step) */
     FptCssScratch sc;
-    FptJacobiScratch js;
 };
 
 /* doubles taken by the two matrices of a window: M0 is m x m, M1 is m x (m|1) (SMACOF keeps B with an odd leading dimension) */
@@ -309,14 +175,9 @@ FPT_D FptCssSmem fpt_css_carve(unsigned char *smem, int m, int wch, int mats_in_
     else { s.M0 = gscratch; s.M1 = gscratch + mm; }
     s.X = (double *)(smem + off); off += (size_t)2 * m * 8;
     s.Z = (double *)(smem + off); off += (size_t)2 * m * 8;
-    s.js.rmean = (double *)(smem + off); off += (size_t)m * 8;
-    const int half = ((m + 1) >> 1) + 1;
-    s.js.rc = (double *)(smem + off); off += (size_t)half * 8;
-    s.js.rs = (double *)(smem + off); off += (size_t)half * 8;
+    s.Zold = (double *)(smem + off); off += (size_t)2 * m * 8;
     s.sc.red = (double *)(smem + off); off += 33 * 8;
     s.sc.redi = (long long *)(smem + off); off += 33 * 8;
-    s.js.rp = (int *)(smem + off); off += (size_t)half * 4;
-    s.js.rq = (int *)(smem + off); off += (size_t)half * 4;
     off = (off + 15) & ~(size_t)15;
     s.sc.pairs = 0;
     if (mats_in_smem) { s.sc.pairs = (int *)(smem + off); off += (((size_t)m * (m - 1) / 2) * 4 + 15) & ~(size_t)15; }
@@ -327,36 +188,11 @@ FPT_D FptCssSmem fpt_css_carve(unsigned char *smem, int m, int wch, int mats_in_
 
 FPT_HD size_t fpt_css_smem_bytes(int m, int wch, int mats_in_smem) {
     const size_t mm = (size_t)m * m;
-    const int half = ((m + 1) >> 1) + 1;
-    size_t off = (mats_in_smem ? (2 * mm + m) * 8 : 0) + (size_t)4 * m * 8 + (size_t)m * 8 + (size_t)2 * half * 8 + 66 * 8 +
-                 (size_t)2 * half * 4;
+    size_t off = (mats_in_smem ? (2 * mm + m) * 8 : 0) + (size_t)6 * m * 8 + 66 * 8;
     off = (off + 15) & ~(size_t)15;
     if (mats_in_smem) off += (((size_t)m * (m - 1) / 2) * 4 + 15) & ~(size_t)15;   /* SMACOF pair table */
     return off + (size_t)wch * 2 * m * 4;
 }
-
-#ifdef FPT_EMU
-/* mds 0 and the first half of mds 2: one CTA walks windows blockIdx.x, +gridDim.x, ... */
-__global__ void __launch_bounds__(128)
-fpt_css_mds_kernel(const unsigned *__restrict__ planes, const double *__restrict__ absdiff, int m,
-                   const int *__restrict__ wleft, const int *__restrict__ wright, long long nwin, int wch,
-                   int mats_in_smem, double *__restrict__ gscratch, double *__restrict__ Xout,
-                   double *__restrict__ evals_out, unsigned char *__restrict__ status) {
-    FPT_DYN_SMEM(smem);
-    FptCssSmem s = fpt_css_carve(smem, m, wch, mats_in_smem, gscratch ? gscratch + (size_t)blockIdx.x * fpt_css_mats_doubles(m) : 0);
-    for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
-        const int l = wleft[w], r = wright[w];
-        if (r <= l) { if (threadIdx.x == 0) status[w] = FPT_WIN_EMPTY; continue; }
-        const int keep = fpt_css_dissimilarity(planes, absdiff, m, l, r, s.M0, s.sc);
-        if (!keep) { if (threadIdx.x == 0) status[w] = FPT_WIN_DISCARDED; __syncthreads(); continue; }
-        fpt_css_cmds(s.M0, s.M1, m, s.X, evals_out ? evals_out + 3 * w : 0, s.js, s.sc);
-        for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) Xout[(size_t)w * 2 * m + e] = s.X[e];
-        if (threadIdx.x == 0) status[w] = FPT_WIN_SCORED;
-        __syncthreads();
-    }
-}
-
-#endif
 
 /* ============================================================================================
  * SMACOF (css.c:907-938). Per iteration, the reference's sequence: B(Z) from the current distances
@@ -368,8 +204,9 @@ fpt_css_mds_kernel(const unsigned *__restrict__ planes, const double *__restrict
  * same expression as calc_dist), its contribution to the stress, and b_ij for the NEXT Guttman transform — distances and B
  * are symmetric, so each pair is evaluated once and mirrored, and the distance matrix itself is never stored. B lives in a
  * matrix with an odd leading dimension, so the row pass (thread = one row and coordinate, the reference's exact operation
- * order) reads it without bank conflicts. The only departure from the reference's operation order is the stress sum, which
- * is a fixed-order parallel tree instead of one running sum.
+ * order) reads it without bank conflicts. The stress is summed as a fixed-order parallel tree and, wherever the summation
+ * order could change the stopping decision or the value returned, again as the reference's single running sum
+ * (fpt_css_smacof): iteration counts and results are those of the reference's operation order.
  */
 FPT_HD int fpt_css_ldb(int m) { return m | 1; }
 
@@ -399,15 +236,79 @@ FPT_D double fpt_css_pairs_pass(const double *X, const double *delta, double *Bm
     return fpt_block_sum(part, sc.red);                     /* has the barriers that publish Bm */
 }
 
-FPT_D double fpt_css_smacof(const double *delta, double *Bm, int m, double *X, double *Z, int max_iters, double eps,
+/* The reference's stress (css.c:767-777): ONE running sum over the pairs, i = m-1..1 and j = i-1..0 — i.e. the pair index
+   p = i(i-1)/2 + j counting down. Warp 0 evaluates it: the lanes compute the next 32 terms (same expressions as the pair pass,
+   so every term has the bits the reference's term has), lane 0's accumulator adds them in order (the padding terms of the last
+   group are +0.0, which leaves a non-negative sum unchanged). ~10 cycles per pair on one warp — used only where the stopping
+   rule or the value handed to smacof_runs depends on the summation order (fpt_css_smacof below). All threads get the result. */
+FPT_D double fpt_css_stress_reforder(const double *X, const double *delta, int m, const FptCssScratch &sc) {
+    const int npairs = (m * (m - 1)) >> 1;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        double acc = 0.0;
+        for (int s0 = 0; s0 < npairs; s0 += 32) {
+            const int sidx = s0 + lane;
+            double term = 0.0;
+            if (sidx < npairs) {
+                const int p = npairs - 1 - sidx;
+                int i, j;
+                if (sc.pairs) { const int pk = sc.pairs[p]; i = pk >> 16; j = pk & 0xffff; }
+                else fpt_pair_of(p, i, j);
+                const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
+                const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                const double err = __dsub_rn(d, delta[i * m + j]);
+                term = __dmul_rn(err, err);
+            }
+#pragma unroll
+            for (int l = 0; l < 32; l++) acc = __dadd_rn(acc, __shfl_sync(FPT_FULL_MASK, term, l));
+        }
+        if (lane == 0) sc.red[32] = acc;
+    }
+    __syncthreads();
+    const double r = sc.red[32];
+    __syncthreads();
+    return r;
+}
+
+/* Every iteration's stress is first summed as a fixed-order parallel tree (fpt_css_pairs_pass). The terms are the reference's,
+   only the order of the additions differs, so tree sum t and running sum r of the same n non-negative terms satisfy
+   |t - r| <= (n - 1 + depth) u S (1 + O(u)), u = 2^-53, depth = additions on the longest path of the tree. The stopping rule
+   `sigma_prev - sigma > eps` (css.c:921) is decided on the tree sums when they clear eps by more than that bound for both
+   stresses; otherwise both running sums are evaluated in the reference's order and decide — same iteration count as the
+   reference, always. The stress returned (compared between starts by smacof_runs, css.c:876) is the running sum. */
+#ifndef FPT_SMACOF_BOUND_SCALE
+#define FPT_SMACOF_BOUND_SCALE 1.0      /* tests build the CPU emulation with 1e12 as well: every decision on the exact path */
+#endif
+FPT_D double fpt_css_smacof(const double *delta, double *Bm, int m, double *X, double *Z, double *Zold, int max_iters, double eps,
                             const FptCssScratch &sc, int *iters_out) {
     const int ldb = fpt_css_ldb(m);
+    const int npairs = (m * (m - 1)) >> 1;
+    const int depth = (npairs + (int)blockDim.x - 1) / (int)blockDim.x + 5 + (int)(blockDim.x >> 5);
+    const double order_bound = FPT_SMACOF_BOUND_SCALE * ((double)npairs + (double)depth) * 1.1102230246251565e-16 * 1.001;
     for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) Z[e] = X[e];
     __syncthreads();
     double sigma = fpt_css_pairs_pass(X, delta, Bm, m, sc), prev = 0.0;
+    double sigma_r = 0.0, prev_r = 0.0;                 /* running-sum values, valid when the flags say so */
+    bool have_r = false, have_prev_r = false;
     int k = 0;
-    while (k == 0 || (__dsub_rn(prev, sigma) > eps && k <= max_iters)) {
-        prev = sigma;
+    for (;;) {
+        if (k > 0) {
+            /* css.c:921: continue while (prev - sigma) > eps and k <= max_iters */
+            if (k > max_iters) break;
+            const double drop = __dsub_rn(prev, sigma);
+            const double slack = order_bound * (prev + sigma) + 4.0 * 1.1102230246251565e-16 * fabs(drop);
+            bool go;
+            if (fabs(drop - eps) > slack && prev == prev && sigma == sigma) go = drop > eps;
+            else {
+                if (!have_prev_r) prev_r = fpt_css_stress_reforder(Zold, delta, m, sc);
+                sigma_r = fpt_css_stress_reforder(X, delta, m, sc);
+                have_r = true;
+                go = __dsub_rn(prev_r, sigma_r) > eps;
+            }
+            if (!go) break;
+        }
+        prev = sigma; prev_r = sigma_r; have_prev_r = have_r; have_r = false;
         k++;
         for (int i = threadIdx.x; i < m; i += blockDim.x) {               /* b_ii = -sum_{j != i} b_ij, j counting down */
             double *brow = Bm + (size_t)i * ldb;
@@ -416,6 +317,7 @@ FPT_D double fpt_css_smacof(const double *delta, double *Bm, int m, double *X, d
             for (int j = i; j--;) dsum = __dadd_rn(dsum, brow[j]);
             brow[i] = __dmul_rn(-1.0, dsum);
         }
+        for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) Zold[e] = Z[e];
         __syncthreads();
         for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {           /* one (row, coordinate) per thread */
             const int i = e >> 1, c = e & 1;
@@ -430,7 +332,7 @@ FPT_D double fpt_css_smacof(const double *delta, double *Bm, int m, double *X, d
         __syncthreads();
     }
     if (iters_out) *iters_out = k;
-    return sigma;
+    return have_r ? sigma_r : fpt_css_stress_reforder(X, delta, m, sc);
 }
 
 /* one CTA per (window, start). nruns = 4 random starts (mds 1) or 1 start from Xin (mds 2). */
@@ -468,7 +370,7 @@ fpt_css_smacof_kernel(const unsigned *__restrict__ planes, const double *__restr
         }
         __syncthreads();
         int iters = 0;
-        const double sigma = fpt_css_smacof(s.M0, s.M1, m, s.X, s.Z, max_iters, eps, s.sc, &iters);
+        const double sigma = fpt_css_smacof(s.M0, s.M1, m, s.X, s.Z, s.Zold, max_iters, eps, s.sc, &iters);
         for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) Xruns[(size_t)it * 2 * m + e] = s.X[e];
         if (threadIdx.x == 0) {
             sigma_runs[it] = sigma;

@@ -372,7 +372,9 @@ fpt_css_mds_large_kernel(const unsigned *__restrict__ planes, const double *__re
     for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
         const int l = wleft[w], r = wright[w];
         if (r <= l) { if (threadIdx.x == 0) status[w] = FPT_WIN_EMPTY; continue; }
+        FPT_LZ_START();
         const int keep = fpt_css_dissimilarity(planes, absdiff, m, l, r, M0, s.sc);
+        FPT_LZ_MARK(0);                                             /* slot 0: compare_all + fill_averages */
         if (!keep) { if (threadIdx.x == 0) status[w] = FPT_WIN_DISCARDED; __syncthreads(); continue; }
         fpt_css_cmds_lanczos(M0, M1, m, Xout + (size_t)w * 2 * m, evals_out ? evals_out + 3 * w : 0, s, steps_out ? steps_out + w : 0, max_form);
         if (threadIdx.x == 0) status[w] = FPT_WIN_SCORED;

@@ -350,7 +350,8 @@ __global__ void fpt_window_table_kernel(const int *__restrict__ pos, long long n
  * is detected from the per-replicate draw counts and repaired by re-running with corrected offsets.
  */
 #define FPT_FET_NSAMPLES 100
-#define FPT_FET_HIST_MAX_NPOS 768        /* counting pass while 100 x npos u16 counters fit shared memory */
+#define FPT_FET_HIST_LD 128              /* u16 counters per value: one per replicate, padded to 2 x 64 (see the kernel) */
+#define FPT_FET_HIST_MAX_NPOS 768        /* counting pass while 128 x npos u16 counters fit shared memory */
 
 FPT_D double fpt_percentile_sorted(const double *x, int n, double q) {
     double h = __dmul_rn((double)(n - 1), q);
@@ -437,13 +438,15 @@ fpt_fet_window_kernel(const double *__restrict__ snp_scores, const int *__restri
                 uint64_t st = fpt_lcg_skip(st_win, (uint64_t)offs[s]);
                 int v0 = 0, v1 = 0;
                 if (use_hist) {
-                    unsigned short *hrow = hist + (size_t)s * n;
-                    for (int i = 0; i < n; i++) hrow[i] = 0;
-                    for (int i = 0; i < n; i++) hrow[fpt_randint_fast((uint32_t)n, lim, mag, st, used)]++;
+                    /* counter of (replicate s, value v) = hcol[v * FPT_FET_HIST_LD]: replicates s and s + 64 share a 32-bit word,
+                       so the 32 lanes of a warp always touch 32 different banks whatever they drew (no replay) */
+                    unsigned short *hcol = hist + (((s & 63) << 1) | (s >> 6));
+                    for (int i = 0; i < n; i++) hcol[(size_t)i * FPT_FET_HIST_LD] = 0;
+                    for (int i = 0; i < n; i++) hcol[(size_t)fpt_randint_fast((uint32_t)n, lim, mag, st, used) * FPT_FET_HIST_LD]++;
                     int cum = 0, v = 0;
-                    for (; v < n; v++) { cum += hrow[v]; if (cum > k) break; }
+                    for (; v < n; v++) { cum += hcol[(size_t)v * FPT_FET_HIST_LD]; if (cum > k) break; }
                     v0 = v; v1 = v;
-                    if (need_next && cum <= k + 1) { for (v++; v < n; v++) if (hrow[v]) break; v1 = v; }
+                    if (need_next && cum <= k + 1) { for (v++; v < n; v++) if (hcol[(size_t)v * FPT_FET_HIST_LD]) break; v1 = v; }
                 } else {
                     fpt_select_by_regeneration(st, n, k, need_next, v0, v1, used);
                 }
@@ -464,7 +467,9 @@ fpt_fet_window_kernel(const double *__restrict__ snp_scores, const int *__restri
                 }
             }
             __syncthreads();
-            if (!changed) break;
+            const int again = changed;                   /* read by everyone BEFORE thread 0 may reset it in the next pass */
+            __syncthreads();
+            if (!again) break;
         }
         if (threadIdx.x == 0) {
             double mu = 0.0;

@@ -50,6 +50,9 @@ extern "C" {
 const char *fpt_last_error(void);
 int fpt_device_count(void);                 /* number of CUDA devices, 0 if none / no driver */
 int fpt_set_device(int device);             /* device used by the host entry points of this process */
+/* The settings below are process-wide. Each is atomic, and every entry point takes one snapshot of them when it starts: a
+   setter racing a scan in another thread affects that thread's NEXT call, never the kernel route of a call in flight.
+   Host entry points that share a device's staging buffers take turns (one per device at a time). */
 void fpt_set_seed(uint64_t seed);           /* seed of the window-keyed random streams (default 20261018) */
 uint64_t fpt_get_seed(void);
 /* CSS label shuffles. 0 (default): permutation k of a window is the reference's Fisher-Yates shuffle (css/css.c:700-706)
@@ -68,7 +71,7 @@ void fpt_set_perm_large_kernel(int tensor_memory);
    (0 distance pass, 1 hand-over of the observed score, 2 shuffles, 3 membership rows, 4 contraction, 5 decisions, 6 label copy-out
    and adjacent-pair sums); synchronises the device */
 int fpt_debug_umma_phases(unsigned long long *out8);
-/* the same for the large-cohort MDS kernel (0 unused, 1 row means + code conversion, 2 products, 3 Gram-Schmidt, 4 tridiagonal
+/* the same for the large-cohort MDS kernel (0 dissimilarity = compare_all + fill_averages, 1 row means + code conversion, 2 products, 3 Gram-Schmidt, 4 tridiagonal
    solves, 5 norms / next vector, 6 coordinates) */
 int fpt_debug_lanczos_phases(unsigned long long *out8);
 /* Large-cohort classical MDS (csrc/fpt_css_lanczos.cuh): the highest form of the matrix the Lanczos product may stream —
@@ -101,7 +104,10 @@ int fpt_profile_summary(char *buf, size_t buflen);
  *                          bound by css/css_cython_parallel.pyx:4-5,14-15
  * fpt_css_compute       == `compute` of css/css.h:10 (css/css.c:49-156), bound by css/css_cython.pyx
  *
- * vals: float64 genotype codes (3, -3, 0, -10000), position-major / individual-minor;
+ * vals: float64 genotype codes, position-major / individual-minor. DOMAIN: {3, -3, 0, -10000}, the codes tools/VCFConvert.py:8-17
+ *       emits. On that domain the CSS pair test is the reference's `((int)a)*b == -9` (css/css.c:291) and the FET count its
+ *       `== 3` / `== -3` (fisher/cFisher.c:212-216). Other doubles are classified as "neither homozygote" here, whereas css.c
+ *       truncates only its first operand (3.9 paired with -3, or 1 with -9, would count there): outside the domain the two differ.
  * pos: int32 position of every value (each SNP position repeated once per individual).
  */
 int fpt_fet_threadcompute(double *avals, double *bvals, int *apos, int *bpos, int regstart, int regend, int wsize,

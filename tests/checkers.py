@@ -89,6 +89,8 @@ def load_oracle():
     o.fpt_oracle_cmds.argtypes = [c_double_p, C.c_int, c_double_p, c_double_p]
     o.fpt_oracle_smacof.restype = C.c_double
     o.fpt_oracle_smacof.argtypes = [c_double_p, C.c_int, c_double_p, C.c_int, C.c_double, c_int_p]
+    o.fpt_oracle_smacof_margin.restype = C.c_double
+    o.fpt_oracle_smacof_margin.argtypes = [c_double_p, C.c_int, c_double_p, C.c_int, C.c_double, c_int_p, c_double_p]
     o.fpt_oracle_smacof_runs.restype = C.c_double
     o.fpt_oracle_smacof_runs.argtypes = [c_double_p, C.c_int, c_double_p, C.c_int, C.c_int, C.c_double, c_u64_p]
     o.fpt_oracle_calc_dist.restype = None

@@ -71,7 +71,7 @@ void emu_fet_window(const double *snp_scores, const int *wleft, const int *wrigh
                     double *out_score, double *out_std, unsigned char *out_flag) {
     int npad = 2;
     while (npad < max_npos) npad <<= 1;
-    size_t smem = (size_t)npad * 8 + (use_hist ? (size_t)FPT_FET_NSAMPLES * max_npos * 2 : 0);
+    size_t smem = (size_t)npad * 8 + (use_hist ? (size_t)FPT_FET_HIST_LD * max_npos * 2 : 0);
     run_grid(grid, 128, smem, [=]() {
         fpt_fet_window_kernel(snp_scores, wleft, wright, wbase, nwin, perc, seed, state_override, npad, use_hist, out_score,
                               out_std, out_flag);
@@ -92,16 +92,6 @@ void emu_css_pack_i8(const signed char *a, const signed char *b, long long nsnp,
 
 void emu_css_absdiff(const double *a, const double *b, long long n, double *out) {
     run_grid(2, 64, 0, [=]() { fpt_css_absdiff_kernel(a, b, n, out); });
-}
-
-void emu_css_mds(const unsigned *planes, const double *absdiff, int m, const int *wleft, const int *wright,
-                 long long nwin, int wch, int mats_in_smem, int grid, double *X, double *evals, unsigned char *status) {
-    size_t smem = fpt_css_smem_bytes(m, wch, mats_in_smem);
-    std::vector<double> gs(mats_in_smem ? 1 : (size_t)grid * fpt_css_mats_doubles(m));
-    double *gp = mats_in_smem ? 0 : gs.data();
-    run_grid(grid, 128, smem, [=]() {
-        fpt_css_mds_kernel(planes, absdiff, m, wleft, wright, nwin, wch, mats_in_smem, gp, X, evals, status);
-    });
 }
 
 void emu_css_mds_large(const unsigned *planes, const double *absdiff, int m, const int *wleft, const int *wright,

@@ -111,6 +111,23 @@ def test_dropin_argument_checks_mirror_cython_buffer_typing():
         fp.fisher_exact_tester(ok64, ok64, ok32, ok32, 0, 1000, 100, 100, 8, 8, 0.95, np.zeros(3), out)
 
 
+def test_extended_api_checks_caller_supplied_outputs():
+    """api.fet_scan / api.css_scan hand `scores`, `stddev`, `p` to C by raw pointer: wrong dtype, stride, size or a read-only
+    array must be refused before the call, not written through"""
+    import fpt_b200.api as api
+    a = np.zeros(8, dtype=np.int8)
+    pos = np.arange(4, dtype=np.int32)
+    for bad in (np.zeros(10, dtype=np.float32), np.zeros(20)[::2], np.zeros(3), np.zeros((2, 5))):
+        with pytest.raises(ValueError):
+            api.fet_scan(a, a, pos, 2, 2, 1000, 100, 100, 0.95, scores=bad)
+        with pytest.raises(ValueError):
+            api.css_scan(a, a, pos, 2, 2, 1000, 100, 100, 5, 10, p=bad)
+    ro = np.zeros(10)
+    ro.flags.writeable = False
+    with pytest.raises(ValueError):
+        api.fet_scan(a, a, pos, 2, 2, 1000, 100, 100, 0.95, stddev=ro)
+
+
 def test_synthetic_generators():
     import fpt_b200.synth as synth
     for gen in (synth.chromosome, synth.chromosome_fast):

@@ -21,6 +21,15 @@ def emu():
     return C.CDLL(os.path.join(HERE, "emu", "libfpt_emu.so"))
 
 
+@pytest.fixture(scope="module")
+def emu_exact_stress():
+    """the same kernels with the SMACOF order bound scaled by 1e12: every stopping decision takes the path that re-sums the
+    stress in the reference's order (csrc/fpt_css.cuh, fpt_css_smacof)"""
+    out = os.path.join(HERE, "emu", "libfpt_emu_exact.so")
+    subprocess.run([os.path.join(HERE, "emu", "build.sh"), out, "-DFPT_SMACOF_BOUND_SCALE=1e12"], check=True, capture_output=True)
+    return C.CDLL(out)
+
+
 def vp(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -152,8 +161,7 @@ def test_css_pack_kernel(emu):
     assert np.array_equal(P8, P.reshape(-1))
 
 
-@pytest.mark.parametrize("kernel", ["warp", "cta", "cta_global"])
-def test_css_mds_kernels(emu, oracle, kernel):
+def test_css_mds_kernels(emu, oracle):
     asize, bsize, S, L, wsize, wstep = 6, 5, 220, 20000, 2500, 500
     m = asize + bsize
     pos, av, bv = _css_input(6, asize, bsize, S, L)
@@ -162,10 +170,7 @@ def test_css_mds_kernels(emu, oracle, kernel):
     wl, wr = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
     emu.emu_window_table(iptr(pos), ll(S), ll(0), ll(n), L, wsize, wstep, 0, iptr(wl), iptr(wr))
     X, ev, st = np.zeros((n, m, 2)), np.zeros((n, 3)), np.zeros(n, dtype=np.uint8)
-    if kernel == "warp":
-        emu.emu_css_mds_warp(vp(planes), None, m, iptr(wl), iptr(wr), ll(n), 4, 2, 3, dptr(X), dptr(ev), vp(st))
-    else:
-        emu.emu_css_mds(vp(planes), None, m, iptr(wl), iptr(wr), ll(n), 4, 1 if kernel == "cta" else 0, 3, dptr(X), dptr(ev), vp(st))
+    emu.emu_css_mds_warp(vp(planes), None, m, iptr(wl), iptr(wr), ll(n), 4, 2, 3, dptr(X), dptr(ev), vp(st))
     scored = 0
     for w in range(n):
         l, r = int(wl[w]), int(wr[w])
@@ -231,8 +236,11 @@ def test_css_mds_large_cohort_kernel(emu, oracle, shape):
         assert steps[st == 2].max() < m          # the residual test stops well before the Krylov space is complete
 
 
+@pytest.mark.parametrize("exact_path", [0, 1])
 @pytest.mark.parametrize("mds", [1, 2])
-def test_css_smacof_and_perm_kernels(emu, oracle, mds):
+def test_css_smacof_and_perm_kernels(emu, emu_exact_stress, oracle, mds, exact_path):
+    if exact_path:
+        emu = emu_exact_stress
     asize, bsize, S, L, wsize, wstep = 4, 4, 90, 6000, 2500, 500
     m = asize + bsize
     pos, av, bv = _css_input(7, asize, bsize, S, L)
@@ -245,6 +253,7 @@ def test_css_smacof_and_perm_kernels(emu, oracle, mds):
     seed = 99
     if mds == 2:
         emu.emu_css_mds_warp(vp(planes), None, m, iptr(wl), iptr(wr), ll(n), 4, 2, 2, dptr(X), dptr(ev), vp(st))
+        X0 = X.copy()
         Xr, sg, it = np.zeros((n, 1, m, 2)), np.zeros(n), np.zeros(n, dtype=np.int32)
         emu.emu_css_smacof(vp(planes), None, m, iptr(wl), iptr(wr), ll(0), ll(n), 4, 1, 3, 1, 0, C.c_uint64(seed), None, 300,
                            C.c_double(1e-6), dptr(X), dptr(Xr), dptr(sg), iptr(it), vp(st))
@@ -254,6 +263,32 @@ def test_css_smacof_and_perm_kernels(emu, oracle, mds):
         emu.emu_css_smacof(vp(planes), None, m, iptr(wl), iptr(wr), ll(0), ll(n), 4, 1, 3, 4, 1, C.c_uint64(seed), None, 300,
                            C.c_double(1e-6), None, dptr(Xr), dptr(sg), iptr(it), vp(st))
         emu.emu_css_pick(dptr(Xr), dptr(sg), m, 4, ll(n), vp(st), dptr(X))
+    # iteration counts and stresses are the reference's (css.c:907-938): the stopping rule is decided on running sums in the
+    # reference's order wherever the order of the additions could matter
+    nruns = 4 if mds == 1 else 1
+    checked = 0
+    for w in range(n):
+        if st[w] != 2:
+            continue
+        l, r = int(wl[w]), int(wr[w])
+        D = np.zeros((m, m))
+        oracle.fpt_oracle_compare_all(dptr(av[l * asize:r * asize].copy()), dptr(bv[l * bsize:r * bsize].copy()), asize, bsize, r - l, dptr(D))
+        assert oracle.fpt_oracle_fill_averages(dptr(D), m)
+        state = C.c_uint64(oracle.fpt_oracle_window_state(seed, w, 1))
+        for run in range(nruns):
+            if mds == 1:
+                Xs = np.array([oracle.fpt_oracle_drand48(C.byref(state)) for _ in range(2 * m)]).reshape(m, 2)
+            else:
+                Xs = X0[w].copy()
+            if not np.isfinite(Xs).all():
+                continue
+            k = C.c_int(0)
+            sig = oracle.fpt_oracle_smacof(dptr(D), m, dptr(Xs), 300, 1e-6, C.byref(k))
+            assert it[w * nruns + run] == k.value
+            assert sg[w * nruns + run] == sig
+            assert np.array_equal(Xr.reshape(n, nruns, m, 2)[w, run], Xs)
+            checked += 1
+    assert checked >= 5
     sc, p, hits, nn = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
     emu.emu_css_perm(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), 7, 150, C.c_uint64(seed), None, 1, 1, 64, 2, 0, 1, dptr(sc), dptr(p),
                      iptr(hits), iptr(nn))

@@ -121,8 +121,19 @@ def test_css_full_size_spot_checks_layouts_and_sharding(fpt, oracle, c3, mds):
         if abs(s[wi] - so) <= 1e-5 * abs(so):
             assert p[wi] == pv[0]
         else:
+            # only excuse: mds 2, and the reference's own stopping rule decided within 1 % of its threshold from the
+            # eigensolver's start (see test_css_scan_matches_oracle in test_gpu_parity.py)
+            assert mds == 2
+            D = np.zeros((40, 40))
+            oracle.fpt_oracle_compare_all(dptr(av[l * 20:r * 20].copy()), dptr(bv[l * 20:r * 20].copy()), 20, 20, r - l, dptr(D))
+            assert oracle.fpt_oracle_fill_averages(dptr(D), 40)
+            Xo, evo = np.zeros((40, 2)), np.zeros(3)
+            oracle.fpt_oracle_cmds(dptr(D), 40, dptr(Xo), dptr(evo))
+            k, margin = C.c_int(0), C.c_double(0)
+            oracle.fpt_oracle_smacof_margin(dptr(D), 40, dptr(Xo), 300, 1e-6, C.byref(k), C.byref(margin))
+            assert margin.value < 1e-8, "window %d differs at stopping margin %g" % (wi, margin.value)
             bad += 1
-    assert bad <= (0 if mds == 0 else 1)
+    assert bad <= (0 if mds != 2 else 1)
     from fpt_b200.sharding import partition_windows, snp_slice
     if mds == 0:
         parts = []

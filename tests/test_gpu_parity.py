@@ -148,6 +148,60 @@ def _css_oracle_scan(oracle, av, bv, apos, bpos, regend, wsize, wstep, mct, mcr,
     return s_o, p_o
 
 
+def _oracle_window_delta(oracle, ch, av, bv, asize, bsize, w, wsize, wstep):
+    """filled dissimilarity matrix of window w (compare_all + fill_averages restated by the oracle)"""
+    l, r = C.c_int64(0), C.c_int64(0)
+    oracle.fpt_oracle_window_bounds(iptr(ch["pos"]), ch["pos"].size, w, wsize, wstep, C.byref(l), C.byref(r))
+    l, r = l.value, r.value
+    m = asize + bsize
+    D = np.zeros((m, m))
+    oracle.fpt_oracle_compare_all(dptr(av[l * asize:r * asize].copy()), dptr(bv[l * bsize:r * bsize].copy()), asize, bsize, r - l, dptr(D))
+    assert oracle.fpt_oracle_fill_averages(dptr(D), m)
+    return D
+
+
+@pytest.mark.parametrize("mds", [1, 2])
+@pytest.mark.parametrize("shape", [(20, 20, 2500, 500), (7, 9, 3000, 1000), (70, 60, 6000, 3000)])
+def test_css_smacof_stage_matches_oracle_bit_for_bit(fpt, oracle, mds, shape):
+    """SMACOF (css.c:852-938) from a given start is the reference's arithmetic operation for operation: iteration count, final
+    stress and final coordinates of every (window, start) equal the oracle's bit for bit — including the windows whose
+    stopping decision `sigma_prev - sigma > 1e-6` falls within rounding of the threshold, where the stress is re-summed in
+    the reference's order (css.c:767-777). mds 1: the four drand48 starts of the window's stream; mds 2: the start is this
+    library's own classical-MDS embedding (probe of an mds 0 scan), handed to the oracle's smacof."""
+    asize, bsize, wsize, wstep = shape
+    m = asize + bsize
+    regend, nsnp, seed = 60000, 1500, 5
+    ch, (av, bv, apos, bpos) = _synth(41 + asize, regend, nsnp, asize, bsize)
+    s_g, p_g, wr, pr = fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 10, 200, mds=mds,
+                                    seed=seed, probes=True)
+    X0 = None
+    if mds == 2:
+        X0 = fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 0, 0, mds=0, seed=seed, probes=True)[3]["X"]
+    nruns = 4 if mds == 1 else 1
+    checked = 0
+    for w in np.flatnonzero(wr == 1):
+        D = _oracle_window_delta(oracle, ch, av, bv, asize, bsize, w, wsize, wstep)
+        state = C.c_uint64(oracle.fpt_oracle_window_state(seed, int(w), 1))
+        best, best_X = None, None
+        for run in range(nruns):
+            if mds == 1:
+                Xs = np.array([oracle.fpt_oracle_drand48(C.byref(state)) for _ in range(2 * m)]).reshape(m, 2)
+            else:
+                Xs = X0[w].copy()
+            if not np.isfinite(Xs).all():
+                break
+            k = C.c_int(0)
+            sig = oracle.fpt_oracle_smacof(dptr(D), m, dptr(Xs), 300, 1e-6, C.byref(k))
+            assert pr["smacof_iters"][w, run] == k.value, "window %d start %d" % (w, run)
+            assert pr["smacof_sigma"][w, run] == sig
+            if best is None or sig < best:
+                best, best_X = sig, Xs
+            checked += 1
+        else:
+            assert np.array_equal(pr["X"][w], best_X)
+    assert checked >= 10 * nruns
+
+
 @pytest.mark.parametrize("mds", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(20, 20, 2500, 500), (7, 9, 3000, 1000), (2, 2, 2500, 500)])
 def test_css_scan_matches_oracle(fpt, oracle, mds, shape):
@@ -167,11 +221,29 @@ def test_css_scan_matches_oracle(fpt, oracle, mds, shape):
         ev = pr["evals"]
         finite &= ~((wr == 1) & ((ev[:, 1] - ev[:, 2]) < 1e-8 * np.maximum(ev[:, 0], 1e-300)))
     assert finite.sum() >= (0.8 if asize + bsize > 4 else 0.4) * (wr == 1).sum()
-    # SMACOF's stopping rule leaves the embedding converged to ~1e-5 only, so a window whose iteration count
-    # differs by one (stress drop within rounding of the 1e-6 threshold) may move by that much; allow a few.
     rel = np.abs(s_g[finite] - s_o[finite]) / np.maximum(np.abs(s_o[finite]), 1e-300)
     bad = rel > CSS_RTOL
-    assert bad.sum() <= (0 if mds == 0 else max(1, int(0.01 * finite.sum()))), "CSS score mismatches: %d (max rel %g)" % (bad.sum(), rel.max())
+    if mds == 2:
+        # mds 2 starts SMACOF from the classical-MDS embedding, i.e. from the eigensolver's output (GSL in the reference,
+        # tred2/tql2 in the oracle, Sturm + inverse iteration here: equal to ~1e-14, not bit for bit — DESIGN.md "GSL boundary").
+        # SMACOF itself is pinned bit for bit from a given start (test_css_smacof_stage_matches_oracle_bit_for_bit); a start
+        # that differs in its last bits changes the iteration count only where the reference's own stopping rule
+        # `sigma_prev - sigma > 1e-6` is decided within 1 % of the threshold — those windows depend on the GSL build in the
+        # reference too. They are identified from the ORACLE's margin and its iteration count, nothing else is excused.
+        n = regend // wstep
+        degenerate = np.zeros(n, dtype=bool)
+        for w in np.flatnonzero(wr == 1):
+            D = _oracle_window_delta(oracle, ch, av, bv, asize, bsize, w, wsize, wstep)
+            Xo, evo = np.zeros((asize + bsize, 2)), np.zeros(3)
+            oracle.fpt_oracle_cmds(dptr(D), asize + bsize, dptr(Xo), dptr(evo))
+            k, margin = C.c_int(0), C.c_double(0)
+            oracle.fpt_oracle_smacof_margin(dptr(D), asize + bsize, dptr(Xo), 300, 1e-6, C.byref(k), C.byref(margin))
+            if k.value != pr["smacof_iters"][w, 0]:
+                assert margin.value < 1e-8, "window %d: %d vs %d iterations at margin %g" % (w, pr["smacof_iters"][w, 0], k.value, margin.value)
+                degenerate[w] = True
+        assert degenerate.sum() <= max(1, int(0.02 * finite.sum()))
+        bad &= ~degenerate[finite]
+    assert bad.sum() == 0, "CSS score mismatches: %d (max rel %g)" % (bad.sum(), rel.max())
     agree = ~bad
     if asize + bsize > 4:
         assert np.array_equal(p_g[finite][agree], p_o[finite][agree])  # identical permutation p-values
@@ -284,8 +356,9 @@ def test_css_larger_cohorts_take_the_fallback_paths(fpt, oracle, asize, bsize):
 
 
 def test_css_large_cohort_500_plus_500(fpt, oracle):
-    """BASELINE configs[4] cohort size (500+500 individuals, 50 kb windows) on a handful of windows: the large-cohort kernels
-    (Lanczos classical MDS; general permutation kernel with matrices in per-CTA global scratch, 16-bit labels, surrogate)"""
+    """BASELINE configs[4] cohort size (500+500 individuals, 50 kb windows) on a handful of windows, one ragged batch of 40
+    permutations: the default large-cohort route (Lanczos classical MDS, observed scores by a warp per window, tcgen05 /
+    tensor-memory permutation kernel); the 1000-permutation case is test_css_large_cohort_default_route_1000_permutations_vs_oracle"""
     asize = bsize = 500
     regend, wsize, wstep, nsnp, seed = 150000, 50000, 50000, 500, 4
     ch, (av, bv, apos, bpos) = _synth(500, regend, nsnp, asize, bsize)
@@ -294,6 +367,31 @@ def test_css_large_cohort_500_plus_500(fpt, oracle):
     assert np.array_equal(wr == 1, p_o != 0) and (wr == 1).sum() == 3
     np.testing.assert_allclose(s_g, s_o, rtol=CSS_RTOL, atol=1e-12)
     assert np.array_equal(p_g, p_o)
+
+
+@pytest.mark.parametrize("asize,bsize,mct,mcr,seed", [(500, 500, 1000, 1000, 4), (500, 500, 150, 1000, 4), (512, 512, 150, 1000, 5),
+                                                      (503, 499, 150, 1000, 6)])
+def test_css_large_cohort_default_route_1000_permutations_vs_oracle(fpt, oracle, asize, bsize, mct, mcr, seed):
+    """BASELINE configs[4] as it is benchmarked: the DEFAULT large-cohort route (Lanczos classical MDS ->
+    fpt_css_observed_kernel -> the tcgen05 / tensor-memory permutation kernel fpt_css_perm_umma_kernel) at
+    mcT / mcR = 1000, i.e. eight batches of 128 permutations per window (accumulator double-buffer phase flips, ring
+    wrap-around across batches, ndone / early-stop bookkeeping), against the CPU oracle (css.c:727-752 restated):
+    full 1000 permutations; early stops that land in batch 2..5; m = 1024 (no K / N padding); m = 1002 with unequal
+    groups (not a multiple of 4 or 8: Lanczos form 0, padded K / N tiles)."""
+    regend, wsize, wstep, nsnp = 150000, 50000, 50000, 500
+    ch, (av, bv, apos, bpos) = _synth(500 + asize, regend, nsnp, asize, bsize)
+    s_o, p_o = _css_oracle_scan(oracle, av, bv, apos, bpos, regend, wsize, wstep, mct, mcr, 0, 0, seed)
+    s_g, p_g, wr, pr = fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, mct, mcr, mds=0,
+                                    seed=seed, probes=True)
+    assert np.array_equal(wr == 1, p_o != 0) and (wr == 1).sum() == 3
+    np.testing.assert_allclose(s_g, s_o, rtol=CSS_RTOL, atol=1e-12)
+    assert np.array_equal(p_g, p_o)                                   # identical hits / permutations drawn
+    assert np.array_equal(p_g, (pr["hits"] + 1.0) / (pr["nperm"] + 1.0))
+    if mct < mcr:                                                     # an early stop beyond the second batch of 128
+        stopped = pr["nperm"][(pr["hits"] == mct)]
+        assert stopped.size and stopped.max() > 256 and stopped.max() < mcr
+    else:
+        assert np.all(pr["nperm"] == mcr)
 
 
 def test_tcgen05_plumbing_against_a_host_product():
