@@ -1,16 +1,27 @@
 #!/usr/bin/env python
 """bench.py — throughput of the two divergence scans on B200, with the reference's CPU path timed beside it.
 
-Headline workload (BASELINE.json configs[2], SURVEY.md 8(d) "C3"): CSS over a 450 Mb stickleback-sized synthetic
+Headline workload (BASELINE.json configs[2], SURVEY.md 8(d) "C3"): CSS over ONE 450 Mb stickleback-sized synthetic
 genome — 21 chromosomes, 1 SNP / 100 bp (4.5 M SNPs), 20+20 diploid individuals, wsize 2500 / wstep 500
-(~900 k windows), classical MDS, mcT = mcR = 1000 permutations per window. One step = one pass over the genome,
-one scan call per chromosome (the reference's call granularity).
+(~900 k windows), classical MDS, mcT = mcR = 1000 permutations per window. One step = one pass over the genome.
 
-  value  windows/s with the float64 genotype arrays already resident in HBM (device API, CUDA events)
-  e2e    windows/s through the drop-in host call fpt_css_compute (host -> device copies of every input from pinned
-         host memory and device -> host reads of the results inside the timed region)
-  fet    the same pair for the FET scan (BASELINE configs[0] geometry, 1 M SNPs, 20+20, 2500/500, perc 0.95)
-         plus direct 2x2 tables with coverage <= 500 (configs[3] per-GPU shard, 12.5 M tables)
+With N GPUs the genome is split into N CONTIGUOUS window ranges (fpt_b200/sharding.py: chromosomes are dealt in order, the
+chromosome a boundary falls into is cut with `partition_windows` / `snp_slice`, each side taking its SNP halo), every rank
+scans its range on its own GPU with no exchange, and scores + p are gathered ONCE with NCCL inside the timed region
+(`"scaling": "strong"`). Random streams are keyed by the window index, so the gathered result is the single-GPU result.
+
+  value     windows/s with the float64 genotype arrays already resident in HBM (device API, CUDA events, max over ranks)
+  e2e       windows/s through the host call (N = 1: the drop-in fpt_css_compute, one call per chromosome as the reference's
+            callers make them; N > 1: fpt_css_scan on every rank's range) — host -> device copies of every input from pinned
+            host memory and device -> host reads of the results inside the timed region
+  kernels   per kernel: live CUDA-event time per launch, share of the step, and algorithmic work / time / the matching
+            MEASURED peak (HBM from MEASURED_PEAKS.json; fp64, shared memory, issue slots, u8 tensor core measured by
+            profiles/microbench/peaks on this box at the start of the run)
+  fet       the FET scan (BASELINE configs[0] geometry) split over the ranks the same way, and BASELINE configs[3]: 100 M
+            direct 2x2 tables with coverage <= 500, 100/N M per GPU, scores gathered at the end
+  large_cohort  BASELINE configs[4] cohort: 500+500 individuals, 50 kb windows, whole chromosomes of 2600 windows dealt over
+            the ranks
+  replicas  (N > 1) the round-1 weak-scaling figure: one whole genome per GPU
 
 `--impl reference` times the reference's own pthreads C (oracle/_ref, compiled unmodified from the reference tree)
 on the host cores, on a bounded sample of the same workload.
@@ -21,6 +32,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -36,11 +48,13 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 CSS = dict(chromosomes=21, length=21_428_500, nsnp=214_285, asize=20, bsize=20, wsize=2500, wstep=500, mds=0,
            mct=1000, mcr=1000, seed0=20261018 + 2)
 FET = dict(length=100_000_000, nsnp=1_000_000, asize=20, bsize=20, wsize=2500, wstep=500, perc=0.95, seed0=20261018 + 0)
-FET_TABLES = dict(n=12_500_000, lo=20, hi=500, seed0=20261018 + 3)
+FET_TABLES = dict(n=100_000_000, chunks=8, lo=20, hi=500, seed0=20261018 + 3)
+LARGE = dict(seed0=20261018 + 4, asize=500, bsize=500, chromosomes=8, windows=2600, wsize=50_000, wstep=50_000,
+             snps_per_window=167, mcr=1000, cpu_windows=4)
 SEED = 20261018
 
 
-def peaks():
+def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
@@ -49,9 +63,29 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel, what="traffic"):
-    """per-launch DRAM bytes (or warp instructions, what="inst") of `kernel` from the committed ncu capture, if one has
-    been summarised"""
+def micro_peaks():
+    """fp64 / shared-memory / issue / u8-tensor peaks measured on THIS box by profiles/microbench/peaks (a few seconds);
+    the committed copy of an earlier run (profiles/r2_peaks.json) is the fallback and is named as such"""
+    exe = os.path.join(ROOT, "profiles", "microbench", "peaks")
+    try:
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        if r.returncode == 0:
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            d["source"] = "profiles/microbench/peaks run on this box at the start of this bench"
+            return d
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_peaks.json")) as f:
+            d = json.load(f)
+        d["source"] = "profiles/r2_peaks.json (committed copy of an earlier run; the live microbenchmark did not run)"
+        return d
+    except Exception:
+        return None
+
+
+def ncu_record(kernel, what="traffic"):
+    """per-launch DRAM bytes (or warp instructions, what="inst") of `kernel` from the committed ncu capture"""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_%s.json" % what)) as f:
             return json.load(f).get(kernel)
@@ -111,17 +145,8 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------------------------ data
-def make_css_genome(rank):
-    import fpt_b200.synth as synth
-    chroms = []
-    for c in range(CSS["chromosomes"]):
-        chroms.append(synth.chromosome_fast(CSS["seed0"] + 1000 * rank + c, CSS["length"], CSS["nsnp"], CSS["asize"],
-                                            CSS["bsize"], wstep=CSS["wstep"]))
-    return chroms
-
-
-def pinned_like(arr):
+# ------------------------------------------------------------------------------------------------ helpers
+def pinned_copy(arr):
     import torch
     t = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0]).dtype).pin_memory()
     v = t.numpy()
@@ -129,287 +154,610 @@ def pinned_like(arr):
     return t, v
 
 
+class Ctx:
+    """one rank's view of the job"""
+
+    def __init__(self, args, rank, world, dist):
+        import torch
+        self.args, self.rank, self.world, self.dist, self.torch = args, rank, world, dist, torch
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.current_stream()
+        self.sp = C.c_void_p(self.stream.cuda_stream)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def sum_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    def timed(self, step, nsteps, flush=None):
+        """K steps between barriers, CUDA events on the launching stream, max over ranks -> ms for all K steps"""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if flush is None:
+            self.barrier()
+            e0.record(self.stream)
+            for _ in range(nsteps):
+                step()
+            e1.record(self.stream)
+            self.barrier()
+            ms = e0.elapsed_time(e1)
+        else:                                            # L2 flushed between timed iterations
+            ms = 0.0
+            for _ in range(nsteps):
+                flush.zero_()
+                self.barrier()
+                e0.record(self.stream)
+                step()
+                e1.record(self.stream)
+                self.barrier()
+                ms += e0.elapsed_time(e1)
+        return self.max_over_ranks(ms)[0]
+
+
+def profile_json(lib):
+    buf = C.create_string_buffer(16384)
+    lib.fpt_profile_summary(buf, 16384)
+    return json.loads(buf.value.decode() or "{}")
+
+
+def genome_pieces(nchrom, nout, rank, world):
+    """the contiguous window range of the whole genome owned by `rank`, as [(chromosome, window_begin, window_end)]"""
+    from fpt_b200.sharding import partition_windows
+    gb, ge = partition_windows(nchrom * nout, world)[rank]
+    out = []
+    for c in range(nchrom):
+        b, e = max(gb, c * nout), min(ge, (c + 1) * nout)
+        if e > b:
+            out.append((c, b - c * nout, e - c * nout))
+    return out, (gb, ge)
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm: CSS
-def bench_css(lib_mod, args, rank, world, dist):
+def bench_css(lib_mod, cx, full_genome_pass):
     import torch
     import fpt_b200.synth as synth
-    from fpt_b200._lib import ScanRange, check
+    from fpt_b200._lib import Genotypes, ScanRange, check
+    from fpt_b200.sharding import partition_windows, snp_slice
+    args, rank, world, dev, sp = cx.args, cx.rank, cx.world, cx.dev, cx.sp
     lib = lib_mod.load()
-    dev = torch.device("cuda", torch.cuda.current_device())
-    chroms = make_css_genome(rank)
     asize, bsize, m = CSS["asize"], CSS["bsize"], CSS["asize"] + CSS["bsize"]
-    regend, wsize, wstep = CSS["length"], CSS["wsize"], CSS["wstep"]
-    nout = regend // wstep
-    host, resident = [], []
-    for ch in chroms:                                    # reference layout: float64 values + repeated int32 positions
-        av, bv, apos, bpos = synth.reference_layout(ch)
-        hp = [pinned_like(x) for x in (av, bv, apos, bpos)]
-        host.append(hp)
-        resident.append((hp[0][0].to(dev), hp[1][0].to(dev), torch.from_numpy(ch["pos"]).to(dev)))
-    nsnp = CSS["nsnp"]
-    planes = torch.empty(lib.fpt_dev_css_planes_bytes(nsnp, m) // 4, dtype=torch.int32, device=dev)
+    regend, wsize, wstep, nsnp = CSS["length"], CSS["wsize"], CSS["wstep"], CSS["nsnp"]
+    nout, nchrom = regend // wstep, CSS["chromosomes"]
+    total = nchrom * nout
+    ranges = partition_windows(total, world)
+    pieces, (gb, ge) = genome_pieces(nchrom, nout, rank, world)
+    need = sorted(set(c for c, _, _ in pieces)) if not full_genome_pass else list(range(nchrom))
+    chroms = {c: synth.chromosome_fast(CSS["seed0"] + c, regend, nsnp, asize, bsize, wstep=wstep) for c in need}
+    # reference layout per chromosome: float64 values + repeated int32 positions (host, pinned) and the values resident in HBM
+    host, resident = {}, {}
+    for c in need:
+        av, bv, apos, bpos = synth.reference_layout(chroms[c])
+        host[c] = [pinned_copy(x) for x in (av, bv, apos, bpos)] + [pinned_copy(chroms[c]["pos"])]
+        resident[c] = (host[c][0][0].to(dev), host[c][1][0].to(dev), torch.from_numpy(chroms[c]["pos"]).to(dev))
+    planes = torch.empty(lib.fpt_dev_css_planes_bytes(nsnp, m) // 4 + 64, dtype=torch.int32, device=dev)
     wl = torch.empty(nout, dtype=torch.int32, device=dev)
     wr = torch.empty(nout, dtype=torch.int32, device=dev)
     mx = torch.zeros(1, dtype=torch.int32, device=dev)
     ws_bytes = lib.fpt_dev_css_workspace_bytes(m, nout, CSS["mds"])
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    out_s = [torch.zeros(nout, dtype=torch.float64, device=dev) for _ in chroms]
-    out_p = [torch.zeros(nout, dtype=torch.float64, device=dev) for _ in chroms]
-    out_st = [torch.zeros(nout, dtype=torch.uint8, device=dev) for _ in chroms]
-    gathered = None
-    if world > 1:
-        gathered = torch.empty(world * len(chroms) * nout * 2, dtype=torch.float64, device=dev)
-    r = ScanRange()
-    r.regend, r.wsize, r.wstep, r.semantics, r.window_begin, r.window_end, r.seed = regend, wsize, wstep, 0, 0, nout, SEED
-    stream = torch.cuda.current_stream()
-    sp = C.c_void_p(stream.cuda_stream)
+    longest = max(e - b for b, e in ranges)
+    local = torch.zeros(2 * longest, dtype=torch.float64, device=dev)        # my scores, then my p (padded to the longest range)
+    status = torch.zeros(longest, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(world * 2 * longest, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def piece_plan(plist):
+        """per piece: SNP slice with halo, 32-SNP aligned start (whole bit-plane words), window range, output offset"""
+        plan, off = [], 0
+        for (c, wb, we) in plist:
+            pos = chroms[c]["pos"]
+            lo, hi = snp_slice(pos, wb, we, wsize, wstep)
+            r = ScanRange()
+            r.regend, r.wsize, r.wstep, r.semantics, r.window_begin, r.window_end, r.seed = regend, wsize, wstep, 0, wb, we, SEED
+            plan.append((c, lo, hi, r, off, we - wb))
+            off += we - wb
+        return plan
+
+    plan = piece_plan(pieces)
+
+    def run_pieces(plan_, out_s, out_p, out_st):
+        for (c, lo, hi, r, off, nw) in plan_:
+            da, db, dpos = resident[c]
+            ns = hi - lo
+            check(lib.fpt_dev_css_pack_f64(da.data_ptr() + lo * asize * 8, db.data_ptr() + lo * bsize * 8, ns, asize, bsize, planes.data_ptr(), sp))
+            mx.zero_()
+            check(lib.fpt_dev_window_table(dpos.data_ptr() + lo * 4, ns, C.byref(r), wl.data_ptr(), wr.data_ptr(), mx.data_ptr(), sp))
+            check(lib.fpt_dev_css_windows(planes.data_ptr(), None, asize, bsize, wl.data_ptr(), wr.data_ptr(), C.byref(r),
+                                          CSS["mct"], CSS["mcr"], CSS["mds"], ws.data_ptr(), ws_bytes, out_s.data_ptr() + off * 8,
+                                          out_p.data_ptr() + off * 8, out_st.data_ptr() + off, None, sp))
 
     def step_resident():
-        for i, (da, db, dpos) in enumerate(resident):
-            check(lib.fpt_dev_css_pack_f64(da.data_ptr(), db.data_ptr(), nsnp, asize, bsize, planes.data_ptr(), sp))
-            mx.zero_()
-            check(lib.fpt_dev_window_table(dpos.data_ptr(), nsnp, C.byref(r), wl.data_ptr(), wr.data_ptr(), mx.data_ptr(), sp))
-            out_st[i].zero_()
-            check(lib.fpt_dev_css_windows(planes.data_ptr(), None, asize, bsize, wl.data_ptr(), wr.data_ptr(), C.byref(r),
-                                          CSS["mct"], CSS["mcr"], CSS["mds"], ws.data_ptr(), ws_bytes, out_s[i].data_ptr(),
-                                          out_p[i].data_ptr(), out_st[i].data_ptr(), None, sp))
+        status.zero_()
+        run_pieces(plan, local, local[longest:], status)
         if world > 1:                                    # the only exchange: results gathered once at the end
-            local = torch.cat([torch.cat(out_s), torch.cat(out_p)])
-            dist.all_gather_into_tensor(gathered, local)
+            cx.dist.all_gather_into_tensor(gathered, local)
 
-    launches_per_step = len(chroms) * 5                  # pack, window table, tridiagonalisation, eigenvectors, permutations
+    launches_per_step = len(plan) * 5 + (1 if world > 1 else 0)   # pack, window table, tridiagonalisation, eigenvectors, permutations (+ gather)
 
-    def step_e2e():
-        total = 0
-        for (av, bv, apos, bpos) in host:
-            s = np.zeros(nout)
-            p = np.zeros(nout)
+    def e2e_piece(c, lo, hi, r, nw):
+        """host call on this rank's range of chromosome c: float64 host arrays (pinned) in, host arrays out"""
+        av, bv, apos, bpos, hpos = host[c]
+        s, p = np.zeros(nw), np.zeros(nw)
+        if world == 1:                                   # the reference's own call: the drop-in, whole chromosome
             check(lib.fpt_css_compute(av[1].ctypes.data, bv[1].ctypes.data, apos[1].ctypes.data, bpos[1].ctypes.data, 0, regend,
                                       wsize, wstep, av[1].size, bv[1].size, CSS["mct"], CSS["mcr"], 0, CSS["mds"],
                                       s.ctypes.data, p.ctypes.data))
-            total += int(np.count_nonzero(p))
-        return total
+        else:
+            g = Genotypes()
+            g.avals, g.bvals = av[1].ctypes.data + lo * asize * 8, bv[1].ctypes.data + lo * bsize * 8
+            g.pos, g.nsnp, g.asize, g.bsize = hpos[1].ctypes.data + lo * 4, hi - lo, asize, bsize
+            check(lib.fpt_css_scan(C.byref(g), C.byref(r), CSS["mct"], CSS["mcr"], 0, CSS["mds"], s.ctypes.data, p.ctypes.data, None, None))
+        return s, p
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    host_local = torch.zeros(2 * longest, dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        scored = 0
+        hv = host_local.numpy()
+        for (c, lo, hi, r, off, nw) in plan:
+            s, p = e2e_piece(c, lo, hi, r, nw)
+            hv[off:off + nw] = s
+            hv[longest + off:longest + off + nw] = p
+            scored += int(np.count_nonzero(p))
+        if world > 1:                                    # gather over NVLink, then every rank holds the genome's results on the host
+            local.copy_(host_local, non_blocking=True)
+            cx.dist.all_gather_into_tensor(gathered, local)
+            _ = gathered.cpu()
+        return scored
 
     for _ in range(args.warmup):
         step_resident()
-    barrier()
+    cx.barrier()
     lib.fpt_profile_enable(1)
-    buf = C.create_string_buffer(4096)
-    lib.fpt_profile_summary(buf, 4096)                   # clear
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    profile_json(lib)                                    # clear
     with ClockSampler(torch.cuda.current_device()) as clk:
-        barrier()
-        e0.record(stream)
-        for _ in range(args.steps):
-            step_resident()
-        e1.record(stream)
-        barrier()
-    ms = e0.elapsed_time(e1)
-    lib.fpt_profile_summary(buf, 4096)
+        ms = cx.timed(step_resident, args.steps)
+    prof = profile_json(lib)
     lib.fpt_profile_enable(0)
-    prof = json.loads(buf.value.decode())
-    scored = int(sum(int((st == 2).sum().item()) for st in out_st))
-    rechecks = int(lib.fpt_css_perm_rechecks())             # exact re-scorings since the library was loaded (all steps so far)
-    windows_per_step = len(chroms) * nout                # window slots visited per rank and step
+    my_scored = int((status == 2).sum().item())
+    scored = int(cx.sum_over_ranks(my_scored)[0])
+    rechecks = int(lib.fpt_css_perm_rechecks())          # exact re-scorings since the library was loaded (all steps so far)
+    sample = None
+    if rank == 0:
+        n0 = plan[0][5]
+        sample = (chroms[0], host[0], local[:n0].cpu().numpy(), local[longest:longest + n0].cpu().numpy())
 
-    # the other two MDS variants of BASELINE configs[2], on chromosome 0 only (device-resident, one warm-up + one timed pass each)
+    # the other two MDS variants of BASELINE configs[2], on chromosome 0 only (rank 0, device-resident, warm-up + one timed pass each)
     variants = {}
-    if not args.small or True:
+    if rank == 0:
         da, db, dpos = resident[0]
+        r = ScanRange()
+        r.regend, r.wsize, r.wstep, r.semantics, r.window_begin, r.window_end, r.seed = regend, wsize, wstep, 0, 0, nout, SEED
         check(lib.fpt_dev_css_pack_f64(da.data_ptr(), db.data_ptr(), nsnp, asize, bsize, planes.data_ptr(), sp))
         mx.zero_()
         check(lib.fpt_dev_window_table(dpos.data_ptr(), nsnp, C.byref(r), wl.data_ptr(), wr.data_ptr(), mx.data_ptr(), sp))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        from fpt_b200._lib import CssProbes
         for mds_v in (1, 2):
+            nruns = 4 if mds_v == 1 else 1
             wsb = lib.fpt_dev_css_workspace_bytes(m, nout, mds_v)
             wsv = torch.empty(wsb, dtype=torch.uint8, device=dev)
             sv, pv, stv = (torch.zeros(nout, dtype=torch.float64, device=dev), torch.zeros(nout, dtype=torch.float64, device=dev),
                            torch.zeros(nout, dtype=torch.uint8, device=dev))
+            iters = torch.zeros(nout * nruns, dtype=torch.int32, device=dev)
+            pr = CssProbes()
+            pr.smacof_iters = iters.data_ptr()
+            lib.fpt_profile_enable(1)
             for it in range(2):
                 stv.zero_()
                 torch.cuda.synchronize()
-                e0.record(stream)
+                profile_json(lib)
+                e0.record(cx.stream)
                 check(lib.fpt_dev_css_windows(planes.data_ptr(), None, asize, bsize, wl.data_ptr(), wr.data_ptr(), C.byref(r),
                                               CSS["mct"], CSS["mcr"], mds_v, wsv.data_ptr(), wsb, sv.data_ptr(), pv.data_ptr(),
-                                              stv.data_ptr(), None, sp))
-                e1.record(stream)
+                                              stv.data_ptr(), C.byref(pr), sp))
+                e1.record(cx.stream)
                 torch.cuda.synchronize()
+            vprof = profile_json(lib)
+            lib.fpt_profile_enable(0)
+            nsc = int((stv == 2).sum().item())
+            tot_iters = int(iters.view(nout, nruns)[stv == 2].sum().item())
             variants["mds%d" % mds_v] = {"windows_per_s": nout / (e0.elapsed_time(e1) * 1e-3), "ms_per_chromosome": e0.elapsed_time(e1),
-                                         "windows_scored": int((stv == 2).sum().item())}
+                                         "windows_scored": nsc, "smacof_iterations_total": tot_iters,
+                                         "kernel_ms": {k: v["ms"] for k, v in vprof.items()}}
             del wsv
-    lib.fpt_profile_summary(buf, 4096)                   # drop the variants' launches from the per-kernel record
 
-    # end to end through the drop-in host call
+    # end to end through the host call
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
-    barrier()
+    cx.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         scored_e2e = step_e2e()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
-    tt = torch.tensor([ms, t_e2e * 1000.0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(tt[0].item()), float(tt[1].item())
-    h2d = sum(av[1].nbytes + bv[1].nbytes + 4 * nsnp for (av, bv, apos, bpos) in host)
-    d2h = len(chroms) * nout * 17
-    return dict(ms=ms, ms_e2e=ms_e2e, windows_per_step=windows_per_step, scored=scored, scored_e2e=scored_e2e, prof=prof,
+    ms_e2e = cx.max_over_ranks(t_e2e * 1000.0)[0]
+    scored_e2e = int(cx.sum_over_ranks(scored_e2e)[0])
+    h2d = sum((hi - lo) * (m * 8 + 4) for (c, lo, hi, r, off, nw) in plan)
+    d2h = sum(nw * 17 for (c, lo, hi, r, off, nw) in plan)
+    h2d, d2h = [int(x) for x in cx.sum_over_ranks(h2d, d2h)]
+
+    # pageable host memory (what HyperBrowser hands over): the drop-in on chromosome 0 with plain numpy arrays, rank 0, N = 1 only
+    pageable = None
+    if world == 1:
+        av, bv, apos, bpos = synth.reference_layout(chroms[0])
+        ts = []
+        for it in range(3):
+            s, p = np.zeros(nout), np.zeros(nout)
+            t0 = time.perf_counter()
+            check(lib.fpt_css_compute(av.ctypes.data, bv.ctypes.data, apos.ctypes.data, bpos.ctypes.data, 0, regend, wsize, wstep, av.size,
+                                      bv.size, CSS["mct"], CSS["mcr"], 0, CSS["mds"], s.ctypes.data, p.ctypes.data))
+            ts.append(time.perf_counter() - t0)
+        pageable = {"value": nout / min(ts[1:]), "unit": "windows/s", "api": "fpt_css_compute, pageable numpy arrays, chromosome 0",
+                    "ms_per_chromosome": min(ts[1:]) * 1e3}
+
+    # secondary: one whole genome per GPU (round-1 weak-scaling replicas)
+    replicas = None
+    if world > 1 and full_genome_pass:
+        plan_full = piece_plan([(c, 0, nout) for c in range(nchrom)])
+        fs = torch.zeros(total, dtype=torch.float64, device=dev)
+        fp_ = torch.zeros(total, dtype=torch.float64, device=dev)
+        fst = torch.zeros(total, dtype=torch.uint8, device=dev)
+        run_pieces(plan_full, fs, fp_, fst)
+        ms_rep = cx.timed(lambda: run_pieces(plan_full, fs, fp_, fst), 2)
+        replicas = {"value": world * total / (ms_rep / 2 * 1e-3), "unit": "windows/s", "scaling": "weak", "ms_per_step": ms_rep / 2,
+                    "config": "one whole 450 Mb genome per GPU, no exchange (the round-1 figure)"}
+    return dict(ms=ms, ms_e2e=ms_e2e, total_windows=total, scored=scored, scored_e2e=scored_e2e, prof=prof, my_windows=ge - gb,
                 launches=launches_per_step * args.steps, h2d=h2d, d2h=d2h, rechecks=rechecks, variants=variants, clocks=clk.summary(),
-                sample=(chroms[0], host[0], out_s[0].cpu().numpy(), out_p[0].cpu().numpy()))
-
-
-def css_kernel_bytes(name, windows, nsnp_total, m):
-    """algorithmic HBM bytes of one step, per kernel (DESIGN.md section 'Kernels and rooflines')"""
-    if name == "css_perm":      # embedding in (16 m), status in (1), score + p out (16)
-        return windows * (16 * m + 17)
-    if name == "css_tridiag":   # the window's bit-plane slab in, window bounds (8); tridiagonal (24 m) + reflectors (4 m (m-1)) + status out
-        return windows * (2 * 2 * m * 4 + 8 + 24 * m + 4 * m * (m - 1) + 1)
-    if name == "css_eigvec":    # tridiagonal + reflectors + status in, embedding (16 m) out
-        return windows * (24 * m + 4 * m * (m - 1) + 1 + 16 * m)
-    if name == "css_mds_large":  # Lanczos kernel, ~80 steps: the matrix as 8-bit codes per step + four passes over the growing basis
-        return windows * (80 * m * m + 4 * 8 * m * (80 * 81 // 2))
-    if name == "css_pack":      # float64 genotypes in, two bit-planes out
-        return nsnp_total * m * 8 + nsnp_total * m // 4
-    if name == "window_table":  # positions are binary-searched (L2 resident); two int32 out
-        return windows * 8
-    return 0
+                sample=sample, pageable=pageable, replicas=replicas, pieces=len(plan), my_scored=my_scored)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm: FET
-def bench_fet(lib_mod, args):
+def bench_fet(lib_mod, cx):
     import torch
     import fpt_b200.synth as synth
-    from fpt_b200._lib import ScanRange, check
+    from fpt_b200._lib import Genotypes, ScanRange, check
+    from fpt_b200.sharding import partition_windows, snp_slice
+    args, rank, world, dev, sp = cx.args, cx.rank, cx.world, cx.dev, cx.sp
     lib = lib_mod.load()
-    dev = torch.device("cuda", torch.cuda.current_device())
     ch = synth.chromosome_fast(FET["seed0"], FET["length"], FET["nsnp"], FET["asize"], FET["bsize"], wstep=FET["wstep"])
-    av, bv, apos, bpos = synth.reference_layout(ch)
-    hp = [pinned_like(x) for x in (av, bv, apos, bpos)]
-    del av, bv, apos, bpos
     nsnp, asize, bsize = FET["nsnp"], FET["asize"], FET["bsize"]
     regend, wsize, wstep = FET["length"], FET["wsize"], FET["wstep"]
     nout = regend // wstep
+    ranges = partition_windows(nout, world)
+    wb, we = ranges[rank]
+    lo, hi = snp_slice(ch["pos"], wb, we, wsize, wstep)
+    ns, nw = hi - lo, we - wb
+    sub = {"pos": ch["pos"][lo:hi], "acodes": ch["acodes"][lo * asize:hi * asize], "bcodes": ch["bcodes"][lo * bsize:hi * bsize],
+           "asize": asize, "bsize": bsize}
+    av, bv, apos, bpos = synth.reference_layout(sub)
+    hp = [pinned_copy(x) for x in (av, bv, apos, bpos, sub["pos"], sub["acodes"], sub["bcodes"])]
     da, db = hp[0][0].to(dev), hp[1][0].to(dev)
-    dpos = torch.from_numpy(ch["pos"]).to(dev)
-    tab = torch.empty(nsnp * 4, dtype=torch.int32, device=dev)
-    snp = torch.empty(nsnp, dtype=torch.float64, device=dev)
-    wl = torch.empty(nout, dtype=torch.int32, device=dev)
-    wr = torch.empty(nout, dtype=torch.int32, device=dev)
+    dpos = hp[4][0].to(dev)
+    tab = torch.empty(ns * 4, dtype=torch.int32, device=dev)
+    snp = torch.empty(ns, dtype=torch.float64, device=dev)
+    wl = torch.empty(nw, dtype=torch.int32, device=dev)
+    wr = torch.empty(nw, dtype=torch.int32, device=dev)
     mx = torch.zeros(1, dtype=torch.int32, device=dev)
-    osc = torch.zeros(nout, dtype=torch.float64, device=dev)
-    osd = torch.zeros(nout, dtype=torch.float64, device=dev)
-    ofl = torch.zeros(nout, dtype=torch.uint8, device=dev)
+    longest = max(e - b for b, e in ranges)
+    local = torch.zeros(2 * longest, dtype=torch.float64, device=dev)
+    ofl = torch.zeros(nw, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(world * 2 * longest, dtype=torch.float64, device=dev) if world > 1 else None
     r = ScanRange()
-    r.regend, r.wsize, r.wstep, r.semantics, r.window_begin, r.window_end, r.seed = regend, wsize, wstep, 0, 0, nout, SEED
-    stream = torch.cuda.current_stream()
-    sp = C.c_void_p(stream.cuda_stream)
+    r.regend, r.wsize, r.wstep, r.semantics, r.window_begin, r.window_end, r.seed = regend, wsize, wstep, 0, wb, we, SEED
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > L2 (126 MB)
 
     def step():
-        check(lib.fpt_dev_fet_count_f64(da.data_ptr(), db.data_ptr(), nsnp, asize, bsize, tab.data_ptr(), sp))
-        check(lib.fpt_dev_fet_score(tab.data_ptr(), nsnp, asize + bsize, 0, snp.data_ptr(), sp))
+        check(lib.fpt_dev_fet_count_f64(da.data_ptr(), db.data_ptr(), ns, asize, bsize, tab.data_ptr(), sp))
+        check(lib.fpt_dev_fet_score(tab.data_ptr(), ns, asize + bsize, 0, snp.data_ptr(), sp))
         mx.zero_()
-        check(lib.fpt_dev_window_table(dpos.data_ptr(), nsnp, C.byref(r), wl.data_ptr(), wr.data_ptr(), mx.data_ptr(), sp))
+        check(lib.fpt_dev_window_table(dpos.data_ptr(), ns, C.byref(r), wl.data_ptr(), wr.data_ptr(), mx.data_ptr(), sp))
         max_npos = int(mx.item())                        # the one host read the scan needs (sizes shared memory)
         ofl.zero_()
         check(lib.fpt_dev_fet_windows(snp.data_ptr(), wl.data_ptr(), wr.data_ptr(), C.byref(r), max_npos, FET["perc"], None,
-                                      osc.data_ptr(), osd.data_ptr(), ofl.data_ptr(), sp))
+                                      local.data_ptr(), local.data_ptr() + longest * 8, ofl.data_ptr(), sp))
+        if world > 1:
+            cx.dist.all_gather_into_tensor(gathered, local)
 
     for _ in range(args.warmup):
         step()
-    torch.cuda.synchronize()
+    cx.barrier()
     lib.fpt_profile_enable(1)
-    buf = C.create_string_buffer(4096)
-    lib.fpt_profile_summary(buf, 4096)
-    tot = 0.0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(args.steps):
-        flush.zero_()                                    # L2 flush between timed iterations (inputs are 320 MB anyway)
-        torch.cuda.synchronize()
-        e0.record(stream)
-        step()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    lib.fpt_profile_summary(buf, 4096)
+    profile_json(lib)
+    ms = cx.timed(step, args.steps, flush=flush) / args.steps
+    prof = profile_json(lib)
     lib.fpt_profile_enable(0)
-    prof = json.loads(buf.value.decode())
-    ms = tot / args.steps
 
-    def e2e():
-        s, d = np.zeros(nout), np.zeros(nout)
-        check(lib.fpt_fet_compute(hp[0][1].ctypes.data, hp[1][1].ctypes.data, hp[2][1].ctypes.data, hp[3][1].ctypes.data, 0,
-                                  regend, wsize, wstep, hp[0][1].size, hp[1][1].size, FET["perc"], s.ctypes.data, d.ctypes.data))
+    def host_call(which):
+        s, d = np.zeros(nw), np.zeros(nw)
+        if which == "dropin":                            # N = 1: the reference's call
+            check(lib.fpt_fet_compute(hp[0][1].ctypes.data, hp[1][1].ctypes.data, hp[2][1].ctypes.data, hp[3][1].ctypes.data, 0,
+                                      regend, wsize, wstep, hp[0][1].size, hp[1][1].size, FET["perc"], s.ctypes.data, d.ctypes.data))
+        else:
+            g = Genotypes()
+            if which == "f64":
+                g.avals, g.bvals = hp[0][1].ctypes.data, hp[1][1].ctypes.data
+            else:
+                g.acodes, g.bcodes = hp[5][1].ctypes.data, hp[6][1].ctypes.data
+            g.pos, g.nsnp, g.asize, g.bsize = hp[4][1].ctypes.data, ns, asize, bsize
+            check(lib.fpt_fet_scan(C.byref(g), C.byref(r), FET["perc"], s.ctypes.data, d.ctypes.data, None))
+        return s, d
+
+    host_local = torch.zeros(2 * longest, dtype=torch.float64).pin_memory()
+
+    def e2e(which):
+        s, d = host_call(which)
+        if world > 1:
+            hv = host_local.numpy()
+            hv[:nw] = s
+            hv[longest:longest + nw] = d
+            local.copy_(host_local, non_blocking=True)
+            cx.dist.all_gather_into_tensor(gathered, local)
+            _ = gathered.cpu()
         return s
-    for _ in range(2):
-        e2e()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        s_host = e2e()
-    ms_e2e = (time.perf_counter() - t0) * 1000.0 / args.steps
-    hbm, hbm_src = peaks()
-    kbytes = {"fet_count": nsnp * ((asize + bsize) * 8 + 16), "fet_score": nsnp * 24,
-              "fet_window": nout * 24 + nsnp * 8 * (wsize // wstep), "window_table": nout * 8}
-    dom = max(prof, key=lambda k: prof[k]["ms"])
-    share = {k: round(v["ms"] / sum(x["ms"] for x in prof.values()), 4) for k, v in prof.items()}
-    per_launch_ms = prof[dom]["ms"] / prof[dom]["launches"]
-    ach = kbytes.get(dom, 0) / (per_launch_ms * 1e-3) / 1e9
-    cnt_ms = prof["fet_count"]["ms"] / prof["fet_count"]["launches"]
+
+    def time_e2e(which):
+        for _ in range(2):
+            e2e(which)
+        cx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            s_host = e2e(which)
+        torch.cuda.synchronize()
+        return cx.max_over_ranks((time.perf_counter() - t0) * 1000.0 / args.steps)[0], s_host
+
+    ms_e2e, s_host = time_e2e("dropin" if world == 1 else "f64")
+    ms_e2e_i8, _ = time_e2e("i8")
+    pageable = None
+    if world == 1:
+        pav, pbv, papos, pbpos = (np.array(hp[k][1]) for k in range(4))         # plain (pageable) numpy copies
+        ts = []
+        for it in range(3):
+            s, d = np.zeros(nw), np.zeros(nw)
+            t0 = time.perf_counter()
+            check(lib.fpt_fet_compute(pav.ctypes.data, pbv.ctypes.data, papos.ctypes.data, pbpos.ctypes.data, 0, regend, wsize, wstep,
+                                      pav.size, pbv.size, FET["perc"], s.ctypes.data, d.ctypes.data))
+            ts.append(time.perf_counter() - t0)
+        pageable = {"value": nsnp / min(ts[1:]), "unit": "SNPs/s", "api": "fpt_fet_compute, pageable numpy arrays"}
+        del pav, pbv, papos, pbpos
     out = {
-        "metric": "fet_snps_per_sec", "unit": "SNPs/s", "value": nsnp / (ms * 1e-3), "ms_per_step": ms,
-        "config": {"workload": "FET scan, 1 chromosome 100 Mb, 1M SNPs, 20+20, wsize 2500 / wstep 500, perc 0.95 "
-                               "(BASELINE configs[0] geometry); L2 flushed between steps", "windows": nout},
+        "metric": "fet_snps_per_sec", "unit": "SNPs/s", "value": nsnp / (ms * 1e-3), "ms_per_step": ms, "n_gpus": world,
+        "scaling": "strong",
+        "config": {"workload": "FET scan, 1 chromosome 100 Mb, 1M SNPs, 20+20, wsize 2500 / wstep 500, perc 0.95 (BASELINE configs[0] "
+                               "geometry), windows split into %d contiguous ranges with SNP halos, scores + sigma gathered once; "
+                               "L2 flushed between steps" % world, "windows": nout},
         "dtype": "f64",
-        "e2e": {"value": nsnp / (ms_e2e * 1e-3), "unit": "SNPs/s", "h2d_bytes_per_step": hp[0][1].nbytes + hp[1][1].nbytes + 4 * nsnp,
-                "d2h_bytes_per_step": nout * 17, "api": "fpt_fet_compute (drop-in, host float64 arrays)"},
-        "gpu_launches": 4 * args.steps,
-        "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                     "peak_source": hbm_src, "traffic": ncu_traffic(dom), "share_of_step": share,
-                     "note": "fet_window is integer/shared-memory bound (100 x npos LCG draws per window); "
-                             "the HBM-bound stage is fet_count, listed in roofline_hbm_stage"},
-        "roofline_hbm_stage": {"kernel": "fet_count", "bound": "hbm", "achieved": kbytes["fet_count"] / (cnt_ms * 1e-3) / 1e9,
-                               "peak": hbm, "unit": "GB/s", "frac": kbytes["fet_count"] / (cnt_ms * 1e-3) / 1e9 / hbm,
-                               "traffic": ncu_traffic("fet_count")},
+        "e2e": {"value": nsnp / (ms_e2e * 1e-3), "unit": "SNPs/s", "h2d_bytes_per_step": nsnp * ((asize + bsize) * 8 + 4),
+                "d2h_bytes_per_step": nout * 17,
+                "api": "fpt_fet_compute (drop-in, host float64 arrays, pinned)" if world == 1 else "fpt_fet_scan per rank (host float64, pinned) + NCCL gather"},
+        "e2e_int8": {"value": nsnp / (ms_e2e_i8 * 1e-3), "unit": "SNPs/s", "h2d_bytes_per_step": nsnp * ((asize + bsize) + 4),
+                     "d2h_bytes_per_step": nout * 17, "api": "fpt_fet_scan (host int8 codes, pinned): 8x fewer PCIe bytes than the drop-in layout"},
+        "e2e_pageable": pageable,
+        "gpu_launches": (4 + (1 if world > 1 else 0)) * args.steps,
+        "_prof": prof, "_ns": ns, "_nw": nw,
     }
-    # direct 2x2 tables, coverage <= 500 (BASELINE configs[3], one GPU's shard of 100 M)
-    n = FET_TABLES["n"]
+    return out, (ch, s_host, wb, we)
+
+
+def tables_chunk(torch, dev, k, n):
+    """chunk k of the configs[3] tables: row sums U{lo..hi}, a ~ Bin(n1, f), c ~ Bin(n2, f_B); the same data
+    whatever the number of ranks"""
     g = torch.Generator(device=dev)
-    g.manual_seed(FET_TABLES["seed0"])
+    g.manual_seed(FET_TABLES["seed0"] + 1000 * k)
     n1 = torch.randint(FET_TABLES["lo"], FET_TABLES["hi"] + 1, (n,), device=dev, generator=g).double()
     n2 = torch.randint(FET_TABLES["lo"], FET_TABLES["hi"] + 1, (n,), device=dev, generator=g).double()
     f = torch.rand(n, device=dev, generator=g, dtype=torch.float64).clamp(0.02, 0.98)
     fb = (f + 0.05 * torch.randn(n, device=dev, generator=g, dtype=torch.float64)).clamp(0.01, 0.99)
     a = torch.binomial(n1, f, generator=g)
     c = torch.binomial(n2, fb, generator=g)
-    T = torch.stack([a, n1 - a, c, n2 - c], dim=1).to(torch.int32).contiguous()
-    del n1, n2, f, fb, a, c
-    outp = torch.empty(n, dtype=torch.float64, device=dev)
+    return torch.stack([a, n1 - a, c, n2 - c], dim=1).to(torch.int32).contiguous()
+
+
+def walk_lengths(T):
+    """per table: a0 = first-tail length (the minimum cell) and T2 = terms of the opposite tail the reference's walk visits
+    (tables on the far side whose probability is below the observed one; cFisher.c:405-455) — SURVEY 8(d) K2 work model"""
+    from scipy.special import gammaln
+    T = T.astype(np.int64)
+    a, b, c, d = T[:, 0], T[:, 1], T[:, 2], T[:, 3]
+    R1, C1, N = a + b, a + c, a + b + c + d
+    lo_, hi_ = np.maximum(0, R1 + C1 - N), np.minimum(R1, C1)
+    a0 = np.minimum(np.minimum(a, b), np.minimum(c, d))
+    width = int((hi_ - lo_).max()) + 1
+    x = lo_[:, None] + np.arange(width)[None, :]
+    valid = x <= hi_[:, None]
+    xa = np.where(valid, x, lo_[:, None])
+
+    def lpmf(xx):
+        return -(gammaln(xx + 1) + gammaln(R1[:, None] - xx + 1) + gammaln(C1[:, None] - xx + 1) + gammaln(N[:, None] - R1[:, None] - C1[:, None] + xx + 1))
+    lp = lpmf(xa)
+    lobs = lpmf(a[:, None])
+    # the observed side: the tail that runs towards the extreme where the minimum cell reaches 0
+    towards_low = (a == a0) | (d == a0)                  # a (or d) shrinks -> x decreases
+    far = np.where(towards_low[:, None], xa > a[:, None], xa < a[:, None])
+    t2 = (valid & far & (lp < lobs - 1e-12)).sum(axis=1)
+    sym = (R1 == (N - R1)) | (C1 == (N - C1))            # cFisher.c:430: P doubled, no second walk
+    t2 = np.where(sym, 0, t2)
+    return a0, t2
+
+
+def bench_fet_tables(lib_mod, cx):
+    import torch
+    from fpt_b200._lib import check
+    args, rank, world, dev, sp = cx.args, cx.rank, cx.world, cx.dev, cx.sp
+    lib = lib_mod.load()
+    nchunks = FET_TABLES["chunks"]
+    per = FET_TABLES["n"] // nchunks
+    mine = [k for k in range(nchunks) if k * world // nchunks == rank] if world <= nchunks else ([rank] if rank < nchunks else [])
+    T = torch.cat([tables_chunk(torch, dev, k, per) for k in mine]) if mine else torch.zeros((0, 4), dtype=torch.int32, device=dev)
+    n_local = T.shape[0]
+    n_total = per * nchunks
+    longest = per * max(1, nchunks // min(world, nchunks))
+    outp = torch.zeros(longest, dtype=torch.float64, device=dev)
+    gathered = torch.empty(world * longest, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        if n_local:
+            check(lib.fpt_dev_fet_score(T.data_ptr(), n_local, 1000, 0, outp.data_ptr(), sp))
+        if world > 1:
+            cx.dist.all_gather_into_tensor(gathered, outp)
+
     for _ in range(args.warmup):
-        check(lib.fpt_dev_fet_score(T.data_ptr(), n, 1000, 0, outp.data_ptr(), sp))
+        step()
+    cx.barrier()
+    lib.fpt_profile_enable(1)
+    profile_json(lib)
+    ms = cx.timed(step, args.steps) / args.steps         # inputs (>= 200 MB per GPU) exceed L2, no flush needed
+    prof = profile_json(lib)
+    lib.fpt_profile_enable(0)
+    k_ms = prof.get("fet_score", {}).get("ms", 0.0) / max(1, prof.get("fet_score", {}).get("launches", 1))
+    k_ms = cx.max_over_ranks(k_ms)[0]
+    # end to end: host int32 tables (pinned) -> host float64 scores
+    e2e_ms = None
+    if n_local:
+        hT = torch.empty((n_local, 4), dtype=torch.int32).pin_memory()
+        hT.copy_(T)
+        ho = np.zeros(n_local)
+        for _ in range(1):
+            check(lib.fpt_fet_tables(hT.data_ptr(), n_local, 0, ho.ctypes.data))
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps - 1)):
+        if n_local:
+            check(lib.fpt_fet_tables(hT.data_ptr(), n_local, 0, ho.ctypes.data))
+        if world > 1:
+            outp[:n_local].copy_(torch.from_numpy(ho), non_blocking=True)
+            cx.dist.all_gather_into_tensor(gathered, outp)
+            _ = gathered.cpu()
     torch.cuda.synchronize()
-    tot = 0.0
-    for _ in range(args.steps):
-        flush.zero_()
+    e2e_ms = cx.max_over_ranks((time.perf_counter() - t0) * 1000.0 / max(1, args.steps - 1))[0]
+    # work model on a sample of this rank's tables (rank 0 reports)
+    work = None
+    if rank == 0 and n_local:
+        smp = T[:: max(1, n_local // 131072)][:131072].cpu().numpy()
+        a0, t2 = walk_lengths(smp)
+        Tw = (a0 + t2).astype(np.float64)
+        work = {"sample_tables": int(smp.shape[0]), "mean_first_tail": float(a0.mean()), "mean_second_tail": float(t2.mean()),
+                "mean_T": float(Tw.mean()), "p99_T": float(np.percentile(Tw, 99)), "max_T": float(Tw.max()),
+                "sum_T_scaled_to_all_tables": float(Tw.mean() * n_total),
+                "warp_divergence_factor": float(np.mean([Tw[i:i + 32].max() for i in range(0, len(Tw) - 31, 32)]) / max(Tw.mean(), 1e-9)),
+                "note": "T = a0 + T2 per table: steps of the reference's two-tailed walk (cFisher.c:405-455); warp_divergence_factor = "
+                        "mean over warps of the longest walk in the warp / mean walk (1 = no divergence loss with one thread per table)"}
+    return {"metric": "fet_snps_per_sec", "unit": "SNPs/s", "value": n_total / (ms * 1e-3), "ms_per_step": ms, "n_gpus": world,
+            "scaling": "strong", "dtype": "f64",
+            "config": {"workload": "BASELINE configs[3]: %d M direct 2x2 tables, row sums U{20..500}, log-space arithmetic, %s tables per GPU, "
+                                   "scores gathered with NCCL at the end (inside the timed region); inputs exceed L2" % (
+                                       n_total // 1_000_000, "%.1f M" % (n_total / world / 1e6)), "tables": n_total},
+            "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "SNPs/s", "h2d_bytes_per_step": n_total * 16, "d2h_bytes_per_step": n_total * 8,
+                    "api": "fpt_fet_tables (host int32 tables, pinned)" + (" per rank + NCCL gather" if world > 1 else "")},
+            "gpu_launches": args.steps, "_kernel_ms": k_ms, "_work": work, "_n_local_max": longest}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm: large cohort
+def large_chromosome(torch, dev, nwin):
+    """one configs[4] chromosome generated on the device (a host generator needs minutes for 434 M genotypes): positions uniform
+    and sorted, f ~ U(0.02, 0.98) per SNP shared by both populations, genotype = number of minor alleles of two draws,
+    codes 3 / 0 / -3, 2 % missing (-128)"""
+    g = torch.Generator(device=dev)
+    g.manual_seed(LARGE["seed0"])
+    nsnp = LARGE["snps_per_window"] * nwin
+    regend = LARGE["wstep"] * nwin
+    pos = torch.sort(torch.randperm(regend, device=dev, generator=g)[:nsnp]).values.to(torch.int32)
+    f = torch.rand(nsnp, device=dev, generator=g) * 0.96 + 0.02
+    out = []
+    for size in (LARGE["asize"], LARGE["bsize"]):
+        u = torch.rand((nsnp, size, 2), device=dev, generator=g)
+        minor = (u < f[:, None, None]).sum(dim=2)
+        codes = (3 - 3 * minor).to(torch.int8)
+        miss = torch.rand((nsnp, size), device=dev, generator=g) < 0.02
+        codes[miss] = -128
+        out.append(codes.reshape(-1).contiguous())
+    return pos.contiguous(), out[0], out[1], regend, nsnp
+
+
+def bench_large_cohort(lib_mod, cx):
+    """BASELINE configs[4] cohort (500+500 individuals, 50 kb windows, ~167 SNPs per window): whole chromosomes of 2600 windows,
+    dealt over the ranks (chromosome k goes to rank k % N); one synthetic chromosome is reused with a different random-stream
+    seed per chromosome. Kernels: bit-plane packing, window table, Lanczos classical MDS, observed scores (a warp per window),
+    permutation test with the between-group sums of 128 permutations as one tcgen05 u8 contraction in tensor memory."""
+    import torch
+    import fpt_b200.api as api
+    from fpt_b200._lib import ScanRange, check
+    args, rank, world, dev, sp = cx.args, cx.rank, cx.world, cx.dev, cx.sp
+    lib = lib_mod.load()
+    nwin = LARGE["windows"] if not args.small else 8
+    nchrom = LARGE["chromosomes"] if not args.small else 2
+    asize, bsize = LARGE["asize"], LARGE["bsize"]
+    m = asize + bsize
+    dpos, da, db, regend, nsnp = large_chromosome(torch, dev, nwin)
+    mine = [k for k in range(nchrom) if k % world == rank]
+    planes = torch.empty(lib.fpt_dev_css_planes_bytes(nsnp, m) // 4 + 64, dtype=torch.int32, device=dev)
+    wl = torch.empty(nwin, dtype=torch.int32, device=dev)
+    wr = torch.empty(nwin, dtype=torch.int32, device=dev)
+    mx = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib.fpt_dev_css_workspace_bytes(m, nwin, 0)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    per_rank = -(-nchrom // world)
+    local = torch.zeros(2 * per_rank * nwin, dtype=torch.float64, device=dev)
+    status = torch.zeros(per_rank * nwin, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(world * local.numel(), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        status.zero_()
+        for i, k in enumerate(mine):
+            r = ScanRange()
+            r.regend, r.wsize, r.wstep, r.semantics, r.window_begin, r.window_end, r.seed = regend, LARGE["wsize"], LARGE["wstep"], 0, 0, nwin, SEED + k
+            check(lib.fpt_dev_css_pack_i8(da.data_ptr(), db.data_ptr(), nsnp, asize, bsize, planes.data_ptr(), sp))
+            mx.zero_()
+            check(lib.fpt_dev_window_table(dpos.data_ptr(), nsnp, C.byref(r), wl.data_ptr(), wr.data_ptr(), mx.data_ptr(), sp))
+            check(lib.fpt_dev_css_windows(planes.data_ptr(), None, asize, bsize, wl.data_ptr(), wr.data_ptr(), C.byref(r), LARGE["mcr"],
+                                          LARGE["mcr"], 0, ws.data_ptr(), ws_bytes, local.data_ptr() + i * nwin * 8,
+                                          local.data_ptr() + (per_rank + i) * nwin * 8, status.data_ptr() + i * nwin, None, sp))
+        if world > 1:
+            cx.dist.all_gather_into_tensor(gathered, local)
+
+    step()                                               # warm-up (first call pays the scratch allocation)
+    cx.barrier()
+    lib.fpt_profile_enable(1)
+    profile_json(lib)
+    nsteps = 1 if args.small else max(1, min(args.steps, 2))
+    ms = cx.timed(step, nsteps) / nsteps
+    prof = profile_json(lib)
+    lib.fpt_profile_enable(0)
+    scored = int(cx.sum_over_ranks(int((status == 2).sum().item()))[0])
+    # end to end: host int8 codes (pinned) through fpt_css_scan, one call per chromosome
+    hpos, ha, hb = (pinned_copy(x.cpu().numpy()) for x in (dpos, da, db))
+    t_e2e = None
+    for it in range(2):
+        cx.barrier()
+        t0 = time.perf_counter()
+        for k in mine:
+            s, p, w = api.css_scan(ha[1], hb[1], hpos[1], asize, bsize, regend, LARGE["wsize"], LARGE["wstep"], LARGE["mcr"], LARGE["mcr"], mds=0, seed=SEED + k)
         torch.cuda.synchronize()
-        e0.record(stream)
-        check(lib.fpt_dev_fet_score(T.data_ptr(), n, 1000, 0, outp.data_ptr(), sp))
-        e1.record(stream)
-        torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    ms_t = tot / args.steps
-    out["tables"] = {"metric": "fet_snps_per_sec", "value": n / (ms_t * 1e-3), "unit": "SNPs/s", "ms_per_step": ms_t,
-                     "config": {"workload": "direct 2x2 tables, row sums U{20..500} (BASELINE configs[3], one GPU's shard of "
-                                            "100 M), log-space arithmetic; L2 flushed between steps", "tables": n},
-                     "roofline": {"kernel": "fet_score", "bound": "hbm", "achieved": n * 24 / (ms_t * 1e-3) / 1e9, "peak": hbm,
-                                  "unit": "GB/s", "frac": n * 24 / (ms_t * 1e-3) / 1e9 / hbm,
-                                  "note": "fp64-pipe bound at this coverage (tail walks of 20-250 divide steps per table)"}}
-    return out, (ch, hp, s_host)
+        t_e2e = cx.max_over_ranks(time.perf_counter() - t0)[0]
+    first = None
+    if rank == 0:
+        first = (hpos[1], ha[1], hb[1], local[:nwin].cpu().numpy(), local[per_rank * nwin:per_rank * nwin + nwin].cpu().numpy(), regend)
+    return {"metric": "css_windows_per_sec_1000perms", "unit": "windows/s", "value": nchrom * nwin / (ms * 1e-3), "ms_per_step": ms,
+            "n_gpus": world, "scaling": "strong", "dtype": "f64",
+            "e2e": {"value": nchrom * nwin / t_e2e, "unit": "windows/s", "api": "fpt_css_scan (host int8 codes, pinned), one call per chromosome",
+                    "h2d_bytes_per_step": int(nchrom * (nsnp * m + nsnp * 4)), "d2h_bytes_per_step": int(nchrom * nwin * 17)},
+            "config": {"workload": "CSS scan, BASELINE configs[4] cohort: %d chromosomes x %d windows (%d of the 60 000 windows of the 3 Gb genome), 500+500 "
+                                   "individuals, 50 kb windows, ~%d SNPs per window, classical MDS, mcT=mcR=1000; chromosome k on rank k %% N, "
+                                   "results gathered once" % (nchrom, nwin, nchrom * nwin, LARGE["snps_per_window"]),
+                       "windows_scored": scored},
+            "gpu_launches": len(mine) * 5 * nsteps, "_prof": prof, "_first": first, "_nwin": nwin, "_chrom_per_rank": len(mine)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -439,7 +787,7 @@ def cpu_css(sample_windows, steps=1, warmup=0):
             dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return dict(seconds=times, windows=n, scores=s[:n], sub=(av, bv, sub["pos"], regend))
+    return dict(seconds=times, windows=n, scores=s[:n])
 
 
 def cpu_fet(sample_snps):
@@ -465,13 +813,63 @@ def cpu_fet(sample_snps):
     return dict(seconds=dt, snps=nsnp_in, windows=n, scores=s[:n], regend=regend)
 
 
-def css_config():
-    return {"workload": "CSS scan, 450 Mb synthetic genome (BASELINE configs[2]): %d chromosomes x %d bp, %d SNPs each, "
+def cpu_fet_tables(n=200_000):
+    """configs[3] lies outside the reference's u64 arithmetic, so the CPU figure is the oracle's log-space port,
+    one core"""
+    import checkers
+    import fpt_b200.synth as synth
+    o = checkers.load_oracle()
+    T = synth.coverage_tables(FET_TABLES["seed0"], n, FET_TABLES["lo"], FET_TABLES["hi"])
+    out = np.zeros(n)
+    t0 = time.perf_counter()
+    o.fpt_oracle_fet_tables(checkers.iptr(T), n, checkers.dptr(out))
+    return n / (time.perf_counter() - t0), T, out
+
+
+def cpu_large(first):
+    """the reference's serial `compute` (css.c:49-156, oracle/_ref) on the first LARGE['cpu_windows'] windows of the large-cohort
+    chromosome: one core (the pthreads driver hands out tasks of 100 windows, threadcss.c:58, so a sample this size would keep
+    one thread busy anyway; 64 threads x 40 MB of matrices per thread is what makes it slow, not impossible)"""
+    import checkers
+    if not checkers.ref_available() or first is None:
+        return None
+    ref = checkers.load_ref_css()
+    hpos, ha, hb, s_gpu, p_gpu, _ = first
+    nw = LARGE["cpu_windows"]
+    regend = nw * LARGE["wstep"]
+    keep = int(np.searchsorted(hpos, regend + LARGE["wsize"], side="right"))
+    asize, bsize = LARGE["asize"], LARGE["bsize"]
+
+    def vals(c):
+        v = c.astype(np.float64)
+        v[c == -128] = -10000.0
+        return v
+    av, bv = vals(ha[:keep * asize]), vals(hb[:keep * bsize])
+    apos, bpos = np.repeat(hpos[:keep], asize).astype(np.int32), np.repeat(hpos[:keep], bsize).astype(np.int32)
+    s, p = np.zeros(nw + 8), np.zeros(nw + 8)
+    with checkers.silence_stdout():
+        t0 = time.perf_counter()
+        ref.compute(checkers.dptr(av), checkers.dptr(bv), checkers.iptr(apos), checkers.iptr(bpos), 0, regend, LARGE["wsize"], LARGE["wstep"],
+                    av.size, bv.size, LARGE["mcr"], LARGE["mcr"], 0, 0, checkers.dptr(s), checkers.dptr(p))
+        dt = time.perf_counter() - t0
+    both = (s[:nw] != 0) & (s_gpu[:nw] != 0)
+    rel = np.abs(s[:nw][both] - s_gpu[:nw][both]) / np.maximum(np.abs(s[:nw][both]), 1e-300)
+    return {"value": nw / dt, "unit": "windows/s", "cores": 1, "kind": "reference",
+            "sample": "first %d windows of the large-cohort chromosome through the reference's serial compute() (%.1f s); css.c against the "
+                      "header-only GSL stand-in" % (nw, dt),
+            "parity_vs_gpu": {"windows_compared": int(both.sum()), "score_max_rel": float(rel.max()) if both.any() else None,
+                              "score_rel_within_1e-5": float((rel <= 1e-5).mean()) if both.any() else None}}
+
+
+def css_config(world):
+    return {"workload": "CSS scan, ONE 450 Mb synthetic genome (BASELINE configs[2]): %d chromosomes x %d bp, %d SNPs each, "
                         "%d+%d individuals, wsize %d / wstep %d, classical MDS (mds=0), mcT=mcR=%d permutations; "
                         "genome inputs (1.44 GB float64) exceed L2, no flush" % (
                             CSS["chromosomes"], CSS["length"], CSS["nsnp"], CSS["asize"], CSS["bsize"], CSS["wsize"],
                             CSS["wstep"], CSS["mcr"]),
-            "windows_per_step_per_gpu": CSS["chromosomes"] * (CSS["length"] // CSS["wstep"]), "sharding": "one genome per GPU (weak)"}
+            "windows_per_step": CSS["chromosomes"] * (CSS["length"] // CSS["wstep"]),
+            "sharding": "%d contiguous window range(s) of the one genome with SNP halos (sharding.py), one NCCL all_gather of scores + p "
+                        "inside the timed region" % world}
 
 
 def run_reference(args, rank, out):
@@ -490,8 +888,8 @@ def run_reference(args, rank, out):
     val = res["windows"] / sec
     sample = "first %d windows of chromosome 0 of the headline workload per step (bounded sample of the same config)" % res["windows"]
     line = {"impl": "reference", "metric": "css_windows_per_sec_1000perms", "value": val, "unit": "windows/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1000.0, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": css_config(),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1000.0, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": css_config(max(1, args.gpus)),
             "cpu_baseline": {"value": val, "unit": "windows/s", "cores": min(64, ncores), "threads": 64, "nproc": ncores,
                              "kind": "reference", "sample": sample,
                              "note": "unmodified reference threadcompute (64 pthreads hard-wired), css.c linked against the "
@@ -514,60 +912,54 @@ class OneLineStdout:
         os.write(self.real, (json.dumps(obj) + "\n").encode())
 
 
-LARGE = dict(seed0=900, asize=500, bsize=500, windows=592, wsize=50_000, wstep=50_000, snps_per_window=167, mcr=1000)
+# ------------------------------------------------------------------------------------------------ rooflines
+def frac(ach, peak):
+    return (ach / peak) if (ach is not None and peak) else None
 
 
-def bench_large_cohort(lib_mod, args):
-    """BASELINE configs[4] cohort (500+500 individuals, 50 kb windows, ~167 SNPs per window) on a slice of windows: the
-    large-cohort kernels (Lanczos classical MDS; observed scores by a warp per window; permutation test with the between-group
-    sums of 128 permutations as one tcgen05 u8 contraction, accumulators in tensor memory). Timed through
-    the host scan entry with compact int8 inputs; the per-kernel split comes from the library's own CUDA events."""
-    import ctypes as C
-    import fpt_b200.api as api
-    import fpt_b200.synth as synth
-    lib = lib_mod.load()
-    nwin = LARGE["windows"] if not args.small else 8
-    regend = LARGE["wstep"] * nwin
-    ch = synth.chromosome_fast(LARGE["seed0"], regend, LARGE["snps_per_window"] * nwin, LARGE["asize"], LARGE["bsize"], wstep=LARGE["wstep"])
-    buf = C.create_string_buffer(8192)
-    secs, prof = [], None
-    lib.fpt_profile_enable(1)
-    for it in range(3):                                          # first call pays the scratch allocation
-        lib.fpt_profile_summary(buf, 8192)
-        t0 = time.perf_counter()
-        s, p, wr = api.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], LARGE["asize"], LARGE["bsize"], regend, LARGE["wsize"], LARGE["wstep"],
-                                LARGE["mcr"], LARGE["mcr"], mds=0, seed=SEED)
-        secs.append(time.perf_counter() - t0)
-        lib.fpt_profile_summary(buf, 8192)
-        prof = json.loads(buf.value.decode() or "{}")
-    lib.fpt_profile_enable(0)
-    scored = int((wr == 1).sum())
-    dev_ms = sum(v["ms"] for v in prof.values())
-    # the permutation kernel's contraction (csrc/fpt_css_perm_umma.cuh): per window ceil(mcr / 128) batches of a
-    # 128 x Np x Kp u8 product per base-256 digit (4 digits), Np / Kp = m padded to 256 / 128
-    m = LARGE["asize"] + LARGE["bsize"]
-    npad, kpad, batches = -(-m // 256) * 256, -(-m // 128) * 128, -(-LARGE["mcr"] // 128)
-    macs = float(scored) * batches * 128 * npad * kpad * 4
-    perm_ms = prof.get("css_perm", {}).get("ms", 0.0)
-    # kind::i8 rate on this part, from the ncu capture of this kernel (profiles/r1_css_perm_umma_raw.csv): the imma sub-pipe is
-    # busy 512 cycles per 128 x 256 x 32 instruction = 2048 MAC/clk/SM (half the bf16 rate), times 148 SMs at the maximum SM clock
-    i8_peak = 2048.0 * 2.0 * 148 * 1.965e9 / 1e12
-    tensor = {"kernel": "css_perm (fpt_css_perm_umma_kernel)", "bound": "tensor", "unit": "TOP/s (u8 x u8 -> s32)",
-              "achieved": 2.0 * macs / (perm_ms * 1e-3) / 1e12 if perm_ms > 0 else None,
-              "peak": i8_peak,
-              "peak_source": "tcgen05 kind::i8 issue rate measured with ncu on this kernel (512 pipe cycles per 128x256x32 MMA = 2048 MAC/clk/SM) x 148 SMs x 1965 MHz; "
-                             "MEASURED_PEAKS.json has no 8-bit figure",
-              "note": "whole-kernel time: the contraction is ~20 % of it and runs with the imma sub-pipe busy throughout (tensor-pipe bound); the rest is SIMT "
-                      "work (surrogate distance pass, label shuffles, adjacent-pair sweep, membership rows)"}
-    if tensor["achieved"] is not None:
-        tensor["frac"] = tensor["achieved"] / tensor["peak"]
-    return {"metric": "css_windows_per_sec_1000perms", "unit": "windows/s", "value": scored / (dev_ms * 1e-3), "roofline_tensor": tensor,
-            "e2e": {"value": scored / min(secs[1:]), "unit": "windows/s", "api": "fpt_css_scan (host int8 codes)",
-                    "h2d_bytes_per_step": int(ch["acodes"].nbytes + ch["bcodes"].nbytes + ch["pos"].nbytes)},
-            "config": {"workload": "CSS scan, %d windows of BASELINE configs[4]: 500+500 individuals, 50 kb windows, ~%d SNPs per window, "
-                                   "classical MDS, mcT=mcR=1000" % (nwin, LARGE["snps_per_window"]), "windows_scored": scored},
-            "kernel_ms": {k: v["ms"] for k, v in prof.items()},
-            "note": "device figure = windows / sum of the kernels' CUDA-event times of one scan; e2e = wall clock of the host call"}
+def css_kernel_table(css, micro, hbm, nsteps):
+    """per kernel of the headline step (rank 0's share of it): time per launch, share, and algorithmic work against the measured
+    peak of the resource that bounds it (DESIGN.md section 4 states each work model)"""
+    m, a, b = CSS["asize"] + CSS["bsize"], CSS["asize"], CSS["bsize"]
+    prof = css["prof"]
+    tot = sum(v["ms"] for v in prof.values()) or 1.0
+    nwin_rank, scored_rank = css["my_windows"], css["my_scored"]
+    nsnp_rank = css["my_windows"] * CSS["wstep"] // 100       # 1 SNP / 100 bp
+    fp64 = micro["fp64"]["tflops"] * 1e12 if micro else None
+    smem = micro["smem"]["tb_per_s"] * 1e12 if micro else None
+    issue = micro["issue"]["gwarp_inst_per_s"] * 1e9 if micro else None
+    out = {}
+    for k, v in prof.items():
+        sec_step = v["ms"] * 1e-3 / nsteps                # this kernel's time per step (all its launches)
+        e = {"ms_per_launch": v["ms"] / v["launches"], "share_of_step": round(v["ms"] / tot, 4)}
+        if k == "css_perm":
+            # SURVEY 8(d) K7: R (asize bsize + m - 2) fp64 adds fed by as many 8-byte shared-memory gathers per scored window
+            gath = scored_rank * CSS["mcr"] * (a * b + m - 2) * 8.0
+            e.update(bound="smem", algorithmic_bytes_per_step=gath, achieved=gath / sec_step / 1e12, peak=smem and smem / 1e12, unit="TB/s",
+                     frac=frac(gath / sec_step, smem),
+                     note="work model of the reference algorithm (one 8-byte gather per score term); the kernel itself replaces most of "
+                          "them by an exact integer surrogate on the u8 tensor cores, so frac > 1 is possible")
+            ninst = ncu_record("css_perm", "inst")
+            if ninst and issue:
+                e["issue"] = {"warp_inst_per_launch_ncu": ninst, "achieved_gwarp_inst_per_s": ninst / (e["ms_per_launch"] * 1e-3) / 1e9,
+                              "peak": issue / 1e9, "frac": ninst / (e["ms_per_launch"] * 1e-3) / issue,
+                              "note": "utilisation of the issue slots, from the committed ncu capture at N = 1 (not a roofline: useless instructions raise it)"}
+        elif k in ("css_tridiag", "css_eigvec"):
+            # K5: double centring ~6 m^2 + dense symmetric eigen-decomposition ~9 m^3 (what the reference's GSL call does); split 2/3 : 1/3
+            fl = scored_rank * ((6.0 * m * m + 9.0 * m ** 3) * (2.0 / 3.0 if k == "css_tridiag" else 1.0 / 3.0))
+            e.update(bound="fp64", algorithmic_flops_per_step=fl, achieved=fl / sec_step / 1e12, peak=fp64 and fp64 / 1e12, unit="TFLOP/s",
+                     frac=frac(fl / sec_step, fp64),
+                     note="dense work model 6 m^2 + 9 m^3 per window (reduction 2/3, eigenvectors 1/3); the kernels do less than that "
+                          "(two eigenpairs only) and are latency / issue bound at one warp per 40 x 40 window")
+        elif k == "css_pack":
+            by = nsnp_rank * (m * 8 + m / 4.0)
+            e.update(bound="hbm", algorithmic_bytes_per_step=by, achieved=by / sec_step / 1e9, peak=hbm, unit="GB/s", frac=frac(by / sec_step / 1e9, hbm),
+                     traffic=ncu_record("css_pack"))
+        elif k == "window_table":
+            by = nwin_rank * 8.0
+            e.update(bound="latency", algorithmic_bytes_per_step=by, note="two binary searches per window over L2-resident positions")
+        out[k] = e
+    return out
 
 
 def main():
@@ -579,14 +971,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-fet", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--skip-large", action="store_true", help="skip the 500+500 cohort slice")
+    ap.add_argument("--skip-large", action="store_true", help="skip the 500+500 cohort chromosomes")
+    ap.add_argument("--skip-replicas", action="store_true", help="N > 1: skip the secondary one-genome-per-GPU figure")
     ap.add_argument("--small", action="store_true", help="tiny shapes: checks that the script runs, not a benchmark")
     ap.add_argument("--chromosomes", type=int, default=None, help="profiling aid: fewer chromosomes than the 21 of the workload")
     args = ap.parse_args()
     if args.small:
         CSS.update(chromosomes=2, length=2_000_000, nsnp=20_000)
         FET.update(length=10_000_000, nsnp=100_000)
-        FET_TABLES.update(n=200_000)
+        FET_TABLES.update(n=1_600_000)
     if args.chromosomes:
         CSS.update(chromosomes=args.chromosomes)
     rank = int(os.environ.get("RANK", "0"))
@@ -605,64 +998,66 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib_mod.load().fpt_set_seed(SEED)
-    css = bench_css(lib_mod, args, rank, world, dist)
-    fet = None
-    if rank == 0 and not args.skip_fet:
-        fet, fet_sample = bench_fet(lib_mod, args)
+    lib = lib_mod.load()
+    lib.fpt_set_seed(SEED)
+    lib.fpt_set_device(local)
+    micro = micro_peaks() if rank == 0 else None
+    cx = Ctx(args, rank, world, dist)
+    css = bench_css(lib_mod, cx, full_genome_pass=(world > 1 and not args.skip_replicas))
+    fet = fet_tab = None
+    if not args.skip_fet:
+        fet, fet_sample = bench_fet(lib_mod, cx)
+        fet_tab = bench_fet_tables(lib_mod, cx)
     large = None
-    if rank == 0 and not args.skip_large:
-        large = bench_large_cohort(lib_mod, args)
+    if not args.skip_large:
+        large = bench_large_cohort(lib_mod, cx)
     if world > 1:
         dist.barrier()
     if rank == 0:
-        hbm, hbm_src = peaks()
+        hbm, hbm_src = hbm_peak()
         m = CSS["asize"] + CSS["bsize"]
         ms_step = css["ms"] / args.steps
-        value = world * css["windows_per_step"] / (ms_step * 1e-3)
-        e2e_val = world * css["windows_per_step"] / (css["ms_e2e"] / args.steps * 1e-3)
-        prof = css["prof"]
-        tot = sum(v["ms"] for v in prof.values())
-        dom = max(prof, key=lambda k: prof[k]["ms"])
-        per_launch_ms = prof[dom]["ms"] / prof[dom]["launches"]
-        nout = CSS["length"] // CSS["wstep"]
-        bytes_launch = css_kernel_bytes(dom, nout, CSS["nsnp"], m)
-        ach = bytes_launch / (per_launch_ms * 1e-3) / 1e9
+        value = css["total_windows"] / (ms_step * 1e-3)
+        e2e_val = css["total_windows"] / (css["ms_e2e"] / args.steps * 1e-3)
+        kernels = css_kernel_table(css, micro, hbm, args.steps)
+        dom = max(css["prof"], key=lambda k: css["prof"][k]["ms"])
+        kd = kernels[dom]
         line = {
             "metric": "css_windows_per_sec_1000perms", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": css_config(),
-            "windows_scored_per_step_per_gpu": css["scored"],
-            "perm_rechecks": {"exact_rescorings": css["rechecks"],
-                              "permutations_scored": css["scored"] * 1024 * (args.steps + args.warmup),
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": css_config(world),
+            "windows_scored_per_step": css["scored"],
+            "perm_rechecks": {"exact_rescorings_rank0": css["rechecks"],
                               "note": "permutations whose integer surrogate score was too close to the observed score to decide "
-                                      "`>=` and were re-scored in the reference's summation order"},
+                                      "`>=` and were re-scored in the reference's summation order (rank 0, all steps so far)"},
             "e2e": {"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": css["h2d"], "d2h_bytes_per_step": css["d2h"],
-                    "api": "fpt_css_compute (drop-in, host float64 arrays in pinned memory), one call per chromosome",
+                    "api": ("fpt_css_compute (drop-in, host float64 arrays in pinned memory), one call per chromosome" if world == 1 else
+                            "fpt_css_scan on every rank's window range (host float64 arrays in pinned memory) + one NCCL all_gather + D2H of the genome's results"),
                     "windows_scored": css["scored_e2e"]},
+            "e2e_pageable": css["pageable"],
             "gpu_launches": css["launches"],
-            "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                         "peak_source": hbm_src, "traffic": ncu_traffic(dom),
-                         "share_of_step": {k: round(v["ms"] / tot, 4) for k, v in prof.items()},
-                         "kernel_ms_per_launch": {k: v["ms"] / v["launches"] for k, v in prof.items()},
-                         "note": "the permutation kernel is instruction-issue bound (48-bit LCG label shuffles, u8 IMMA between-group "
-                                 "sums over a quantised distance matrix held in shared memory, exact fp64 re-scoring of near ties); "
-                                 "it reads ~0.7 KB per window from HBM, so the HBM fraction is small by construction; see "
-                                 "roofline_issue for the bound that applies"},
+            "roofline": {"kernel": dom, "bound": kd.get("bound"), "achieved": kd.get("achieved"), "peak": kd.get("peak"), "unit": kd.get("unit"),
+                         "frac": kd.get("frac"), "traffic": ncu_record(dom),
+                         "peak_source": (micro or {}).get("source", "unavailable"),
+                         "share_of_step": {k: v["share_of_step"] for k, v in kernels.items()},
+                         "kernel_ms_per_launch": {k: v["ms_per_launch"] for k, v in kernels.items()},
+                         "note": kd.get("note")},
+            "kernels": kernels,
+            "peaks": {"hbm_gbs": hbm, "hbm_source": hbm_src, "micro": micro},
             "clocks": css["clocks"],
-            "mds_variants": {"note": "same workload, chromosome 0 only, device-resident: mds=1 is SMACOF from 4 random starts, mds=2 is "
+            "mds_variants": {"note": "same workload, chromosome 0 only, device-resident (rank 0): mds=1 is SMACOF from 4 random starts, mds=2 is "
                                      "classical MDS followed by SMACOF (css.c:208-218)", **css["variants"]},
         }
-        # issue-slot roofline of the dominant kernel: warp instructions of one launch (ncu capture of the same workload,
-        # profiles/ncu_inst.json) over the live launch time, against 4 schedulers x 148 SMs x the sampled SM clock
-        n_inst = ncu_traffic(dom, "inst")
-        if n_inst and css["clocks"].get("sm_mhz"):
-            issue_peak = 4 * 148 * css["clocks"]["sm_mhz"] * 1e6 / 1e9
-            issue_ach = n_inst / (per_launch_ms * 1e-3) / 1e9
-            line["roofline_issue"] = {"kernel": dom, "bound": "issue", "achieved": issue_ach, "peak": issue_peak,
-                                      "unit": "Gwarp-inst/s", "frac": issue_ach / issue_peak,
-                                      "peak_source": "1 warp-inst/clk/scheduler x 4 x 148 SMs x sampled SM clock",
-                                      "inst_per_launch": n_inst}
+        # K6 roofline of the SMACOF kernel: iterations x 14 m^2 fp64 flops
+        if micro:
+            for kname, v in css["variants"].items():
+                ms_k = v["kernel_ms"].get("css_smacof")
+                if ms_k:
+                    fl = v["smacof_iterations_total"] * 14.0 * m * m
+                    v["roofline_smacof"] = {"bound": "fp64", "algorithmic_flops": fl, "achieved": fl / (ms_k * 1e-3) / 1e12,
+                                            "peak": micro["fp64"]["tflops"], "unit": "TFLOP/s", "frac": fl / (ms_k * 1e-3) / 1e12 / micro["fp64"]["tflops"]}
+        if css["replicas"]:
+            line["replicas"] = css["replicas"]
         if world == 1 and not args.skip_cpu:
             cb = cpu_css(1000)
             if cb is not None:                           # scale the sample to roughly 15 s of CPU wall time
@@ -688,11 +1083,35 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": "windows/s", "cores": 0, "kind": "reference",
                                         "sample": "oracle/_ref not available"}
         if fet is not None:
+            prof = fet.pop("_prof")
+            ns, nw = fet.pop("_ns"), fet.pop("_nw")
+            asz = FET["asize"] + FET["bsize"]
+            ftot = sum(v["ms"] for v in prof.values()) or 1.0
+            kb = {"fet_count": ns * (asz * 8 + 16), "fet_score": ns * 24, "window_table": nw * 8}
+            fk = {}
+            for k, v in prof.items():
+                per = v["ms"] / v["launches"]
+                e = {"ms_per_launch": per, "share_of_step": round(v["ms"] / ftot, 4)}
+                if k in kb and k != "window_table":
+                    e.update(bound="hbm", algorithmic_bytes=kb[k], achieved=kb[k] / (per * 1e-3) / 1e9, peak=hbm, unit="GB/s",
+                             frac=kb[k] / (per * 1e-3) / 1e9 / hbm, traffic=ncu_record(k))
+                elif k == "fet_window" and micro:
+                    # K3: 100 x npos draws per window, each one counter read-modify-write (2 x 2 B) plus the counting pass; report
+                    # draws/s and the shared-memory bytes they imply against the measured shared-memory peak
+                    draws = 100.0 * ns * (FET["wsize"] // FET["wstep"])
+                    e.update(bound="smem/issue", bootstrap_draws=draws, draws_per_s=draws / (per * 1e-3),
+                             smem_bytes_min=draws * 4, achieved=draws * 4 / (per * 1e-3) / 1e12, peak=micro["smem"]["tb_per_s"], unit="TB/s",
+                             frac=draws * 4 / (per * 1e-3) / 1e12 / micro["smem"]["tb_per_s"],
+                             note="integer / shared-memory bound (48-bit LCG draw + counter update per bootstrap index); no meaningful HBM fraction")
+                fk[k] = e
+            fet["kernels"] = fk
+            domf = max(prof, key=lambda k: prof[k]["ms"])
+            fet["roofline"] = dict(kernel=domf, **{k: v for k, v in fk[domf].items() if k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "note")})
             if world == 1 and not args.skip_cpu:
                 cf = cpu_fet(200_000)
                 if cf is not None:
                     ncores = os.cpu_count() or 1
-                    ch, hp, s_host = fet_sample
+                    ch, s_host, wb, we = fet_sample
                     n = cf["windows"]
                     fet["cpu_baseline"] = {"value": cf["snps"] / cf["seconds"], "unit": "SNPs/s", "cores": min(64, ncores), "threads": 64,
                                            "nproc": ncores, "kind": "reference",
@@ -700,7 +1119,69 @@ def main():
                                                cf["snps"], n, cf["seconds"]),
                                            "parity_vs_gpu": {"score_max_abs_diff": float(np.max(np.abs(s_host[:n - 8] - cf["scores"][:n - 8])))}}
             line["fet"] = fet
+        if fet_tab is not None:
+            k_ms, work, n_loc = fet_tab.pop("_kernel_ms"), fet_tab.pop("_work"), fet_tab.pop("_n_local_max")
+            rf = {"kernel": "fet_score (log mode)", "ms_per_launch": k_ms, "tables_per_launch": n_loc}
+            if k_ms:
+                rf["hbm"] = {"bound": "hbm", "algorithmic_bytes": n_loc * 24, "achieved": n_loc * 24 / (k_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                             "frac": n_loc * 24 / (k_ms * 1e-3) / 1e9 / hbm}
+                if work and micro:
+                    # 6 T + 12 flops per table (and T divides, counted as one flop each here)
+                    fl = (7.0 * work["mean_T"] + 12.0) * n_loc
+                    rf["fp64"] = {"bound": "fp64", "algorithmic_flops": fl, "achieved": fl / (k_ms * 1e-3) / 1e12, "peak": micro["fp64"]["tflops"],
+                                  "unit": "TFLOP/s", "frac": fl / (k_ms * 1e-3) / 1e12 / micro["fp64"]["tflops"],
+                                  "note": "work of the reference's full two-tailed walk (7 T + 12 per table, divides counted as one); the kernel skips "
+                                          "tail terms below 2^-60 by bisection, so it does less"}
+                rf["bound"] = "fp64" if ("fp64" in rf and rf["fp64"]["frac"] > rf["hbm"]["frac"]) else "hbm"
+            fet_tab["roofline"] = rf
+            fet_tab["work_model"] = work
+            if world == 1 and not args.skip_cpu:
+                rate, Tc, oc = cpu_fet_tables()
+                g = np.zeros(len(Tc))
+                from fpt_b200._lib import check
+                check(lib.fpt_fet_tables(Tc.ctypes.data, len(Tc), 0, g.ctypes.data))
+                rel = np.abs(g - oc) / np.maximum(np.abs(oc), 1e-300)
+                fet_tab["cpu_baseline"] = {"value": rate, "unit": "SNPs/s", "cores": 1, "kind": "port",
+                                           "sample": "%d tables of the same distribution through the oracle's log-space restatement (the reference's "
+                                                     "u64 binomials overflow beyond N = 67, SURVEY Q2)" % len(Tc),
+                                           "parity_vs_gpu": {"max_rel": float(rel[oc != 0].max())}}
+            line["fet_tables"] = fet_tab
         if large is not None:
+            prof = large.pop("_prof")
+            first = large.pop("_first")
+            nwin, cpr = large.pop("_nwin"), large.pop("_chrom_per_rank")
+            mL = LARGE["asize"] + LARGE["bsize"]
+            ltot = sum(v["ms"] for v in prof.values()) or 1.0
+            lk = {}
+            for k, v in prof.items():
+                per = v["ms"] / v["launches"]
+                e = {"ms_per_launch": per, "share_of_step": round(v["ms"] / ltot, 4)}
+                if k == "css_mds_large":
+                    # algorithmic HBM bytes per window: the window's bit-planes in (2 planes x m x ceil(npos/32) words) and the embedding out (16 m)
+                    words = -(-LARGE["snps_per_window"] // 32) + 1
+                    by = nwin * (2.0 * mL * words * 4 + 16.0 * mL)
+                    tr = ncu_record("css_mds_large")
+                    e.update(bound="hbm", algorithmic_bytes=by, achieved=by / (per * 1e-3) / 1e9, peak=hbm, unit="GB/s", frac=by / (per * 1e-3) / 1e9 / hbm,
+                             traffic=tr, traffic_over_algorithmic=(tr / by) if tr else None,
+                             note="64 KB of input + output per window; everything above that in `traffic` is the kernel re-streaming its own "
+                                  "matrix and Lanczos basis")
+                    if micro:
+                        fl = nwin * (6.0 * mL * mL + 9.0 * float(mL) ** 3)
+                        e["fp64_dense_model"] = {"algorithmic_flops": fl, "achieved": fl / (per * 1e-3) / 1e12, "peak": micro["fp64"]["tflops"],
+                                                 "frac": fl / (per * 1e-3) / 1e12 / micro["fp64"]["tflops"], "unit": "TFLOP/s",
+                                                 "note": "dense work model 6 m^2 + 9 m^3; Lanczos does ~2 m^2 x steps"}
+                elif k == "css_perm" and micro:
+                    npad, kpad, batches = -(-mL // 256) * 256, -(-mL // 128) * 128, -(-LARGE["mcr"] // 128)
+                    macs = float(nwin) * batches * 128 * npad * kpad * 4
+                    e.update(bound="tensor", algorithmic_macs=macs, achieved=2.0 * macs / (per * 1e-3) / 1e12, peak=micro["umma_i8"]["tops"], unit="TOP/s",
+                             frac=2.0 * macs / (per * 1e-3) / 1e12 / micro["umma_i8"]["tops"],
+                             note="u8 contraction work of the kernel (4 base-256 digits) over the WHOLE kernel time, against the kind::i8 rate measured "
+                                  "with both operands resident in shared memory (profiles/microbench/peaks.cu)")
+                lk[k] = e
+            large["kernels"] = lk
+            large["kernel_ms_per_chromosome"] = {k: v["ms"] / max(1, v["launches"]) for k, v in prof.items()}
+            if world == 1 and not args.skip_cpu and not args.small:
+                large["cpu_baseline"] = cpu_large(first)
             line["large_cohort"] = large
         out.emit(line)
     if world > 1:

@@ -54,14 +54,16 @@ __global__ void __launch_bounds__(1024) smem_kernel(unsigned *out, int iters) {
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) buf[i] = make_uint4(i, i + 1, i + 2, i + 3);
     __syncthreads();
     unsigned acc = 0;
-    int idx = threadIdx.x;
+    const unsigned base = (unsigned)__cvta_generic_to_shared(buf);
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const uint4 v = buf[(idx + u * 256) & 2047];    /* consecutive lanes -> consecutive 16-byte words: conflict-free */
-            acc ^= v.x ^ v.y ^ v.z ^ v.w;
+            /* volatile asm: the loads cannot be hoisted or merged. Consecutive lanes -> consecutive 16-byte words: conflict-free */
+            unsigned x, y, z, w;
+            const unsigned addr = base + ((((unsigned)threadIdx.x + u * 256 + i * 32) & 2047u) << 4);
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr));
+            acc ^= x ^ y ^ z ^ w;
         }
-        idx = (idx + 1024 + (acc & 0)) & 2047;
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }

@@ -22,7 +22,22 @@ static void run_grid(unsigned nb, unsigned nt, size_t smem, F f) {
     emu::launch(nb, nt, smem, [](void *p) { (*(F *)p)(); }, &f);
 }
 
+/* detector self-test for profiles/emu_sanitizers.sh: neighbouring threads exchange a value through dynamic shared memory, with
+   or without the barrier between the write and the read. Under ThreadSanitizer the barrier-less variant MUST be reported (it shows
+   that the instrumentation sees the kernels' shared-memory traffic), and overrun != 0 reads one word past the allocation for ASan. */
+static void emu_selftest_kernel(int with_barrier, int overrun, int *out) {
+    FPT_DYN_SMEM(smem);
+    int *buf = reinterpret_cast<int *>(smem);
+    buf[threadIdx.x] = (int)threadIdx.x;
+    if (with_barrier) __syncthreads();
+    out[threadIdx.x] = buf[(threadIdx.x + 1) % blockDim.x + (overrun ? blockDim.x : 0)];
+}
+
 extern "C" {
+
+void emu_selftest(int with_barrier, int overrun, int *out) {
+    run_grid(1, 64, 64 * sizeof(int), [=]() { emu_selftest_kernel(with_barrier, overrun, out); });
+}
 
 uint64_t emu_window_state(uint64_t seed, long long w, int stream) { return fpt_stream_state(seed, w, stream); }
 uint64_t emu_lcg_skip(uint64_t s, uint64_t n) { return fpt_lcg_skip(s, n); }

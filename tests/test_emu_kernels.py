@@ -17,6 +17,11 @@ CODES = np.array([3.0, -3.0, 0.0, -10000.0])
 
 @pytest.fixture(scope="module")
 def emu():
+    # FPT_EMU_LIB: a prebuilt variant of the emulation library, e.g. the ThreadSanitizer / AddressSanitizer builds that
+    # profiles/emu_sanitizers.sh runs this suite under (race and bounds checks of the kernel logic without a GPU tool)
+    override = os.environ.get("FPT_EMU_LIB")
+    if override:
+        return C.CDLL(override)
     subprocess.run([os.path.join(HERE, "emu", "build.sh")], check=True, capture_output=True)
     return C.CDLL(os.path.join(HERE, "emu", "libfpt_emu.so"))
 
@@ -25,6 +30,9 @@ def emu():
 def emu_exact_stress():
     """the same kernels with the SMACOF order bound scaled by 1e12: every stopping decision takes the path that re-sums the
     stress in the reference's order (csrc/fpt_css.cuh, fpt_css_smacof)"""
+    override = os.environ.get("FPT_EMU_LIB_EXACT")           # sanitizer builds, see the emu fixture
+    if override:
+        return C.CDLL(override)
     out = os.path.join(HERE, "emu", "libfpt_emu_exact.so")
     subprocess.run([os.path.join(HERE, "emu", "build.sh"), out, "-DFPT_SMACOF_BOUND_SCALE=1e12"], check=True, capture_output=True)
     return C.CDLL(out)
