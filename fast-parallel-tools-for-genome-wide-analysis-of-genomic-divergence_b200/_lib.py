@@ -54,6 +54,8 @@ SYMBOLS = {
     "fpt_debug_umma_phases": (_I, [_P]),
     "fpt_debug_lanczos_phases": (_I, [_P]),
     "fpt_set_lanczos_form": (None, [_I]),
+    "fpt_set_k4_mode": (None, [_I]),
+    "fpt_debug_k4_phases": (_I, [_P]),
     "fpt_css_perm_rechecks": (C.c_longlong, []),
     "fpt_release": (None, []),
     "fpt_window_state": (C.c_uint64, [C.c_uint64, C.c_int64, _I]),

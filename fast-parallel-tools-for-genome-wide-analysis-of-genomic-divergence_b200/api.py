@@ -45,6 +45,11 @@ def set_lanczos_form(max_form):
     _lib.load().fpt_set_lanczos_form(int(max_form))
 
 
+def set_k4_mode(mode):
+    """Large cohorts, genotype-distance matrix: 2 = tcgen05 u8 GEMM (default), 1 = popcounts, 0 = legacy fp64 matrix."""
+    _lib.load().fpt_set_k4_mode(int(mode))
+
+
 def set_perm_large_kernel(tensor_memory):
     """Large cohorts (m > 250): 1 / True = tcgen05 permutation kernel (default), 0 / False = the general kernel, 2 = tcgen05
     kernel with a coarse (10-bit) surrogate that forces many exact re-scorings. Same results in every mode."""

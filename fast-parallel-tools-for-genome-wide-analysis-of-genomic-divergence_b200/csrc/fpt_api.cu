@@ -27,6 +27,7 @@
 #include "fpt_css.cuh"
 #include "fpt_css_eig.cuh"
 #include "fpt_css_lanczos.cuh"
+#include "fpt_css_k4.cuh"
 #include "fpt_css_perm.cuh"
 #include "fpt_css_perm_large.cuh"
 #include "fpt_css_perm_umma.cuh"
@@ -43,9 +44,14 @@ static std::atomic<int> g_device{-1};           /* -1: whatever device is curren
 static std::atomic<int> g_lanczos_form{2};      /* large-cohort MDS: highest product form allowed (2 8-bit codes, 1 16-bit codes, 0 fp64 matrix) */
 static std::atomic<int> g_perm_umma{1};         /* large cohorts: 1 = tcgen05 permutation kernel, 0 = the general (mma.sync) kernel */
 static std::atomic<int> g_perm_chain{0};        /* CSS label shuffles: 0 = independent per permutation, 1 = the reference's chain */
+static std::atomic<int> g_k4_mode{2};           /* large cohorts, genotype-distance matrix: 2 = tcgen05 u8 GEMM, 1 = popcounts, 0 = legacy fp64 matrix */
 
-struct Knobs { int lanczos_form, perm_umma, perm_chain; };
-static Knobs knobs_now() { Knobs k; k.lanczos_form = g_lanczos_form.load(); k.perm_umma = g_perm_umma.load(); k.perm_chain = g_perm_chain.load(); return k; }
+struct Knobs { int lanczos_form, perm_umma, perm_chain, k4_mode; };
+static Knobs knobs_now() {
+    Knobs k;
+    k.lanczos_form = g_lanczos_form.load(); k.perm_umma = g_perm_umma.load(); k.perm_chain = g_perm_chain.load(); k.k4_mode = g_k4_mode.load();
+    return k;
+}
 
 static int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -287,6 +293,13 @@ extern "C" void fpt_set_perm_mode(int chain) { g_perm_chain.store(chain != 0); }
 extern "C" int fpt_get_perm_mode(void) { return g_perm_chain.load(); }
 extern "C" void fpt_set_perm_large_kernel(int tensor_memory) { g_perm_umma.store(tensor_memory); }
 extern "C" void fpt_set_lanczos_form(int max_form) { g_lanczos_form.store(max_form < 0 ? 0 : (max_form > 2 ? 2 : max_form)); }
+extern "C" void fpt_set_k4_mode(int mode) { g_k4_mode.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode)); }
+extern "C" int fpt_debug_k4_phases(unsigned long long *out4) {
+    unsigned long long zero[4] = { 0 };
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(out4, fpt_k4_phase_cycles, sizeof zero) != cudaSuccess ||
+        cudaMemcpyToSymbol(fpt_k4_phase_cycles, zero, sizeof zero) != cudaSuccess) return FPT_ERR_CUDA;
+    return FPT_OK;
+}
 extern "C" int fpt_debug_lanczos_phases(unsigned long long *out8) {
     unsigned long long zero[8] = { 0 };
     if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(out8, fpt_lanczos_phase_cycles, sizeof zero) != cudaSuccess ||
@@ -550,8 +563,10 @@ static CssPlan css_plan(const DeviceCtx *c, int m, const Knobs &kn) {
     return p;
 }
 
+#define FPT_K4_BATCH 1024                         /* windows per pass of the code route: bounds the code buffer (2 MB per window at m = 1000) */
 struct CssWorkspace {
-    double *X, *Xruns, *sigma, *evals, *gscratch, *tri, *refl;
+    double *X, *Xruns, *sigma, *evals, *gscratch, *tri, *refl, *basis;
+    unsigned char *codes;
     int *iters;
     unsigned char *perm_scratch;
     size_t total;
@@ -569,7 +584,12 @@ static CssWorkspace css_carve(const CssPlan &p, long long nwin, int mds, unsigne
     size_t oE = take((size_t)nwin * 3 * 8);
     size_t oI = take((size_t)nwin * nruns * 4);
     const bool need_g = !p.mats_in_smem || p.mds_warps == 0;
-    size_t oG = take(need_g ? (size_t)p.max_ctas * fpt_css_mats_doubles(p.m) * 8 : 0);
+    /* large cohorts: the legacy matrices (per CTA) and the code route's buffers (codes of one batch of windows + a Lanczos
+       basis per CTA) are never live together (SMACOF's matrices are used after classical MDS is done): one region */
+    const size_t legacy_g = need_g ? (size_t)p.max_ctas * fpt_css_mats_doubles(p.m) * 8 : 0;
+    const size_t codes_b = p.mds_warps == 0 ? (size_t)std::min<long long>(nwin, FPT_K4_BATCH) * fpt_k4_window_stride(p.m) : 0;
+    const size_t basis_b = p.mds_warps == 0 ? (((size_t)p.max_ctas * fpt_lanczos_cap(p.m) * p.m * 8) + 255) & ~(size_t)255 : 0;
+    size_t oG = take(std::max(legacy_g, codes_b + basis_b));
     size_t oP = take((size_t)p.max_ctas * p.perm_scratch_per_cta);
     const bool warp_mds = p.mds_warps > 0 && mds != 1;      /* tridiagonal + reflectors handed from phase A to phase B */
     size_t oT = take(warp_mds ? (size_t)nwin * 3 * p.m * 8 : 0);
@@ -579,6 +599,8 @@ static CssWorkspace css_carve(const CssPlan &p, long long nwin, int mds, unsigne
         w.X = (double *)(base + oX); w.Xruns = (double *)(base + oXr); w.sigma = (double *)(base + oS);
         w.evals = (double *)(base + oE); w.iters = (int *)(base + oI);
         w.gscratch = need_g ? (double *)(base + oG) : nullptr;
+        w.basis = (double *)(base + oG);
+        w.codes = base + oG + basis_b;
         w.perm_scratch = p.perm_scratch_per_cta ? base + oP : nullptr;
         w.tri = (double *)(base + oT); w.refl = (double *)(base + oR);
     }
@@ -677,10 +699,39 @@ static int dev_css_windows(const Knobs &kn, const uint32_t *planes, const double
         } else {                                           /* cohorts too large for a warp's shared-memory slice: Lanczos, CTA per window */
             if (p.smem_large > (size_t)c->smem_optin)
                 return fail(FPT_ERR_ARG, "cohort of %d individuals does not fit the large-cohort kernel's shared memory", m);
+            /* code route: the genotype-distance matrix as count codes from the u8 GEMM (or the popcount kernel), then Lanczos on
+               the codes. Needs bit-planes and counts that fit 16 bits (a window of wsize bp holds at most wsize + 1 positions). */
+            const bool code_route = kn.k4_mode > 0 && planes && !absdiff && r->wsize < 65535 && kn.lanczos_form >= 2;
+            if (code_route) {
+                const size_t stride = fpt_k4_window_stride(m);
+                const size_t smem_lz = fpt_lanczos_smem_bytes(m, 0);
+                int grid_lz;
+                CHECK(persistent_grid(c, fpt_css_mds_codes_kernel, 512, smem_lz, nwin, &grid_lz));
+                grid_lz = std::min(grid_lz, p.max_ctas);
+                for (long long w0 = 0; w0 < nwin; w0 += FPT_K4_BATCH) {
+                    const long long nb = std::min<long long>(FPT_K4_BATCH, nwin - w0);
+                    if (kn.k4_mode == 2) {
+                        CU(cudaFuncSetAttribute(fpt_css_k4_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FPT_K4_SMEM));
+                        const int g4 = (int)std::max(1LL, std::min<long long>(c->sms, nb));     /* 512 columns of tensor memory: one CTA per SM */
+                        { ProfScope ps_("css_k4", st); fpt_css_k4_umma_kernel<<<g4, FPT_K4_THREADS, FPT_K4_SMEM, st>>>(planes, m, wleft + w0, wright + w0, nb, ws.codes, stride); }
+                    } else {
+                        const size_t smem4 = fpt_k4_popc_smem(m);
+                        if (smem4 > (size_t)c->smem_optin) return fail(FPT_ERR_ARG, "cohort of %d individuals exceeds the popcount kernel's shared memory", m);
+                        int g4;
+                        CHECK(persistent_grid(c, fpt_css_k4_popc_kernel, 256, smem4, nb, &g4));
+                        { ProfScope ps_("css_k4", st); fpt_css_k4_popc_kernel<<<g4, 256, smem4, st>>>(planes, m, wleft + w0, wright + w0, nb, ws.codes, stride); }
+                    }
+                    CU(cudaGetLastError());
+                    { ProfScope ps_("css_mds_large", st); fpt_css_mds_codes_kernel<<<(int)std::min<long long>(grid_lz, nb), 512, smem_lz, st>>>(
+                          ws.codes, stride, m, wleft + w0, wright + w0, nb, ws.basis, ws.X + (size_t)w0 * 2 * m, ws.evals + (size_t)w0 * 3, status + w0, nullptr); }
+                    CU(cudaGetLastError());
+                }
+            } else {
             CHECK(persistent_grid(c, fpt_css_mds_large_kernel, 512, p.smem_large, nwin, &grid));
             grid = std::min(grid, p.max_ctas);
             { ProfScope ps_("css_mds_large", st); fpt_css_mds_large_kernel<<<grid, 512, p.smem_large, st>>>(planes, absdiff, m, wleft, wright, nwin, p.wch_large,
                                                              ws.gscratch, ws.X, ws.evals, status, nullptr, kn.lanczos_form); }
+            }
         }
         CU(cudaGetLastError());
     }

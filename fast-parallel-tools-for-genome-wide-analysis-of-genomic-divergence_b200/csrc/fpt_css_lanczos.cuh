@@ -53,7 +53,7 @@ struct FptLanczosSmem {
 
 FPT_HD size_t fpt_lanczos_smem_bytes(int m, int wch) {
     const int cap = fpt_lanczos_cap(m);
-    size_t off = (size_t)3 * m * 8 + (size_t)3 * cap * 8 + (size_t)13 * cap * 8 + 66 * 8;
+    size_t off = (size_t)(3 * m + 16) * 8 + (size_t)3 * cap * 8 + (size_t)13 * cap * 8 + 66 * 8;
     off = (off + 15) & ~(size_t)15;
     return off + (size_t)wch * 2 * m * 4;
 }
@@ -62,7 +62,7 @@ FPT_D FptLanczosSmem fpt_lanczos_carve(unsigned char *smem, int m, int wch) {
     FptLanczosSmem s;
     const int cap = fpt_lanczos_cap(m);
     double *p = (double *)smem;
-    s.q = p; p += m; s.w = p; p += m; s.rmean = p; p += m;
+    s.q = p; p += m + 16; s.w = p; p += m; s.rmean = p; p += m;      /* q: 16 spare entries, kept zero (padded code columns) */
     s.alpha = p; p += cap; s.beta = p; p += cap; s.h = p; p += cap;
     s.ew.A = 0;
     s.ew.d = p; p += cap; s.ew.e = p; p += cap; s.ew.tau = p; p += cap;
@@ -112,21 +112,21 @@ FPT_D void fpt_cta_symv(const double *__restrict__ B, int m, const double *x, do
    ROWS rows in flight (eight with 8-bit codes: 2 KB of loads outstanding per warp), each lane one 8-byte load of consecutive codes: four 16-bit ones (m % 4 == 0) or, when no count exceeds
    255, eight 8-bit ones (m % 8 == 0). sx = 1'x and rx = r'x are given. */
 template <typename CodeT, int ROWS>
-FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, const double *x, double *y, const double *rmean,
+FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, int ld, const double *x, double *y, const double *rmean,
                               double g, double v2, double sx, double rx) {
     constexpr int PER = 8 / (int)sizeof(CodeT);                 /* codes per 8-byte load: 4 or 8 */
     constexpr int BITS = 8 * (int)sizeof(CodeT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int i = ROWS * warp; i < m; i += ROWS * nwarp) {
         const int nr = m - i < ROWS ? m - i : ROWS;
-        const CodeT *r0 = C + (size_t)i * m;
+        const CodeT *r0 = C + (size_t)i * ld;                  /* columns m .. ld-1 (if any) meet x = 0 */
         double acc[ROWS];
 #pragma unroll
         for (int r = 0; r < ROWS; r++) acc[r] = 0.0;
         for (int j = PER * lane; j < m; j += 32 * PER) {
             uint2 cc[ROWS];                                     /* ROWS 8-byte loads in flight per lane */
 #pragma unroll
-            for (int r = 0; r < ROWS; r++) cc[r] = *reinterpret_cast<const uint2 *>(r0 + (size_t)(r < nr ? r : 0) * m + j);
+            for (int r = 0; r < ROWS; r++) cc[r] = *reinterpret_cast<const uint2 *>(r0 + (size_t)(r < nr ? r : 0) * ld + j);
 #pragma unroll
             for (int k = 0; k < PER; k += 2) {
                 const double2 xv = *reinterpret_cast<const double2 *>(x + j + k);
@@ -173,74 +173,29 @@ FPT_D void fpt_cta_cgs_pass(const double *__restrict__ Q, int nq, int m, double 
     __syncthreads();
 }
 
-/* A (m x m, global) holds the filled dissimilarities on entry and B on exit; Q (>= cap x m doubles, global) receives the
-   Lanczos basis. X: 2m doubles (shared or global) written by the CTA; evals3 optional. All threads of the CTA take part. */
-FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *evals3, const FptLanczosSmem &s, int *steps_out,
-                                int max_form = 2) {
+/* The matrix B = -1/2 J (D.D) J as the Lanczos product streams it: 8-bit count codes (form 2), 16-bit count codes (form 1) —
+   code c >= 1: S = c^2, code 0: S = v2, and y = -1/2 (S x - r (1'x) - 1 (r'x) + g (1'x)) — or B itself in fp64 (form 0). `ld` is the
+   row stride in elements (codes: columns m .. ld-1 hold code 0 and meet the zero tail of the Lanczos vector). */
+struct FptLzMatrix {
+    int form, ld;
+    const void *data;
+    double g, v2;
+};
+
+/* Lanczos with full re-orthogonalisation on B (given as FptLzMatrix; s.rmean holds the row means of S for the code forms);
+   Q (>= cap x m doubles, global) receives the basis. X: 2m doubles written by the CTA; evals3 optional. All threads take part. */
+FPT_D void fpt_lanczos_iterate(const FptLzMatrix &M, double *Q, int m, double *X, double *evals3, const FptLanczosSmem &s, int *steps_out) {
     const int T = blockDim.x, tid = threadIdx.x;
     const int cap = fpt_lanczos_cap(m);
-    const size_t mm = (size_t)m * m;
     __shared__ double sh_val[4];
     __shared__ int sh_flag;
     FPT_LZ_START();
-    /* ---- 1. row means of S = D.D and the grand mean (same closed form as the small-cohort paths); on the way, whether
-       the matrix has the compact form: every entry a count in 1..65535 or the fill value v0 (the diagonal always is) */
-    const double v0 = A[0];
-    int compact = (m & 3) == 0, narrow = 1;                     /* narrow: every count fits a byte */
-    {
-        const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
-        for (int i = warp; i < m; i += nwarp) {                /* row sums, coalesced */
-            const double *row = A + (size_t)i * m;
-            double acc = 0.0;
-            for (int j = lane; j < m; j += 32) {
-                const double d = row[j];
-                acc += d * d;
-                if (!(d == v0 || (d >= 1.0 && d <= 65535.0 && d == floor(d)))) compact = 0;
-                if (d > 255.0) narrow = 0;
-            }
-            acc = fpt_warp_sum(acc);
-            if (lane == 0) s.rmean[i] = acc / m;
-        }
-    }
-    compact = __syncthreads_and(compact);
-    narrow = __syncthreads_and(narrow);
-    /* product form: 2 8-bit codes, 1 16-bit codes, 0 fp64 matrix; `max_form` caps it (parity tests) */
-    const int ok2 = compact && narrow && (m & 7) == 0, ok1 = compact;
-    const int form = (ok2 && max_form >= 2) ? 2 : ((ok1 && max_form >= 1) ? 1 : 0);
-    narrow = form == 2;
-    compact = form > 0;
-    double g = 0.0;
-    for (int i = tid; i < m; i += T) g += s.rmean[i];
-    g = fpt_block_sum(g, s.sc.red) / m;
-    unsigned short *codes = reinterpret_cast<unsigned short *>(A);
-    unsigned char *codes8 = reinterpret_cast<unsigned char *>(A);
-    const double v2 = v0 * v0;
-    if (compact) {
-        /* in place: the codes of a block of 8 T entries land in the first quarter of the bytes those entries occupied,
-           which only the block itself has still to read — hence the barrier between its loads and its stores */
-        for (size_t base = 0; base < mm; base += (size_t)8 * T) {
-            double d[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) { const size_t e = base + tid + (size_t)u * T; d[u] = e < mm ? A[e] : 0.0; }
-            __syncthreads();
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const size_t e = base + tid + (size_t)u * T;
-                if (e < mm) {
-                    const unsigned c = (d[u] >= 1.0 && d[u] == floor(d[u])) ? (unsigned)d[u] : 0u;
-                    if (narrow) codes8[e] = (unsigned char)c; else codes[e] = (unsigned short)c;
-                }
-            }
-        }
-    } else {
-        for (size_t e = tid; e < mm; e += T) {
-            const int i = (int)(e / m), j = (int)(e - (size_t)i * m);
-            const double d = A[e];
-            A[e] = -0.5 * (((d * d - s.rmean[i]) - s.rmean[j]) + g);
-        }
-    }
-    __syncthreads();
-    FPT_LZ_MARK(1);
+    const int compact = M.form > 0, narrow = M.form == 2;
+    const unsigned short *codes = reinterpret_cast<const unsigned short *>(M.data);
+    const unsigned char *codes8 = reinterpret_cast<const unsigned char *>(M.data);
+    const double *A = reinterpret_cast<const double *>(M.data);
+    const double g = M.g, v2 = M.v2;
+    for (int e = tid; e < 16; e += T) s.q[m + e] = 0.0;
     /* ---- 2. Lanczos. Start vector: fixed pseudo-random signs and magnitudes (any vector with a component along the
        leading eigenvectors works; a fixed one keeps runs reproducible) */
     double nn = 0.0;
@@ -264,20 +219,41 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
             for (int e = tid; e < m; e += T) { const double v = s.q[e]; sx += v; rx += s.rmean[e] * v; }
             sx = fpt_block_sum(sx, s.sc.red);
             rx = fpt_block_sum(rx, s.sc.red);
-            if (narrow) fpt_cta_symv_codes<unsigned char, 8>(codes8, m, s.q, s.w, s.rmean, g, v2, sx, rx);
-            else fpt_cta_symv_codes<unsigned short, 4>(codes, m, s.q, s.w, s.rmean, g, v2, sx, rx);
+            if (narrow) fpt_cta_symv_codes<unsigned char, 8>(codes8, m, M.ld, s.q, s.w, s.rmean, g, v2, sx, rx);
+            else fpt_cta_symv_codes<unsigned short, 4>(codes, m, M.ld, s.q, s.w, s.rmean, g, v2, sx, rx);
         } else {
             fpt_cta_symv(A, m, s.q, s.w);
         }
         FPT_LZ_MARK(2);
+        /* Orthogonalisation = the three-term recurrence (the two large components, along q_j and q_{j-1}, removed locally)
+           followed by ONE classical Gram-Schmidt pass against the whole basis, which then only has to remove what rounding
+           re-introduced; a second pass runs when the first one took away more than half of the vector (the "twice is enough"
+           criterion) — with the recurrence in front that is the exception, so the basis is read once per step, not twice. */
         for (int i = tid; i <= j; i += T) s.h[i] = 0.0;
+        double aj = 0.0;
+        for (int e = tid; e < m; e += T) aj += s.q[e] * s.w[e];
+        aj = fpt_block_sum(aj, s.sc.red);
+        {
+            const double bprev = j > 0 ? s.beta[j - 1] : 0.0;
+            const double *qp = Q + (size_t)(j > 0 ? j - 1 : 0) * m;
+            for (int e = tid; e < m; e += T) s.w[e] -= aj * s.q[e] + (j > 0 ? bprev * qp[e] : 0.0);
+            if (tid == 0) s.h[j] = aj;
+        }
         __syncthreads();
+        double n0 = 0.0;
+        for (int e = tid; e < m; e += T) n0 += s.w[e] * s.w[e];
+        n0 = fpt_block_sum(n0, s.sc.red);
         fpt_cta_cgs_pass(Q, j + 1, m, s.w, s.h, s.ew.lu);            /* lu is free between tridiagonal solves */
-        fpt_cta_cgs_pass(Q, j + 1, m, s.w, s.h, s.ew.lu);
-        FPT_LZ_MARK(3);
         double b2 = 0.0;
         for (int e = tid; e < m; e += T) b2 += s.w[e] * s.w[e];
         b2 = fpt_block_sum(b2, s.sc.red);
+        if (!(b2 >= 0.5 * n0)) {
+            fpt_cta_cgs_pass(Q, j + 1, m, s.w, s.h, s.ew.lu);
+            b2 = 0.0;
+            for (int e = tid; e < m; e += T) b2 += s.w[e] * s.w[e];
+            b2 = fpt_block_sum(b2, s.sc.red);
+        }
+        FPT_LZ_MARK(3);
         const double bj = sqrt(b2);
         if (tid == 0) { s.alpha[j] = s.h[j]; s.beta[j] = bj; }
         __syncthreads();
@@ -359,7 +335,150 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
     FPT_LZ_MARK(6);
 }
 
-/* mds 0 (and the first half of mds 2) for large cohorts: one CTA walks windows blockIdx.x, +gridDim.x, ...;
+/* A (m x m, global) holds the filled dissimilarities on entry and B on exit; Q (>= cap x m doubles, global) receives the
+   Lanczos basis. X: 2m doubles (shared or global) written by the CTA; evals3 optional. All threads of the CTA take part. */
+FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *evals3, const FptLanczosSmem &s, int *steps_out,
+                                int max_form = 2) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int cap = fpt_lanczos_cap(m);
+    const size_t mm = (size_t)m * m;
+    FPT_LZ_START();
+    /* ---- 1. row means of S = D.D and the grand mean (same closed form as the small-cohort paths); on the way, whether
+       the matrix has the compact form: every entry a count in 1..65535 or the fill value v0 (the diagonal always is) */
+    const double v0 = A[0];
+    int compact = (m & 3) == 0, narrow = 1;                     /* narrow: every count fits a byte */
+    {
+        const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+        for (int i = warp; i < m; i += nwarp) {                /* row sums, coalesced */
+            const double *row = A + (size_t)i * m;
+            double acc = 0.0;
+            for (int j = lane; j < m; j += 32) {
+                const double d = row[j];
+                acc += d * d;
+                if (!(d == v0 || (d >= 1.0 && d <= 65535.0 && d == floor(d)))) compact = 0;
+                if (d > 255.0) narrow = 0;
+            }
+            acc = fpt_warp_sum(acc);
+            if (lane == 0) s.rmean[i] = acc / m;
+        }
+    }
+    compact = __syncthreads_and(compact);
+    narrow = __syncthreads_and(narrow);
+    /* product form: 2 8-bit codes, 1 16-bit codes, 0 fp64 matrix; `max_form` caps it (parity tests) */
+    const int ok2 = compact && narrow && (m & 7) == 0, ok1 = compact;
+    const int form = (ok2 && max_form >= 2) ? 2 : ((ok1 && max_form >= 1) ? 1 : 0);
+    narrow = form == 2;
+    compact = form > 0;
+    double g = 0.0;
+    for (int i = tid; i < m; i += T) g += s.rmean[i];
+    g = fpt_block_sum(g, s.sc.red) / m;
+    unsigned short *codes = reinterpret_cast<unsigned short *>(A);
+    unsigned char *codes8 = reinterpret_cast<unsigned char *>(A);
+    const double v2 = v0 * v0;
+    if (compact) {
+        /* in place: the codes of a block of 8 T entries land in the first quarter of the bytes those entries occupied,
+           which only the block itself has still to read — hence the barrier between its loads and its stores */
+        for (size_t base = 0; base < mm; base += (size_t)8 * T) {
+            double d[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const size_t e = base + tid + (size_t)u * T; d[u] = e < mm ? A[e] : 0.0; }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const size_t e = base + tid + (size_t)u * T;
+                if (e < mm) {
+                    const unsigned c = (d[u] >= 1.0 && d[u] == floor(d[u])) ? (unsigned)d[u] : 0u;
+                    if (narrow) codes8[e] = (unsigned char)c; else codes[e] = (unsigned short)c;
+                }
+            }
+        }
+    } else {
+        for (size_t e = tid; e < mm; e += T) {
+            const int i = (int)(e / m), j = (int)(e - (size_t)i * m);
+            const double d = A[e];
+            A[e] = -0.5 * (((d * d - s.rmean[i]) - s.rmean[j]) + g);
+        }
+    }
+    __syncthreads();
+    FPT_LZ_MARK(1);
+    FptLzMatrix M;
+    M.form = form; M.ld = m; M.data = A; M.g = g; M.v2 = v2;
+    fpt_lanczos_iterate(M, Q, m, X, evals3, s, steps_out);
+}
+
+/* Large cohorts, default route. The window's count codes were written by fpt_css_k4_umma_kernel / fpt_css_k4_popc_kernel
+   (fpt_css_k4.cuh); here fill_averages (css.c:337-366) and the double centring of cmds (css.c:505-531) are derived from them in
+   integers — blanks = codes 0, their replacement = (sum of the counts) / m^2, row sums of squares exact — and the Lanczos
+   iteration streams the codes. basis: per CTA fpt_lanczos_cap(m) x m doubles. */
+__global__ void __launch_bounds__(512, 2)
+fpt_css_mds_codes_kernel(const unsigned char *__restrict__ codes, size_t stride, int m, const int *__restrict__ wleft,
+                         const int *__restrict__ wright, long long nwin, double *__restrict__ basis, double *__restrict__ Xout,
+                         double *__restrict__ evals_out, unsigned char *__restrict__ status, int *__restrict__ steps_out) {
+    FPT_DYN_SMEM(smem);
+    const FptLanczosSmem s = fpt_lanczos_carve(smem, m, 0);
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    const int ld = (m + 15) & ~15;
+    double *Q = basis + (size_t)blockIdx.x * fpt_lanczos_cap(m) * m;
+    for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
+        const int l = wleft[w], r = wright[w];
+        if (r <= l) { if (tid == 0) status[w] = FPT_WIN_EMPTY; continue; }
+        FPT_LZ_START();
+        const int wide = (r - l) > 255;                           /* two-byte codes (fpt_k4_code_bytes) */
+        const unsigned char *c8 = codes + (size_t)w * stride;
+        const unsigned short *c16 = reinterpret_cast<const unsigned short *>(c8);
+        long long blanks = 0, total = 0;
+        for (int i = warp; i < m; i += nwarp) {                   /* a warp per row, 16 bytes per lane and load */
+            unsigned long long sq = 0;
+            unsigned sum = 0, nb = 0;
+            if (!wide) {
+                for (int j = 16 * lane; j < m; j += 512) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(c8 + (size_t)i * ld + j);
+                    const unsigned ww[4] = { v.x, v.y, v.z, v.w };
+                    const int valid = min(16, m - j);
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        const unsigned c = (ww[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                        sum += c; sq += c * c; nb += (k < valid && c == 0u);
+                    }
+                }
+            } else {
+                for (int j = 8 * lane; j < m; j += 256) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(c16 + (size_t)i * ld + j);
+                    const unsigned ww[4] = { v.x, v.y, v.z, v.w };
+                    const int valid = min(8, m - j);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const unsigned c = (ww[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+                        sum += c; sq += (unsigned long long)c * c; nb += (k < valid && c == 0u);
+                    }
+                }
+            }
+            long long sq_w = fpt_warp_sum_i64((long long)sq), sum_w = fpt_warp_sum_i64((long long)sum), nb_w = fpt_warp_sum_i64((long long)nb);
+            sq_w = __shfl_sync(FPT_FULL_MASK, sq_w, 0); sum_w = __shfl_sync(FPT_FULL_MASK, sum_w, 0); nb_w = __shfl_sync(FPT_FULL_MASK, nb_w, 0);
+            if (lane == 0) { s.rmean[i] = (double)sq_w; s.w[i] = (double)nb_w; blanks += nb_w; total += sum_w; }
+        }
+        blanks = fpt_block_sum_i64(blanks, s.sc.redi);
+        total = fpt_block_sum_i64(total, s.sc.redi);
+        const long long mm = (long long)m * m;
+        if (blanks > mm / 2) { if (tid == 0) status[w] = FPT_WIN_DISCARDED; __syncthreads(); continue; }   /* css.c:355 */
+        const double avg = __ddiv_rn((double)total, (double)mm);                                            /* css.c:357 */
+        const double v2 = avg * avg;
+        for (int i = tid; i < m; i += T) s.rmean[i] = (s.rmean[i] + s.w[i] * v2) / m;
+        __syncthreads();
+        double g = 0.0;
+        for (int i = tid; i < m; i += T) g += s.rmean[i];
+        g = fpt_block_sum(g, s.sc.red) / m;
+        FPT_LZ_MARK(1);
+        FptLzMatrix M;
+        M.form = wide ? 1 : 2; M.ld = ld; M.data = c8; M.g = g; M.v2 = v2;
+        fpt_lanczos_iterate(M, Q, m, Xout + (size_t)w * 2 * m, evals_out ? evals_out + 3 * w : 0, s, steps_out ? steps_out + w : 0);
+        if (tid == 0) status[w] = FPT_WIN_SCORED;
+        __syncthreads();
+    }
+}
+
+/* Legacy route (fpt_set_k4_mode(0), the frequency metric, windows of more than 65535 SNPs): dissimilarities as an fp64 matrix.
+   mds 0 (and the first half of mds 2) for large cohorts: one CTA walks windows blockIdx.x, +gridDim.x, ...;
    gscratch: per CTA fpt_css_mats_doubles(m) doubles (B, then the Lanczos basis) */
 __global__ void __launch_bounds__(512, 2)
 fpt_css_mds_large_kernel(const unsigned *__restrict__ planes, const double *__restrict__ absdiff, int m,

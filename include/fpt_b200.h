@@ -78,6 +78,14 @@ int fpt_debug_lanczos_phases(unsigned long long *out8);
    2 (default) 8-bit count codes, 1 16-bit count codes, 0 the fp64 matrix B. Every window takes the highest form it qualifies
    for; lower settings exist for the parity tests. */
 void fpt_set_lanczos_form(int max_form);
+/* Large cohorts, the genotype-distance matrix D = [P|M][M|P]' (compare_all, css/css.c:277-327; csrc/fpt_css_k4.cuh): 2 (default) one
+   u8 GEMM per window on tcgen05 with the accumulators in tensor memory, 1 bit-plane popcounts — both write count codes that the
+   Lanczos kernel streams — 0 the round-1 route (fp64 matrix in global memory, converted to codes in place). Identical results in
+   modes 1 and 2 (integers); mode 0 differs by rounding only. A lanczos_form below 2 implies mode 0. */
+void fpt_set_k4_mode(int mode);
+/* diagnostic: SM cycles per phase of the tcgen05 GEMM kernel since the last call (0 operand expansion, 1 waiting for MMAs,
+   2 accumulator drain + code stores) */
+int fpt_debug_k4_phases(unsigned long long *out4);
 /* number of permutations since the last call whose integer surrogate score could not decide `permuted >= observed` and
    were re-scored in the reference's summation order (diagnostic; synchronises the device); -1 on error */
 long long fpt_css_perm_rechecks(void);
