@@ -56,6 +56,7 @@ SYMBOLS = {
     "fpt_set_lanczos_form": (None, [_I]),
     "fpt_set_k4_mode": (None, [_I]),
     "fpt_debug_k4_phases": (_I, [_P]),
+    "fpt_debug_k4_counts": (_I, [C.POINTER(Genotypes), C.POINTER(ScanRange), _I, C.c_int64, _P]),
     "fpt_css_perm_rechecks": (C.c_longlong, []),
     "fpt_release": (None, []),
     "fpt_window_state": (C.c_uint64, [C.c_uint64, C.c_int64, _I]),

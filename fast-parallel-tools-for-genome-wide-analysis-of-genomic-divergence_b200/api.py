@@ -50,6 +50,18 @@ def set_k4_mode(mode):
     _lib.load().fpt_set_k4_mode(int(mode))
 
 
+def k4_counts(a, b, pos, asize, bsize, regend, wsize, wstep, window, mode=2):
+    """Parity probe: the m x m opposite-homozygote counts of one window as the tcgen05 GEMM (mode 2) or the popcount kernel (mode 1)
+    produces them."""
+    keep = []
+    g = _genotypes(a, b, pos, asize, bsize, keep)
+    r, n = _range(regend, wsize, wstep, FPT_SCAN_SERIAL, None, None, None, None, None, keep)
+    m = asize + bsize
+    out = np.zeros((m, m), dtype=np.int32)
+    _lib.check(_lib.load().fpt_debug_k4_counts(C.byref(g), C.byref(r), int(mode), int(window), out.ctypes.data))
+    return out
+
+
 def set_perm_large_kernel(tensor_memory):
     """Large cohorts (m > 250): 1 / True = tcgen05 permutation kernel (default), 0 / False = the general kernel, 2 = tcgen05
     kernel with a coarse (10-bit) surrogate that forces many exact re-scorings. Same results in every mode."""

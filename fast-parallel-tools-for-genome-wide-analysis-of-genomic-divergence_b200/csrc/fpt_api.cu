@@ -1175,6 +1175,58 @@ extern "C" int fpt_css_scan(const fpt_genotypes *g, const fpt_scan_range *r, int
     return css_scan_core(c, ar, g, d, plan, r, treshold, runs, drosophila, mds, scores, p, written, probes);
 }
 
+/* parity probe: the count codes of ONE window (global index `window`) as the chosen K4 kernel writes them, expanded to int32
+   counts[m * m] on the host (mode 2 tcgen05 GEMM, 1 popcounts) */
+extern "C" int fpt_debug_k4_counts(const fpt_genotypes *g, const fpt_scan_range *r, int mode, int64_t window, int32_t *counts) {
+    DeviceCtx *c;
+    CHECK(get_ctx(&c));
+    CHECK(check_genotypes(g));
+    long long nwin;
+    CHECK(check_range(r, &nwin));
+    if (!counts || !g->pos || window < r->window_begin || window >= r->window_end) return fail(FPT_ERR_ARG, "k4 probe: bad arguments");
+    if (mode != 1 && mode != 2) return fail(FPT_ERR_ARG, "k4 probe: mode must be 1 (popcounts) or 2 (tcgen05)");
+    const int m = g->asize + g->bsize;
+    HostStream hs;
+    CHECK(hs.make());
+    Arena ar(hs.st);
+    DevGenotypes d;
+    UploadPlan plan;
+    CHECK(upload_genotypes(ar, g, &d, &plan, FPT_CHUNK_BYTES_CSS));
+    ScanFront f;
+    CHECK(scan_front(ar, g, r, &f));
+    CHECK(upload_enqueue(&plan, plan.n));
+    CU(cudaStreamWaitEvent(hs.st, plan.ev[plan.n - 1], 0));
+    uint32_t *d_planes;
+    CHECK(ar.get(&d_planes, fpt_dev_css_planes_bytes(g->nsnp, m) / 4));
+    if (d.a64) CHECK(fpt_dev_css_pack_f64(d.a64, d.b64, g->nsnp, g->asize, g->bsize, d_planes, hs.st));
+    else CHECK(fpt_dev_css_pack_i8((const int8_t *)d.a8, (const int8_t *)d.b8, g->nsnp, g->asize, g->bsize, d_planes, hs.st));
+    const size_t stride = fpt_k4_window_stride(m);
+    unsigned char *d_codes;
+    CHECK(ar.get(&d_codes, stride));
+    CU(cudaMemsetAsync(d_codes, 0xEE, stride, hs.st));
+    const long long wi = window - r->window_begin;
+    if (mode == 2) {
+        CU(cudaFuncSetAttribute(fpt_css_k4_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FPT_K4_SMEM));
+        fpt_css_k4_umma_kernel<<<1, FPT_K4_THREADS, FPT_K4_SMEM, hs.st>>>(d_planes, m, f.d_wl + wi, f.d_wr + wi, 1, d_codes, stride);
+    } else {
+        const size_t smem4 = fpt_k4_popc_smem(m);
+        if (smem4 > 48 * 1024) CU(cudaFuncSetAttribute(fpt_css_k4_popc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        fpt_css_k4_popc_kernel<<<1, 256, smem4, hs.st>>>(d_planes, m, f.d_wl + wi, f.d_wr + wi, 1, d_codes, stride);
+    }
+    CU(cudaGetLastError());
+    std::vector<unsigned char> h(stride);
+    int32_t lr[2];
+    CU(cudaMemcpyAsync(h.data(), d_codes, stride, cudaMemcpyDeviceToHost, hs.st));
+    CU(cudaMemcpyAsync(&lr[0], f.d_wl + wi, 4, cudaMemcpyDeviceToHost, hs.st));
+    CU(cudaMemcpyAsync(&lr[1], f.d_wr + wi, 4, cudaMemcpyDeviceToHost, hs.st));
+    CU(cudaStreamSynchronize(hs.st));
+    const int ld = fpt_k4_ld(m), esz = fpt_k4_code_bytes(lr[1] - lr[0]);
+    for (int i = 0; i < m; i++)
+        for (int j = 0; j < m; j++)
+            counts[(size_t)i * m + j] = lr[1] <= lr[0] ? -1 : (esz == 1 ? (int32_t)h[(size_t)i * ld + j] : (int32_t)((const unsigned short *)h.data())[(size_t)i * ld + j]);
+    return FPT_OK;
+}
+
 /* ------------------------------------------------------------------------------------------------ drop-ins */
 /* comparative.c:25-34 get_population_size, bounded by the array length (the reference runs off the end
    when every position is equal) */

@@ -230,6 +230,7 @@ FPT_D void fpt_lanczos_iterate(const FptLzMatrix &M, double *Q, int m, double *X
            re-introduced; a second pass runs when the first one took away more than half of the vector (the "twice is enough"
            criterion) — with the recurrence in front that is the exception, so the basis is read once per step, not twice. */
         for (int i = tid; i <= j; i += T) s.h[i] = 0.0;
+        __syncthreads();                                            /* the product's rows were written by other warps */
         double aj = 0.0;
         for (int e = tid; e < m; e += T) aj += s.q[e] * s.w[e];
         aj = fpt_block_sum(aj, s.sc.red);
@@ -340,7 +341,6 @@ FPT_D void fpt_lanczos_iterate(const FptLzMatrix &M, double *Q, int m, double *X
 FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *evals3, const FptLanczosSmem &s, int *steps_out,
                                 int max_form = 2) {
     const int T = blockDim.x, tid = threadIdx.x;
-    const int cap = fpt_lanczos_cap(m);
     const size_t mm = (size_t)m * m;
     FPT_LZ_START();
     /* ---- 1. row means of S = D.D and the grand mean (same closed form as the small-cohort paths); on the way, whether

@@ -86,6 +86,11 @@ void fpt_set_k4_mode(int mode);
 /* diagnostic: SM cycles per phase of the tcgen05 GEMM kernel since the last call (0 operand expansion, 1 waiting for MMAs,
    2 accumulator drain + code stores) */
 int fpt_debug_k4_phases(unsigned long long *out4);
+/* parity probe: opposite-homozygote counts of every pair of individuals in window `window` (global index inside r), as the chosen
+   kernel (2 tcgen05 GEMM, 1 popcounts) writes them: counts[m * m] int32 on the host; -1 everywhere for an empty window */
+struct fpt_genotypes;
+struct fpt_scan_range;
+int fpt_debug_k4_counts(const struct fpt_genotypes *g, const struct fpt_scan_range *r, int mode, int64_t window, int32_t *counts);
 /* number of permutations since the last call whose integer surrogate score could not decide `permuted >= observed` and
    were re-scored in the reference's summation order (diagnostic; synchronises the device); -1 on error */
 long long fpt_css_perm_rechecks(void);

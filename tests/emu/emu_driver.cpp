@@ -12,6 +12,7 @@ FPT_EMU_DEFINE_GLOBALS
 #include "fpt_css.cuh"
 #include "fpt_css_eig.cuh"
 #include "fpt_css_lanczos.cuh"
+#include "fpt_css_k4.cuh"
 #include "fpt_css_perm.cuh"
 #include "fpt_css_perm_large.cuh"
 #include "fpt_css_observed.cuh"
@@ -115,6 +116,20 @@ void emu_css_mds_large(const unsigned *planes, const double *absdiff, int m, con
     double *gp = gs.data();
     run_grid(grid, threads, fpt_lanczos_smem_bytes(m, wch), [=]() {
         fpt_css_mds_large_kernel(planes, absdiff, m, wleft, wright, nwin, wch, gp, X, evals, status, steps);
+    });
+}
+
+/* large-cohort code route: popcount count codes (fpt_css_k4.cuh), then Lanczos on the codes */
+void emu_css_mds_codes(const unsigned *planes, int m, const int *wleft, const int *wright, long long nwin, int threads, int grid,
+                       double *X, double *evals, unsigned char *status, int *steps) {
+    const size_t stride = fpt_k4_window_stride(m);
+    std::vector<unsigned char> codes((size_t)nwin * stride + 64, 0xAB);
+    unsigned char *pc = codes.data();
+    run_grid(grid, 64, fpt_k4_popc_smem(m), [=]() { fpt_css_k4_popc_kernel(planes, m, wleft, wright, nwin, pc, stride); });
+    std::vector<double> basis((size_t)grid * fpt_lanczos_cap(m) * m + 1);
+    double *pb = basis.data();
+    run_grid(grid, threads, fpt_lanczos_smem_bytes(m, 0), [=]() {
+        fpt_css_mds_codes_kernel(pc, stride, m, wleft, wright, nwin, pb, X, evals, status, steps);
     });
 }
 

@@ -203,8 +203,9 @@ def test_css_mds_kernels(emu, oracle):
     assert scored >= 10
 
 
-@pytest.mark.parametrize("shape", [(6, 5, 220, 20000), (30, 34, 260, 12000), (1, 1, 60, 6000)])
-def test_css_mds_large_cohort_kernel(emu, oracle, shape):
+@pytest.mark.parametrize("route", ["legacy", "codes"])
+@pytest.mark.parametrize("shape", [(6, 5, 220, 20000), (30, 34, 260, 12000), (1, 1, 60, 6000), (9, 8, 3000, 12000)])
+def test_css_mds_large_cohort_kernel(emu, oracle, shape, route):
     """the Lanczos kernel used beyond the one-warp path, run here on small and medium cohorts (it is size-agnostic): early
     stop by the residual test (m = 64), complete Krylov space (m = 11, 2), windows discarded by fill_averages"""
     asize, bsize, S, L = shape
@@ -216,7 +217,10 @@ def test_css_mds_large_cohort_kernel(emu, oracle, shape):
     wl, wr = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
     emu.emu_window_table(iptr(pos), ll(S), ll(0), ll(n), L, wsize, wstep, 0, iptr(wl), iptr(wr))
     X, ev, st, steps = np.zeros((n, m, 2)), np.zeros((n, 3)), np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.int32)
-    emu.emu_css_mds_large(vp(planes), None, m, iptr(wl), iptr(wr), ll(n), 2, 64, 2, dptr(X), dptr(ev), vp(st), iptr(steps))
+    if route == "legacy":      # fp64 dissimilarity matrix in global memory, converted to codes in place where it qualifies
+        emu.emu_css_mds_large(vp(planes), None, m, iptr(wl), iptr(wr), ll(n), 2, 64, 2, dptr(X), dptr(ev), vp(st), iptr(steps))
+    else:                      # count codes from the popcount form of the genotype GEMM (u8, and u16 beyond 255 SNPs per window)
+        emu.emu_css_mds_codes(vp(planes), m, iptr(wl), iptr(wr), ll(n), 64, 2, dptr(X), dptr(ev), vp(st), iptr(steps))
     scored = 0
     for w in range(n):
         l, r = int(wl[w]), int(wr[w])

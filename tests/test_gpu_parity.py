@@ -394,6 +394,52 @@ def test_css_large_cohort_default_route_1000_permutations_vs_oracle(fpt, oracle,
         assert np.all(pr["nperm"] == mcr)
 
 
+@pytest.mark.parametrize("asize,bsize,nsnp,wsize", [(500, 500, 600, 50000), (130, 171, 700, 50000), (200, 184, 2400, 50000), (150, 150, 6000, 25000),
+                                                    (77, 90, 9000, 100000)])
+def test_css_genotype_gemm_counts_equal_a_host_product(fpt, asize, bsize, nsnp, wsize):
+    """the tcgen05 u8 GEMM D = [P|M][M|P]' (and the popcount kernel) against numpy's integer product of the same indicator
+    matrices, every pair of every probed window: exact. Covers tile padding (m = 301, 167), one- and two-byte codes, K chunks
+    (192 SNPs each) with accumulation in tensor memory including ragged last chunks, window edges inside a bit-plane word."""
+    regend = 200000
+    ch, _ = _synth(900 + nsnp, regend, nsnp, asize, bsize)
+    m = asize + bsize
+    pos = ch["pos"]
+    G = np.concatenate([ch["acodes"].reshape(-1, asize), ch["bcodes"].reshape(-1, bsize)], axis=1)
+    for w in (0, 1, regend // wsize - 1):
+        l, r = int(np.searchsorted(pos, w * wsize, "left")), int(np.searchsorted(pos, w * wsize + wsize, "right"))
+        P, M = (G[l:r] == 3).astype(np.int64), (G[l:r] == -3).astype(np.int64)
+        want = P.T @ M + M.T @ P
+        for mode in (2, 1):
+            got = fpt.k4_counts(ch["acodes"], ch["bcodes"], pos, asize, bsize, regend, wsize, wsize, w, mode=mode)
+            assert np.array_equal(got, want), "window %d mode %d: %d of %d pairs differ" % (w, mode, int((got != want).sum()), m * m)
+
+
+@pytest.mark.parametrize("asize,bsize,nsnp,wsize", [(500, 500, 600, 50000), (130, 171, 700, 50000), (200, 184, 2400, 50000), (150, 150, 6000, 25000)])
+def test_css_genotype_gemm_on_tensor_cores_matches_popcounts(fpt, asize, bsize, nsnp, wsize):
+    """Large cohorts: the genotype-distance matrix D = [P|M][M|P]' (compare_all, css.c:277-327) as ONE u8 GEMM per window on
+    tcgen05 / tensor memory (fpt_css_k4_umma_kernel, the default) against the bit-plane popcount kernel writing the same count
+    codes: integers, so embedding, scores and p-values must be IDENTICAL — m = 1000; m = 301 (row / column padding of the 128 x 256
+    tiles); ~600 SNPs per window (two-byte codes, four K chunks with accumulation in tensor memory); ~750 SNPs per window with
+    ragged last chunks. The round-1 route (fp64 matrix, mode 0) agrees to rounding."""
+    from fpt_b200 import api
+    regend, wstep, seed = 200000, wsize, 21
+    ch, _ = _synth(900 + nsnp, regend, nsnp, asize, bsize)
+    out = []
+    try:
+        for mode in (2, 1, 0):
+            api.set_k4_mode(mode)
+            out.append(fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 20, 100, mds=0, seed=seed, probes=True))
+    finally:
+        api.set_k4_mode(2)
+    (s2, p2, w2, pr2), (s1, p1, w1, pr1), (s0, p0, w0, pr0) = out
+    assert (w2 == 1).sum() >= 3 and np.array_equal(w2, w1) and np.array_equal(w2, w0)
+    assert np.array_equal(pr2["X"], pr1["X"], equal_nan=True)           # same integers in, same arithmetic after
+    assert np.array_equal(s2, s1, equal_nan=True) and np.array_equal(p2, p1)
+    np.testing.assert_allclose(s0, s2, rtol=1e-9, atol=1e-12)
+    assert np.array_equal(p0, p2)
+    np.testing.assert_allclose(pr0["evals"], pr2["evals"], rtol=1e-10, atol=1e-9)
+
+
 def test_tcgen05_plumbing_against_a_host_product():
     """csrc/fpt_umma.cuh on its own: bulk TMA copies into shared memory, shared-memory descriptors of the K-major core-matrix
     layout, `tcgen05.mma kind::i8` into tensor memory, `tcgen05.ld` back — a 128 x 256 x 128 u8 product equal to the host's."""
