@@ -51,6 +51,7 @@ SYMBOLS = {
     "fpt_set_perm_mode": (None, [_I]),
     "fpt_get_perm_mode": (_I, []),
     "fpt_set_perm_large_kernel": (None, [_I]),
+    "fpt_set_perm_small_kernel": (None, [_I]),
     "fpt_debug_umma_phases": (_I, [_P]),
     "fpt_debug_lanczos_phases": (_I, [_P]),
     "fpt_set_lanczos_form": (None, [_I]),

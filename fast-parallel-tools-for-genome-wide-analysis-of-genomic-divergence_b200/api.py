@@ -45,6 +45,11 @@ def set_lanczos_form(max_form):
     _lib.load().fpt_set_lanczos_form(int(max_form))
 
 
+def set_perm_small_kernel(v):
+    """Cohorts of 8..64, independent shuffles: 1 / True = fpt_css_perm3_kernel (default), 0 / False = the round-1 kernel."""
+    _lib.load().fpt_set_perm_small_kernel(int(v))
+
+
 def set_k4_mode(mode):
     """Large cohorts, genotype-distance matrix: 2 = tcgen05 u8 GEMM (default), 1 = popcounts, 0 = legacy fp64 matrix."""
     _lib.load().fpt_set_k4_mode(int(mode))

@@ -29,6 +29,7 @@
 #include "fpt_css_lanczos.cuh"
 #include "fpt_css_k4.cuh"
 #include "fpt_css_perm.cuh"
+#include "fpt_css_perm3.cuh"
 #include "fpt_css_perm_large.cuh"
 #include "fpt_css_perm_umma.cuh"
 #include "fpt_fet.cuh"
@@ -44,12 +45,13 @@ static std::atomic<int> g_device{-1};           /* -1: whatever device is curren
 static std::atomic<int> g_lanczos_form{2};      /* large-cohort MDS: highest product form allowed (2 8-bit codes, 1 16-bit codes, 0 fp64 matrix) */
 static std::atomic<int> g_perm_umma{1};         /* large cohorts: 1 = tcgen05 permutation kernel, 0 = the general (mma.sync) kernel */
 static std::atomic<int> g_perm_chain{0};        /* CSS label shuffles: 0 = independent per permutation, 1 = the reference's chain */
+static std::atomic<int> g_perm_small{1};        /* cohorts of 8..64, independent shuffles: 1 = fpt_css_perm3_kernel, 0 = the round-1 kernel (fpt_css_perm2_kernel) */
 static std::atomic<int> g_k4_mode{2};           /* large cohorts, genotype-distance matrix: 2 = tcgen05 u8 GEMM, 1 = popcounts, 0 = legacy fp64 matrix */
 
-struct Knobs { int lanczos_form, perm_umma, perm_chain, k4_mode; };
+struct Knobs { int lanczos_form, perm_umma, perm_chain, k4_mode, perm_small; };
 static Knobs knobs_now() {
     Knobs k;
-    k.lanczos_form = g_lanczos_form.load(); k.perm_umma = g_perm_umma.load(); k.perm_chain = g_perm_chain.load(); k.k4_mode = g_k4_mode.load();
+    k.lanczos_form = g_lanczos_form.load(); k.perm_umma = g_perm_umma.load(); k.perm_chain = g_perm_chain.load(); k.k4_mode = g_k4_mode.load(); k.perm_small = g_perm_small.load();
     return k;
 }
 
@@ -293,6 +295,7 @@ extern "C" void fpt_set_perm_mode(int chain) { g_perm_chain.store(chain != 0); }
 extern "C" int fpt_get_perm_mode(void) { return g_perm_chain.load(); }
 extern "C" void fpt_set_perm_large_kernel(int tensor_memory) { g_perm_umma.store(tensor_memory); }
 extern "C" void fpt_set_lanczos_form(int max_form) { g_lanczos_form.store(max_form < 0 ? 0 : (max_form > 2 ? 2 : max_form)); }
+extern "C" void fpt_set_perm_small_kernel(int v) { g_perm_small.store(v != 0); }
 extern "C" void fpt_set_k4_mode(int mode) { g_k4_mode.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode)); }
 extern "C" int fpt_debug_k4_phases(unsigned long long *out4) {
     unsigned long long zero[4] = { 0 };
@@ -764,10 +767,17 @@ static int dev_css_windows(const Knobs &kn, const uint32_t *planes, const double
         const long long terms = (long long)std::min(asize, bsize) * m + 1;
         int qb = fpt_css_perm2_uses_mma(m) ? 23 : 22;     /* tensor-core path: three base-256 digits (q <= 2^23 fits 24 bits) */
         while (qb > 4 && (terms << qb) >= (1LL << 31)) qb--;
-        CHECK(persistent_grid(c, fpt_css_perm2_kernel, p.perm_threads, p.smem_perm2, nwin, &grid));
-        { ProfScope ps_("css_perm", st); fpt_css_perm2_kernel<<<grid, p.perm_threads, p.smem_perm2, st>>>(
-              ws.X, m, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, kn.perm_chain, qb, scores, pv,
-              hits, nperm, c->rechecks); }
+        const size_t smem3 = fpt_css_perm3_smem_bytes(m);
+        if (kn.perm_small && fpt_css_perm3_ok(m, kn.perm_chain) && smem3 <= (size_t)c->smem_optin) {
+            CHECK(persistent_grid(c, fpt_css_perm3_kernel, FPT_P3_T, smem3, nwin, &grid));
+            { ProfScope ps_("css_perm", st); fpt_css_perm3_kernel<<<grid, FPT_P3_T, smem3, st>>>(
+                  ws.X, m, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, qb, scores, pv, hits, nperm, c->rechecks); }
+        } else {
+            CHECK(persistent_grid(c, fpt_css_perm2_kernel, p.perm_threads, p.smem_perm2, nwin, &grid));
+            { ProfScope ps_("css_perm", st); fpt_css_perm2_kernel<<<grid, p.perm_threads, p.smem_perm2, st>>>(
+                  ws.X, m, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, kn.perm_chain, qb, scores, pv,
+                  hits, nperm, c->rechecks); }
+        }
         CU(cudaGetLastError());
     } else if (p.perm_umma) {
         CHECK(launch_perm_umma(c, kn, p, ws, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, scores, pv,

@@ -47,13 +47,14 @@ struct FptLanczosSmem {
     double *beta;     /* cap */
     double *h;        /* cap: projections on the basis */
     double *rmean;    /* m */
+    double *lut;      /* 256: S(code) of the 8-bit code form */
     FptEigWork ew;    /* tridiagonal eigen-solve of order <= cap, warp 0 */
     FptCssScratch sc; /* reductions + bit-plane words of the dissimilarity stage */
 };
 
 FPT_HD size_t fpt_lanczos_smem_bytes(int m, int wch) {
     const int cap = fpt_lanczos_cap(m);
-    size_t off = (size_t)(3 * m + 16) * 8 + (size_t)3 * cap * 8 + (size_t)13 * cap * 8 + 66 * 8;
+    size_t off = (size_t)(3 * m + 16) * 8 + 256 * 8 + (size_t)3 * cap * 8 + (size_t)13 * cap * 8 + 66 * 8;
     off = (off + 15) & ~(size_t)15;
     return off + (size_t)wch * 2 * m * 4;
 }
@@ -63,6 +64,7 @@ FPT_D FptLanczosSmem fpt_lanczos_carve(unsigned char *smem, int m, int wch) {
     const int cap = fpt_lanczos_cap(m);
     double *p = (double *)smem;
     s.q = p; p += m + 16; s.w = p; p += m; s.rmean = p; p += m;      /* q: 16 spare entries, kept zero (padded code columns) */
+    s.lut = p; p += 256;
     s.alpha = p; p += cap; s.beta = p; p += cap; s.h = p; p += cap;
     s.ew.A = 0;
     s.ew.d = p; p += cap; s.ew.e = p; p += cap; s.ew.tau = p; p += cap;
@@ -111,9 +113,9 @@ FPT_D void fpt_cta_symv(const double *__restrict__ B, int m, const double *x, do
    The integer c^2 becomes a double by the 2^52 trick (one fp64 add instead of a conversion instruction). A warp per row,
    ROWS rows in flight (eight with 8-bit codes: 2 KB of loads outstanding per warp), each lane one 8-byte load of consecutive codes: four 16-bit ones (m % 4 == 0) or, when no count exceeds
    255, eight 8-bit ones (m % 8 == 0). sx = 1'x and rx = r'x are given. */
-template <typename CodeT, int ROWS>
+template <typename CodeT, int ROWS, bool LUT>
 FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, int ld, const double *x, double *y, const double *rmean,
-                              double g, double v2, double sx, double rx) {
+                              double g, double v2, double sx, double rx, const double *lut) {
     constexpr int PER = 8 / (int)sizeof(CodeT);                 /* codes per 8-byte load: 4 or 8 */
     constexpr int BITS = 8 * (int)sizeof(CodeT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -137,8 +139,15 @@ FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, int ld, const 
                     for (int r = 0; r < ROWS; r++) {
                         const unsigned word = ((k + kk) * BITS) < 32 ? cc[r].x : cc[r].y;
                         const unsigned c = (word >> (((k + kk) * BITS) & 31)) & ((1u << BITS) - 1u);
-                        const double sq = __hiloint2double(0x43300000, (int)(c * c)) - 4503599627370496.0;
-                        acc[r] = fma(c ? sq : v2, xk, acc[r]);
+                        if (LUT) {
+                            /* 8-bit codes: S(c) from a 256-entry shared-memory table (c^2, or v2 for c = 0) — one load instead
+                               of a multiply, the 2^52 conversion add, a compare and two selects per element; the product is
+                               bound by instruction issue, not by bytes */
+                            acc[r] = fma(lut[c], xk, acc[r]);
+                        } else {
+                            const double sq = __hiloint2double(0x43300000, (int)(c * c)) - 4503599627370496.0;
+                            acc[r] = fma(c ? sq : v2, xk, acc[r]);
+                        }
                     }
                 }
             }
@@ -196,6 +205,7 @@ FPT_D void fpt_lanczos_iterate(const FptLzMatrix &M, double *Q, int m, double *X
     const double *A = reinterpret_cast<const double *>(M.data);
     const double g = M.g, v2 = M.v2;
     for (int e = tid; e < 16; e += T) s.q[m + e] = 0.0;
+    if (narrow) for (int e = tid; e < 256; e += T) s.lut[e] = e ? (double)(e * e) : v2;
     /* ---- 2. Lanczos. Start vector: fixed pseudo-random signs and magnitudes (any vector with a component along the
        leading eigenvectors works; a fixed one keeps runs reproducible) */
     double nn = 0.0;
@@ -219,8 +229,8 @@ FPT_D void fpt_lanczos_iterate(const FptLzMatrix &M, double *Q, int m, double *X
             for (int e = tid; e < m; e += T) { const double v = s.q[e]; sx += v; rx += s.rmean[e] * v; }
             sx = fpt_block_sum(sx, s.sc.red);
             rx = fpt_block_sum(rx, s.sc.red);
-            if (narrow) fpt_cta_symv_codes<unsigned char, 8>(codes8, m, M.ld, s.q, s.w, s.rmean, g, v2, sx, rx);
-            else fpt_cta_symv_codes<unsigned short, 4>(codes, m, M.ld, s.q, s.w, s.rmean, g, v2, sx, rx);
+            if (narrow) fpt_cta_symv_codes<unsigned char, 8, true>(codes8, m, M.ld, s.q, s.w, s.rmean, g, v2, sx, rx, s.lut);
+            else fpt_cta_symv_codes<unsigned short, 4, false>(codes, m, M.ld, s.q, s.w, s.rmean, g, v2, sx, rx, s.lut);
         } else {
             fpt_cta_symv(A, m, s.q, s.w);
         }

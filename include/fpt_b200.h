@@ -67,6 +67,10 @@ int fpt_get_perm_mode(void);
    a large share of the permutations through the exact re-scoring. Same decisions in every mode; the switch exists for the
    parity tests. */
 void fpt_set_perm_large_kernel(int tensor_memory);
+/* Cohorts of 8..64 individuals (the genome scans), independent shuffles: 1 (default) fpt_css_perm3_kernel (two permutations in
+   flight per thread, conflict-free label layout, no fp64 distance matrix; csrc/fpt_css_perm3.cuh), 0 the round-1 kernel
+   fpt_css_perm2_kernel. Same hits, permutations drawn, p and scores from both; the switch exists for the parity tests. */
+void fpt_set_perm_small_kernel(int v);
 /* diagnostic: SM cycles per phase of the tensor-memory permutation kernel since the last call, summed over CTAs and windows
    (0 distance pass, 1 hand-over of the observed score, 2 shuffles, 3 membership rows, 4 contraction, 5 decisions, 6 label copy-out
    and adjacent-pair sums); synchronises the device */

@@ -14,6 +14,7 @@ FPT_EMU_DEFINE_GLOBALS
 #include "fpt_css_lanczos.cuh"
 #include "fpt_css_k4.cuh"
 #include "fpt_css_perm.cuh"
+#include "fpt_css_perm3.cuh"
 #include "fpt_css_perm_large.cuh"
 #include "fpt_css_observed.cuh"
 #include "fpt_tables.h"
@@ -204,6 +205,17 @@ unsigned long long emu_css_perm_sur(const double *Xall, int m, int asize, int bs
                   int *out_hits, int *out_n) {
     return emu_css_perm_impl(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override, dist_in_smem, tracks_in_smem,
                              nthreads, grid, wide_tracks, chain, qbits, out_score, out_p, out_hits, out_n);
+}
+
+unsigned long long emu_css_perm3(const double *Xall, int m, int asize, int bsize, long long wbase, long long nwin,
+                                 const unsigned char *status, int treshold, int runs, uint64_t seed, const uint64_t *state_override,
+                                 int qbits, int grid, double *out_score, double *out_p, int *out_hits, int *out_n) {
+    unsigned long long rechecks = 0, *pr = &rechecks;
+    run_grid(grid, FPT_P3_T, fpt_css_perm3_smem_bytes(m), [=]() {
+        fpt_css_perm3_kernel(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override, qbits, out_score, out_p,
+                             out_hits, out_n, pr);
+    });
+    return rechecks;
 }
 
 unsigned long long emu_css_perm2(const double *Xall, int m, int asize, int bsize, long long wbase, long long nwin,

@@ -380,6 +380,42 @@ def test_css_perm_kernels_chunks_early_stop_and_scratch_paths(emu, oracle, chain
             emu.emu_css_perm2(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), tres, runs, C.c_uint64(0), vp(states), chain, qbits, 32, 2,
                               dptr(sc), dptr(p), iptr(hits), iptr(nn))
             assert list(hits) == want_h and list(nn) == want_n and list(p) == want_p
+            if not chain and 8 <= m <= 64:
+                # the headline kernel (two permutations in flight per thread, [word][slot] labels, split LCG, no fp64 distances)
+                emu.emu_css_perm3.restype = C.c_ulonglong
+                sc3, p3, hits3, nn3 = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+                emu.emu_css_perm3(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), tres, runs, C.c_uint64(0), vp(states), qbits, 2,
+                                  dptr(sc3), dptr(p3), iptr(hits3), iptr(nn3))
+                assert list(hits3) == want_h and list(nn3) == want_n and list(p3) == want_p
+                assert np.array_equal(sc3, sc)                     # observed score: same bits as the round-1 kernel's
+
+
+def test_css_perm3_rounds_and_ragged_tails(emu, oracle):
+    """fpt_css_perm3_kernel over several rounds of 512 permutations: early stops in the first, second and third round, a ragged
+    last round, 20+20 (two k-steps of the u8 MMA) and 9+7 individuals, against the oracle's independent-shuffle restatement"""
+    emu.emu_css_perm3.restype = C.c_ulonglong
+    rng = np.random.default_rng(18)
+    for asize, bsize, n in ((20, 20, 3), (9, 7, 4)):
+        m = asize + bsize
+        X = rng.normal(size=(n, m, 2))
+        X[:, :asize, 0] += np.linspace(0.0, 0.8, n)[:, None]
+        st = np.full(n, 2, dtype=np.uint8)
+        states = (np.arange(n, dtype=np.uint64) * 104729 + 77)
+        qbits = min(21, int(np.floor(np.log2(2 ** 31 / (min(asize, bsize) * m + 1)))))
+        for tres, runs in ((1000, 1000), (150, 1300), (400, 1100)):
+            want = []
+            for w in range(n):
+                dist = np.zeros((m, m))
+                oracle.fpt_oracle_calc_dist(dptr(X[w].copy()), m, dptr(dist))
+                tr = np.arange(m, dtype=np.int32)
+                score = oracle.fpt_oracle_css(dptr(dist), m, iptr(tr), iptr(tr[asize:]), asize, bsize)
+                h, nn = C.c_int(), C.c_int()
+                pv = oracle.fpt_oracle_significance_indep(dptr(dist), m, asize, bsize, score, tres, runs, int(states[w]), C.byref(h), C.byref(nn))
+                want.append((score, pv, h.value, nn.value))
+            sc, p, hits, nn = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+            emu.emu_css_perm3(dptr(X), m, asize, bsize, ll(0), ll(n), vp(st), tres, runs, C.c_uint64(0), vp(states), qbits, 2,
+                              dptr(sc), dptr(p), iptr(hits), iptr(nn))
+            assert [(a, b, int(c), int(d)) for a, b, c, d in zip(sc, p, hits, nn)] == want
 
 
 def test_css_perm_surrogate_many_tiles(emu, oracle):

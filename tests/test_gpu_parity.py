@@ -265,6 +265,33 @@ def test_css_permutation_early_stop_matches_oracle(fpt, oracle, mct, mcr):
     assert np.array_equal(p_g, p_o)
 
 
+@pytest.mark.parametrize("asize,bsize,mct,mcr", [(20, 20, 1000, 1000), (20, 20, 10, 5000), (7, 9, 300, 1300), (30, 34, 50, 600), (4, 4, 5, 100)])
+def test_css_headline_permutation_kernel_matches_round1_kernel(fpt, oracle, asize, bsize, mct, mcr):
+    """cohorts of 8..64: fpt_css_perm3_kernel (default) and the round-1 kernel fpt_css_perm2_kernel take the same decisions —
+    scores bit-identical, hits, permutations drawn and p identical — over several rounds, early stops and ragged tails; and
+    both equal the oracle (css.c:727-752 restated)"""
+    from fpt_b200 import api
+    regend, wsize, wstep, nsnp, seed = 60000, 2500, 500, 1500, 23
+    ch, (av, bv, apos, bpos) = _synth(61 + asize, regend, nsnp, asize, bsize, planted_every=4, planted_len=10)
+    out = []
+    try:
+        for v in (1, 0):
+            api.set_perm_small_kernel(v)
+            out.append(fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, mct, mcr, mds=0, seed=seed, probes=True))
+    finally:
+        api.set_perm_small_kernel(1)
+    (s3, p3, w3, pr3), (s2, p2, w2, pr2) = out
+    assert (w3 == 1).sum() > 50 and np.array_equal(w3, w2)
+    assert np.array_equal(s3, s2, equal_nan=True) and np.array_equal(p3, p2)
+    assert np.array_equal(pr3["hits"], pr2["hits"]) and np.array_equal(pr3["nperm"], pr2["nperm"])
+    s_o, p_o = _css_oracle_scan(oracle, av, bv, apos, bpos, regend, wsize, wstep, mct, mcr, 0, 0, seed)
+    np.testing.assert_allclose(s3, s_o, rtol=CSS_RTOL, atol=1e-12)
+    if asize + bsize > 8:
+        # 4+4: one permutation in 70 swaps the two groups as sets and ties with the observed score up to rounding, so `>=` is
+        # decided by the last bits of the embedding, i.e. by the eigensolver (GSL boundary, see test_css_scan_matches_oracle)
+        assert np.array_equal(p3, p_o)
+
+
 def test_css_dropin_matches_reference(fpt, ref_css):
     """drop-in call vs the reference's serial `compute`, classical MDS (deterministic score column)"""
     import fpt_b200.css_cython as serial
