@@ -951,6 +951,12 @@ def css_kernel_table(css, micro, hbm, nsteps):
                      frac=frac(fl / sec_step, fp64),
                      note="dense work model 6 m^2 + 9 m^3 per window (reduction 2/3, eigenvectors 1/3); the kernels do less than that "
                           "(two eigenpairs only) and are latency / issue bound at one warp per 40 x 40 window")
+        elif k == "css_observed":
+            # the observed score: asize bsize + m - 2 DEPENDENT fp64 additions per scored window (css.c:608-647), one warp per window
+            adds = scored_rank * float(a * b + m - 2)
+            e.update(bound="fp64 add latency", algorithmic_flops_per_step=adds,
+                     note="a chain of dependent additions in the reference's order: the bound is the add latency times the chain length "
+                          "over the windows resident at once, not a throughput peak")
         elif k == "css_pack":
             by = nsnp_rank * (m * 8 + m / 4.0)
             e.update(bound="hbm", algorithmic_bytes_per_step=by, achieved=by / sec_step / 1e9, peak=hbm, unit="GB/s", frac=frac(by / sec_step / 1e9, hbm),

@@ -768,10 +768,22 @@ static int dev_css_windows(const Knobs &kn, const uint32_t *planes, const double
         int qb = fpt_css_perm2_uses_mma(m) ? 23 : 22;     /* tensor-core path: three base-256 digits (q <= 2^23 fits 24 bits) */
         while (qb > 4 && (terms << qb) >= (1LL << 31)) qb--;
         const size_t smem3 = fpt_css_perm3_smem_bytes(m);
-        if (kn.perm_small && fpt_css_perm3_ok(m, kn.perm_chain) && smem3 <= (size_t)c->smem_optin) {
-            CHECK(persistent_grid(c, fpt_css_perm3_kernel, FPT_P3_T, smem3, nwin, &grid));
-            { ProfScope ps_("css_perm", st); fpt_css_perm3_kernel<<<grid, FPT_P3_T, smem3, st>>>(
-                  ws.X, m, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, qb, scores, pv, hits, nperm, c->rechecks); }
+        if (kn.perm_small && fpt_css_perm3_ok(m, kn.perm_chain) && ((qb + 8) >> 3) == 3 && smem3 <= (size_t)c->smem_optin) {
+            /* observed scores first (one warp per window, handed over in `scores`), then the permutation test */
+            const size_t smem_obs = fpt_css_observed_smem_bytes(m);
+            int grid_obs;
+            CHECK(persistent_grid(c, fpt_css_observed_kernel, FPT_OBS_WARPS * 32, smem_obs, (nwin + FPT_OBS_WARPS - 1) / FPT_OBS_WARPS, &grid_obs));
+            { ProfScope ps_("css_observed", st); fpt_css_observed_kernel<<<grid_obs, FPT_OBS_WARPS * 32, smem_obs, st>>>(ws.X, m, asize, bsize, nwin, status, scores); }
+            CU(cudaGetLastError());
+            if (fpt_css_perm3_ksteps(m) == 2) {
+                CHECK(persistent_grid(c, fpt_css_perm3_kernel<2>, FPT_P3_T, smem3, nwin, &grid));
+                { ProfScope ps_("css_perm", st); fpt_css_perm3_kernel<2><<<grid, FPT_P3_T, smem3, st>>>(
+                      ws.X, m, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, qb, scores, pv, hits, nperm, c->rechecks); }
+            } else {
+                CHECK(persistent_grid(c, fpt_css_perm3_kernel<1>, FPT_P3_T, smem3, nwin, &grid));
+                { ProfScope ps_("css_perm", st); fpt_css_perm3_kernel<1><<<grid, FPT_P3_T, smem3, st>>>(
+                      ws.X, m, asize, bsize, r->window_begin, nwin, status, treshold, runs, r->seed, st_perm, qb, scores, pv, hits, nperm, c->rechecks); }
+            }
         } else {
             CHECK(persistent_grid(c, fpt_css_perm2_kernel, p.perm_threads, p.smem_perm2, nwin, &grid));
             { ProfScope ps_("css_perm", st); fpt_css_perm2_kernel<<<grid, p.perm_threads, p.smem_perm2, st>>>(

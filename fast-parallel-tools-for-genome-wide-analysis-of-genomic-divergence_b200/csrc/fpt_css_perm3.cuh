@@ -1,47 +1,71 @@
 /*
- * fpt_css_perm3.cuh — score + Monte-Carlo permutation test for the cohorts the genome scans are made of (8 <= m <= 64,
- * independent shuffles): the headline kernel of BASELINE configs[2]. Same decisions as fpt_css_perm2_kernel (fpt_css_perm.cuh):
- * reference Fisher-Yates from the window's nrand48 stream (css/css.c:700-706), every permutation scored by the exact integer
- * surrogate on the u8 tensor cores, the rare permutation within the proven bound of the observed score re-scored in the
- * reference's summation order (css.c:608-647), early stop and p as css.c:727-752. What changed is how the work meets the SM
- * (ncu of the round-1 kernel: 38 % of the shared-memory wavefronts were bank-conflict replays of the random label swaps, warps
- * stalled ~2 cycles per issue each on fixed-latency chains, shared-memory loads and CTA barriers):
+ * fpt_css_perm3.cuh — Monte-Carlo permutation test for the cohorts the genome scans are made of (8 <= m <= 64, independent
+ * shuffles): the headline kernel of BASELINE configs[2]. Same decisions as fpt_css_perm2_kernel (fpt_css_perm.cuh): reference
+ * Fisher-Yates from the window's nrand48 stream (css/css.c:700-706), every permutation scored by the exact integer surrogate on
+ * the u8 tensor cores, the rare permutation within the proven bound of the observed score re-scored in the reference's summation
+ * order (css.c:608-647), early stop and p as css.c:727-752. The observed score itself comes from fpt_css_observed_kernel (one
+ * warp per window at full occupancy: it is a chain of asize*bsize dependent fp64 additions, and inside this kernel seven warps
+ * of eight waited for it — 20 % of all warp samples in the ncu capture of the previous form, profiles/r2_perm3_before.md).
  *
- *   - two permutations per thread IN FLIGHT: their LCG chains, draws and swaps are independent, so one hides the other's latency;
- *   - labels live in a [position][column] layout, one 256-byte line per position: thread t owns byte (t >> 6) of word (t & 63),
- *     so the address of position idx is ONE multiply-add (base_t + 256 idx) and, whatever index a draw picks, the 32 lanes of a
- *     warp touch 32 different banks — the random swaps are conflict-free by construction;
- *   - the 48-bit LCG runs on a (32 high bits, 16 low bits) split: five integer instructions per step and the draw is a shift;
- *   - no fp64 distance matrix: distances are quantised as they are computed (scale from the bounding box of the embedding), the
- *     observed score is summed in the reference's order by one warp straight from the embedding WHILE the other warps build the
- *     digit matrices, and the rare exact re-score recomputes its distances (same expression as calc_dist, css.c:573-587, so
- *     the same bits);
- *   - one block scan per 512 permutations instead of barriers around every stage.
+ * How the work meets the SM (ncu of the round-1 kernel: 90 warp instructions per permutation, 38 % of the shared-memory
+ * wavefronts bank-conflict replays of the random label swaps, a third of the warp samples waiting at CTA barriers):
+ *
+ *   - 128 threads per CTA, FOUR permutations per thread in flight: their LCG chains, draws and swaps are independent, so the
+ *     fixed-latency chains hide each other; the per-step table load and loop overhead are paid once for four;
+ *   - labels live in a [position][thread] layout, one 32-bit word per thread and position, byte k = permutation k of the thread:
+ *     the address of position idx is one multiply-add and, whatever index a draw picks, the 32 lanes of a warp touch 32
+ *     different banks — the random swaps are conflict-free by construction. The words are private to their thread: the reset to
+ *     identity needs no barrier, and the four labels at the position a step finalises come with ONE load;
+ *   - a step stores only the label that moves down (position i is final and never read again by the shuffle): membership mask
+ *     and adjacent-pair sums are read off the swaps as they happen. The rare permutation that needs its labels (exact re-score,
+ *     rejected draw) is regenerated alone from its stream position;
+ *   - draws: the 48-bit LCG on a (32 high, 16 low) split, r mod n by an exact 32-bit magic quotient (no fix-up), the rejection
+ *     test as one running maximum (r <= 2^31 - 64 is accepted for every n <= 64);
+ *   - between-group sums: 32 permutations x m individuals x 3 base-256 digits per warp on mma.sync m16n8k32 (u8 x u8 -> s32)
+ *     with the contraction index PERMUTED so that each lane's A and B fragments of both k-steps are 16 contiguous bytes: one
+ *     128-bit load per membership row and one per (column tile, digit); the column mask comes from the membership bit masks by
+ *     four shuffles, not from shared memory; the per-row sums are reduced by a 3-shuffle reduce-scatter;
+ *   - one CTA barrier per round, and only in rounds that can stop early or end the window.
  */
 #ifndef FPT_CSS_PERM3_CUH
 #define FPT_CSS_PERM3_CUH
 
 #include "fpt_css_perm.cuh"
 
-#define FPT_P3_T 256                      /* threads per CTA */
-#define FPT_P3_ROUND (2 * FPT_P3_T)       /* permutations per round: two per thread */
+#define FPT_P3_T 128                      /* threads per CTA */
+#define FPT_P3_PP 4                       /* permutations per thread in flight */
+#define FPT_P3_ROUND (FPT_P3_PP * FPT_P3_T)
+#define FPT_P3_LINE (4 * FPT_P3_T)        /* bytes per label position: one word per thread */
+#define FPT_P3_WARPS (FPT_P3_T / 32)
 
 FPT_HD int fpt_css_perm3_ok(int m, int chain) { return !chain && m >= 8 && m <= 64; }
-#define FPT_P3_LINE 256                   /* bytes per label position: 64 words x 4 threads per word */
+FPT_HD int fpt_css_perm3_ksteps(int m) { return m <= 32 ? 1 : 2; }
 
 FPT_HD size_t fpt_css_perm3_smem_bytes(int m) {
-    const int qd_rows = ((m + 7) >> 3) << 3;
+    const int qd_rows = ((m + 7) >> 3) << 3, kb = 32 * fpt_css_perm3_ksteps(m);
     size_t off = (size_t)2 * m * 8;                                   /* X */
     off += (size_t)m * m * 4;                                         /* q */
-    off += (size_t)3 * qd_rows * FPT_QD_STRIDE;                       /* digit matrices */
+    off += (size_t)(m + 1) * 8;                                       /* (magic, shift) per n */
     off = (off + 15) & ~(size_t)15;
-    off += (size_t)2 * m * FPT_P3_LINE;                               /* labels: two sets of m lines */
-    off += (size_t)FPT_P3_T * FPT_IND_STRIDE;                         /* membership rows */
-    off += (size_t)(m + 1) * 8;                                       /* (limit, magic) per n */
-    off = (off + 15) & ~(size_t)15;
-    off += (size_t)(FPT_P3_T + 2) * 16;                               /* affine skip maps: per thread, per round, per permutation */
-    off += 40 * 8 + 33 * 4 + 16;                                      /* reductions, scan */
+    off += (size_t)3 * qd_rows * kb;                                  /* digit matrices */
+    off += (size_t)m * FPT_P3_LINE;                                   /* labels */
+    off += (size_t)FPT_P3_WARPS * 32 * kb;                            /* membership rows, one set per warp */
+    off += 2 * 2 * FPT_P3_WARPS * 4 + 16;                             /* per-warp hit counts (double-buffered), stop flag */
     return off;
+}
+
+/* exact quotient of a 31-bit draw by n (2 <= n <= 64): floor(r / n) = umulhi(r, M) >> sh with M = ceil(2^(31+s) / n),
+   s = ceil(log2 n), sh = s - 1. M fits 32 bits (n > 2^(s-1), or n = 2^s and M = 2^31); the error term r e / (n 2^(31+s)),
+   e = M n - 2^(31+s) < n <= 2^s, stays below 1/n for r < 2^31, so the floor is exact (tests/test_emu_kernels.py sweeps it). */
+FPT_HD uint2 fpt_p3_magic(uint32_t n) {
+    uint2 r; r.x = 0u; r.y = 0u;
+    if (n < 2) return r;
+    uint32_t s = 0;
+    while ((1u << s) < n) s++;
+    const unsigned long long p = 1ULL << (31 + s);
+    r.x = (uint32_t)((p + n - 1) / n);
+    r.y = s - 1;
+    return r;
 }
 
 /* X <- A X + C mod 2^48 on the split state (hi = bits 16..47, lo = bits 0..15); returns nrand48's 31-bit draw (bits 17..47) */
@@ -52,188 +76,255 @@ FPT_D uint32_t fpt_p3_lcg(uint32_t &hi, uint32_t &lo) {
     return hi >> 1;
 }
 
-FPT_D uint64_t fpt_p3_join(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 16) | (uint64_t)lo; }
+/* the four permutations of a thread */
+template <bool WIDE> struct FptP3Mask { typedef uint32_t type; };
+template <> struct FptP3Mask<true> { typedef unsigned long long type; };
 
-/* label at position `idx` of the row whose position 0 lives at `row` (row = set base + the thread's column byte) */
-FPT_D unsigned char *fpt_p3_label(unsigned char *row, int idx) { return row + (unsigned)idx * FPT_P3_LINE; }
-
-/* reference-order score (css.c:608-647) of the labelling `lab` (byte idx -> individual, read through fpt_p3_label) with the
-   distances recomputed from the embedding on the fly; one thread */
-FPT_D double fpt_p3_exact_score(const double *X, unsigned char *row, int asize, int bsize) {
-    double bet = 0.0;
-    for (int i = asize; i--;) {
-        const int a = *fpt_p3_label(row, i);
-        const double xa = X[2 * a], ya = X[2 * a + 1];
-        for (int j = bsize; j--;) {
-            const int b = *fpt_p3_label(row, asize + j);
-            const double dx = __dsub_rn(xa, X[2 * b]), dy = __dsub_rn(ya, X[2 * b + 1]);
-            bet = __dadd_rn(bet, a == b ? 0.0 : __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
-        }
-    }
-    bet = __ddiv_rn(bet, (double)((long long)asize * bsize));
-    double wa = 0.0, wb = 0.0;
-    if (asize > 1) {
-        for (int i = asize - 1; i--;) {
-            const int a = *fpt_p3_label(row, i), b = *fpt_p3_label(row, i + 1);
-            const double dx = __dsub_rn(X[2 * a], X[2 * b]), dy = __dsub_rn(X[2 * a + 1], X[2 * b + 1]);
-            wa = __dadd_rn(wa, __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
-        }
-        wa = __ddiv_rn(wa, (double)((long long)asize * asize * (asize - 1)));
-    }
-    if (bsize > 1) {
-        for (int i = bsize - 1; i--;) {
-            const int a = *fpt_p3_label(row, asize + i), b = *fpt_p3_label(row, asize + i + 1);
-            const double dx = __dsub_rn(X[2 * a], X[2 * b]), dy = __dsub_rn(X[2 * a + 1], X[2 * b + 1]);
-            wb = __dadd_rn(wb, __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
-        }
-        wb = __ddiv_rn(wb, (double)((long long)bsize * bsize * (bsize - 1)));
-    }
-    return __dsub_rn(bet, __dmul_rn((double)(asize + bsize), __dadd_rn(wa, wb)));
-}
-
-/* the observed score (identity labels) by ONE WARP: the lanes compute the next 32 terms, every lane's accumulator adds them in
-   the reference's order (all lanes hold the same running sum) */
-FPT_D double fpt_p3_observed_score(const double *X, int asize, int bsize) {
-    const int lane = threadIdx.x & 31;
-    const int nbet = asize * bsize;
-    double bet = 0.0;
-    for (int t0 = 0; t0 < nbet; t0 += 32) {                           /* term t: i = asize-1 - t / bsize, j = bsize-1 - t % bsize */
-        const int t = t0 + lane;
-        double term = 0.0;
-        if (t < nbet) {
-            const int a = asize - 1 - t / bsize, b = asize + (bsize - 1 - t % bsize);
-            const double dx = __dsub_rn(X[2 * a], X[2 * b]), dy = __dsub_rn(X[2 * a + 1], X[2 * b + 1]);
-            term = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-        }
-        const int cnt = min(32, nbet - t0);
-        for (int l = 0; l < cnt; l++) bet = __dadd_rn(bet, __shfl_sync(FPT_FULL_MASK, term, l));
-    }
-    bet = __ddiv_rn(bet, (double)((long long)asize * bsize));
-    double w2[2] = { 0.0, 0.0 };
-    for (int grp = 0; grp < 2; grp++) {
-        const int n = grp ? bsize : asize, base = grp ? asize : 0;
-        if (n <= 1) continue;
-        double acc = 0.0;
-        for (int t0 = 0; t0 < n - 1; t0 += 32) {                      /* term t: i = n-2 - t, pair (base+i, base+i+1) */
-            const int t = t0 + lane;
-            double term = 0.0;
-            if (t < n - 1) {
-                const int a = base + (n - 2 - t), b = a + 1;
-                const double dx = __dsub_rn(X[2 * a], X[2 * b]), dy = __dsub_rn(X[2 * a + 1], X[2 * b + 1]);
-                term = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-            }
-            const int cnt = min(32, n - 1 - t0);
-            for (int l = 0; l < cnt; l++) acc = __dadd_rn(acc, __shfl_sync(FPT_FULL_MASK, term, l));
-        }
-        w2[grp] = __ddiv_rn(acc, (double)((long long)n * n * (n - 1)));
-    }
-    return __dsub_rn(bet, __dmul_rn((double)(asize + bsize), __dadd_rn(w2[0], w2[1])));
-}
-
-/* both permutations of a thread, one Fisher-Yates step each (position i is final afterwards). MEMBER: position i belongs to the
-   smaller group, so the label landing there joins the membership mask; PAIR: the adjacent pair (i, i + 1) counts, its quantised
-   distance is added to the running within-group sum. */
-struct FptP3Pair {
-    uint32_t h0, l0, h1, l1;            /* split LCG states */
-    uint32_t over0, over1;              /* bit 31 set once a draw exceeded its limit */
-    uint32_t mlo0, mhi0, mlo1, mhi1;    /* membership masks (individuals 0..31, 32..63) */
-    int acc0, acc1, prev0, prev1;
+template <bool WIDE>
+struct FptP3State {
+    uint32_t h[FPT_P3_PP], l[FPT_P3_PP];             /* split LCG states */
+    typename FptP3Mask<WIDE>::type mask[FPT_P3_PP];  /* membership of the smaller group, bit = individual */
+    int acc[FPT_P3_PP];                              /* running adjacent-pair sum of quantised distances */
+    uint32_t prev[FPT_P3_PP];                        /* label at the position above */
+    uint32_t maxr;                                   /* largest draw so far (rejection test) */
 };
 
-template <bool MEMBER, bool PAIR>
-FPT_D void fpt_p3_step(FptP3Pair &p, int i, const uint2 lm, unsigned char *pos0, unsigned char *pos1, unsigned char *row0,
-                       unsigned char *row1, const unsigned *q, int m) {
-    const uint32_t n = (uint32_t)(i + 1);
-    const uint32_t r0 = fpt_p3_lcg(p.h0, p.l0), r1 = fpt_p3_lcg(p.h1, p.l1);
-    p.over0 |= lm.x - r0; p.over1 |= lm.x - r1;
-    uint32_t rem0 = r0 - __umulhi(r0, lm.y) * n, rem1 = r1 - __umulhi(r1, lm.y) * n;
-    rem0 = min(rem0, rem0 - n); rem1 = min(rem1, rem1 - n);          /* unsigned: rem - n wraps unless rem >= n */
-    unsigned char *pr0 = row0 + rem0 * FPT_P3_LINE, *pr1 = row1 + rem1 * FPT_P3_LINE;
-    const int a0 = *pos0, c0 = *pr0, a1 = *pos1, c1 = *pr1;
-    *pos0 = (unsigned char)c0; *pr0 = (unsigned char)a0;
-    *pos1 = (unsigned char)c1; *pr1 = (unsigned char)a1;
-    if (MEMBER) {
-        const uint32_t b0 = 1u << (c0 & 31), b1 = 1u << (c1 & 31);
-        if (c0 & 32) p.mhi0 |= b0; else p.mlo0 |= b0;
-        if (c1 & 32) p.mhi1 |= b1; else p.mlo1 |= b1;
+/* one Fisher-Yates step of all four permutations: position i (n = i + 1) becomes final. `word_i` = my label word at position i,
+   `col0` = my word at position 0. MEMBER: position i belongs to the smaller group, so the label landing there joins the
+   membership mask; PAIR: the adjacent pair (i, i + 1) counts, its quantised distance is added to the running sum. */
+template <bool MEMBER, bool PAIR, bool WIDE>
+FPT_D void fpt_p3_step(FptP3State<WIDE> &p, uint32_t n, const uint2 mg, const unsigned char *word_i, unsigned char *col0,
+                       const unsigned *q, int m) {
+    const uint32_t aw = *reinterpret_cast<const uint32_t *>(word_i);
+#pragma unroll
+    for (int k = 0; k < FPT_P3_PP; k++) {
+        const uint32_t r = fpt_p3_lcg(p.h[k], p.l[k]);
+        p.maxr = max(p.maxr, r);
+        const uint32_t rem = r - (__umulhi(r, mg.x) >> mg.y) * n;
+        unsigned char *pr = col0 + rem * FPT_P3_LINE + k;
+        const uint32_t a = (aw >> (8 * k)) & 0xffu;
+        const uint32_t c = *pr;                                      /* rem == i: reads a itself and stores it back */
+        *pr = (unsigned char)a;
+        if (MEMBER) p.mask[k] |= (typename FptP3Mask<WIDE>::type)1 << c;
+        if (PAIR) p.acc[k] += (int)q[c * m + p.prev[k]];
+        p.prev[k] = c;
     }
-    if (PAIR) { p.acc0 += (int)q[c0 * m + p.prev0]; p.acc1 += (int)q[c1 * m + p.prev1]; }
-    p.prev0 = c0; p.prev1 = c1;
 }
 
-/* positions [hi, lo] (descending) of both permutations */
-template <bool MEMBER, bool PAIR>
-FPT_D void fpt_p3_run(FptP3Pair &p, int hi, int lo, const uint2 *rtab, unsigned char *row0, unsigned char *row1, const unsigned *q, int m) {
-    unsigned char *pos0 = row0 + (unsigned)hi * FPT_P3_LINE, *pos1 = row1 + (unsigned)hi * FPT_P3_LINE;
+/* positions [hi, lo] (descending) */
+template <bool MEMBER, bool PAIR, bool WIDE>
+FPT_D void fpt_p3_run(FptP3State<WIDE> &p, int hi, int lo, const uint2 *rtab, unsigned char *col0, const unsigned *q, int m) {
+    const unsigned char *w = col0 + (unsigned)hi * FPT_P3_LINE;
+#pragma unroll 2
     for (int i = hi; i >= lo; i--) {
-        fpt_p3_step<MEMBER, PAIR>(p, i, rtab[i + 1], pos0, pos1, row0, row1, q, m);
-        pos0 -= FPT_P3_LINE; pos1 -= FPT_P3_LINE;
+        fpt_p3_step<MEMBER, PAIR, WIDE>(p, (uint32_t)(i + 1), rtab[i + 1], w, col0, q, m);
+        w -= FPT_P3_LINE;
     }
 }
 
-/* identity labels for both sets, written cooperatively: the word of (position, column) holds the four threads of that column,
-   and all four hold `position` there; the caller's next barrier publishes them */
-FPT_D void fpt_p3_identity(unsigned char *labels, int m) {
-    unsigned *lw = reinterpret_cast<unsigned *>(labels);
-    for (int e = threadIdx.x; e < 2 * m * (FPT_P3_LINE / 4); e += blockDim.x) {
-        int pos = e >> 6;
-        if (pos >= m) pos -= m;
-        lw[e] = (unsigned)pos * 0x01010101u;
+/* one permutation regenerated on its own, on the exact path (rejections honoured), with every store: byte column `col`
+   (position idx at col + idx * FPT_P3_LINE) holds the final labels afterwards */
+FPT_D void fpt_p3_regen(unsigned char *col, int m, uint64_t st) {
+    for (int e = 0; e < m; e++) col[(unsigned)e * FPT_P3_LINE] = (unsigned char)e;
+    int used = 0;
+    for (int i = m - 1; i > 0; i--) {
+        const int rr = (int)fpt_randint((uint32_t)(i + 1), st, used);
+        unsigned char *pi = col + (unsigned)i * FPT_P3_LINE, *pr = col + (unsigned)rr * FPT_P3_LINE;
+        const unsigned char t = *pi; *pi = *pr; *pr = t;
     }
 }
 
-__global__ void __launch_bounds__(FPT_P3_T, 3)
+/* reference-order sums (css.c:608-647) over the labels in byte column `col` by a whole warp: the lanes compute the next 32
+   distances (calc_dist, css.c:573-587, from the embedding: the same expression, hence the same bits) while lane 0 adds the
+   previous 32 in order. kind 0: between-group pairs, 1 / 2: adjacent pairs of the first / second group. Lane 0 holds the sum. */
+FPT_D double fpt_p3_chain(const double *X, double *stage, int kind, int asize, int bsize, int lane, const unsigned char *col) {
+    const int total = kind == 0 ? asize * bsize : (kind == 1 ? asize - 1 : bsize - 1);
+    double acc = 0.0;
+    auto dist_of = [&](int e) -> double {
+        int i, j;
+        if (kind == 0) { const int r = e / bsize; i = asize - 1 - r; j = asize + bsize - 1 - (e - r * bsize); }
+        else if (kind == 1) { i = asize - 2 - e; j = i + 1; }
+        else { i = asize + bsize - 2 - e; j = i + 1; }
+        i = col[(unsigned)i * FPT_P3_LINE]; j = col[(unsigned)j * FPT_P3_LINE];
+        const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
+        return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    };
+    double dcur = lane < total ? dist_of(lane) : 0.0;
+    for (int base = 0; base < total; base += 32) {
+        stage[lane] = dcur;
+        __syncwarp();
+        const int nxt = base + 32 + lane;
+        const double dnext = nxt < total ? dist_of(nxt) : 0.0;
+        if (lane == 0) {
+            const int cnt = total - base < 32 ? total - base : 32;
+            if (cnt == 32) {
+#pragma unroll
+                for (int t = 0; t < 32; t++) acc = __dadd_rn(acc, stage[t]);
+            } else {
+                for (int t = 0; t < cnt; t++) acc = __dadd_rn(acc, stage[t]);
+            }
+        }
+        __syncwarp();
+        dcur = dnext;
+    }
+    return acc;
+}
+
+/* css() of css.c:608-647 for the labels in byte column `col`, by the whole warp; every lane returns the score */
+FPT_D double fpt_p3_warp_exact_score(const double *X, double *stage, const unsigned char *col, int asize, int bsize, int lane) {
+    double bet = fpt_p3_chain(X, stage, 0, asize, bsize, lane, col);
+    const double wa0 = asize > 1 ? fpt_p3_chain(X, stage, 1, asize, bsize, lane, col) : 0.0;
+    const double wb0 = bsize > 1 ? fpt_p3_chain(X, stage, 2, asize, bsize, lane, col) : 0.0;
+    bet = __ddiv_rn(bet, (double)((long long)asize * bsize));
+    const double wa = asize > 1 ? __ddiv_rn(wa0, (double)((long long)asize * asize * (asize - 1))) : 0.0;
+    const double wb = bsize > 1 ? __ddiv_rn(wb0, (double)((long long)bsize * bsize * (bsize - 1))) : 0.0;
+    return __shfl_sync(FPT_FULL_MASK, __dsub_rn(bet, __dmul_rn((double)(asize + bsize), __dadd_rn(wa, wb))), 0);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------------
+ * Between-group sums of the warp's 32 permutations (one per lane) on the u8 tensor cores.
+ *
+ * R = Z Q_d per base-256 digit d, Z (32 x K) the 0/1 membership rows of the smaller group, then sum_j (1 - z_j) R_j.
+ * mma.sync.m16n8k32 (g = lane / 4, t = lane % 4): A regs a0/a2 = row g, k-slots 4t..4t+3 / 16+4t..; a1/a3 = row g + 8;
+ * B regs b0/b1 = the same k-slots of column g; C c0,c1 = row g, columns 2t, 2t+1; c2,c3 = row g + 8.
+ * The hardware only requires that A and B agree on which individual sits in which k-slot, so slot (k-step s, register half h,
+ * byte b) of lane t is individual 8 KS t + 8 s + 4 h + b: the 8 KS bytes a lane needs from a membership row — and from a digit
+ * row — are contiguous: one 128-bit load (KS = 2) or one 64-bit load (KS = 1) each.
+ * Membership rows: 32 KS bytes per lane, 16-byte chunks XOR-swizzled so that both the row-wise stores and the fragment loads are
+ * bank-conflict-free. `nm` = this lane's NOT-membership mask (bit j set: individual j outside the smaller group).
+ */
+template <int KS> FPT_D unsigned fpt_p3_chunk_slot(int row, int chunk) { return KS == 2 ? (unsigned)(chunk ^ ((row >> 1) & 3)) : (unsigned)(chunk ^ ((row >> 2) & 1)); }
+
+/* my membership row (lane = row) from the bit mask; chunks beyond the cohort stay zero from the kernel prologue */
+template <int KS>
+FPT_D void fpt_p3_write_row(unsigned char *indw, int lane, unsigned long long mask, int nchunks) {
+    unsigned char *row = indw + (size_t)lane * (32 * KS);
+#pragma unroll
+    for (int c = 0; c < 2 * KS; c++) {
+        if (c < nchunks) {
+            const uint32_t src = (uint32_t)(mask >> (16 * c)) & 0xffffu;
+            uint4 v;
+            v.x = ((src & 0xfu) * 0x00204081u) & 0x01010101u;
+            v.y = (((src >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
+            v.z = (((src >> 8) & 0xfu) * 0x00204081u) & 0x01010101u;
+            v.w = ((src >> 12) * 0x00204081u) & 0x01010101u;
+            *reinterpret_cast<uint4 *>(row + 16 * fpt_p3_chunk_slot<KS>(lane, c)) = v;
+        }
+    }
+}
+
+template <int KS>
+FPT_D long long fpt_p3_bet_mma(const unsigned char *indw, const unsigned char *qd, int ntiles, int qd_rows,
+                               typename FptP3Mask<KS == 2>::type nm) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    constexpr int KB = 32 * KS;
+    /* A fragments: rows g, g + 8 (tile 0) and g + 16, g + 24 (tile 1) */
+    unsigned a[2][KS][4];
+#pragma unroll
+    for (int tile = 0; tile < 2; tile++) {
+        const int r0 = 16 * tile + g, r1 = r0 + 8;
+        if (KS == 2) {
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(indw + (size_t)r0 * KB + 16 * fpt_p3_chunk_slot<KS>(r0, t));
+            const uint4 v1 = *reinterpret_cast<const uint4 *>(indw + (size_t)r1 * KB + 16 * fpt_p3_chunk_slot<KS>(r1, t));
+            a[tile][0][0] = v0.x; a[tile][0][1] = v1.x; a[tile][0][2] = v0.y; a[tile][0][3] = v1.y;
+            a[tile][KS - 1][0] = v0.z; a[tile][KS - 1][1] = v1.z; a[tile][KS - 1][2] = v0.w; a[tile][KS - 1][3] = v1.w;
+        } else {
+            const uint2 v0 = *reinterpret_cast<const uint2 *>(indw + (size_t)r0 * KB + 16 * fpt_p3_chunk_slot<KS>(r0, t >> 1) + 8 * (t & 1));
+            const uint2 v1 = *reinterpret_cast<const uint2 *>(indw + (size_t)r1 * KB + 16 * fpt_p3_chunk_slot<KS>(r1, t >> 1) + 8 * (t & 1));
+            a[tile][0][0] = v0.x; a[tile][0][1] = v1.x; a[tile][0][2] = v0.y; a[tile][0][3] = v1.y;
+        }
+    }
+    /* column masks of my four rows (permutations g + 8 s), shifted so that bit 8 nt (+1) is column 8 nt + 2 t (+1) */
+    typename FptP3Mask<KS == 2>::type nmr[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) nmr[s] = __shfl_sync(FPT_FULL_MASK, nm, g + 8 * s) >> (2 * t);
+    int sum[4] = { 0, 0, 0, 0 };                        /* every partial sum is a part of sum_{G x not G} q < 2^31 */
+    const unsigned char *colbase = qd + (size_t)g * KB + 8 * KS * t;
+    const size_t dstride = (size_t)qd_rows * KB;
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+        if (nt < ntiles) {
+            int c[3][2][4];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const unsigned char *src = colbase + (size_t)d * dstride + (size_t)(8 * nt) * KB;
+                unsigned b[2 * KS];
+                if (KS == 2) { const uint4 v = *reinterpret_cast<const uint4 *>(src); b[0] = v.x; b[1] = v.y; b[2 * KS - 2] = v.z; b[2 * KS - 1] = v.w; }
+                else { const uint2 v = *reinterpret_cast<const uint2 *>(src); b[0] = v.x; b[1] = v.y; }
+#pragma unroll
+                for (int tile = 0; tile < 2; tile++) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) c[d][tile][e] = 0;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++) fpt_mma_u8(c[d][tile], a[tile][ks], b[2 * ks], b[2 * ks + 1]);
+                }
+            }
+            /* the three digits of R, then the columns outside the group */
+#pragma unroll
+            for (int tile = 0; tile < 2; tile++) {
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int s = 2 * tile + (e >> 1);
+                    const int v = (c[2][tile][e] * 256 + c[1][tile][e]) * 256 + c[0][tile][e];   /* < min(a, b) * 2^(qbits + 1) < 2^31 */
+                    if ((nmr[s] >> (8 * nt + (e & 1))) & 1) sum[s] += v;
+                }
+            }
+        }
+    }
+    /* reduce over the four lanes of a quad so that lane t keeps row s = t (reduce-scatter), then hand every lane its own row */
+    const bool b0 = (t & 1) != 0, b1 = (t & 2) != 0;
+    const int u0 = (b0 ? sum[1] : sum[0]) + __shfl_xor_sync(FPT_FULL_MASK, b0 ? sum[0] : sum[1], 1);
+    const int u1 = (b0 ? sum[3] : sum[2]) + __shfl_xor_sync(FPT_FULL_MASK, b0 ? sum[2] : sum[3], 1);
+    const int mine = (b1 ? u1 : u0) + __shfl_xor_sync(FPT_FULL_MASK, b1 ? u0 : u1, 2);
+    return (long long)__shfl_sync(FPT_FULL_MASK, mine, 4 * (lane & 7) + (lane >> 3));
+}
+
+template <int KS>
+__global__ void __launch_bounds__(FPT_P3_T, 4)
 fpt_css_perm3_kernel(const double *__restrict__ Xall, int m, int asize, int bsize, long long wbase, long long nwin,
                      const unsigned char *__restrict__ status, int treshold, int runs, uint64_t seed,
-                     const uint64_t *__restrict__ state_override, int qbits, double *__restrict__ out_score,
+                     const uint64_t *__restrict__ state_override, int qbits, const double *__restrict__ obs_score,
                      double *__restrict__ out_p, int *__restrict__ out_hits, int *__restrict__ out_n,
                      unsigned long long *__restrict__ recheck_counter) {
     FPT_DYN_SMEM(smem);
+    constexpr bool WIDE = KS == 2;
+    constexpr int KB = 32 * KS;
+    typedef typename FptP3Mask<WIDE>::type mask_t;
     const int T = FPT_P3_T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ndigits = (qbits + 8) >> 3;
-    const int qd_rows = ((m + 7) >> 3) << 3;
+    const int qd_rows = ((m + 7) >> 3) << 3, ntiles = qd_rows >> 3, nchunks = (m + 15) >> 4;
     size_t off = 0;
     double *X = (double *)(smem + off); off += (size_t)2 * m * 8;
     unsigned *q = (unsigned *)(smem + off); off += (size_t)m * m * 4;
-    unsigned char *qd = smem + off; off += (size_t)3 * qd_rows * FPT_QD_STRIDE;
-    off = (off + 15) & ~(size_t)15;
-    unsigned char *labels = smem + off; off += (size_t)2 * m * FPT_P3_LINE;
-    unsigned char *ind = smem + off; off += (size_t)T * FPT_IND_STRIDE;
     uint2 *rtab = (uint2 *)(smem + off); off += (size_t)(m + 1) * 8;
     off = (off + 15) & ~(size_t)15;
-    ulonglong2 *skipmap = (ulonglong2 *)(smem + off); off += (size_t)(T + 2) * 16;
-    double *red = (double *)(smem + off); off += 40 * 8;
-    int *scan = (int *)(smem + off);
-    unsigned char *myind = ind + (size_t)tid * FPT_IND_STRIDE, *warpind = ind + (size_t)(tid & ~31) * FPT_IND_STRIDE;
-    __shared__ double s_score;
-    __shared__ int s_flag;
+    unsigned char *qd = smem + off; off += (size_t)3 * qd_rows * KB;
+    unsigned char *labels = smem + off; off += (size_t)m * FPT_P3_LINE;
+    unsigned char *indw = smem + off + (size_t)warp * 32 * KB; off += (size_t)FPT_P3_WARPS * 32 * KB;
+    int *whits = (int *)(smem + off); off += 2 * 2 * FPT_P3_WARPS * 4;         /* [parity][0: round hits, 1: pending hits][warp] */
+    int *s_flag = (int *)(smem + off);
+    double *stage = reinterpret_cast<double *>(indw);                          /* exact re-scoring: the warp's rows are idle then */
+    unsigned char *col0 = labels + 4 * tid;                                    /* my label word at position 0 */
     const int use_a = asize <= bsize;
     const int draws = m - 1;
-    unsigned char *row0 = labels + ((tid & 63) << 2) + (tid >> 6);  /* my two label rows (position 0): sets 0 and 1 */
-    unsigned char *row1 = row0 + (size_t)m * FPT_P3_LINE;
     unsigned long long rechecks = 0;
+    /* affine maps x -> a x + b (mod 2^48) of the stream: to my first permutation of a round, over one permutation, over a round */
+    uint64_t map_t_a, map_t_b, map_1_a, map_1_b, map_r_a, map_r_b;
     {
-        /* affine maps x -> a x + b (mod 2^48) of the stream: [tid] to thread tid's first permutation of a round, [T] over a whole
-           round, [T + 1] over one permutation */
-        const uint64_t n_t = (uint64_t)tid * 2 * (uint64_t)draws;
-        const uint64_t b_t = fpt_lcg_skip(0ULL, n_t);
-        skipmap[tid] = make_ulonglong2((fpt_lcg_skip(1ULL, n_t) - b_t) & FPT_MASK48, b_t);
-        if (tid < 2) {
-            const uint64_t n_c = tid == 0 ? (uint64_t)FPT_P3_ROUND * (uint64_t)draws : (uint64_t)draws;
-            const uint64_t b_c = fpt_lcg_skip(0ULL, n_c);
-            skipmap[T + tid] = make_ulonglong2((fpt_lcg_skip(1ULL, n_c) - b_c) & FPT_MASK48, b_c);
-        }
+        const uint64_t n_t = (uint64_t)tid * FPT_P3_PP * (uint64_t)draws;
+        map_t_b = fpt_lcg_skip(0ULL, n_t); map_t_a = (fpt_lcg_skip(1ULL, n_t) - map_t_b) & FPT_MASK48;
+        map_1_b = fpt_lcg_skip(0ULL, (uint64_t)draws); map_1_a = (fpt_lcg_skip(1ULL, (uint64_t)draws) - map_1_b) & FPT_MASK48;
+        const uint64_t n_r = (uint64_t)FPT_P3_ROUND * (uint64_t)draws;
+        map_r_b = fpt_lcg_skip(0ULL, n_r); map_r_a = (fpt_lcg_skip(1ULL, n_r) - map_r_b) & FPT_MASK48;
     }
-    for (int n = tid; n <= m; n += T) {
-        uint2 lm;
-        lm.x = n > 0 ? fpt_randint_limit((uint32_t)n) : 0u; lm.y = n > 0 ? fpt_randint_magic((uint32_t)n) : 0u;
-        rtab[n] = lm;
-    }
+    for (int n = tid; n <= m; n += T) rtab[n] = fpt_p3_magic((uint32_t)n);
+    for (int e = lane; e < 32 * KB / 16; e += 32) reinterpret_cast<uint4 *>(indw)[e] = make_uint4(0u, 0u, 0u, 0u);
+    int parity = 0;
     __syncthreads();
 
     for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
         if (status[w] != FPT_WIN_SCORED) continue;
         for (int e = tid; e < 2 * m; e += T) X[e] = Xall[(size_t)w * 2 * m + e];
+        const double score = obs_score[w];
         __syncthreads();
         /* surrogate scale from the bounding box of the embedding: dmax >= every distance, known before the distances are */
         double dmax;
@@ -255,28 +346,24 @@ fpt_css_perm3_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
         }
         const bool scale_ok = (dmax > 0.0) && (dmax < 1e300);
         const double S = scale_ok ? (double)(1u << qbits) / dmax : 0.0;
-        if (warp == 0) {
-            /* the observed score in the reference's order, while the other warps quantise */
-            const double sc = fpt_p3_observed_score(X, asize, bsize);
-            if (lane == 0) s_score = sc;
-        } else {
-            /* quantised distances q = rint(d S) <= 2^qbits (|q/S - d| <= 0.5/S), symmetric, zero diagonal */
-            for (int e = tid - 32; e < m * m; e += T - 32) {
-                const int i = e / m, j = e - i * m;
+        /* quantised distances q = rint(d S) <= 2^qbits (|q/S - d| <= 0.5/S), symmetric, zero diagonal */
+        for (int i = warp; i < m; i += FPT_P3_WARPS) {
+            const double xi = X[2 * i], yi = X[2 * i + 1];
+            for (int j = lane; j <= i; j += 32) {
+                unsigned qv = 0u;
                 if (j < i) {
-                    const double dx = __dsub_rn(X[2 * i], X[2 * j]), dy = __dsub_rn(X[2 * i + 1], X[2 * j + 1]);
+                    const double dx = __dsub_rn(xi, X[2 * j]), dy = __dsub_rn(yi, X[2 * j + 1]);
                     const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-                    const unsigned qv = (scale_ok && d == d) ? (unsigned)__double2ll_rn(d * S) : 0u;
-                    q[e] = qv; q[j * m + i] = qv;
-                } else if (j == i) q[e] = 0u;
+                    qv = (scale_ok && d == d) ? (unsigned)__double2ll_rn(d * S) : 0u;
+                }
+                q[i * m + j] = qv; q[j * m + i] = qv;
             }
         }
         __syncthreads();
-        const double score = s_score;
         const bool use_surrogate = scale_ok && (score == score) && (fabs(score) < 1e300);
-        /* base-256 digits of q, zero padded to 8-row / 64-column tiles */
-        for (int e = tid; e < ndigits * qd_rows * 16; e += T) {
-            const int d = e / (qd_rows * 16), rem = e - d * qd_rows * 16, n = rem >> 4, k4 = (rem & 15) << 2;
+        /* base-256 digits of q: row n = individual n, byte k = individual k, zero padded to 8-row tiles and KB columns */
+        for (int e = tid; e < 3 * qd_rows * (KB / 4); e += T) {
+            const int d = e / (qd_rows * (KB / 4)), rem = e - d * qd_rows * (KB / 4), n = rem / (KB / 4), k4 = (rem - n * (KB / 4)) << 2;
             unsigned wv = 0;
             if (n < m) {
 #pragma unroll
@@ -286,7 +373,7 @@ fpt_css_perm3_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
                     wv |= v << (8 * b);
                 }
             }
-            *reinterpret_cast<unsigned *>(qd + ((size_t)d * qd_rows + n) * FPT_QD_STRIDE + k4) = wv;
+            *reinterpret_cast<unsigned *>(qd + ((size_t)d * qd_rows + n) * KB + k4) = wv;
         }
         /* |surrogate - reference score| <= E: quantisation (0.5/S)(1 + (a+b)(1/a^2 + 1/b^2)) on the three means plus a generous
            bound on the fp64 rounding of both evaluations (same bound as fpt_css_perm2_kernel) */
@@ -299,158 +386,174 @@ fpt_css_perm3_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
         const double c_wb = bsize > 1 ? invS / (b_ * b_ * (b_ - 1.0)) : 0.0;
         const uint64_t st_win = state_override ? state_override[w] : fpt_stream_state(seed, wbase + w, FPT_STREAM_RESAMPLE);
         uint64_t st_round = st_win;                         /* window state advanced by the finished rounds */
-        int hits = 0, ndone = 0;
+        int hits = 0, ndone = 0, pending = 0;               /* pending: my hits of rounds that ended without a barrier */
         bool stopped = false;
-        fpt_p3_identity(labels, m);
         __syncthreads();
         while (!stopped && hits < treshold && ndone < runs) {
             const int nvalid = min(FPT_P3_ROUND, runs - ndone);
-            const int first = 2 * tid;                      /* my permutations of this round: first, first + 1 */
-            const int mycount = max(0, min(2, nvalid - first));
-            const bool warp_active = (tid & ~31) * 2 < nvalid;
-            int hit0 = 0, hit1 = 0;
+            const int first = FPT_P3_PP * tid;              /* my permutations of this round: first .. first + 3 */
+            const int mycount = max(0, min(FPT_P3_PP, nvalid - first));
+            const bool warp_active = (tid & ~31) * FPT_P3_PP < nvalid;
+            unsigned hitmask = 0u;
             if (warp_active) {
-                /* ---- both shuffles at once */
-                uint32_t h0, l0, h1, l1;
+                /* ---- identity labels (my own words), then the four shuffles at once */
+                for (int e = 0; e < m; e++) *reinterpret_cast<uint32_t *>(col0 + (unsigned)e * FPT_P3_LINE) = (uint32_t)e * 0x01010101u;
+                FptP3State<WIDE> pp;
                 {
-                    const ulonglong2 sk = skipmap[tid], s1 = skipmap[T + 1];
-                    const uint64_t a = (sk.x * st_round + sk.y) & FPT_MASK48, b = (s1.x * a + s1.y) & FPT_MASK48;
-                    h0 = (uint32_t)(a >> 16); l0 = (uint32_t)a & 0xffffu; h1 = (uint32_t)(b >> 16); l1 = (uint32_t)b & 0xffffu;
+                    uint64_t s = (map_t_a * st_round + map_t_b) & FPT_MASK48;
+#pragma unroll
+                    for (int k = 0; k < FPT_P3_PP; k++) {
+                        pp.h[k] = (uint32_t)(s >> 16); pp.l[k] = (uint32_t)s & 0xffffu;
+                        pp.mask[k] = 0; pp.acc[k] = 0; pp.prev[k] = 0u;
+                        s = (map_1_a * s + map_1_b) & FPT_MASK48;
+                    }
+                    pp.maxr = 0u;
                 }
                 /* Fisher-Yates fixes position i at step i (i = m-1 .. 1), so everything the score needs is read off the swap as it
-                   happens: the label that lands at i joins the membership mask of its group (m <= 64: two words per permutation)
-                   and closes the adjacent pair (i, i+1), whose quantised distance goes to the within-B sum while i >= asize and
-                   to the within-A sum below asize - 1 (the pair across the group boundary counts for neither, css.c:627-643).
-                   The position ranges are split so that each loop has a fixed body. */
-                FptP3Pair pp;
-                pp.h0 = h0; pp.l0 = l0; pp.h1 = h1; pp.l1 = l1;
-                pp.over0 = pp.over1 = 0u; pp.mlo0 = pp.mhi0 = pp.mlo1 = pp.mhi1 = 0u;
-                pp.acc0 = pp.acc1 = 0; pp.prev0 = pp.prev1 = 0;
-                int wb0 = 0, wb1 = 0;
-                /* group B positions m-1 .. asize (the first one closes no pair) */
+                   happens: the label that lands at i joins the membership mask of its group and closes the adjacent pair
+                   (i, i+1), whose quantised distance goes to the within-B sum while i >= asize and to the within-A sum below
+                   asize - 1 (the pair across the group boundary counts for neither, css.c:627-643). The position ranges are
+                   split so that each loop has a fixed body. */
+                int wa[FPT_P3_PP], wb[FPT_P3_PP];
                 if (use_a) {
-                    if (m - 1 >= asize && m - 1 >= 1) fpt_p3_run<false, false>(pp, m - 1, m - 1, rtab, row0, row1, q, m);
-                    fpt_p3_run<false, true>(pp, m - 2, max(asize, 1), rtab, row0, row1, q, m);
+                    if (m - 1 >= asize && m - 1 >= 1) fpt_p3_run<false, false, WIDE>(pp, m - 1, m - 1, rtab, col0, q, m);
+                    fpt_p3_run<false, true, WIDE>(pp, m - 2, max(asize, 1), rtab, col0, q, m);
                 } else {
-                    if (m - 1 >= asize && m - 1 >= 1) fpt_p3_run<true, false>(pp, m - 1, m - 1, rtab, row0, row1, q, m);
-                    fpt_p3_run<true, true>(pp, m - 2, max(asize, 1), rtab, row0, row1, q, m);
+                    if (m - 1 >= asize && m - 1 >= 1) fpt_p3_run<true, false, WIDE>(pp, m - 1, m - 1, rtab, col0, q, m);
+                    fpt_p3_run<true, true, WIDE>(pp, m - 2, max(asize, 1), rtab, col0, q, m);
                 }
-                wb0 = pp.acc0; wb1 = pp.acc1; pp.acc0 = 0; pp.acc1 = 0;
+#pragma unroll
+                for (int k = 0; k < FPT_P3_PP; k++) { wb[k] = pp.acc[k]; pp.acc[k] = 0; }
                 /* position asize-1: first of group A from the top, its pair with position asize crosses the boundary */
                 if (asize - 1 >= 1) {
-                    if (use_a) fpt_p3_run<true, false>(pp, asize - 1, asize - 1, rtab, row0, row1, q, m);
-                    else fpt_p3_run<false, false>(pp, asize - 1, asize - 1, rtab, row0, row1, q, m);
-                    if (use_a) fpt_p3_run<true, true>(pp, asize - 2, 1, rtab, row0, row1, q, m);
-                    else fpt_p3_run<false, true>(pp, asize - 2, 1, rtab, row0, row1, q, m);
+                    if (use_a) {
+                        fpt_p3_run<true, false, WIDE>(pp, asize - 1, asize - 1, rtab, col0, q, m);
+                        fpt_p3_run<true, true, WIDE>(pp, asize - 2, 1, rtab, col0, q, m);
+                    } else {
+                        fpt_p3_run<false, false, WIDE>(pp, asize - 1, asize - 1, rtab, col0, q, m);
+                        fpt_p3_run<false, true, WIDE>(pp, asize - 2, 1, rtab, col0, q, m);
+                    }
                 }
                 {   /* position 0 keeps what is left there */
-                    const int c0 = *row0, c1 = *row1;
-                    if (use_a) {
-                        const uint32_t b0 = 1u << (c0 & 31), b1 = 1u << (c1 & 31);
-                        if (c0 & 32) pp.mhi0 |= b0; else pp.mlo0 |= b0;
-                        if (c1 & 32) pp.mhi1 |= b1; else pp.mlo1 |= b1;
+                    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(col0);
+#pragma unroll
+                    for (int k = 0; k < FPT_P3_PP; k++) {
+                        const uint32_t c = (w0 >> (8 * k)) & 0xffu;
+                        if (use_a) pp.mask[k] |= (mask_t)1 << c;
+                        if (asize >= 2) pp.acc[k] += (int)q[c * m + pp.prev[k]];
+                        wa[k] = pp.acc[k];
                     }
-                    if (asize >= 2) { pp.acc0 += (int)q[c0 * m + pp.prev0]; pp.acc1 += (int)q[c1 * m + pp.prev1]; }
                 }
-                const uint32_t over0 = pp.over0, over1 = pp.over1;
-                uint32_t mlo0 = pp.mlo0, mhi0 = pp.mhi0, mlo1 = pp.mlo1, mhi1 = pp.mhi1;
-                const int acc0 = pp.acc0, acc1 = pp.acc1;
-                int wa0 = acc0, wa1 = acc1;
-                /* a rejected draw (probability < n / 2^31 each): replay that permutation on the exact path and walk its labels */
-                if ((over0 | over1) >> 31) {
-                    for (int k = 0; k < 2; k++) {
-                        if (!(((k ? over1 : over0) >> 31) & 1u)) continue;
-                        uint64_t st = fpt_lcg_skip(st_win, (uint64_t)(ndone + first + k) * (uint64_t)draws);
-                        int used = 0;
-                        unsigned char *row = k ? row1 : row0;
-                        for (int e = 0; e < m; e++) *fpt_p3_label(row, e) = (unsigned char)e;
-                        for (int i = m - 1; i > 0; i--) {
-                            const uint2 lm = rtab[i + 1];
-                            const int rr = (int)fpt_randint_fast((uint32_t)(i + 1), lm.x, lm.y, st, used);
-                            unsigned char *pi = fpt_p3_label(row, i), *pr = fpt_p3_label(row, rr);
-                            const unsigned char t = *pi; *pi = *pr; *pr = t;
-                        }
-                        uint32_t lo = 0u, hi = 0u;
-                        int wa = 0, wb = 0, prev = 0;
+                /* a draw above 2^31 - 64 may have been a rejected one (probability < 2^-25 per permutation): regenerate that
+                   permutation alone on the exact path and walk its labels */
+                if (pp.maxr > 2147483648u - 64u) {
+                    for (int k = 0; k < FPT_P3_PP; k++) {
+                        unsigned char *col = col0 + k;
+                        fpt_p3_regen(col, m, fpt_lcg_skip(st_win, (uint64_t)(ndone + first + k) * (uint64_t)draws));
+                        mask_t mk = 0;
+                        int a = 0, b = 0, prev = 0;
                         for (int i = 0; i < m; i++) {
-                            const int c = *fpt_p3_label(row, i);
+                            const int c = col[(unsigned)i * FPT_P3_LINE];
                             const bool in_a = i < asize;
-                            if (in_a == (use_a != 0)) { if (c & 32) hi |= 1u << (c & 31); else lo |= 1u << (c & 31); }
-                            if (i != 0 && i != asize) { const int qv = (int)q[prev * m + c]; if (in_a) wa += qv; else wb += qv; }
+                            if (in_a == (use_a != 0)) mk |= (mask_t)1 << c;
+                            if (i != 0 && i != asize) { const int qv = (int)q[prev * m + c]; if (in_a) a += qv; else b += qv; }
                             prev = c;
                         }
-                        if (k) { mlo1 = lo; mhi1 = hi; wa1 = wa; wb1 = wb; } else { mlo0 = lo; mhi0 = hi; wa0 = wa; wb0 = wb; }
+                        pp.mask[k] = mk; wa[k] = a; wb[k] = b;
                     }
                 }
-                /* ---- score both, one after the other (the tensor-core product is a warp-wide operation) */
+                /* ---- score: the tensor-core product is a warp-wide operation, one batch of 32 permutations (permutation k of
+                   every lane) after the other */
 #pragma unroll 1
-                for (int k = 0; k < 2; k++) {
+                for (int k = 0; k < FPT_P3_PP; k++) {
                     const bool valid = k < mycount;
-                    unsigned char *row = k ? row1 : row0;
                     int hit = 0;
                     bool exact = valid && !use_surrogate;
                     if (use_surrogate) {
-                        /* membership row of the smaller group (the A operand of the u8 MMA): four mask bits -> four 0/1 bytes */
-                        const uint32_t lo = valid ? (k ? mlo1 : mlo0) : 0u, hi = valid ? (k ? mhi1 : mhi0) : 0u;
-                        uint4 *row4 = reinterpret_cast<uint4 *>(myind);
-#pragma unroll
-                        for (int g = 0; g < 4; g++) {
-                            const uint32_t src = g < 2 ? lo : hi, sh = (uint32_t)(g & 1) * 16u;
-                            uint4 v;
-                            v.x = (((src >> sh) & 0xfu) * 0x00204081u) & 0x01010101u;
-                            v.y = (((src >> (sh + 4u)) & 0xfu) * 0x00204081u) & 0x01010101u;
-                            v.z = (((src >> (sh + 8u)) & 0xfu) * 0x00204081u) & 0x01010101u;
-                            v.w = (((src >> (sh + 12u)) & 0xfu) * 0x00204081u) & 0x01010101u;
-                            row4[g] = v;
-                        }
+                        const mask_t mk = pp.mask[0];
+                        fpt_p3_write_row<KS>(indw, lane, (unsigned long long)mk, nchunks);
                         __syncwarp();
-                        const long long bet = (long long)fpt_bet_mma(warpind, qd, m, ndigits);
+                        const long long bet = fpt_p3_bet_mma<KS>(indw, qd, ntiles, qd_rows, (mask_t)~mk);
                         __syncwarp();
                         if (valid) {
-                            const int wa = k ? wa1 : wa0, wb = k ? wb1 : wb0;
-                            const double approx = (double)bet * c_bet - (a_ + b_) * ((double)wa * c_wa + (double)wb * c_wb);
+                            const double approx = (double)bet * c_bet - (a_ + b_) * ((double)wa[0] * c_wa + (double)wb[0] * c_wb);
                             const double diff = approx - score;
                             hit = diff > 0.0;
                             exact = !(fabs(diff) > E);
                         }
                     }
-                    if (exact) {
-                        hit = fpt_p3_exact_score(X, row, asize, bsize) >= score ? 1 : 0;
-                        rechecks++;
+                    /* the rare permutation too close to the observed score: its labels regenerated by their lane, re-scored in the
+                       reference's order by the whole warp */
+                    unsigned ex = __ballot_sync(FPT_FULL_MASK, exact);
+                    while (ex) {
+                        const int src = 31 - __clz((int)(ex & (0u - ex)));
+                        ex &= ex - 1u;
+                        unsigned char *col = labels + 4 * ((tid & ~31) + src) + k;
+                        if (lane == src) fpt_p3_regen(col, m, fpt_lcg_skip(st_win, (uint64_t)(ndone + first + k) * (uint64_t)draws));
+                        __syncwarp();
+                        const double sc = fpt_p3_warp_exact_score(X, stage, col, asize, bsize, lane);
+                        if (lane == src) { hit = sc >= score ? 1 : 0; rechecks++; }
+                        __syncwarp();
+                        /* the stage buffer aliases the membership rows: chunks beyond the cohort must read zero again */
+                        for (int e = lane; e < 32 * 8 / 16; e += 32) reinterpret_cast<uint4 *>(indw)[e] = make_uint4(0u, 0u, 0u, 0u);
+                        __syncwarp();
                     }
-                    if (k == 0) hit0 = hit; else hit1 = hit;
+                    hitmask |= (unsigned)hit << k;
+                    /* rotate: permutation k + 1 moves to slot 0 (keeps the loop body free of dynamic register indexing) */
+#pragma unroll
+                    for (int j = 0; j + 1 < FPT_P3_PP; j++) { pp.mask[j] = pp.mask[j + 1]; wa[j] = wa[j + 1]; wb[j] = wb[j + 1]; }
                 }
             }
-            const int myhits = hit0 + hit1;
-            int round_hits = 0;
-            const int hincl = fpt_block_scan_incl(myhits, scan, &round_hits);
-            if (tid == 0) s_flag = -1;
-            __syncthreads();
-            if (myhits > 0 && hits + hincl >= treshold && hits + hincl - myhits < treshold) {
-                /* the treshold-th hit is one of mine: which permutation */
-                const int need = treshold - (hits + hincl - myhits);
-                s_flag = first + ((need == 1 && hit0) ? 0 : 1);
+            const int myhits = __popc(hitmask);
+            const bool can_stop = ndone + nvalid >= treshold;          /* hits <= permutations drawn: no stop before that */
+            const bool last = ndone + nvalid >= runs;
+            if (!can_stop && !last) {
+                pending += myhits; ndone += nvalid;
+                st_round = (map_r_a * st_round + map_r_b) & FPT_MASK48;
+                continue;
             }
+            /* hits of this round in permutation order (warp scan + per-warp totals), pending hits summed */
+            int incl = myhits, pend = pending;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(FPT_FULL_MASK, incl, o);
+                if (lane >= o) incl += y;
+            }
+            for (int o = 16; o > 0; o >>= 1) pend += __shfl_xor_sync(FPT_FULL_MASK, pend, o);
+            int *wh = whits + parity * 2 * FPT_P3_WARPS;
+            if (lane == 31) { wh[warp] = incl; wh[FPT_P3_WARPS + warp] = pend; }
+            if (tid == 0) *s_flag = -1;
             __syncthreads();
-            if (s_flag >= 0) {
-                ndone += s_flag + 1; hits = treshold; stopped = true;
+            int before = 0, round_hits = 0, pend_all = 0;
+#pragma unroll
+            for (int v = 0; v < FPT_P3_WARPS; v++) {
+                const int h = wh[v];
+                if (v < warp) before += h;
+                round_hits += h; pend_all += wh[FPT_P3_WARPS + v];
+            }
+            parity ^= 1;
+            hits += pend_all; pending = 0;
+            incl += before;
+            if (hits + round_hits >= treshold) {
+                /* the treshold-th hit falls into this round: its owner says which permutation it is */
+                if (myhits > 0 && hits + incl >= treshold && hits + incl - myhits < treshold) {
+                    int need = treshold - (hits + incl - myhits), which = 0;
+                    for (int j = 0; j < FPT_P3_PP; j++) if ((hitmask >> j) & 1u) { if (--need == 0) { which = j; break; } }
+                    *s_flag = first + which;
+                }
+                __syncthreads();
+                ndone += *s_flag + 1; hits = treshold; stopped = true;
             } else {
                 hits += round_hits; ndone += nvalid;
-                const ulonglong2 sk = skipmap[T];
-                st_round = (sk.x * st_round + sk.y) & FPT_MASK48;
-                fpt_p3_identity(labels, m);                 /* every warp is past its last use of the labels (barriers above) */
+                st_round = (map_r_a * st_round + map_r_b) & FPT_MASK48;
             }
-            __syncthreads();
         }
         if (tid == 0) {
-            out_score[w] = score;
             out_p[w] = __ddiv_rn(__dmul_rn((double)(hits + 1), 1.0), (double)(ndone + 1));
             if (out_hits) out_hits[w] = hits;
             if (out_n) out_n[w] = ndone;
         }
         __syncthreads();
     }
-    (void)red;
     if (recheck_counter && rechecks) atomicAdd(recheck_counter, rechecks);
 }
 

@@ -211,11 +211,35 @@ unsigned long long emu_css_perm3(const double *Xall, int m, int asize, int bsize
                                  const unsigned char *status, int treshold, int runs, uint64_t seed, const uint64_t *state_override,
                                  int qbits, int grid, double *out_score, double *out_p, int *out_hits, int *out_n) {
     unsigned long long rechecks = 0, *pr = &rechecks;
-    run_grid(grid, FPT_P3_T, fpt_css_perm3_smem_bytes(m), [=]() {
-        fpt_css_perm3_kernel(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override, qbits, out_score, out_p,
-                             out_hits, out_n, pr);
+    /* observed scores first, as fpt_api.cu does */
+    run_grid(grid, FPT_OBS_WARPS * 32, fpt_css_observed_smem_bytes(m), [=]() {
+        fpt_css_observed_kernel(Xall, m, asize, bsize, nwin, status, out_score);
     });
+    if (fpt_css_perm3_ksteps(m) == 2)
+        run_grid(grid, FPT_P3_T, fpt_css_perm3_smem_bytes(m), [=]() {
+            fpt_css_perm3_kernel<2>(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override, qbits, out_score, out_p,
+                                    out_hits, out_n, pr);
+        });
+    else
+        run_grid(grid, FPT_P3_T, fpt_css_perm3_smem_bytes(m), [=]() {
+            fpt_css_perm3_kernel<1>(Xall, m, asize, bsize, wbase, nwin, status, treshold, runs, seed, state_override, qbits, out_score, out_p,
+                                    out_hits, out_n, pr);
+        });
     return rechecks;
+}
+
+/* exact-quotient magic of the headline permutation kernel: returns the number of (n, r) pairs with a wrong remainder */
+long long emu_p3_magic_check(const unsigned *rs, long long nr) {
+    long long bad = 0;
+    for (unsigned n = 2; n <= 64; n++) {
+        const uint2 mg = fpt_p3_magic(n);
+        for (long long k = 0; k < nr; k++) {
+            const unsigned r = rs[k] & 0x7fffffffu;
+            const unsigned rem = r - (unsigned)((((unsigned long long)r * mg.x) >> 32) >> mg.y) * n;
+            if (rem != r % n) bad++;
+        }
+    }
+    return bad;
 }
 
 unsigned long long emu_css_perm2(const double *Xall, int m, int asize, int bsize, long long wbase, long long nwin,

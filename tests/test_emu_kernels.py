@@ -493,3 +493,17 @@ def test_large_cohort_observed_score_shuffle_and_surrogate_distance(emu, oracle)
     assert np.all(dij[:5] == 0.0)
     rel = np.abs(dij[5:] - exact[5:]) / exact[5:]
     assert rel.max() < 2.0 ** -50
+
+
+def test_perm3_exact_quotient_magic(emu):
+    """fpt_p3_magic: r mod n through one multiply-high and a shift, exact for every 31-bit draw and 2 <= n <= 64 — random
+    draws plus the edges where a rounded-up magic number would first fail (multiples of n and their neighbours near 2^31)"""
+    emu.emu_p3_magic_check.restype = C.c_longlong
+    rng = np.random.default_rng(5)
+    rs = [rng.integers(0, 2 ** 31, size=200000, dtype=np.int64)]
+    top = 2 ** 31 - 1
+    for n in range(2, 65):
+        k = top // n
+        rs.append(np.array([k * n - 1, k * n, k * n + 1, top, top - 1, (k - 1) * n - 1, (k - 1) * n, n - 1, n, 0, 1], dtype=np.int64))
+    rs = np.concatenate(rs).clip(0, top).astype(np.uint32)
+    assert emu.emu_p3_magic_check(vp(rs), ll(rs.size)) == 0
