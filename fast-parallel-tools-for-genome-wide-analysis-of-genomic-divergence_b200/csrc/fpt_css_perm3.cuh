@@ -49,7 +49,7 @@ FPT_HD size_t fpt_css_perm3_smem_bytes(int m) {
     off = (off + 15) & ~(size_t)15;
     off += (size_t)3 * qd_rows * kb;                                  /* digit matrices */
     off += (size_t)m * FPT_P3_LINE;                                   /* labels */
-    off += (size_t)FPT_P3_WARPS * 32 * kb;                            /* membership rows, one set per warp */
+    off += (size_t)FPT_P3_WARPS * 32 * 8;                             /* exact re-scoring: 32 staged distances per warp */
     off += 2 * 2 * FPT_P3_WARPS * 4 + 16;                             /* per-warp hit counts (double-buffered), stop flag */
     return off;
 }
@@ -188,56 +188,40 @@ FPT_D double fpt_p3_warp_exact_score(const double *X, double *stage, const unsig
  * mma.sync.m16n8k32 (g = lane / 4, t = lane % 4): A regs a0/a2 = row g, k-slots 4t..4t+3 / 16+4t..; a1/a3 = row g + 8;
  * B regs b0/b1 = the same k-slots of column g; C c0,c1 = row g, columns 2t, 2t+1; c2,c3 = row g + 8.
  * The hardware only requires that A and B agree on which individual sits in which k-slot, so slot (k-step s, register half h,
- * byte b) of lane t is individual 8 KS t + 8 s + 4 h + b: the 8 KS bytes a lane needs from a membership row — and from a digit
- * row — are contiguous: one 128-bit load (KS = 2) or one 64-bit load (KS = 1) each.
- * Membership rows: 32 KS bytes per lane, 16-byte chunks XOR-swizzled so that both the row-wise stores and the fragment loads are
- * bank-conflict-free. `nm` = this lane's NOT-membership mask (bit j set: individual j outside the smaller group).
+ * byte b) of lane t is individual 8 KS t + 8 s + 4 h + b: the 8 KS bytes a lane needs from a digit row are contiguous (one
+ * 128-bit load per column tile and digit at KS = 2, one 64-bit load at KS = 1), and the 8 KS membership bytes of a row are 8 KS
+ * consecutive BITS of that permutation's mask: the A fragments are expanded from the masks in registers, straight into the
+ * register quads the MMA reads — no shared-memory round trip, no fragment shuffling. (A first form staged the rows through
+ * shared memory with one 128-bit load per row: the loaded registers were in (row, row) order, the MMA wants (row, row + 8)
+ * interleaved, and the 240 register moves per call that followed were a third of the kernel's instructions.)
+ * `mk` = this lane's membership mask (bit j set: individual j belongs to the smaller group of this lane's permutation).
  */
-template <int KS> FPT_D unsigned fpt_p3_chunk_slot(int row, int chunk) { return KS == 2 ? (unsigned)(chunk ^ ((row >> 1) & 3)) : (unsigned)(chunk ^ ((row >> 2) & 1)); }
-
-/* my membership row (lane = row) from the bit mask; chunks beyond the cohort stay zero from the kernel prologue */
-template <int KS>
-FPT_D void fpt_p3_write_row(unsigned char *indw, int lane, unsigned long long mask, int nchunks) {
-    unsigned char *row = indw + (size_t)lane * (32 * KS);
-#pragma unroll
-    for (int c = 0; c < 2 * KS; c++) {
-        if (c < nchunks) {
-            const uint32_t src = (uint32_t)(mask >> (16 * c)) & 0xffffu;
-            uint4 v;
-            v.x = ((src & 0xfu) * 0x00204081u) & 0x01010101u;
-            v.y = (((src >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
-            v.z = (((src >> 8) & 0xfu) * 0x00204081u) & 0x01010101u;
-            v.w = ((src >> 12) * 0x00204081u) & 0x01010101u;
-            *reinterpret_cast<uint4 *>(row + 16 * fpt_p3_chunk_slot<KS>(lane, c)) = v;
-        }
-    }
-}
+FPT_D unsigned fpt_p3_nibble_bytes(unsigned x) { return ((x & 0xfu) * 0x00204081u) & 0x01010101u; }   /* bit i -> byte i */
 
 template <int KS>
-FPT_D long long fpt_p3_bet_mma(const unsigned char *indw, const unsigned char *qd, int ntiles, int qd_rows,
-                               typename FptP3Mask<KS == 2>::type nm) {
+FPT_D long long fpt_p3_bet_mma(const unsigned char *qd, int ntiles, int qd_rows, typename FptP3Mask<KS == 2>::type mk) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     constexpr int KB = 32 * KS;
-    /* A fragments: rows g, g + 8 (tile 0) and g + 16, g + 24 (tile 1) */
+    /* masks of my four rows (permutations g + 8 s: rows g, g + 8 of tile 0, then of tile 1) */
+    typename FptP3Mask<KS == 2>::type mr[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) mr[s] = __shfl_sync(FPT_FULL_MASK, mk, g + 8 * s);
+    /* A fragments: my 8 KS individuals of each row */
     unsigned a[2][KS][4];
 #pragma unroll
-    for (int tile = 0; tile < 2; tile++) {
-        const int r0 = 16 * tile + g, r1 = r0 + 8;
-        if (KS == 2) {
-            const uint4 v0 = *reinterpret_cast<const uint4 *>(indw + (size_t)r0 * KB + 16 * fpt_p3_chunk_slot<KS>(r0, t));
-            const uint4 v1 = *reinterpret_cast<const uint4 *>(indw + (size_t)r1 * KB + 16 * fpt_p3_chunk_slot<KS>(r1, t));
-            a[tile][0][0] = v0.x; a[tile][0][1] = v1.x; a[tile][0][2] = v0.y; a[tile][0][3] = v1.y;
-            a[tile][KS - 1][0] = v0.z; a[tile][KS - 1][1] = v1.z; a[tile][KS - 1][2] = v0.w; a[tile][KS - 1][3] = v1.w;
-        } else {
-            const uint2 v0 = *reinterpret_cast<const uint2 *>(indw + (size_t)r0 * KB + 16 * fpt_p3_chunk_slot<KS>(r0, t >> 1) + 8 * (t & 1));
-            const uint2 v1 = *reinterpret_cast<const uint2 *>(indw + (size_t)r1 * KB + 16 * fpt_p3_chunk_slot<KS>(r1, t >> 1) + 8 * (t & 1));
-            a[tile][0][0] = v0.x; a[tile][0][1] = v1.x; a[tile][0][2] = v0.y; a[tile][0][3] = v1.y;
+    for (int s = 0; s < 4; s++) {
+        const unsigned bits = (unsigned)(mr[s] >> (8 * KS * t));     /* 8 KS valid bits */
+        const int tile = s >> 1, j = s & 1;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            a[tile][ks][j] = fpt_p3_nibble_bytes(bits >> (8 * ks));
+            a[tile][ks][2 + j] = fpt_p3_nibble_bytes(bits >> (8 * ks + 4));
         }
     }
-    /* column masks of my four rows (permutations g + 8 s), shifted so that bit 8 nt (+1) is column 8 nt + 2 t (+1) */
-    typename FptP3Mask<KS == 2>::type nmr[4];
+    /* column masks: bit 8 nt (+1) of nm[s] is column 8 nt + 2 t (+1) of row s; set = outside the group */
+    typename FptP3Mask<KS == 2>::type nm[4];
 #pragma unroll
-    for (int s = 0; s < 4; s++) nmr[s] = __shfl_sync(FPT_FULL_MASK, nm, g + 8 * s) >> (2 * t);
+    for (int s = 0; s < 4; s++) nm[s] = ~mr[s] >> (2 * t);
     int sum[4] = { 0, 0, 0, 0 };                        /* every partial sum is a part of sum_{G x not G} q < 2^31 */
     const unsigned char *colbase = qd + (size_t)g * KB + 8 * KS * t;
     const size_t dstride = (size_t)qd_rows * KB;
@@ -266,7 +250,7 @@ FPT_D long long fpt_p3_bet_mma(const unsigned char *indw, const unsigned char *q
                 for (int e = 0; e < 4; e++) {
                     const int s = 2 * tile + (e >> 1);
                     const int v = (c[2][tile][e] * 256 + c[1][tile][e]) * 256 + c[0][tile][e];   /* < min(a, b) * 2^(qbits + 1) < 2^31 */
-                    if ((nmr[s] >> (8 * nt + (e & 1))) & 1) sum[s] += v;
+                    if ((nm[s] >> (8 * nt + (e & 1))) & 1) sum[s] += v;
                 }
             }
         }
@@ -291,7 +275,7 @@ fpt_css_perm3_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
     constexpr int KB = 32 * KS;
     typedef typename FptP3Mask<WIDE>::type mask_t;
     const int T = FPT_P3_T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int qd_rows = ((m + 7) >> 3) << 3, ntiles = qd_rows >> 3, nchunks = (m + 15) >> 4;
+    const int qd_rows = ((m + 7) >> 3) << 3, ntiles = qd_rows >> 3;
     size_t off = 0;
     double *X = (double *)(smem + off); off += (size_t)2 * m * 8;
     unsigned *q = (unsigned *)(smem + off); off += (size_t)m * m * 4;
@@ -299,10 +283,9 @@ fpt_css_perm3_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
     off = (off + 15) & ~(size_t)15;
     unsigned char *qd = smem + off; off += (size_t)3 * qd_rows * KB;
     unsigned char *labels = smem + off; off += (size_t)m * FPT_P3_LINE;
-    unsigned char *indw = smem + off + (size_t)warp * 32 * KB; off += (size_t)FPT_P3_WARPS * 32 * KB;
+    double *stage = reinterpret_cast<double *>(smem + off) + warp * 32; off += (size_t)FPT_P3_WARPS * 32 * 8;
     int *whits = (int *)(smem + off); off += 2 * 2 * FPT_P3_WARPS * 4;         /* [parity][0: round hits, 1: pending hits][warp] */
     int *s_flag = (int *)(smem + off);
-    double *stage = reinterpret_cast<double *>(indw);                          /* exact re-scoring: the warp's rows are idle then */
     unsigned char *col0 = labels + 4 * tid;                                    /* my label word at position 0 */
     const int use_a = asize <= bsize;
     const int draws = m - 1;
@@ -317,7 +300,6 @@ fpt_css_perm3_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
         map_r_b = fpt_lcg_skip(0ULL, n_r); map_r_a = (fpt_lcg_skip(1ULL, n_r) - map_r_b) & FPT_MASK48;
     }
     for (int n = tid; n <= m; n += T) rtab[n] = fpt_p3_magic((uint32_t)n);
-    for (int e = lane; e < 32 * KB / 16; e += 32) reinterpret_cast<uint4 *>(indw)[e] = make_uint4(0u, 0u, 0u, 0u);
     int parity = 0;
     __syncthreads();
 
@@ -470,11 +452,7 @@ fpt_css_perm3_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
                     int hit = 0;
                     bool exact = valid && !use_surrogate;
                     if (use_surrogate) {
-                        const mask_t mk = pp.mask[0];
-                        fpt_p3_write_row<KS>(indw, lane, (unsigned long long)mk, nchunks);
-                        __syncwarp();
-                        const long long bet = fpt_p3_bet_mma<KS>(indw, qd, ntiles, qd_rows, (mask_t)~mk);
-                        __syncwarp();
+                        const long long bet = fpt_p3_bet_mma<KS>(qd, ntiles, qd_rows, pp.mask[0]);
                         if (valid) {
                             const double approx = (double)bet * c_bet - (a_ + b_) * ((double)wa[0] * c_wa + (double)wb[0] * c_wb);
                             const double diff = approx - score;
@@ -493,9 +471,6 @@ fpt_css_perm3_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
                         __syncwarp();
                         const double sc = fpt_p3_warp_exact_score(X, stage, col, asize, bsize, lane);
                         if (lane == src) { hit = sc >= score ? 1 : 0; rechecks++; }
-                        __syncwarp();
-                        /* the stage buffer aliases the membership rows: chunks beyond the cohort must read zero again */
-                        for (int e = lane; e < 32 * 8 / 16; e += 32) reinterpret_cast<uint4 *>(indw)[e] = make_uint4(0u, 0u, 0u, 0u);
                         __syncwarp();
                     }
                     hitmask |= (unsigned)hit << k;
