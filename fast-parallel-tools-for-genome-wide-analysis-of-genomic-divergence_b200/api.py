@@ -50,6 +50,11 @@ def set_perm_small_kernel(v):
     _lib.load().fpt_set_perm_small_kernel(int(v))
 
 
+def set_mds_small_kernel(v):
+    """Cohorts of 3..48, classical MDS: 1 / True = tridiagonalisation in registers (default), 0 / False = the shared-memory kernel."""
+    _lib.load().fpt_set_mds_small_kernel(int(v))
+
+
 def set_k4_mode(mode):
     """Large cohorts, genotype-distance matrix: 2 = tcgen05 u8 GEMM (default), 1 = popcounts, 0 = legacy fp64 matrix."""
     _lib.load().fpt_set_k4_mode(int(mode))

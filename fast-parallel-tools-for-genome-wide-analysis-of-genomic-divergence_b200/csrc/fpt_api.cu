@@ -26,6 +26,7 @@
 #include "../../include/fpt_b200.h"
 #include "fpt_css.cuh"
 #include "fpt_css_eig.cuh"
+#include "fpt_css_eig_reg.cuh"
 #include "fpt_css_lanczos.cuh"
 #include "fpt_css_k4.cuh"
 #include "fpt_css_perm.cuh"
@@ -46,12 +47,13 @@ static std::atomic<int> g_lanczos_form{2};      /* large-cohort MDS: highest pro
 static std::atomic<int> g_perm_umma{1};         /* large cohorts: 1 = tcgen05 permutation kernel, 0 = the general (mma.sync) kernel */
 static std::atomic<int> g_perm_chain{0};        /* CSS label shuffles: 0 = independent per permutation, 1 = the reference's chain */
 static std::atomic<int> g_perm_small{1};        /* cohorts of 8..64, independent shuffles: 1 = fpt_css_perm3_kernel, 0 = the round-1 kernel (fpt_css_perm2_kernel) */
+static std::atomic<int> g_mds_small{1};         /* cohorts of 3..48, classical MDS: 1 = tridiagonalisation in registers (fpt_css_tridiag_reg_kernel), 0 = the shared-memory kernel */
 static std::atomic<int> g_k4_mode{2};           /* large cohorts, genotype-distance matrix: 2 = tcgen05 u8 GEMM, 1 = popcounts, 0 = legacy fp64 matrix */
 
-struct Knobs { int lanczos_form, perm_umma, perm_chain, k4_mode, perm_small; };
+struct Knobs { int lanczos_form, perm_umma, perm_chain, k4_mode, perm_small, mds_small; };
 static Knobs knobs_now() {
     Knobs k;
-    k.lanczos_form = g_lanczos_form.load(); k.perm_umma = g_perm_umma.load(); k.perm_chain = g_perm_chain.load(); k.k4_mode = g_k4_mode.load(); k.perm_small = g_perm_small.load();
+    k.lanczos_form = g_lanczos_form.load(); k.perm_umma = g_perm_umma.load(); k.perm_chain = g_perm_chain.load(); k.k4_mode = g_k4_mode.load(); k.perm_small = g_perm_small.load(); k.mds_small = g_mds_small.load();
     return k;
 }
 
@@ -296,6 +298,7 @@ extern "C" int fpt_get_perm_mode(void) { return g_perm_chain.load(); }
 extern "C" void fpt_set_perm_large_kernel(int tensor_memory) { g_perm_umma.store(tensor_memory); }
 extern "C" void fpt_set_lanczos_form(int max_form) { g_lanczos_form.store(max_form < 0 ? 0 : (max_form > 2 ? 2 : max_form)); }
 extern "C" void fpt_set_perm_small_kernel(int v) { g_perm_small.store(v != 0); }
+extern "C" void fpt_set_mds_small_kernel(int v) { g_mds_small.store(v != 0); }
 extern "C" void fpt_set_k4_mode(int mode) { g_k4_mode.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode)); }
 extern "C" int fpt_debug_k4_phases(unsigned long long *out4) {
     unsigned long long zero[4] = { 0 };
@@ -691,9 +694,28 @@ static int dev_css_windows(const Knobs &kn, const uint32_t *planes, const double
     int grid;
     if (mds == 0 || mds == 2) {
         if (p.mds_warps > 0) {
-            const int block = 32 * p.mds_warps;
-            CHECK(persistent_grid(c, fpt_css_tridiag_kernel, block, p.smem_mds_warp, (nwin + p.mds_warps - 1) / p.mds_warps, &grid));
-            { ProfScope ps_("css_tridiag", st); fpt_css_tridiag_kernel<<<grid, block, p.smem_mds_warp, st>>>(planes, absdiff, m, wleft, wright, nwin, 3, ws.tri, ws.refl, status); }
+            if (kn.mds_small && planes && !absdiff && fpt_tridiag_reg_ok(m)) {
+                /* the genome scans' cohorts: the whole matrix in the registers of the warp */
+                const int block = 32 * FPT_TREG_WARPS, pad = fpt_tridiag_reg_pad(m);
+                const size_t smem_r = fpt_tridiag_reg_work_bytes(m) * FPT_TREG_WARPS;
+                const long long items = (nwin + FPT_TREG_WARPS - 1) / FPT_TREG_WARPS;
+                ProfScope ps_("css_tridiag", st);
+                if (pad == 32) {
+                    CHECK(persistent_grid(c, fpt_css_tridiag_reg_kernel<4, 8>, block, smem_r, items, &grid));
+                    fpt_css_tridiag_reg_kernel<4, 8><<<grid, block, smem_r, st>>>(planes, m, wleft, wright, nwin, ws.tri, ws.refl, status);
+                } else if (pad == 40) {
+                    CHECK(persistent_grid(c, fpt_css_tridiag_reg_kernel<5, 10>, block, smem_r, items, &grid));
+                    fpt_css_tridiag_reg_kernel<5, 10><<<grid, block, smem_r, st>>>(planes, m, wleft, wright, nwin, ws.tri, ws.refl, status);
+                } else {
+                    CHECK(persistent_grid(c, fpt_css_tridiag_reg_kernel<6, 12>, block, smem_r, items, &grid));
+                    fpt_css_tridiag_reg_kernel<6, 12><<<grid, block, smem_r, st>>>(planes, m, wleft, wright, nwin, ws.tri, ws.refl, status);
+                }
+            } else {
+                const int block = 32 * p.mds_warps;
+                CHECK(persistent_grid(c, fpt_css_tridiag_kernel, block, p.smem_mds_warp, (nwin + p.mds_warps - 1) / p.mds_warps, &grid));
+                ProfScope ps_("css_tridiag", st);
+                fpt_css_tridiag_kernel<<<grid, block, p.smem_mds_warp, st>>>(planes, absdiff, m, wleft, wright, nwin, 3, ws.tri, ws.refl, status);
+            }
             CU(cudaGetLastError());
             const size_t smem_b = fpt_eigvec_work_bytes(m) * 4;
             CHECK(persistent_grid(c, fpt_css_eigvec_kernel, 128, smem_b, (nwin + 3) / 4, &grid));

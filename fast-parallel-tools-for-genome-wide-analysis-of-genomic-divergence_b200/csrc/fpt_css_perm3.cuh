@@ -44,7 +44,7 @@ FPT_HD int fpt_css_perm3_ksteps(int m) { return m <= 32 ? 1 : 2; }
 FPT_HD size_t fpt_css_perm3_smem_bytes(int m) {
     const int qd_rows = ((m + 7) >> 3) << 3, kb = 32 * fpt_css_perm3_ksteps(m);
     size_t off = (size_t)2 * m * 8;                                   /* X */
-    off += (size_t)m * m * 4;                                         /* q */
+    off += ((size_t)m * m * 4 + 7) & ~(size_t)7;                      /* q (odd m: the 8-byte table behind it stays aligned) */
     off += (size_t)(m + 1) * 8;                                       /* (magic, shift) per n */
     off = (off + 15) & ~(size_t)15;
     off += (size_t)3 * qd_rows * kb;                                  /* digit matrices */
@@ -278,7 +278,7 @@ fpt_css_perm3_kernel(const double *__restrict__ Xall, int m, int asize, int bsiz
     const int qd_rows = ((m + 7) >> 3) << 3, ntiles = qd_rows >> 3;
     size_t off = 0;
     double *X = (double *)(smem + off); off += (size_t)2 * m * 8;
-    unsigned *q = (unsigned *)(smem + off); off += (size_t)m * m * 4;
+    unsigned *q = (unsigned *)(smem + off); off += ((size_t)m * m * 4 + 7) & ~(size_t)7;
     uint2 *rtab = (uint2 *)(smem + off); off += (size_t)(m + 1) * 8;
     off = (off + 15) & ~(size_t)15;
     unsigned char *qd = smem + off; off += (size_t)3 * qd_rows * KB;

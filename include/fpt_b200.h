@@ -71,6 +71,10 @@ void fpt_set_perm_large_kernel(int tensor_memory);
    flight per thread, conflict-free label layout, no fp64 distance matrix; csrc/fpt_css_perm3.cuh), 0 the round-1 kernel
    fpt_css_perm2_kernel. Same hits, permutations drawn, p and scores from both; the switch exists for the parity tests. */
 void fpt_set_perm_small_kernel(int v);
+/* Cohorts of 3..48 individuals, classical MDS (mds 0 and the start of mds 2): 1 (default) the Householder tridiagonalisation with the
+   matrix in the registers of one warp (csrc/fpt_css_eig_reg.cuh), 0 the shared-memory kernel that serves every cohort up to the
+   one-warp limit (csrc/fpt_css_eig.cuh). Results agree to rounding; the switch exists for the parity tests. */
+void fpt_set_mds_small_kernel(int v);
 /* diagnostic: SM cycles per phase of the tensor-memory permutation kernel since the last call, summed over CTAs and windows
    (0 distance pass, 1 hand-over of the observed score, 2 shuffles, 3 membership rows, 4 contraction, 5 decisions, 6 label copy-out
    and adjacent-pair sums); synchronises the device */

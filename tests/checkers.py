@@ -259,3 +259,30 @@ def silence_stdout():
             os.close(saved)
             os.close(devnull)
     return _cm()
+
+
+def fet_exact_rule(a, b, c, d):
+    """The reference's two-tailed rule (fisher/cFisher.c:245-340: first tail towards the minimum cell, strict `<` on the second
+    tail, doubling on equal margins) in exact rational arithmetic; returns P as a Fraction."""
+    from fractions import Fraction
+    from math import comb
+    R1, R2, C1, C2 = a + b, c + d, a + c, b + d
+    n = R1 + R2
+    cw = [a, b, d, c]
+    at = cw.index(min(cw))
+    x_dir = -1 if at in (0, 2) else 1                     # minimum cell is a or d: x = cell(0,0) decreases
+    lo, hi = max(0, C1 - R2), min(R1, C1)
+    pm = lambda x: Fraction(comb(R1, x) * comb(R2, C1 - x), comb(n, C1))
+    P0 = pm(a)
+    xs = range(lo, a + 1) if x_dir < 0 else range(a, hi + 1)
+    P = sum(pm(x) for x in xs)
+    if R1 == R2 or C1 == C2:
+        P = 2 * P
+    else:
+        other = range(hi, a, -1) if x_dir < 0 else range(lo, a)
+        for x in other:
+            if pm(x) < P0:
+                P += pm(x)
+            else:
+                break
+    return min(P, Fraction(1))

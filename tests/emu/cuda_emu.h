@@ -115,6 +115,7 @@ static inline int __syncthreads_or(int p) {
 }
 
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 static inline int __syncthreads_and(int p) { return !__syncthreads_or(!p); }
 static inline double __hiloint2double(int hi, int lo) {
     unsigned long long bits = ((unsigned long long)(unsigned)hi << 32) | (unsigned long long)(unsigned)lo;

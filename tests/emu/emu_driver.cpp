@@ -11,6 +11,7 @@ FPT_EMU_DEFINE_GLOBALS
 #include "fpt_fet.cuh"
 #include "fpt_css.cuh"
 #include "fpt_css_eig.cuh"
+#include "fpt_css_eig_reg.cuh"
 #include "fpt_css_lanczos.cuh"
 #include "fpt_css_k4.cuh"
 #include "fpt_css_perm.cuh"
@@ -143,6 +144,22 @@ void emu_css_mds_warp(const unsigned *planes, const double *absdiff, int m, cons
         fpt_css_tridiag_kernel(planes, absdiff, m, wleft, wright, nwin, wch, pt, pr, status);
     });
     run_grid(grid, 32 * warps, fpt_eigvec_work_bytes(m) * warps, [=]() {
+        fpt_css_eigvec_kernel(m, nwin, pt, pr, status, X, evals);
+    });
+}
+
+/* the same with phase A in registers (fpt_css_eig_reg.cuh), 3 <= m <= 48 */
+void emu_css_mds_warp_reg(const unsigned *planes, int m, const int *wleft, const int *wright, long long nwin, int grid,
+                          double *X, double *evals, unsigned char *status) {
+    std::vector<double> tri((size_t)nwin * 3 * m + 1), refl((size_t)nwin * ((size_t)m * (m - 1) / 2) + 1);
+    double *pt = tri.data(), *pr = refl.data();
+    const int pad = fpt_tridiag_reg_pad(m);
+    run_grid(grid, 32 * FPT_TREG_WARPS, fpt_tridiag_reg_work_bytes(m) * FPT_TREG_WARPS, [=]() {
+        if (pad == 32) fpt_css_tridiag_reg_kernel<4, 8>(planes, m, wleft, wright, nwin, pt, pr, status);
+        else if (pad == 40) fpt_css_tridiag_reg_kernel<5, 10>(planes, m, wleft, wright, nwin, pt, pr, status);
+        else fpt_css_tridiag_reg_kernel<6, 12>(planes, m, wleft, wright, nwin, pt, pr, status);
+    });
+    run_grid(grid, 64, fpt_eigvec_work_bytes(m) * 2, [=]() {
         fpt_css_eigvec_kernel(m, nwin, pt, pr, status, X, evals);
     });
 }

@@ -169,8 +169,14 @@ def test_css_pack_kernel(emu):
     assert np.array_equal(P8, P.reshape(-1))
 
 
-def test_css_mds_kernels(emu, oracle):
-    asize, bsize, S, L, wsize, wstep = 6, 5, 220, 20000, 2500, 500
+@pytest.mark.parametrize("kernel,asize,bsize,S,L", [("smem", 6, 5, 220, 20000), ("reg", 6, 5, 220, 20000), ("reg", 1, 2, 120, 8000),
+                                                   ("reg", 16, 16, 200, 10000), ("reg", 20, 20, 200, 10000), ("reg", 17, 20, 150, 8000),
+                                                   ("reg", 25, 23, 220, 9000), ("reg", 20, 20, 2500, 9000)])
+def test_css_mds_kernels(emu, oracle, kernel, asize, bsize, S, L):
+    """phase A + phase B of the one-warp classical MDS against the oracle's cmds (css.c:505-560): the shared-memory
+    tridiagonalisation and the register one (fpt_css_eig_reg.cuh) in each of its three paddings (32, 40, 48), a 3-individual
+    cohort, and dense windows that span several 32-SNP words"""
+    wsize, wstep = 2500, 500
     m = asize + bsize
     pos, av, bv = _css_input(6, asize, bsize, S, L)
     planes = _pack(emu, av, bv, S, asize, bsize)
@@ -178,7 +184,10 @@ def test_css_mds_kernels(emu, oracle):
     wl, wr = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
     emu.emu_window_table(iptr(pos), ll(S), ll(0), ll(n), L, wsize, wstep, 0, iptr(wl), iptr(wr))
     X, ev, st = np.zeros((n, m, 2)), np.zeros((n, 3)), np.zeros(n, dtype=np.uint8)
-    emu.emu_css_mds_warp(vp(planes), None, m, iptr(wl), iptr(wr), ll(n), 4, 2, 3, dptr(X), dptr(ev), vp(st))
+    if kernel == "reg":
+        emu.emu_css_mds_warp_reg(vp(planes), m, iptr(wl), iptr(wr), ll(n), 2, dptr(X), dptr(ev), vp(st))
+    else:
+        emu.emu_css_mds_warp(vp(planes), None, m, iptr(wl), iptr(wr), ll(n), 4, 2, 3, dptr(X), dptr(ev), vp(st))
     scored = 0
     for w in range(n):
         l, r = int(wl[w]), int(wr[w])
@@ -200,7 +209,7 @@ def test_css_mds_kernels(emu, oracle):
         if np.isfinite(do).all() and np.isfinite(dg).all() and evo[1] - evo[2] > 1e-8 * evo[0]:
             assert np.allclose(do, dg, rtol=1e-9, atol=1e-10 * do.max())
             scored += 1
-    assert scored >= 10
+    assert scored >= (10 if m > 3 else 3)
 
 
 @pytest.mark.parametrize("route", ["legacy", "codes"])

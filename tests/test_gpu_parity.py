@@ -79,6 +79,26 @@ def test_fet_log_mode_high_coverage(fpt, oracle):
     assert close.mean() > 0.99
 
 
+def test_fet_log_mode_against_exact_rationals(fpt):
+    """The GPU's log-space walk (tables beyond the reference's u64 domain, N > 67: SURVEY Q2, fisher/cFisher.c:256-284,473-483) against
+    exact rational arithmetic of the reference's two-tailed rule — no oracle in between."""
+    from math import log10
+    rng = np.random.default_rng(19)
+    T = []
+    for _ in range(400):
+        n1, n2 = int(rng.integers(40, 500)), int(rng.integers(40, 500))
+        f = rng.uniform(0.05, 0.95)
+        a, c = int(rng.binomial(n1, f)), int(rng.binomial(n2, min(0.99, max(0.01, f + rng.normal(0, 0.08)))))
+        T.append((a, n1 - a, c, n2 - c))
+    T = np.ascontiguousarray(np.array(T, dtype=np.int32))
+    assert (T.sum(axis=1) > 67).all()
+    got = fpt.fet_tables(T)
+    for t, g in zip(T, got):
+        P = checkers.fet_exact_rule(*[int(v) for v in t])
+        want = 0.0 if P == 1 else -(log10(P.numerator) - log10(P.denominator))
+        assert g == pytest.approx(want, rel=1e-9, abs=1e-10), tuple(t)
+
+
 @pytest.mark.parametrize("semantics", [0, 1])
 @pytest.mark.parametrize("geom", [(2500, 500), (1000, 1000), (700, 300)])
 def test_fet_scan_matches_oracle(fpt, oracle, semantics, geom):
@@ -265,7 +285,7 @@ def test_css_permutation_early_stop_matches_oracle(fpt, oracle, mct, mcr):
     assert np.array_equal(p_g, p_o)
 
 
-@pytest.mark.parametrize("asize,bsize,mct,mcr", [(20, 20, 1000, 1000), (20, 20, 10, 5000), (7, 9, 300, 1300), (30, 34, 50, 600), (4, 4, 5, 100)])
+@pytest.mark.parametrize("asize,bsize,mct,mcr", [(20, 20, 1000, 1000), (20, 20, 10, 5000), (7, 9, 300, 1300), (30, 34, 50, 600), (4, 4, 5, 100), (13, 20, 40, 700)])
 def test_css_headline_permutation_kernel_matches_round1_kernel(fpt, oracle, asize, bsize, mct, mcr):
     """cohorts of 8..64: fpt_css_perm3_kernel (default) and the round-1 kernel fpt_css_perm2_kernel take the same decisions —
     scores bit-identical, hits, permutations drawn and p identical — over several rounds, early stops and ragged tails; and
@@ -290,6 +310,36 @@ def test_css_headline_permutation_kernel_matches_round1_kernel(fpt, oracle, asiz
         # 4+4: one permutation in 70 swaps the two groups as sets and ties with the observed score up to rounding, so `>=` is
         # decided by the last bits of the embedding, i.e. by the eigensolver (GSL boundary, see test_css_scan_matches_oracle)
         assert np.array_equal(p3, p_o)
+
+
+@pytest.mark.parametrize("asize,bsize", [(20, 20), (1, 2), (16, 16), (13, 20), (25, 23), (7, 9)])
+def test_css_register_tridiagonalisation_matches_shared_memory_kernel(fpt, oracle, asize, bsize):
+    """cohorts of 3..48, classical MDS: the tridiagonalisation with the matrix in registers (default, csrc/fpt_css_eig_reg.cuh,
+    paddings 32 / 40 / 48) and the shared-memory kernel (csrc/fpt_css_eig.cuh) keep the same windows and agree to rounding on
+    scores and eigenvalues; both are within tolerance of the oracle's cmds + css (css.c:505-560,608-647)"""
+    from fpt_b200 import api
+    regend, wsize, wstep, nsnp, seed = 60000, 2500, 500, 1800, 29
+    ch, (av, bv, apos, bpos) = _synth(71 + asize, regend, nsnp, asize, bsize, planted_every=4, planted_len=10)
+    out = []
+    try:
+        for v in (1, 0):
+            api.set_mds_small_kernel(v)
+            out.append(fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 50, 200, mds=0, seed=seed, probes=True))
+    finally:
+        api.set_mds_small_kernel(1)
+    (s1, p1, w1, pr1), (s0, p0, w0, pr0) = out
+    assert np.array_equal(w1, w0) and (w1 == 1).sum() > 40
+    fin = np.isfinite(s0) & (w0 == 1)
+    assert np.array_equal(np.isfinite(s1), np.isfinite(s0))
+    gap_ok = (pr0["evals"][:, 1] - pr0["evals"][:, 2]) > 1e-6 * np.abs(pr0["evals"][:, 0])       # lambda2 ~ lambda3: any solver's choice (SURVEY Q11)
+    sel = fin & gap_ok
+    assert sel.sum() > 30
+    np.testing.assert_allclose(s1[sel], s0[sel], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(pr1["evals"][sel, :2], pr0["evals"][sel, :2], rtol=1e-10, atol=1e-10 * np.abs(pr0["evals"][sel, 0]).max())
+    s_o, p_o = _css_oracle_scan(oracle, av, bv, apos, bpos, regend, wsize, wstep, 50, 200, 0, 0, seed)
+    np.testing.assert_allclose(s1[sel], s_o[sel], rtol=CSS_RTOL, atol=1e-12)
+    if asize + bsize > 4:
+        assert np.array_equal(p1[sel], p_o[sel])
 
 
 def test_css_dropin_matches_reference(fpt, ref_css):

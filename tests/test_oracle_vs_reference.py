@@ -52,31 +52,9 @@ def test_fet_random_tables_up_to_n67(oracle, ref_fet, n, data):
 def test_log_mode_against_exact_rationals(oracle):
     """outside the reference's u64 domain: the log-space walk against exact rational arithmetic of the same
     two-tailed rule (first tail towards the minimum cell, strict `<` on the second tail, doubling on equal margins)"""
-    from fractions import Fraction
-    from math import comb, log10
+    from math import log10
     rng = np.random.default_rng(9)
-
-    def exact_rule(a, b, c, d):
-        R1, R2, C1, C2 = a + b, c + d, a + c, b + d
-        n = R1 + R2
-        cw = [a, b, d, c]
-        at = cw.index(min(cw))
-        x_dir = -1 if at in (0, 2) else 1                     # minimum cell is a or d: x = cell(0,0) decreases
-        lo, hi = max(0, C1 - R2), min(R1, C1)
-        pm = lambda x: Fraction(comb(R1, x) * comb(R2, C1 - x), comb(n, C1))
-        P0 = pm(a)
-        xs = range(lo, a + 1) if x_dir < 0 else range(a, hi + 1)
-        P = sum(pm(x) for x in xs)
-        if R1 == R2 or C1 == C2:
-            P = 2 * P
-        else:
-            other = range(hi, a, -1) if x_dir < 0 else range(lo, a)
-            for x in other:
-                if pm(x) < P0:
-                    P += pm(x)
-                else:
-                    break
-        return min(P, Fraction(1))
+    exact_rule = checkers.fet_exact_rule
 
     for _ in range(300):
         n1, n2 = int(rng.integers(40, 400)), int(rng.integers(40, 400))
