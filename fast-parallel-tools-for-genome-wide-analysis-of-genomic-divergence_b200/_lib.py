@@ -53,6 +53,7 @@ SYMBOLS = {
     "fpt_set_perm_large_kernel": (None, [_I]),
     "fpt_set_perm_small_kernel": (None, [_I]),
     "fpt_set_mds_small_kernel": (None, [_I]),
+    "fpt_set_lanczos_threads": (None, [_I]),
     "fpt_debug_umma_phases": (_I, [_P]),
     "fpt_debug_lanczos_phases": (_I, [_P]),
     "fpt_set_lanczos_form": (None, [_I]),

@@ -44,16 +44,17 @@ static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_seed{20261018ULL};
 static std::atomic<int> g_device{-1};           /* -1: whatever device is current */
 static std::atomic<int> g_lanczos_form{2};      /* large-cohort MDS: highest product form allowed (2 8-bit codes, 1 16-bit codes, 0 fp64 matrix) */
+static std::atomic<int> g_lanczos_threads{512};  /* large-cohort MDS on count codes: threads per CTA (512 or 384) */
 static std::atomic<int> g_perm_umma{1};         /* large cohorts: 1 = tcgen05 permutation kernel, 0 = the general (mma.sync) kernel */
 static std::atomic<int> g_perm_chain{0};        /* CSS label shuffles: 0 = independent per permutation, 1 = the reference's chain */
 static std::atomic<int> g_perm_small{1};        /* cohorts of 8..64, independent shuffles: 1 = fpt_css_perm3_kernel, 0 = the round-1 kernel (fpt_css_perm2_kernel) */
 static std::atomic<int> g_mds_small{1};         /* cohorts of 3..48, classical MDS: 1 = tridiagonalisation in registers (fpt_css_tridiag_reg_kernel), 0 = the shared-memory kernel */
 static std::atomic<int> g_k4_mode{2};           /* large cohorts, genotype-distance matrix: 2 = tcgen05 u8 GEMM, 1 = popcounts, 0 = legacy fp64 matrix */
 
-struct Knobs { int lanczos_form, perm_umma, perm_chain, k4_mode, perm_small, mds_small; };
+struct Knobs { int lanczos_form, perm_umma, perm_chain, k4_mode, perm_small, mds_small, lanczos_threads; };
 static Knobs knobs_now() {
     Knobs k;
-    k.lanczos_form = g_lanczos_form.load(); k.perm_umma = g_perm_umma.load(); k.perm_chain = g_perm_chain.load(); k.k4_mode = g_k4_mode.load(); k.perm_small = g_perm_small.load(); k.mds_small = g_mds_small.load();
+    k.lanczos_form = g_lanczos_form.load(); k.perm_umma = g_perm_umma.load(); k.perm_chain = g_perm_chain.load(); k.k4_mode = g_k4_mode.load(); k.perm_small = g_perm_small.load(); k.mds_small = g_mds_small.load(); k.lanczos_threads = g_lanczos_threads.load();
     return k;
 }
 
@@ -299,6 +300,7 @@ extern "C" void fpt_set_perm_large_kernel(int tensor_memory) { g_perm_umma.store
 extern "C" void fpt_set_lanczos_form(int max_form) { g_lanczos_form.store(max_form < 0 ? 0 : (max_form > 2 ? 2 : max_form)); }
 extern "C" void fpt_set_perm_small_kernel(int v) { g_perm_small.store(v != 0); }
 extern "C" void fpt_set_mds_small_kernel(int v) { g_mds_small.store(v != 0); }
+extern "C" void fpt_set_lanczos_threads(int threads) { g_lanczos_threads.store(threads == 384 ? 384 : 512); }
 extern "C" void fpt_set_k4_mode(int mode) { g_k4_mode.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode)); }
 extern "C" int fpt_debug_k4_phases(unsigned long long *out4) {
     unsigned long long zero[4] = { 0 };
@@ -731,7 +733,9 @@ static int dev_css_windows(const Knobs &kn, const uint32_t *planes, const double
                 const size_t stride = fpt_k4_window_stride(m);
                 const size_t smem_lz = fpt_lanczos_smem_bytes(m, 0);
                 int grid_lz;
-                CHECK(persistent_grid(c, fpt_css_mds_codes_kernel, 512, smem_lz, nwin, &grid_lz));
+                const int lzt = kn.lanczos_threads;
+                if (lzt == 384) CHECK(persistent_grid(c, fpt_css_mds_codes_kernel<384>, 384, smem_lz, nwin, &grid_lz));
+                else CHECK(persistent_grid(c, fpt_css_mds_codes_kernel<512>, 512, smem_lz, nwin, &grid_lz));
                 grid_lz = std::min(grid_lz, p.max_ctas);
                 for (long long w0 = 0; w0 < nwin; w0 += FPT_K4_BATCH) {
                     const long long nb = std::min<long long>(FPT_K4_BATCH, nwin - w0);
@@ -747,8 +751,12 @@ static int dev_css_windows(const Knobs &kn, const uint32_t *planes, const double
                         { ProfScope ps_("css_k4", st); fpt_css_k4_popc_kernel<<<g4, 256, smem4, st>>>(planes, m, wleft + w0, wright + w0, nb, ws.codes, stride); }
                     }
                     CU(cudaGetLastError());
-                    { ProfScope ps_("css_mds_large", st); fpt_css_mds_codes_kernel<<<(int)std::min<long long>(grid_lz, nb), 512, smem_lz, st>>>(
-                          ws.codes, stride, m, wleft + w0, wright + w0, nb, ws.basis, ws.X + (size_t)w0 * 2 * m, ws.evals + (size_t)w0 * 3, status + w0, nullptr); }
+                    {
+                        ProfScope ps_("css_mds_large", st);
+                        const int g_ = (int)std::min<long long>(grid_lz, nb);
+                        if (lzt == 384) fpt_css_mds_codes_kernel<384><<<g_, 384, smem_lz, st>>>(ws.codes, stride, m, wleft + w0, wright + w0, nb, ws.basis, ws.X + (size_t)w0 * 2 * m, ws.evals + (size_t)w0 * 3, status + w0, nullptr);
+                        else fpt_css_mds_codes_kernel<512><<<g_, 512, smem_lz, st>>>(ws.codes, stride, m, wleft + w0, wright + w0, nb, ws.basis, ws.X + (size_t)w0 * 2 * m, ws.evals + (size_t)w0 * 3, status + w0, nullptr);
+                    }
                     CU(cudaGetLastError());
                 }
             } else {

@@ -119,16 +119,42 @@ FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, int ld, const 
     constexpr int PER = 8 / (int)sizeof(CodeT);                 /* codes per 8-byte load: 4 or 8 */
     constexpr int BITS = 8 * (int)sizeof(CodeT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int i = ROWS * warp; i < m; i += ROWS * nwarp) {
+    /* The (row group, column chunk) pairs of this warp as ONE sequence, software-pipelined: the ROWS loads of the next pair are
+       issued before the multiply-adds of the current one, so a warp's own arithmetic covers its own load latency (ncu of the
+       nested-loop form: 42 % of the warp cycles waiting on the loads just issued, issue slots 39 % busy). */
+    const int nchunk = (m + 32 * PER - 1) / (32 * PER);
+    const int first = ROWS * warp, gstep = ROWS * nwarp;
+    const int ngrp = first < m ? (m - first + gstep - 1) / gstep : 0;
+    const int total = ngrp * nchunk;
+    const int j0 = PER * lane;
+    uint2 nxt[ROWS];
+    int gi = first, ch = 0;
+    auto load = [&](int i, int chunk, uint2 (&cc)[ROWS]) {
+        const int j = j0 + chunk * 32 * PER;
         const int nr = m - i < ROWS ? m - i : ROWS;
-        const CodeT *r0 = C + (size_t)i * ld;                  /* columns m .. ld-1 (if any) meet x = 0 */
-        double acc[ROWS];
+        const CodeT *r0 = C + (size_t)i * ld + j;              /* columns m .. ld-1 (if any) meet x = 0 */
+        if (j < m) {
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) acc[r] = 0.0;
-        for (int j = PER * lane; j < m; j += 32 * PER) {
-            uint2 cc[ROWS];                                     /* ROWS 8-byte loads in flight per lane */
+            for (int r = 0; r < ROWS; r++) cc[r] = *reinterpret_cast<const uint2 *>(r0 + (size_t)(r < nr ? r : 0) * ld);
+        } else {
 #pragma unroll
-            for (int r = 0; r < ROWS; r++) cc[r] = *reinterpret_cast<const uint2 *>(r0 + (size_t)(r < nr ? r : 0) * ld + j);
+            for (int r = 0; r < ROWS; r++) cc[r] = make_uint2(0u, 0u);
+        }
+    };
+    if (total > 0) load(gi, ch, nxt);
+    double acc[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) acc[r] = 0.0;
+#pragma unroll 1
+    for (int t = 0; t < total; t++) {
+        uint2 cc[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) cc[r] = nxt[r];
+        const int i = gi, j = j0 + ch * 32 * PER;
+        const bool last_chunk = ch == nchunk - 1;
+        if (last_chunk) { ch = 0; gi += gstep; } else ch++;
+        if (t + 1 < total) load(gi, ch, nxt);
+        if (j < m) {
 #pragma unroll
             for (int k = 0; k < PER; k += 2) {
                 const double2 xv = *reinterpret_cast<const double2 *>(x + j + k);
@@ -141,8 +167,7 @@ FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, int ld, const 
                         const unsigned c = (word >> (((k + kk) * BITS) & 31)) & ((1u << BITS) - 1u);
                         if (LUT) {
                             /* 8-bit codes: S(c) from a 256-entry shared-memory table (c^2, or v2 for c = 0) — one load instead
-                               of a multiply, the 2^52 conversion add, a compare and two selects per element; the product is
-                               bound by instruction issue, not by bytes */
+                               of a multiply, the 2^52 conversion add, a compare and two selects per element */
                             acc[r] = fma(lut[c], xk, acc[r]);
                         } else {
                             const double sq = __hiloint2double(0x43300000, (int)(c * c)) - 4503599627370496.0;
@@ -152,12 +177,17 @@ FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, int ld, const 
                 }
             }
         }
+        if (last_chunk) {
+            const int nr = m - i < ROWS ? m - i : ROWS;
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) acc[r] = fpt_warp_sum(acc[r]);
-        if (lane == 0) {
+            for (int r = 0; r < ROWS; r++) acc[r] = fpt_warp_sum(acc[r]);
+            if (lane == 0) {
 #pragma unroll
-            for (int r = 0; r < ROWS; r++)
-                if (r < nr) y[i + r] = -0.5 * (((acc[r] - rmean[i + r] * sx) - rx) + g * sx);
+                for (int r = 0; r < ROWS; r++)
+                    if (r < nr) y[i + r] = -0.5 * (((acc[r] - rmean[i + r] * sx) - rx) + g * sx);
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) acc[r] = 0.0;
         }
     }
 }
@@ -168,15 +198,29 @@ FPT_D void fpt_cta_cgs_pass(const double *__restrict__ Q, int nq, int m, double 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int i = warp; i < nq; i += nwarp) {
         const double *qi = Q + (size_t)i * m;
-        double s = 0.0;
-        for (int e = lane; e < m; e += 32) s += qi[e] * w[e];
-        s = fpt_warp_sum(s);
+        double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;              /* four loads in flight per lane */
+        int e = lane;
+        for (; e + 96 < m; e += 128) {
+            const double a0 = qi[e], a1 = qi[e + 32], a2 = qi[e + 64], a3 = qi[e + 96];
+            s = fma(a0, w[e], s); s1 = fma(a1, w[e + 32], s1); s2 = fma(a2, w[e + 64], s2); s3 = fma(a3, w[e + 96], s3);
+        }
+        for (; e < m; e += 32) s = fma(qi[e], w[e], s);
+        s = fpt_warp_sum((s + s1) + (s2 + s3));
         if (lane == 0) { hpass[i] = s; h[i] += s; }
     }
     __syncthreads();
     for (int e = threadIdx.x; e < m; e += blockDim.x) {
         double acc = w[e];
-        for (int i = 0; i < nq; i++) acc -= hpass[i] * Q[(size_t)i * m + e];
+        const double *qe = Q + e;
+        int i = 0;
+        for (; i + 8 <= nq; i += 8) {                                /* eight independent loads, then the eight updates in order */
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = qe[(size_t)(i + u) * m];
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc = fma(-hpass[i + u], v[u], acc);
+        }
+        for (; i < nq; i++) acc = fma(-hpass[i], qe[(size_t)i * m], acc);
         w[e] = acc;
     }
     __syncthreads();
@@ -419,8 +463,10 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
 /* Large cohorts, default route. The window's count codes were written by fpt_css_k4_umma_kernel / fpt_css_k4_popc_kernel
    (fpt_css_k4.cuh); here fill_averages (css.c:337-366) and the double centring of cmds (css.c:505-531) are derived from them in
    integers — blanks = codes 0, their replacement = (sum of the counts) / m^2, row sums of squares exact — and the Lanczos
-   iteration streams the codes. basis: per CTA fpt_lanczos_cap(m) x m doubles. */
-__global__ void __launch_bounds__(512, 2)
+   iteration streams the codes. basis: per CTA fpt_lanczos_cap(m) x m doubles. THREADS: 512 (64 registers per thread) or 384 (80:
+   room for the software-pipelined loads of the product without spills); two CTAs per SM either way. */
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2)
 fpt_css_mds_codes_kernel(const unsigned char *__restrict__ codes, size_t stride, int m, const int *__restrict__ wleft,
                          const int *__restrict__ wright, long long nwin, double *__restrict__ basis, double *__restrict__ Xout,
                          double *__restrict__ evals_out, unsigned char *__restrict__ status, int *__restrict__ steps_out) {

@@ -75,6 +75,9 @@ void fpt_set_perm_small_kernel(int v);
    matrix in the registers of one warp (csrc/fpt_css_eig_reg.cuh), 0 the shared-memory kernel that serves every cohort up to the
    one-warp limit (csrc/fpt_css_eig.cuh). Results agree to rounding; the switch exists for the parity tests. */
 void fpt_set_mds_small_kernel(int v);
+/* Large-cohort MDS on count codes: threads per CTA, 512 (default) or 384 (more registers per thread for the pipelined loads of the
+   Lanczos product). Tuning aid; results are identical up to the summation order inside a warp, which does not depend on it. */
+void fpt_set_lanczos_threads(int threads);
 /* diagnostic: SM cycles per phase of the tensor-memory permutation kernel since the last call, summed over CTAs and windows
    (0 distance pass, 1 hand-over of the observed score, 2 shuffles, 3 membership rows, 4 contraction, 5 decisions, 6 label copy-out
    and adjacent-pair sums); synchronises the device */

@@ -131,7 +131,7 @@ void emu_css_mds_codes(const unsigned *planes, int m, const int *wleft, const in
     std::vector<double> basis((size_t)grid * fpt_lanczos_cap(m) * m + 1);
     double *pb = basis.data();
     run_grid(grid, threads, fpt_lanczos_smem_bytes(m, 0), [=]() {
-        fpt_css_mds_codes_kernel(pc, stride, m, wleft, wright, nwin, pb, X, evals, status, steps);
+        fpt_css_mds_codes_kernel<512>(pc, stride, m, wleft, wright, nwin, pb, X, evals, status, steps);
     });
 }
 
