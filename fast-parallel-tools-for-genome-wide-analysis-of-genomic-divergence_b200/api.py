@@ -41,7 +41,8 @@ def get_perm_mode():
 
 
 def set_lanczos_form(max_form):
-    """Large-cohort MDS: highest matrix form the Lanczos product may stream (2 8-bit / 1 16-bit count codes, 0 fp64 matrix)."""
+    """Large-cohort MDS: highest matrix form the Lanczos product may stream (3 8-bit codes + blank list, 2 8-bit codes through a
+    table, 1 16-bit count codes, 0 fp64 matrix)."""
     _lib.load().fpt_set_lanczos_form(int(max_form))
 
 

@@ -43,8 +43,8 @@ static thread_local char g_err[512] = "";
    a setter racing a scan in another thread affects the next call, never the kernel route of a call in flight. */
 static std::atomic<uint64_t> g_seed{20261018ULL};
 static std::atomic<int> g_device{-1};           /* -1: whatever device is current */
-static std::atomic<int> g_lanczos_form{2};      /* large-cohort MDS: highest product form allowed (2 8-bit codes, 1 16-bit codes, 0 fp64 matrix) */
-static std::atomic<int> g_lanczos_threads{512};  /* large-cohort MDS on count codes: threads per CTA (512 or 384) */
+static std::atomic<int> g_lanczos_form{3};      /* large-cohort MDS: highest product form allowed (3 8-bit codes with arithmetic squares + blank list, 2 8-bit codes through the table, 1 16-bit codes, 0 fp64 matrix) */
+static std::atomic<int> g_lanczos_threads{256};  /* large-cohort MDS on count codes: threads per CTA (512 or 384) */
 static std::atomic<int> g_perm_umma{1};         /* large cohorts: 1 = tcgen05 permutation kernel, 0 = the general (mma.sync) kernel */
 static std::atomic<int> g_perm_chain{0};        /* CSS label shuffles: 0 = independent per permutation, 1 = the reference's chain */
 static std::atomic<int> g_perm_small{1};        /* cohorts of 8..64, independent shuffles: 1 = fpt_css_perm3_kernel, 0 = the round-1 kernel (fpt_css_perm2_kernel) */
@@ -297,10 +297,10 @@ extern "C" int fpt_set_device(int device) {
 extern "C" void fpt_set_perm_mode(int chain) { g_perm_chain.store(chain != 0); }
 extern "C" int fpt_get_perm_mode(void) { return g_perm_chain.load(); }
 extern "C" void fpt_set_perm_large_kernel(int tensor_memory) { g_perm_umma.store(tensor_memory); }
-extern "C" void fpt_set_lanczos_form(int max_form) { g_lanczos_form.store(max_form < 0 ? 0 : (max_form > 2 ? 2 : max_form)); }
+extern "C" void fpt_set_lanczos_form(int max_form) { g_lanczos_form.store(max_form < 0 ? 0 : (max_form > 3 ? 3 : max_form)); }
 extern "C" void fpt_set_perm_small_kernel(int v) { g_perm_small.store(v != 0); }
 extern "C" void fpt_set_mds_small_kernel(int v) { g_mds_small.store(v != 0); }
-extern "C" void fpt_set_lanczos_threads(int threads) { g_lanczos_threads.store(threads == 384 ? 384 : 512); }
+extern "C" void fpt_set_lanczos_threads(int threads) { g_lanczos_threads.store(threads == 384 || threads == 256 ? threads : 512); }
 extern "C" void fpt_set_k4_mode(int mode) { g_k4_mode.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode)); }
 extern "C" int fpt_debug_k4_phases(unsigned long long *out4) {
     unsigned long long zero[4] = { 0 };
@@ -596,7 +596,7 @@ static CssWorkspace css_carve(const CssPlan &p, long long nwin, int mds, unsigne
        basis per CTA) are never live together (SMACOF's matrices are used after classical MDS is done): one region */
     const size_t legacy_g = need_g ? (size_t)p.max_ctas * fpt_css_mats_doubles(p.m) * 8 : 0;
     const size_t codes_b = p.mds_warps == 0 ? (size_t)std::min<long long>(nwin, FPT_K4_BATCH) * fpt_k4_window_stride(p.m) : 0;
-    const size_t basis_b = p.mds_warps == 0 ? (((size_t)p.max_ctas * fpt_lanczos_cap(p.m) * p.m * 8) + 255) & ~(size_t)255 : 0;
+    const size_t basis_b = p.mds_warps == 0 ? (size_t)p.max_ctas * fpt_lanczos_cta_scratch_bytes(p.m) : 0;
     size_t oG = take(std::max(legacy_g, codes_b + basis_b));
     size_t oP = take((size_t)p.max_ctas * p.perm_scratch_per_cta);
     const bool warp_mds = p.mds_warps > 0 && mds != 1;      /* tridiagonal + reflectors handed from phase A to phase B */
@@ -732,10 +732,18 @@ static int dev_css_windows(const Knobs &kn, const uint32_t *planes, const double
             if (code_route) {
                 const size_t stride = fpt_k4_window_stride(m);
                 const size_t smem_lz = fpt_lanczos_smem_bytes(m, 0);
-                int grid_lz;
                 const int lzt = kn.lanczos_threads;
-                if (lzt == 384) CHECK(persistent_grid(c, fpt_css_mds_codes_kernel<384>, 384, smem_lz, nwin, &grid_lz));
-                else CHECK(persistent_grid(c, fpt_css_mds_codes_kernel<512>, 512, smem_lz, nwin, &grid_lz));
+                const bool arith = kn.lanczos_form >= 3;
+                int grid_lz, grid_lza = 0;
+                if (lzt == 384) CHECK(persistent_grid(c, fpt_css_mds_codes_kernel<384, false>, 384, smem_lz, nwin, &grid_lz));
+                else if (lzt == 256) CHECK(persistent_grid(c, fpt_css_mds_codes_kernel<256, false>, 256, smem_lz, nwin, &grid_lz));
+                else CHECK(persistent_grid(c, fpt_css_mds_codes_kernel<512, false>, 512, smem_lz, nwin, &grid_lz));
+                if (arith) {
+                    if (lzt == 384) CHECK(persistent_grid(c, fpt_css_mds_codes_kernel<384, true>, 384, smem_lz, nwin, &grid_lza));
+                    else if (lzt == 256) CHECK(persistent_grid(c, fpt_css_mds_codes_kernel<256, true>, 256, smem_lz, nwin, &grid_lza));
+                    else CHECK(persistent_grid(c, fpt_css_mds_codes_kernel<512, true>, 512, smem_lz, nwin, &grid_lza));
+                    grid_lza = std::min(grid_lza, p.max_ctas);
+                }
                 grid_lz = std::min(grid_lz, p.max_ctas);
                 for (long long w0 = 0; w0 < nwin; w0 += FPT_K4_BATCH) {
                     const long long nb = std::min<long long>(FPT_K4_BATCH, nwin - w0);
@@ -753,9 +761,14 @@ static int dev_css_windows(const Knobs &kn, const uint32_t *planes, const double
                     CU(cudaGetLastError());
                     {
                         ProfScope ps_("css_mds_large", st);
-                        const int g_ = (int)std::min<long long>(grid_lz, nb);
-                        if (lzt == 384) fpt_css_mds_codes_kernel<384><<<g_, 384, smem_lz, st>>>(ws.codes, stride, m, wleft + w0, wright + w0, nb, ws.basis, ws.X + (size_t)w0 * 2 * m, ws.evals + (size_t)w0 * 3, status + w0, nullptr);
-                        else fpt_css_mds_codes_kernel<512><<<g_, 512, smem_lz, st>>>(ws.codes, stride, m, wleft + w0, wright + w0, nb, ws.basis, ws.X + (size_t)w0 * 2 * m, ws.evals + (size_t)w0 * 3, status + w0, nullptr);
+                        const int g_ = (int)std::min<long long>(grid_lz, nb), ga_ = (int)std::min<long long>(grid_lza, nb);
+                        double *X_ = ws.X + (size_t)w0 * 2 * m, *ev_ = ws.evals + (size_t)w0 * 3;
+                        /* arithmetic-product kernel first; the windows it leaves pending (more than 255 SNPs, too many blanks) go to the general one */
+#define FPT_LZ_LAUNCH(T_, A_, G_, P_) fpt_css_mds_codes_kernel<T_, A_><<<G_, T_, smem_lz, st>>>(ws.codes, stride, m, wleft + w0, wright + w0, nb, ws.basis, X_, ev_, status + w0, nullptr, P_)
+                        if (arith) { if (lzt == 384) FPT_LZ_LAUNCH(384, true, ga_, 0); else if (lzt == 256) FPT_LZ_LAUNCH(256, true, ga_, 0); else FPT_LZ_LAUNCH(512, true, ga_, 0); }
+                        const int pend_ = arith ? 1 : 0;
+                        if (lzt == 384) FPT_LZ_LAUNCH(384, false, g_, pend_); else if (lzt == 256) FPT_LZ_LAUNCH(256, false, g_, pend_); else FPT_LZ_LAUNCH(512, false, g_, pend_);
+#undef FPT_LZ_LAUNCH
                     }
                     CU(cudaGetLastError());
                 }

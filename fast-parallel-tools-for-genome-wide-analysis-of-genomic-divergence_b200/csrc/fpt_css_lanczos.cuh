@@ -48,6 +48,7 @@ struct FptLanczosSmem {
     double *h;        /* cap: projections on the basis */
     double *rmean;    /* m */
     double *lut;      /* 256: S(code) of the 8-bit code form */
+    int *zoff;        /* m + 1: row offsets into the list of blank (code 0) entries, arithmetic form of the product */
     FptEigWork ew;    /* tridiagonal eigen-solve of order <= cap, warp 0 */
     FptCssScratch sc; /* reductions + bit-plane words of the dissimilarity stage */
 };
@@ -56,7 +57,16 @@ FPT_HD size_t fpt_lanczos_smem_bytes(int m, int wch) {
     const int cap = fpt_lanczos_cap(m);
     size_t off = (size_t)(3 * m + 16) * 8 + 256 * 8 + (size_t)3 * cap * 8 + (size_t)13 * cap * 8 + 66 * 8;
     off = (off + 15) & ~(size_t)15;
+    off += ((size_t)(m + 1) * 4 + 15) & ~(size_t)15;
     return off + (size_t)wch * 2 * m * 4;
+}
+
+/* capacity of the per-CTA list of blank entries (column indices, row by row): windows with more blanks than that stream their
+   squares through the table form of the product instead */
+FPT_HD size_t fpt_lanczos_zcap(int m) { return (size_t)16 * m; }
+/* global scratch per CTA of the code route: the Lanczos basis, then the blank list */
+FPT_HD size_t fpt_lanczos_cta_scratch_bytes(int m) {
+    return (((size_t)fpt_lanczos_cap(m) * m * 8 + fpt_lanczos_zcap(m) * 4) + 255) & ~(size_t)255;
 }
 
 FPT_D FptLanczosSmem fpt_lanczos_carve(unsigned char *smem, int m, int wch) {
@@ -76,6 +86,8 @@ FPT_D FptLanczosSmem fpt_lanczos_carve(unsigned char *smem, int m, int wch) {
     s.sc.redi = (long long *)p; p += 33;
     size_t off = (size_t)((unsigned char *)p - smem);
     off = (off + 15) & ~(size_t)15;
+    s.zoff = (int *)(smem + off);
+    off += ((size_t)(m + 1) * 4 + 15) & ~(size_t)15;
     s.sc.wbuf = (unsigned *)(smem + off);
     s.sc.wch = wch;
     s.sc.pairs = 0;
@@ -113,9 +125,9 @@ FPT_D void fpt_cta_symv(const double *__restrict__ B, int m, const double *x, do
    The integer c^2 becomes a double by the 2^52 trick (one fp64 add instead of a conversion instruction). A warp per row,
    ROWS rows in flight (eight with 8-bit codes: 2 KB of loads outstanding per warp), each lane one 8-byte load of consecutive codes: four 16-bit ones (m % 4 == 0) or, when no count exceeds
    255, eight 8-bit ones (m % 8 == 0). sx = 1'x and rx = r'x are given. */
-template <typename CodeT, int ROWS, bool LUT>
+template <typename CodeT, int ROWS, bool LUT, bool ZLIST>
 FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, int ld, const double *x, double *y, const double *rmean,
-                              double g, double v2, double sx, double rx, const double *lut) {
+                              double g, double v2, double sx, double rx, const double *lut, const int *zoff, const int *zlist) {
     constexpr int PER = 8 / (int)sizeof(CodeT);                 /* codes per 8-byte load: 4 or 8 */
     constexpr int BITS = 8 * (int)sizeof(CodeT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -165,7 +177,14 @@ FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, int ld, const 
                     for (int r = 0; r < ROWS; r++) {
                         const unsigned word = ((k + kk) * BITS) < 32 ? cc[r].x : cc[r].y;
                         const unsigned c = (word >> (((k + kk) * BITS) & 31)) & ((1u << BITS) - 1u);
-                        if (LUT) {
+                        if (ZLIST) {
+                            /* arithmetic form: c^2 lands in the mantissa of 2^52 by ONE wide multiply-add (IMAD.WIDE with the
+                               exponent pattern as the addend), one fp64 add removes the 2^52; blanks contribute nothing here —
+                               their fill value is added per row from the blank list below. No shared-memory traffic per element
+                               (ncu of the table form: the table look-ups keep the shared-memory pipe 56 % busy). */
+                            const unsigned long long t52 = (unsigned long long)c * c + 0x4330000000000000ULL;
+                            acc[r] = fma(__longlong_as_double((long long)t52) - 4503599627370496.0, xk, acc[r]);
+                        } else if (LUT) {
                             /* 8-bit codes: S(c) from a 256-entry shared-memory table (c^2, or v2 for c = 0) — one load instead
                                of a multiply, the 2^52 conversion add, a compare and two selects per element */
                             acc[r] = fma(lut[c], xk, acc[r]);
@@ -181,7 +200,26 @@ FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, int ld, const 
             const int nr = m - i < ROWS ? m - i : ROWS;
 #pragma unroll
             for (int r = 0; r < ROWS; r++) acc[r] = fpt_warp_sum(acc[r]);
-            if (lane == 0) {
+            if (ZLIST) {
+                /* lane r finishes row i + r: the sum of x over the row's blank columns (the diagonal at least) times the fill value */
+                const int zb = lane < nr ? zoff[i + lane] : 0, zl = lane < nr ? zoff[i + lane + 1] - zb : 0;
+                double zc = 0.0;
+                if (__all_sync(FPT_FULL_MASK, zl <= 4)) {
+                    for (int t = 0; t < zl; t++) zc += x[zlist[zb + t]];
+                } else {
+                    for (int r = 0; r < nr; r++) {
+                        const int b = __shfl_sync(FPT_FULL_MASK, zb, r), l = __shfl_sync(FPT_FULL_MASK, zl, r);
+                        double part = 0.0;
+                        for (int t = lane; t < l; t += 32) part += x[zlist[b + t]];
+                        part = fpt_warp_sum(part);
+                        if (lane == r) zc = part;
+                    }
+                }
+                double mine = 0.0;
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) if (lane == r) mine = acc[r];
+                if (lane < nr) y[i + lane] = -0.5 * ((((mine + v2 * zc) - rmean[i + lane] * sx) - rx) + g * sx);
+            } else if (lane == 0) {
 #pragma unroll
                 for (int r = 0; r < ROWS; r++)
                     if (r < nr) y[i + r] = -0.5 * (((acc[r] - rmean[i + r] * sx) - rx) + g * sx);
@@ -233,10 +271,14 @@ struct FptLzMatrix {
     int form, ld;
     const void *data;
     double g, v2;
+    const int *zlist;     /* form 2 only: non-null = arithmetic squares + the blank list (row offsets in FptLanczosSmem::zoff) */
 };
 
 /* Lanczos with full re-orthogonalisation on B (given as FptLzMatrix; s.rmean holds the row means of S for the code forms);
-   Q (>= cap x m doubles, global) receives the basis. X: 2m doubles written by the CTA; evals3 optional. All threads take part. */
+   Q (>= cap x m doubles, global) receives the basis. X: 2m doubles written by the CTA; evals3 optional. All threads take part.
+   PRODUCT 3: only the arithmetic 8-bit product is compiled in (M.form == 2 with a blank list) — the kernel that carries it holds
+   one hot loop and keeps it in registers; PRODUCT 0: table, 16-bit and fp64 products, chosen per window from M.form. */
+template <int PRODUCT>
 FPT_D void fpt_lanczos_iterate(const FptLzMatrix &M, double *Q, int m, double *X, double *evals3, const FptLanczosSmem &s, int *steps_out) {
     const int T = blockDim.x, tid = threadIdx.x;
     const int cap = fpt_lanczos_cap(m);
@@ -249,7 +291,7 @@ FPT_D void fpt_lanczos_iterate(const FptLzMatrix &M, double *Q, int m, double *X
     const double *A = reinterpret_cast<const double *>(M.data);
     const double g = M.g, v2 = M.v2;
     for (int e = tid; e < 16; e += T) s.q[m + e] = 0.0;
-    if (narrow) for (int e = tid; e < 256; e += T) s.lut[e] = e ? (double)(e * e) : v2;
+    if (PRODUCT != 3 && narrow) for (int e = tid; e < 256; e += T) s.lut[e] = e ? (double)(e * e) : v2;
     /* ---- 2. Lanczos. Start vector: fixed pseudo-random signs and magnitudes (any vector with a component along the
        leading eigenvectors works; a fixed one keeps runs reproducible) */
     double nn = 0.0;
@@ -273,9 +315,10 @@ FPT_D void fpt_lanczos_iterate(const FptLzMatrix &M, double *Q, int m, double *X
             for (int e = tid; e < m; e += T) { const double v = s.q[e]; sx += v; rx += s.rmean[e] * v; }
             sx = fpt_block_sum(sx, s.sc.red);
             rx = fpt_block_sum(rx, s.sc.red);
-            if (narrow) fpt_cta_symv_codes<unsigned char, 8, true>(codes8, m, M.ld, s.q, s.w, s.rmean, g, v2, sx, rx, s.lut);
-            else fpt_cta_symv_codes<unsigned short, 4, false>(codes, m, M.ld, s.q, s.w, s.rmean, g, v2, sx, rx, s.lut);
-        } else {
+            if (PRODUCT == 3) fpt_cta_symv_codes<unsigned char, 8, false, true>(codes8, m, M.ld, s.q, s.w, s.rmean, g, v2, sx, rx, s.lut, s.zoff, M.zlist);
+            else if (narrow) fpt_cta_symv_codes<unsigned char, 8, true, false>(codes8, m, M.ld, s.q, s.w, s.rmean, g, v2, sx, rx, s.lut, nullptr, nullptr);
+            else fpt_cta_symv_codes<unsigned short, 4, false, false>(codes, m, M.ld, s.q, s.w, s.rmean, g, v2, sx, rx, s.lut, nullptr, nullptr);
+        } else if (PRODUCT != 3) {
             fpt_cta_symv(A, m, s.q, s.w);
         }
         FPT_LZ_MARK(2);
@@ -456,30 +499,38 @@ FPT_D void fpt_css_cmds_lanczos(double *A, double *Q, int m, double *X, double *
     __syncthreads();
     FPT_LZ_MARK(1);
     FptLzMatrix M;
-    M.form = form; M.ld = m; M.data = A; M.g = g; M.v2 = v2;
-    fpt_lanczos_iterate(M, Q, m, X, evals3, s, steps_out);
+    M.form = form; M.ld = m; M.data = A; M.g = g; M.v2 = v2; M.zlist = nullptr;
+    fpt_lanczos_iterate<0>(M, Q, m, X, evals3, s, steps_out);
 }
 
 /* Large cohorts, default route. The window's count codes were written by fpt_css_k4_umma_kernel / fpt_css_k4_popc_kernel
    (fpt_css_k4.cuh); here fill_averages (css.c:337-366) and the double centring of cmds (css.c:505-531) are derived from them in
    integers — blanks = codes 0, their replacement = (sum of the counts) / m^2, row sums of squares exact — and the Lanczos
-   iteration streams the codes. basis: per CTA fpt_lanczos_cap(m) x m doubles. THREADS: 512 (64 registers per thread) or 384 (80:
+   iteration streams the codes. ARITH = true: the kernel of the arithmetic product — windows of at most 255 SNPs whose blank entries fit
+   the list; any other window is marked FPT_WIN_PENDING for a second launch with ARITH = false, only_pending = 1 (table / 16-bit
+   products). basis: per CTA fpt_lanczos_cta_scratch_bytes(m). THREADS: 512 (64 registers per thread) or 384 (80:
    room for the software-pipelined loads of the product without spills); two CTAs per SM either way. */
-template <int THREADS>
+#define FPT_WIN_PENDING 3     /* code route, between its two kernels: left by the arithmetic kernel for the table / 16-bit kernel */
+
+template <int THREADS, bool ARITH>
 __global__ void __launch_bounds__(THREADS, 2)
 fpt_css_mds_codes_kernel(const unsigned char *__restrict__ codes, size_t stride, int m, const int *__restrict__ wleft,
                          const int *__restrict__ wright, long long nwin, double *__restrict__ basis, double *__restrict__ Xout,
-                         double *__restrict__ evals_out, unsigned char *__restrict__ status, int *__restrict__ steps_out) {
+                         double *__restrict__ evals_out, unsigned char *__restrict__ status, int *__restrict__ steps_out,
+                         int only_pending) {
     FPT_DYN_SMEM(smem);
     const FptLanczosSmem s = fpt_lanczos_carve(smem, m, 0);
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     const int ld = (m + 15) & ~15;
-    double *Q = basis + (size_t)blockIdx.x * fpt_lanczos_cap(m) * m;
+    double *Q = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(basis) + (size_t)blockIdx.x * fpt_lanczos_cta_scratch_bytes(m));
+    int *zlist = reinterpret_cast<int *>(Q + (size_t)fpt_lanczos_cap(m) * m);
     for (long long w = blockIdx.x; w < nwin; w += gridDim.x) {
+        if (!ARITH && only_pending && status[w] != FPT_WIN_PENDING) continue;
         const int l = wleft[w], r = wright[w];
         if (r <= l) { if (tid == 0) status[w] = FPT_WIN_EMPTY; continue; }
         FPT_LZ_START();
         const int wide = (r - l) > 255;                           /* two-byte codes (fpt_k4_code_bytes) */
+        if (ARITH && wide) { if (tid == 0) status[w] = FPT_WIN_PENDING; continue; }
         const unsigned char *c8 = codes + (size_t)w * stride;
         const unsigned short *c16 = reinterpret_cast<const unsigned short *>(c8);
         long long blanks = 0, total = 0;
@@ -524,10 +575,48 @@ fpt_css_mds_codes_kernel(const unsigned char *__restrict__ codes, size_t stride,
         double g = 0.0;
         for (int i = tid; i < m; i += T) g += s.rmean[i];
         g = fpt_block_sum(g, s.sc.red) / m;
+        /* the blank entries (code 0, the diagonal among them) as a list of column indices, row by row in column order: the
+           arithmetic form of the product skips them and adds their fill value per row. One more pass over the codes. */
+        const bool zl_on = ARITH && blanks <= (long long)fpt_lanczos_zcap(m);
+        if (ARITH && !zl_on) { if (tid == 0) status[w] = FPT_WIN_PENDING; __syncthreads(); continue; }
+        if (zl_on) {
+            if (warp == 0) {                                          /* exclusive scan of the rows' blank counts (s.w) */
+                const int per = (m + 31) >> 5, b0 = lane * per, b1 = min(m, b0 + per);
+                int loc = 0;
+                for (int i = b0; i < b1; i++) loc += (int)s.w[i];
+                int inc = loc;
+                for (int o = 1; o < 32; o <<= 1) { const int yv = __shfl_up_sync(FPT_FULL_MASK, inc, o); if (lane >= o) inc += yv; }
+                int run = inc - loc;
+                for (int i = b0; i < b1; i++) { s.zoff[i] = run; run += (int)s.w[i]; }
+                if (lane == 31) s.zoff[m] = inc;
+            }
+            __syncthreads();
+            for (int i = warp; i < m; i += nwarp) {
+                int base = s.zoff[i];
+                for (int j0 = 0; j0 < m; j0 += 512) {
+                    const int j = j0 + 16 * lane;
+                    unsigned zmask = 0u;
+                    if (j < m) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(c8 + (size_t)i * ld + j);
+                        const unsigned ww[4] = { v.x, v.y, v.z, v.w };
+                        const int valid = min(16, m - j);
+#pragma unroll
+                        for (int k = 0; k < 16; k++) if (k < valid && ((ww[k >> 2] >> (8 * (k & 3))) & 0xffu) == 0u) zmask |= 1u << k;
+                    }
+                    const int cntl = __popc(zmask);
+                    int inc = cntl;
+                    for (int o = 1; o < 32; o <<= 1) { const int yv = __shfl_up_sync(FPT_FULL_MASK, inc, o); if (lane >= o) inc += yv; }
+                    int at = base + inc - cntl;
+                    while (zmask) { const int k = __ffs((int)zmask) - 1; zmask &= zmask - 1u; zlist[at++] = j + k; }
+                    base += __shfl_sync(FPT_FULL_MASK, inc, 31);
+                }
+            }
+            __syncthreads();
+        }
         FPT_LZ_MARK(1);
         FptLzMatrix M;
-        M.form = wide ? 1 : 2; M.ld = ld; M.data = c8; M.g = g; M.v2 = v2;
-        fpt_lanczos_iterate(M, Q, m, Xout + (size_t)w * 2 * m, evals_out ? evals_out + 3 * w : 0, s, steps_out ? steps_out + w : 0);
+        M.form = wide ? 1 : 2; M.ld = ld; M.data = c8; M.g = g; M.v2 = v2; M.zlist = zl_on ? zlist : nullptr;
+        fpt_lanczos_iterate<ARITH ? 3 : 0>(M, Q, m, Xout + (size_t)w * 2 * m, evals_out ? evals_out + 3 * w : 0, s, steps_out ? steps_out + w : 0);
         if (tid == 0) status[w] = FPT_WIN_SCORED;
         __syncthreads();
     }

@@ -205,20 +205,40 @@ FPT_D double fpt_log_point_prob(const FptTable &f, const double *lf) {
         __dadd_rn(__dadd_rn(__dadd_rn(lf[f.a], lf[f.b]), lf[f.c]), lf[f.d]));
 }
 
+/* 1/q for q = a product of two cell counts (1 .. 2^40: inside single-precision range): single-precision seed and two Newton steps,
+   relative error ~2^-52. The log-mode walk is not an operation-for-operation replay of anything (the reference overflows where it
+   runs): it is validated against exact rationals to 1e-9, and its `<` decisions carry a 1e-10 guard. */
+FPT_D double fpt_fet_rcp(double q) {
+#ifndef FPT_EMU
+    float r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"((float)q));
+    double r = (double)r0;
+#else
+    double r = (double)(1.0f / (float)q);
+#endif
+    r = fma(r, fma(-q, r, 1.0), r);
+    r = fma(r, fma(-q, r, 1.0), r);
+    return r;
+}
+
 FPT_D double fpt_fet_neglog10_logmode(FptTable f, const double *lf) {
     const int R1 = f.a + f.b, R2 = f.c + f.d, C1 = f.a + f.c, C2 = f.b + f.d;
     fpt_rotate_min_first(f);
     const double lp0 = fpt_log_point_prob(f, lf);
     double S = 1.0, u = 1.0;
-    while (f.a > 0) {
-        f.b++; f.c++;
-        u = __dmul_rn(fpt_ratio(f.a, f.d, f.b, f.c), u);
-        S = __dadd_rn(S, u);
-        f.a--; f.d--;
-        if (u < __dmul_rn(S, FPT_FET_TINY)) {          /* nothing further along this tail can change S */
-            f.b += f.a; f.c += f.a; f.d -= f.a; f.a = 0;
-            break;
+    {   /* first tail, towards a = 0: u_k+1 = u_k (a d) / ((b+1)(c+1)); the cells ride along as doubles (an add instead of a
+           conversion each), the division is a multiplication by the Newton reciprocal */
+        double fa = (double)f.a, fb = (double)f.b, fc = (double)f.c, fd = (double)f.d;
+        int left = f.a;
+        while (left > 0) {
+            fb += 1.0; fc += 1.0;
+            u *= (fa * fd) * fpt_fet_rcp(fb * fc);
+            S += u;
+            fa -= 1.0; fd -= 1.0; left--;
+            if (u < S * FPT_FET_TINY) break;             /* nothing further along this tail can change S */
         }
+        /* the walk ends at a = 0 either way (the skipped terms are below 2^-60 of S) */
+        f.b += f.a; f.c += f.a; f.d -= f.a; f.a = 0;
     }
     if (R1 == R2 || C1 == C2) {
         S = __dmul_rn(2.0, S);
@@ -245,12 +265,14 @@ FPT_D double fpt_fet_neglog10_logmode(FptTable f, const double *lf) {
             lu = __dsub_rn(fpt_log_point_prob(f, lf), lp0);
         }
         double u2 = exp(lu);
+        double fa = (double)f.a, fb = (double)f.b, fc = (double)f.c, fd = (double)f.d;
+        int left = min(f.b, f.c);
         while (u2 < 1.0 - FPT_FET_TIE_GUARD) {
-            S = __dadd_rn(S, u2);
-            if (f.b == 0 || f.c == 0) break;
-            f.a++; f.d++;
-            u2 = __dmul_rn(fpt_ratio(f.b, f.c, f.a, f.d), u2);
-            f.b--; f.c--;
+            S += u2;
+            if (left == 0) break;
+            fa += 1.0; fd += 1.0;
+            u2 *= (fb * fc) * fpt_fet_rcp(fa * fd);
+            fb -= 1.0; fc -= 1.0; left--;
         }
     }
     double lp = __dadd_rn(lp0, log(S));

@@ -75,8 +75,8 @@ void fpt_set_perm_small_kernel(int v);
    matrix in the registers of one warp (csrc/fpt_css_eig_reg.cuh), 0 the shared-memory kernel that serves every cohort up to the
    one-warp limit (csrc/fpt_css_eig.cuh). Results agree to rounding; the switch exists for the parity tests. */
 void fpt_set_mds_small_kernel(int v);
-/* Large-cohort MDS on count codes: threads per CTA, 512 (default) or 384 (more registers per thread for the pipelined loads of the
-   Lanczos product). Tuning aid; results are identical up to the summation order inside a warp, which does not depend on it. */
+/* Large-cohort MDS on count codes: threads per CTA — 256 (default: up to 128 registers per thread, the pipelined loads of the
+   Lanczos product stay in registers), 384 (80 registers) or 512 (64). Tuning aid; results are identical up to the summation order inside a warp, which does not depend on it. */
 void fpt_set_lanczos_threads(int threads);
 /* diagnostic: SM cycles per phase of the tensor-memory permutation kernel since the last call, summed over CTAs and windows
    (0 distance pass, 1 hand-over of the observed score, 2 shuffles, 3 membership rows, 4 contraction, 5 decisions, 6 label copy-out
@@ -86,7 +86,8 @@ int fpt_debug_umma_phases(unsigned long long *out8);
    solves, 5 norms / next vector, 6 coordinates) */
 int fpt_debug_lanczos_phases(unsigned long long *out8);
 /* Large-cohort classical MDS (csrc/fpt_css_lanczos.cuh): the highest form of the matrix the Lanczos product may stream —
-   2 (default) 8-bit count codes, 1 16-bit count codes, 0 the fp64 matrix B. Every window takes the highest form it qualifies
+   3 (default) 8-bit count codes squared arithmetically with the blank entries kept as a list, 2 8-bit count codes through a
+   shared-memory table of squares, 1 16-bit count codes, 0 the fp64 matrix B. Every window takes the highest form it qualifies
    for; lower settings exist for the parity tests. */
 void fpt_set_lanczos_form(int max_form);
 /* Large cohorts, the genotype-distance matrix D = [P|M][M|P]' (compare_all, css/css.c:277-327; csrc/fpt_css_k4.cuh): 2 (default) one

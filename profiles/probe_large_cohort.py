@@ -9,9 +9,9 @@ nwin=int(sys.argv[1]) if len(sys.argv)>1 else 148
 regend=50000*nwin
 ch=synth.chromosome_fast(3, regend, 167*nwin, asize, bsize, wstep=50000)
 lib.fpt_profile_enable(1)
-lib.fpt_set_lanczos_form(int(__import__('os').environ.get('FPT_LANCZOS_FORM', '2')))
+lib.fpt_set_lanczos_form(int(__import__('os').environ.get('FPT_LANCZOS_FORM', '3')))
 lib.fpt_set_k4_mode(int(__import__('os').environ.get('FPT_K4_MODE', '2')))
-lib.fpt_set_lanczos_threads(int(__import__('os').environ.get('FPT_LANCZOS_THREADS', '512')))
+lib.fpt_set_lanczos_threads(int(__import__('os').environ.get('FPT_LANCZOS_THREADS', '256')))
 for runs in (1000,):
     t=time.time()
     s,p,wr=api.css_scan(ch["acodes"],ch["bcodes"],ch["pos"],asize,bsize,regend,50000,50000,1000,runs,mds=0,seed=1)

@@ -137,6 +137,7 @@ static inline long long __double2ll_rn(double v) { return llrint(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
     return (unsigned long long)(((unsigned __int128)a * b) >> 64);
@@ -174,6 +175,7 @@ static inline ulonglong2 make_ulonglong2(unsigned long long a, unsigned long lon
 struct double2 { double x, y; };
 static inline int4 make_int4(int a, int b, int c, int d) { int4 r = { a, b, c, d }; return r; }
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r = { a, b, c, d }; return r; }
+static inline uint2 make_uint2(unsigned a, unsigned b) { uint2 r = { a, b }; return r; }
 static inline int2 make_int2(int a, int b) { int2 r = { a, b }; return r; }
 static inline double2 make_double2(double a, double b) { double2 r = { a, b }; return r; }
 

@@ -123,15 +123,18 @@ void emu_css_mds_large(const unsigned *planes, const double *absdiff, int m, con
 
 /* large-cohort code route: popcount count codes (fpt_css_k4.cuh), then Lanczos on the codes */
 void emu_css_mds_codes(const unsigned *planes, int m, const int *wleft, const int *wright, long long nwin, int threads, int grid,
-                       double *X, double *evals, unsigned char *status, int *steps) {
+                       double *X, double *evals, unsigned char *status, int *steps, int arithmetic) {
     const size_t stride = fpt_k4_window_stride(m);
     std::vector<unsigned char> codes((size_t)nwin * stride + 64, 0xAB);
     unsigned char *pc = codes.data();
     run_grid(grid, 64, fpt_k4_popc_smem(m), [=]() { fpt_css_k4_popc_kernel(planes, m, wleft, wright, nwin, pc, stride); });
-    std::vector<double> basis((size_t)grid * fpt_lanczos_cap(m) * m + 1);
+    std::vector<double> basis((size_t)grid * fpt_lanczos_cta_scratch_bytes(m) / 8 + 1);
     double *pb = basis.data();
     run_grid(grid, threads, fpt_lanczos_smem_bytes(m, 0), [=]() {
-        fpt_css_mds_codes_kernel<512>(pc, stride, m, wleft, wright, nwin, pb, X, evals, status, steps);
+        if (arithmetic) fpt_css_mds_codes_kernel<512, true>(pc, stride, m, wleft, wright, nwin, pb, X, evals, status, steps, 0);
+    });
+    run_grid(grid, threads, fpt_lanczos_smem_bytes(m, 0), [=]() {
+        fpt_css_mds_codes_kernel<512, false>(pc, stride, m, wleft, wright, nwin, pb, X, evals, status, steps, arithmetic);
     });
 }
 

@@ -705,7 +705,8 @@ def test_concurrent_host_calls_serialise(fpt):
 
 @pytest.mark.parametrize("asize,bsize,nsnp", [(500, 500, 600), (200, 200, 100), (152, 148, 100)])
 def test_css_large_cohort_mds_forms_agree(fpt, asize, bsize, nsnp):
-    """Large-cohort classical MDS: the Lanczos product from 8-bit count codes (m % 8 == 0), from 16-bit count codes (m % 4 == 0)
+    """Large-cohort classical MDS: the Lanczos product from 8-bit count codes squared arithmetically with the blanks as a list
+    (default), from 8-bit count codes through the table of squares (m % 8 == 0), from 16-bit count codes (m % 4 == 0)
     and from the fp64 matrix B give the same embedding up to rounding — dense windows, and sparse ones where many pairs never
     differ and take the fill value — hence the same scores to 1e-9 and the same permutation p-values."""
     from fpt_b200 import api
@@ -713,7 +714,7 @@ def test_css_large_cohort_mds_forms_agree(fpt, asize, bsize, nsnp):
     ch, _ = _synth(400 + nsnp, regend, nsnp, asize, bsize)
     out = []
     try:
-        for form in (2, 1, 0):
+        for form in (3, 2, 1, 0):
             api.set_lanczos_form(form)
             out.append(fpt.css_scan(ch["acodes"], ch["bcodes"], ch["pos"], asize, bsize, regend, wsize, wstep, 20, 100, mds=0, seed=seed, probes=True))
     finally:
