@@ -129,16 +129,32 @@ FPT_D int fpt_warp_fill(int m, const FptEigWork &w) {
     return 1;
 }
 
-/* number of eigenvalues of the tridiagonal (d, e2 = e^2) below x: negative pivots of T - xI (LAPACK dstebz scheme).
-   Works on the matrix scaled to unit norm, so every pivot is inside single-precision range for the fast reciprocal. */
+/* number of eigenvalues of the tridiagonal (d, e2 = e^2) below x = sign changes of the Sturm sequence p_0 = 1, p_1 = d_0 - x,
+   p_i+1 = (d_i - x) p_i - e_i-1^2 p_i-1 (the leading principal minors of T - xI). The determinant form needs two multiply-adds
+   and a sign test per step where the pivot form q_i = p_i / p_i-1 (LAPACK dstebz) needs a reciprocal — ncu of the eigenvector
+   kernel: 36 instructions per step in the pivot form, 47 % of the kernel. Works on the matrix scaled to unit norm (|d - x| <= 2.3,
+   e^2 <= 1: growth below 3.3 per step); the pair is rescaled every eight steps, which keeps it inside the fp64 range for any
+   sequence that does not lose 200 decades within eight steps. A minor that is exactly zero counts as a sign change and
+   continues as -1e-30 of its predecessor (the pivot form's pivmin). */
 FPT_D int fpt_sturm_count(const double *d, const double *e2, int n, double x, double pivmin) {
-    double q = d[0] - x;
-    int cnt = q < 0.0 ? 1 : 0;
+    (void)pivmin;
+    double pm = 1.0, p = d[0] - x;
+    if (p == 0.0) p = -1e-30;
+    int cnt = (int)((unsigned)__double2hiint(p) >> 31);
+    int i = 1;
     #pragma unroll 1
-    for (int i = 1; i < n; i++) {
-        if (fabs(q) < pivmin) q = -pivmin;
-        q = (d[i] - x) - e2[i - 1] * fpt_fast_rcp(q);
-        cnt += q < 0.0 ? 1 : 0;
+    while (i < n) {
+        const int stop = min(n, i + 8);
+        #pragma unroll 8
+        for (; i < stop; i++) {
+            double pn = fma(d[i] - x, p, -(e2[i - 1] * pm));
+            if (pn == 0.0) pn = -1e-30 * p;
+            cnt += (int)(((unsigned)__double2hiint(pn) ^ (unsigned)__double2hiint(p)) >> 31);
+            pm = p; p = pn;
+        }
+        const double ap = fmax(fabs(p), fabs(pm));
+        if (ap > 1e100) { p *= 1e-100; pm *= 1e-100; }
+        else if (ap < 1e-100) { p *= 1e100; pm *= 1e100; }
     }
     return cnt;
 }

@@ -143,6 +143,7 @@ static inline unsigned long long __umul64hi(unsigned long long a, unsigned long 
     return (unsigned long long)(((unsigned __int128)a * b) >> 64);
 }
 static inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8); return r; }
+static inline int __double2hiint(double d) { long long r; memcpy(&r, &d, 8); return (int)(r >> 32); }
 static inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
