@@ -213,8 +213,11 @@ def test_css_mds_kernels(emu, oracle, kernel, asize, bsize, S, L):
     assert scored >= (10 if m > 3 else 3)
 
 
-@pytest.mark.parametrize("route", ["legacy", "codes", "codes_table"])
-@pytest.mark.parametrize("shape", [(6, 5, 220, 20000), (30, 34, 260, 12000), (1, 1, 60, 6000), (9, 8, 3000, 12000)])
+_LARGE_SHAPES = [(6, 5, 220, 20000), (30, 34, 170, 7000), (1, 1, 60, 6000), (9, 8, 3000, 12000)]
+
+
+@pytest.mark.parametrize("shape,route", [(sh, r) for sh in _LARGE_SHAPES for r in ("legacy", "codes", "codes_table")
+                                         if not (r == "codes_table" and sh[0] in (30, 1))])
 def test_css_mds_large_cohort_kernel(emu, oracle, shape, route):
     """the Lanczos kernel used beyond the one-warp path, run here on small and medium cohorts (it is size-agnostic): early
     stop by the residual test (m = 64), complete Krylov space (m = 11, 2), windows discarded by fill_averages"""
