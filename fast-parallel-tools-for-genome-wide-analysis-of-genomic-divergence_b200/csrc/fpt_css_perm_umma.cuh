@@ -32,6 +32,7 @@
 #define FPT_UMMA_KC 128                    /* bytes of K per ring stage */
 #define FPT_UMMA_STAGE (FPT_UMMA_NT * FPT_UMMA_KC)
 #define FPT_UMMA_DIGITS 4
+#define FPT_UMMA_LRING (2 * FPT_UMMA_BATCH) /* label rows kept in the CTA's global scratch: shuffle rounds run ahead of the batches */
 
 FPT_HD int fpt_umma_kp(int m) { return ((m + FPT_UMMA_KC - 1) / FPT_UMMA_KC) * FPT_UMMA_KC; }
 FPT_HD int fpt_umma_np(int m) { return ((m + FPT_UMMA_NT - 1) / FPT_UMMA_NT) * FPT_UMMA_NT; }
@@ -40,7 +41,7 @@ FPT_HD int fpt_umma_rbytes(int m) { return (int)((((size_t)m * 2 + 3) >> 2) | 1)
 /* per-CTA global scratch: digit matrices in tile layout, label rows of one batch */
 FPT_HD size_t fpt_umma_scratch_bytes(int m) {
     size_t b = (size_t)FPT_UMMA_DIGITS * fpt_umma_np(m) * fpt_umma_kp(m);
-    b += ((size_t)FPT_UMMA_BATCH * m * 2 + 255) & ~(size_t)255;
+    b += ((size_t)FPT_UMMA_LRING * m * 2 + 255) & ~(size_t)255;
     return b;
 }
 FPT_HD size_t fpt_umma_smem_bytes(int m) {
@@ -48,7 +49,7 @@ FPT_HD size_t fpt_umma_smem_bytes(int m) {
     off += (size_t)FPT_UMMA_BATCH * fpt_umma_kp(m) + 2 * FPT_UMMA_STAGE;
     off += (size_t)2 * m * 8;                                   /* X */
     off += (size_t)(m + 1) * 8;                                 /* per-n (limit, magic) of the shuffle draws */
-    off += (size_t)2 * FPT_UMMA_BATCH * 8;                      /* adjacent-pair sums */
+    off += (size_t)2 * FPT_UMMA_LRING * 8;                      /* adjacent-pair sums */
     off += (size_t)(FPT_UMMA_THREADS / 32) * 32 * 8;            /* per-warp staging of the exact re-scoring */
     off += (size_t)FPT_UMMA_BATCH * 4 + 33 * 4 + 16;            /* hits, scan */
     return (off + 15) & ~(size_t)15;
@@ -80,7 +81,7 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
     size_t off = shuf_bytes;
     double *X = (double *)(smem + off); off += (size_t)2 * m * 8;
     uint2 *rtab = (uint2 *)(smem + off); off += (size_t)(m + 1) * 8;
-    long long *wsum = (long long *)(smem + off); off += (size_t)2 * FPT_UMMA_BATCH * 8;
+    long long *wsum = (long long *)(smem + off); off += (size_t)2 * FPT_UMMA_LRING * 8;
     double *stage = (double *)(smem + off) + 32 * warp; off += (size_t)(FPT_UMMA_THREADS / 32) * 32 * 8;
     int *hit_s = (int *)(smem + off); off += (size_t)FPT_UMMA_BATCH * 4;
     int *scan = (int *)(smem + off);
@@ -89,11 +90,7 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
     unsigned short *labels = (unsigned short *)gs;
     const size_t qd_digit = (size_t)np * kp;
 
-    for (int n = tid; n <= m; n += T) {
-        uint2 lm;
-        lm.x = n > 0 ? fpt_randint_limit((uint32_t)n) : 0u; lm.y = n > 0 ? fpt_randint_magic((uint32_t)n) : 0u;
-        rtab[n] = lm;
-    }
+    for (int n = tid; n <= m; n += T) rtab[n] = fpt_umma_rtab_entry(n);
     if (tid == 0) {
         for (int s = 0; s < 2; s++) {
             fpt_mbar_init(&bar_full[s], 1); fpt_mbar_init(&bar_empty[s], 1);
@@ -195,40 +192,44 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
         const int use_a = asize <= bsize;
         const uint64_t st_win = state_override ? state_override[w] : fpt_stream_state(seed, wbase + w, FPT_STREAM_RESAMPLE);
         const int draws = m - 1;
-        int hits = 0, ndone = 0;
+        int hits = 0, ndone = 0, produced = 0;                 /* produced: permutations shuffled so far (ring rows written) */
         bool stopped = false;
         while (!stopped && hits < treshold && ndone < runs) {
             const int nvalid = min(FPT_UMMA_BATCH, runs - ndone);
             /* independent shuffles: permutation k starts k (m-1) draws into the window's stream. Random swaps want shared
-               memory: as many label rows at a time as the tile space holds, copied out to the batch's global rows. */
-            for (int base = 0; base < nvalid; base += rows_fit) {
-                const int nb = min(rows_fit, nvalid - base);
+               memory: as many label rows at a time as the tile space holds (98 at m = 1000), copied out to a ring of 256 rows
+               in global memory. A round is one dependent chain of m - 1 swaps whatever the number of rows, so the rounds are
+               always full and run ahead of the batches: 11 rounds per 1000 permutations, not two per batch of 128. */
+            while (produced < ndone + nvalid) {
+                const int nb = min(rows_fit, runs - produced);
                 /* one row per thread on the first warps: consecutive lanes on consecutive rows (an odd word count apart: no
                    bank conflicts on equal indices), full warps so that the chain's instructions are issued once per 32 rows */
                 const int myrow = tid;
-                if (myrow < nb)
-                    fpt_umma_shuffle(reinterpret_cast<unsigned short *>(tileA + (size_t)myrow * rbytes), m, rtab,
-                                     fpt_lcg_skip(st_win, (uint64_t)(ndone + base + myrow) * (uint64_t)draws));
-                __syncthreads();
-                FPT_UMMA_MARK(2);
-                /* one warp per row: labels out to the batch's global rows, and the two adjacent-pair sums of the surrogate
-                   from the embedding itself (the same quantised values the distance pass stores, no gathers) */
-                for (int rr = warp; rr < nb; rr += T >> 5) {
-                    const unsigned short *row = reinterpret_cast<const unsigned short *>(tileA + (size_t)rr * rbytes);
-                    unsigned short *orow = labels + (size_t)(base + rr) * m;
+                if (myrow < nb) {
                     long long sa = 0, sb = 0;
-#pragma unroll 4
-                    for (int col = lane; col < m; col += 32) {
-                        const int c = row[col], pc = row[col > 0 ? col - 1 : 0];
-                        orow[col] = (unsigned short)c;
-                        const long long qv = use_surrogate ? (long long)fpt_umma_q(X, c, pc, S) : 0;
-                        sa += (col != 0 && col < asize) ? qv : 0;
-                        sb += (col > asize) ? qv : 0;
-                    }
-                    for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(FPT_FULL_MASK, sa, o); sb += __shfl_xor_sync(FPT_FULL_MASK, sb, o); }
-                    if (lane == 0) { wsum[base + rr] = sa; wsum[FPT_UMMA_BATCH + base + rr] = sb; }
+                    fpt_umma_shuffle(reinterpret_cast<unsigned short *>(tileA + (size_t)myrow * rbytes), m, rtab,
+                                     fpt_lcg_skip(st_win, (uint64_t)(produced + myrow) * (uint64_t)draws), use_surrogate, X, S, asize, &sa, &sb);
+                    const int slot = (produced + myrow) & (FPT_UMMA_LRING - 1);
+                    wsum[slot] = sa; wsum[FPT_UMMA_LRING + slot] = sb;
                 }
                 __syncthreads();
+                FPT_UMMA_MARK(2);
+                /* labels out to the ring's global rows, one warp per row, a 32-bit word (two labels) per lane and trip */
+                for (int rr = warp; rr < nb; rr += T >> 5) {
+                    const unsigned short *row = reinterpret_cast<const unsigned short *>(tileA + (size_t)rr * rbytes);
+                    unsigned short *orow = labels + (size_t)((produced + rr) & (FPT_UMMA_LRING - 1)) * m;
+                    if ((m & 1) == 0) {
+                        const uint32_t *rw = reinterpret_cast<const uint32_t *>(row);
+                        uint32_t *ow = reinterpret_cast<uint32_t *>(orow);
+#pragma unroll 4
+                        for (int e = lane; e < (m >> 1); e += 32) ow[e] = rw[e];
+                    } else {
+                        for (int col = lane; col < m; col += 32) orow[col] = row[col];
+                    }
+                }
+                __syncthreads();
+                FPT_UMMA_MARK(6);
+                produced += nb;
             }
             FPT_UMMA_MARK(6);
             /* membership rows of the smaller group (the A operand): one sweep over its labels, a byte store each */
@@ -244,7 +245,7 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
                     for (int u = 0; u < 8; u++) {
                         const int e = e0 + u * T;
                         pp[u] = e < total ? e / cnt : -1;
-                        cc[u] = e < total ? (int)labels[(size_t)pp[u] * m + lo + (e - pp[u] * cnt)] : 0;
+                        cc[u] = e < total ? (int)labels[(size_t)((ndone + pp[u]) & (FPT_UMMA_LRING - 1)) * m + lo + (e - pp[u] * cnt)] : 0;
                     }
 #pragma unroll
                     for (int u = 0; u < 8; u++)
@@ -330,7 +331,8 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
                     long long bet = 0;
 #pragma unroll
                     for (int d = FPT_UMMA_DIGITS; d--;) bet = (bet << 8) + (long long)acc[d];
-                    const double approx = (double)bet * c_bet - (a_ + b_) * ((double)wsum[p] * c_wa + (double)wsum[FPT_UMMA_BATCH + p] * c_wb);
+                    const int pslot = (ndone + p) & (FPT_UMMA_LRING - 1);
+                    const double approx = (double)bet * c_bet - (a_ + b_) * ((double)wsum[pslot] * c_wa + (double)wsum[FPT_UMMA_LRING + pslot] * c_wb);
                     const double diff = approx - score;
                     int hit = diff > 0.0;
                     /* within E of the observed score: the whole warp re-scores that permutation in the reference's order */
@@ -338,14 +340,14 @@ fpt_css_perm_umma_kernel(const double *__restrict__ Xall, int m, int asize, int 
                     while (need) {
                         const int src = __ffs(need) - 1;
                         need &= need - 1;
-                        const double sc = fpt_warp_css_score(X, stage, labels + (size_t)(wq * 32 + src) * m, asize, bsize, lane);
+                        const double sc = fpt_warp_css_score(X, stage, labels + (size_t)((ndone + wq * 32 + src) & (FPT_UMMA_LRING - 1)) * m, asize, bsize, lane);
                         if (lane == src) { hit = sc >= score ? 1 : 0; rechecks++; }
                     }
                     if (p < nvalid) hit_s[p] = hit;
                 }
             } else {                                            /* no surrogate (NaN embedding ...): every permutation exactly */
                 for (int p = warp; p < nvalid; p += T >> 5) {
-                    const double sc = fpt_warp_css_score(X, stage, labels + (size_t)p * m, asize, bsize, lane);
+                    const double sc = fpt_warp_css_score(X, stage, labels + (size_t)((ndone + p) & (FPT_UMMA_LRING - 1)) * m, asize, bsize, lane);
                     if (lane == 0) hit_s[p] = sc >= score ? 1 : 0;
                 }
             }

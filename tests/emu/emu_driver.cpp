@@ -290,6 +290,9 @@ void emu_umma_shuffle_and_score(const double *X, int m, int asize, int bsize, ui
     std::vector<uint2> rtab(m + 1);
     for (int n = 0; n <= m; n++) { rtab[n].x = n > 0 ? fpt_randint_limit((uint32_t)n) : 0u; rtab[n].y = n > 0 ? fpt_randint_magic((uint32_t)n) : 0u; }
     const uint2 *rt = rtab.data();
+    std::vector<uint2> rtab_fast(m + 1);
+    for (int n = 0; n <= m; n++) rtab_fast[n] = fpt_umma_rtab_entry(n);
+    const uint2 *rtf = rtab_fast.data();
     run_grid(1, 32, 32 * 8, [=]() {
         const int lane = threadIdx.x;
         double *stage = (double *)emu::g_dyn_smem;
@@ -297,8 +300,18 @@ void emu_umma_shuffle_and_score(const double *X, int m, int asize, int bsize, ui
             const int p = p0 + lane;
             if (p < nperm) {
                 const uint64_t st = fpt_lcg_skip(state, (uint64_t)p * (uint64_t)(m - 1));
-                fpt_umma_shuffle(labels_fast + (size_t)p * m, m, rt, st);
+                long long sa = -1, sb = -1;
+                const double S = 1048576.0 / 64.0;
+                fpt_umma_shuffle(labels_fast + (size_t)p * m, m, rtf, st, true, X, S, asize, &sa, &sb);
                 fpt_generate_labels<unsigned short>(labels_ref + (size_t)p * m, m, rt, st);
+                /* the adjacent-pair sums read off the swaps against a sweep over the finished labels */
+                long long ra = 0, rb = 0;
+                const unsigned short *lf = labels_fast + (size_t)p * m;
+                for (int col = 1; col < m; col++) {
+                    const long long qv = (long long)fpt_umma_q(X, lf[col], lf[col - 1], S);
+                    if (col < asize) ra += qv; else if (col > asize) rb += qv;
+                }
+                if (ra != sa || rb != sb) labels_fast[(size_t)p * m] = 0xffff;          /* poison: the test's comparison fails */
             }
             __syncwarp();
             for (int q = p0; q < p0 + 32 && q < nperm; q++) {
