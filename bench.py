@@ -378,6 +378,19 @@ def bench_css(lib_mod, cx, full_genome_pass):
                                          "windows_scored": nsc, "smacof_iterations_total": tot_iters,
                                          "kernel_ms": {k: v["ms"] for k, v in vprof.items()}}
             del wsv
+            # the same chromosome end to end through the drop-in (pinned host float64 arrays in, host results out)
+            hav, hbv, hapos, hbpos, _ = host[0]
+            ts, hs = [], None
+            for it in range(2):
+                hs, hp = np.zeros(nout), np.zeros(nout)
+                t0 = time.perf_counter()
+                check(lib.fpt_css_compute(hav[1].ctypes.data, hbv[1].ctypes.data, hapos[1].ctypes.data, hbpos[1].ctypes.data, 0, regend,
+                                          wsize, wstep, hav[1].size, hbv[1].size, CSS["mct"], CSS["mcr"], 0, mds_v, hs.ctypes.data, hp.ctypes.data))
+                ts.append(time.perf_counter() - t0)
+            variants["mds%d" % mds_v]["e2e"] = {"value": nout / ts[-1], "unit": "windows/s", "ms_per_chromosome": ts[-1] * 1e3,
+                                                "api": "fpt_css_compute (drop-in, pinned host float64 arrays), chromosome 0",
+                                                "h2d_bytes": int(hav[1].nbytes + hbv[1].nbytes + hapos[1].nbytes + hbpos[1].nbytes), "d2h_bytes": 16 * nout}
+            variants["mds%d" % mds_v]["_scores"] = hs
 
     # end to end through the host call
     for _ in range(max(1, min(args.warmup, 2))):
@@ -761,7 +774,7 @@ def bench_large_cohort(lib_mod, cx):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
-def cpu_css(sample_windows, steps=1, warmup=0):
+def cpu_css(sample_windows, steps=1, warmup=0, mds=None):
     """the reference's own pthreads CSS (oracle/_ref/libref_css.so, 64 threads hard-wired) on a bounded sample:
     the first `sample_windows` windows of chromosome 0 of the headline workload"""
     import checkers
@@ -782,7 +795,7 @@ def cpu_css(sample_windows, steps=1, warmup=0):
         with checkers.silence_stdout():
             t0 = time.perf_counter()
             ref.threadcompute(checkers.dptr(av), checkers.dptr(bv), checkers.iptr(apos), checkers.iptr(bpos), 0, regend,
-                              CSS["wsize"], CSS["wstep"], av.size, bv.size, CSS["mct"], CSS["mcr"], 0, CSS["mds"],
+                              CSS["wsize"], CSS["wstep"], av.size, bv.size, CSS["mct"], CSS["mcr"], 0, CSS["mds"] if mds is None else mds,
                               checkers.dptr(s), checkers.dptr(p))
             dt = time.perf_counter() - t0
         if it >= warmup:
@@ -1085,9 +1098,33 @@ def main():
                                                           "same_windows_scored": bool(np.array_equal(ref_s[:n - 8] != 0, s0[:n - 8] != 0)),
                                                           "score_rel_within_1e-5": float((rel <= 1e-5).mean()) if both.any() else None,
                                                           "score_max_rel": float(rel.max()) if both.any() else None}}
+                # the other two MDS variants: the reference's threadcompute with mds = 1 / 2 on a smaller sample (SMACOF is ~10-40x the work);
+                # mds = 2 starts from classical MDS, so its scores are comparable window by window; mds = 1 starts from clock-seeded
+                # random configurations in the reference (css.c:863-864), so only its time is reported
+                for mds_v, nsamp in ((2, 3000), (1, 1200)):
+                    v = css["variants"].get("mds%d" % mds_v)
+                    if not v:
+                        continue
+                    cv = cpu_css(nsamp, mds=mds_v)
+                    if not cv:
+                        continue
+                    secv = cv["seconds"][0]
+                    e = {"value": cv["windows"] / secv, "unit": "windows/s", "cores": min(64, ncores), "threads": 64, "kind": "reference",
+                         "sample": "first %d windows of chromosome 0, reference threadcompute with mds = %d (%.1f s)" % (cv["windows"], mds_v, secv)}
+                    gs = v.get("_scores")
+                    if mds_v == 2 and gs is not None:
+                        nn = cv["windows"]
+                        rs = cv["scores"]
+                        bothv = (rs != 0) & (gs[:nn] != 0) & np.isfinite(rs)
+                        relv = np.abs(gs[:nn][bothv] - rs[bothv]) / np.maximum(np.abs(rs[bothv]), 1e-300)
+                        e["parity_vs_gpu"] = {"windows_compared": int(bothv.sum()), "score_rel_within_1e-5": float((relv <= 1e-5).mean()) if bothv.any() else None,
+                                              "score_max_rel": float(relv.max()) if bothv.any() else None}
+                    v["cpu_baseline"] = e
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "windows/s", "cores": 0, "kind": "reference",
                                         "sample": "oracle/_ref not available"}
+        for v in css["variants"].values():
+            v.pop("_scores", None)
         if fet is not None:
             prof = fet.pop("_prof")
             ns, nw = fet.pop("_ns"), fet.pop("_nw")

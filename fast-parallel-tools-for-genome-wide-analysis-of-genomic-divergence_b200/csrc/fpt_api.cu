@@ -420,8 +420,17 @@ extern "C" int fpt_dev_fet_score(const int32_t *tables, int64_t n, int max_n, in
     int lf_in_smem = lf_bytes <= 96 * 1024;
     size_t smem = FPT_BINOM_ENTRIES * sizeof(unsigned long long) + (lf_in_smem ? lf_bytes : 0);
     int grid;
-    CHECK(persistent_grid(c, fpt_fet_score_kernel, 256, smem, (n + 255) / 256, &grid));
-    { ProfScope ps_("fet_score", st); fpt_fet_score_kernel<<<grid, 256, smem, st>>>((const int4 *)tables, n, c->binom, lf, max_n, lf_in_smem, force_log, out); }
+    const size_t smem_sorted = smem + fpt_fet_sorted_smem_extra();
+    if ((max_n > FPT_FET_EXACT_MAX_N || force_log) && n >= 4 * FPT_FET_TILE && smem_sorted <= (size_t)c->smem_optin) {
+        /* tables beyond the exact domain walk for tens to hundreds of terms: sort each tile by estimated walk length first */
+        CHECK(persistent_grid(c, fpt_fet_score_sorted_kernel, FPT_FET_SORT_THREADS, smem_sorted, (n + FPT_FET_TILE - 1) / FPT_FET_TILE, &grid));
+        ProfScope ps_("fet_score", st);
+        fpt_fet_score_sorted_kernel<<<grid, FPT_FET_SORT_THREADS, smem_sorted, st>>>((const int4 *)tables, n, c->binom, lf, max_n, lf_in_smem, force_log, out);
+    } else {
+        CHECK(persistent_grid(c, fpt_fet_score_kernel, 256, smem, (n + 255) / 256, &grid));
+        ProfScope ps_("fet_score", st);
+        fpt_fet_score_kernel<<<grid, 256, smem, st>>>((const int4 *)tables, n, c->binom, lf, max_n, lf_in_smem, force_log, out);
+    }
     CU(cudaGetLastError());
     return FPT_OK;
 }

@@ -230,38 +230,45 @@ FPT_D void fpt_cta_symv_codes(const CodeT *__restrict__ C, int m, int ld, const 
     }
 }
 
-/* one classical Gram-Schmidt pass of w against the nq basis vectors Q[0..nq) (rows of length m in global memory);
-   the projections are ADDED to h so that two passes accumulate the exact coefficients */
+/* one Gram-Schmidt pass of w against the nq basis vectors Q[0..nq) (rows of length m in global memory), BLOCK by block of one
+   vector per warp: the projections of w on the block (a warp per vector), then w minus the block's share — so the second read of
+   a basis vector follows its first within microseconds and comes from L1 / L2, and the basis crosses the HBM bus once per step
+   instead of twice (the basis of 296 resident windows is ~190 MB: it does not live in L2). Between blocks this is modified
+   Gram-Schmidt, inside a block classical; the projections are ADDED to h so that two passes accumulate the exact coefficients. */
 FPT_D void fpt_cta_cgs_pass(const double *__restrict__ Q, int nq, int m, double *w, double *h, double *hpass) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int i = warp; i < nq; i += nwarp) {
-        const double *qi = Q + (size_t)i * m;
-        double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;              /* four loads in flight per lane */
-        int e = lane;
-        for (; e + 96 < m; e += 128) {
-            const double a0 = qi[e], a1 = qi[e + 32], a2 = qi[e + 64], a3 = qi[e + 96];
-            s = fma(a0, w[e], s); s1 = fma(a1, w[e + 32], s1); s2 = fma(a2, w[e + 64], s2); s3 = fma(a3, w[e + 96], s3);
+    for (int b0 = 0; b0 < nq; b0 += nwarp) {
+        const int nb = min(nwarp, nq - b0);
+        if (warp < nb) {
+            const int i = b0 + warp;
+            const double *qi = Q + (size_t)i * m;
+            double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;          /* four loads in flight per lane */
+            int e = lane;
+            for (; e + 96 < m; e += 128) {
+                const double a0 = qi[e], a1 = qi[e + 32], a2 = qi[e + 64], a3 = qi[e + 96];
+                s = fma(a0, w[e], s); s1 = fma(a1, w[e + 32], s1); s2 = fma(a2, w[e + 64], s2); s3 = fma(a3, w[e + 96], s3);
+            }
+            for (; e < m; e += 32) s = fma(qi[e], w[e], s);
+            s = fpt_warp_sum((s + s1) + (s2 + s3));
+            if (lane == 0) { hpass[i] = s; h[i] += s; }
         }
-        for (; e < m; e += 32) s = fma(qi[e], w[e], s);
-        s = fpt_warp_sum((s + s1) + (s2 + s3));
-        if (lane == 0) { hpass[i] = s; h[i] += s; }
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < m; e += blockDim.x) {
-        double acc = w[e];
-        const double *qe = Q + e;
-        int i = 0;
-        for (; i + 8 <= nq; i += 8) {                                /* eight independent loads, then the eight updates in order */
-            double v[8];
+        __syncthreads();
+        for (int e = threadIdx.x; e < m; e += blockDim.x) {
+            double acc = w[e];
+            const double *qe = Q + (size_t)b0 * m + e;
+            int u0 = 0;
+            for (; u0 + 8 <= nb; u0 += 8) {                            /* eight independent loads, then the eight updates in order */
+                double v[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = qe[(size_t)(i + u) * m];
+                for (int u = 0; u < 8; u++) v[u] = qe[(size_t)(u0 + u) * m];
 #pragma unroll
-            for (int u = 0; u < 8; u++) acc = fma(-hpass[i + u], v[u], acc);
+                for (int u = 0; u < 8; u++) acc = fma(-hpass[b0 + u0 + u], v[u], acc);
+            }
+            for (; u0 < nb; u0++) acc = fma(-hpass[b0 + u0], qe[(size_t)u0 * m], acc);
+            w[e] = acc;
         }
-        for (; i < nq; i++) acc = fma(-hpass[i], qe[(size_t)i * m], acc);
-        w[e] = acc;
+        __syncthreads();
     }
-    __syncthreads();
 }
 
 /* The matrix B = -1/2 J (D.D) J as the Lanczos product streams it: 8-bit count codes (form 2), 16-bit count codes (form 1) —

@@ -304,6 +304,109 @@ fpt_fet_score_kernel(const int4 *__restrict__ tables, long long n, const unsigne
     }
 }
 
+/* Tables at sequencing coverage (row sums up to 500 and beyond, BASELINE configs[3]): the walk takes 10 .. 400 terms per table, and at
+   one table per thread a warp waits for its longest one (host model on the benchmark tables: the longest of 32 is 1.9x the mean).
+   This kernel sorts before it walks. A CTA stages a tile of FPT_FET_TILE tables in shared memory, estimates each table's walk
+   length from the normal approximation of its hypergeometric law — both tails end where the term drops below 2^-60 of the
+   observed one, i.e. L = sigma (sqrt(z0^2 + 120 ln 2) - z0) terms away, capped by the cells — counting-sorts the tile by that
+   estimate (64 buckets of 8 terms) and hands consecutive runs of 32 to its warps: the lanes of a warp then walk tables of nearly
+   equal length (model: 1.2x), every warp gets one run from each eighth of the distribution. Scores go back through shared memory,
+   so loads and stores stay coalesced; the order inside a bucket does not matter (each score lands at its table's index). */
+#define FPT_FET_TILE 1024
+#define FPT_FET_SORT_THREADS 256
+#define FPT_FET_BUCKETS 64
+FPT_HD size_t fpt_fet_sorted_smem_extra() {
+    return (size_t)FPT_FET_TILE * 16 + (size_t)FPT_FET_TILE * 8 + (size_t)FPT_FET_TILE * 2 + (size_t)(FPT_FET_BUCKETS + 1) * 4 + 12;
+}
+
+FPT_D int fpt_fet_walk_bucket(int4 t) {
+    const float a = (float)t.x, b = (float)t.y, c = (float)t.z, d = (float)t.w;
+    const float R1 = a + b, R2 = c + d, C1 = a + c, C2 = b + d, N = R1 + R2;
+    if (!(N > 1.0f)) return 0;
+    const int a0i = min(min(t.x, t.y), min(t.z, t.w));
+    const float mu = R1 * C1 / N;
+    const float var = fmaxf(R1 * R2 / N * (C1 / N) * (C2 / (N - 1.0f)), 1e-6f);
+    const float sg = sqrtf(var), z0 = fabsf(a - mu) / sg;
+    const float L = sg * (sqrtf(z0 * z0 + 83.18f) - z0);
+    const bool towards_low = (t.x == a0i) || (t.w == a0i);          /* the first tail shrinks cell a (or d) */
+    const float lo = fmaxf(0.0f, R1 + C1 - N), hi = fminf(R1, C1);
+    const float far_ = towards_low ? hi - a : a - lo;
+    const bool sym = (R1 == R2) || (C1 == C2);
+    const float est = fminf((float)a0i, L) + (sym ? 0.0f : fminf(far_, L));
+    return min(FPT_FET_BUCKETS - 1, (int)(est * 0.125f));
+}
+
+__global__ void __launch_bounds__(FPT_FET_SORT_THREADS)
+fpt_fet_score_sorted_kernel(const int4 *__restrict__ tables, long long n, const unsigned long long *__restrict__ binom_global,
+                            const double *__restrict__ lf_global, int maxn, int lf_in_smem, int force_log,
+                            double *__restrict__ scores) {
+    FPT_DYN_SMEM(smem);
+    const int T = FPT_FET_SORT_THREADS, tid = threadIdx.x;
+    constexpr int PER = FPT_FET_TILE / FPT_FET_SORT_THREADS;
+    size_t off = 0;
+    int4 *tt = reinterpret_cast<int4 *>(smem + off); off += (size_t)FPT_FET_TILE * 16;
+    double *ts = reinterpret_cast<double *>(smem + off); off += (size_t)FPT_FET_TILE * 8;
+    unsigned long long *binom = reinterpret_cast<unsigned long long *>(smem + off); off += FPT_BINOM_ENTRIES * sizeof(unsigned long long);
+    double *lf_s = reinterpret_cast<double *>(smem + off); off += lf_in_smem ? ((size_t)maxn + 1) * 8 : 0;
+    off = (off + 3) & ~(size_t)3;
+    int *hist = reinterpret_cast<int *>(smem + off); off += (size_t)(FPT_FET_BUCKETS + 1) * 4;
+    unsigned short *perm = reinterpret_cast<unsigned short *>(smem + off);
+    for (int i = tid; i < FPT_BINOM_ENTRIES; i += T) binom[i] = binom_global[i];
+    if (lf_in_smem)
+        for (int i = tid; i <= maxn; i += T) lf_s[i] = lf_global[i];
+    const double *lf = lf_in_smem ? lf_s : lf_global;
+    const long long ntiles = (n + FPT_FET_TILE - 1) / FPT_FET_TILE;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * FPT_FET_TILE;
+        const int cnt = (int)min((long long)FPT_FET_TILE, n - base);
+        for (int b = tid; b <= FPT_FET_BUCKETS; b += T) hist[b] = 0;
+        __syncthreads();                                           /* also: the previous tile's scores have been written out */
+        int bucket[PER], rank[PER];
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int e = tid + k * T;
+            bucket[k] = 0; rank[k] = 0;
+            if (e < cnt) {
+                const int4 t = tables[base + e];
+                tt[e] = t;
+                bucket[k] = fpt_fet_walk_bucket(t);
+                rank[k] = atomicAdd(&hist[bucket[k]], 1);
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {                                            /* exclusive scan of the 64 bucket counts */
+            const int c0 = hist[2 * tid], c1 = hist[2 * tid + 1];
+            int inc = c0 + c1;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FPT_FULL_MASK, inc, o); if (tid >= o) inc += y; }
+            const int ex = inc - (c0 + c1);
+            __syncwarp();
+            hist[2 * tid] = ex; hist[2 * tid + 1] = ex + c0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int e = tid + k * T;
+            if (e < cnt) perm[hist[bucket[k]] + rank[k]] = (unsigned short)e;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int k = 0; k < PER; k++) {
+            const int pos = tid + k * T;
+            if (pos < cnt) {
+                const int e = perm[pos];
+                const int4 t = tt[e];
+                FptTable f = { t.x, t.y, t.z, t.w };
+                double P, sc;
+                if (!force_log && fpt_fet_exact(f, binom, P)) sc = __dmul_rn(-1.0, log10(P));
+                else sc = fpt_fet_neglog10_logmode(f, lf);
+                ts[e] = sc;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < cnt; e += T) scores[base + e] = ts[e];
+    }
+}
+
 /* max over all tables of N = a+b+c+d (sizes the log-factorial table for direct-table input) */
 __global__ void fpt_fet_maxn_kernel(const int4 *__restrict__ tables, long long n, int *__restrict__ out) {
     int m = 0;

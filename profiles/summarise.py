@@ -10,7 +10,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "profiles")
+OUT = os.environ.get("FPT_SUMM_OUT") or os.path.join(ROOT, "profiles")     # on the GPU box: a directory under gpurun_out/
+BASE = os.path.join(ROOT, "profiles")                                       # committed records to merge into
 SRC = os.path.join(ROOT, "gpurun_out")
 KEYS = [
     "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -27,6 +28,9 @@ KEYS = [
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
 ]
 UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
+# capture name -> the kernel label bench.py's live profile uses
+ALIAS = {"css_perm2": "css_perm", "css_perm3": "css_perm", "css_tridiag_reg": "css_tridiag", "css_mds_codes": "css_mds_large",
+         "fet_score_tables": "fet_score_log", "css_k4_umma": "css_k4"}
 
 
 def raw(rep):
@@ -37,10 +41,11 @@ def raw(rep):
 
 def main():
     tag = sys.argv[1]
+    os.makedirs(OUT, exist_ok=True)
     kernels = sys.argv[2:] or [f[5:-8] for f in sorted(os.listdir(SRC)) if f.startswith("prof_") and f.endswith(".ncu-rep")]
     md = ["# ncu summaries, round %s" % tag, "",
           "One `ncu --set full --clock-control none --import-source on` capture per kernel (one launch each), taken by",
-          "`gpurun` on a B200 from `python bench.py --chromosomes 2 --steps 1 --warmup 1 --skip-cpu`; raw metric tables in",
+          "`gpurun` on a B200 (commands: `profiles/run_%s_final.sh` / `profiles/capture.sh`); raw metric tables in" % tag,
           "`%s_<kernel>_raw.csv`. Times under ncu are serialised and cold-cache: compare shares, not absolutes." % tag, ""]
     traffic = {}
     insts = {}
@@ -65,23 +70,22 @@ def main():
         md.append("")
         try:
             rd, wr = vals["dram__bytes_read.sum"], vals["dram__bytes_write.sum"]
-            traffic[{'css_perm2': 'css_perm'}.get(k, k)] = float(rd[0].replace(",", "")) * UNIT.get(rd[1], 1.0) + float(wr[0].replace(",", "")) * UNIT.get(wr[1], 1.0)
+            traffic[ALIAS.get(k, k)] = float(rd[0].replace(",", "")) * UNIT.get(rd[1], 1.0) + float(wr[0].replace(",", "")) * UNIT.get(wr[1], 1.0)
         except Exception:
             pass
         if "smsp__inst_executed.sum" in vals:
-            insts[{'css_perm2': 'css_perm'}.get(k, k)] = float(vals["smsp__inst_executed.sum"][0].replace(",", ""))
+            insts[ALIAS.get(k, k)] = float(vals["smsp__inst_executed.sum"][0].replace(",", ""))
     with open(os.path.join(OUT, "%s_ncu_summary.md" % tag), "w") as f:
         f.write("\n".join(md) + "\n")
-    tpath = os.path.join(OUT, "ncu_traffic.json")
-    old = {}
-    if os.path.exists(tpath):
-        old = json.load(open(tpath))
+    os.makedirs(OUT, exist_ok=True)
+    tpath = os.path.join(BASE, "ncu_traffic.json")
+    old = json.load(open(tpath)) if os.path.exists(tpath) else {}
     old.update(traffic)
-    json.dump(old, open(tpath, "w"), indent=1, sort_keys=True)
-    ipath = os.path.join(OUT, "ncu_inst.json")          # warp instructions per launch, for the issue-slot roofline
+    json.dump(old, open(os.path.join(OUT, "ncu_traffic.json"), "w"), indent=1, sort_keys=True)
+    ipath = os.path.join(BASE, "ncu_inst.json")         # warp instructions per launch, for the issue-slot roofline
     old = json.load(open(ipath)) if os.path.exists(ipath) else {}
     old.update(insts)
-    json.dump(old, open(ipath, "w"), indent=1, sort_keys=True)
+    json.dump(old, open(os.path.join(OUT, "ncu_inst.json"), "w"), indent=1, sort_keys=True)
     # launch list -> per-kernel totals and shares
     for fn in sorted(os.listdir(SRC)):
         if fn.startswith("launches_%s" % tag) and fn.endswith(".csv"):

@@ -68,6 +68,18 @@ void emu_fet_score(const int *tables, long long n, int maxn, int lf_in_smem, int
     });
 }
 
+/* the tile-sorting form of the score kernel (coverage-scale tables): needs 256 threads per CTA */
+void emu_fet_score_sorted(const int *tables, long long n, int maxn, int lf_in_smem, int force_log, int grid, double *scores) {
+    std::vector<unsigned long long> binom = fpt_build_binom_table();
+    std::vector<double> lf = fpt_build_lfact_table(maxn);
+    size_t smem = FPT_BINOM_ENTRIES * 8 + (lf_in_smem ? ((size_t)maxn + 1) * 8 : 0) + fpt_fet_sorted_smem_extra();
+    const unsigned long long *bp = binom.data();
+    const double *lp = lf.data();
+    run_grid(grid, FPT_FET_SORT_THREADS, smem, [=]() {
+        fpt_fet_score_sorted_kernel((const int4 *)tables, n, bp, lp, maxn, lf_in_smem, force_log, scores);
+    });
+}
+
 int emu_fet_maxn(const int *tables, long long n) {
     int out = 0;
     int *po = &out;

@@ -89,6 +89,16 @@ def test_fet_count_and_score_kernels(emu, oracle):
     emu.emu_fet_score(iptr(T), ll(500), int(T.sum(1).max()), 0, 0, 2, dptr(se))
     # the kernel's log-mode walk multiplies by a Newton reciprocal where the oracle divides: equal to rounding
     np.testing.assert_allclose(se, so, rtol=1e-12, atol=1e-13)
+    # the tile-sorting form (ragged last tile, exact-mode and log-mode tables mixed): the same scores, bit for bit, at the same indices
+    nbig = 2 * 1024 + 77
+    n1, n2 = rng.integers(2, 501, nbig), rng.integers(2, 501, nbig)
+    f = np.clip(rng.beta(.5, .5, nbig), .02, .98)
+    a, c = rng.binomial(n1, f), rng.binomial(n2, np.clip(f + rng.normal(0, .1, nbig), .01, .99))
+    Tb = np.stack([a, n1 - a, c, n2 - c], 1).astype(np.int32).copy()
+    s_plain, s_sorted = np.zeros(nbig), np.full(nbig, -7.0)
+    emu.emu_fet_score(iptr(Tb), ll(nbig), int(Tb.sum(1).max()), 1, 0, 2, dptr(s_plain))
+    emu.emu_fet_score_sorted(iptr(Tb), ll(nbig), int(Tb.sum(1).max()), 1, 0, 2, dptr(s_sorted))
+    assert np.array_equal(s_plain, s_sorted)
 
 
 @pytest.mark.parametrize("threaded", [0, 1])
