@@ -1101,7 +1101,7 @@ def main():
                 # the other two MDS variants: the reference's threadcompute with mds = 1 / 2 on a smaller sample (SMACOF is ~10-40x the work);
                 # mds = 2 starts from classical MDS, so its scores are comparable window by window; mds = 1 starts from clock-seeded
                 # random configurations in the reference (css.c:863-864), so only its time is reported
-                for mds_v, nsamp in ((2, 3000), (1, 1200)):
+                for mds_v, nsamp in ((2, 20000), (1, 6000)):
                     v = css["variants"].get("mds%d" % mds_v)
                     if not v:
                         continue
@@ -1187,7 +1187,9 @@ def main():
                 fet_tab["cpu_baseline"] = {"value": rate, "unit": "SNPs/s", "cores": 1, "kind": "port",
                                            "sample": "%d tables of the same distribution through the oracle's log-space restatement (the reference's "
                                                      "u64 binomials overflow beyond N = 67, SURVEY Q2)" % len(Tc),
-                                           "parity_vs_gpu": {"max_rel": float(rel[oc != 0].max())}}
+                                           "parity_vs_gpu": {"max_rel_where_score_above_1e-6": float(rel[np.abs(oc) > 1e-6].max()),
+                                                             "max_abs": float(np.abs(g - oc).max()),
+                                                             "within_1e-9_rel_plus_1e-12_abs": bool(np.all(np.abs(g - oc) <= 1e-9 * np.abs(oc) + 1e-12))}}
             line["fet_tables"] = fet_tab
         if large is not None:
             prof = large.pop("_prof")

@@ -88,7 +88,7 @@ def test_fet_count_and_score_kernels(emu, oracle):
     assert emu.emu_fet_maxn(iptr(T), ll(500)) == T.sum(1).max()
     emu.emu_fet_score(iptr(T), ll(500), int(T.sum(1).max()), 0, 0, 2, dptr(se))
     # the kernel's log-mode walk multiplies by a Newton reciprocal where the oracle divides: equal to rounding
-    np.testing.assert_allclose(se, so, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(se, so, rtol=1e-10, atol=1e-12)
     # the tile-sorting form (ragged last tile, exact-mode and log-mode tables mixed): the same scores, bit for bit, at the same indices
     nbig = 2 * 1024 + 77
     n1, n2 = rng.integers(2, 501, nbig), rng.integers(2, 501, nbig)
