@@ -24,8 +24,8 @@
 #include "fpt_css_eig.cuh"
 
 /* diagnostic: SM cycles thread 0 spent per phase of the large-cohort MDS kernel, summed over CTAs and windows (0 dissimilarity,
-   1 row means + code conversion, 2 products, 3 Gram-Schmidt, 4 tridiagonal solves, 5 norms / next vector, 6 coordinates);
-   read and reset by fpt_debug_lanczos_phases() */
+   1 row means + code conversion, 2 products, 3 Gram-Schmidt, 4 tridiagonal solves, 5 norms / next vector, 6 coordinates; slot 7
+   counts Lanczos steps over all windows); read and reset by fpt_debug_lanczos_phases() */
 #ifndef FPT_EMU
 __device__ unsigned long long fpt_lanczos_phase_cycles[8];
 #define FPT_LZ_MARK(slot) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&fpt_lanczos_phase_cycles[slot], (unsigned long long)(now_ - lz_mark)); lz_mark = now_; } } while (0)
@@ -242,13 +242,23 @@ FPT_D void fpt_cta_cgs_pass(const double *__restrict__ Q, int nq, int m, double 
         if (warp < nb) {
             const int i = b0 + warp;
             const double *qi = Q + (size_t)i * m;
-            double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;          /* four loads in flight per lane */
-            int e = lane;
-            for (; e + 96 < m; e += 128) {
-                const double a0 = qi[e], a1 = qi[e + 32], a2 = qi[e + 64], a3 = qi[e + 96];
-                s = fma(a0, w[e], s); s1 = fma(a1, w[e + 32], s1); s2 = fma(a2, w[e + 64], s2); s3 = fma(a3, w[e + 96], s3);
+            /* a basis vector is read once and comes from L2 / HBM: the pass is a chain of load latencies unless a lane has its
+               share of the vector in flight in a few large batches — 16 loads per lane, 512 elements per trip (the four-loads form
+               spent 8 latencies per 1000-element vector; Gram-Schmidt was 29 % of the kernel) */
+            double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int base = 0; base < m; base += 512) {
+                double v[16];
+#pragma unroll
+                for (int u = 0; u < 16; u++) { const int e = base + lane + 32 * u; v[u] = e < m ? qi[e] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 16; u += 4) {
+                    const int e = base + lane + 32 * u;
+                    if (e < m) s = fma(v[u], w[e], s);
+                    if (e + 32 < m) s1 = fma(v[u + 1], w[e + 32], s1);
+                    if (e + 64 < m) s2 = fma(v[u + 2], w[e + 64], s2);
+                    if (e + 96 < m) s3 = fma(v[u + 3], w[e + 96], s3);
+                }
             }
-            for (; e < m; e += 32) s = fma(qi[e], w[e], s);
             s = fpt_warp_sum((s + s1) + (s2 + s3));
             if (lane == 0) { hpass[i] = s; h[i] += s; }
         }
@@ -405,6 +415,9 @@ FPT_D void fpt_lanczos_iterate(const FptLzMatrix &M, double *Q, int m, double *X
         __syncthreads();
     }
     if (steps_out && tid == 0) *steps_out = nvec;
+#ifndef FPT_EMU
+    if (tid == 0) atomicAdd(&fpt_lanczos_phase_cycles[7], (unsigned long long)nvec);     /* slot 7: Lanczos steps, not cycles */
+#endif
     FPT_LZ_MARK(5);
 
     /* ---- 3. coordinates */

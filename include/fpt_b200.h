@@ -83,7 +83,7 @@ void fpt_set_lanczos_threads(int threads);
    and adjacent-pair sums); synchronises the device */
 int fpt_debug_umma_phases(unsigned long long *out8);
 /* the same for the large-cohort MDS kernel (0 dissimilarity = compare_all + fill_averages, 1 row means + code conversion, 2 products, 3 Gram-Schmidt, 4 tridiagonal
-   solves, 5 norms / next vector, 6 coordinates) */
+   solves, 5 norms / next vector, 6 coordinates; slot 7 is not a cycle count: it is the number of Lanczos steps taken, summed over windows) */
 int fpt_debug_lanczos_phases(unsigned long long *out8);
 /* Large-cohort classical MDS (csrc/fpt_css_lanczos.cuh): the highest form of the matrix the Lanczos product may stream —
    3 (default) 8-bit count codes squared arithmetically with the blank entries kept as a list, 2 8-bit count codes through a

@@ -28,5 +28,7 @@ for runs in (1000,):
         tot=sum(k4) or 1
         print('k4 (tcgen05 genotype GEMM) phase share (expand, wait for MMAs, drain+store):', [round(x/tot,3) for x in k4][:3], 'Mcycles per window', round(tot/1e6/max(1,nwin),3))
     if lib.fpt_debug_lanczos_phases(ph)==0:
+        steps=ph[7]; ph[7]=0
         tot=sum(ph) or 1
+        print('lanczos steps per window', round(steps/max(1,nwin),1))
         print('lanczos phase share (-, means+codes, products, gram-schmidt, tri-solves, norms, coordinates):', [round(x/tot,3) for x in ph][:7], 'Mcycles per window', round(tot/1e6/max(1,nwin),2))
