@@ -937,10 +937,15 @@ static int upload_genotypes(Arena &ar, const fpt_genotypes *g, DevGenotypes *d, 
     const int want = (int)std::min<size_t>(FPT_MAX_CHUNKS, std::max<size_t>(1, bytes / chunk_bytes));
     long long per = ((g->nsnp + want - 1) / want + 4095) & ~4095LL;
     if (per <= 0) per = 4096;
-    /* a single chunk of tens of MB still leaves the GPU idle for a millisecond: lead with an eighth of it, whose windows
-       then run while the other seven eighths are on the bus */
-    long long first = per;
-    if (want == 1 && bytes >= ((size_t)32 << 20)) first = std::max<long long>(4096, (g->nsnp / 8 + 4095) & ~4095LL);
+    /* a single chunk of tens of MB still leaves the GPU idle for a millisecond: lead with an eighth of it, then a quarter, then
+       the rest. Where the compute per SNP outlasts its upload (the CSS scan: ~6 ms of kernels for ~1.3 ms of DMA per chromosome)
+       each piece arrives while the windows of the one before are being scored, and only the first eighth's upload is exposed;
+       with two pieces (1/8, 7/8) the GPU finished the first before the second had arrived. */
+    long long first = per, second = per;
+    if (want == 1 && bytes >= ((size_t)32 << 20)) {
+        first = std::max<long long>(4096, (g->nsnp / 8 + 4095) & ~4095LL);
+        second = std::max<long long>(4096, (g->nsnp / 4 + 4095) & ~4095LL);
+    }
     CU(cudaStreamCreateWithFlags(&plan->cs, cudaStreamNonBlocking));
     cudaEvent_t ready;                           /* the copy stream starts once the stream-ordered allocations exist */
     CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
@@ -948,7 +953,7 @@ static int upload_genotypes(Arena &ar, const fpt_genotypes *g, DevGenotypes *d, 
     CU(cudaStreamWaitEvent(plan->cs, ready, 0));
     CU(cudaEventDestroy(ready));
     for (long long s0 = 0; s0 < g->nsnp && plan->n < FPT_MAX_CHUNKS;) {
-        const long long s1 = (plan->n == FPT_MAX_CHUNKS - 1) ? g->nsnp : std::min<long long>(g->nsnp, s0 + (plan->n == 0 ? first : per));
+        const long long s1 = (plan->n == FPT_MAX_CHUNKS - 1) ? g->nsnp : std::min<long long>(g->nsnp, s0 + (plan->n == 0 ? first : (plan->n == 1 ? second : per)));
         CU(cudaEventCreateWithFlags(&plan->ev[plan->n], cudaEventDisableTiming));
         plan->snp_end[plan->n++] = s1;
         s0 = s1;

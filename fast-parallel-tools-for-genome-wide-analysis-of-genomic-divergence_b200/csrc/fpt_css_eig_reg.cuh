@@ -30,8 +30,13 @@
 
 FPT_HD int fpt_tridiag_reg_ok(int m) { return m >= 3 && m <= 48; }
 FPT_HD int fpt_tridiag_reg_pad(int m) { return m <= 32 ? 32 : (m <= 40 ? 40 : 48); }
-/* per warp: two vectors of `pad` doubles (column / v, w) — the same bytes first stage two 32-SNP words of both bit-planes */
-FPT_HD size_t fpt_tridiag_reg_work_bytes(int m) { return (size_t)16 * fpt_tridiag_reg_pad(m); }
+/* per warp: two vectors of `pad` doubles (column / v, w) — the same bytes first stage two 32-SNP words of both bit-planes —
+   then d, e, tau (3 pad) and the reflectors (pad (pad - 1) / 2): they are collected in shared memory and leave for the hand-over
+   buffer in one coalesced sweep per window (per-step scalar stores cost a 64-bit address computation each, ~10 % of the loop) */
+FPT_HD size_t fpt_tridiag_reg_work_bytes(int m) {
+    const size_t pad = (size_t)fpt_tridiag_reg_pad(m);
+    return 8 * (2 * pad + 3 * pad + pad * (pad - 1) / 2);
+}
 
 /* column k of the register matrix (every row) to vb[row]: the lanes of column group k % 4 hold it in column slot k / 4 */
 template <int RS, int CS>
@@ -119,7 +124,8 @@ fpt_css_tridiag_reg_kernel(const unsigned *__restrict__ planes, int m, const int
     FPT_DYN_SMEM(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int rg = lane >> 2, cg = lane & 3;
-    double *vb = reinterpret_cast<double *>(smem + (size_t)warp * 16 * MP), *wb = vb + MP;
+    double *vb = reinterpret_cast<double *>(smem + (size_t)warp * (8 * (5 * MP + MP * (MP - 1) / 2))), *wb = vb + MP;
+    double *ts = wb + MP, *rs = ts + 3 * MP;              /* d | e | tau at stride m, reflectors in the fpt_refl_col layout */
     unsigned *words = reinterpret_cast<unsigned *>(vb);
     const size_t nrefl = (size_t)m * (m - 1) / 2;
     const int mm = m * m;
@@ -230,8 +236,6 @@ fpt_css_tridiag_reg_kernel(const unsigned *__restrict__ planes, int m, const int
             __syncwarp();
         }
         /* ---- Householder tridiagonalisation (LAPACK dsytd2, lower): H_k = I - tau v v', v(k+1) = 1 */
-        double *t = tri_out + (size_t)win * 3 * m;
-        double *refl = refl_out + (size_t)win * nrefl;
 #pragma unroll 1
         for (int k = 0; k + 2 < m; k++) {
             fpt_treg_dump_col<RS, CS>(a, k, rg, cg, vb);
@@ -240,9 +244,9 @@ fpt_css_tridiag_reg_kernel(const unsigned *__restrict__ planes, int m, const int
             const double xl = vb[lane], xh = lane + 32 < MP ? vb[lane + 32] : 0.0;
             double s2 = (lane >= k + 2 ? xl * xl : 0.0) + (lane + 32 >= k + 2 ? xh * xh : 0.0);
             s2 = fpt_warp_sum(s2);
-            if (lane == 0) t[k] = dk;
+            if (lane == 0) ts[k] = dk;
             if (s2 == 0.0) {                                 /* column already tridiagonal: H = I */
-                if (lane == 0) { t[m + k] = x0; t[2 * m + k] = 0.0; }
+                if (lane == 0) { ts[m + k] = x0; ts[2 * m + k] = 0.0; }
                 __syncwarp();
                 continue;
             }
@@ -261,11 +265,11 @@ fpt_css_tridiag_reg_kernel(const unsigned *__restrict__ planes, int m, const int
             }
             const double alpha = x0 >= 0.0 ? -nrm : nrm;
             {   /* the reflector to the hand-over buffer: rcol[i] = v_i, i = k+1 .. m-1 */
-                double *rcol = refl + fpt_refl_col(m, k) - (k + 1);
+                double *rcol = rs + fpt_refl_col(m, k) - (k + 1);
                 if (lane > k && lane < m) rcol[lane] = lane == k + 1 ? 1.0 : xl * scal;
                 if (lane + 32 > k && lane + 32 < m) rcol[lane + 32] = lane + 32 == k + 1 ? 1.0 : xh * scal;
             }
-            if (lane == 0) { t[m + k] = alpha; t[2 * m + k] = tau; }
+            if (lane == 0) { ts[m + k] = alpha; ts[2 * m + k] = tau; }
             switch ((k + 1) >> 3) {
                 case 0: fpt_treg_step<RS, CS, 0>(a, k, scal, tau, rg, cg, vb, wb); break;
                 case 1: fpt_treg_step<RS, CS, 1>(a, k, scal, tau, rg, cg, vb, wb); break;
@@ -283,9 +287,16 @@ fpt_css_tridiag_reg_kernel(const unsigned *__restrict__ planes, int m, const int
         fpt_treg_dump_col<RS, CS>(a, m - 1, rg, cg, vb);
         __syncwarp();
         if (lane == 0) {
-            t[m - 2] = d2; t[m + m - 2] = e2; t[m - 1] = vb[m - 1];
-            t[m + m - 1] = 0.0; t[2 * m + m - 1] = 0.0; t[2 * m + m - 2] = 0.0;   /* entries the reduction does not produce */
+            ts[m - 2] = d2; ts[m + m - 2] = e2; ts[m - 1] = vb[m - 1];
+            ts[m + m - 1] = 0.0; ts[2 * m + m - 1] = 0.0; ts[2 * m + m - 2] = 0.0;   /* entries the reduction does not produce */
             status[win] = 2;
+        }
+        __syncwarp();
+        {   /* hand-over: one coalesced sweep (a column whose reflector was the identity keeps stale entries: tau = 0 says so) */
+            double *t = tri_out + (size_t)win * 3 * m;
+            double *refl = refl_out + (size_t)win * nrefl;
+            for (int e = lane; e < 3 * m; e += 32) t[e] = ts[e];
+            for (int e = lane; e < (int)nrefl; e += 32) refl[e] = rs[e];
         }
         __syncwarp();
     }
