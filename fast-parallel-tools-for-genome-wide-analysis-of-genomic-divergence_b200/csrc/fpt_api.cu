@@ -18,6 +18,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <chrono>
 #include <mutex>
 #include <thread>
@@ -1315,35 +1317,89 @@ static int population_size(const int *pos, int len) {
     return n;
 }
 
-/* reference layout -> one position per SNP (into pinned staging); verifies that A and B describe the same SNPs.
-   The reads are strided (one int per asize / bsize), i.e. one cache line per SNP and population: on a genome-sized call
-   this is ~128 bytes of host memory traffic per SNP, so it is split over a few threads to stay behind the DMA it overlaps. */
-static int gather_positions(const int *apos, const int *bpos, int asize, int bsize, long long nsnp, int32_t *pos) {
-    const unsigned hw = std::thread::hardware_concurrency();
-    const int nt = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(12, hw ? hw : 1), nsnp / 16384));
-    std::vector<long long> bad((size_t)nt, -1);
-    auto work = [&](int t) {
-        const long long lo = nsnp * t / nt, hi = nsnp * (t + 1) / nt;
-        for (long long k = lo; k < hi; k++) {
-            const int pa = apos[k * asize];
-            if (pa != bpos[k * bsize]) { bad[(size_t)t] = k; return; }
-            pos[k] = pa;
+/* reference layout -> one position per SNP (into pinned staging). The reads are strided (one int per asize individuals), i.e. one
+   cache line per SNP: on a genome-sized call this is ~64 bytes of host memory traffic per SNP and population, so it is split over
+   a few threads. Only population A's positions are gathered on the critical path (nothing can be launched before the window
+   table has them); that B lists the same SNPs (the reference silently mis-pairs them otherwise) is verified by
+   PositionCheck below while the GPU is already scoring. */
+/* A few parked helper threads: starting a std::thread costs ~30 us, and a dozen of them started one after the other cost more
+   than the gather they were meant to speed up (measured: 0.4 ms per chromosome either way). One job at a time (the mutex). */
+class HelperPool {
+    std::mutex job_mu, mu;
+    std::condition_variable cv, done_cv;
+    std::vector<std::thread> th;
+    std::function<void(int)> fn;
+    int nt = 0, gen = 0, left = 0;
+    bool stop = false;
+    void loop(int id) {
+        int seen = 0;
+        for (;;) {
+            std::function<void(int)> f;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || gen != seen; });
+                if (stop) return;
+                seen = gen;
+                if (id >= nt) continue;
+                f = fn;
+            }
+            f(id);
+            { std::lock_guard<std::mutex> lk(mu); if (--left == 0) done_cv.notify_all(); }
         }
-    };
-    if (nt == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) th.emplace_back(work, t);
-        work(0);
-        for (auto &x : th) x.join();
     }
-    for (int t = 0; t < nt; t++) {
-        const long long k = bad[(size_t)t];
-        if (k >= 0) return fail(FPT_ERR_POSITIONS, "SNP %lld: position %d in A but %d in B", k, apos[k * asize], bpos[k * bsize]);
+public:
+    explicit HelperPool(int n) { for (int i = 0; i < n; i++) th.emplace_back(&HelperPool::loop, this, i + 1); }
+    ~HelperPool() { { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_all(); for (auto &x : th) x.join(); }
+    int helpers() const { return (int)th.size(); }
+    /* f(0 .. parts-1), part 0 on the caller; parts - 1 <= helpers() */
+    void run(int parts, const std::function<void(int)> &f) {
+        std::lock_guard<std::mutex> job(job_mu);
+        if (parts > 1) {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = f; nt = parts; left = parts - 1; gen++;
+        }
+        if (parts > 1) cv.notify_all();
+        f(0);
+        if (parts > 1) { std::unique_lock<std::mutex> lk(mu); done_cv.wait(lk, [&] { return left == 0; }); }
     }
-    return FPT_OK;
+};
+static HelperPool &helper_pool() {
+    static HelperPool pool((int)std::max(1u, std::min(11u, std::thread::hardware_concurrency() ? std::thread::hardware_concurrency() - 1 : 1u)));
+    return pool;
 }
+
+static void gather_positions(const int *apos, int asize, long long nsnp, int32_t *pos) {
+    HelperPool &pool = helper_pool();
+    const int nt = (int)std::max<long long>(1, std::min<long long>(pool.helpers() + 1, nsnp / 16384));
+    pool.run(nt, [=](int t) {
+        const long long lo = nsnp * t / nt, hi = nsnp * (t + 1) / nt;
+        for (long long k = lo; k < hi; k++) pos[k] = apos[k * asize];
+    });
+}
+
+/* bpos[k * bsize] == pos[k] for every SNP, checked on helper threads; result() joins them */
+struct PositionCheck {
+    std::vector<std::thread> th;
+    std::vector<long long> bad;
+    void start(const int32_t *pos, const int *bpos, int bsize, long long nsnp) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const int nt = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(2, hw ? hw : 1), nsnp / 1000000));   /* it has the whole scan to finish */
+        bad.assign((size_t)nt, -1);
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([this, pos, bpos, bsize, nsnp, nt, t]() {
+                const long long lo = nsnp * t / nt, hi = nsnp * (t + 1) / nt;
+                for (long long k = lo; k < hi; k++)
+                    if (pos[k] != bpos[k * bsize]) { bad[(size_t)t] = k; return; }
+            });
+    }
+    long long result() {                                   /* first mismatching SNP, or -1 */
+        for (auto &x : th) x.join();
+        th.clear();
+        for (long long k : bad) if (k >= 0) return k;
+        return -1;
+    }
+    ~PositionCheck() { for (auto &x : th) if (x.joinable()) x.join(); }
+};
 
 static fpt_scan_range full_range(int regend, int wsize, int wstep, int semantics) {
     fpt_scan_range r;
@@ -1385,15 +1441,23 @@ static int dropin(int css, double *avals, double *bvals, int *apos, int *bpos, i
     Arena ar(hs.st);
     DevGenotypes d;
     UploadPlan plan;
-    CHECK(upload_genotypes(ar, &g, &d, &plan, css ? FPT_CHUNK_BYTES_CSS : FPT_CHUNK_BYTES_FET));            /* asynchronous when the caller's arrays are page-locked */
-    const auto t1 = std::chrono::steady_clock::now();
     void *hpos;
     CHECK(pinned_slot(c, 3, (size_t)na * sizeof(int32_t), &hpos));
-    CHECK(gather_positions(apos, bpos, g.asize, g.bsize, na, (int32_t *)hpos));
+    CHECK(upload_genotypes(ar, &g, &d, &plan, css ? FPT_CHUNK_BYTES_CSS : FPT_CHUNK_BYTES_FET));            /* asynchronous when the caller's arrays are page-locked */
+    const auto t1 = std::chrono::steady_clock::now();
+    gather_positions(apos, g.asize, na, (int32_t *)hpos);
     g.pos = (const int32_t *)hpos;
+    PositionCheck pc;
+    pc.start(g.pos, bpos, g.bsize, na);
     const auto t2 = std::chrono::steady_clock::now();
-    const int rc = css ? css_scan_core(c, ar, &g, d, plan, &r, treshold, runs, drosophila, mds, out0, out1, nullptr, nullptr)
-                       : fet_scan_core(c, ar, &g, d, plan, &r, perc, out0, out1, nullptr);
+    int rc = css ? css_scan_core(c, ar, &g, d, plan, &r, treshold, runs, drosophila, mds, out0, out1, nullptr, nullptr)
+                 : fet_scan_core(c, ar, &g, d, plan, &r, perc, out0, out1, nullptr);
+    const long long badk = pc.result();
+    if (badk >= 0) {
+        /* the outputs were written from mis-paired SNPs: put the caller's pre-zeroed arrays back */
+        for (long long w = 0; w < r.window_end; w++) { out0[w] = 0.0; out1[w] = 0.0; }
+        rc = fail(FPT_ERR_POSITIONS, "SNP %lld: position %d in A but %d in B", badk, apos[badk * g.asize], bpos[badk * g.bsize]);
+    }
     if (trace) {
         const auto t3 = std::chrono::steady_clock::now();
         auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {

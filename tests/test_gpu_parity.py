@@ -589,9 +589,17 @@ def test_position_mismatch_is_an_error(fpt):
     ch, (av, bv, apos, bpos) = _synth(91, 50000, 500, 4, 4)
     bpos = bpos.copy()
     bpos[40:44] += 1
+    s, d = np.zeros(100), np.zeros(100)
     with pytest.raises(fpt.FptError) as e:
-        serial.fisher_exact_tester(av, bv, apos, bpos, 0, 50000, 2500, 500, av.size, bv.size, 0.95, np.zeros(100), np.zeros(100))
+        serial.fisher_exact_tester(av, bv, apos, bpos, 0, 50000, 2500, 500, av.size, bv.size, 0.95, s, d)
     assert e.value.code == -3
+    # the A/B check runs beside the scan (off the critical path): a failed call leaves the caller's pre-zeroed outputs untouched
+    assert not s.any() and not d.any()
+    import fpt_b200.css_cython as css_serial
+    s, d = np.zeros(100), np.zeros(100)
+    with pytest.raises(fpt.FptError) as e:
+        css_serial.cluster_separation_scorer(av, bv, apos, bpos, 0, 50000, 2500, 500, av.size, bv.size, 10, 50, 0, 0, s, d)
+    assert e.value.code == -3 and not s.any() and not d.any()
 
 
 # ------------------------------------------------------------------------------------------------ whole pipeline
