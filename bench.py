@@ -289,7 +289,7 @@ def bench_css(lib_mod, cx, full_genome_pass):
         if world > 1:                                    # the only exchange: results gathered once at the end
             cx.dist.all_gather_into_tensor(gathered, local)
 
-    launches_per_step = len(plan) * 5 + (1 if world > 1 else 0)   # pack, window table, tridiagonalisation, eigenvectors, permutations (+ gather)
+    launches_per_step = len(plan) * 6 + (1 if world > 1 else 0)   # pack, window table, tridiagonalisation, eigenvectors, observed scores, permutations (+ gather)
 
     def e2e_piece(c, lo, hi, r, nw):
         """host call on this rank's range of chromosome c: float64 host arrays (pinned) in, host arrays out"""
