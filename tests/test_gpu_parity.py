@@ -37,7 +37,11 @@ def test_fet_per_snp_tables_and_scores(fpt, oracle, asize, bsize, nsnp):
         tab, sc = fpt.fet_per_snp(a, b, asize, bsize)
         assert np.array_equal(tab, tab_o)                        # bit-exact contingency tables
         np.testing.assert_allclose(sc, sc_o, rtol=FET_RTOL, atol=1e-13)
-        assert np.array_equal(sc == 0, sc_o == 0)
+        # P = 1 (score 0) where both say so; a table whose P is 1 up to the rounding of lp0 + log S (|score| < 1e-12) may come out as
+        # -0.0 on one side and as 1e-17 on the other (exact mode is operation-identical, the log-mode walk is not)
+        assert np.array_equal(np.abs(sc) > 1e-12, np.abs(sc_o) > 1e-12)
+        if asize + bsize <= 67:
+            assert np.array_equal(sc == 0, sc_o == 0)
 
 
 def test_fet_exact_domain_all_small_tables(fpt, oracle):
