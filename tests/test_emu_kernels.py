@@ -483,6 +483,8 @@ def test_large_cohort_observed_score_shuffle_and_surrogate_distance(emu, oracle)
     for asize, bsize in ((37, 30), (5, 64), (1, 3)):
         m, nwin = asize + bsize, 5
         X = rng.normal(size=(nwin, m, 2)) * rng.uniform(0.1, 50.0, size=(nwin, 1, 1))
+        if m > 8:
+            X[0, 3] = X[0, 5]; X[0, 7] = X[0, 5]; X[0, 1] = X[0, 0]       # coincident points: distance exactly 0 (common in real embeddings)
         status = np.full(nwin, 2, dtype=np.uint8)
         status[3] = 1
         got = np.zeros(nwin)
