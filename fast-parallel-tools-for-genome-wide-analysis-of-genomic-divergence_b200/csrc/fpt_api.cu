@@ -895,6 +895,52 @@ struct DevGenotypes { const double *a64 = nullptr, *b64 = nullptr; const signed 
 #define FPT_CHUNK_BYTES_FET ((size_t)16 << 20)    /* the copy dominates a FET scan: many chunks, windows released early */
 #define FPT_CHUNK_BYTES_CSS ((size_t)96 << 20)    /* compute dominates a CSS scan: sub-range launches cost more in tails than the
                                                      copy they hide until the input is several hundred MB */
+/* A few parked helper threads: starting a std::thread costs ~30 us, and a dozen of them started one after the other cost more
+   than the gather they were meant to speed up (measured: 0.4 ms per chromosome either way). One job at a time (the mutex). */
+class HelperPool {
+    std::mutex job_mu, mu;
+    std::condition_variable cv, done_cv;
+    std::vector<std::thread> th;
+    std::function<void(int)> fn;
+    int nt = 0, gen = 0, left = 0;
+    bool stop = false;
+    void loop(int id) {
+        int seen = 0;
+        for (;;) {
+            std::function<void(int)> f;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || gen != seen; });
+                if (stop) return;
+                seen = gen;
+                if (id >= nt) continue;
+                f = fn;
+            }
+            f(id);
+            { std::lock_guard<std::mutex> lk(mu); if (--left == 0) done_cv.notify_all(); }
+        }
+    }
+public:
+    explicit HelperPool(int n) { for (int i = 0; i < n; i++) th.emplace_back(&HelperPool::loop, this, i + 1); }
+    ~HelperPool() { { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_all(); for (auto &x : th) x.join(); }
+    int helpers() const { return (int)th.size(); }
+    /* f(0 .. parts-1), part 0 on the caller; parts - 1 <= helpers() */
+    void run(int parts, const std::function<void(int)> &f) {
+        std::lock_guard<std::mutex> job(job_mu);
+        if (parts > 1) {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = f; nt = parts; left = parts - 1; gen++;
+        }
+        if (parts > 1) cv.notify_all();
+        f(0);
+        if (parts > 1) { std::unique_lock<std::mutex> lk(mu); done_cv.wait(lk, [&] { return left == 0; }); }
+    }
+};
+static HelperPool &helper_pool() {
+    static HelperPool pool((int)std::max(1u, std::min(11u, std::thread::hardware_concurrency() ? std::thread::hardware_concurrency() - 1 : 1u)));
+    return pool;
+}
+
 struct UploadPlan {
     int n = 0;                                   /* chunks */
     int queued = 0;                              /* chunks already handed to the copy stream */
@@ -903,6 +949,7 @@ struct UploadPlan {
     cudaStream_t cs = nullptr;
     char *da = nullptr, *db = nullptr;           /* device arrays */
     const char *ha = nullptr, *hb = nullptr;     /* host arrays */
+    char *sa = nullptr, *sb = nullptr;           /* pageable host arrays: page-locked staging copies (non-null = staged upload) */
     size_t rowa = 0, rowb = 0;                   /* bytes per SNP */
     ~UploadPlan() {
         if (cs) cudaStreamSynchronize(cs);       /* error paths: no copy may outlive the buffers it writes */
@@ -915,8 +962,25 @@ struct UploadPlan {
 static int upload_enqueue(UploadPlan *p, int upto) {
     for (; p->queued < upto && p->queued < p->n; p->queued++) {
         const long long s0 = p->queued ? p->snp_end[p->queued - 1] : 0, s1 = p->snp_end[p->queued];
-        CU(cudaMemcpyAsync(p->da + (size_t)s0 * p->rowa, p->ha + (size_t)s0 * p->rowa, (size_t)(s1 - s0) * p->rowa, cudaMemcpyHostToDevice, p->cs));
-        CU(cudaMemcpyAsync(p->db + (size_t)s0 * p->rowb, p->hb + (size_t)s0 * p->rowb, (size_t)(s1 - s0) * p->rowb, cudaMemcpyHostToDevice, p->cs));
+        const char *srca = p->ha, *srcb = p->hb;
+        if (p->sa) {
+            /* pageable caller arrays (what numpy hands over): a cudaMemcpyAsync from them is staged by the driver through one
+               thread at ~10 GB/s and blocks the caller; copying the chunk into our own page-locked buffer with the helper threads
+               runs at several times that and leaves the DMA asynchronous */
+            const size_t ba = (size_t)(s1 - s0) * p->rowa, bb = (size_t)(s1 - s0) * p->rowb, oa = (size_t)s0 * p->rowa, ob = (size_t)s0 * p->rowb;
+            HelperPool &pool = helper_pool();
+            const int parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)pool.helpers() + 1, (ba + bb) >> 20));
+            char *sa = p->sa, *sb = p->sb;
+            const char *ha = p->ha, *hb = p->hb;
+            pool.run(parts, [=](int t) {
+                const size_t a0 = ba * t / parts, a1 = ba * (t + 1) / parts, b0 = bb * t / parts, b1 = bb * (t + 1) / parts;
+                memcpy(sa + oa + a0, ha + oa + a0, a1 - a0);
+                memcpy(sb + ob + b0, hb + ob + b0, b1 - b0);
+            });
+            srca = p->sa; srcb = p->sb;
+        }
+        CU(cudaMemcpyAsync(p->da + (size_t)s0 * p->rowa, srca + (size_t)s0 * p->rowa, (size_t)(s1 - s0) * p->rowa, cudaMemcpyHostToDevice, p->cs));
+        CU(cudaMemcpyAsync(p->db + (size_t)s0 * p->rowb, srcb + (size_t)s0 * p->rowb, (size_t)(s1 - s0) * p->rowb, cudaMemcpyHostToDevice, p->cs));
         CU(cudaEventRecord(p->ev[p->queued], p->cs));
     }
     return FPT_OK;
@@ -933,9 +997,20 @@ static int upload_genotypes(Arena &ar, const fpt_genotypes *g, DevGenotypes *d, 
     plan->ha = g->avals ? (const char *)g->avals : (const char *)g->acodes;
     plan->hb = g->avals ? (const char *)g->bvals : (const char *)g->bcodes;
     plan->rowa = (size_t)g->asize * esz; plan->rowb = (size_t)g->bsize * esz;
+    if ((na + nb) * esz >= ((size_t)1 << 20)) {
+        cudaPointerAttributes at;
+        const bool pageable = cudaPointerGetAttributes(&at, plan->ha) == cudaSuccess && at.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        DeviceCtx *c;
+        if (pageable && get_ctx(&c) == FPT_OK) {
+            void *s4 = nullptr, *s5 = nullptr;
+            if (pinned_slot(c, 4, na * esz, &s4) == FPT_OK && pinned_slot(c, 5, nb * esz, &s5) == FPT_OK) { plan->sa = (char *)s4; plan->sb = (char *)s5; }
+        }
+    }
     /* one chunk per `chunk_bytes` (FPT_UPLOAD_CHUNK_BYTES overrides: tests use it to cut small inputs), at most FPT_MAX_CHUNKS */
     const size_t bytes = (na + nb) * esz;
     if (const char *e = getenv("FPT_UPLOAD_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) chunk_bytes = (size_t)v; }
+    if (plan->sa) chunk_bytes = std::min(chunk_bytes, (size_t)16 << 20);    /* staged: the host copy of chunk k+1 overlaps the DMA of chunk k */
     const int want = (int)std::min<size_t>(FPT_MAX_CHUNKS, std::max<size_t>(1, bytes / chunk_bytes));
     long long per = ((g->nsnp + want - 1) / want + 4095) & ~4095LL;
     if (per <= 0) per = 4096;
@@ -990,6 +1065,7 @@ extern "C" int fpt_fet_per_snp(const fpt_genotypes *g, int32_t *tables, double *
     CHECK(get_ctx(&c));
     CHECK(check_genotypes(g));
     if (g->nsnp == 0) return FPT_OK;
+    std::lock_guard<std::mutex> host_lock(g_host_mu[c->device]);   /* the staging buffers of a pageable upload are per device */
     HostStream hs;
     CHECK(hs.make());
     Arena ar(hs.st);
@@ -1069,7 +1145,7 @@ static int fet_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const 
         CU(cudaMemcpyAsync(d_states, r->states_resample, (size_t)nwin * 8, cudaMemcpyHostToDevice, st));
     }
     /* the small host->device copies above (positions, stream states) are now ahead of the remaining chunks in the DMA queue */
-    CHECK(upload_enqueue(&plan, plan.n));
+    if (!plan.sa) CHECK(upload_enqueue(&plan, plan.n));         /* staged uploads copy on the host: one chunk ahead of the launches, below */
     CU(cudaMemsetAsync(d_fl, 0, (size_t)nwin, st));
     CU(cudaMemcpyAsync(&f.max_npos, f.d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));                          /* positions and window table only: the genotypes are on plan.cs */
@@ -1077,6 +1153,7 @@ static int fet_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const 
     long long wdone = 0, s0 = 0;
     for (int k = 0; k < plan.n; k++) {
         const long long s1 = plan.snp_end[k];
+        if (plan.sa) CHECK(upload_enqueue(&plan, k + 2));
         CU(cudaStreamWaitEvent(st, plan.ev[k], 0));
         if (d.a64) CHECK(fpt_dev_fet_count_f64(d.a64 + (size_t)s0 * g->asize, d.b64 + (size_t)s0 * g->bsize, s1 - s0, g->asize, g->bsize, d_tab + 4 * s0, st));
         else CHECK(fpt_dev_fet_count_i8((const int8_t *)d.a8 + (size_t)s0 * g->asize, (const int8_t *)d.b8 + (size_t)s0 * g->bsize, s1 - s0, g->asize,
@@ -1163,7 +1240,7 @@ static int css_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const 
         if (dp.X) CU(cudaMemsetAsync(dp.X, 0, (size_t)nwin * 2 * m * 8, st));
     }
     /* the small host->device copies above (positions, stream states) are now ahead of the remaining chunks in the DMA queue */
-    CHECK(upload_enqueue(&plan, plan.n));
+    if (!plan.sa) CHECK(upload_enqueue(&plan, plan.n));         /* staged uploads: one chunk ahead of the launches, in the loop */
     /* per upload chunk: pack its SNPs, then score every window whose SNPs have all arrived (see fet_scan_core). Only where
        a sub-range still fills the GPU many times over: the CTA-per-window kernels of large cohorts run a few hundred windows
        at a time, and a short extra launch costs them a whole wave. */
@@ -1171,6 +1248,7 @@ static int css_scan_core(DeviceCtx *c, Arena &ar, const fpt_genotypes *g, const 
     long long wdone = 0, s0 = 0;
     for (int k = 0; k < plan.n; k++) {
         const long long s1 = plan.snp_end[k];
+        if (plan.sa) CHECK(upload_enqueue(&plan, k + 2));
         CU(cudaStreamWaitEvent(st, plan.ev[k], 0));
         if (drosophila) CHECK(fpt_dev_css_absdiff(d.a64 + s0, d.b64 + s0, s1 - s0, d_abs + s0, st));
         else {
@@ -1267,6 +1345,7 @@ extern "C" int fpt_debug_k4_counts(const fpt_genotypes *g, const fpt_scan_range 
     if (!counts || !g->pos || window < r->window_begin || window >= r->window_end) return fail(FPT_ERR_ARG, "k4 probe: bad arguments");
     if (mode != 1 && mode != 2) return fail(FPT_ERR_ARG, "k4 probe: mode must be 1 (popcounts) or 2 (tcgen05)");
     const int m = g->asize + g->bsize;
+    std::lock_guard<std::mutex> host_lock(g_host_mu[c->device]);
     HostStream hs;
     CHECK(hs.make());
     Arena ar(hs.st);
@@ -1322,52 +1401,6 @@ static int population_size(const int *pos, int len) {
    a few threads. Only population A's positions are gathered on the critical path (nothing can be launched before the window
    table has them); that B lists the same SNPs (the reference silently mis-pairs them otherwise) is verified by
    PositionCheck below while the GPU is already scoring. */
-/* A few parked helper threads: starting a std::thread costs ~30 us, and a dozen of them started one after the other cost more
-   than the gather they were meant to speed up (measured: 0.4 ms per chromosome either way). One job at a time (the mutex). */
-class HelperPool {
-    std::mutex job_mu, mu;
-    std::condition_variable cv, done_cv;
-    std::vector<std::thread> th;
-    std::function<void(int)> fn;
-    int nt = 0, gen = 0, left = 0;
-    bool stop = false;
-    void loop(int id) {
-        int seen = 0;
-        for (;;) {
-            std::function<void(int)> f;
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return stop || gen != seen; });
-                if (stop) return;
-                seen = gen;
-                if (id >= nt) continue;
-                f = fn;
-            }
-            f(id);
-            { std::lock_guard<std::mutex> lk(mu); if (--left == 0) done_cv.notify_all(); }
-        }
-    }
-public:
-    explicit HelperPool(int n) { for (int i = 0; i < n; i++) th.emplace_back(&HelperPool::loop, this, i + 1); }
-    ~HelperPool() { { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_all(); for (auto &x : th) x.join(); }
-    int helpers() const { return (int)th.size(); }
-    /* f(0 .. parts-1), part 0 on the caller; parts - 1 <= helpers() */
-    void run(int parts, const std::function<void(int)> &f) {
-        std::lock_guard<std::mutex> job(job_mu);
-        if (parts > 1) {
-            std::lock_guard<std::mutex> lk(mu);
-            fn = f; nt = parts; left = parts - 1; gen++;
-        }
-        if (parts > 1) cv.notify_all();
-        f(0);
-        if (parts > 1) { std::unique_lock<std::mutex> lk(mu); done_cv.wait(lk, [&] { return left == 0; }); }
-    }
-};
-static HelperPool &helper_pool() {
-    static HelperPool pool((int)std::max(1u, std::min(11u, std::thread::hardware_concurrency() ? std::thread::hardware_concurrency() - 1 : 1u)));
-    return pool;
-}
-
 static void gather_positions(const int *apos, int asize, long long nsnp, int32_t *pos) {
     HelperPool &pool = helper_pool();
     const int nt = (int)std::max<long long>(1, std::min<long long>(pool.helpers() + 1, nsnp / 16384));
