@@ -805,11 +805,16 @@ static int dev_css_windows(const Knobs &kn, const uint32_t *planes, const double
                 if (best < 0 || cost < best) { best = cost; sthreads = t; }
             }
         }
-        CHECK(persistent_grid(c, fpt_css_smacof_kernel, sthreads, p.smem_win, nwin * nruns, &grid));
+        if (p.mats_in_smem) CHECK(persistent_grid(c, fpt_css_smacof_kernel<true>, sthreads, p.smem_win, nwin * nruns, &grid));
+        else CHECK(persistent_grid(c, fpt_css_smacof_kernel<false>, sthreads, p.smem_win, nwin * nruns, &grid));
         grid = std::min(grid, p.max_ctas);
-        { ProfScope ps_("css_smacof", st); fpt_css_smacof_kernel<<<grid, sthreads, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, r->window_begin, nwin, p.wch,
-                                                            p.mats_in_smem, ws.gscratch, nruns, mds == 1, r->seed, st_init,
-                                                            300, 0.000001, ws.X, ws.Xruns, ws.sigma, ws.iters, status); }
+        {
+            ProfScope ps_("css_smacof", st);
+            if (p.mats_in_smem) fpt_css_smacof_kernel<true><<<grid, sthreads, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, r->window_begin, nwin, p.wch,
+                                                            1, ws.gscratch, nruns, mds == 1, r->seed, st_init, 300, 0.000001, ws.X, ws.Xruns, ws.sigma, ws.iters, status);
+            else fpt_css_smacof_kernel<false><<<grid, sthreads, p.smem_win, st>>>(planes, absdiff, m, wleft, wright, r->window_begin, nwin, p.wch,
+                                                            0, ws.gscratch, nruns, mds == 1, r->seed, st_init, 300, 0.000001, ws.X, ws.Xruns, ws.sigma, ws.iters, status);
+        }
         CU(cudaGetLastError());
         int g2 = (int)std::min<long long>(nwin, (long long)c->sms * 16);
         { ProfScope ps_("css_pick", st); fpt_css_pick_kernel<<<g2, 64, 0, st>>>(ws.Xruns, ws.sigma, m, nruns, nwin, status, ws.X); }

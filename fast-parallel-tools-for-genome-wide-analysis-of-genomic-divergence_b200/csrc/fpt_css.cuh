@@ -335,7 +335,11 @@ FPT_D double fpt_css_smacof(const double *delta, double *Bm, int m, double *X, d
     return have_r ? sigma_r : fpt_css_stress_reforder(X, delta, m, sc);
 }
 
-/* one CTA per (window, start). nruns = 4 random starts (mds 1) or 1 start from Xin (mds 2). */
+/* one CTA per (window, start). nruns = 4 random starts (mds 1) or 1 start from Xin (mds 2). MATS_SMEM is a template parameter so
+   that, where the two matrices live in shared memory (every cohort up to ~115 individuals), the compiler sees shared-memory pointers
+   and emits LDS / STS: with the choice made at run time every access to delta and B was a generic LD / ST (ncu: 7 % of the kernel's
+   instructions, each paying the address-space check). */
+template <bool MATS_SMEM>
 __global__ void __launch_bounds__(256)
 fpt_css_smacof_kernel(const unsigned *__restrict__ planes, const double *__restrict__ absdiff, int m,
                       const int *__restrict__ wleft, const int *__restrict__ wright, long long wbase, long long nwin,
@@ -344,7 +348,8 @@ fpt_css_smacof_kernel(const unsigned *__restrict__ planes, const double *__restr
                       const double *__restrict__ Xin, double *__restrict__ Xruns, double *__restrict__ sigma_runs,
                       int *__restrict__ iters_runs, unsigned char *__restrict__ status) {
     FPT_DYN_SMEM(smem);
-    FptCssSmem s = fpt_css_carve(smem, m, wch, mats_in_smem, gscratch ? gscratch + (size_t)blockIdx.x * fpt_css_mats_doubles(m) : 0);
+    /* MATS_SMEM = true: the caller guarantees mats_in_smem != 0 and the constant is used; false: the run-time value decides */
+    FptCssSmem s = fpt_css_carve(smem, m, wch, MATS_SMEM ? 1 : mats_in_smem, gscratch ? gscratch + (size_t)blockIdx.x * fpt_css_mats_doubles(m) : 0);
     if (s.sc.pairs) {                                     /* the pair decode is the same for every window and iteration */
         for (int p = threadIdx.x; p < (m * (m - 1)) >> 1; p += blockDim.x) { int i, j; fpt_pair_of(p, i, j); s.sc.pairs[p] = (i << 16) | j; }
         __syncthreads();

@@ -187,7 +187,9 @@ void emu_css_smacof(const unsigned *planes, const double *absdiff, int m, const 
     std::vector<double> gs(mats_in_smem ? 1 : (size_t)grid * fpt_css_mats_doubles(m));
     double *gp = mats_in_smem ? 0 : gs.data();
     run_grid(grid, 128, smem, [=]() {
-        fpt_css_smacof_kernel(planes, absdiff, m, wleft, wright, wbase, nwin, wch, mats_in_smem, gp, nruns, random_start, seed,
+        if (mats_in_smem) fpt_css_smacof_kernel<true>(planes, absdiff, m, wleft, wright, wbase, nwin, wch, 1, gp, nruns, random_start, seed,
+                              state_override, max_iters, eps, Xin, Xruns, sigma_runs, iters_runs, status);
+        else fpt_css_smacof_kernel<false>(planes, absdiff, m, wleft, wright, wbase, nwin, wch, 0, gp, nruns, random_start, seed,
                               state_override, max_iters, eps, Xin, Xruns, sigma_runs, iters_runs, status);
     });
 }
