@@ -687,6 +687,29 @@ def test_scans_with_chunked_upload_match_single_pass(fpt, oracle, monkeypatch, s
     np.testing.assert_allclose(d_g, d_o, rtol=1e-9, atol=1e-12)
 
 
+def test_page_locked_and_pageable_inputs_agree(fpt):
+    """caller arrays in page-locked memory are copied from directly; pageable ones (plain numpy) go through the library's staging
+    buffers, chunk by chunk on helper threads: same results bit for bit, for both scans and both layouts"""
+    import torch
+    asize, bsize, regend, wsize, wstep, nsnp = 9, 8, 900000, 2500, 500, 30000
+    ch, (av, bv, apos, bpos) = _synth(322, regend, nsnp, asize, bsize)
+    keep = []
+
+    def pinned(x):
+        t = torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+        keep.append(t)
+        return t.numpy()
+    big_a, big_b = np.tile(ch["acodes"], 1), np.tile(ch["bcodes"], 1)
+    for a, b in ((av, bv), (big_a, big_b)):
+        f0 = fpt.fet_scan(a, b, ch["pos"], asize, bsize, regend, wsize, wstep, 0.95, seed=5)
+        f1 = fpt.fet_scan(pinned(a), pinned(b), pinned(ch["pos"]), asize, bsize, regend, wsize, wstep, 0.95, seed=5)
+        c0 = fpt.css_scan(a, b, ch["pos"], asize, bsize, regend, wsize, wstep, 5, 40, mds=0, seed=5)
+        c1 = fpt.css_scan(pinned(a), pinned(b), pinned(ch["pos"]), asize, bsize, regend, wsize, wstep, 5, 40, mds=0, seed=5)
+        for x, y in zip(f0 + c0, f1 + c1):
+            assert np.array_equal(x, y, equal_nan=True)
+    assert (f0[2] == 1).sum() > 1000
+
+
 def test_concurrent_host_calls_serialise(fpt):
     """two Python threads (ctypes drops the GIL) scanning at once: the host entry points share per-device staging buffers and
     must therefore take turns; results equal the ones of back-to-back calls"""
