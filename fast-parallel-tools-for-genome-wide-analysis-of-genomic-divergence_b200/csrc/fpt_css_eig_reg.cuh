@@ -57,24 +57,19 @@ FPT_D void fpt_treg_dump_col(const double (&a)[RS][CS], int k, int rg, int cg, d
     }
 }
 
-/* Householder step k on the block of row slots >= R0, column slots >= 2 R0 (everything before them lies above / left of row and
-   column k + 1). vb holds column k (rows >= m read zero), scal = 1 / (x0 - alpha). */
+/* Householder step on the block of row slots >= R0, column slots >= 2 R0 (everything before them lies above / left of row and
+   column k + 1). vb holds the reflector v itself (0 up to row k, 1 at k + 1, the scaled column below; rows >= m read zero).
+   Rows and columns <= k inside the live slots are NOT masked: they are never read again as matrix entries, their v is zero (so they
+   add nothing to p of a live row, nor to v'p), and what the step does to them is the same orthogonal update as everywhere else —
+   they stay finite, and skipping the masks saves a compare and two selects per element and step. */
 template <int RS, int CS, int R0>
-FPT_D void fpt_treg_step(double (&a)[RS][CS], int k, double scal, double tau, int rg, int cg, const double *vb, double *wb) {
+FPT_D void fpt_treg_step(double (&a)[RS][CS], double tau, int rg, int cg, const double *vb, double *wb) {
     constexpr int C0 = 2 * R0;
     double vr[RS], vc[CS], p[RS];
 #pragma unroll
-    for (int r = R0; r < RS; r++) {
-        const int i = 8 * r + rg;
-        const double x = vb[i];
-        vr[r] = i >= k + 2 ? x * scal : (i == k + 1 ? 1.0 : 0.0);
-    }
+    for (int r = R0; r < RS; r++) vr[r] = vb[8 * r + rg];
 #pragma unroll
-    for (int c = C0; c < CS; c++) {
-        const int j = 4 * c + cg;
-        const double x = vb[j];
-        vc[c] = j >= k + 2 ? x * scal : (j == k + 1 ? 1.0 : 0.0);
-    }
+    for (int c = C0; c < CS; c++) vc[c] = vb[4 * c + cg];
     /* p = tau A v: my columns' share of my rows, then the other three column groups' */
 #pragma unroll
     for (int r = R0; r < RS; r++) {
@@ -87,11 +82,10 @@ FPT_D void fpt_treg_step(double (&a)[RS][CS], int k, double scal, double tau, in
     for (int r = R0; r < RS; r++) p[r] += __shfl_xor_sync(FPT_FULL_MASK, p[r], 1);
 #pragma unroll
     for (int r = R0; r < RS; r++) p[r] += __shfl_xor_sync(FPT_FULL_MASK, p[r], 2);
-    /* rows above the block take no part (their v is zero; their w must be) */
     double pv = 0.0;
 #pragma unroll
     for (int r = R0; r < RS; r++) {
-        p[r] = 8 * r + rg > k ? p[r] * tau : 0.0;
+        p[r] *= tau;
         pv = fma(p[r], vr[r], pv);
     }
     pv += __shfl_xor_sync(FPT_FULL_MASK, pv, 4);
@@ -264,19 +258,26 @@ fpt_css_tridiag_reg_kernel(const unsigned *__restrict__ planes, int m, const int
                 scal = (x0 >= 0.0 ? 1.0 : -1.0) / (ax0 + nrm);
             }
             const double alpha = x0 >= 0.0 ? -nrm : nrm;
-            {   /* the reflector to the hand-over buffer: rcol[i] = v_i, i = k+1 .. m-1 */
+            {   /* the reflector v (0 up to row k, 1 at k + 1, the scaled column below): to the hand-over buffer (rcol[i] = v_i,
+                   i = k+1 .. m-1) and, in place of the column, to vb, where the step reads its row and column copies */
+                const double vl = lane >= k + 2 ? xl * scal : (lane == k + 1 ? 1.0 : 0.0);
+                const double vh = lane + 32 >= k + 2 ? xh * scal : (lane + 32 == k + 1 ? 1.0 : 0.0);
                 double *rcol = rs + fpt_refl_col(m, k) - (k + 1);
-                if (lane > k && lane < m) rcol[lane] = lane == k + 1 ? 1.0 : xl * scal;
-                if (lane + 32 > k && lane + 32 < m) rcol[lane + 32] = lane + 32 == k + 1 ? 1.0 : xh * scal;
+                if (lane > k && lane < m) rcol[lane] = vl;
+                if (lane + 32 > k && lane + 32 < m) rcol[lane + 32] = vh;
+                __syncwarp();                                /* every lane has read the column */
+                vb[lane] = vl;
+                if (lane + 32 < MP) vb[lane + 32] = vh;
+                __syncwarp();
             }
             if (lane == 0) { ts[m + k] = alpha; ts[2 * m + k] = tau; }
             switch ((k + 1) >> 3) {
-                case 0: fpt_treg_step<RS, CS, 0>(a, k, scal, tau, rg, cg, vb, wb); break;
-                case 1: fpt_treg_step<RS, CS, 1>(a, k, scal, tau, rg, cg, vb, wb); break;
-                case 2: fpt_treg_step<RS, CS, 2>(a, k, scal, tau, rg, cg, vb, wb); break;
-                case 3: fpt_treg_step<RS, CS, 3>(a, k, scal, tau, rg, cg, vb, wb); break;
-                case 4: if (RS > 4) fpt_treg_step<RS, CS, (RS > 4 ? 4 : 0)>(a, k, scal, tau, rg, cg, vb, wb); break;
-                default: if (RS > 5) fpt_treg_step<RS, CS, (RS > 5 ? 5 : 0)>(a, k, scal, tau, rg, cg, vb, wb); break;
+                case 0: fpt_treg_step<RS, CS, 0>(a, tau, rg, cg, vb, wb); break;
+                case 1: fpt_treg_step<RS, CS, 1>(a, tau, rg, cg, vb, wb); break;
+                case 2: fpt_treg_step<RS, CS, 2>(a, tau, rg, cg, vb, wb); break;
+                case 3: fpt_treg_step<RS, CS, 3>(a, tau, rg, cg, vb, wb); break;
+                case 4: if (RS > 4) fpt_treg_step<RS, CS, (RS > 4 ? 4 : 0)>(a, tau, rg, cg, vb, wb); break;
+                default: if (RS > 5) fpt_treg_step<RS, CS, (RS > 5 ? 5 : 0)>(a, tau, rg, cg, vb, wb); break;
             }
         }
         /* the last 2 x 2 block: d[m-2], e[m-2], d[m-1] */
