@@ -51,6 +51,11 @@ def set_perm_small_kernel(v):
     _lib.load().fpt_set_perm_small_kernel(int(v))
 
 
+def set_lanczos_threads(threads):
+    """Large-cohort MDS on count codes: threads per CTA (256 default, 384 or 512). Tuning aid."""
+    _lib.load().fpt_set_lanczos_threads(int(threads))
+
+
 def set_mds_small_kernel(v):
     """Cohorts of 3..48, classical MDS: 1 / True = tridiagonalisation in registers (default), 0 / False = the shared-memory kernel."""
     _lib.load().fpt_set_mds_small_kernel(int(v))
