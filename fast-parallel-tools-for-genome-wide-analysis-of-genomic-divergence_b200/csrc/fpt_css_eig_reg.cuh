@@ -10,7 +10,9 @@
  * Here the 32 lanes form an 8 x 4 grid (rg = lane / 4, cg = lane % 4) and lane (rg, cg) owns the elements
  * (8 r + rg, 4 c + cg), r < RS, c < CS of the full (both triangles) matrix, padded with zeros to 8 RS = 4 CS: a cyclic layout,
  * so the trailing block of a Householder step stays spread over all 32 lanes however small it gets. Per step:
- *   - column k goes through shared memory once (the owners store it, every lane reads its rows and its columns of v);
+ *   - column k goes through shared memory once (the owners store it), its norm is a warp reduction, and the reflector v built from
+ *     it (0 up to row k, 1 at k + 1, the scaled column below) replaces it there: every lane reads its rows and its columns of v,
+ *     no selects in the step; v, d_k, e_k and tau_k stay in shared memory until the window is done and leave in one coalesced sweep;
  *   - p = tau A v is RS x CS register multiply-adds per lane and a two-stage butterfly over the four column groups;
  *   - v'p is a three-stage butterfly over the row groups; w = p - (tau/2)(v'p) v goes through shared memory for its column copy;
  *   - A -= v w' + w v' is 2 RS CS register multiply-adds.
