@@ -118,3 +118,25 @@ def test_world_size_2_gloo_gather_matches_single_rank():
     for rank, s, d, cs, cp in got:            # every rank ends up with the full, identical result
         assert np.array_equal(s, s1) and np.array_equal(d, d1)
         assert np.array_equal(cs, c1, equal_nan=True) and np.array_equal(cp, p1)
+
+
+def test_bench_genome_pieces_tile_the_genome():
+    """bench.py --gpus N splits ONE genome into N contiguous window ranges (chromosomes dealt contiguously, the boundary
+    chromosome cut): every window of every chromosome belongs to exactly one rank, in order, for every N the bench is run at"""
+    import importlib
+    bench = importlib.import_module("bench")
+    nchrom, nout = 21, 42857
+    for world in (1, 2, 3, 4, 8):
+        seen = []
+        prev_end = 0
+        for rank in range(world):
+            pieces, (gb, ge) = bench.genome_pieces(nchrom, nout, rank, world)
+            assert gb == prev_end
+            prev_end = ge
+            assert sum(e - b for _, b, e in pieces) == ge - gb
+            for c, b, e in pieces:
+                assert 0 <= b < e <= nout
+                seen.append((c * nout + b, c * nout + e))
+        assert prev_end == nchrom * nout
+        seen.sort()
+        assert seen[0][0] == 0 and all(a[1] == b[0] for a, b in zip(seen, seen[1:])) and seen[-1][1] == nchrom * nout
