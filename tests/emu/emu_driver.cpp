@@ -276,6 +276,22 @@ long long emu_p3_magic_check(const unsigned *rs, long long nr) {
     return bad;
 }
 
+/* the same for the large-cohort shuffle's table (fpt_magic31, shift from clz): n = 2 .. nmax */
+long long emu_magic31_check(const unsigned *rs, long long nr, unsigned nmax) {
+    long long bad = 0;
+    for (unsigned n = 2; n <= nmax; n++) {
+        const uint2 lm = fpt_umma_rtab_entry((int)n);
+        const int sh = 31 - __clz((int)(n - 1));
+        for (long long k = 0; k < nr; k++) {
+            const unsigned r = rs[k] & 0x7fffffffu;
+            const unsigned rem = r - (__umulhi(r, lm.y) >> sh) * n;
+            if (rem != r % n) bad++;
+            if ((r > lm.x) != (r > 2147483647u - (2147483648u % n))) bad++;
+        }
+    }
+    return bad;
+}
+
 unsigned long long emu_css_perm2(const double *Xall, int m, int asize, int bsize, long long wbase, long long nwin,
                                  const unsigned char *status, int treshold, int runs, uint64_t seed, const uint64_t *state_override,
                                  int chain, int qbits, int nthreads, int grid, double *out_score, double *out_p, int *out_hits,

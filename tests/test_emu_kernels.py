@@ -534,3 +534,17 @@ def test_perm3_exact_quotient_magic(emu):
         rs.append(np.array([k * n - 1, k * n, k * n + 1, top, top - 1, (k - 1) * n - 1, (k - 1) * n, n - 1, n, 0, 1], dtype=np.int64))
     rs = np.concatenate(rs).clip(0, top).astype(np.uint32)
     assert emu.emu_p3_magic_check(vp(rs), ll(rs.size)) == 0
+
+
+def test_large_cohort_shuffle_exact_quotient_magic(emu):
+    """fpt_magic31 (the table of the large-cohort shuffle, shift taken from clz(n - 1)): exact remainder and the reference's
+    acceptance limit for every n up to 1100, random draws plus the edges near multiples of n and near 2^31"""
+    emu.emu_magic31_check.restype = C.c_longlong
+    rng = np.random.default_rng(6)
+    rs = [rng.integers(0, 2 ** 31, size=4000, dtype=np.int64)]
+    top = 2 ** 31 - 1
+    for n in (2, 3, 7, 64, 65, 127, 128, 129, 500, 999, 1000, 1023, 1024, 1025, 1100):
+        k = top // n
+        rs.append(np.array([k * n - 1, k * n, k * n + 1, top, top - 1, (k - 1) * n, n - 1, n, 0, 1], dtype=np.int64))
+    rs = np.concatenate(rs).clip(0, top).astype(np.uint32)
+    assert emu.emu_magic31_check(vp(rs), ll(rs.size), C.c_uint(1100)) == 0
