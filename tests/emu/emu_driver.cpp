@@ -276,6 +276,11 @@ long long emu_p3_magic_check(const unsigned *rs, long long nr) {
     return bad;
 }
 
+/* Sturm counts of fpt_css_eig.cuh (scaled determinant recurrence) for nx probes of one tridiagonal (d, e2 = e^2, unit norm) */
+void emu_sturm_counts(const double *d, const double *e2, int n, const double *xs, int nx, int *counts) {
+    for (int k = 0; k < nx; k++) counts[k] = fpt_sturm_count(d, e2, n, xs[k], 1e-30);
+}
+
 /* the same for the large-cohort shuffle's table (fpt_magic31, shift from clz): n = 2 .. nmax */
 long long emu_magic31_check(const unsigned *rs, long long nr, unsigned nmax) {
     long long bad = 0;

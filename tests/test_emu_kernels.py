@@ -548,3 +548,32 @@ def test_large_cohort_shuffle_exact_quotient_magic(emu):
         rs.append(np.array([k * n - 1, k * n, k * n + 1, top, top - 1, (k - 1) * n, n - 1, n, 0, 1], dtype=np.int64))
     rs = np.concatenate(rs).clip(0, top).astype(np.uint32)
     assert emu.emu_magic31_check(vp(rs), ll(rs.size), C.c_uint(1100)) == 0
+
+
+def test_sturm_counts_by_the_determinant_recurrence(emu):
+    """fpt_sturm_count (the eigenvector kernel's multisection probe, also used on the Lanczos tridiagonals up to order 384): the
+    number of eigenvalues below x from sign changes of the rescaled determinant recurrence equals numpy's count — random
+    matrices, graded ones spanning 12 decades (the rescaling), decoupled blocks (e = 0) and probes ON diagonal entries"""
+    rng = np.random.default_rng(8)
+    cases = []
+    for n in (2, 3, 11, 40, 64, 165, 384):
+        d, e = rng.normal(size=n), rng.normal(size=n - 1)
+        cases.append((d, e))
+        g = 10.0 ** (-12.0 * np.arange(n) / max(1, n - 1))                # graded: entries from 1 down to 1e-12
+        cases.append((d * g, e * np.sqrt(g[:-1] * g[1:])))
+        e0 = e.copy(); e0[n // 2 - 1 if n > 2 else 0] = 0.0               # two decoupled blocks
+        cases.append((d, e0))
+        cases.append((np.full(n, 0.3), np.zeros(n - 1)))                  # diagonal matrix, all entries equal
+    for d, e in cases:
+        n = d.size
+        T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+        nrm = np.abs(T).sum(axis=1).max()
+        d, e, T = d / nrm, e / nrm, T / nrm
+        ev = np.linalg.eigvalsh(T)
+        xs = np.concatenate([rng.uniform(-1.1, 1.1, 60), 0.5 * (ev[:-1] + ev[1:]) if n > 1 else [], ev + 1e-7, ev - 1e-7, d[: min(n, 8)]])
+        xs = np.ascontiguousarray(xs[np.abs(xs[:, None] - ev[None, :]).min(axis=1) > 1e-9], dtype=np.float64)   # not within rounding of an eigenvalue
+        cnt = np.zeros(xs.size, dtype=np.int32)
+        e2 = np.ascontiguousarray(np.append(e * e, 0.0))
+        emu.emu_sturm_counts(dptr(np.ascontiguousarray(d)), dptr(e2), n, dptr(xs), xs.size, iptr(cnt))
+        want = (ev[None, :] < xs[:, None]).sum(axis=1)
+        assert np.array_equal(cnt, want), (n, np.flatnonzero(cnt != want)[:5])
