@@ -577,3 +577,28 @@ def test_sturm_counts_by_the_determinant_recurrence(emu):
         emu.emu_sturm_counts(dptr(np.ascontiguousarray(d)), dptr(e2), n, dptr(xs), xs.size, iptr(cnt))
         want = (ev[None, :] < xs[:, None]).sum(axis=1)
         assert np.array_equal(cnt, want), (n, np.flatnonzero(cnt != want)[:5])
+
+
+def test_fet_log_mode_walk_against_exact_rationals(emu):
+    """the score kernel's log-mode walk as compiled for the CPU (term ratios by first differences of numerator and denominator,
+    Newton reciprocal, cut-off every fourth term) against exact rational arithmetic of the reference's two-tailed rule, both forms
+    of the kernel (plain and tile-sorting)"""
+    from math import log10
+    import checkers
+    rng = np.random.default_rng(23)
+    T = []
+    for _ in range(1100):
+        n1, n2 = int(rng.integers(40, 500)), int(rng.integers(40, 500))
+        f = rng.uniform(0.05, 0.95)
+        a, c = int(rng.binomial(n1, f)), int(rng.binomial(n2, min(0.99, max(0.01, f + rng.normal(0, 0.08)))))
+        T.append((a, n1 - a, c, n2 - c))
+    T = np.ascontiguousarray(np.array(T, dtype=np.int32))
+    maxn = int(T.sum(1).max())
+    plain, srt = np.zeros(len(T)), np.zeros(len(T))
+    emu.emu_fet_score(iptr(T), ll(len(T)), maxn, 1, 0, 2, dptr(plain))
+    emu.emu_fet_score_sorted(iptr(T), ll(len(T)), maxn, 1, 0, 1, dptr(srt))
+    assert np.array_equal(plain, srt)
+    for t, g in list(zip(T, plain))[:300]:
+        P = checkers.fet_exact_rule(*[int(v) for v in t])
+        want = 0.0 if P == 1 else -(log10(P.numerator) - log10(P.denominator))
+        assert g == pytest.approx(want, rel=1e-9, abs=1e-10), tuple(t)
