@@ -52,6 +52,7 @@ FET_TABLES = dict(n=100_000_000, chunks=8, lo=20, hi=500, seed0=20261018 + 3)
 LARGE = dict(seed0=20261018 + 4, asize=500, bsize=500, chromosomes=8, windows=2600, wsize=50_000, wstep=50_000,
              snps_per_window=167, mcr=1000, cpu_windows=4)
 SEED = 20261018
+NCU_LARGE_WINDOWS = 296      # windows in the one launch the committed large-cohort ncu captures hold (profiles/capture.sh: probe_large_cohort.py 296)
 
 
 def hbm_peak():
@@ -775,7 +776,10 @@ def bench_large_cohort(lib_mod, cx):
                                    "individuals, 50 kb windows, ~%d SNPs per window, classical MDS, mcT=mcR=1000; chromosome k on rank k %% N, "
                                    "results gathered once" % (nchrom, nwin, nchrom * nwin, LARGE["snps_per_window"]),
                        "windows_scored": scored},
-            "gpu_launches": len(mine) * 7 * nsteps, "_prof": prof, "_first": first, "_nwin": nwin, "_chrom_per_rank": len(mine),
+            # kernels launched on this rank per step: one per profile scope, and the Lanczos scope holds two (the arithmetic-product
+            # kernel, then the general one for the windows it left pending)
+            "gpu_launches": (sum(v["launches"] for v in prof.values()) + prof.get("css_mds_large", {}).get("launches", 0)) // max(1, nsteps) * nsteps,
+            "_prof": prof, "_first": first, "_nwin": nwin, "_chrom_per_rank": len(mine), "_nsteps": nsteps,
             "_lanczos_steps": lanczos_steps}
 
 
@@ -1205,18 +1209,25 @@ def main():
             mL = LARGE["asize"] + LARGE["bsize"]
             ltot = sum(v["ms"] for v in prof.values()) or 1.0
             lk = {}
+            nsteps_l = large.pop("_nsteps")
             for k, v in prof.items():
-                per = v["ms"] / v["launches"]
-                e = {"ms_per_launch": per, "share_of_step": round(v["ms"] / ltot, 4)}
+                # the code route runs a chromosome in passes of <= 1024 windows (one profile scope per pass), so the work models are
+                # set against this kernel's time per CHROMOSOME (all its passes), never per scope
+                per = v["ms"] / max(1, nsteps_l * cpr)
+                e = {"ms_per_chromosome": per, "ms_per_launch": v["ms"] / v["launches"], "scopes_per_chromosome": v["launches"] / max(1, nsteps_l * cpr),
+                     "share_of_step": round(v["ms"] / ltot, 4)}
                 if k == "css_mds_large":
                     # algorithmic HBM bytes per window: the window's bit-planes in (2 planes x m x ceil(npos/32) words) and the embedding out (16 m)
                     words = -(-LARGE["snps_per_window"] // 32) + 1
                     by = nwin * (2.0 * mL * words * 4 + 16.0 * mL)
+                    # the committed ncu capture (profiles/capture.sh) is ONE launch over NCU_LARGE_WINDOWS windows: scale it to a chromosome
                     tr = ncu_record("css_mds_large")
+                    tr = tr * nwin / NCU_LARGE_WINDOWS if tr else None
                     e.update(bound="hbm", algorithmic_bytes=by, achieved=by / (per * 1e-3) / 1e9, peak=hbm, unit="GB/s", frac=by / (per * 1e-3) / 1e9 / hbm,
                              traffic=tr, traffic_over_algorithmic=(tr / by) if tr else None,
-                             note="64 KB of input + output per window; everything above that in `traffic` is the kernel re-streaming its own "
-                                  "matrix and Lanczos basis")
+                             note="per chromosome of %d windows: 72 KB of input + output per window; everything above that in `traffic` (ncu capture "
+                                  "of %d windows, scaled by the window count) is the kernel re-streaming its own code matrix and Lanczos basis"
+                                  % (nwin, NCU_LARGE_WINDOWS))
                     if micro and lz_steps:
                         # what bounds it: the fp64 pipe. Work of the Krylov method itself per window: steps x (2 m^2 for the product
                         # + 4 m x (mean basis size = steps / 2) for the Gram-Schmidt pass); the dense 9 m^3 of the reference's solver is not
@@ -1238,7 +1249,7 @@ def main():
                                   "with both operands resident in shared memory (profiles/microbench/peaks.cu)")
                 lk[k] = e
             large["kernels"] = lk
-            large["kernel_ms_per_chromosome"] = {k: v["ms"] / max(1, v["launches"]) for k, v in prof.items()}
+            large["kernel_ms_per_chromosome"] = {k: v["ms"] / max(1, nsteps_l * cpr) for k, v in prof.items()}
             if world == 1 and not args.skip_cpu and not args.small:
                 large["cpu_baseline"] = cpu_large(first)
             line["large_cohort"] = large
