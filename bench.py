@@ -991,6 +991,58 @@ def css_kernel_table(css, micro, hbm, nsteps):
     return out
 
 
+def large_kernel_table(large, micro, hbm):
+    """per kernel of the large-cohort leg (rank 0's chromosomes): time per chromosome, share, and the work models of the Lanczos and
+    permutation kernels. The code route runs a chromosome in passes of <= 1024 windows (one profile scope per pass), so every
+    model is set against the kernel's time per CHROMOSOME (all its passes), never per scope."""
+    prof = large.pop("_prof")
+    nwin, cpr, nsteps = large.pop("_nwin"), large.pop("_chrom_per_rank"), large.pop("_nsteps")
+    lz_steps = large.pop("_lanczos_steps")
+    mL = LARGE["asize"] + LARGE["bsize"]
+    ltot = sum(v["ms"] for v in prof.values()) or 1.0
+    passes = max(1, nsteps * cpr)                         # chromosomes this rank ran while the profile was on
+    lk = {}
+    for k, v in prof.items():
+        per = v["ms"] / passes
+        e = {"ms_per_chromosome": per, "ms_per_launch": v["ms"] / v["launches"], "scopes_per_chromosome": v["launches"] / passes,
+             "share_of_step": round(v["ms"] / ltot, 4)}
+        if k == "css_mds_large":
+            # algorithmic HBM bytes per window: the window's bit-planes in (2 planes x m x ceil(npos/32) words) and the embedding out (16 m)
+            words = -(-LARGE["snps_per_window"] // 32) + 1
+            by = nwin * (2.0 * mL * words * 4 + 16.0 * mL)
+            # the committed ncu capture (profiles/capture.sh) is ONE launch over NCU_LARGE_WINDOWS windows: scale it to a chromosome
+            tr = ncu_record("css_mds_large")
+            tr = tr * nwin / NCU_LARGE_WINDOWS if tr else None
+            e.update(bound="hbm", algorithmic_bytes=by, achieved=by / (per * 1e-3) / 1e9, peak=hbm, unit="GB/s", frac=by / (per * 1e-3) / 1e9 / hbm,
+                     traffic=tr, traffic_over_algorithmic=(tr / by) if tr else None,
+                     note="per chromosome of %d windows: 72 KB of input + output per window; everything above that in `traffic` (ncu capture "
+                          "of %d windows, scaled by the window count) is the kernel re-streaming its own code matrix and Lanczos basis"
+                          % (nwin, NCU_LARGE_WINDOWS))
+            if micro and lz_steps:
+                # what bounds it: issue slots and the fp64 pipe of the product. Work of the Krylov method itself per window: steps x
+                # (2 m^2 for the product + 4 m x (mean basis size = steps / 2) for the Gram-Schmidt pass); the dense 9 m^3 of the
+                # reference's solver is not what this kernel does, so it is not used as a roofline
+                fl = nwin * lz_steps * (2.0 * mL * mL + 4.0 * mL * lz_steps / 2.0)
+                e.update(bound="fp64", lanczos_steps_per_window=lz_steps,
+                         fp64={"algorithmic_flops": fl, "achieved": fl / (per * 1e-3) / 1e12, "peak": micro["fp64"]["tflops"],
+                               "frac": fl / (per * 1e-3) / 1e12 / micro["fp64"]["tflops"], "unit": "TFLOP/s",
+                               "note": "Lanczos work model: steps x (2 m^2 + 2 m steps) flops per window, steps counted by the kernel; the "
+                                       "product spends a second fp64 instruction per element on turning c^2 into a double"},
+                         hbm={"algorithmic_bytes": by, "frac": by / (per * 1e-3) / 1e9 / hbm, "traffic": tr,
+                              "traffic_over_algorithmic": (tr / by) if tr else None})
+        elif k == "css_perm" and micro:
+            npad, kpad, batches = -(-mL // 256) * 256, -(-mL // 128) * 128, -(-LARGE["mcr"] // 128)
+            macs = float(nwin) * batches * 128 * npad * kpad * 4
+            e.update(bound="tensor", algorithmic_macs=macs, achieved=2.0 * macs / (per * 1e-3) / 1e12, peak=micro["umma_i8"]["tops"], unit="TOP/s",
+                     frac=2.0 * macs / (per * 1e-3) / 1e12 / micro["umma_i8"]["tops"],
+                     note="u8 contraction work of the kernel (4 base-256 digits) over the WHOLE kernel time, against the kind::i8 rate measured "
+                          "with both operands resident in shared memory (profiles/microbench/peaks.cu)")
+        lk[k] = e
+    large["kernels"] = lk
+    large["kernel_ms_per_chromosome"] = {k: v["ms"] / passes for k, v in prof.items()}
+    return large
+
+
 def main():
     out = OneLineStdout()
     ap = argparse.ArgumentParser()
@@ -1202,54 +1254,8 @@ def main():
                                                              "within_1e-9_rel_plus_1e-12_abs": bool(np.all(np.abs(g - oc) <= 1e-9 * np.abs(oc) + 1e-12))}}
             line["fet_tables"] = fet_tab
         if large is not None:
-            prof = large.pop("_prof")
             first = large.pop("_first")
-            nwin, cpr = large.pop("_nwin"), large.pop("_chrom_per_rank")
-            lz_steps = large.pop("_lanczos_steps")
-            mL = LARGE["asize"] + LARGE["bsize"]
-            ltot = sum(v["ms"] for v in prof.values()) or 1.0
-            lk = {}
-            nsteps_l = large.pop("_nsteps")
-            for k, v in prof.items():
-                # the code route runs a chromosome in passes of <= 1024 windows (one profile scope per pass), so the work models are
-                # set against this kernel's time per CHROMOSOME (all its passes), never per scope
-                per = v["ms"] / max(1, nsteps_l * cpr)
-                e = {"ms_per_chromosome": per, "ms_per_launch": v["ms"] / v["launches"], "scopes_per_chromosome": v["launches"] / max(1, nsteps_l * cpr),
-                     "share_of_step": round(v["ms"] / ltot, 4)}
-                if k == "css_mds_large":
-                    # algorithmic HBM bytes per window: the window's bit-planes in (2 planes x m x ceil(npos/32) words) and the embedding out (16 m)
-                    words = -(-LARGE["snps_per_window"] // 32) + 1
-                    by = nwin * (2.0 * mL * words * 4 + 16.0 * mL)
-                    # the committed ncu capture (profiles/capture.sh) is ONE launch over NCU_LARGE_WINDOWS windows: scale it to a chromosome
-                    tr = ncu_record("css_mds_large")
-                    tr = tr * nwin / NCU_LARGE_WINDOWS if tr else None
-                    e.update(bound="hbm", algorithmic_bytes=by, achieved=by / (per * 1e-3) / 1e9, peak=hbm, unit="GB/s", frac=by / (per * 1e-3) / 1e9 / hbm,
-                             traffic=tr, traffic_over_algorithmic=(tr / by) if tr else None,
-                             note="per chromosome of %d windows: 72 KB of input + output per window; everything above that in `traffic` (ncu capture "
-                                  "of %d windows, scaled by the window count) is the kernel re-streaming its own code matrix and Lanczos basis"
-                                  % (nwin, NCU_LARGE_WINDOWS))
-                    if micro and lz_steps:
-                        # what bounds it: the fp64 pipe. Work of the Krylov method itself per window: steps x (2 m^2 for the product
-                        # + 4 m x (mean basis size = steps / 2) for the Gram-Schmidt pass); the dense 9 m^3 of the reference's solver is not
-                        # what this kernel does, so it is not used as a roofline
-                        fl = nwin * lz_steps * (2.0 * mL * mL + 4.0 * mL * lz_steps / 2.0)
-                        e.update(bound="fp64", lanczos_steps_per_window=lz_steps,
-                                 fp64={"algorithmic_flops": fl, "achieved": fl / (per * 1e-3) / 1e12, "peak": micro["fp64"]["tflops"],
-                                       "frac": fl / (per * 1e-3) / 1e12 / micro["fp64"]["tflops"], "unit": "TFLOP/s",
-                                       "note": "Lanczos work model: steps x (2 m^2 + 2 m steps) flops per window, steps counted by the kernel; the "
-                                               "product spends a second fp64 instruction per element on turning c^2 into a double"},
-                                 hbm={"algorithmic_bytes": by, "frac": by / (per * 1e-3) / 1e9 / hbm, "traffic": tr,
-                                      "traffic_over_algorithmic": (tr / by) if tr else None})
-                elif k == "css_perm" and micro:
-                    npad, kpad, batches = -(-mL // 256) * 256, -(-mL // 128) * 128, -(-LARGE["mcr"] // 128)
-                    macs = float(nwin) * batches * 128 * npad * kpad * 4
-                    e.update(bound="tensor", algorithmic_macs=macs, achieved=2.0 * macs / (per * 1e-3) / 1e12, peak=micro["umma_i8"]["tops"], unit="TOP/s",
-                             frac=2.0 * macs / (per * 1e-3) / 1e12 / micro["umma_i8"]["tops"],
-                             note="u8 contraction work of the kernel (4 base-256 digits) over the WHOLE kernel time, against the kind::i8 rate measured "
-                                  "with both operands resident in shared memory (profiles/microbench/peaks.cu)")
-                lk[k] = e
-            large["kernels"] = lk
-            large["kernel_ms_per_chromosome"] = {k: v["ms"] / max(1, nsteps_l * cpr) for k, v in prof.items()}
+            large_kernel_table(large, micro, hbm)
             if world == 1 and not args.skip_cpu and not args.small:
                 large["cpu_baseline"] = cpu_large(first)
             line["large_cohort"] = large

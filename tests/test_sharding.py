@@ -140,3 +140,33 @@ def test_bench_genome_pieces_tile_the_genome():
         assert prev_end == nchrom * nout
         seen.sort()
         assert seen[0][0] == 0 and all(a[1] == b[0] for a, b in zip(seen, seen[1:])) and seen[-1][1] == nchrom * nout
+
+
+def test_bench_large_cohort_work_models_are_per_chromosome():
+    """bench.py's large-cohort kernel table: a chromosome of 2600 windows runs the code route in three passes of <= 1024 windows
+    (one profile scope each), so the Lanczos and GEMM work of the whole chromosome is set against the sum of the passes, not
+    against one pass. Fed with the profile of the committed round-2 line (2 steps x 8 chromosomes on one GPU)."""
+    import importlib
+    bench = importlib.import_module("bench")
+    prof = {"css_pack": {"ms": 7.248, "launches": 16}, "window_table": {"ms": 0.362, "launches": 16},
+            "css_k4": {"ms": 76.33, "launches": 48}, "css_mds_large": {"ms": 1739.28, "launches": 48},
+            "css_observed": {"ms": 110.82, "launches": 16}, "css_perm": {"ms": 841.88, "launches": 16}}
+    large = {"_prof": prof, "_nwin": 2600, "_chrom_per_rank": 8, "_nsteps": 2, "_lanczos_steps": 73.6}
+    micro = {"fp64": {"tflops": 33.783}, "umma_i8": {"tops": 4525.1}}
+    out = bench.large_kernel_table(large, micro, 6552.6)
+    assert not [k for k in out if k.startswith("_")]
+    k = out["kernels"]
+    assert abs(k["css_mds_large"]["ms_per_chromosome"] - 108.7) < 0.05 and k["css_mds_large"]["scopes_per_chromosome"] == 3
+    assert abs(k["css_mds_large"]["ms_per_launch"] - 36.235) < 0.01
+    fl = 2600 * 73.6 * (2.0e6 + 2000.0 * 73.6)
+    assert abs(k["css_mds_large"]["fp64"]["algorithmic_flops"] - fl) < 1e-6 * fl
+    assert abs(k["css_mds_large"]["fp64"]["frac"] - fl / 108.705e-3 / 33.783e12) < 1e-4
+    assert 0.10 < k["css_mds_large"]["fp64"]["frac"] < 0.12
+    assert k["css_mds_large"]["algorithmic_bytes"] == 2600 * 72000.0
+    tr = k["css_mds_large"]["traffic"]
+    if tr is not None:                                    # profiles/ncu_traffic.json: one 296-window launch, scaled to the chromosome
+        assert abs(tr / 2600 - bench.ncu_record("css_mds_large") / 296) < 1.0
+        assert 1000 < k["css_mds_large"]["traffic_over_algorithmic"] < 1500
+    assert abs(k["css_perm"]["ms_per_chromosome"] - 52.6175) < 1e-3 and k["css_perm"]["scopes_per_chromosome"] == 1
+    assert abs(sum(v["share_of_step"] for v in k.values()) - 1.0) < 1e-3
+    assert abs(sum(out["kernel_ms_per_chromosome"].values()) - sum(v["ms"] for v in prof.values()) / 16) < 1e-9
