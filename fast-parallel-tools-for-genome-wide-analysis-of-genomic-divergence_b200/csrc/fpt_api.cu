@@ -756,8 +756,13 @@ static int dev_css_windows(const Knobs &kn, const uint32_t *planes, const double
                     grid_lza = std::min(grid_lza, p.max_ctas);
                 }
                 grid_lz = std::min(grid_lz, p.max_ctas);
-                for (long long w0 = 0; w0 < nwin; w0 += FPT_K4_BATCH) {
-                    const long long nb = std::min<long long>(FPT_K4_BATCH, nwin - w0);
+                /* the Lanczos CTAs walk a pass's windows at a fixed stride (window blockIdx.x, + gridDim.x, ...), so a pass whose window
+                   count is not a multiple of the grid ends with a round in which part of the SMs idle: passes of whole rounds
+                   (1024 -> 888 windows for 296 CTAs; a 2600-window chromosome takes 9 rounds instead of 4 + 4 + 2) */
+                const long long grid_main = std::max(1, arith ? grid_lza : grid_lz);
+                const long long pass = grid_main <= FPT_K4_BATCH ? (FPT_K4_BATCH / grid_main) * grid_main : FPT_K4_BATCH;
+                for (long long w0 = 0; w0 < nwin; w0 += pass) {
+                    const long long nb = std::min<long long>(pass, nwin - w0);
                     if (kn.k4_mode == 2) {
                         CU(cudaFuncSetAttribute(fpt_css_k4_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FPT_K4_SMEM));
                         const int g4 = (int)std::max(1LL, std::min<long long>(c->sms, nb));     /* 512 columns of tensor memory: one CTA per SM */
