@@ -52,6 +52,7 @@ FET_TABLES = dict(n=100_000_000, chunks=8, lo=20, hi=500, seed0=20261018 + 3)
 LARGE = dict(seed0=20261018 + 4, asize=500, bsize=500, chromosomes=8, windows=2600, wsize=50_000, wstep=50_000,
              snps_per_window=167, mcr=1000, cpu_windows=4)
 SEED = 20261018
+NCU_CSS_SCORED = 38810        # scored windows of the chromosome launch the committed headline captures hold (chromosome 0 of the workload)
 NCU_LARGE_WINDOWS = 296      # windows in the one launch the committed large-cohort ncu captures hold (profiles/capture.sh: probe_large_cohort.py 296)
 
 
@@ -963,9 +964,13 @@ def css_kernel_table(css, micro, hbm, nsteps):
                      note="work model of the reference algorithm (one 8-byte gather per score term); the kernel itself replaces most of "
                           "them by an exact integer surrogate on the u8 tensor cores, so frac > 1 is possible")
             ninst = ncu_record("css_perm", "inst")
-            if ninst and issue:
-                e["issue"] = {"warp_inst_per_launch_ncu": ninst, "achieved_gwarp_inst_per_s": ninst / (e["ms_per_launch"] * 1e-3) / 1e9,
-                              "peak": issue / 1e9, "frac": ninst / (e["ms_per_launch"] * 1e-3) / issue,
+            if ninst and issue and scored_rank:
+                # the capture is the launch of chromosome 0 (NCU_CSS_SCORED scored windows): instructions per scored window x the
+                # windows this rank scored per step, so that partial chromosomes (N > 1) and --small shapes stay comparable
+                inst_step = ninst / NCU_CSS_SCORED * scored_rank
+                e["issue"] = {"warp_inst_per_launch_ncu": ninst, "warp_inst_per_scored_window": ninst / NCU_CSS_SCORED,
+                              "achieved_gwarp_inst_per_s": inst_step / sec_step / 1e9,
+                              "peak": issue / 1e9, "frac": inst_step / sec_step / issue,
                               "note": "utilisation of the issue slots, from the committed ncu capture at N = 1 (not a roofline: useless instructions raise it)"}
         elif k in ("css_tridiag", "css_eigvec"):
             # K5: double centring ~6 m^2 + dense symmetric eigen-decomposition ~9 m^3 (what the reference's GSL call does); split 2/3 : 1/3

@@ -170,3 +170,31 @@ def test_bench_large_cohort_work_models_are_per_chromosome():
     assert abs(k["css_perm"]["ms_per_chromosome"] - 52.6175) < 1e-3 and k["css_perm"]["scopes_per_chromosome"] == 1
     assert abs(sum(v["share_of_step"] for v in k.values()) - 1.0) < 1e-3
     assert abs(sum(out["kernel_ms_per_chromosome"].values()) - sum(v["ms"] for v in prof.values()) / 16) < 1e-9
+
+
+def test_bench_headline_kernel_table_follows_its_work_models():
+    """bench.py's headline kernel table on the profile of the committed round-2 line (3 steps x 21 chromosome launches): the
+    permutation kernel's SURVEY 8(d) gather model against the shared-memory peak, its issue utilisation per scored window (so a
+    rank's partial chromosomes at N > 1 stay comparable), and the dense fp64 model of the two MDS kernels."""
+    import importlib
+    bench = importlib.import_module("bench")
+    prof = {"css_pack": {"ms": 1.4613, "launches": 63}, "window_table": {"ms": 1.0317, "launches": 63},
+            "css_tridiag": {"ms": 83.4677, "launches": 63}, "css_eigvec": {"ms": 65.8804, "launches": 63},
+            "css_observed": {"ms": 8.6592, "launches": 63}, "css_perm": {"ms": 197.657, "launches": 63}}
+    css = {"prof": prof, "my_windows": 899997, "my_scored": 815731}
+    micro = {"fp64": {"tflops": 33.783}, "smem": {"tb_per_s": 36.992}, "issue": {"gwarp_inst_per_s": 1116.1}}
+    k = bench.css_kernel_table(css, micro, 6552.6, 3)
+    gath = 815731 * 1000 * (400 + 38) * 8.0
+    assert k["css_perm"]["algorithmic_bytes_per_step"] == gath
+    assert abs(k["css_perm"]["frac"] - gath / (197.657e-3 / 3) / 36.992e12) < 1e-9 and 1.16 < k["css_perm"]["frac"] < 1.18
+    assert abs(k["css_perm"]["ms_per_launch"] - 3.13741) < 1e-4
+    iss = k["css_perm"].get("issue")
+    if iss is not None:                                   # profiles/ncu_inst.json present
+        assert abs(iss["frac"] - iss["warp_inst_per_scored_window"] * 815731 / (197.657e-3 / 3) / 1116.1e9) < 1e-9
+        assert 0.55 < iss["frac"] < 0.62
+        half = dict(css, my_scored=815731 // 2, prof={n: {"ms": v["ms"] / 2, "launches": v["launches"]} for n, v in prof.items()})
+        assert abs(bench.css_kernel_table(half, micro, 6552.6, 3)["css_perm"]["issue"]["frac"] - iss["frac"]) < 1e-3
+    fl = 815731 * (6.0 * 1600 + 9.0 * 64000)
+    assert abs(k["css_tridiag"]["algorithmic_flops_per_step"] - fl * 2 / 3) < 1.0
+    assert abs(k["css_eigvec"]["frac"] - fl / 3 / (65.8804e-3 / 3) / 33.783e12) < 1e-9
+    assert abs(sum(v["share_of_step"] for v in k.values()) - 1.0) < 1e-3
