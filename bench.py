@@ -998,7 +998,7 @@ def css_kernel_table(css, micro, hbm, nsteps):
 
 def large_kernel_table(large, micro, hbm):
     """per kernel of the large-cohort leg (rank 0's chromosomes): time per chromosome, share, and the work models of the Lanczos and
-    permutation kernels. The code route runs a chromosome in passes of <= 1024 windows (one profile scope per pass), so every
+    permutation kernels. The code route runs a chromosome in passes of <= 4096 windows (one profile scope per pass; 1024 in earlier builds), so every
     model is set against the kernel's time per CHROMOSOME (all its passes), never per scope."""
     prof = large.pop("_prof")
     nwin, cpr, nsteps = large.pop("_nwin"), large.pop("_chrom_per_rank"), large.pop("_nsteps")

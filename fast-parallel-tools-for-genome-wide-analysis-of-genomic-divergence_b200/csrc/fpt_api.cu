@@ -582,7 +582,7 @@ static CssPlan css_plan(const DeviceCtx *c, int m, const Knobs &kn) {
     return p;
 }
 
-#define FPT_K4_BATCH 1024                         /* windows per pass of the code route: bounds the code buffer (2 MB per window at m = 1000) */
+#define FPT_K4_BATCH 4096                         /* windows per pass of the code route: bounds the code buffer (2 MB per window at m = 1000, so 8 GB at most) */
 struct CssWorkspace {
     double *X, *Xruns, *sigma, *evals, *gscratch, *tri, *refl, *basis;
     unsigned char *codes;

@@ -143,8 +143,8 @@ def test_bench_genome_pieces_tile_the_genome():
 
 
 def test_bench_large_cohort_work_models_are_per_chromosome():
-    """bench.py's large-cohort kernel table: a chromosome of 2600 windows runs the code route in three passes of <= 1024 windows
-    (one profile scope each), so the Lanczos and GEMM work of the whole chromosome is set against the sum of the passes, not
+    """bench.py's large-cohort kernel table: a chromosome of 2600 windows ran the code route in three passes of <= 1024 windows when
+    that line was taken (one profile scope each; a chromosome is one pass since), so the Lanczos and GEMM work of the whole chromosome is set against the sum of the passes, not
     against one pass. Fed with the profile of the committed round-2 line (2 steps x 8 chromosomes on one GPU)."""
     import importlib
     bench = importlib.import_module("bench")
