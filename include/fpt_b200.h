@@ -220,7 +220,9 @@ int fpt_dev_css_pack_f64(const double *avals, const double *bvals, int64_t nsnp,
 int fpt_dev_css_pack_i8(const int8_t *acodes, const int8_t *bcodes, int64_t nsnp, int asize, int bsize,
                         uint32_t *planes, void *stream);
 int fpt_dev_css_absdiff(const double *afreq, const double *bfreq, int64_t nsnp, double *absdiff, void *stream);
-/* workspace for fpt_dev_css_windows (embeddings of every window and start, per-CTA scratch for large m) */
+/* workspace for fpt_dev_css_windows (embeddings of every window and start, per-CTA scratch for large m). Cohorts beyond the
+   one-warp MDS path (m >~ 165) also hold the genotype-distance count codes of one pass here: 2 m^2 bytes per window for at most
+   4096 windows (8 GB at m = 1000); longer ranges run in several passes inside the call. */
 size_t fpt_dev_css_workspace_bytes(int m, int64_t nwin, int mds);
 /* planes (or absdiff when drosophila != 0) -> scores, p, status (nwin each). states_* and probes hold
    DEVICE pointers here. */
