@@ -758,7 +758,8 @@ static int dev_css_windows(const Knobs &kn, const uint32_t *planes, const double
                 grid_lz = std::min(grid_lz, p.max_ctas);
                 /* the Lanczos CTAs walk a pass's windows at a fixed stride (window blockIdx.x, + gridDim.x, ...), so a pass whose window
                    count is not a multiple of the grid ends with a round in which part of the SMs idle: passes of whole rounds
-                   (1024 -> 888 windows for 296 CTAs; a 2600-window chromosome takes 9 rounds instead of 4 + 4 + 2) */
+                   (with a cap of 1024 windows: 888 for 296 CTAs, and a 2600-window chromosome took 9 rounds instead of 4 + 4 + 2; with the cap of
+                   4096 a configs[4] chromosome is one pass of 8-9 windows per CTA) */
                 const long long grid_main = std::max(1, arith ? grid_lza : grid_lz);
                 const long long pass = grid_main <= FPT_K4_BATCH ? (FPT_K4_BATCH / grid_main) * grid_main : FPT_K4_BATCH;
                 for (long long w0 = 0; w0 < nwin; w0 += pass) {
