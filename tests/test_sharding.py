@@ -198,3 +198,14 @@ def test_bench_headline_kernel_table_follows_its_work_models():
     assert abs(k["css_tridiag"]["algorithmic_flops_per_step"] - fl * 2 / 3) < 1.0
     assert abs(k["css_eigvec"]["frac"] - fl / 3 / (65.8804e-3 / 3) / 33.783e12) < 1e-9
     assert abs(sum(v["share_of_step"] for v in k.values()) - 1.0) < 1e-3
+
+
+def test_bench_finds_the_committed_capture_records_it_quotes():
+    """the DRAM traffic and instruction counts bench.py puts beside its live timings come from profiles/ncu_*.json: every
+    record the bench asks for is there (a missing one would silently turn `traffic` into null)"""
+    import importlib
+    bench = importlib.import_module("bench")
+    for k in ("css_perm", "css_pack", "css_mds_large", "fet_count", "fet_score"):
+        assert bench.ncu_record(k) and bench.ncu_record(k) > 0, k
+    assert bench.ncu_record("css_perm", "inst") > 1e9
+    assert bench.NCU_LARGE_WINDOWS == 296 and bench.NCU_CSS_SCORED == 38810
